@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+metric  : SE3 Exp+Log Mops/s (1 op = one se3->SE3 Exp plus one SE3->se3 Log on one element)
+workload: BASELINE.json configs[1] — batch 10^6, fp32, per GPU (weak scaling, no data-path collective)
+step    : one Exp launch + one Log launch over one resident batch; batches rotate through a ring whose
+          footprint exceeds the 126 MB L2, so every step streams from / to HBM.
+value   : device-timed (CUDA events, max over ranks), inputs resident in HBM.
+e2e     : same metric through the public API (pp.se3(...).Exp().Log()) with pinned HOST buffers,
+          H2D and D2H copies inside the timed region.
+The reference arm (--impl reference) times the torch-CPU port of the reference's Exp/Log op
+sequence (oracle/torch_port.py) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 1_000_000
+BYTES_EXP = 4 * (6 + 7)      # algorithmic bytes / element: read se3 (24) + write SE3 (28)
+BYTES_LOG = 4 * (7 + 6)
+L2_BYTES = 126 * 2 ** 20
+METRIC = "SE3 Exp+Log throughput (batch 1e6, fp32)"
+UNIT = "Mops/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def run_ours(args):
+    import pypose_b200 as pp
+    from pypose_b200 import _C
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(1234 + rank)
+    n = BATCH
+    ring = 8                                  # 8 x 76 MB = 608 MB of distinct buffers, > 4 x L2
+    xs = [pp.randn_se3(n, sigma=1.0, device=dev, dtype=torch.float32).tensor().contiguous() for _ in range(ring)]
+    for x in xs:   # rotation angle ~ U(0, pi - 0.01) (SURVEY.md §8d cfg 2)
+        phi = x[:, 3:]
+        ang = torch.rand(n, 1, device=dev) * (3.14159265 - 0.01)
+        phi.copy_(phi / phi.norm(dim=-1, keepdim=True) * ang)
+    Xs = [torch.empty(n, 7, device=dev) for _ in range(ring)]
+    ys = [torch.empty(n, 6, device=dev) for _ in range(ring)]
+    footprint = ring * n * (24 + 28 + 24)
+    f_exp, f_log = _C.fn("b200_se3_exp_fwd_f32"), _C.fn("b200_SE3_log_fwd_f32")
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i, sp):
+        j = i % ring
+        _C.check(f_exp(ctypes.c_void_p(xs[j].data_ptr()), ctypes.c_void_p(Xs[j].data_ptr()), n, sp), "exp")
+        _C.check(f_log(ctypes.c_void_p(Xs[j].data_ptr()), ctypes.c_void_p(ys[j].data_ptr()), n, sp), "log")
+
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        sp = ctypes.c_void_p(side.cuda_stream)
+        for i in range(max(args.warmup, ring)):
+            step(i, sp)
+        side.synchronize()
+        # one CUDA graph = one trip round the ring (ring steps, 2*ring kernel launches)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            spc = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for i in range(ring):
+                step(i, spc)
+    torch.cuda.synchronize()
+    trips = max(1, args.steps // ring)
+    steps = trips * ring
+    for _ in range(3):
+        graph.replay()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(trips):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier(world)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms, world, dev)
+    ms_per_step = ms / steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # per-kernel durations (each kernel alone, same ring, same graph technique) for the roofline
+    def time_kernel(which):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                spc = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                for j in range(ring):
+                    if which == "exp":
+                        f_exp(ctypes.c_void_p(xs[j].data_ptr()), ctypes.c_void_p(Xs[j].data_ptr()), n, spc)
+                    else:
+                        f_log(ctypes.c_void_p(Xs[j].data_ptr()), ctypes.c_void_p(ys[j].data_ptr()), n, spc)
+        torch.cuda.synchronize()
+        g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(trips):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (trips * ring)
+
+    t_exp, t_log = time_kernel("exp"), time_kernel("log")
+    peak, peak_src = peaks()
+    dom, t_dom, b_dom = ("se3_exp_fwd_f32", t_exp, BYTES_EXP) if t_exp >= t_log else ("SE3_log_fwd_f32", t_log, BYTES_LOG)
+    ach = n * b_dom / (t_dom * 1e-3) / 1e9
+    step_gbs = n * (BYTES_EXP + BYTES_LOG) / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"stream_kernel<{dom}>", "achieved": round(ach, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
+                "us_per_launch": round(t_dom * 1e3, 2), "exp_us": round(t_exp * 1e3, 2), "log_us": round(t_log * 1e3, 2),
+                "step_gbs": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4)}
+
+    # ---- e2e through the public API with pinned host buffers
+    e2e_steps = max(8, min(64, steps // 50))
+    hx = [xs[j % ring].cpu().pin_memory() for j in range(2)]
+    hy = [torch.empty(n, 6).pin_memory() for _ in range(2)]
+    dx = [torch.empty(n, 6, device=dev) for _ in range(2)]
+
+    def e2e_step(i):
+        k = i % 2
+        dx[k].copy_(hx[k], non_blocking=True)
+        y = pp.se3(dx[k]).Exp().Log()
+        hy[k].copy_(y.tensor(), non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier(world)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(a.elapsed_time(b), world, dev) / e2e_steps
+    e2e = {"value": round(world * n / (e2e_ms * 1e-3) / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": n * 24,
+           "d2h_bytes_per_step": n * 24, "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps,
+           "api": "pp.se3(x).Exp().Log() with pinned host in/out"}
+
+    cpu = cpu_baseline(sample_batches=10) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    extra = {}
+    try:
+        from pypose_b200 import _bench_extra
+        extra = _bench_extra.run(args, rank, world, dev)
+    except ImportError:
+        pass
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": max(args.warmup, ring), "ms_per_step": round(ms_per_step, 6), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "SE3 Exp+Log, batch 1e6 per GPU, fp32 (BASELINE.json configs[1])",
+                           "batch_per_gpu": n, "angles": "U(0, pi-0.01)", "launch": "CUDA graph of one ring trip",
+                           "l2": f"inputs larger than L2: ring of {ring} batches, footprint {footprint >> 20} MiB > 126 MiB L2",
+                           "parallelism": f"dp{world} (independent batches, no collective)"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * steps, "clocks": clocks}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+# (profiles/); None until measured.
+TRAFFIC = {}
+try:
+    TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+except (OSError, ValueError):
+    pass
+
+
+def cpu_baseline(sample_batches):
+    """Reference's torch-CPU op sequence (oracle/torch_port.py) on all host cores."""
+    from oracle import torch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(BATCH, 6, generator=g)
+    torch_port.SE3_log(torch_port.se3_exp(x))          # warm-up
+    best = float("inf")
+    t_all = time.perf_counter()
+    for _ in range(sample_batches):
+        t = time.perf_counter()
+        torch_port.SE3_log(torch_port.se3_exp(x))
+        best = min(best, time.perf_counter() - t)
+    total = time.perf_counter() - t_all
+    return {"value": round(BATCH / (total / sample_batches) / 1e6, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "best_value": round(BATCH / best / 1e6, 3),
+            "sample": f"{sample_batches} x (Exp+Log over one 1e6-element fp32 batch), torch {torch.__version__} CPU, "
+                      f"{cores} threads; mean over the sample"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import torch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(BATCH, 6, generator=g)
+    steps = min(args.steps, 60)
+    for _ in range(min(args.warmup, 3)):
+        torch_port.SE3_log(torch_port.se3_exp(x))
+    t = time.perf_counter()
+    for _ in range(steps):
+        torch_port.SE3_log(torch_port.se3_exp(x))
+    ms = (time.perf_counter() - t) * 1e3 / steps
+    v = round(BATCH / (ms * 1e-3) / 1e6, 3)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SE3 Exp+Log, batch 1e6, fp32 (BASELINE.json configs[1])", "batch_per_gpu": BATCH,
+                       "note": "each step = one full 1e6-element batch on the host; step count bounded to 60"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} x Exp+Log over a 1e6 fp32 batch (oracle/torch_port.py, torch CPU)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

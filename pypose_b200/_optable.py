@@ -1,0 +1,82 @@
+"""Single source of truth for the C-ABI of libb200pose.so.
+
+Every entry point declared in include/b200pose.h, instantiated in csrc/*.cu and bound in _C.py is
+derived from this table (tools/gen_header.py writes the header; tests/test_abi.py checks that the
+built library exports exactly these symbols).
+
+Group layouts follow the reference (pypose/lietensor/lietensor.py:196-198, 354-356, 494-496,
+638-640): D = data width of a group element, K = tangent (manifold) width.
+"""
+
+GROUPS = {
+    # group name: (algebra name, D, K)
+    "SO3": ("so3", 4, 3),
+    "SE3": ("se3", 7, 6),
+    "RxSO3": ("rxso3", 5, 4),
+    "Sim3": ("sim3", 8, 7),
+}
+
+DTYPES = {"f32": "float", "f64": "double"}
+
+# (op, which name prefixes the symbol, input widths, output widths, reference citation)
+# widths: "D" / "K" resolve per group; integers are literal.
+LIE_OPS = [
+    ("exp_fwd", "alg", [("x", "K")], [("X", "D")],
+     "so3_Exp/se3_Exp/rxso3_Exp/sim3_Exp.forward, pypose/lietensor/operation.py:343-357,401-405,448-451,496-500"),
+    ("exp_bwd", "alg", [("x", "K"), ("gX", "D")], [("gx", "K")],
+     "*_Exp.backward: gX[:K] @ Jl(x), operation.py:365-370,413-418,459-464,508-513"),
+    ("log_fwd", "grp", [("X", "D")], [("x", "K")],
+     "SO3_Log/SE3_Log/RxSO3_Log/Sim3_Log.forward, operation.py:308-324,377-382,425-428,471-476"),
+    ("log_bwd", "grp", [("x", "K"), ("gx", "K")], [("gX", "D")],
+     "*_Log.backward: [gx @ Jl^-1(x), 0], operation.py:331-337,389-395,435-441,483-489"),
+    ("inv_fwd", "grp", [("X", "D")], [("Y", "D")],
+     "*_Inv.forward, operation.py:934-936,956-960,980-984,1004-1008"),
+    ("inv_bwd", "grp", [("Y", "D"), ("gY", "D")], [("gX", "D")],
+     "*_Inv.backward: [-gY[:K] @ Adj(Y), 0], operation.py:944-949,968-973,992-997,1016-1021"),
+    ("mul_fwd", "grp", [("X", "D"), ("Y", "D")], [("Z", "D")],
+     "*_Mul.forward, operation.py:833-837,859-862,884-887,909-912"),
+    ("mul_bwd", "grp", [("X", "D"), ("gZ", "D")], [("gX", "D"), ("gY", "D")],
+     "*_Mul.backward: gX=[gZ[:K],0], gY=[gZ[:K] @ Adj(X),0], operation.py:845-852,870-877,895-902,920-927"),
+    ("act_fwd", "grp", [("X", "D"), ("p", 3)], [("out", 3)],
+     "*_Act.forward, operation.py:520-525,549-551,575-577,601-603"),
+    ("act_bwd", "grp", [("X", "D"), ("out", 3), ("g", 3)], [("gX", "D"), ("gp", 3)],
+     "*_Act.backward, operation.py:534-542,560-568,586-594,612-620"),
+    ("act4_fwd", "grp", [("X", "D"), ("p", 4)], [("out", 4)],
+     "*_Act4.forward, operation.py:627-629,652-655,678-680,703-706"),
+    ("act4_bwd", "grp", [("X", "D"), ("out", 4), ("g", 4)], [("gX", "D"), ("gp", 4)],
+     "*_Act4.backward, operation.py:638-646,664-672,689-697,715-722"),
+    ("adj_fwd", "grp", [("X", "D"), ("a", "K")], [("out", "K")],
+     "*_AdjXa.forward: Adj(X) a, operation.py:729-732,755-758,781-784,807-810"),
+    ("adj_bwd", "grp", [("X", "D"), ("out", "K"), ("g", "K")], [("gX", "D"), ("ga", "K")],
+     "*_AdjXa.backward: gX=[-g @ ad(out),0], ga=g @ Adj(X), operation.py:742-748,768-774,794-800,820-826"),
+    ("adjt_fwd", "grp", [("X", "D"), ("a", "K")], [("out", "K")],
+     "*_AdjTXa.forward: Adj(X^-1) a, operation.py:1028-1030,1051-1053,1074-1076,1097-1099"),
+    ("adjt_bwd", "grp", [("X", "D"), ("a", "K"), ("g", "K")], [("gX", "D"), ("ga", "K")],
+     "*_AdjTXa.backward: ga=Adj(X) g, gX=[-a @ ad(ga),0], operation.py:1038-1044,1061-1067,1084-1090,1107-1113"),
+    ("jinvp_fwd", "grp", [("X", "D"), ("p", "K")], [("out", "K")],
+     "LieType.Jinvp: Jl^-1(Log X) p, pypose/lietensor/lietensor.py:257-264,422-429,556-563,700-707"),
+]
+
+# ops that exist for one group only
+EXTRA_OPS = [
+    ("b200_so3_jr", [("x", 3)], [("J", 9)],
+     "so3Type.Jr, pypose/lietensor/lietensor.py:343-351"),
+]
+
+
+def width(w, D, K):
+    return D if w == "D" else K if w == "K" else int(w)
+
+
+def lie_symbols():
+    """Yield (symbol, ctype, ins[(name,width)], outs[(name,width)], citation) for every Lie-op entry point."""
+    for grp, (alg, D, K) in GROUPS.items():
+        for op, which, ins, outs, cite in LIE_OPS:
+            prefix = alg if which == "alg" else grp
+            for sfx, ct in DTYPES.items():
+                yield (f"b200_{prefix}_{op}_{sfx}", ct,
+                       [(n, width(w, D, K)) for n, w in ins],
+                       [(n, width(w, D, K)) for n, w in outs], cite)
+    for base, ins, outs, cite in EXTRA_OPS:
+        for sfx, ct in DTYPES.items():
+            yield (f"{base}_{sfx}", ct, list(ins), list(outs), cite)

@@ -1,0 +1,48 @@
+"""Projection / reprojection residual models (reference: pypose/function/geometry.py:7-225).
+
+Only the camera-model functions the LM configs use are in scope; the
+point-cloud utilities (knn, svdtf, filters) are not part of the hot path.
+"""
+import torch
+
+from ..basics import pm
+from .checking import is_lietensor
+
+
+def cart2homo(coordinates: torch.Tensor):
+    """Append a homogeneous 1 (geometry.py:7-34)."""
+    return torch.cat([coordinates, torch.ones_like(coordinates[..., :1])], dim=-1)
+
+
+def homo2cart(coordinates: torch.Tensor):
+    """Divide by the last coordinate, sign-preserving clamp away from 0 (geometry.py:37-57)."""
+    last = coordinates[..., -1:]
+    denom = pm(last) * last.abs().clamp_(min=torch.finfo(coordinates.dtype).tiny)
+    return coordinates[..., :-1] / denom
+
+
+def point2pixel(points, intrinsics, extrinsics=None):
+    """Pinhole projection of (..., N, 3) points with (..., 3, 3) intrinsics (geometry.py:60-112)."""
+    assert points.size(-1) == 3, "Points shape incorrect"
+    assert intrinsics.size(-1) == intrinsics.size(-2) == 3, "Intrinsics shape incorrect."
+    if extrinsics is None:
+        torch.broadcast_shapes(points.shape[:-2], intrinsics.shape[:-2])
+    else:
+        assert is_lietensor(extrinsics) and extrinsics.shape[-1] == 7, "Type incorrect."
+        torch.broadcast_shapes(points.shape[:-2], intrinsics.shape[:-2], extrinsics.shape[:-1])
+        points = extrinsics.unsqueeze(-2) @ points
+    return homo2cart(points @ intrinsics.mT)
+
+
+def reprojerr(points, pixels, intrinsics, extrinsics=None, reduction='none'):
+    """Per-pixel reprojection error (geometry.py:171-225)."""
+    torch.broadcast_shapes(points.shape[:-2], pixels.shape[:-2], intrinsics.shape[:-2])
+    assert points.size(-1) == 3 and pixels.size(-1) == 2 and \
+        intrinsics.size(-1) == intrinsics.size(-2) == 3, "Shape not compatible."
+    assert reduction in {'norm', 'sum', 'none'}, "Reduction method can only be 'norm'|'sum'|'none'."
+    err = point2pixel(points, intrinsics, extrinsics) - pixels
+    if reduction == 'norm':
+        return err.norm(dim=-1)
+    if reduction == 'sum':
+        return err.sum(dim=-1)
+    return err

@@ -1,0 +1,58 @@
+"""The C-ABI shared library: loads, exports exactly the symbols include/b200pose.h declares, and
+the package has no CPU path (checked in a clean interpreter without the test conftest)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "b200pose.h")).read()
+    return re.findall(r"^(?:int|long long|void|const char\*)\s+(b200_\w+)\s*\(", text, flags=re.M)
+
+
+def test_header_is_generated_from_optable():
+    from pypose_b200._optable import lie_symbols
+    declared = set(header_symbols())
+    assert {s for s, *_ in lie_symbols()} <= declared
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from pypose_b200 import _C
+    lib = ctypes.CDLL(_C.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 138
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_library_exports_nothing_undeclared():
+    from pypose_b200 import _C
+    out = subprocess.run(["nm", "-D", "--defined-only", _C.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and "b200_" in l}
+    assert exported == set(header_symbols())
+
+
+def test_no_cpu_fallback_in_shipped_package():
+    code = (
+        "import torch, pypose_b200 as pp\n"
+        "x = pp.randn_so3(4)\n"
+        "try:\n"
+        "    x.Exp()\n"
+        "except NotImplementedError as e:\n"
+        "    assert 'CPU' in str(e); print('RAISED')\n"
+    )
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert "RAISED" in r.stdout, r.stdout + r.stderr
+
+
+def test_package_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pypose_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

@@ -1,0 +1,78 @@
+"""The device math headers (csrc/lie_math.cuh, lie_ops.cuh) compiled for the HOST by g++ and checked
+against the oracle.  This validates the cross-product re-derivations of every op functor without
+a GPU; the GPU tests (test_lie_gpu.py) then validate the kernels proper through the C-ABI.
+
+Tolerances: fp64 1e-12 (north_star), fp32 2e-6 relative to (1 + |truth|).
+Tiny-angle rows are compared with the oracle in wide_taylor() mode (see oracle/lie_oracle.py)."""
+import numpy as np
+import pytest
+
+from oracle import lie_oracle as O
+from tests import hostmath
+from tests.util import all_ops, gold_case, make_inputs
+
+OPS = all_ops()
+
+
+def _check(res, truth, tol):
+    for r, t in zip(res, truth):
+        err = np.abs(r.astype(np.float64) - t) / (1.0 + np.abs(t))
+        assert err.max() <= tol, f"max rel err {err.max():.3e}"
+
+
+@pytest.mark.parametrize("key,grp,op,inw,outw", OPS, ids=[o[0] for o in OPS])
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-12), (np.float32, 2e-6)], ids=["f64", "f32"])
+def test_functor_vs_oracle_random(key, grp, op, inw, outw, dt, tol):
+    rng = np.random.default_rng(abs(hash(key)) % (2 ** 31))
+    ins = [a.astype(dt) for a in make_inputs(rng, grp, op, 257)]
+    truth = O.run(key, *[a.astype(np.float64) for a in ins])
+    _check(hostmath.run(grp, op, ins, outw), truth, tol)
+
+
+@pytest.mark.parametrize("key,grp,op,inw,outw", OPS, ids=[o[0] for o in OPS])
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-12), (np.float32, 2e-6)], ids=["f64", "f32"])
+def test_functor_vs_golden_inputs_incl_edges(golden, key, grp, op, inw, outw, dt, tol):
+    ins, _ = gold_case(golden, key)
+    ins = [a.astype(dt) for a in ins]
+    with O.wide_taylor():
+        truth = O.run(key, *[a.astype(np.float64) for a in ins])
+    _check(hostmath.run(grp, op, ins, outw), truth, tol)
+
+
+def test_functor_vs_reference_golden_where_reference_is_accurate(golden):
+    """Against the raw reference outputs, restricted to rows with theta >= 1e-2 (above that the
+    reference's fp64 closed forms are accurate to ~1e-12)."""
+    for key, grp, op, inw, outw in OPS:
+        ins, outs = gold_case(golden, key)
+        res = hostmath.run(grp, op, ins, outw)
+        with O.wide_taylor():
+            truth = O.run(key, *ins)
+        ok = np.ones(ins[0].shape[0], bool)
+        for o, t in zip(outs, truth):       # rows where the reference itself is within 1e-11 of truth
+            ok &= (np.abs(o - t) / (1 + np.abs(t))).max(1) < 1e-11
+        assert ok.sum() >= 40
+        for r, o in zip(res, outs):
+            assert (np.abs(r - o)[ok] / (1 + np.abs(o[ok]))).max() < 1e-11, key
+
+
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-12), (np.float32, 2e-6)], ids=["f64", "f32"])
+def test_so3_jr(golden, dt, tol):
+    ins, _ = gold_case(golden, "so3_jr")
+    with O.wide_taylor():
+        truth = O.run("so3_jr", ins[0])
+    _check(hostmath.run("SO3", "jr", [ins[0].astype(dt)], [9]), truth, tol)
+
+
+@pytest.mark.parametrize("grp", ["SO3", "SE3", "RxSO3", "Sim3"])
+def test_exp_log_roundtrip_tolerance(grp):
+    """north_star: Exp o Log round trip <= 1e-6 (fp32) / 1e-12 (fp64), angles in (0, pi-0.01)."""
+    from pypose_b200._optable import GROUPS
+    _, D, K = GROUPS[grp]
+    rng = np.random.default_rng(7)
+    from tests.util import rand_algebra
+    x = rand_algebra(rng, grp, 4096, tmin=1e-6, tmax=np.pi - 0.01)
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 1e-6)):
+        X = hostmath.run(grp, "exp_fwd", [x.astype(dt)], [D])[0]
+        x2 = hostmath.run(grp, "log_fwd", [X], [K])[0]
+        err = np.abs(x2.astype(np.float64) - x.astype(dt).astype(np.float64)) / (1 + np.abs(x))
+        assert err.max() <= tol, f"{grp} {dt.__name__}: {err.max():.3e}"

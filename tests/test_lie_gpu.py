@@ -1,0 +1,133 @@
+"""GPU parity: every C-ABI Lie-op entry point vs the oracle (fp64 numpy restatement of the
+reference), called through the C-ABI (ctypes) on device buffers.
+
+Tolerances (stated per north_star): fp64 1e-12, fp32 2e-6, both relative to (1 + |truth|).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lie_oracle as O
+from tests.util import all_ops, gold_case, make_inputs, rand_algebra
+from pypose_b200 import _C
+from pypose_b200._optable import GROUPS
+
+pytestmark = pytest.mark.gpu
+OPS = all_ops()
+TOL = {torch.float64: 1e-12, torch.float32: 2e-6}
+
+
+def run_abi(key, ins_np, outw, dtype):
+    ins = [torch.from_numpy(np.ascontiguousarray(a)).to(dtype).cuda() for a in ins_np]
+    outs = _C.launch_rows(f"b200_{key}", ins, outw)
+    torch.cuda.synchronize()
+    return [o.double().cpu().numpy() for o in outs], ins
+
+
+def check(res, truth, tol, what=""):
+    for r, t in zip(res, truth):
+        assert r.shape == t.shape
+        err = np.abs(r - t) / (1.0 + np.abs(t))
+        assert np.isfinite(r).all(), what
+        assert err.max() <= tol, f"{what}: max rel err {err.max():.3e}"
+
+
+@pytest.mark.parametrize("key,grp,op,inw,outw", OPS, ids=[o[0] for o in OPS])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_op_vs_oracle_random(key, grp, op, inw, outw, dtype):
+    rng = np.random.default_rng(abs(hash(key)) % (2 ** 31))
+    ins = make_inputs(rng, grp, op, 20011)      # ragged: not a multiple of 4 / of the tile
+    res, dev_ins = run_abi(key, ins, outw, dtype)
+    truth = O.run(key, *[t.double().cpu().numpy() for t in dev_ins])
+    check(res, truth, TOL[dtype], key)
+
+
+@pytest.mark.parametrize("key,grp,op,inw,outw", OPS, ids=[o[0] for o in OPS])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_op_vs_golden_inputs_incl_edges(golden, key, grp, op, inw, outw, dtype):
+    ins, outs = gold_case(golden, key)
+    res, dev_ins = run_abi(key, ins, outw, dtype)
+    with O.wide_taylor():
+        truth = O.run(key, *[t.double().cpu().numpy() for t in dev_ins])
+    check(res, truth, TOL[dtype], key)
+    if dtype == torch.float64:
+        # raw reference outputs, on the rows where the reference itself is accurate
+        ok = np.ones(ins[0].shape[0], bool)
+        for o, t in zip(outs, truth):
+            ok &= (np.abs(o - t) / (1 + np.abs(t))).max(1) < 1e-11
+        for r, o in zip(res, outs):
+            assert (np.abs(r - o)[ok] / (1 + np.abs(o[ok]))).max() < 1e-11
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+def test_so3_jr(golden, dtype):
+    ins, _ = gold_case(golden, "so3_jr")
+    res, dev_ins = run_abi("so3_jr", ins, [9], dtype)
+    with O.wide_taylor():
+        truth = O.run("so3_jr", dev_ins[0].double().cpu().numpy())
+    check(res, truth, TOL[dtype])
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 255, 256, 257, 1023, 4099])
+def test_ragged_and_empty_sizes(n):
+    rng = np.random.default_rng(n)
+    x = rand_algebra(rng, "SE3", n) if n else np.zeros((0, 6))
+    res, _ = run_abi("se3_exp_fwd", [x], [7], torch.float64)
+    assert res[0].shape == (n, 7)
+    if n:
+        check(res, [O.exp("SE3", x)], 1e-12)
+
+
+def test_misaligned_base_pointers_take_scalar_path():
+    rng = np.random.default_rng(5)
+    x = rand_algebra(rng, "SE3", 1000)
+    buf = torch.zeros(1000 * 6 + 1, dtype=torch.float32, device="cuda")
+    xv = buf[1:].view(1000, 6)                       # 4-byte aligned only
+    xv.copy_(torch.from_numpy(x).float())
+    assert xv.data_ptr() % 16 != 0
+    (X,) = _C.launch_rows("b200_se3_exp_fwd", [xv], [7])
+    truth = O.exp("SE3", xv.double().cpu().numpy())
+    check([X.double().cpu().numpy()], [truth], 2e-6)
+
+
+@pytest.mark.parametrize("grp", list(GROUPS))
+def test_full_size_roundtrip_and_properties(grp):
+    """BASELINE.json configs[1] size (10^6, fp32 and fp64): size-independent properties.
+    Exp->Log round trip <= 1e-6 / 1e-12; X * X^-1 = identity; Adj(X) a identity of
+    reference tests/lietensor/test_lietensor.py:108-111 in the group."""
+    alg, D, K = GROUPS[grp]
+    n = 1_000_000
+    rng = np.random.default_rng(11)
+    x64 = rand_algebra(rng, grp, n, tmin=1e-6, tmax=np.pi - 0.01)
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 1e-6)):
+        x = torch.from_numpy(x64).to(dtype).cuda()
+        (X,) = _C.launch_rows(f"b200_{alg}_exp_fwd", [x], [D])
+        (x2,) = _C.launch_rows(f"b200_{grp}_log_fwd", [X], [K])
+        err = ((x2 - x).abs() / (1 + x.abs())).max().item()
+        assert err <= tol, f"{grp} {dtype}: round trip {err:.3e}"
+        (Xi,) = _C.launch_rows(f"b200_{grp}_inv_fwd", [X], [D])
+        (I,) = _C.launch_rows(f"b200_{grp}_mul_fwd", [X, Xi], [D])
+        (li,) = _C.launch_rows(f"b200_{grp}_log_fwd", [I], [K])
+        assert li.abs().max().item() <= 50 * tol
+        # Adj(X, a).Exp() * X == X * a.Exp()
+        a = 0.3 * torch.randn(n, K, dtype=dtype, device="cuda")
+        (Aa,) = _C.launch_rows(f"b200_{grp}_adj_fwd", [X, a], [K])
+        (EA,) = _C.launch_rows(f"b200_{alg}_exp_fwd", [Aa], [D])
+        (Ea,) = _C.launch_rows(f"b200_{alg}_exp_fwd", [a], [D])
+        (L,) = _C.launch_rows(f"b200_{grp}_mul_fwd", [EA, X], [D])
+        (R,) = _C.launch_rows(f"b200_{grp}_mul_fwd", [X, Ea], [D])
+        (Ri,) = _C.launch_rows(f"b200_{grp}_inv_fwd", [R], [D])
+        (Dl,) = _C.launch_rows(f"b200_{grp}_mul_fwd", [L, Ri], [D])
+        (d,) = _C.launch_rows(f"b200_{grp}_log_fwd", [Dl], [K])
+        assert d.abs().max().item() <= (2e-4 if dtype == torch.float32 else 1e-9)
+
+
+def test_python_api_runs_on_cuda_and_autograd():
+    import pypose_b200 as pp
+    x = pp.randn_se3(64, device="cuda", dtype=torch.float64, requires_grad=True)
+    X = x.Exp()
+    y = (X.Inv() @ X).Log().tensor()
+    assert y.abs().max() < 1e-12
+    loss = (pp.randn_SE3(64, device="cuda", dtype=torch.float64) @ X).Log().tensor().square().sum()
+    loss.backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all()
