@@ -142,7 +142,7 @@ def rxso3_Ws(x):
     sl, tl = np.abs(sigma) > np.finfo(x.dtype).eps, th > np.finfo(x.dtype).eps
     s, s2, t2 = np.exp(sigma), sigma * sigma, th * th
     with np.errstate(all="ignore"):
-        C = np.where(sl, (s - 1.0) / sigma, 1.0)
+        C = np.where(sl, (np.expm1(sigma) if _WIDE[0] else (s - 1.0)) / sigma, 1.0)   # wide: no (e^s - 1) cancellation
         A1, B1 = 0.5, 1.0 / 6
         A2, B2 = (1.0 - np.cos(th)) / t2, (th - np.sin(th)) / (t2 * th)
         if _WIDE[0]:

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "lie_ops.cuh"
 
 namespace b200pose {
@@ -103,6 +104,141 @@ __global__ void __launch_bounds__(kThreads) stream_kernel(StreamParams<typename 
   }
 }
 
+// ----------------------------------------------------------------------------
+// v2 shell: persistent CTAs, 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) into a multi-stage
+// shared-memory ring signalled by mbarriers, bulk stores back (cp.async.bulk.global.shared).
+// One elected thread issues all copies, so the other threads spend their issue slots on math only
+// and loads for tile i+S overlap the math of tile i *inside* a CTA (v1 relies on other CTAs for that,
+// which fails when a single wave of CTAs runs in lock-step: ncu profiles/r1a).
+// Requirements: all base pointers 16 B aligned and every tile a multiple of 4 elements (the launcher
+// guarantees both; the <= 3 element remainder and unaligned tensors go through the v1 kernel).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class Op, int S, int OS> struct TmaLayout {
+  using T = typename Op::T;
+  static constexpr int TILE = kThreads;
+  static constexpr int IN_WORDS = TILE * (Op::DI0 + (Op::NIN > 1 ? Op::DI1 : 0) + (Op::NIN > 2 ? Op::DI2 : 0));
+  static constexpr int OUT_WORDS = TILE * (Op::DO0 + (Op::NOUT > 1 ? Op::DO1 : 0));
+  static constexpr int BYTES = (S * IN_WORDS + OS * OUT_WORDS) * (int)sizeof(T) + 8 * S;
+};
+
+template <class Op, int S, int OS>
+__global__ void __launch_bounds__(kThreads) stream_kernel_tma(StreamParams<typename Op::T, Op::NIN, Op::NOUT> p) {
+  using T = typename Op::T;
+  using L = TmaLayout<Op, S, OS>;
+  constexpr int TILE = L::TILE;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T* s_in = reinterpret_cast<T*>(smem_raw);
+  T* s_out = s_in + S * L::IN_WORDS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_out + OS * L::OUT_WORDS);
+
+  const long long begin = (long long)blockIdx.x * p.chunk;
+  long long end = begin + p.chunk;
+  if (end > p.n) end = p.n;
+  const int ntiles = begin < end ? (int)((end - begin + TILE - 1) / TILE) : 0;
+  const int tid = threadIdx.x;
+
+  // Programmatic dependent launch: let the next kernel in the stream start its launch/prologue now, and
+  // hold our own first global access until the previous kernel has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
+
+  const int last_cnt = ntiles ? (int)(end - begin - (long long)(ntiles - 1) * TILE) : 0;
+
+  auto issue_load = [&](int t, int s) {   // thread 0 only: tile t -> stage s
+    const long long base = begin + (long long)t * TILE;
+    const int cnt = (t == ntiles - 1) ? last_cnt : TILE;
+    T* dst = s_in + s * L::IN_WORDS;
+    const uint32_t b0 = cnt * Op::DI0 * sizeof(T), b1 = Op::NIN > 1 ? cnt * Op::DI1 * sizeof(T) : 0,
+                   b2 = Op::NIN > 2 ? cnt * Op::DI2 * sizeof(T) : 0;
+    mbar_expect_tx(&full[s], b0 + b1 + b2);
+    bulk_g2s(dst, p.in[0] + base * Op::DI0, b0, &full[s]);
+    if (Op::NIN > 1) bulk_g2s(dst + TILE * Op::DI0, p.in[Op::NIN > 1 ? 1 : 0] + base * Op::DI1, b1, &full[s]);
+    if (Op::NIN > 2)
+      bulk_g2s(dst + TILE * (Op::DI0 + Op::DI1), p.in[Op::NIN > 2 ? 2 : 0] + base * Op::DI2, b2, &full[s]);
+  };
+
+  if (tid == 0) {
+    const int pre = ntiles < S ? ntiles : S;
+    for (int t = 0; t < pre; ++t) issue_load(t, t);
+  }
+
+  int s = 0, os = 0;          // running stage indices (no i % S in the loop)
+  uint32_t parity = 0;
+  for (int i = 0; i < ntiles; ++i) {
+    const int cnt = (i == ntiles - 1) ? last_cnt : TILE;
+    const T* in0 = s_in + s * L::IN_WORDS;
+    const T* in1 = in0 + TILE * Op::DI0;
+    const T* in2 = in1 + (Op::NIN > 1 ? TILE * Op::DI1 : 0);
+    T* out0 = s_out + os * L::OUT_WORDS;
+    T* out1 = out0 + TILE * Op::DO0;
+
+    mbar_wait(&full[s], parity);
+    if (tid < cnt) {
+      T i0[Op::DI0], i1[Op::DI1], i2[Op::DI2], o0[Op::DO0], o1[Op::DO1];
+      row_get<Op::DI0>(in0, tid, i0);
+      if (Op::NIN > 1) row_get<Op::DI1>(in1, tid, i1);
+      if (Op::NIN > 2) row_get<Op::DI2>(in2, tid, i2);
+      Op::apply(i0, i1, i2, o0, o1);
+      row_put<Op::DO0>(out0, tid, o0);
+      if (Op::NOUT > 1) row_put<Op::DO1>(out1, tid, o1);
+    }
+    // out[(i+1) % OS] is written next iteration: its previous store (tile i+1-OS) must have been read
+    // out of shared memory.  Stores pending now: tiles <= i-1; allow the newest OS-2 of them to stay.
+    if (tid == 0) bulk_wait_read<(OS >= 2 ? OS - 2 : 0)>();
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const long long base = begin + (long long)i * TILE;
+      bulk_s2g(p.out[0] + base * Op::DO0, out0, cnt * Op::DO0 * sizeof(T));
+      if (Op::NOUT > 1) bulk_s2g(p.out[Op::NOUT > 1 ? 1 : 0] + base * Op::DO1, out1, cnt * Op::DO1 * sizeof(T));
+      bulk_commit();
+      if (i + S < ntiles) issue_load(i + S, s);
+    }
+    if (++s == S) { s = 0; parity ^= 1; }
+    if (++os == OS) os = 0;
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
 struct DeviceInfo { int sms; };
 inline const DeviceInfo& device_info() {
   static thread_local int cached_dev = -1;
@@ -147,13 +283,80 @@ int launch_stream_ept(const typename Op::T* const* in, typename Op::T* const* ou
   return (int)cudaGetLastError();
 }
 
+// B200POSE_STREAM=v1 forces the plain-load shell (A/B measurements); B200POSE_CTAS_PER_SM caps residency.
+inline int stream_impl_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200POSE_STREAM"); v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }
+  return v;
+}
+inline int stream_pdl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200POSE_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
+}
+inline int stream_max_ctas_per_sm() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200POSE_CTAS_PER_SM"); v = e ? atoi(e) : 8; if (v < 1) v = 8; }
+  return v;
+}
+
+template <class Op, int S, int OS>
+int launch_stream_tma(const typename Op::T* const* in, typename Op::T* const* out, long long n, cudaStream_t stream) {
+  using T = typename Op::T;
+  using L = TmaLayout<Op, S, OS>;
+  auto kern = stream_kernel_tma<Op, S, OS>;
+  static thread_local int occ = 0;
+  if (occ == 0) {
+    if (L::BYTES > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, L::BYTES);
+    if (occ < 1) occ = 1;
+    if (occ > stream_max_ctas_per_sm()) occ = stream_max_ctas_per_sm();
+  }
+  StreamParams<T, Op::NIN, Op::NOUT> p;
+  for (int i = 0; i < Op::NIN; ++i) p.in[i] = in[i];
+  for (int i = 0; i < Op::NOUT; ++i) p.out[i] = out[i];
+  p.vec_ok = 1;
+  p.n = n;
+  long long tiles = (n + L::TILE - 1) / L::TILE;
+  long long slots = (long long)device_info().sms * occ;
+  long long grid = tiles < slots ? tiles : slots;
+  long long chunk = (n + grid - 1) / grid;
+  chunk = (chunk + 3) & ~3LL;
+  grid = (n + chunk - 1) / chunk;
+  p.chunk = chunk;
+  kern<<<(unsigned)grid, kThreads, L::BYTES, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
 template <class Op>
-int launch_stream(const typename Op::T* const* in, typename Op::T* const* out, long long n, cudaStream_t stream) {
-  if (n <= 0) return 0;
+int launch_stream_v1(const typename Op::T* const* in, typename Op::T* const* out, long long n, cudaStream_t stream) {
   // two rows per thread per barrier once there is enough work to fill the machine twice over
   if (n >= 2LL * kThreads * 2 * device_info().sms * 4 && sizeof(typename Op::T) == 4)
     return launch_stream_ept<Op, 2>(in, out, n, stream);
   return launch_stream_ept<Op, 1>(in, out, n, stream);
+}
+
+template <class Op>
+int launch_stream(const typename Op::T* const* in, typename Op::T* const* out, long long n, cudaStream_t stream) {
+  using T = typename Op::T;
+  if (n <= 0) return 0;
+  uintptr_t align = 0;
+  for (int i = 0; i < Op::NIN; ++i) align |= reinterpret_cast<uintptr_t>(in[i]);
+  for (int i = 0; i < Op::NOUT; ++i) align |= reinterpret_cast<uintptr_t>(out[i]);
+  const long long n4 = n & ~3LL;
+  if ((align & 15) != 0 || n4 == 0 || stream_impl_v1()) return launch_stream_v1<Op>(in, out, n, stream);
+  constexpr int S = sizeof(T) == 4 ? 3 : 2;
+  constexpr int OS = 2;
+  int rc = launch_stream_tma<Op, S, OS>(in, out, n4, stream);
+  if (rc != 0 || n4 == n) return rc;
+  // <= 3 trailing elements: plain-load kernel on offset pointers
+  const T* in_t[3] = {nullptr, nullptr, nullptr};
+  T* out_t[2] = {nullptr, nullptr};
+  const int di[3] = {Op::DI0, Op::DI1, Op::DI2};
+  const int dout[2] = {Op::DO0, Op::DO1};
+  for (int i = 0; i < Op::NIN; ++i) in_t[i] = in[i] + n4 * di[i];
+  for (int i = 0; i < Op::NOUT; ++i) out_t[i] = out[i] + n4 * dout[i];
+  return launch_stream_ept<Op, 1>(in_t, out_t, n - n4, stream);
 }
 
 // ----------------------------------------------------------------------------

@@ -66,6 +66,31 @@ LM_HD void m_sincos(double x, double& s, double& c) {
 #endif
 }
 
+// Reciprocal and reciprocal square root.  fp32 on the device: one MUFU approximation + one Newton step
+// (~1 ulp, 3-4 instructions, no branches) instead of the IEEE division / sqrt sequences whose
+// denormal fix-up paths cost ~10 extra instructions and a divergent branch each (ncu profiles/r1a).
+// x = 0 yields inf/NaN exactly like 1/x would; callers select those lanes away.
+LM_HD float m_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+  return 1.0f / x;
+#endif
+}
+LM_HD double m_rcp(double x) { return 1.0 / x; }
+LM_HD float m_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return fmaf(0.5f * y, fmaf(-x * y, y, 1.0f), y);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+LM_HD double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+
 // pm(x): sign with pm(0) = +1 (reference basics/ops.py:26)
 template <typename T> LM_HD T pm(T x) { return x < T(0) ? T(-1) : T(1); }
 
@@ -131,19 +156,19 @@ template <typename T> LM_HD RotCoef<T> rot_coef(const V3<T>& phi) {
   RotCoef<T> r;
   T x = dot(phi, phi);
   r.theta2 = x;
-  r.theta = m_sqrt(x);
   r.small = x < num<T>::small2;
+  const T inv = m_rsqrt(x);          // 1/theta (inf at 0: only used through selects)
+  r.theta = (x > T(1e-30)) ? x * inv : T(0);   // theta < 1e-15 behaves as 0 (cos(theta/2) == 1)
   m_sincos(T(0.5) * r.theta, r.sh, r.ch);
-  if (r.small) {
-    // series in x; remainder < 1e-10 (fp32 window) / 1e-22 (fp64 window)
-    r.imag = T(0.5) + x * (T(-1.0 / 48) + x * (T(1.0 / 3840) + x * (T(-1.0 / 645120) + x * T(1.0 / 185794560))));
-    r.c2 = T(1.0 / 6) + x * (T(-1.0 / 120) + x * (T(1.0 / 5040) + x * (T(-1.0 / 362880) + x * T(1.0 / 39916800))));
-  } else {
-    T inv = T(1) / r.theta;
-    r.imag = r.sh * inv;
-    // theta - sin(theta) = theta - 2 sh ch
-    r.c2 = (r.theta - T(2) * r.sh * r.ch) * inv * inv * inv;
-  }
+  // both evaluations are computed and selected (FSEL): warps almost always hold both kinds of lanes,
+  // so a branch would execute both sides anyway plus the divergence bookkeeping.
+  // series in x; remainder < 1e-10 (fp32 window) / 1e-22 (fp64 window)
+  const T imag_s = T(0.5) + x * (T(-1.0 / 48) + x * (T(1.0 / 3840) + x * (T(-1.0 / 645120) + x * T(1.0 / 185794560))));
+  const T c2_s = T(1.0 / 6) + x * (T(-1.0 / 120) + x * (T(1.0 / 5040) + x * (T(-1.0 / 362880) + x * T(1.0 / 39916800))));
+  const T imag_c = r.sh * inv;
+  const T c2_c = (r.theta - T(2) * r.sh * r.ch) * inv * inv * inv;     // theta - sin(theta) = theta - 2 sh ch
+  r.imag = r.small ? imag_s : imag_c;
+  r.c2 = r.small ? c2_s : c2_c;
   r.c1 = T(2) * r.imag * r.imag;  // (1-cos)/theta^2 = 2 sin^2(theta/2)/theta^2, no cancellation
   return r;
 }
@@ -155,26 +180,26 @@ template <typename T> LM_HD T jlinv_series(T x) {
 }
 template <typename T> LM_HD T jlinv_coef(const V3<T>& phi) {
   T x = dot(phi, phi);
-  if (x < num<T>::small2) return jlinv_series(x);
-  T th = m_sqrt(x), s, c;
+  const bool small = x < num<T>::small2;
+  T th = x * m_rsqrt(x), s, c;          // NaN at x = 0 is selected away below
   m_sincos(T(0.5) * th, s, c);
-  return (T(1) - T(0.5) * th * c / s) / x;
+  const T closed = (T(1) - T(0.5) * th * c * m_rcp(s)) * m_rcp(x);
+  return small ? jlinv_series(x) : closed;
 }
 
 // extra coefficients of Q(tau, phi) (op.py:37-58): a1 = c2, a2, a3
 template <typename T> LM_HD void q_coef(const RotCoef<T>& r, T& a2, T& a3) {
-  T x = r.theta2;
-  if (r.small) {
-    a2 = T(1.0 / 24) + x * (T(-1.0 / 720) + x * (T(1.0 / 40320) + x * (T(-1.0 / 3628800) + x * T(1.0 / 479001600))));
-    a3 = T(1.0 / 120) + x * (T(-2.0 / 5040) + x * (T(3.0 / 362880) + x * (T(-4.0 / 39916800) + x * T(5.0 / 6227020800.0))));
-  } else {
-    T th = r.theta;
-    T st = T(2) * r.sh * r.ch;               // sin(theta)
-    T one_m_cos = T(2) * r.sh * r.sh;        // 1 - cos(theta)
-    T x2 = x * x;
-    a2 = (x - T(2) * one_m_cos) / (T(2) * x2);                       // (th^2 + 2cos - 2)/(2 th^4)
-    a3 = (T(3) * (th - st) - th * one_m_cos) / (T(2) * x2 * th);     // (2th - 3sin + th cos)/(2 th^5)
-  }
+  const T x = r.theta2;
+  const T a2_s = T(1.0 / 24) + x * (T(-1.0 / 720) + x * (T(1.0 / 40320) + x * (T(-1.0 / 3628800) + x * T(1.0 / 479001600))));
+  const T a3_s = T(1.0 / 120) + x * (T(-2.0 / 5040) + x * (T(3.0 / 362880) + x * (T(-4.0 / 39916800) + x * T(5.0 / 6227020800.0))));
+  const T th = r.theta;
+  const T st = T(2) * r.sh * r.ch;               // sin(theta)
+  const T one_m_cos = T(2) * r.sh * r.sh;        // 1 - cos(theta)
+  const T ix2 = m_rcp(T(2) * x * x);
+  const T a2_c = (x - T(2) * one_m_cos) * ix2;                          // (th^2 + 2cos - 2)/(2 th^4)
+  const T a3_c = (T(3) * (th - st) - th * one_m_cos) * ix2 * m_rcp(th); // (2th - 3sin + th cos)/(2 th^5)
+  a2 = r.small ? a2_s : a2_c;
+  a3 = r.small ? a3_s : a3_c;
 }
 
 // ----------------------------------------------------------------------------
@@ -189,25 +214,25 @@ template <typename T> LM_HD Q4<T> so3_exp(const V3<T>& phi, const RotCoef<T>& r)
 // principal branch, so no sincos is needed.
 template <typename T> LM_HD V3<T> so3_log(const Q4<T>& q, T& jinv_c) {
   const T eps = num<T>::eps;
-  T n2 = dot(q.v, q.v);
-  T n = m_sqrt(n2);
-  T w = q.w;
-  T factor;
-  if (n > eps) {
-    if (m_abs(w) > eps) {
-      T half = m_atan(n / w);           // theta/2 in (-pi/2, pi/2)
-      factor = T(2) * half / n;
-      T x = T(4) * half * half;
-      // (1 - (theta/2)(w/n)) / theta^2
-      jinv_c = (x < num<T>::small2) ? jlinv_series(x) : (T(1) - half * w / n) / x;
-    } else {
-      factor = pm(w) * T(3.14159265358979323846) / n;
-      jinv_c = T(1) / T(3.14159265358979323846 * 3.14159265358979323846);
-    }
-  } else {
-    factor = T(2) * (T(1) / w - n2 / (T(3) * w * w * w));
-    jinv_c = T(1.0 / 12);
-  }
+  const T PI = T(3.14159265358979323846);
+  const T n2 = dot(q.v, q.v);
+  const T inv_n = m_rsqrt(n2);
+  const T n = n2 * inv_n;                // NaN at n2 = 0: that lane takes the third branch below
+  const T w = q.w;
+  // branch 1 (op.py:320): |v| > eps and |w| > eps
+  const T half = m_atan(n * m_rcp(w));   // theta/2 in (-pi/2, pi/2)
+  const T x = T(4) * half * half;
+  const T f1 = T(2) * half * inv_n;
+  const T c1 = (x < num<T>::small2) ? jlinv_series(x) : (T(1) - half * w * inv_n) * m_rcp(x);
+  // branch 2 (op.py:321): |w| <= eps -> theta = +-pi
+  const T f2 = pm(w) * PI * inv_n;
+  const T c2 = T(1) / (PI * PI);
+  // branch 3 (op.py:322): |v| <= eps -> series in |v|/w
+  const T iw = m_rcp(w);
+  const T f3 = T(2) * (iw - n2 * iw * iw * iw * T(1.0 / 3));
+  const bool vbig = n2 > eps * eps, wbig = m_abs(w) > eps;
+  const T factor = vbig ? (wbig ? f1 : f2) : f3;
+  jinv_c = vbig ? (wbig ? c1 : c2) : T(1.0 / 12);
   return factor * q.v;
 }
 
@@ -270,7 +295,7 @@ template <typename T> LM_HD WsCoef<T> ws_coef(const V3<T>& phi, T sigma) {
   T s = em1 + T(1);
   bool sig_small = m_abs(sigma) < num<T>::sig_small;
   // C = (e^sigma - 1)/sigma
-  o.C = (m_abs(sigma) > num<T>::eps) ? em1 / sigma : T(1);
+  o.C = (m_abs(sigma) > num<T>::eps) ? em1 * m_rcp(sigma) : T(1);
   if (x < num<T>::tiny2) {
     // theta -> 0 limits: A = ((sigma-1)s+1)/sigma^2, B = (s(sigma^2/2 - sigma + 1) - 1)/sigma^3.
     // A multiplies K (|K| = theta) and B multiplies K^2, so first-order accuracy is enough.
@@ -279,8 +304,9 @@ template <typename T> LM_HD WsCoef<T> ws_coef(const V3<T>& phi, T sigma) {
       o.B = T(1.0 / 6) + sigma * (T(1.0 / 8) + sigma * (T(1.0 / 20) + sigma * T(1.0 / 72)));
     } else {
       T s2 = sigma * sigma;
-      o.A = ((sigma - T(1)) * s + T(1)) / s2;
-      o.B = (s * (T(0.5) * s2 - sigma + T(1)) - T(1)) / (s2 * sigma);
+      const T is2 = m_rcp(s2);
+      o.A = ((sigma - T(1)) * s + T(1)) * is2;
+      o.B = (s * (T(0.5) * s2 - sigma + T(1)) - T(1)) * is2 * m_rcp(sigma);
     }
     return o;
   }
@@ -291,9 +317,9 @@ template <typename T> LM_HD WsCoef<T> ws_coef(const V3<T>& phi, T sigma) {
   T ct = T(1) - omc;                // cos(theta)
   T a = s * st;
   T bm1 = em1 * ct - omc;           // s cos(theta) - 1, cancellation-free
-  T c = x + sigma * sigma;
-  o.A = (a * sigma - bm1 * th) / (th * c);
-  o.B = (o.C - (bm1 * sigma + a * th) / c) / x;
+  const T ic = m_rcp(x + sigma * sigma);
+  o.A = (a * sigma - bm1 * th) * ic * m_rcp(th);
+  o.B = (o.C - (bm1 * sigma + a * th) * ic) * m_rcp(x);
   return o;
 }
 template <typename T> LM_HD V3<T> ws_apply(const WsCoef<T>& k, const V3<T>& phi, const V3<T>& u) {
@@ -304,10 +330,10 @@ template <typename T> LM_HD V3<T> ws_apply(const WsCoef<T>& k, const V3<T>& phi,
 // calls a numeric 3x3 .inverse() (op.py:473)
 template <typename T> LM_HD V3<T> ws_inv_apply(const WsCoef<T>& k, const V3<T>& phi, const V3<T>& u) {
   T D = k.C - k.theta2 * k.B;
-  T det = D * D + k.theta2 * k.A * k.A;
-  T alpha = T(1) / k.C;
-  T beta = -k.A / det;
-  T gamma = alpha * (k.A * k.A - k.B * D) / det;
+  T idet = m_rcp(D * D + k.theta2 * k.A * k.A);
+  T alpha = m_rcp(k.C);
+  T beta = -k.A * idet;
+  T gamma = alpha * (k.A * k.A - k.B * D) * idet;
   V3<T> a = cross(phi, u);
   return alpha * u + beta * a + gamma * cross(phi, a);
 }
@@ -483,7 +509,7 @@ template <class G, typename T> LM_HD Tang<T> jlinv_apply_g(const Tang<T>& x, con
 // Inv (op.py:930-936, 952-960, 976-984, 1000-1008)
 template <class G, typename T> LM_HD Elem<T> g_inv(const Elem<T>& X) {
   Elem<T> Y; Y.q = qconj(X.q); Y.s = T(1); Y.t = mk(T(0), T(0), T(0));
-  if (has_s<G>::v) Y.s = T(1) / X.s;
+  if (has_s<G>::v) Y.s = m_rcp(X.s);
   if (has_t<G>::v) { V3<T> r = qrot(Y.q, X.t); Y.t = -(Y.s * r); }
   return Y;
 }

