@@ -1,0 +1,147 @@
+"""CPU oracle of the LM inner loop — TEST INFRASTRUCTURE ONLY (see lie_oracle.py header).
+
+Restates pypose/optim/optimizer.py:645-680 (dense LevenbergMarquardt.step) in numpy, twice:
+
+* `dense_lm_step`  — literally the reference algorithm on a dense Jacobian with 7 columns per SE3 pose
+  (the 7th identically zero, optimizer.py:657 clamp making its diagonal 1e-6);
+* block functions (`poseinv_trial`, `reproj_accum`, `solve6_retract`, ...) with the C-ABI signatures
+  of csrc/lm.cu, which are what the CUDA kernels are compared against.
+
+tests/test_lm.py checks block == dense, and both against trajectories recorded from the reference's
+own LM (tests/golden/lm.npz, oracle/make_golden_lm.py).
+"""
+import numpy as np
+
+from . import lie_oracle as O
+
+
+def _triu_pack(A):
+    iu = np.triu_indices(6)
+    return A[..., iu[0], iu[1]]
+
+
+def _triu_unpack(H21):
+    iu = np.triu_indices(6)
+    A = np.zeros(H21.shape[:-1] + (6, 6), dtype=H21.dtype)
+    A[..., iu[0], iu[1]] = H21
+    A[..., iu[1], iu[0]] = H21
+    return A
+
+
+# ------------------------------------------------------------------ PoseInv: r = Log(P X)
+def poseinv_residual(P, X):
+    return O.log("SE3", O.mul("SE3", P, X))
+
+
+def poseinv_jac_blocks(P, X):
+    """d Log(P X) / dP (left perturbation) = Jl^-1(r): the reference obtains it as the product of
+    SE3_Log.backward (op.py:389-395) and SE3_Mul.backward wrt X (identity, op.py:870-877)."""
+    r = poseinv_residual(P, X)
+    return r, O.se3_Jl_inv(r)
+
+
+def damped_solve(A, g, scale, dmin, dmax):
+    """clamp (optimizer.py:657), cumulative damping (:666), Cholesky solve (solver.py:213-216)."""
+    A0 = A.copy()
+    A = A.copy()
+    idx = np.arange(A.shape[-1])
+    A[..., idx, idx] = np.clip(A[..., idx, idx], dmin, dmax) * scale
+    L = np.linalg.cholesky(A)
+    y = np.linalg.solve(L, -g[..., None])
+    D = np.linalg.solve(np.swapaxes(L, -1, -2), y)[..., 0]
+    predicted = np.einsum('...i,...ij,...j->...', D, A0, D) + 2 * np.einsum('...i,...i->...', D, g)
+    return D, predicted
+
+
+def retract(D, P):
+    return O.mul("SE3", O.exp("SE3", D), P)
+
+
+def poseinv_loss(P, X):
+    return np.array([(poseinv_residual(P, X) ** 2).sum()])
+
+
+def poseinv_trial(P, X, scale, dmin, dmax):
+    r, J = poseinv_jac_blocks(P, X)
+    A = np.swapaxes(J, -1, -2) @ J
+    g = (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0]
+    D, pred = damped_solve(A, g, scale, dmin, dmax)
+    Pt = retract(D, P)
+    rt = poseinv_residual(Pt, X)
+    return Pt, np.array([(r ** 2).sum(), (rt ** 2).sum(), pred.sum(), 0.0])
+
+
+# ------------------------------------------------------------------ Reproj: r = pi(T p) - z
+def reproj_residual(poses, pts, pix, cidx):
+    y = O.act("SE3", poses[cidx], pts)
+    return -y[:, :2] / y[:, 2:] - pix
+
+
+def reproj_jac_rows(poses, pts, cidx):
+    """(m, 2, 6): d pi/dy @ [I, -y^]  (SE3_Act_Jacobian, op.py:225-227, applied to out = T p)."""
+    y = O.act("SE3", poses[cidx], pts)
+    m = y.shape[0]
+    dpi = np.zeros((m, 2, 3))
+    dpi[:, 0, 0] = -1 / y[:, 2]
+    dpi[:, 1, 1] = -1 / y[:, 2]
+    dpi[:, 0, 2] = y[:, 0] / y[:, 2] ** 2
+    dpi[:, 1, 2] = y[:, 1] / y[:, 2] ** 2
+    dy = np.concatenate([np.broadcast_to(np.eye(3), (m, 3, 3)), O.vec2skew(-y)], -1)
+    return dpi @ dy
+
+
+def reproj_accum(poses, pts, pix, seg):
+    C = poses.shape[0]
+    cidx = np.repeat(np.arange(C), np.diff(seg))
+    r = reproj_residual(poses, pts, pix, cidx)
+    J = reproj_jac_rows(poses, pts, cidx)
+    A = np.zeros((C, 6, 6))
+    g = np.zeros((C, 6))
+    np.add.at(A, cidx, np.swapaxes(J, -1, -2) @ J)
+    np.add.at(g, cidx, (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0])
+    return _triu_pack(A), g, np.array([(r ** 2).sum()])
+
+
+def solve6_retract(H21, g, P, scale, dmin, dmax):
+    D, pred = damped_solve(_triu_unpack(H21), g, scale, dmin, dmax)
+    return retract(D, P), D, np.array([pred.sum(), 0.0])
+
+
+def reproj_loss(poses, pts, pix, cidx):
+    return np.array([(reproj_residual(poses, pts, pix, cidx) ** 2).sum()])
+
+
+# ------------------------------------------------------------------ the dense reference algorithm
+def dense_lm_step(residual_fn, jac_fn, P, damping, dmin=1e-6, dmax=1e32, reject=16, last=None, update=None):
+    """One LevenbergMarquardt.step with a constant damping (optimizer.py:645-680) on parameters P (N,7).
+
+    residual_fn(P) -> R (M,);  jac_fn(P) -> dense J (M, 7N) in the reference's column layout.
+    Returns (P_new, loss, last, reject_count)."""
+    R = residual_fn(P)
+    J = jac_fn(P)
+    A = J.T @ J
+    d = np.arange(A.shape[0])
+    A[d, d] = np.clip(A[d, d], dmin, dmax)
+    loss = last = (R ** 2).sum() if last is None else last
+    rej = 0
+    while last <= loss:
+        A[d, d] += A[d, d] * damping
+        L = np.linalg.cholesky(A)
+        D = np.linalg.solve(L.T, np.linalg.solve(L, -(J.T @ R)))
+        Pn = retract(D.reshape(-1, 7)[:, :6], P)
+        loss = (residual_fn(Pn) ** 2).sum()
+        if last < loss and rej < reject:
+            loss, rej = last, rej + 1
+        else:
+            P = Pn
+            break
+    return P, loss, last, rej
+
+
+def dense_jac_from_blocks(blocks, row_param, n_params):
+    """Assemble the reference's dense (M*d, 7*N) Jacobian from per-residual (d,6) blocks."""
+    m, d, _ = blocks.shape
+    J = np.zeros((m * d, 7 * n_params))
+    for k in range(m):
+        J[k * d:(k + 1) * d, 7 * row_param[k]:7 * row_param[k] + 6] = blocks[k]
+    return J

@@ -1,0 +1,94 @@
+"""Record LM trajectories from the REFERENCE's own optimizer (pypose v0.9.5, fp64, CPU):
+
+    python oracle/make_golden_lm.py        # writes tests/golden/lm.npz
+
+* PoseInv: README.md:120-135 InvNet, N = 6 poses, 4 steps, Constant(1e-4) and default TrustRegion.
+* Reproj:  r = -(T_c p)[:2]/(T_c p)[2] - z with C = 4 cameras / 40 observations, 4 steps, Constant(1e-4).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+from torch import nn
+
+sys.path.insert(0, os.environ.get("PYPOSE_REFERENCE", "/root/reference"))
+sys.dont_write_bytecode = True
+import pypose as ref  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "lm.npz")
+
+
+class InvNet(nn.Module):
+    def __init__(self, pose):
+        super().__init__()
+        self.pose = ref.Parameter(pose)
+
+    def forward(self, input):
+        return (self.pose @ input).Log().tensor()
+
+
+class Reproj(nn.Module):
+    def __init__(self, poses):
+        super().__init__()
+        self.poses = ref.Parameter(poses)
+
+    def forward(self, points, pixels, cidx):
+        y = self.poses[cidx].Act(points)
+        return -y[..., :2] / y[..., 2:] - pixels
+
+
+def run(model, input, strategy, steps, pname):
+    opt = ref.optim.LM(model, strategy=strategy)
+    losses, poses, rejects = [], [], []
+    for _ in range(steps):
+        losses.append(float(opt.step(input)))
+        poses.append(getattr(model, pname).detach().clone().numpy())
+        rejects.append(opt.reject_count)
+    return np.array(losses), np.stack(poses), np.array(rejects)
+
+
+def main():
+    torch.manual_seed(7)
+    g = {}
+    P0 = ref.randn_SE3(6, sigma=0.3, dtype=torch.float64)
+    X = ref.randn_SE3(6, sigma=0.8, dtype=torch.float64)
+    g["poseinv/P0"], g["poseinv/X"] = P0.numpy().copy(), X.numpy().copy()
+    for name, strat in (("constant", lambda: ref.optim.strategy.Constant(damping=1e-4)),
+                        ("trustregion", lambda: ref.optim.strategy.TrustRegion()),
+                        ("adaptive", lambda: ref.optim.strategy.Adaptive(damping=1e-2))):
+        losses, poses, rej = run(InvNet(P0.clone()), X, strat(), 4, "pose")
+        g[f"poseinv/{name}/loss"], g[f"poseinv/{name}/poses"], g[f"poseinv/{name}/reject"] = losses, poses, rej
+
+    C, M = 4, 40
+    gt = ref.randn_SE3(C, sigma=0.2, dtype=torch.float64)
+    gt.tensor()[:, 2] += 0.0
+    cidx = torch.arange(M) % C
+    pts_cam = torch.rand(M, 3, dtype=torch.float64) * torch.tensor([4.0, 4.0, 4.0]) + torch.tensor([-2.0, -2.0, 2.0])
+    pts = gt[cidx].Inv().Act(pts_cam)                       # world points seen at pts_cam in the GT cameras
+    pix = -pts_cam[:, :2] / pts_cam[:, 2:] + 1e-3 * torch.randn(M, 2, dtype=torch.float64)
+    init = ref.se3(0.05 * torch.randn(C, 6, dtype=torch.float64)).Exp() * gt
+    g["reproj/poses0"], g["reproj/pts"], g["reproj/pix"], g["reproj/cidx"] = (init.numpy().copy(), pts.numpy().copy(),
+                                                                               pix.numpy().copy(), cidx.numpy().copy())
+    for name, strat in (("constant", lambda: ref.optim.strategy.Constant(damping=1e-4)),
+                        ("trustregion", lambda: ref.optim.strategy.TrustRegion())):
+        losses, poses, rej = run(Reproj(init.clone()), (pts, pix, cidx), strat(), 4, "poses")
+        g[f"reproj/{name}/loss"], g[f"reproj/{name}/poses"], g[f"reproj/{name}/reject"] = losses, poses, rej
+    # a badly initialised problem whose default TrustRegion run rejects steps (reject counts 4,0,0,1,0,0):
+    # exercises the cumulative damping / undo path of optimizer.py:662-680
+    torch.manual_seed(0)
+    gt = ref.randn_SE3(C, sigma=0.2, dtype=torch.float64)
+    pts_cam = torch.rand(M, 3, dtype=torch.float64) * 4 + torch.tensor([-2.0, -2.0, 2.0])
+    pts = gt[cidx].Inv().Act(pts_cam)
+    pix = -pts_cam[:, :2] / pts_cam[:, 2:]
+    init = ref.se3(0.8 * torch.randn(C, 6, dtype=torch.float64)).Exp() * gt
+    g["reproj_hard/poses0"], g["reproj_hard/pts"], g["reproj_hard/pix"], g["reproj_hard/cidx"] = (
+        init.numpy().copy(), pts.numpy().copy(), pix.numpy().copy(), cidx.numpy().copy())
+    losses, poses, rej = run(Reproj(init.clone()), (pts, pix, cidx), ref.optim.strategy.TrustRegion(), 6, "poses")
+    g["reproj_hard/trustregion/loss"], g["reproj_hard/trustregion/poses"], g["reproj_hard/trustregion/reject"] = losses, poses, rej
+    np.savez_compressed(OUT, **g)
+    print("wrote", OUT, {k: (v if v.ndim == 1 and v.size <= 4 else v.shape) for k, v in g.items() if "loss" in k or "reject" in k})
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,7 @@ import os
 
 import torch
 
-from ._optable import lie_symbols
+from ._optable import lie_symbols, lm_symbols
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200pose.so")
@@ -41,6 +41,8 @@ def _bind(symbol, n_in, n_out, extra=()):
 
 
 _LIE = {s: (ct, ins, outs) for s, ct, ins, outs, _ in lie_symbols()}
+_LM = {s: args for s, args, _ in lm_symbols()}
+_CT = {"double": ctypes.c_double, "int": ctypes.c_int}
 
 
 def fn(symbol):
@@ -49,6 +51,11 @@ def fn(symbol):
         if symbol in _LIE:
             _, ins, outs = _LIE[symbol]
             f = _bind(symbol, len(ins), len(outs))
+        elif symbol in _LM:
+            f = getattr(lib(), symbol)
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.c_void_p if "*" in t else _CT[t] for t, _, _ in _LM[symbol]] + \
+                [ctypes.c_longlong, ctypes.c_void_p]
         else:
             raise B200PoseError(f"unknown C-ABI symbol {symbol}")
         _fns[symbol] = f

@@ -1,0 +1,105 @@
+"""Extra legs of bench.py: LM step/s (the second half of BASELINE.json's metric).
+
+lm_poseinv : BASELINE.json configs[2] — README InvNet, 1e5 SE3 poses per GPU, fp32, Constant(1e-4), Cholesky.
+lm_reproj  : BASELINE.json configs[4] (single-pose form) — 1e4 poses, 1e6 reprojection residuals in total,
+             residual-sharded over the ranks (strong scaling), one packed NCCL all-reduce of [H | g] per
+             iteration + scalar all-reduces.
+A timed LM step is one `optimizer.step()` through the public API (host control flow and its syncs
+included) from a freshly perturbed state, so every timed step linearises, solves, retracts and
+evaluates the trial loss (a "productive" step); the re-perturbation itself is not timed.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+
+def _time_steps(step_fn, reset_fn, steps, warmup):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        reset_fn(); step_fn()
+    tot = 0.0
+    for _ in range(steps):
+        reset_fn()
+        e0.record()
+        step_fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+def run(args, rank, world, dev):
+    import pypose_b200 as pp
+    import torch.distributed as dist
+    group = True if world > 1 else None
+    out = {}
+    steps = max(10, min(100, args.steps // 200))
+
+    # ---- PoseInv (poses sharded: weak scaling, 1e5 poses per GPU)
+    class InvNet(nn.Module):
+        def __init__(self, pose):
+            super().__init__()
+            self.pose = pp.Parameter(pose)
+
+        def forward(self, input):
+            return (self.pose @ input).Log().tensor()
+
+    torch.manual_seed(100 + rank)
+    n = 100_000
+    X = pp.randn_SE3(n, sigma=0.9, device=dev)
+    P0 = pp.randn_SE3(n, sigma=0.9, device=dev)
+    net = InvNet(P0.clone())
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.Constant(damping=1e-4), group=group)
+
+    def reset():
+        with torch.no_grad():
+            net.pose.copy_(P0)
+        if hasattr(opt, 'loss'):
+            del opt.loss
+    ms = _time_steps(lambda: opt.step(X), reset, steps, 3)
+    ms = _max(ms, world, dev)
+    assert opt._problem is not None
+    out["lm_poseinv"] = {"steps_per_s": round(1e3 / ms, 1), "ms_per_step": round(ms, 4), "poses_per_gpu": n,
+                         "residuals_total": 6 * n * world, "scaling": "weak", "dtype": "f32",
+                         "hbm_gbs": round(n * 140 / (ms * 1e-3) / 1e9, 1),
+                         "config": "README InvNet, Constant(1e-4), Cholesky (BASELINE.json configs[2])"}
+
+    # ---- reprojection pose graph (residual-sharded: strong scaling, 1e6 residuals in total)
+    C, M = 10_000, 1_000_000
+    rng = np.random.default_rng(5)
+    from_np = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    gt = pp.randn_SE3(C, sigma=0.3, device=dev, generator=None) if False else None
+    g = torch.Generator(device="cpu").manual_seed(5)
+    gt = pp.se3(0.3 * torch.randn(C, 6, generator=g)).to(dev).Exp()
+    cidx_all = torch.from_numpy(np.sort(rng.integers(0, C, M))).to(dev)
+    pc = torch.rand(M, 3, generator=g).to(dev) * 4 + torch.tensor([-2.0, -2.0, 2.0], device=dev)
+    pts_all = gt[cidx_all].Inv().Act(pc)
+    pix_all = -pc[:, :2] / pc[:, 2:]
+    init = pp.se3(0.05 * torch.randn(C, 6, generator=g)).to(dev).Exp() * gt
+    lo, hi = rank * M // world, (rank + 1) * M // world
+    inp = (pts_all[lo:hi].contiguous(), pix_all[lo:hi].contiguous(), cidx_all[lo:hi].contiguous())
+    net2 = pp.module.PoseReproj(init.clone())
+    opt2 = pp.optim.LM(net2, strategy=pp.optim.strategy.TrustRegion(), group=group)
+
+    def reset2():
+        with torch.no_grad():
+            net2.poses.copy_(init)
+        if hasattr(opt2, 'loss'):
+            del opt2.loss
+        opt2.param_groups[0]['damping'] = 1e-6
+    ms2 = _time_steps(lambda: opt2.step(inp), reset2, steps, 3)
+    ms2 = _max(ms2, world, dev)
+    out["lm_reproj"] = {"steps_per_s": round(1e3 / ms2, 1), "ms_per_step": round(ms2, 4), "poses": C,
+                        "residuals_total": M, "residuals_per_gpu": hi - lo, "scaling": "strong", "dtype": "f32",
+                        "config": "1e4 SE3 poses, 1e6 reprojection residuals, block-diagonal JtJ, TrustRegion "
+                                  "(BASELINE.json configs[4], single-pose form)"}
+    return out
+
+
+def _max(ms, world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms

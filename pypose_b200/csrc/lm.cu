@@ -1,0 +1,321 @@
+// lm.cu — fused kernels of the Levenberg-Marquardt inner loop (C-ABI: include/b200pose.h, section LM).
+//
+// Replaces, for the residual families whose block structure is known (lm_math.cuh), the reference's
+// modjac -> dense J -> J^T J -> clamp/damp -> cholesky_ex/cholesky_solve -> p.add_ -> loss sequence
+// (pypose/optim/optimizer.py:645-680, optim/functional.py:130-153, optim/solver.py:213-216).
+//
+// Scalars that the host control flow reads (loss, trial loss, predicted reduction) are reduced on the
+// device in fp64: per-CTA partials, then the last CTA to finish folds them in a fixed order, so results
+// are deterministic for a given grid.  Work is enqueued on the caller's stream; nothing synchronises.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lm_math.cuh"
+
+namespace b200pose {
+
+#define B200_EXPORT extern "C" __attribute__((visibility("default")))
+constexpr int kLmThreads = 128;
+constexpr int kMaxSums = 4;
+
+inline int lm_sms() {
+  static thread_local int dev_cached = -1, sms = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+  return sms;
+}
+
+// Block-reduce NS doubles per thread, store the CTA partial, and let the last CTA produce the totals.
+// workspace layout (doubles): [0 .. NS) totals | [7] ticket (as unsigned) | [8 ..) partials[grid][NS]
+template <int NS>
+__device__ __forceinline__ void reduce_sums(double (&v)[NS], double* ws) {
+  __shared__ double sh[kLmThreads / 32][NS];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int k = 0; k < NS; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sh[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* part = ws + 8 + (size_t)blockIdx.x * NS;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double t = 0;
+      for (int w = 0; w < kLmThreads / 32; ++w) t += sh[w][k];
+      part[k] = t;
+    }
+    __threadfence();
+    unsigned* ticket = reinterpret_cast<unsigned*>(ws + 7);
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    // fixed-order fold by one warp: lane-strided partial sums, then a shuffle tree
+    if (threadIdx.x < 32) {
+      double t[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) t[k] = 0;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += 32)
+#pragma unroll
+        for (int k = 0; k < NS; ++k) t[k] += ws[8 + (size_t)b * NS + k];
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) ws[k] = t[k];
+        *reinterpret_cast<unsigned*>(ws + 7) = 0u;   // re-arm the ticket for the next launch
+      }
+    }
+  }
+}
+
+template <typename T> __device__ __forceinline__ Elem<T> load_se3(const T* p) { return load_elem<SE3g, T>(p); }
+
+// ------------------------------------------------------------------------------------------------
+// PoseInv (BASELINE.json configs[2], README.md:120-135 InvNet): residual Log(P_i X_i), one 6x6 system per pose.
+// ------------------------------------------------------------------------------------------------
+// loss = sum_i |Log(P_i X_i)|^2     (RobustModel.loss with the trivial kernel, optimizer.py:118-125)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_poseinv_loss_kernel(const T* __restrict__ P, const T* __restrict__ X,
+                                                                      double* ws, long long n) {
+  double acc[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T p[7], x[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { p[k] = P[i * 7 + k]; x[k] = X[i * 7 + k]; }
+    acc[0] += (double)tang6_sqnorm(poseinv_residual(load_se3(p), load_se3(x)));
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+// One complete LM trial per pose, entirely in registers:
+//   linearise (r, J = Jl^-1(r)) -> A = J^T J, g = J^T r -> clamp/damp -> Cholesky -> D -> P' = Exp(D) P -> |r'|^2
+// sums: [0] sum |r|^2 (current loss), [1] sum |r'|^2 (trial loss), [2] sum (J D)^T (2 R + J D), [3] #failed pivots
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_poseinv_trial_kernel(const T* __restrict__ P, const T* __restrict__ X,
+                                                                       T* __restrict__ Pt, double* ws, T scale, T dmin,
+                                                                       T dmax, long long n) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T p[7], x[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { p[k] = P[i * 7 + k]; x[k] = X[i * 7 + k]; }
+    const Elem<T> Pe = load_se3(p), Xe = load_se3(x);
+    Tang<T> r;
+    Sys6<T> s;
+    poseinv_linearize(Pe, Xe, r, s);
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    const Elem<T> Pn = se3_retract(D, Pe);
+    T o[7];
+    store_elem<SE3g, T>(o, Pn);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Pt[i * 7 + k] = o[k];
+    acc[0] += (double)tang6_sqnorm(r);
+    acc[1] += (double)tang6_sqnorm(poseinv_residual(Pn, Xe));
+    acc[2] += (double)pred;
+    acc[3] += ok ? 0.0 : 1.0;
+  }
+  reduce_sums<4>(acc, ws);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pose-graph LM with reprojection residuals (BASELINE.json configs[4], single-pose form, SURVEY.md §8d cfg 5-min):
+//   r_k = pi(T_{c_k} p_k) - z_k, observations sorted by camera, seg[c] .. seg[c+1] = camera c's rows.
+// ------------------------------------------------------------------------------------------------
+// One warp per camera: lanes stride over the camera's observations, accumulate the 6x6 system in registers,
+// shuffle-reduce, lane 0 writes H[c] (21 upper-triangular entries, row-major) and g[c] (6): no atomics.
+// sums: [0] sum |r|^2.   With residual sharding each rank sees only its rows; H/g/loss are all-reduced by the host.
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
+                                                                      const T* __restrict__ pix, const int* __restrict__ seg,
+                                                                      T* __restrict__ H, T* __restrict__ g, double* ws,
+                                                                      int ncam) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
+  double acc[1] = {0.0};
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+    T pr[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
+    const Elem<T> Tc = load_se3(pr);
+    Sys6<T> s;
+    sys6_zero(s);
+    T loss = T(0);
+    const int b = seg[c], e = seg[c + 1];
+    for (int k = b + lane; k < e; k += 32) {
+      const V3<T> p = mk(pts[(long long)k * 3], pts[(long long)k * 3 + 1], pts[(long long)k * 3 + 2]);
+      T rx, ry;
+      V3<T> y;
+      reproj_residual(Tc, p, pix[(long long)k * 2], pix[(long long)k * 2 + 1], rx, ry, y);
+      T j0[6], j1[6];
+      reproj_rows(y, j0, j1);
+      sys6_add_row(s, j0, rx);
+      sys6_add_row(s, j1, ry);
+      loss += rx * rx + ry * ry;
+    }
+    // warp reduction of 21 + 6 + 1 values
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
+#pragma unroll
+        for (int bb = a; bb < 6; ++bb) s.A[a][bb] += __shfl_xor_sync(0xffffffffu, s.A[a][bb], o);
+      }
+      loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    }
+    if (lane == 0) {
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        g[(long long)c * 6 + a] = s.g[a];
+#pragma unroll
+        for (int bb = a; bb < 6; ++bb) H[(long long)c * 21 + q++] = s.A[a][bb];
+      }
+      acc[0] += (double)loss;
+    }
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+// Generic damped batched 6x6 solve + retraction on packed blocks (also the second half of the reprojection step):
+//   D_c = (clamp(diag H_c) * scale + offdiag H_c)^-1 (-g_c);  P'_c = Exp(D_c) P_c
+// sums: [0] sum predicted = sum D^T H D + 2 D^T g, [1] #failed pivots
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_solve6_retract_kernel(const T* __restrict__ H, const T* __restrict__ g,
+                                                                        const T* __restrict__ P, T* __restrict__ Pt,
+                                                                        T* __restrict__ Dout, double* ws, T scale, T dmin,
+                                                                        T dmax, long long n) {
+  double acc[2] = {0.0, 0.0};
+  for (long long c = (long long)blockIdx.x * kLmThreads + threadIdx.x; c < n; c += (long long)gridDim.x * kLmThreads) {
+    Sys6<T> s;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      s.g[a] = g[c * 6 + a];
+#pragma unroll
+      for (int b = a; b < 6; ++b) s.A[a][b] = H[c * 21 + q++];
+    }
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    T pr[7], o[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = P[c * 7 + k];
+    store_elem<SE3g, T>(o, se3_retract(D, load_se3(pr)));
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Pt[c * 7 + k] = o[k];
+    if (Dout)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) Dout[c * 6 + k] = D[k];
+    acc[0] += (double)pred;
+    acc[1] += ok ? 0.0 : 1.0;
+  }
+  reduce_sums<2>(acc, ws);
+}
+
+// trial loss over a shard of observations (flat, one thread per observation, pose gathered through L2)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_reproj_loss_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
+                                                                     const T* __restrict__ pix, const int* __restrict__ cidx,
+                                                                     double* ws, long long m) {
+  double acc[1] = {0.0};
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const int c = cidx[k];
+    T pr[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) pr[q] = __ldg(poses + (long long)c * 7 + q);
+    const V3<T> p = mk(pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]);
+    T rx, ry;
+    V3<T> y;
+    reproj_residual(load_se3(pr), p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
+    acc[0] += (double)(rx * rx + ry * ry);
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+// residual vector r (m, 2) for API-level forward() parity
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_reproj_residual_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
+                                                                         const T* __restrict__ pix, const int* __restrict__ cidx,
+                                                                         T* __restrict__ r, long long m) {
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const int c = cidx[k];
+    T pr[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) pr[q] = __ldg(poses + (long long)c * 7 + q);
+    const V3<T> p = mk(pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]);
+    T rx, ry;
+    V3<T> y;
+    reproj_residual(load_se3(pr), p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
+    r[k * 2] = rx;
+    r[k * 2 + 1] = ry;
+  }
+}
+
+inline unsigned lm_grid(long long work_items, int per_block) {
+  long long need = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)lm_sms() * 8;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+}  // namespace b200pose
+
+using namespace b200pose;
+
+// workspace: at least b200_lm_workspace_doubles() doubles, zero-initialised ONCE by the caller (the kernels
+// re-arm it themselves).  Totals are in ws[0..3] after the kernel completes.
+B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kMaxSums * 8 * 1024; }
+
+#define LM_ABI(SFX, CT)                                                                                               \
+  B200_EXPORT int b200_lm_poseinv_loss_##SFX(const CT* P, const CT* X, double* ws, long long n, void* stream) {        \
+    if (n <= 0) return 0;                                                                                             \
+    lm_poseinv_loss_kernel<CT><<<lm_grid(n, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(P, X, ws, n);         \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_poseinv_trial_##SFX(const CT* P, const CT* X, CT* P_trial, double* ws, double scale,        \
+                                              double dmin, double dmax, long long n, void* stream) {                  \
+    if (n <= 0) return 0;                                                                                             \
+    lm_poseinv_trial_kernel<CT><<<lm_grid(n, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                     \
+        P, X, P_trial, ws, (CT)scale, (CT)dmin, (CT)dmax, n);                                                         \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_reproj_accum_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* seg, CT* H,    \
+                                             CT* g, double* ws, long long ncam, void* stream) {                       \
+    if (ncam <= 0) return 0;                                                                                          \
+    lm_reproj_accum_kernel<CT><<<lm_grid(ncam, kLmThreads / 32), kLmThreads, 0, (cudaStream_t)stream>>>(              \
+        poses, pts, pix, seg, H, g, ws, (int)ncam);                                                                   \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_solve6_retract_##SFX(const CT* H, const CT* g, const CT* P, CT* P_trial, CT* D, double* ws, \
+                                               double scale, double dmin, double dmax, long long n, void* stream) {   \
+    if (n <= 0) return 0;                                                                                             \
+    lm_solve6_retract_kernel<CT><<<lm_grid(n, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                    \
+        H, g, P, P_trial, D, ws, (CT)scale, (CT)dmin, (CT)dmax, n);                                                   \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_reproj_loss_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* cidx,           \
+                                            double* ws, long long m, void* stream) {                                  \
+    if (m <= 0) return 0;                                                                                             \
+    lm_reproj_loss_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(poses, pts, pix, cidx, \
+                                                                                               ws, m);                \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_reproj_residual_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* cidx,       \
+                                                CT* r, long long m, void* stream) {                                   \
+    if (m <= 0) return 0;                                                                                             \
+    lm_reproj_residual_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(poses, pts, pix,   \
+                                                                                                   cidx, r, m);       \
+    return (int)cudaGetLastError();                                                                                   \
+  }
+
+LM_ABI(f32, float)
+LM_ABI(f64, double)

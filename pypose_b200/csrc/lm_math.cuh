@@ -1,0 +1,195 @@
+// lm_math.cuh — per-block math of the Levenberg-Marquardt inner loop (host+device, see lie_math.cuh).
+//
+// Reference semantics (pypose/optim/optimizer.py:645-680, dense branch), specialised to the block
+// structure the reference's dense Jacobian actually has (SURVEY.md §3.3, §8a "analytic Jacobians"):
+//   * PoseInv  r = Log(P X):        dr/dP = Jl^-1(r)                      (6x6 per pose)
+//   * Reproj   r = pi(T p) - z:     dr/dT = dpi/dy [I, -y^], y = T p      (2x6 per observation)
+// with left perturbations and K = 6 tangent columns (the 7th dense column is identically zero and only
+// produces D[6] = 0 in the reference).
+#pragma once
+#include "lie_math.cuh"
+
+namespace b200pose {
+
+template <typename T> struct M3 { T m[3][3]; };
+
+template <typename T> LM_HD M3<T> m3_skew(const V3<T>& v) {
+  M3<T> a;
+  a.m[0][0] = T(0); a.m[0][1] = -v.z; a.m[0][2] = v.y;
+  a.m[1][0] = v.z;  a.m[1][1] = T(0); a.m[1][2] = -v.x;
+  a.m[2][0] = -v.y; a.m[2][1] = v.x;  a.m[2][2] = T(0);
+  return a;
+}
+template <typename T> LM_HD M3<T> m3_mul(const M3<T>& a, const M3<T>& b) {
+  M3<T> c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+  return c;
+}
+template <typename T> LM_HD M3<T> m3_t(const M3<T>& a) {
+  M3<T> c;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c.m[i][j] = a.m[j][i];
+  return c;
+}
+
+// Ji = Jl^-1(phi) and B = -Ji Q Ji of se3_Jl_inv (operation.py:68-75) as explicit 3x3 blocks.
+template <typename T> LM_HD void se3_jlinv_blocks(const Tang<T>& x, M3<T>& Ji, M3<T>& B) {
+  const RotCoef<T> r = rot_coef(x.phi);
+  const T c = jlinv_coef(x.phi);
+  T a2, a3;
+  q_coef(r, a2, a3);
+  const T a1 = r.c2;
+  const M3<T> P = m3_skew(x.phi), Tm = m3_skew(x.tau);
+  const M3<T> PP = m3_mul(P, P);
+  const M3<T> PT = m3_mul(P, Tm);       // TP = PT^T
+  const M3<T> PTP = m3_mul(PT, P);
+  const M3<T> PPT = m3_mul(P, PT);      // TPP = -PPT^T
+  const M3<T> PTPP = m3_mul(PTP, P);    // PPTP = PTPP^T
+  M3<T> Q;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Ji.m[i][j] = (i == j ? T(1) : T(0)) - T(0.5) * P.m[i][j] + c * PP.m[i][j];
+      Q.m[i][j] = T(0.5) * Tm.m[i][j] + a1 * (PT.m[i][j] + PT.m[j][i] + PTP.m[i][j]) +
+                  a2 * (PPT.m[i][j] - PPT.m[j][i] - T(3) * PTP.m[i][j]) + a3 * (PTPP.m[i][j] + PTPP.m[j][i]);
+    }
+  const M3<T> JQJ = m3_mul(m3_mul(Ji, Q), Ji);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) B.m[i][j] = -JQJ.m[i][j];
+}
+
+// One 6x6 normal-equation block, symmetric, full storage in registers.
+template <typename T> struct Sys6 {
+  T A[6][6];   // J^T J (only j >= i is maintained)
+  T g[6];      // J^T r
+};
+template <typename T> LM_HD void sys6_zero(Sys6<T>& s) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    s.g[i] = T(0);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s.A[i][j] = T(0);
+  }
+}
+// rank-1 update with one Jacobian row j (1x6) and residual component r
+template <typename T> LM_HD void sys6_add_row(Sys6<T>& s, const T (&j)[6], T r) {
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    s.g[a] += j[a] * r;
+#pragma unroll
+    for (int b = a; b < 6; ++b) s.A[a][b] += j[a] * j[b];
+  }
+}
+
+// LM damping + Cholesky solve of one block (optimizer.py:657, 666, 668; solver.py:213-216):
+//   diag <- clamp(diag, dmin, dmax) * scale      (scale = prod (1 + damping_k) over the trials so far)
+//   D = A^-1 (-g);   predicted = (J D)^T (2 R + J D) = D^T A0 D + 2 D^T g   with A0 the undamped J^T J
+// Returns false if the factorisation hit a non-positive pivot.
+template <typename T> LM_HD bool sys6_damped_solve(const Sys6<T>& s, T scale, T dmin, T dmax, T (&D)[6], T& predicted) {
+  T L[6][6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    T djj = s.A[j][j];
+    djj = djj < dmin ? dmin : (djj > dmax ? dmax : djj);
+    T sum = djj * scale;
+#pragma unroll
+    for (int k = 0; k < j; ++k) sum -= L[j][k] * L[j][k];
+    ok = ok && (sum > T(0));
+    const T inv = m_rsqrt(sum);
+    L[j][j] = sum * inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      T v = s.A[j][i];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
+  }
+  T y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {       // L y = -g
+    T v = -s.g[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+    y[i] = v * m_rcp(L[i][i]);
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {      // L^T D = y
+    T v = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= L[k][i] * D[k];
+    D[i] = v * m_rcp(L[i][i]);
+  }
+  T q = T(0), lin = T(0);
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    lin += D[a] * s.g[a];
+    T row = T(0);
+#pragma unroll
+    for (int b = 0; b < 6; ++b) row += (b >= a ? s.A[a][b] : s.A[b][a]) * D[b];
+    q += D[a] * row;
+  }
+  predicted = q + T(2) * lin;
+  return ok;
+}
+
+// ---------------------------------------------------------------- PoseInv: r = Log(P X)
+template <typename T> LM_HD Tang<T> poseinv_residual(const Elem<T>& P, const Elem<T>& X) {
+  return g_log<SE3g, T>(g_mul<SE3g, T>(P, X));
+}
+template <typename T> LM_HD void poseinv_linearize(const Elem<T>& P, const Elem<T>& X, Tang<T>& r, Sys6<T>& s) {
+  r = poseinv_residual(P, X);
+  M3<T> Ji, B;
+  se3_jlinv_blocks(r, Ji, B);
+  // J = [[Ji, B], [0, Ji]]; rows 0-2: [Ji_i, B_i], rows 3-5: [0, Ji_i]
+  sys6_zero(s);
+  const T rr[6] = {r.tau.x, r.tau.y, r.tau.z, r.phi.x, r.phi.y, r.phi.z};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const T top[6] = {Ji.m[i][0], Ji.m[i][1], Ji.m[i][2], B.m[i][0], B.m[i][1], B.m[i][2]};
+    const T bot[6] = {T(0), T(0), T(0), Ji.m[i][0], Ji.m[i][1], Ji.m[i][2]};
+    sys6_add_row(s, top, rr[i]);
+    sys6_add_row(s, bot, rr[i + 3]);
+  }
+}
+template <typename T> LM_HD T tang6_sqnorm(const Tang<T>& r) { return dot(r.tau, r.tau) + dot(r.phi, r.phi); }
+
+// retraction of the optimizers: P <- Exp(D) P   (lietensor.py:442-444)
+template <typename T> LM_HD Elem<T> se3_retract(const T (&D)[6], const Elem<T>& P) {
+  Tang<T> d; d.tau = mk(D[0], D[1], D[2]); d.phi = mk(D[3], D[4], D[5]); d.sigma = T(0);
+  return g_mul<SE3g, T>(g_exp<SE3g, T>(d), P);
+}
+
+// ---------------------------------------------------------------- Reprojection: r = pi(T p) - z, pi(y) = -y[:2]/y[2]
+// (README.md:170-178 `project`; the Jacobian of T p w.r.t. T is [I, -y^], operation.py:225-227)
+template <typename T> LM_HD void reproj_residual(const Elem<T>& Tc, const V3<T>& p, T zx, T zy, T& rx, T& ry, V3<T>& y) {
+  y = g_act<SE3g, T>(Tc, p);
+  const T iz = m_rcp(y.z);
+  rx = -y.x * iz - zx;
+  ry = -y.y * iz - zy;
+}
+template <typename T> LM_HD void reproj_rows(const V3<T>& y, T (&j0)[6], T (&j1)[6]) {
+  const T iz = m_rcp(y.z), iz2 = iz * iz;
+  // dpi/dy = [[-1/z, 0, x/z^2], [0, -1/z, y/z^2]];  d y / d xi = [I, -y^]
+  const T a0 = -iz, c0 = y.x * iz2, c1 = y.y * iz2;
+  // -y^ = [[0, z, -y], [-z, 0, x], [y, -x, 0]]
+  j0[0] = a0; j0[1] = T(0); j0[2] = c0;
+  j0[3] = c0 * y.y;              // a0*0 + 0*(-z) + c0*y
+  j0[4] = a0 * y.z - c0 * y.x;   // a0*z + c0*(-x)
+  j0[5] = -a0 * y.y;             // a0*(-y)
+  j1[0] = T(0); j1[1] = a0; j1[2] = c1;
+  j1[3] = -a0 * y.z + c1 * y.y;  // a0*(-z) + c1*y
+  j1[4] = -c1 * y.x;             // c1*(-x)
+  j1[5] = a0 * y.x;              // a0*x
+}
+
+}  // namespace b200pose

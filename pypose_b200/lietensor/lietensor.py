@@ -36,6 +36,11 @@ def _raw(x):
     return x.tensor() if isinstance(x, LieTensor) else x
 
 
+# When a list is installed here, group multiplies and Logs append (op, arg0, arg1, result): the structured
+# LM route uses it to recognise residual models from unchanged user modules (optim/structured.py).
+_RECORD = None
+
+
 class LieType:
     """Spec of one of the eight Lie types (lt.py:37-193).
 
@@ -69,21 +74,30 @@ class LieType:
 
     # -- unary ---------------------------------------------------------------------------------
     def Exp(self, x):
+        if _RECORD is not None:
+            _RECORD.append(("exp", x, None, None))
         if not self.algebra:
             raise AttributeError("Lie Group has no Exp attribute")
         return self._wrap(ops.unary(f"{self.alg_name}_exp_fwd", _raw(x), self.D), self.dual)
 
     def Log(self, X):
         self._need_group("Log")
-        return self._wrap(ops.unary(f"{self.group}_log_fwd", _raw(X), self.K), self.dual)
+        out = self._wrap(ops.unary(f"{self.group}_log_fwd", _raw(X), self.K), self.dual)
+        if _RECORD is not None:
+            _RECORD.append(("log", X, None, out))
+        return out
 
     def Inv(self, X):
+        if _RECORD is not None:
+            _RECORD.append(("inv", X, None, None))
         if self.algebra:   # lt.py:77-80: inverse on the algebra is negation
             return self._wrap(-_raw(X), self)
         return self._wrap(ops.unary(f"{self.group}_inv_fwd", _raw(X), self.D), self)
 
     # -- binary --------------------------------------------------------------------------------
     def Act(self, X, p):
+        if _RECORD is not None:
+            _RECORD.append(("act", X, p, None))
         self._need_group("Act")
         assert isinstance(p, Tensor), "Act expects a Tensor of points"
         assert p.shape[-1] in (3, 4), "Invalid Tensor Dimension"
@@ -95,7 +109,10 @@ class LieType:
         if self.algebra:   # (scalar or tensor) * algebra element stays in the algebra
             return self._wrap(torch.mul(Xr, _raw(Y) if isinstance(Y, Tensor) else Y), self)
         if isinstance(Y, LieTensor) and not Y.ltype.on_manifold:   # group composition
-            return self._wrap(ops.binary(f"{self.group}_mul_fwd", Xr, Y.tensor(), self.D), self)
+            out = self._wrap(ops.binary(f"{self.group}_mul_fwd", Xr, Y.tensor(), self.D), self)
+            if _RECORD is not None:
+                _RECORD.append(("mul", X, Y, out))
+            return out
         if isinstance(Y, Tensor):  # transform on points (lt.py:226-227)
             return self.Act(X, Y)
         raise NotImplementedError('Invalid __mul__ operation')
@@ -106,6 +123,8 @@ class LieType:
         return a.Exp() * X
 
     def _tangent_binary(self, what, op, X, a):
+        if _RECORD is not None:
+            _RECORD.append((op, X, a, None))
         self._need_group(what)
         return self._wrap(ops.binary(f"{self.group}_{op}_fwd", _raw(X), _raw(a), self.K), self.dual)
 

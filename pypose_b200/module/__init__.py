@@ -1,0 +1,1 @@
+from .reproj import PoseReproj

@@ -1,0 +1,117 @@
+"""torch custom ops `b200pose::lm_*` over the fused LM kernels (csrc/lm.cu).
+
+Like the Lie ops, only the CUDA dispatch key has a kernel.  All host-visible scalars come back as
+a small fp64 tensor on the device (`sums`), so the caller decides when to synchronise.
+"""
+import ctypes
+
+import torch
+from torch import Tensor
+
+from .. import _C
+
+NS = "b200pose"
+_ws = {}
+
+
+def _workspace(device):
+    """Per-device fp64 reduction workspace, zeroed once (the kernels re-arm it)."""
+    key = (device.type, device.index)
+    w = _ws.get(key)
+    if w is None:
+        n = _C.lib().b200_lm_workspace_doubles
+        n.restype = ctypes.c_longlong
+        w = torch.zeros(int(n()), dtype=torch.float64, device=device)
+        _ws[key] = w
+    return w
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _launch(base, ref: Tensor, args, n):
+    if not ref.is_cuda:
+        raise _C.B200PoseError(f"{base}: expected CUDA tensors (no CPU path), got {ref.device}")
+    sym = f"{base}_{_C.suffix(ref.dtype)}"
+    with torch.cuda.device(ref.device):
+        _C.check(_C.fn(sym)(*args, n, _C.stream_ptr(ref.device)), sym)
+
+
+def _same(*ts):
+    dt, dev = ts[0].dtype, ts[0].device
+    for t in ts:
+        if t.dtype != dt or t.device != dev:
+            raise TypeError("b200pose LM ops need one dtype/device for all floating inputs")
+    return [t.contiguous() for t in ts]
+
+
+torch.library.define(f"{NS}::lm_poseinv_loss", "(Tensor P, Tensor X) -> Tensor")
+torch.library.define(f"{NS}::lm_poseinv_trial",
+                     "(Tensor P, Tensor X, float scale, float dmin, float dmax) -> (Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_reproj_accum", "(Tensor poses, Tensor pts, Tensor pix, Tensor seg) -> (Tensor, Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_solve6_retract",
+                     "(Tensor H, Tensor g, Tensor P, float scale, float dmin, float dmax) -> (Tensor, Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_reproj_loss", "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx) -> Tensor")
+torch.library.define(f"{NS}::lm_reproj_residual", "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx) -> Tensor")
+
+
+@torch.library.impl(f"{NS}::lm_poseinv_loss", "CUDA")
+def _poseinv_loss(P, X):
+    P, X = _same(P, X)
+    ws = _workspace(P.device)
+    _launch("b200_lm_poseinv_loss", P, [_p(P), _p(X), _p(ws)], P.shape[0])
+    return ws[:1].clone()
+
+
+@torch.library.impl(f"{NS}::lm_poseinv_trial", "CUDA")
+def _poseinv_trial(P, X, scale, dmin, dmax):
+    P, X = _same(P, X)
+    ws = _workspace(P.device)
+    Pt = torch.empty_like(P)
+    _launch("b200_lm_poseinv_trial", P, [_p(P), _p(X), _p(Pt), _p(ws), scale, dmin, dmax], P.shape[0])
+    return Pt, ws[:4].clone()
+
+
+@torch.library.impl(f"{NS}::lm_reproj_accum", "CUDA")
+def _reproj_accum(poses, pts, pix, seg):
+    poses, pts, pix = _same(poses, pts, pix)
+    assert seg.dtype == torch.int32 and seg.numel() == poses.shape[0] + 1
+    ws = _workspace(poses.device)
+    C = poses.shape[0]
+    H = torch.empty(C, 21, dtype=poses.dtype, device=poses.device)
+    g = torch.empty(C, 6, dtype=poses.dtype, device=poses.device)
+    _launch("b200_lm_reproj_accum", poses, [_p(poses), _p(pts), _p(pix), _p(seg), _p(H), _p(g), _p(ws)], C)
+    return H, g, ws[:1].clone()
+
+
+@torch.library.impl(f"{NS}::lm_solve6_retract", "CUDA")
+def _solve6_retract(H, g, P, scale, dmin, dmax):
+    H, g, P = _same(H, g, P)
+    ws = _workspace(P.device)
+    Pt, D = torch.empty_like(P), torch.empty(P.shape[0], 6, dtype=P.dtype, device=P.device)
+    _launch("b200_lm_solve6_retract", P, [_p(H), _p(g), _p(P), _p(Pt), _p(D), _p(ws), scale, dmin, dmax], P.shape[0])
+    return Pt, D, ws[:2].clone()
+
+
+@torch.library.impl(f"{NS}::lm_reproj_loss", "CUDA")
+def _reproj_loss(poses, pts, pix, cidx):
+    poses, pts, pix = _same(poses, pts, pix)
+    assert cidx.dtype == torch.int32
+    ws = _workspace(poses.device)
+    _launch("b200_lm_reproj_loss", poses, [_p(poses), _p(pts), _p(pix), _p(cidx), _p(ws)], pts.shape[0])
+    return ws[:1].clone()
+
+
+@torch.library.impl(f"{NS}::lm_reproj_residual", "CUDA")
+def _reproj_residual(poses, pts, pix, cidx):
+    poses, pts, pix = _same(poses, pts, pix)
+    assert cidx.dtype == torch.int32
+    r = torch.empty(pts.shape[0], 2, dtype=poses.dtype, device=poses.device)
+    _launch("b200_lm_reproj_residual", poses, [_p(poses), _p(pts), _p(pix), _p(cidx), _p(r)], pts.shape[0])
+    return r
+
+
+LM_OPS = ["lm_poseinv_loss", "lm_poseinv_trial", "lm_reproj_accum", "lm_solve6_retract", "lm_reproj_loss",
+          "lm_reproj_residual"]
+ops = torch.ops.b200pose

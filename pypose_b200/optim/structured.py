@@ -1,0 +1,143 @@
+"""Structured LM problems: residual families whose Jacobian blocks are known in closed form.
+
+The reference builds an (R x 7N) dense Jacobian by vmapped autograd even when it is exactly
+block-diagonal.  For the families below the same normal equations are formed
+block-wise inside fused kernels (csrc/lm.cu, lm_math.cuh):
+
+  PoseInv  — README.md:120-129 InvNet:  forward(input) = (pose @ input).Log().tensor()
+  Reproj   — README.md:170-178 project / SURVEY.md §8d cfg 5-min:  -(T_c p)[:2]/(T_c p)[2] - z
+
+PoseInv is *recognised* from an unchanged user module by recording the LieTensor ops its forward
+executes (one group multiply followed by one Log).  Reproj is recognised by model type
+(pypose_b200.module.PoseReproj).
+
+Multi-GPU (`group`): PoseInv shards poses (each rank owns its rows; only the scalar sums are
+all-reduced).  Reproj shards residuals (each rank accumulates H/g for its rows; H, g and the
+scalars are all-reduced; the 6x6 solves run redundantly on every rank).
+"""
+import torch
+
+from ..lietensor import lietensor as _lt
+from ..lietensor.lietensor import LieTensor, Parameter, SE3_type
+from . import _fused  # noqa: F401  (registers the ops)
+
+ops = torch.ops.b200pose
+
+
+def _allreduce(t, group):
+    if group is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(t, group=group if group is not True else None)
+    return t
+
+
+class _Problem:
+    def _scalar(self, x):
+        return x.to(self.dtype)
+
+
+class PoseInvProblem(_Problem):
+    def __init__(self, model, param, X, key, group):
+        self.model, self.param, self.X, self.key, self.group = model, param, X, key, group
+        self.dtype = param.dtype
+        self._trial = None
+
+    def matches(self, model, input):
+        return model is self.model and _input_key(input) == self.key
+
+    def _rows(self):
+        return self.param.tensor().reshape(-1, 7), self.X.tensor().reshape(-1, 7)
+
+    def loss(self):
+        P, X = self._rows()
+        return self._scalar(_allreduce(ops.lm_poseinv_loss(P, X), self.group)[0])
+
+    def linearize(self):
+        return None         # everything lives in registers inside the trial kernel
+
+    def trial(self, lin, scale, dmin, dmax):
+        P, X = self._rows()
+        self._trial, sums = ops.lm_poseinv_trial(P, X, float(scale), float(dmin), float(dmax))
+        sums = _allreduce(sums, self.group)
+        return self._scalar(sums[1]), self._scalar(sums[2]), float(sums[3])
+
+    def accept(self):
+        self.param.copy_(self._trial.view(self.param.shape))
+
+
+class ReprojProblem(_Problem):
+    def __init__(self, model, data, key, group):
+        self.model, self.key, self.group = model, key, group
+        self.param = model.poses
+        self.dtype = self.param.dtype
+        self.pts, self.pix, self.cidx, self.seg = data
+        self._trial = None
+
+    def matches(self, model, input):
+        return model is self.model and _input_key(input) == self.key
+
+    def _poses(self):
+        return self.param.tensor().reshape(-1, 7)
+
+    def loss(self):
+        s = ops.lm_reproj_loss(self._poses(), self.pts, self.pix, self.cidx)
+        return self._scalar(_allreduce(s, self.group)[0])
+
+    def linearize(self):
+        H, g, s = ops.lm_reproj_accum(self._poses(), self.pts, self.pix, self.seg)
+        if self.group is not None:
+            packed = torch.cat([H.reshape(-1), g.reshape(-1)])      # one packed all-reduce per LM iteration
+            _allreduce(packed, self.group)
+            n = H.numel()
+            H, g = packed[:n].view_as(H), packed[n:].view_as(g)
+        return H, g
+
+    def trial(self, lin, scale, dmin, dmax):
+        H, g = lin
+        self._trial, _, sums = ops.lm_solve6_retract(H, g, self._poses(), float(scale), float(dmin), float(dmax))
+        loss = _allreduce(ops.lm_reproj_loss(self._trial, self.pts, self.pix, self.cidx), self.group)
+        return self._scalar(loss[0]), self._scalar(sums[0]), float(sums[1])
+
+    def accept(self):
+        self.param.copy_(self._trial.view(self.param.shape))
+
+
+def _input_key(input):
+    items = input if isinstance(input, (tuple, list)) else (input,)
+    return tuple((t.data_ptr(), tuple(t.shape), t.dtype, t._version) if torch.is_tensor(t) else id(t) for t in items)
+
+
+def _is_se3_param(p):
+    return isinstance(p, Parameter) and getattr(p, 'ltype', None) is SE3_type and p.requires_grad and p.is_cuda is not None
+
+
+def recognize(model, input, params, group=None):
+    """Return a structured problem for (model, input) or None (-> generic dense route)."""
+    params = [p for p in params if p.requires_grad]
+    if len(params) != 1 or not _is_se3_param(params[0]) or params[0].dtype not in (torch.float32, torch.float64):
+        return None
+    param = params[0]
+    from ..module.reproj import PoseReproj
+    if isinstance(model, PoseReproj):
+        if param is not model.poses:
+            return None
+        return ReprojProblem(model, model.prepare(*input), _input_key(input), group)
+    if isinstance(input, (tuple, list, dict)) or not isinstance(input, LieTensor) or input.ltype is not SE3_type:
+        return None
+    # record the LieTensor ops of one forward pass
+    rec = []
+    _lt._RECORD = rec
+    try:
+        with torch.no_grad():
+            out = model(input)
+    finally:
+        _lt._RECORD = None
+    if not torch.is_tensor(out) or isinstance(out, LieTensor) or len(rec) != 2:
+        return None
+    (op0, a, b, z), (op1, z1, _, y) = rec
+    ok = (op0 == "mul" and op1 == "log" and a is param and b is input and z1 is z
+          and out.data_ptr() == y.data_ptr() and out.shape == param.shape[:-1] + (6,)
+          and input.shape == param.shape and not input.requires_grad and input.dtype == param.dtype
+          and input.device == param.device)
+    if not ok:
+        return None
+    return PoseInvProblem(model, param, input, _input_key(input), group)

@@ -62,3 +62,52 @@ _install_cpu_oracle_kernels()
 @pytest.fixture(scope="session")
 def golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "lie_ops.npz"))
+
+
+def _install_cpu_oracle_lm_kernels():
+    """Test-only CPU kernels for the fused LM ops, backed by oracle/lm_oracle.py."""
+    from pypose_b200.optim import _fused  # noqa: F401
+    from oracle import lm_oracle as L
+
+    def t(a, like):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(like.dtype)
+
+    def f64(a):
+        return torch.from_numpy(np.asarray(a, dtype=np.float64))
+
+    def n(x):
+        return x.detach().double().numpy()
+
+    def poseinv_loss(P, X):
+        return f64(L.poseinv_loss(n(P), n(X)))
+
+    def poseinv_trial(P, X, scale, dmin, dmax):
+        Pt, sums = L.poseinv_trial(n(P), n(X), scale, dmin, dmax)
+        return t(Pt, P), f64(sums)
+
+    def reproj_accum(poses, pts, pix, seg):
+        H, g, s = L.reproj_accum(n(poses), n(pts), n(pix), seg.numpy())
+        return t(H, poses), t(g, poses), f64(s)
+
+    def solve6_retract(H, g, P, scale, dmin, dmax):
+        Pt, D, s = L.solve6_retract(n(H), n(g), n(P), scale, dmin, dmax)
+        return t(Pt, P), t(D, P), f64(s)
+
+    def reproj_loss(poses, pts, pix, cidx):
+        return f64(L.reproj_loss(n(poses), n(pts), n(pix), cidx.numpy()))
+
+    def reproj_residual(poses, pts, pix, cidx):
+        return t(L.reproj_residual(n(poses), n(pts), n(pix), cidx.numpy()), poses)
+
+    for name, fn in (("lm_poseinv_loss", poseinv_loss), ("lm_poseinv_trial", poseinv_trial),
+                     ("lm_reproj_accum", reproj_accum), ("lm_solve6_retract", solve6_retract),
+                     ("lm_reproj_loss", reproj_loss), ("lm_reproj_residual", reproj_residual)):
+        torch.library.impl(f"b200pose::{name}", "CPU")(fn)
+
+
+_install_cpu_oracle_lm_kernels()
+
+
+@pytest.fixture(scope="session")
+def golden_lm():
+    return np.load(os.path.join(ROOT, "tests", "golden", "lm.npz"))

