@@ -8,7 +8,7 @@ import os
 
 import torch
 
-from ._optable import lie_symbols, lm_symbols
+from ._optable import lie_symbols, lm_symbols, scan_symbols
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200pose.so")
@@ -42,7 +42,8 @@ def _bind(symbol, n_in, n_out, extra=()):
 
 _LIE = {s: (ct, ins, outs) for s, ct, ins, outs, _ in lie_symbols()}
 _LM = {s: args for s, args, _ in lm_symbols()}
-_CT = {"double": ctypes.c_double, "int": ctypes.c_int}
+_SCAN = {s: args for s, args, _ in scan_symbols()}
+_CT = {"double": ctypes.c_double, "int": ctypes.c_int, "long long": ctypes.c_longlong}
 
 
 def fn(symbol):
@@ -56,6 +57,10 @@ def fn(symbol):
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.c_void_p if "*" in t else _CT[t] for t, _, _ in _LM[symbol]] + \
                 [ctypes.c_longlong, ctypes.c_void_p]
+        elif symbol in _SCAN:
+            f = getattr(lib(), symbol)
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.c_void_p if "*" in t else _CT[t] for t, _, _ in _SCAN[symbol]] + [ctypes.c_void_p]
         else:
             raise B200PoseError(f"unknown C-ABI symbol {symbol}")
         _fns[symbol] = f

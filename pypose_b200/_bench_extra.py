@@ -93,6 +93,18 @@ def run(args, rank, world, dev):
                         "residuals_total": M, "residuals_per_gpu": hi - lo, "scaling": "strong", "dtype": "f32",
                         "config": "1e4 SE3 poses, 1e6 reprojection residuals, block-diagonal JtJ, TrustRegion "
                                   "(BASELINE.json configs[4], single-pose form)"}
+    # ---- IMU preintegration (trajectories sharded: weak scaling, 1e3 x 1e4 fp64 samples per GPU)
+    B, F = 1000, 10_000
+    dt = torch.full((B, F, 1), 0.005, dtype=torch.float64, device=dev)
+    gyro = 0.1 * torch.randn(B, F, 3, dtype=torch.float64, device=dev)
+    acc = torch.randn(B, F, 3, dtype=torch.float64, device=dev) + torch.tensor([0, 0, 9.81], dtype=torch.float64, device=dev)
+    imu = pp.module.IMUPreintegrator(prop_cov=False, reset=True).double().to(dev)
+    ms3 = _max(_time_steps(lambda: imu(dt, gyro, acc), lambda: None, max(5, steps // 4), 2), world, dev)
+    ms3k = _max(_time_steps(lambda: imu.integrate(dt, gyro, acc), lambda: None, max(5, steps // 4), 2), world, dev)
+    out["imu"] = {"msamples_per_s": round(world * B * F / (ms3 * 1e-3) / 1e6, 1), "ms_per_call": round(ms3, 4),
+                  "integrate_kernel_ms": round(ms3k, 4), "integrate_hbm_gbs": round(B * F * 136 / (ms3k * 1e-3) / 1e9, 1),
+                  "trajectories_per_gpu": B, "samples": F, "dtype": "f64", "scaling": "weak",
+                  "config": "IMUPreintegrator(prop_cov=False), 1e3 x 1e4 samples fp64 (BASELINE.json configs[3])"}
     return out
 
 

@@ -126,3 +126,32 @@ def lm_symbols():
     for base, args, cite in LM_OPS:
         for sfx, ct in DTYPES.items():
             yield f"{base}_{sfx}", [(t.replace("REAL", ct), n, c) for t, n, c in args], cite
+
+
+# ----------------------------------------------------------------------------------------------
+# scans (csrc/scan.cu): explicit declarations, (symbol base, args, citation); REAL as above.
+# ----------------------------------------------------------------------------------------------
+SCAN_OPS = [
+    (f"b200_{g}_cumprod",
+     [("const REAL*", "in", f"(B,L,{d})"), ("REAL*", "out", f"(B,L,{d})"), ("long long", "B", "sequences"),
+      ("long long", "L", "scan length"), ("int", "left", "1: y_i = x_i y_{i-1}; 0: y_i = y_{i-1} x_i")],
+     "cumprod / cummul on group LieTensors = cumops_ with the group product, pypose/basics/ops.py:29-58, "
+     "lietensor.py:171-193")
+    for g, (_, d, _) in GROUPS.items()
+] + [
+    ("b200_imu_integrate",
+     [("const REAL*", "dt", "(B,F,1)"), ("const REAL*", "gyro", "(B,F,3)"), ("const REAL*", "acc", "(B,F,3)"),
+      ("const REAL*", "rot", "(B,F,4) known rotations or NULL"), ("const REAL*", "init_rot", "(B,4) / (1,4) or NULL"),
+      ("long long", "init_stride", "4 for per-sequence init_rot, 0 to broadcast one"),
+      ("const REAL*", "gravity3_host", "HOST pointer to the 3 gravity components"),
+      ("REAL*", "a", "(B,F,3)"), ("REAL*", "Dp", "(B,F,3)"), ("REAL*", "Dv", "(B,F,3)"), ("REAL*", "Dr", "(B,F,4)"),
+      ("REAL*", "Dt", "(B,F,1)"), ("REAL*", "w", "(B,F,4)"), ("long long", "B", "trajectories"),
+      ("long long", "F", "samples per trajectory")],
+     "IMUPreintegrator.integrate, pypose/module/imu_preintegrator.py:314-384"),
+]
+
+
+def scan_symbols():
+    for base, args, cite in SCAN_OPS:
+        for sfx, ct in DTYPES.items():
+            yield f"{base}_{sfx}", [(t.replace("REAL", ct), n, c) for t, n, c in args], cite

@@ -1,1 +1,2 @@
 from .reproj import PoseReproj
+from .imu_preintegrator import IMUPreintegrator

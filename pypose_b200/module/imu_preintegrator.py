@@ -1,0 +1,116 @@
+"""IMU preintegration (reference: pypose/module/imu_preintegrator.py).
+
+`integrate` — the hot loop of the reference (an so3 Exp, a log-step SO3 product scan, two rotations
+per sample and three cumsums, imu_preintegrator.py:314-384) — is ONE fused single-pass kernel here
+(csrc/scan.cu `imu_integrate_kernel`).  `predict` and the state carry-over are the same small
+LieTensor expressions as in the reference.  `propagate_cov` follows imu_preintegrator.py:428-465 with
+torch matrix ops on top of the fused outputs (optional path, `prop_cov=True`).
+"""
+import torch
+from torch import nn
+
+from ..basics import cumprod
+from ..lietensor import LieTensor, SO3, identity_SO3, so3, vec2skew
+
+
+class IMUPreintegrator(nn.Module):
+    def __init__(self, pos=torch.zeros(3), rot=identity_SO3(), vel=torch.zeros(3), gravity=9.81007,
+                 gyro_cov=(3.2e-3) ** 2, acc_cov=(8e-2) ** 2, prop_cov=True, reset=False):
+        super().__init__()
+        if not reset and not prop_cov:
+            raise RuntimeError('"prop_cov" and "reset" cannot be False simultaneously.')
+        self.reset, self.prop_cov = reset, prop_cov
+        if isinstance(acc_cov, float):
+            acc_cov = torch.tensor([[acc_cov, acc_cov, acc_cov]])
+        if isinstance(gyro_cov, float):
+            gyro_cov = torch.tensor([[gyro_cov, gyro_cov, gyro_cov]])
+        # the reference stores gravity in a float32 buffer (imu_preintegrator.py:108): keep that rounding
+        self._g = float(torch.tensor(gravity, dtype=torch.float32))
+        self.register_buffer('gravity', torch.tensor([0, 0, gravity]), persistent=False)
+        self.register_buffer('pos', self._check(pos).clone(), persistent=False)
+        self.register_buffer('rot', self._check(rot).clone(), persistent=False)
+        self.register_buffer('vel', self._check(vel).clone(), persistent=False)
+        self.register_buffer('cov', torch.zeros(1, 9, 9), persistent=False)
+        self.register_buffer('gyro_cov', gyro_cov, persistent=False)
+        self.register_buffer('acc_cov', acc_cov, persistent=False)
+        self.Rij = None
+
+    def _check(self, obj):
+        if obj is not None:
+            if len(obj.shape) == 2:
+                obj = obj[None, ...]
+            elif len(obj.shape) == 1:
+                obj = obj[None, None, ...]
+        return obj
+
+    def forward(self, dt, gyro, acc, rot: SO3 = None, gyro_cov=None, acc_cov=None, init_state=None):
+        assert 0 < len(acc.shape) == len(dt.shape) == len(gyro.shape) <= 3
+        acc, gyro, dt, rot = self._check(acc), self._check(gyro), self._check(dt), self._check(rot)
+        B = dt.shape[0]
+        if init_state is None:
+            init_state = {'pos': self.pos, 'rot': self.rot, 'vel': self.vel}
+        inte = self.integrate(dt, gyro, acc, rot=rot, init_rot=init_state['rot'])
+        predict = self.predict(init_state, inte)
+        if self.prop_cov:
+            gyro_cov = self.gyro_cov.repeat([B, 1, 1]) if gyro_cov is None else gyro_cov
+            acc_cov = self.acc_cov.repeat([B, 1, 1]) if acc_cov is None else acc_cov
+            if 'cov' not in init_state or init_state['cov'] is None:
+                init_cov = self.cov.expand(B, 9, 9)
+            else:
+                init_cov = init_state['cov']
+            Rij = init_state['Rij'] if 'Rij' in init_state else self.Rij
+            Rij = Rij * inte['Dr'] if Rij is not None else inte['Dr']
+            cov_in = {'Rij': Rij.detach(), 'Rk': inte['w'].detach(), 'Ha': vec2skew(inte['a'].detach()),
+                      'dt': dt.detach()}
+            cov = self.propagate_cov(cov_input=cov_in, init_cov=init_cov, gyro_cov=gyro_cov, acc_cov=acc_cov)
+        else:
+            cov = {'cov': None}
+        if not self.reset:      # carry the last state over to the next call (imu_preintegrator.py:305-310)
+            self.pos = predict['pos'][..., -1:, :]
+            self.rot = predict['rot'][..., -1:, :]
+            self.vel = predict['vel'][..., -1:, :]
+            self.cov = cov['cov']
+            self.Rij = Rij[..., -1:, :]
+        return {**predict, **cov}
+
+    def integrate(self, dt, gyro, acc, rot: SO3 = None, init_rot: SO3 = None):
+        """Fused preintegration: returns a, Dp, Dv, Dr, Dt, w exactly as imu_preintegrator.py:383-384."""
+        dtype = dt.dtype
+        rot_t = rot.tensor() if isinstance(rot, LieTensor) else None
+        init_t = init_rot.tensor() if (rot_t is None and init_rot is not None) else None
+        a, Dp, Dv, Dr, Dt, w = torch.ops.b200pose.imu_integrate(
+            dt, gyro.to(dtype), acc.to(dtype), rot_t, init_t, [0.0, 0.0, self._g])
+        return {'a': a, 'Dp': Dp, 'Dv': Dv, 'Dr': SO3(Dr), 'Dt': Dt, 'w': SO3(w)}
+
+    @classmethod
+    def predict(cls, init_state, integrate):
+        """rot = R0 Dr, vel = v0 + R0 Dv, pos = p0 + R0 Dp + v0 Dt (imu_preintegrator.py:422-426)."""
+        return {'rot': init_state['rot'] * integrate['Dr'],
+                'vel': init_state['vel'] + init_state['rot'] * integrate['Dv'],
+                'pos': init_state['pos'] + init_state['rot'] * integrate['Dp'] + init_state['vel'] * integrate['Dt']}
+
+    @classmethod
+    def propagate_cov(cls, cov_input, init_cov, gyro_cov, acc_cov):
+        """Covariance propagation Sigma <- A Sigma A^T + B (imu_preintegrator.py:428-465)."""
+        dt = cov_input['dt']
+        B, F = dt.shape[:2]
+        dev, dtype = dt.device, dt.dtype
+        Cg, Ca = torch.diag_embed(gyro_cov), torch.diag_embed(acc_cov)
+        Rk, Rij, Ha = cov_input['Rk'].matrix(), cov_input['Rij'].matrix(), cov_input['Ha']
+        dt1, dt2 = dt.unsqueeze(-1), (dt ** 2).unsqueeze(-1)
+        A = torch.eye(9, device=dev, dtype=dtype).repeat([B, F + 1, 1, 1])
+        A[:, :-1, 0:3, 0:3] = Rk.mT
+        RH = Rij @ Ha
+        A[:, :-1, 3:6, 0:3] = -RH * dt1
+        A[:, :-1, 6:9, 0:3] = -0.5 * RH * dt2
+        A[:, :-1, 6:9, 3:6] = torch.eye(3, device=dev, dtype=dtype) * dt1
+        Bg = torch.zeros(B, F, 9, 3, device=dev, dtype=dtype)
+        Ba = torch.zeros(B, F, 9, 3, device=dev, dtype=dtype)
+        Bg[..., 0:3, 0:3] = cov_input['Rk'].Jr() * dt1
+        Ba[..., 3:6, 0:3] = Rij * dt1
+        Ba[..., 6:9, 0:3] = 0.5 * Rij * dt2
+        B_cov = (Bg @ Cg @ Bg.mT + Ba @ Ca @ Ba.mT) / dt1
+        B_cov = torch.cat([init_cov[:, None, ...], B_cov], dim=1)
+        A_left_cum = cumprod(A.flip([1]), dim=1).flip([1])
+        cov = torch.sum(A_left_cum @ B_cov @ A_left_cum.mT, dim=1)
+        return {'cov': cov, 'Rij': cov_input['Rij'][..., -1:, :]}

@@ -111,3 +111,29 @@ _install_cpu_oracle_lm_kernels()
 @pytest.fixture(scope="session")
 def golden_lm():
     return np.load(os.path.join(ROOT, "tests", "golden", "lm.npz"))
+
+
+def _install_cpu_oracle_scan_kernels():
+    from pypose_b200.lietensor import scan as _scan  # noqa: F401
+    from oracle import scan_oracle as S
+
+    def cumprod(x, group, left):
+        return torch.from_numpy(S.cumprod(group, x.detach().double().numpy(), left)).to(x.dtype)
+
+    def imu(dt, gyro, acc, rot, init_rot, gravity):
+        n = lambda t: None if t is None else t.detach().double().numpy()
+        B, F = dt.shape[:2]
+        r = None if rot is None else np.broadcast_to(n(rot), (B, F, 4))
+        outs = S.imu_integrate(n(dt), n(gyro), n(acc), r, n(init_rot), gravity)
+        return tuple(torch.from_numpy(np.ascontiguousarray(o)).to(dt.dtype) for o in outs)
+
+    torch.library.impl("b200pose::cumprod", "CPU")(cumprod)
+    torch.library.impl("b200pose::imu_integrate", "CPU")(imu)
+
+
+_install_cpu_oracle_scan_kernels()
+
+
+@pytest.fixture(scope="session")
+def golden_scan():
+    return np.load(os.path.join(ROOT, "tests", "golden", "scan_imu.npz"))

@@ -15,10 +15,11 @@ def header_symbols():
 
 
 def test_header_is_generated_from_optable():
-    from pypose_b200._optable import lie_symbols, lm_symbols
+    from pypose_b200._optable import lie_symbols, lm_symbols, scan_symbols
     declared = set(header_symbols())
     assert {s for s, *_ in lie_symbols()} <= declared
     assert {s for s, *_ in lm_symbols()} <= declared
+    assert {s for s, *_ in scan_symbols()} <= declared
 
 
 def test_library_loads_and_exports_every_declared_symbol():

@@ -1,0 +1,140 @@
+"""Scans and IMU preintegration: oracle pinned to the reference goldens; host logic on CPU; kernels on GPU."""
+import numpy as np
+import pytest
+import torch
+
+import pypose_b200 as pp
+from oracle import scan_oracle as S
+from oracle import lie_oracle as O
+
+GROUPS = ["SO3", "SE3", "RxSO3", "Sim3"]
+CTOR = {"SO3": pp.SO3, "SE3": pp.SE3, "RxSO3": pp.RxSO3, "Sim3": pp.Sim3}
+
+
+@pytest.mark.parametrize("grp", GROUPS)
+def test_oracle_cumprod_matches_reference(golden_scan, grp):
+    x = golden_scan[f"cumprod/{grp}/in"]
+    np.testing.assert_allclose(S.cumprod(grp, x, True), golden_scan[f"cumprod/{grp}/left"], atol=1e-12)
+    np.testing.assert_allclose(S.cumprod(grp, x, False), golden_scan[f"cumprod/{grp}/right"], atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["free", "rot"])
+def test_oracle_imu_matches_reference(golden_scan, tag):
+    g = golden_scan
+    rot = g["imu/rot"] if tag == "rot" else None
+    outs = S.imu_integrate(g["imu/dt"], g["imu/gyro"], g["imu/acc"], rot, g["imu/init_rot"])
+    for name, o in zip(("a", "Dp", "Dv", "Dr", "Dt", "w"), outs):
+        np.testing.assert_allclose(o, g[f"imu/{tag}/inte/{name}"], atol=1e-12, err_msg=name)
+
+
+def _dev(request):
+    return "cuda" if request.node.get_closest_marker("gpu") else "cpu"
+
+
+def _check_cumprod_api(golden_scan, grp, dev, tol):
+    x = CTOR[grp](torch.from_numpy(golden_scan[f"cumprod/{grp}/in"]).to(dev))
+    for left, key in ((True, "left"), (False, "right")):
+        y = x.cumprod(dim=1, left=left)
+        assert isinstance(y, pp.LieTensor) and y.ltype is x.ltype
+        np.testing.assert_allclose(y.tensor().cpu().numpy(), golden_scan[f"cumprod/{grp}/{key}"], atol=tol)
+        np.testing.assert_allclose(pp.cummul(x, 1, left).tensor().cpu().numpy(), golden_scan[f"cumprod/{grp}/{key}"], atol=tol)
+    # scan along dim 0 of a (L, B, D) view, in place variant, and the explicit 4-factor product
+    # (reference tests/basics/test_ops.py:15-57)
+    xt = CTOR[grp](x.tensor().transpose(0, 1).contiguous())
+    y0 = xt.cumprod(dim=0, left=True)
+    np.testing.assert_allclose(y0.tensor().transpose(0, 1).cpu().numpy(), golden_scan[f"cumprod/{grp}/left"], atol=tol)
+    four = x[:, :4]
+    last = four.cumprod(dim=1, left=True)[:, -1]
+    ref = four[:, 3] @ four[:, 2] @ four[:, 1] @ four[:, 0]
+    np.testing.assert_allclose(last.tensor().cpu().numpy(), ref.tensor().cpu().numpy(), atol=tol)
+    z = x.clone()
+    z.cumprod_(dim=1, left=False)
+    np.testing.assert_allclose(z.tensor().cpu().numpy(), golden_scan[f"cumprod/{grp}/right"], atol=tol)
+
+
+@pytest.mark.parametrize("grp", GROUPS)
+def test_cumprod_api_cpu(golden_scan, grp):
+    _check_cumprod_api(golden_scan, grp, "cpu", 1e-12)
+
+
+def test_cumops_generic_equals_cumsum():
+    # reference tests/lietensor/test_lietensor.py:214-221
+    for n in (1, 2, 3, 17, 100, 257):
+        x = torch.randn(n, 3, dtype=torch.float64)
+        torch.testing.assert_close(pp.cumops(x, 0, lambda a, b: a + b), torch.cumsum(x, 0))
+
+
+def _check_imu_module(golden_scan, dev, tol):
+    g = golden_scan
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    init = {"pos": t("imu/init_pos"), "rot": pp.SO3(t("imu/init_rot")), "vel": t("imu/init_vel")}
+    for tag in ("free", "rot"):
+        m = pp.module.IMUPreintegrator(prop_cov=True, reset=True).double().to(dev)
+        kw = {"rot": pp.SO3(t("imu/rot"))} if tag == "rot" else {}
+        out = m(t("imu/dt"), t("imu/gyro"), t("imu/acc"), init_state=init, **kw)
+        for k in ("rot", "vel", "pos", "cov"):
+            v = out[k].tensor() if isinstance(out[k], pp.LieTensor) else out[k]
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"imu/{tag}/out/{k}"], atol=tol, rtol=tol, err_msg=f"{tag}/{k}")
+
+
+def test_imu_module_cpu(golden_scan):
+    _check_imu_module(golden_scan, "cpu", 1e-10)
+
+
+def test_imu_docstring_known_answer():
+    """imu_preintegrator.py:28-53: one sample, dt = 0.002, known identity rotation (rot/vel/pos; the
+    docstring's printed cov is stale)."""
+    p = pp.module.IMUPreintegrator(torch.zeros(3), pp.identity_SO3(), torch.zeros(3), prop_cov=False, reset=True)
+    out = p(torch.tensor([0.002]), torch.tensor([0.1, 0.1, 0.1]), torch.tensor([0.1, 0.1, 0.1]), pp.identity_SO3())
+    torch.testing.assert_close(out["rot"].tensor().flatten(), torch.tensor([1e-4, 1e-4, 1e-4, 1.0]), atol=1e-7, rtol=0)
+    torch.testing.assert_close(out["vel"].flatten(), torch.tensor([0.0002, 0.0002, -0.0194]), atol=5e-5, rtol=0)
+    torch.testing.assert_close(out["pos"].flatten(), torch.tensor([2.0e-07, 2.0e-07, -1.9420e-05]), atol=5e-9, rtol=0)
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("grp", GROUPS)
+def test_cumprod_api_gpu(golden_scan, grp):
+    _check_cumprod_api(golden_scan, grp, "cuda", 1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grp", GROUPS)
+@pytest.mark.parametrize("L", [1, 2, 31, 32, 33, 127, 128, 129, 1000, 4097])
+@pytest.mark.parametrize("dt,tol", [(torch.float64, 1e-11), (torch.float32, 2e-4)], ids=["f64", "f32"])
+def test_cumprod_kernel_vs_oracle_lengths(grp, L, dt, tol):
+    from tests.util import rand_group
+    rng = np.random.default_rng(L)
+    x = rand_group(rng, grp, 3 * L, tmax=0.3, t_sigma=0.1, s_sigma=0.02).reshape(3, L, -1)
+    xd = torch.from_numpy(x).to(dt).cuda()
+    for left in (True, False):
+        y = torch.ops.b200pose.cumprod(xd, grp, left).double().cpu().numpy()
+        ref = S.cumprod(grp, xd.double().cpu().numpy(), left)
+        assert np.abs(y - ref).max() <= tol * (1 + np.abs(ref).max()), (grp, L, left)
+
+
+@pytest.mark.gpu
+def test_imu_module_gpu(golden_scan):
+    _check_imu_module(golden_scan, "cuda", 1e-10)
+
+
+@pytest.mark.gpu
+def test_imu_config4_size_vs_oracle_subset():
+    """BASELINE.json configs[3]: 1e3 trajectories x 1e4 samples, fp64; the first 4 trajectories are
+    checked against the oracle (rot via Log(a^-1 b) <= 1e-9, vel/pos relative 1e-9)."""
+    torch.manual_seed(0)
+    B, F = 1000, 10_000
+    dt = torch.full((B, F, 1), 0.005, dtype=torch.float64, device="cuda")
+    gyro = 0.1 * torch.randn(B, F, 3, dtype=torch.float64, device="cuda")
+    acc = torch.randn(B, F, 3, dtype=torch.float64, device="cuda") + torch.tensor([0, 0, 9.81], dtype=torch.float64, device="cuda")
+    m = pp.module.IMUPreintegrator(prop_cov=False, reset=True).double().cuda()
+    out = m(dt, gyro, acc)
+    o = S.imu_integrate(dt[:4].cpu().numpy(), gyro[:4].cpu().numpy(), acc[:4].cpu().numpy())
+    Dp, Dv, Dr = o[1], o[2], o[3]
+    # default init state is identity / zeros -> predict == integrate
+    rot = out["rot"].tensor()[:4].cpu().numpy()
+    d = O.log("SO3", O.mul("SO3", O.inv("SO3", Dr.reshape(-1, 4)), rot.reshape(-1, 4)))
+    assert np.abs(d).max() <= 1e-9
+    assert np.abs(out["vel"][:4].cpu().numpy() - Dv).max() <= 1e-9 * (1 + np.abs(Dv).max())
+    assert np.abs(out["pos"][:4].cpu().numpy() - Dp).max() <= 1e-9 * (1 + np.abs(Dp).max())
+    assert torch.isfinite(out["pos"]).all()
