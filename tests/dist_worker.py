@@ -1,0 +1,62 @@
+"""Worker for tests/test_dist_gloo.py: runs the sharded LM on `world` CPU processes (gloo) with the
+oracle-backed test kernels and writes its loss / pose trajectory to an .npz."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tests.conftest  # noqa: F401,E402  (installs the CPU oracle kernels)
+import pypose_b200 as pp  # noqa: E402
+from torch import nn  # noqa: E402
+
+
+class InvNet(nn.Module):
+    def __init__(self, pose):
+        super().__init__()
+        self.pose = pp.Parameter(pose)
+
+    def forward(self, input):
+        return (self.pose @ input).Log().tensor()
+
+
+def main():
+    out = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['MASTER_PORT']}", rank=rank, world_size=world)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lm.npz"))
+    res = {}
+    # PoseInv: poses sharded (each rank owns a slice); scalar sums all-reduced
+    P0, X = g["poseinv/P0"], g["poseinv/X"]
+    lo, hi = rank * len(P0) // world, (rank + 1) * len(P0) // world
+    net = InvNet(pp.SE3(torch.from_numpy(P0[lo:hi].copy())))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), group=True)
+    Xs = pp.SE3(torch.from_numpy(X[lo:hi].copy()))
+    losses = [float(opt.step(Xs)) for _ in range(4)]
+    gathered = [torch.zeros(len(P0) // world, 7, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, net.pose.detach().tensor().contiguous())
+    res["poseinv_loss"], res["poseinv_poses"] = np.array(losses), torch.cat(gathered).numpy()
+    # Reproj: residuals sharded, poses replicated; [H | g] and the scalars all-reduced
+    for case, steps in (("reproj", 4), ("reproj_hard", 6)):
+        pts, pix, cidx = g[f"{case}/pts"], g[f"{case}/pix"], g[f"{case}/cidx"]
+        M = len(cidx)
+        sl = slice(rank * M // world, (rank + 1) * M // world)
+        net2 = pp.module.PoseReproj(pp.SE3(torch.from_numpy(g[f"{case}/poses0"].copy())))
+        opt2 = pp.optim.LM(net2, strategy=pp.optim.strategy.TrustRegion(), group=True)
+        inp = (torch.from_numpy(pts[sl]), torch.from_numpy(pix[sl]), torch.from_numpy(cidx[sl]))
+        l2, rej = [], []
+        for _ in range(steps):
+            l2.append(float(opt2.step(inp)))
+            rej.append(opt2.reject_count)
+        res[f"{case}_loss"], res[f"{case}_poses"], res[f"{case}_reject"] = np.array(l2), net2.poses.detach().numpy(), np.array(rej)
+    if rank == 0:
+        np.savez(out, **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

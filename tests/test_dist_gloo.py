@@ -1,0 +1,38 @@
+"""World-size-2 (gloo, CPU) run of the sharded LM: pose-sharded PoseInv and residual-sharded reprojection
+must reproduce the reference's single-process trajectories (tests/golden/lm.npz)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_sharded_lm_world2_matches_reference(tmp_path, golden_lm):
+    out = str(tmp_path / "dist.npz")
+    port = str(_free_port())
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port,
+                   PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), out], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    r, g = np.load(out), golden_lm
+    np.testing.assert_allclose(r["poseinv_loss"], g["poseinv/trustregion/loss"], rtol=1e-5, atol=1e-20)
+    np.testing.assert_allclose(r["poseinv_poses"], g["poseinv/trustregion/poses"][-1], atol=1e-9)
+    for case in ("reproj", "reproj_hard"):
+        np.testing.assert_allclose(r[f"{case}_loss"], g[f"{case}/trustregion/loss"], rtol=1e-6)
+        np.testing.assert_allclose(r[f"{case}_poses"], g[f"{case}/trustregion/poses"][-1], atol=1e-8)
+        np.testing.assert_array_equal(r[f"{case}_reject"], g[f"{case}/trustregion/reject"])
