@@ -17,7 +17,7 @@ from .lietensor import identity_Sim3, identity_sim3, identity_RxSO3, identity_rx
 from .lietensor import add, add_, mul, Exp, Log, Inv, Mul, Retr, Act, Adj, AdjT, Jinvp, Jr
 from .lietensor import SO3_type, so3_type, SE3_type, se3_type
 from .lietensor import Sim3_type, sim3_type, RxSO3_type, rxso3_type
-from .lietensor import tensor, translation, rotation, scale, matrix, euler, vec2skew
+from .lietensor import tensor, translation, rotation, scale, matrix, euler, vec2skew, quat2unit
 from .lietensor.lietensor import retain_ltype
 from . import func
 from .function import *

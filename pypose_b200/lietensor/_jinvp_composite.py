@@ -76,10 +76,10 @@ def jlinv_times(grp, x, p):
 
 
 def grad_X(grp, X, p, g):
-    from .ops import _op
+    from .ops import _apply
     with torch.enable_grad():
         Xd = X.detach().requires_grad_(True)
-        x = _op(f"{grp}_log_fwd")(Xd)
+        x = _apply(f"{grp}_log_fwd", Xd)
         out = jlinv_times(grp, x, p.detach())
         (gX,) = torch.autograd.grad(out, Xd, g)
     return gX

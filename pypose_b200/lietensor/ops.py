@@ -2,10 +2,11 @@
 
 This replaces the 32 `torch.autograd.Function` classes of the reference
 (pypose/lietensor/operation.py:304-1113).  Each reference Function becomes a forward op plus a
-backward op (both single fused CUDA kernels, csrc/lie_kernels.cuh) tied together with
-`torch.library.register_autograd`; `register_vmap` folds a vmapped dimension into the batch so
-`torch.func.jacrev/vmap` and `torch.autograd.functional.jacobian(vectorize=True)` keep working
-(the reference relies on `generate_vmap_rule = True` for the same purpose).
+backward op (both single fused CUDA kernels, csrc/lie_kernels.cuh) tied together by a generated
+`torch.autograd.Function` (setup_context + generate_vmap_rule); `register_vmap` on the raw ops folds
+a vmapped dimension into the batch so `torch.func.jacrev/vmap` and
+`torch.autograd.functional.jacobian(vectorize=True)` keep working (the reference relies on
+`generate_vmap_rule = True` for the same purpose).
 
 Only the CUDA dispatch key gets a kernel: CPU tensors fail loudly in the dispatcher.
 """
@@ -97,94 +98,74 @@ _define("so3_jr", "b200_so3_jr", [3], [9])
 
 
 # ----------------------------------------------------------------------------
-# autograd: backward rules of the reference, each a single fused kernel
+# autograd: one torch.autograd.Function per reference Function, forward and backward each a single fused
+# kernel.  `setup_context` + `generate_vmap_rule` make them usable under torch.func (jacrev / vmap / vjp)
+# and under torch.autograd.functional.jacobian(vectorize=True), exactly like the reference's
+# `generate_vmap_rule = True` Functions (operation.py:305 etc.); the raw ops carry the vmap rule.
 # ----------------------------------------------------------------------------
+FUNCS = {}
+
+
+def _make_function(name, fwd, save, bwd):
+    def forward(*args):
+        return _op(fwd)(*args)
+
+    def setup_context(ctx, inputs, output):
+        ctx.save_for_backward(*save(inputs, output))
+
+    def backward(ctx, g):
+        return bwd(ctx, ctx.saved_tensors, g.contiguous())
+
+    cls = type(name, (torch.autograd.Function,), {
+        "generate_vmap_rule": True, "forward": staticmethod(forward),
+        "setup_context": staticmethod(setup_context), "backward": staticmethod(backward)})
+    FUNCS[fwd] = cls
+    return cls
+
+
 def _register_autograd(grp, alg):
-    exp_f, exp_b = f"{alg}_exp_fwd", f"{alg}_exp_bwd"
-    log_f, log_b = f"{grp}_log_fwd", f"{grp}_log_bwd"
-
-    def exp_setup(ctx, inputs, output):
-        ctx.save_for_backward(inputs[0])
-
-    def exp_bwd(ctx, g):
-        (x,) = ctx.saved_tensors
-        return _op(exp_b)(x, g.contiguous())
-
-    torch.library.register_autograd(f"{NS}::{exp_f}", exp_bwd, setup_context=exp_setup)
-
-    def log_setup(ctx, inputs, output):
-        ctx.save_for_backward(output)
-
-    def log_bwd(ctx, g):
-        (out,) = ctx.saved_tensors
-        return _op(log_b)(out, g.contiguous())
-
-    torch.library.register_autograd(f"{NS}::{log_f}", log_bwd, setup_context=log_setup)
-
-    def inv_setup(ctx, inputs, output):
-        ctx.save_for_backward(output)
-
-    def inv_bwd(ctx, g):
-        (Y,) = ctx.saved_tensors
-        return _op(f"{grp}_inv_bwd")(Y, g.contiguous())
-
-    torch.library.register_autograd(f"{NS}::{grp}_inv_fwd", inv_bwd, setup_context=inv_setup)
-
-    def mul_setup(ctx, inputs, output):
-        ctx.save_for_backward(inputs[0])
-
-    def mul_bwd(ctx, g):
-        (X,) = ctx.saved_tensors
-        gX, gY = _op(f"{grp}_mul_bwd")(X, g.contiguous())
-        return gX, gY
-
-    torch.library.register_autograd(f"{NS}::{grp}_mul_fwd", mul_bwd, setup_context=mul_setup)
-
+    # Exp: save x; grad = gX[:K] @ Jl(x)                         (operation.py:359-370 etc.)
+    _make_function(f"{alg}_Exp", f"{alg}_exp_fwd", lambda i, o: (i[0],),
+                   lambda ctx, s, g: _op(f"{alg}_exp_bwd")(s[0], g))
+    # Log: save output; grad = [g @ Jl^-1(out), 0]               (operation.py:326-337 etc.)
+    _make_function(f"{grp}_Log", f"{grp}_log_fwd", lambda i, o: (o,),
+                   lambda ctx, s, g: _op(f"{grp}_log_bwd")(s[0], g))
+    # Inv: save output Y; grad = [-g[:K] @ Adj(Y), 0]            (operation.py:938-949 etc.)
+    _make_function(f"{grp}_Inv", f"{grp}_inv_fwd", lambda i, o: (o,),
+                   lambda ctx, s, g: _op(f"{grp}_inv_bwd")(s[0], g))
+    # Mul: save X; gX = [g[:K],0], gY = [g[:K] @ Adj(X), 0]      (operation.py:839-852 etc.)
+    _make_function(f"{grp}_Mul", f"{grp}_mul_fwd", lambda i, o: (i[0],),
+                   lambda ctx, s, g: tuple(_op(f"{grp}_mul_bwd")(s[0], g)))
+    # Act / Act4 / AdjXa: save X and the output                  (operation.py:527-542, 631-646, 734-748 etc.)
     for act in ("act", "act4", "adj"):
-        def xo_setup(ctx, inputs, output):
-            ctx.save_for_backward(inputs[0], output)
+        _make_function(f"{grp}_{act}", f"{grp}_{act}_fwd", lambda i, o: (i[0], o),
+                       lambda ctx, s, g, _n=f"{grp}_{act}_bwd": tuple(_op(_n)(s[0], s[1], g)))
+    # AdjTXa: save X and a                                        (operation.py:1032-1044 etc.)
+    _make_function(f"{grp}_AdjT", f"{grp}_adjt_fwd", lambda i, o: (i[0], i[1]),
+                   lambda ctx, s, g: tuple(_op(f"{grp}_adjt_bwd")(s[0], s[1], g)))
 
-        def xo_bwd(ctx, g, _name=f"{grp}_{act}_bwd"):
-            X, out = ctx.saved_tensors
-            gX, g2 = _op(_name)(X, out, g.contiguous())
-            return gX, g2
-
-        torch.library.register_autograd(f"{NS}::{grp}_{act}_fwd", xo_bwd, setup_context=xo_setup)
-
-    def adjt_setup(ctx, inputs, output):
-        ctx.save_for_backward(inputs[0], inputs[1])
-
-    def adjt_bwd(ctx, g):
-        X, a = ctx.saved_tensors
-        gX, ga = _op(f"{grp}_adjt_bwd")(X, a, g.contiguous())
-        return gX, ga
-
-    torch.library.register_autograd(f"{NS}::{grp}_adjt_fwd", adjt_bwd, setup_context=adjt_setup)
-
-    # Jinvp has no custom backward in the reference (plain autograd through Log and the matrix
-    # build, lietensor.py:261).  d/dp is g @ Jl^-1(x) (the Log-backward kernel); d/dX goes through
-    # a differentiable composite of our own ops (rare path, not on the hot loop).
-    def jinvp_setup(ctx, inputs, output):
-        ctx.save_for_backward(inputs[0], inputs[1])
-        ctx.needs_X = ctx.needs_input_grad[0]
-
-    def jinvp_bwd(ctx, g):
-        X, p = ctx.saved_tensors
-        g = g.contiguous()
-        x = _op(log_f)(X)
-        K = p.shape[-1]
-        gp = _op(log_b)(x, g)[:, :K]
+    # Jinvp has no custom backward in the reference (plain autograd through Log and the matrix build,
+    # lietensor.py:261).  d/dp is g @ Jl^-1(x) (the Log-backward kernel); d/dX goes through a
+    # differentiable composite of our own ops (rare path, not on the hot loop).
+    def jinvp_bwd(ctx, s, g):
+        X, p = s
+        x = _op(f"{grp}_log_fwd")(X)
+        gp = _op(f"{grp}_log_bwd")(x, g)[:, :p.shape[-1]]
         gX = None
-        if ctx.needs_X:
+        if ctx.needs_input_grad[0]:
             from . import _jinvp_composite
             gX = _jinvp_composite.grad_X(grp, X, p, g)
         return gX, gp
-
-    torch.library.register_autograd(f"{NS}::{grp}_jinvp_fwd", jinvp_bwd, setup_context=jinvp_setup)
+    _make_function(f"{grp}_Jinvp", f"{grp}_jinvp_fwd", lambda i, o: (i[0], i[1]), jinvp_bwd)
 
 
 for _grp, (_alg, _D, _K) in GROUPS.items():
     _register_autograd(_grp, _alg)
+
+
+def _apply(name, *args):
+    f = FUNCS.get(name)
+    return f.apply(*args) if f is not None else _op(name)(*args)
 
 
 # ----------------------------------------------------------------------------
@@ -196,7 +177,7 @@ def _rows(t: Tensor):
 
 def unary(name, x: Tensor, out_w):
     """Apply op `name` on the last dim of an N-D tensor."""
-    y = _op(name)(_rows(x))
+    y = _apply(name, _rows(x))
     return y.view(x.shape[:-1] + (out_w,))
 
 
@@ -211,5 +192,5 @@ def broadcast_inputs(x: Tensor, y: Tensor):
 
 def binary(name, x: Tensor, y: Tensor, out_w):
     xr, yr, out_shape = broadcast_inputs(x, y)
-    out = _op(name)(xr, yr)
+    out = _apply(name, xr, yr)
     return out.view(out_shape + (out_w,))
