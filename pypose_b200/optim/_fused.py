@@ -112,6 +112,21 @@ def _reproj_residual(poses, pts, pix, cidx):
     return r
 
 
+# ----------------------------------------------------------------------------------------------------
+# Fast path used by optim/structured.py: for CUDA tensors call the C-ABI directly (the torch dispatcher
+# plus a Python kernel costs ~20-40 us per op, comparable to the kernels themselves); CPU tensors go
+# through torch.ops so that the test-only oracle kernels are reachable.
+# ----------------------------------------------------------------------------------------------------
+def call(name, *args):
+    first = args[0]
+    if first.is_cuda:
+        return _DIRECT[name](*args)
+    return getattr(torch.ops.b200pose, name)(*args)
+
+
+_DIRECT = {"lm_poseinv_loss": _poseinv_loss, "lm_poseinv_trial": _poseinv_trial, "lm_reproj_accum": _reproj_accum,
+           "lm_solve6_retract": _solve6_retract, "lm_reproj_loss": _reproj_loss, "lm_reproj_residual": _reproj_residual}
+
 LM_OPS = ["lm_poseinv_loss", "lm_poseinv_trial", "lm_reproj_accum", "lm_solve6_retract", "lm_reproj_loss",
           "lm_reproj_residual"]
 ops = torch.ops.b200pose

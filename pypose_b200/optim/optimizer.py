@@ -194,24 +194,38 @@ class LevenbergMarquardt(_SecondOrder):
         return self._problem
 
     def _step_structured(self, prob, pg):
-        self.last = self.loss = self.loss if hasattr(self, 'loss') else prob.loss()
+        """Same control flow as the dense branch below (optimizer.py:659-680), driven by host floats that
+        come back from the device in ONE read per trial."""
+        cached = hasattr(self, 'loss')
+        if cached:
+            if getattr(self, '_loss_t', None) is not self.loss:      # loss was set / replaced from outside
+                self._loss_f = float(self.loss)
+            last_f = loss_f = self._loss_f
+            self.last = self.loss
         self.reject_count = 0
         scale = 1.0                       # cumulative diagonal multiplier: A_ii <- A_ii (1 + damping) per trial
         lin = prob.linearize()
-        while self.last <= self.loss:
+        first = True
+        while first or last_f <= loss_f:
             scale *= 1.0 + pg['damping']
-            trial_loss, predicted, failed = prob.trial(lin, scale, pg['min'], pg['max'])
-            if failed > 0:                # solver.py:214-215 -> optimizer.py:669-671
+            r = prob.trial(lin, scale, pg['min'], pg['max'])
+            if first and not cached:      # `self.last = self.loss = model.loss(...)` of the first ever step
+                last_f = loss_f = r["cur"]
+                self.last = self.loss = r["cur_t"]
+            first = False
+            if r["failed"] > 0:           # solver.py:214-215 -> optimizer.py:669-671
                 print('Cholesky decomposition failed. Check your matrix (may not be positive-definite)',
                       '\nLinear solver failed. Breaking optimization step...')
                 break
-            self.loss = trial_loss
-            self.strategy.update(pg, last=self.last, loss=self.loss, J=None, D=None, R=None, predicted=predicted)
-            if self.last < self.loss and self.reject_count < self.reject:
-                self.loss, self.reject_count = self.last, self.reject_count + 1     # parameters untouched
+            loss_f, self.loss = r["loss"], r["loss_t"]
+            self.strategy.update(pg, last=last_f, loss=loss_f, J=None, D=None, R=None, predicted=r["predicted"])
+            if last_f < loss_f and self.reject_count < self.reject:
+                loss_f, self.loss = last_f, self.last                # rejected: parameters untouched
+                self.reject_count += 1
             else:
                 prob.accept()
                 break
+        self._loss_f, self._loss_t = loss_f, self.loss
         return self.loss
 
     # -- reference (dense) route -----------------------------------------------------------------------

@@ -31,8 +31,20 @@ def _allreduce(t, group):
 
 
 class _Problem:
-    def _scalar(self, x):
-        return x.to(self.dtype)
+    """A structured problem exposes:
+         linearize()                      -> opaque state reused across the rejected trials of one step
+         trial(lin, scale, dmin, dmax)    -> dict(cur=float, loss=float, predicted=float, failed=float,
+                                                  cur_t=Tensor, loss_t=Tensor)    (ONE host sync)
+         accept()                         -> parameters <- trial parameters
+         loss()                           -> current loss (Tensor)
+    """
+
+    def _result(self, sums, order):
+        """sums: small fp64 device tensor; one D2H read gives every scalar the host control flow needs."""
+        vals = sums.tolist()
+        r = {k: vals[i] for k, i in order.items()}
+        r["cur_t"], r["loss_t"] = sums[order["cur"]].to(self.dtype), sums[order["loss"]].to(self.dtype)
+        return r
 
 
 class PoseInvProblem(_Problem):
@@ -49,16 +61,16 @@ class PoseInvProblem(_Problem):
 
     def loss(self):
         P, X = self._rows()
-        return self._scalar(_allreduce(ops.lm_poseinv_loss(P, X), self.group)[0])
+        return _allreduce(_fused.call("lm_poseinv_loss", P, X), self.group)[0].to(self.dtype)
 
     def linearize(self):
         return None         # everything lives in registers inside the trial kernel
 
     def trial(self, lin, scale, dmin, dmax):
         P, X = self._rows()
-        self._trial, sums = ops.lm_poseinv_trial(P, X, float(scale), float(dmin), float(dmax))
+        self._trial, sums = _fused.call("lm_poseinv_trial", P, X, float(scale), float(dmin), float(dmax))
         sums = _allreduce(sums, self.group)
-        return self._scalar(sums[1]), self._scalar(sums[2]), float(sums[3])
+        return self._result(sums, {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
 
     def accept(self):
         self.param.copy_(self._trial.view(self.param.shape))
@@ -79,23 +91,25 @@ class ReprojProblem(_Problem):
         return self.param.tensor().reshape(-1, 7)
 
     def loss(self):
-        s = ops.lm_reproj_loss(self._poses(), self.pts, self.pix, self.cidx)
-        return self._scalar(_allreduce(s, self.group)[0])
+        s = _fused.call("lm_reproj_loss", self._poses(), self.pts, self.pix, self.cidx)
+        return _allreduce(s, self.group)[0].to(self.dtype)
 
     def linearize(self):
-        H, g, s = ops.lm_reproj_accum(self._poses(), self.pts, self.pix, self.seg)
+        H, g, s = _fused.call("lm_reproj_accum", self._poses(), self.pts, self.pix, self.seg)
         if self.group is not None:
             packed = torch.cat([H.reshape(-1), g.reshape(-1)])      # one packed all-reduce per LM iteration
             _allreduce(packed, self.group)
             n = H.numel()
             H, g = packed[:n].view_as(H), packed[n:].view_as(g)
-        return H, g
+        return H, g, s
 
     def trial(self, lin, scale, dmin, dmax):
-        H, g = lin
-        self._trial, _, sums = ops.lm_solve6_retract(H, g, self._poses(), float(scale), float(dmin), float(dmax))
-        loss = _allreduce(ops.lm_reproj_loss(self._trial, self.pts, self.pix, self.cidx), self.group)
-        return self._scalar(loss[0]), self._scalar(sums[0]), float(sums[1])
+        H, g, cur = lin
+        self._trial, _, sums = _fused.call("lm_solve6_retract", H, g, self._poses(), float(scale), float(dmin), float(dmax))
+        tl = _fused.call("lm_reproj_loss", self._trial, self.pts, self.pix, self.cidx)
+        shard = torch.cat([cur, tl])                 # [current loss, trial loss] of this rank's residuals
+        shard = _allreduce(shard, self.group)
+        return self._result(torch.cat([shard, sums]), {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
 
     def accept(self):
         self.param.copy_(self._trial.view(self.param.shape))
