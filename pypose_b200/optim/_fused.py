@@ -56,7 +56,6 @@ torch.library.define(f"{NS}::lm_reproj_loss", "(Tensor poses, Tensor pts, Tensor
 torch.library.define(f"{NS}::lm_reproj_residual", "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx) -> Tensor")
 
 
-@torch.library.impl(f"{NS}::lm_poseinv_loss", "CUDA")
 def _poseinv_loss(P, X):
     P, X = _same(P, X)
     ws = _workspace(P.device)
@@ -64,7 +63,6 @@ def _poseinv_loss(P, X):
     return ws[:1].clone()
 
 
-@torch.library.impl(f"{NS}::lm_poseinv_trial", "CUDA")
 def _poseinv_trial(P, X, scale, dmin, dmax):
     P, X = _same(P, X)
     ws = _workspace(P.device)
@@ -73,7 +71,6 @@ def _poseinv_trial(P, X, scale, dmin, dmax):
     return Pt, ws[:4].clone()
 
 
-@torch.library.impl(f"{NS}::lm_reproj_accum", "CUDA")
 def _reproj_accum(poses, pts, pix, seg):
     poses, pts, pix = _same(poses, pts, pix)
     assert seg.dtype == torch.int32 and seg.numel() == poses.shape[0] + 1
@@ -85,7 +82,6 @@ def _reproj_accum(poses, pts, pix, seg):
     return H, g, ws[:1].clone()
 
 
-@torch.library.impl(f"{NS}::lm_solve6_retract", "CUDA")
 def _solve6_retract(H, g, P, scale, dmin, dmax):
     H, g, P = _same(H, g, P)
     ws = _workspace(P.device)
@@ -94,7 +90,6 @@ def _solve6_retract(H, g, P, scale, dmin, dmax):
     return Pt, D, ws[:2].clone()
 
 
-@torch.library.impl(f"{NS}::lm_reproj_loss", "CUDA")
 def _reproj_loss(poses, pts, pix, cidx):
     poses, pts, pix = _same(poses, pts, pix)
     assert cidx.dtype == torch.int32
@@ -103,13 +98,20 @@ def _reproj_loss(poses, pts, pix, cidx):
     return ws[:1].clone()
 
 
-@torch.library.impl(f"{NS}::lm_reproj_residual", "CUDA")
 def _reproj_residual(poses, pts, pix, cidx):
     poses, pts, pix = _same(poses, pts, pix)
     assert cidx.dtype == torch.int32
     r = torch.empty(pts.shape[0], 2, dtype=poses.dtype, device=poses.device)
     _launch("b200_lm_reproj_residual", poses, [_p(poses), _p(pts), _p(pix), _p(cidx), _p(r)], pts.shape[0])
     return r
+
+
+torch.library.impl(f"{NS}::lm_poseinv_loss", "CUDA")(_poseinv_loss)
+torch.library.impl(f"{NS}::lm_poseinv_trial", "CUDA")(_poseinv_trial)
+torch.library.impl(f"{NS}::lm_reproj_accum", "CUDA")(_reproj_accum)
+torch.library.impl(f"{NS}::lm_solve6_retract", "CUDA")(_solve6_retract)
+torch.library.impl(f"{NS}::lm_reproj_loss", "CUDA")(_reproj_loss)
+torch.library.impl(f"{NS}::lm_reproj_residual", "CUDA")(_reproj_residual)
 
 
 # ----------------------------------------------------------------------------------------------------
