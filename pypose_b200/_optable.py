@@ -144,10 +144,14 @@ SCAN_OPS = [
       ("const REAL*", "rot", "(B,F,4) known rotations or NULL"), ("const REAL*", "init_rot", "(B,4) / (1,4) or NULL"),
       ("long long", "init_stride", "4 for per-sequence init_rot, 0 to broadcast one"),
       ("const REAL*", "gravity3_host", "HOST pointer to the 3 gravity components"),
-      ("REAL*", "a", "(B,F,3)"), ("REAL*", "Dp", "(B,F,3)"), ("REAL*", "Dv", "(B,F,3)"), ("REAL*", "Dr", "(B,F,4)"),
-      ("REAL*", "Dt", "(B,F,1)"), ("REAL*", "w", "(B,F,4)"), ("long long", "B", "trajectories"),
+      ("REAL*", "a", "(B,F,3) or NULL to skip all six integrate outputs"), ("REAL*", "Dp", "(B,F,3)"),
+      ("REAL*", "Dv", "(B,F,3)"), ("REAL*", "Dr", "(B,F,4)"), ("REAL*", "Dt", "(B,F,1)"), ("REAL*", "w", "(B,F,4)"),
+      ("const REAL*", "init_pos", "(B,3) / (1,3) or NULL"), ("const REAL*", "init_vel", "(B,3) / (1,3) or NULL"),
+      ("long long", "pv_stride", "3 per-sequence, 0 broadcast"),
+      ("REAL*", "rot_out", "(B,F,4) predicted rotation or NULL to skip the three predict outputs"),
+      ("REAL*", "vel_out", "(B,F,3)"), ("REAL*", "pos_out", "(B,F,3)"), ("long long", "B", "trajectories"),
       ("long long", "F", "samples per trajectory")],
-     "IMUPreintegrator.integrate, pypose/module/imu_preintegrator.py:314-384"),
+     "IMUPreintegrator.integrate + .predict, pypose/module/imu_preintegrator.py:314-384, 386-426"),
 ]
 
 

@@ -165,15 +165,23 @@ template <typename T, int CH>
 __global__ void __launch_bounds__(kScanThreads) imu_integrate_kernel(
     const T* __restrict__ dt, const T* __restrict__ gyro, const T* __restrict__ acc, const T* __restrict__ rot,
     const T* __restrict__ init_rot, long long init_stride, T gx, T gy, T gz, T* __restrict__ a_out, T* __restrict__ Dp,
-    T* __restrict__ Dv, T* __restrict__ Dr, T* __restrict__ Dt, T* __restrict__ w_out, long long F) {
+    T* __restrict__ Dv, T* __restrict__ Dr, T* __restrict__ Dt, T* __restrict__ w_out, const T* __restrict__ init_pos,
+    const T* __restrict__ init_vel, long long pv_stride, T* __restrict__ rot_o, T* __restrict__ vel_o,
+    T* __restrict__ pos_o, long long F) {
   __shared__ T sh[(kScanThreads / 32) * 8];
   const long long b = blockIdx.x;
   dt += b * F; gyro += b * F * 3; acc += b * F * 3;
   if (rot) rot += b * F * 4;
-  a_out += b * F * 3; Dp += b * F * 3; Dv += b * F * 3; Dr += b * F * 4; Dt += b * F; w_out += b * F * 4;
+  // every output is optional: the integrate outputs (imu_preintegrator.py:383-384) and/or the predicted
+  // states rot = R0 Dr, vel = v0 + R0 Dv, pos = p0 + R0 Dp + v0 Dt (imu_preintegrator.py:422-426)
+  if (a_out) { a_out += b * F * 3; Dp += b * F * 3; Dv += b * F * 3; Dr += b * F * 4; Dt += b * F; w_out += b * F * 4; }
+  if (rot_o) { rot_o += b * F * 4; vel_o += b * F * 3; pos_o += b * F * 3; }
   const V3<T> grav = mk(gx, gy, gz);
   Elem<T> R0 = elem_identity<T>();
   if (init_rot) R0.q = ldq(init_rot + b * init_stride);
+  V3<T> p0 = mk(T(0), T(0), T(0)), v0 = p0;
+  if (init_pos) p0 = ld3(init_pos + b * pv_stride);
+  if (init_vel) v0 = ld3(init_vel + b * pv_stride);
   Elem<T> carryR = elem_identity<T>();
   Vpt<T> carry = vpt_identity<T>();
   constexpr long long TILE = (long long)kScanThreads * CH;
@@ -214,9 +222,12 @@ __global__ void __launch_bounds__(kScanThreads) imu_integrate_kernel(
         const V3<T> Ra = qrot(Rbefore.q, ak);
         Vpt<T> e; e.v = dts[c] * Ra; e.p = (T(0.5) * dts[c] * dts[c]) * Ra; e.t = dts[c];
         vrun = vpt_combine(vrun, e);
-        st3(a_out + k * 3, ak);
-        stq(Dr + k * 4, Rafter.q);
-        stq(w_out + k * 4, drs[c].q);
+        if (a_out) {
+          st3(a_out + k * 3, ak);
+          stq(Dr + k * 4, Rafter.q);
+          stq(w_out + k * 4, drs[c].q);
+        }
+        if (rot_o) stq(rot_o + k * 4, qmul(R0.q, Rafter.q));
       }
       vloc[c] = vrun;
     }
@@ -227,9 +238,15 @@ __global__ void __launch_bounds__(kScanThreads) imu_integrate_kernel(
       if (first + c < F) {
         const long long k = first + c;
         const Vpt<T> y = vpt_combine(preV, vloc[c]);
-        st3(Dv + k * 3, y.v);
-        st3(Dp + k * 3, y.p);
-        Dt[k] = y.t;
+        if (a_out) {
+          st3(Dv + k * 3, y.v);
+          st3(Dp + k * 3, y.p);
+          Dt[k] = y.t;
+        }
+        if (rot_o) {
+          st3(vel_o + k * 3, v0 + qrot(R0.q, y.v));
+          st3(pos_o + k * 3, p0 + qrot(R0.q, y.p) + y.t * v0);
+        }
       }
     }
     carryR = g_mul<SO3g, T>(carryR, totR);
@@ -256,11 +273,13 @@ SCAN_ABI(Sim3, Sim3g)
 #define IMU_ABI(SFX, CT, CH)                                                                                           \
   B200_EXPORT int b200_imu_integrate_##SFX(const CT* dt, const CT* gyro, const CT* acc, const CT* rot,                 \
                                            const CT* init_rot, long long init_stride, const CT* gravity3_host, CT* a,  \
-                                           CT* Dp, CT* Dv, CT* Dr, CT* Dt, CT* w, long long B, long long F, void* s) { \
+                                           CT* Dp, CT* Dv, CT* Dr, CT* Dt, CT* w, const CT* init_pos,                  \
+                                           const CT* init_vel, long long pv_stride, CT* rot_out, CT* vel_out,          \
+                                           CT* pos_out, long long B, long long F, void* s) {                           \
     if (B <= 0 || F <= 0) return 0;                                                                                    \
     imu_integrate_kernel<CT, CH><<<(unsigned)B, kScanThreads, 0, (cudaStream_t)s>>>(                                   \
         dt, gyro, acc, rot, init_rot, init_stride, gravity3_host[0], gravity3_host[1], gravity3_host[2], a, Dp, Dv,    \
-        Dr, Dt, w, F);                                                                                                 \
+        Dr, Dt, w, init_pos, init_vel, pv_stride, rot_out, vel_out, pos_out, F);                                       \
     return (int)cudaGetLastError();                                                                                    \
   }
 IMU_ABI(f32, float, 4)

@@ -10,6 +10,9 @@ torch.library.define(f"{NS}::cumprod", "(Tensor x, str group, bool left) -> Tens
 torch.library.define(f"{NS}::imu_integrate",
                      "(Tensor dt, Tensor gyro, Tensor acc, Tensor? rot, Tensor? init_rot, float[] gravity) -> "
                      "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
+torch.library.define(f"{NS}::imu_predict",
+                     "(Tensor dt, Tensor gyro, Tensor acc, Tensor? rot, Tensor init_rot, Tensor init_pos, Tensor init_vel, "
+                     "float[] gravity) -> (Tensor, Tensor, Tensor)")
 
 
 def _p(t):
@@ -30,28 +33,50 @@ def _cumprod_cuda(x, group, left):
     return out
 
 
-@torch.library.impl(f"{NS}::imu_integrate", "CUDA")
-def _imu_cuda(dt, gyro, acc, rot, init_rot, gravity):
+def _imu_launch(dt, gyro, acc, rot, init_rot, gravity, want_inte, init_pos=None, init_vel=None):
     dt, gyro, acc = dt.contiguous(), gyro.contiguous(), acc.contiguous()
     B, F = dt.shape[:2]
     dtype, dev = dt.dtype, dt.device
     rot = None if rot is None else rot.to(dtype).expand(B, F, 4).contiguous()
-    stride = 0
-    if init_rot is not None:
-        init_rot = init_rot.to(dtype).reshape(-1, 4).contiguous()
-        assert init_rot.shape[0] in (1, B), "init_rot must be (1,1,4) or (B,1,4)"
-        stride = 4 if init_rot.shape[0] == B and B > 1 else 0
+
+    def per_seq(t, w):
+        if t is None:
+            return None, 0
+        t = t.to(dtype).reshape(-1, w).contiguous()
+        assert t.shape[0] in (1, B), f"initial state must have batch 1 or {B}"
+        return t, (w if t.shape[0] == B and B > 1 else 0)
+
+    init_rot, rstride = per_seq(init_rot, 4)
+    init_pos, pstride = per_seq(init_pos, 3)
+    init_vel, vstride = per_seq(init_vel, 3)
+    if init_pos is not None and pstride != vstride:     # one stride for both: expand the broadcast one
+        init_pos, init_vel = init_pos.expand(B, 3).contiguous(), init_vel.expand(B, 3).contiguous()
+        pstride = 3
     new = lambda w: torch.empty(B, F, w, dtype=dtype, device=dev)
-    a, Dp, Dv, Dr, Dt, w = new(3), new(3), new(3), new(4), new(1), new(4)
-    if B * F == 0:
-        return a, Dp, Dv, Dr, Dt, w
-    cty = ctypes.c_float if dtype == torch.float32 else ctypes.c_double
-    g = (cty * 3)(*[float(v) for v in gravity])
-    sym = f"b200_imu_integrate_{_C.suffix(dtype)}"
-    with torch.cuda.device(dev):
-        _C.check(_C.fn(sym)(_p(dt), _p(gyro), _p(acc), _p(rot), _p(init_rot), stride, ctypes.cast(g, ctypes.c_void_p),
-                            _p(a), _p(Dp), _p(Dv), _p(Dr), _p(Dt), _p(w), B, F, _C.stream_ptr(dev)), sym)
-    return a, Dp, Dv, Dr, Dt, w
+    inte = (new(3), new(3), new(3), new(4), new(1), new(4)) if want_inte else (None,) * 6
+    pred = (new(4), new(3), new(3)) if init_pos is not None else (None,) * 3
+    if B * F:
+        cty = ctypes.c_float if dtype == torch.float32 else ctypes.c_double
+        g = (cty * 3)(*[float(v) for v in gravity])
+        sym = f"b200_imu_integrate_{_C.suffix(dtype)}"
+        with torch.cuda.device(dev):
+            _C.check(_C.fn(sym)(_p(dt), _p(gyro), _p(acc), _p(rot), _p(init_rot), rstride, ctypes.cast(g, ctypes.c_void_p),
+                                *[_p(t) for t in inte], _p(init_pos), _p(init_vel), pstride, *[_p(t) for t in pred],
+                                B, F, _C.stream_ptr(dev)), sym)
+    return inte, pred
+
+
+def _imu_cuda(dt, gyro, acc, rot, init_rot, gravity):
+    return _imu_launch(dt, gyro, acc, rot, init_rot, gravity, True)[0]
+
+
+def _imu_predict_cuda(dt, gyro, acc, rot, init_rot, init_pos, init_vel, gravity):
+    """integrate + predict in one launch; only rot / vel / pos are written (80 B/sample instead of 224)."""
+    return _imu_launch(dt, gyro, acc, rot, init_rot, gravity, False, init_pos, init_vel)[1]
+
+
+torch.library.impl(f"{NS}::imu_integrate", "CUDA")(_imu_cuda)
+torch.library.impl(f"{NS}::imu_predict", "CUDA")(_imu_predict_cuda)
 
 
 def try_cumprod(input, dim, left):

@@ -49,6 +49,17 @@ class IMUPreintegrator(nn.Module):
         B = dt.shape[0]
         if init_state is None:
             init_state = {'pos': self.pos, 'rot': self.rot, 'vel': self.vel}
+        if not self.prop_cov:
+            # integrate + predict fused: nothing but the predicted states leaves the kernel
+            rot_t = rot.tensor() if isinstance(rot, LieTensor) else None
+            r, v, p = torch.ops.b200pose.imu_predict(
+                dt, gyro.to(dt.dtype), acc.to(dt.dtype), rot_t, init_state['rot'].tensor(), init_state['pos'],
+                init_state['vel'], [0.0, 0.0, self._g])
+            predict = {'rot': SO3(r), 'vel': v, 'pos': p}
+            if not self.reset:
+                self.pos, self.rot, self.vel = p[..., -1:, :], predict['rot'][..., -1:, :], v[..., -1:, :]
+                self.cov = None
+            return {**predict, 'cov': None}
         inte = self.integrate(dt, gyro, acc, rot=rot, init_rot=init_state['rot'])
         predict = self.predict(init_state, inte)
         if self.prop_cov:

@@ -127,8 +127,21 @@ def _install_cpu_oracle_scan_kernels():
         outs = S.imu_integrate(n(dt), n(gyro), n(acc), r, n(init_rot), gravity)
         return tuple(torch.from_numpy(np.ascontiguousarray(o)).to(dt.dtype) for o in outs)
 
+    def imu_predict(dt, gyro, acc, rot, init_rot, init_pos, init_vel, gravity):
+        a, Dp, Dv, Dr, Dt, w = imu(dt, gyro, acc, rot, init_rot, gravity)
+        from oracle import lie_oracle as O
+        B, F = dt.shape[:2]
+        R0 = np.broadcast_to(init_rot.detach().double().numpy().reshape(-1, 1, 4), (B, F, 4))
+        p0 = init_pos.detach().double().numpy().reshape(-1, 1, 3)
+        v0 = init_vel.detach().double().numpy().reshape(-1, 1, 3)
+        rot_o = O.SO3_mul(R0, Dr.double().numpy())
+        vel_o = v0 + O.SO3_act(R0, Dv.double().numpy())
+        pos_o = p0 + O.SO3_act(R0, Dp.double().numpy()) + v0 * Dt.double().numpy()
+        return tuple(torch.from_numpy(np.ascontiguousarray(o)).to(dt.dtype) for o in (rot_o, vel_o, pos_o))
+
     torch.library.impl("b200pose::cumprod", "CPU")(cumprod)
     torch.library.impl("b200pose::imu_integrate", "CPU")(imu)
+    torch.library.impl("b200pose::imu_predict", "CPU")(imu_predict)
 
 
 _install_cpu_oracle_scan_kernels()

@@ -75,6 +75,13 @@ def _check_imu_module(golden_scan, dev, tol):
         for k in ("rot", "vel", "pos", "cov"):
             v = out[k].tensor() if isinstance(out[k], pp.LieTensor) else out[k]
             np.testing.assert_allclose(v.cpu().numpy(), g[f"imu/{tag}/out/{k}"], atol=tol, rtol=tol, err_msg=f"{tag}/{k}")
+        # fused integrate+predict path (prop_cov=False)
+        m2 = pp.module.IMUPreintegrator(prop_cov=False, reset=True).double().to(dev)
+        out2 = m2(t("imu/dt"), t("imu/gyro"), t("imu/acc"), init_state=init, **kw)
+        for k in ("rot", "vel", "pos"):
+            v = out2[k].tensor() if isinstance(out2[k], pp.LieTensor) else out2[k]
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"imu/{tag}/out/{k}"], atol=tol, rtol=tol, err_msg=f"fused {tag}/{k}")
+        assert out2["cov"] is None
 
 
 def test_imu_module_cpu(golden_scan):
