@@ -28,6 +28,33 @@ def _triu_unpack(H21):
     return A
 
 
+# ------------------------------------------------------------------ robust kernels + FastTriggs
+def robust(kind, delta, x):
+    """rho(x), rho'(x) for pypose/optim/kernel.py (Huber :5-45, PseudoHuber :48-86, Cauchy :89-126,
+    SoftLOne :129-168, Arctan :171-207, Scale :258-297); FastTriggs scales R and J rows by sqrt(rho')
+    (corrector.py:73-95)."""
+    d2 = delta * delta
+    with np.errstate(all="ignore"):
+        if kind == 1:
+            root = np.sqrt(x)
+            return np.where(root < delta, x, 2 * delta * root - d2), np.where(root < delta, 1.0, delta / root)
+        if kind == 2:
+            q = np.sqrt(x / d2 + 1)
+            return 2 * d2 * (q - 1), 1 / q
+        if kind == 3:
+            q = x / d2 + 1
+            return d2 * np.log(q), 1 / q
+        if kind == 4:
+            q = np.sqrt(1 / d2 + x)
+            return 2 * (delta * q - 1), delta / q
+        if kind == 5:
+            q = x / d2
+            return d2 * np.arctan(q), 1 / (1 + q * q)
+        if kind == 6:
+            return delta * x, np.full_like(x, delta)
+    return x, np.ones_like(x)
+
+
 # ------------------------------------------------------------------ PoseInv: r = Log(P X)
 def poseinv_residual(P, X):
     return O.log("SE3", O.mul("SE3", P, X))
@@ -57,18 +84,19 @@ def retract(D, P):
     return O.mul("SE3", O.exp("SE3", D), P)
 
 
-def poseinv_loss(P, X):
-    return np.array([(poseinv_residual(P, X) ** 2).sum()])
+def poseinv_loss(P, X, kind=0, delta=1.0):
+    return np.array([robust(kind, delta, (poseinv_residual(P, X) ** 2).sum(-1))[0].sum()])
 
 
-def poseinv_trial(P, X, scale, dmin, dmax):
+def poseinv_trial(P, X, scale, dmin, dmax, kind=0, delta=1.0):
     r, J = poseinv_jac_blocks(P, X)
-    A = np.swapaxes(J, -1, -2) @ J
-    g = (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0]
+    rho, w = robust(kind, delta, (r ** 2).sum(-1))
+    A = np.swapaxes(J, -1, -2) @ J * w[:, None, None]
+    g = (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0] * w[:, None]
     D, pred = damped_solve(A, g, scale, dmin, dmax)
     Pt = retract(D, P)
-    rt = poseinv_residual(Pt, X)
-    return Pt, np.array([(r ** 2).sum(), (rt ** 2).sum(), pred.sum(), 0.0])
+    rho_t, _ = robust(kind, delta, (poseinv_residual(Pt, X) ** 2).sum(-1))
+    return Pt, np.array([rho.sum(), rho_t.sum(), pred.sum(), 0.0])
 
 
 # ------------------------------------------------------------------ Reproj: r = pi(T p) - z
@@ -90,16 +118,17 @@ def reproj_jac_rows(poses, pts, cidx):
     return dpi @ dy
 
 
-def reproj_accum(poses, pts, pix, seg):
+def reproj_accum(poses, pts, pix, seg, kind=0, delta=1.0):
     C = poses.shape[0]
     cidx = np.repeat(np.arange(C), np.diff(seg))
     r = reproj_residual(poses, pts, pix, cidx)
     J = reproj_jac_rows(poses, pts, cidx)
+    rho, w = robust(kind, delta, (r ** 2).sum(-1))
     A = np.zeros((C, 6, 6))
     g = np.zeros((C, 6))
-    np.add.at(A, cidx, np.swapaxes(J, -1, -2) @ J)
-    np.add.at(g, cidx, (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0])
-    return _triu_pack(A), g, np.array([(r ** 2).sum()])
+    np.add.at(A, cidx, np.swapaxes(J, -1, -2) @ J * w[:, None, None])
+    np.add.at(g, cidx, (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0] * w[:, None])
+    return _triu_pack(A), g, np.array([rho.sum()])
 
 
 def solve6_retract(H21, g, P, scale, dmin, dmax):
@@ -107,8 +136,8 @@ def solve6_retract(H21, g, P, scale, dmin, dmax):
     return retract(D, P), D, np.array([pred.sum(), 0.0])
 
 
-def reproj_loss(poses, pts, pix, cidx):
-    return np.array([(reproj_residual(poses, pts, pix, cidx) ** 2).sum()])
+def reproj_loss(poses, pts, pix, cidx, kind=0, delta=1.0):
+    return np.array([robust(kind, delta, (reproj_residual(poses, pts, pix, cidx) ** 2).sum(-1))[0].sum()])
 
 
 # ------------------------------------------------------------------ the dense reference algorithm

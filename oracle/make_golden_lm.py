@@ -86,6 +86,34 @@ def main():
         init.numpy().copy(), pts.numpy().copy(), pix.numpy().copy(), cidx.numpy().copy())
     losses, poses, rej = run(Reproj(init.clone()), (pts, pix, cidx), ref.optim.strategy.TrustRegion(), 6, "poses")
     g["reproj_hard/trustregion/loss"], g["reproj_hard/trustregion/poses"], g["reproj_hard/trustregion/reject"] = losses, poses, rej
+    # robust kernels (default FastTriggs corrector): reprojection with 10 % gross outliers under Huber,
+    # PoseInv under Cauchy (optimizer.py:474-480, corrector.py:73-95, kernel.py)
+    torch.manual_seed(3)
+    gt = ref.randn_SE3(C, sigma=0.2, dtype=torch.float64)
+    pts_cam = torch.rand(M, 3, dtype=torch.float64) * 4 + torch.tensor([-2.0, -2.0, 2.0])
+    pts = gt[cidx].Inv().Act(pts_cam)
+    pix = -pts_cam[:, :2] / pts_cam[:, 2:]
+    pix[::10] += 0.5 * torch.randn(M // 10, 2, dtype=torch.float64)
+    init = ref.se3(0.05 * torch.randn(C, 6, dtype=torch.float64)).Exp() * gt
+    g["robust_reproj/poses0"], g["robust_reproj/pts"], g["robust_reproj/pix"], g["robust_reproj/cidx"] = (
+        init.numpy().copy(), pts.numpy().copy(), pix.numpy().copy(), cidx.numpy().copy())
+    for kname, kern in (("huber", lambda: ref.optim.kernel.Huber(delta=0.05)), ("cauchy", lambda: ref.optim.kernel.Cauchy(delta=0.1)),
+                        ("pseudohuber", lambda: ref.optim.kernel.PseudoHuber(delta=0.05)),
+                        ("softlone", lambda: ref.optim.kernel.SoftLOne(delta=0.1)), ("arctan", lambda: ref.optim.kernel.Arctan(delta=0.3))):
+        model = Reproj(init.clone())
+        opt = ref.optim.LM(model, strategy=ref.optim.strategy.TrustRegion(), kernel=kern())
+        losses, poses, rej = [], [], []
+        for _ in range(5):
+            losses.append(float(opt.step((pts, pix, cidx))))
+            poses.append(model.poses.detach().clone().numpy()); rej.append(opt.reject_count)
+        g[f"robust_reproj/{kname}/loss"], g[f"robust_reproj/{kname}/poses"], g[f"robust_reproj/{kname}/reject"] = (
+            np.array(losses), np.stack(poses), np.array(rej))
+    net = InvNet(P0.clone())
+    opt = ref.optim.LM(net, strategy=ref.optim.strategy.Constant(damping=1e-4), kernel=ref.optim.kernel.Cauchy(delta=0.5))
+    losses, poses = [], []
+    for _ in range(4):
+        losses.append(float(opt.step(X))); poses.append(net.pose.detach().clone().numpy())
+    g["poseinv/cauchy/loss"], g["poseinv/cauchy/poses"] = np.array(losses), np.stack(poses)
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, {k: (v if v.ndim == 1 and v.size <= 4 else v.shape) for k, v in g.items() if "loss" in k or "reject" in k})
 

@@ -89,20 +89,20 @@ def lie_symbols():
 LM_OPS = [
     ("b200_lm_poseinv_loss",
      [("const REAL*", "P", "(n,7) SE3 parameters"), ("const REAL*", "X", "(n,7) SE3 inputs"),
-      ("double*", "ws", "workspace; ws[0] = sum |Log(P X)|^2")],
+      ("double*", "ws", "workspace; ws[0] = sum rho(|Log(P X)|^2)"), ("int", "robust", "0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale (optim/kernel.py) with FastTriggs scaling"), ("double", "delta", "kernel parameter")],
      "RobustModel.loss of the README InvNet model, pypose/optim/optimizer.py:118-125 + README.md:120-129"),
     ("b200_lm_poseinv_trial",
      [("const REAL*", "P", "(n,7)"), ("const REAL*", "X", "(n,7)"), ("REAL*", "P_trial", "(n,7) Exp(D) P"),
       ("double*", "ws", "ws[0..3] = loss, trial loss, (JD)^T(2R+JD), failed pivots"),
       ("double", "scale", "prod(1+damping) over trials"), ("double", "dmin", "diag clamp min"),
-      ("double", "dmax", "diag clamp max")],
+      ("double", "dmax", "diag clamp max"), ("int", "robust", "0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale (optim/kernel.py) with FastTriggs scaling"), ("double", "delta", "kernel parameter")],
      "one LevenbergMarquardt trial: modjac + J^T J + clamp/damp + Cholesky + update + loss, "
      "pypose/optim/optimizer.py:645-673, optim/solver.py:213-216, lietensor/lietensor.py:442-444"),
     ("b200_lm_reproj_accum",
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3) sorted by camera"),
       ("const REAL*", "pix", "(m,2)"), ("const int*", "seg", "(ncam+1) row offsets per camera"),
       ("REAL*", "H", "(ncam,21) upper triangles of J^T J"), ("REAL*", "g", "(ncam,6) J^T r"),
-      ("double*", "ws", "ws[0] = sum |r|^2")],
+      ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale (optim/kernel.py) with FastTriggs scaling"), ("double", "delta", "kernel parameter")],
      "J^T J / J^T R assembly of optimizer.py:655-656 for r = pi(T p) - z (README.md:170-178)"),
     ("b200_lm_solve6_retract",
      [("const REAL*", "H", "(n,21)"), ("const REAL*", "g", "(n,6)"), ("const REAL*", "P", "(n,7)"),
@@ -112,7 +112,7 @@ LM_OPS = [
      "diag clamp (optimizer.py:657) + damping (:666) + Cholesky solve (solver.py:213-216) + p.add_ (:139-140)"),
     ("b200_lm_reproj_loss",
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),
-      ("const int*", "cidx", "(m) camera of each row"), ("double*", "ws", "ws[0] = sum |r|^2")],
+      ("const int*", "cidx", "(m) camera of each row"), ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale (optim/kernel.py) with FastTriggs scaling"), ("double", "delta", "kernel parameter")],
      "model.loss after the update, optimizer.py:673"),
     ("b200_lm_reproj_residual",
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),

@@ -84,13 +84,15 @@ template <typename T> __device__ __forceinline__ Elem<T> load_se3(const T* p) { 
 // loss = sum_i |Log(P_i X_i)|^2     (RobustModel.loss with the trivial kernel, optimizer.py:118-125)
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_poseinv_loss_kernel(const T* __restrict__ P, const T* __restrict__ X,
-                                                                      double* ws, long long n) {
+                                                                      double* ws, int rk, T rdelta, long long n) {
   double acc[1] = {0.0};
   for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
     T p[7], x[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) { p[k] = P[i * 7 + k]; x[k] = X[i * 7 + k]; }
-    acc[0] += (double)tang6_sqnorm(poseinv_residual(load_se3(p), load_se3(x)));
+    T rho, w;
+    robust_eval(rk, rdelta, tang6_sqnorm(poseinv_residual(load_se3(p), load_se3(x))), rho, w);
+    acc[0] += (double)rho;
   }
   reduce_sums<1>(acc, ws);
 }
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_poseinv_loss_kernel(const T* __
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_poseinv_trial_kernel(const T* __restrict__ P, const T* __restrict__ X,
                                                                        T* __restrict__ Pt, double* ws, T scale, T dmin,
-                                                                       T dmax, long long n) {
+                                                                       T dmax, int rk, T rdelta, long long n) {
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
     T p[7], x[7];
@@ -111,6 +113,9 @@ __global__ void __launch_bounds__(kLmThreads) lm_poseinv_trial_kernel(const T* _
     Tang<T> r;
     Sys6<T> s;
     poseinv_linearize(Pe, Xe, r, s);
+    T rho0, w0, rho1, w1;
+    robust_eval(rk, rdelta, tang6_sqnorm(r), rho0, w0);
+    if (rk) sys6_scale(s, w0);
     T D[6], pred;
     const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
     const Elem<T> Pn = se3_retract(D, Pe);
@@ -118,8 +123,9 @@ __global__ void __launch_bounds__(kLmThreads) lm_poseinv_trial_kernel(const T* _
     store_elem<SE3g, T>(o, Pn);
 #pragma unroll
     for (int k = 0; k < 7; ++k) Pt[i * 7 + k] = o[k];
-    acc[0] += (double)tang6_sqnorm(r);
-    acc[1] += (double)tang6_sqnorm(poseinv_residual(Pn, Xe));
+    robust_eval(rk, rdelta, tang6_sqnorm(poseinv_residual(Pn, Xe)), rho1, w1);
+    acc[0] += (double)rho0;
+    acc[1] += (double)rho1;
     acc[2] += (double)pred;
     acc[3] += ok ? 0.0 : 1.0;
   }
@@ -137,7 +143,7 @@ template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
                                                                       const T* __restrict__ pix, const int* __restrict__ seg,
                                                                       T* __restrict__ H, T* __restrict__ g, double* ws,
-                                                                      int ncam) {
+                                                                      int rk, T rdelta, int ncam) {
   const int lane = threadIdx.x & 31;
   const int wpb = kLmThreads / 32;
   double acc[1] = {0.0};
@@ -157,9 +163,17 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __
       reproj_residual(Tc, p, pix[(long long)k * 2], pix[(long long)k * 2 + 1], rx, ry, y);
       T j0[6], j1[6];
       reproj_rows(y, j0, j1);
+      T rho, w;
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      if (rk) {                      // FastTriggs: rows and residual scaled by sqrt(rho')
+        const T sw = m_sqrt(w);
+        rx *= sw; ry *= sw;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+      }
       sys6_add_row(s, j0, rx);
       sys6_add_row(s, j1, ry);
-      loss += rx * rx + ry * ry;
+      loss += rho;
     }
     // warp reduction of 21 + 6 + 1 values
 #pragma unroll
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_solve6_retract_kernel(const T* 
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_reproj_loss_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
                                                                      const T* __restrict__ pix, const int* __restrict__ cidx,
-                                                                     double* ws, long long m) {
+                                                                     double* ws, int rk, T rdelta, long long m) {
   double acc[1] = {0.0};
   for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
     const int c = cidx[k];
@@ -236,7 +250,9 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_loss_kernel(const T* __r
     T rx, ry;
     V3<T> y;
     reproj_residual(load_se3(pr), p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
-    acc[0] += (double)(rx * rx + ry * ry);
+    T rho, w;
+    robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+    acc[0] += (double)rho;
   }
   reduce_sums<1>(acc, ws);
 }
@@ -276,23 +292,27 @@ using namespace b200pose;
 B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kMaxSums * 8 * 1024; }
 
 #define LM_ABI(SFX, CT)                                                                                               \
-  B200_EXPORT int b200_lm_poseinv_loss_##SFX(const CT* P, const CT* X, double* ws, long long n, void* stream) {        \
+  B200_EXPORT int b200_lm_poseinv_loss_##SFX(const CT* P, const CT* X, double* ws, int robust, double delta,          \
+                                             long long n, void* stream) {                                             \
     if (n <= 0) return 0;                                                                                             \
-    lm_poseinv_loss_kernel<CT><<<lm_grid(n, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(P, X, ws, n);         \
+    lm_poseinv_loss_kernel<CT><<<lm_grid(n, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(P, X, ws, robust,     \
+                                                                                                (CT)delta, n);        \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_poseinv_trial_##SFX(const CT* P, const CT* X, CT* P_trial, double* ws, double scale,        \
-                                              double dmin, double dmax, long long n, void* stream) {                  \
+                                              double dmin, double dmax, int robust, double delta, long long n,        \
+                                              void* stream) {                                                         \
     if (n <= 0) return 0;                                                                                             \
     lm_poseinv_trial_kernel<CT><<<lm_grid(n, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                     \
-        P, X, P_trial, ws, (CT)scale, (CT)dmin, (CT)dmax, n);                                                         \
+        P, X, P_trial, ws, (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta, n);                                      \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_reproj_accum_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* seg, CT* H,    \
-                                             CT* g, double* ws, long long ncam, void* stream) {                       \
+                                             CT* g, double* ws, int robust, double delta, long long ncam,             \
+                                             void* stream) {                                                          \
     if (ncam <= 0) return 0;                                                                                          \
     lm_reproj_accum_kernel<CT><<<lm_grid(ncam, kLmThreads / 32), kLmThreads, 0, (cudaStream_t)stream>>>(              \
-        poses, pts, pix, seg, H, g, ws, (int)ncam);                                                                   \
+        poses, pts, pix, seg, H, g, ws, robust, (CT)delta, (int)ncam);                                                \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_solve6_retract_##SFX(const CT* H, const CT* g, const CT* P, CT* P_trial, CT* D, double* ws, \
@@ -303,10 +323,10 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_reproj_loss_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* cidx,           \
-                                            double* ws, long long m, void* stream) {                                  \
+                                            double* ws, int robust, double delta, long long m, void* stream) {        \
     if (m <= 0) return 0;                                                                                             \
-    lm_reproj_loss_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(poses, pts, pix, cidx, \
-                                                                                               ws, m);                \
+    lm_reproj_loss_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                       \
+        poses, pts, pix, cidx, ws, robust, (CT)delta, m);                                                             \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_reproj_residual_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* cidx,       \

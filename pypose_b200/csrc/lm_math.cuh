@@ -142,6 +142,52 @@ template <typename T> LM_HD bool sys6_damped_solve(const Sys6<T>& s, T scale, T 
   return ok;
 }
 
+// ---------------------------------------------------------------- robust kernels (optim/kernel.py) + FastTriggs
+// rho(x) on x = |r|^2 and its derivative w = rho'(x).  FastTriggs (optim/corrector.py:73-95) scales the
+// residual and its Jacobian rows by sqrt(w), i.e. J^T J and J^T r by w; the loss is sum rho(x) (optimizer.py:118-125).
+// kind: 0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale
+template <typename T> LM_HD void robust_eval(int kind, T delta, T x, T& rho, T& w) {
+  const T d2 = delta * delta;
+  switch (kind) {
+    case 1: {                                   // kernel.py:5-45
+      const T root = m_sqrt(x);
+      const bool in = root < delta;
+      rho = in ? x : T(2) * delta * root - d2;
+      w = in ? T(1) : delta / root;
+    } break;
+    case 2: {                                   // kernel.py:48-86
+      const T q = m_sqrt(x / d2 + T(1));
+      rho = T(2) * d2 * (q - T(1));
+      w = T(1) / q;
+    } break;
+    case 3: {                                   // kernel.py:89-126
+      const T q = x / d2 + T(1);
+      rho = d2 * m_log(q);
+      w = T(1) / q;
+    } break;
+    case 4: {                                   // kernel.py:129-168
+      const T q = m_sqrt(T(1) / d2 + x);
+      rho = T(2) * (delta * q - T(1));
+      w = delta / q;
+    } break;
+    case 5: {                                   // kernel.py:171-207
+      const T q = x / d2;
+      rho = d2 * m_atan(q);
+      w = T(1) / (T(1) + q * q);
+    } break;
+    case 6: rho = delta * x; w = delta; break;  // kernel.py:258-297
+    default: rho = x; w = T(1);
+  }
+}
+template <typename T> LM_HD void sys6_scale(Sys6<T>& s, T w) {
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    s.g[a] *= w;
+#pragma unroll
+    for (int b = a; b < 6; ++b) s.A[a][b] *= w;
+  }
+}
+
 // ---------------------------------------------------------------- PoseInv: r = Log(P X)
 template <typename T> LM_HD Tang<T> poseinv_residual(const Elem<T>& P, const Elem<T>& X) {
   return g_log<SE3g, T>(g_mul<SE3g, T>(P, X));

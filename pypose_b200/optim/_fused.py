@@ -46,39 +46,43 @@ def _same(*ts):
     return [t.contiguous() for t in ts]
 
 
-torch.library.define(f"{NS}::lm_poseinv_loss", "(Tensor P, Tensor X) -> Tensor")
+torch.library.define(f"{NS}::lm_poseinv_loss", "(Tensor P, Tensor X, int robust, float delta) -> Tensor")
 torch.library.define(f"{NS}::lm_poseinv_trial",
-                     "(Tensor P, Tensor X, float scale, float dmin, float dmax) -> (Tensor, Tensor)")
-torch.library.define(f"{NS}::lm_reproj_accum", "(Tensor poses, Tensor pts, Tensor pix, Tensor seg) -> (Tensor, Tensor, Tensor)")
+                     "(Tensor P, Tensor X, float scale, float dmin, float dmax, int robust, float delta) -> (Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_reproj_accum",
+                     "(Tensor poses, Tensor pts, Tensor pix, Tensor seg, int robust, float delta) -> (Tensor, Tensor, Tensor)")
 torch.library.define(f"{NS}::lm_solve6_retract",
                      "(Tensor H, Tensor g, Tensor P, float scale, float dmin, float dmax) -> (Tensor, Tensor, Tensor)")
-torch.library.define(f"{NS}::lm_reproj_loss", "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx) -> Tensor")
+torch.library.define(f"{NS}::lm_reproj_loss",
+                     "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx, int robust, float delta) -> Tensor")
 torch.library.define(f"{NS}::lm_reproj_residual", "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx) -> Tensor")
 
 
-def _poseinv_loss(P, X):
+def _poseinv_loss(P, X, robust=0, delta=1.0):
     P, X = _same(P, X)
     ws = _workspace(P.device)
-    _launch("b200_lm_poseinv_loss", P, [_p(P), _p(X), _p(ws)], P.shape[0])
+    _launch("b200_lm_poseinv_loss", P, [_p(P), _p(X), _p(ws), int(robust), float(delta)], P.shape[0])
     return ws[:1].clone()
 
 
-def _poseinv_trial(P, X, scale, dmin, dmax):
+def _poseinv_trial(P, X, scale, dmin, dmax, robust=0, delta=1.0):
     P, X = _same(P, X)
     ws = _workspace(P.device)
     Pt = torch.empty_like(P)
-    _launch("b200_lm_poseinv_trial", P, [_p(P), _p(X), _p(Pt), _p(ws), scale, dmin, dmax], P.shape[0])
+    _launch("b200_lm_poseinv_trial", P, [_p(P), _p(X), _p(Pt), _p(ws), scale, dmin, dmax, int(robust), float(delta)],
+            P.shape[0])
     return Pt, ws[:4].clone()
 
 
-def _reproj_accum(poses, pts, pix, seg):
+def _reproj_accum(poses, pts, pix, seg, robust=0, delta=1.0):
     poses, pts, pix = _same(poses, pts, pix)
     assert seg.dtype == torch.int32 and seg.numel() == poses.shape[0] + 1
     ws = _workspace(poses.device)
     C = poses.shape[0]
     H = torch.empty(C, 21, dtype=poses.dtype, device=poses.device)
     g = torch.empty(C, 6, dtype=poses.dtype, device=poses.device)
-    _launch("b200_lm_reproj_accum", poses, [_p(poses), _p(pts), _p(pix), _p(seg), _p(H), _p(g), _p(ws)], C)
+    _launch("b200_lm_reproj_accum", poses, [_p(poses), _p(pts), _p(pix), _p(seg), _p(H), _p(g), _p(ws), int(robust),
+                                                   float(delta)], C)
     return H, g, ws[:1].clone()
 
 
@@ -90,11 +94,12 @@ def _solve6_retract(H, g, P, scale, dmin, dmax):
     return Pt, D, ws[:2].clone()
 
 
-def _reproj_loss(poses, pts, pix, cidx):
+def _reproj_loss(poses, pts, pix, cidx, robust=0, delta=1.0):
     poses, pts, pix = _same(poses, pts, pix)
     assert cidx.dtype == torch.int32
     ws = _workspace(poses.device)
-    _launch("b200_lm_reproj_loss", poses, [_p(poses), _p(pts), _p(pix), _p(cidx), _p(ws)], pts.shape[0])
+    _launch("b200_lm_reproj_loss", poses, [_p(poses), _p(pts), _p(pix), _p(cidx), _p(ws), int(robust), float(delta)],
+            pts.shape[0])
     return ws[:1].clone()
 
 

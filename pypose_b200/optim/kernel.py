@@ -11,11 +11,13 @@ def _nonneg(x):
 
 class Huber(nn.Module):
     """s if sqrt(s) < delta else 2 delta sqrt(s) - delta^2 (kernel.py:5-45)."""
+    b200_kind = 1      # id of this kernel inside the fused LM kernels (csrc/lm_math.cuh robust_eval)
 
     def __init__(self, delta: float = 1.0) -> None:
         super().__init__()
         assert delta > 0, ValueError("delta has to be positive: {}".format(delta))
         self.delta, self.delta2 = delta, delta ** 2
+        self.b200_delta = delta
 
     def forward(self, input: Tensor) -> Tensor:
         _nonneg(input)
@@ -25,11 +27,13 @@ class Huber(nn.Module):
 
 class PseudoHuber(nn.Module):
     """2 delta^2 (sqrt(s/delta^2 + 1) - 1) (kernel.py:48-86)."""
+    b200_kind = 2      # id of this kernel inside the fused LM kernels (csrc/lm_math.cuh robust_eval)
 
     def __init__(self, delta: float = 1.0) -> None:
         super().__init__()
         assert delta > 0, ValueError("delta has to be positive: {}".format(delta))
         self.delta2 = delta ** 2
+        self.b200_delta = delta
 
     def forward(self, input: Tensor) -> Tensor:
         _nonneg(input)
@@ -38,11 +42,13 @@ class PseudoHuber(nn.Module):
 
 class Cauchy(nn.Module):
     """delta^2 log(s/delta^2 + 1) (kernel.py:89-126)."""
+    b200_kind = 3      # id of this kernel inside the fused LM kernels (csrc/lm_math.cuh robust_eval)
 
     def __init__(self, delta: float = 1.0) -> None:
         super().__init__()
         assert delta > 0, ValueError("delta has to be positive: {}".format(delta))
         self.delta2 = delta ** 2
+        self.b200_delta = delta
 
     def forward(self, input: Tensor) -> Tensor:
         _nonneg(input)
@@ -51,11 +57,13 @@ class Cauchy(nn.Module):
 
 class SoftLOne(nn.Module):
     """2 (delta sqrt(1/delta^2 + s) - 1) (kernel.py:129-168)."""
+    b200_kind = 4      # id of this kernel inside the fused LM kernels (csrc/lm_math.cuh robust_eval)
 
     def __init__(self, delta: float = 1.0) -> None:
         super().__init__()
         assert delta > 0, ValueError("delta has to be positive: {}".format(delta))
         self.delta1, self.delta2 = delta, delta ** 2
+        self.b200_delta = delta
 
     def forward(self, input: Tensor) -> Tensor:
         _nonneg(input)
@@ -64,10 +72,12 @@ class SoftLOne(nn.Module):
 
 class Arctan(nn.Module):
     """delta^2 atan(s/delta^2) (kernel.py:171-207)."""
+    b200_kind = 5      # id of this kernel inside the fused LM kernels (csrc/lm_math.cuh robust_eval)
 
     def __init__(self, delta: float = 1.0) -> None:
         super().__init__()
         self.delta2 = delta ** 2
+        self.b200_delta = delta
 
     def forward(self, input: Tensor) -> Tensor:
         _nonneg(input)
@@ -90,11 +100,13 @@ class Tolerant(nn.Module):
 
 class Scale(nn.Module):
     """delta * s (kernel.py:258-297)."""
+    b200_kind = 6      # id of this kernel inside the fused LM kernels (csrc/lm_math.cuh robust_eval)
 
     def __init__(self, delta: float = 1.0) -> None:
         super().__init__()
         assert 0 < delta <= 1, ValueError("delta has to be between 0 and 1: {}".format(delta))
         self.delta = delta
+        self.b200_delta = delta
 
     def forward(self, input):
         return self.delta * input

@@ -172,7 +172,12 @@ class LevenbergMarquardt(_SecondOrder):
         self.solver = Cholesky() if solver is None else solver
         self.reject, self.reject_count = reject, 0
         self.weight = weight
-        self._plain = kernel is None and corrector is None
+        # structured route: no kernel, or ONE known robust kernel with the default FastTriggs corrector
+        self._robust = None
+        if kernel is None and corrector is None:
+            self._robust = (0, 1.0)
+        elif corrector is None and not isinstance(kernel, (tuple, list)) and hasattr(kernel, 'b200_kind'):
+            self._robust = (int(kernel.b200_kind), float(kernel.b200_delta))
         kernel, self.corrector = _setup_correctors(kernel, corrector)
         self.model = RobustModel(model, kernel)
         self._problem = None
@@ -182,7 +187,7 @@ class LevenbergMarquardt(_SecondOrder):
 
     # -- structured route ------------------------------------------------------------------------------
     def _structured(self, input, target, weight):
-        if not (self._plain and weight is None and self.weight is None and target is None):
+        if not (self._robust is not None and weight is None and self.weight is None and target is None):
             return None
         if not isinstance(self.solver, Cholesky) or self.solver.upper:
             return None
@@ -190,7 +195,8 @@ class LevenbergMarquardt(_SecondOrder):
             return None
         if self._problem is not None and self._problem.matches(self.model.model, input):
             return self._problem
-        self._problem = structured.recognize(self.model.model, input, self.param_groups[0]['params'], self.group)
+        self._problem = structured.recognize(self.model.model, input, self.param_groups[0]['params'], self.group,
+                                             self._robust)
         return self._problem
 
     def _step_structured(self, prob, pg):

@@ -48,8 +48,9 @@ class _Problem:
 
 
 class PoseInvProblem(_Problem):
-    def __init__(self, model, param, X, key, group):
+    def __init__(self, model, param, X, key, group, robust=(0, 1.0)):
         self.model, self.param, self.X, self.key, self.group = model, param, X, key, group
+        self.robust = robust
         self.dtype = param.dtype
         self._trial = None
 
@@ -61,14 +62,14 @@ class PoseInvProblem(_Problem):
 
     def loss(self):
         P, X = self._rows()
-        return _allreduce(_fused.call("lm_poseinv_loss", P, X), self.group)[0].to(self.dtype)
+        return _allreduce(_fused.call("lm_poseinv_loss", P, X, *self.robust), self.group)[0].to(self.dtype)
 
     def linearize(self):
         return None         # everything lives in registers inside the trial kernel
 
     def trial(self, lin, scale, dmin, dmax):
         P, X = self._rows()
-        self._trial, sums = _fused.call("lm_poseinv_trial", P, X, float(scale), float(dmin), float(dmax))
+        self._trial, sums = _fused.call("lm_poseinv_trial", P, X, float(scale), float(dmin), float(dmax), *self.robust)
         sums = _allreduce(sums, self.group)
         return self._result(sums, {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
 
@@ -77,8 +78,8 @@ class PoseInvProblem(_Problem):
 
 
 class ReprojProblem(_Problem):
-    def __init__(self, model, data, key, group):
-        self.model, self.key, self.group = model, key, group
+    def __init__(self, model, data, key, group, robust=(0, 1.0)):
+        self.model, self.key, self.group, self.robust = model, key, group, robust
         self.param = model.poses
         self.dtype = self.param.dtype
         self.pts, self.pix, self.cidx, self.seg = data
@@ -91,11 +92,11 @@ class ReprojProblem(_Problem):
         return self.param.tensor().reshape(-1, 7)
 
     def loss(self):
-        s = _fused.call("lm_reproj_loss", self._poses(), self.pts, self.pix, self.cidx)
+        s = _fused.call("lm_reproj_loss", self._poses(), self.pts, self.pix, self.cidx, *self.robust)
         return _allreduce(s, self.group)[0].to(self.dtype)
 
     def linearize(self):
-        H, g, s = _fused.call("lm_reproj_accum", self._poses(), self.pts, self.pix, self.seg)
+        H, g, s = _fused.call("lm_reproj_accum", self._poses(), self.pts, self.pix, self.seg, *self.robust)
         if self.group is not None:
             packed = torch.cat([H.reshape(-1), g.reshape(-1)])      # one packed all-reduce per LM iteration
             _allreduce(packed, self.group)
@@ -106,7 +107,7 @@ class ReprojProblem(_Problem):
     def trial(self, lin, scale, dmin, dmax):
         H, g, cur = lin
         self._trial, _, sums = _fused.call("lm_solve6_retract", H, g, self._poses(), float(scale), float(dmin), float(dmax))
-        tl = _fused.call("lm_reproj_loss", self._trial, self.pts, self.pix, self.cidx)
+        tl = _fused.call("lm_reproj_loss", self._trial, self.pts, self.pix, self.cidx, *self.robust)
         shard = torch.cat([cur, tl])                 # [current loss, trial loss] of this rank's residuals
         shard = _allreduce(shard, self.group)
         return self._result(torch.cat([shard, sums]), {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
@@ -124,7 +125,7 @@ def _is_se3_param(p):
     return isinstance(p, Parameter) and getattr(p, 'ltype', None) is SE3_type and p.requires_grad and p.is_cuda is not None
 
 
-def recognize(model, input, params, group=None):
+def recognize(model, input, params, group=None, robust=(0, 1.0)):
     """Return a structured problem for (model, input) or None (-> generic dense route)."""
     params = [p for p in params if p.requires_grad]
     if len(params) != 1 or not _is_se3_param(params[0]) or params[0].dtype not in (torch.float32, torch.float64):
@@ -134,7 +135,7 @@ def recognize(model, input, params, group=None):
     if isinstance(model, PoseReproj):
         if param is not model.poses:
             return None
-        return ReprojProblem(model, model.prepare(*input), _input_key(input), group)
+        return ReprojProblem(model, model.prepare(*input), _input_key(input), group, robust)
     if isinstance(input, (tuple, list, dict)) or not isinstance(input, LieTensor) or input.ltype is not SE3_type:
         return None
     # record the LieTensor ops of one forward pass
@@ -154,4 +155,4 @@ def recognize(model, input, params, group=None):
           and input.device == param.device)
     if not ok:
         return None
-    return PoseInvProblem(model, param, input, _input_key(input), group)
+    return PoseInvProblem(model, param, input, _input_key(input), group, robust)

@@ -78,23 +78,23 @@ def _install_cpu_oracle_lm_kernels():
     def n(x):
         return x.detach().double().numpy()
 
-    def poseinv_loss(P, X):
-        return f64(L.poseinv_loss(n(P), n(X)))
+    def poseinv_loss(P, X, robust, delta):
+        return f64(L.poseinv_loss(n(P), n(X), robust, delta))
 
-    def poseinv_trial(P, X, scale, dmin, dmax):
-        Pt, sums = L.poseinv_trial(n(P), n(X), scale, dmin, dmax)
+    def poseinv_trial(P, X, scale, dmin, dmax, robust, delta):
+        Pt, sums = L.poseinv_trial(n(P), n(X), scale, dmin, dmax, robust, delta)
         return t(Pt, P), f64(sums)
 
-    def reproj_accum(poses, pts, pix, seg):
-        H, g, s = L.reproj_accum(n(poses), n(pts), n(pix), seg.numpy())
+    def reproj_accum(poses, pts, pix, seg, robust, delta):
+        H, g, s = L.reproj_accum(n(poses), n(pts), n(pix), seg.numpy(), robust, delta)
         return t(H, poses), t(g, poses), f64(s)
 
     def solve6_retract(H, g, P, scale, dmin, dmax):
         Pt, D, s = L.solve6_retract(n(H), n(g), n(P), scale, dmin, dmax)
         return t(Pt, P), t(D, P), f64(s)
 
-    def reproj_loss(poses, pts, pix, cidx):
-        return f64(L.reproj_loss(n(poses), n(pts), n(pix), cidx.numpy()))
+    def reproj_loss(poses, pts, pix, cidx, robust, delta):
+        return f64(L.reproj_loss(n(poses), n(pts), n(pix), cidx.numpy(), robust, delta))
 
     def reproj_residual(poses, pts, pix, cidx):
         return t(L.reproj_residual(n(poses), n(pts), n(pix), cidx.numpy()), poses)

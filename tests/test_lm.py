@@ -191,3 +191,37 @@ def test_cg_golden_vector():
     b = torch.tensor([[2.64306851], [4.03276688], [2.57966207], [4.0433152], [3.83152219]])
     x = pp.optim.solver.CG()(A, b)
     torch.testing.assert_close(A @ x, b, atol=1e-3, rtol=1e-3)
+
+
+KERNELS = {"huber": lambda: pp.optim.kernel.Huber(delta=0.05), "cauchy": lambda: pp.optim.kernel.Cauchy(delta=0.1),
+           "pseudohuber": lambda: pp.optim.kernel.PseudoHuber(delta=0.05), "softlone": lambda: pp.optim.kernel.SoftLOne(delta=0.1),
+           "arctan": lambda: pp.optim.kernel.Arctan(delta=0.3)}
+
+
+@pytest.mark.parametrize("kname", list(KERNELS))
+@pytest.mark.parametrize("route", ["structured", "generic"])
+def test_lm_robust_kernel_matches_reference_trajectory(golden_lm, kname, route):
+    """Robust kernels with the default FastTriggs corrector, fused into the structured route."""
+    g = golden_lm
+    net = pp.module.PoseReproj(pp.SE3(torch.from_numpy(g["robust_reproj/poses0"].copy())))
+    inp = tuple(torch.from_numpy(g[f"robust_reproj/{k}"]) for k in ("pts", "pix", "cidx"))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), kernel=KERNELS[kname](),
+                      solver=None if route == "structured" else pp.optim.solver.Cholesky(upper=True))
+    for k in range(5):
+        loss = opt.step(inp)
+        assert (opt._problem is not None) == (route == "structured")
+        np.testing.assert_allclose(float(loss), g[f"robust_reproj/{kname}/loss"][k], rtol=1e-6)
+        np.testing.assert_allclose(net.poses.detach().numpy(), g[f"robust_reproj/{kname}/poses"][k], atol=1e-8)
+        assert opt.reject_count == g[f"robust_reproj/{kname}/reject"][k]
+
+
+def test_lm_poseinv_cauchy_matches_reference(golden_lm):
+    g = golden_lm
+    net = InvNet(pp.SE3(torch.from_numpy(g["poseinv/P0"].copy())))
+    X = pp.SE3(torch.from_numpy(g["poseinv/X"].copy()))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.Constant(damping=1e-4), kernel=pp.optim.kernel.Cauchy(delta=0.5))
+    for k in range(4):
+        loss = opt.step(X)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g["poseinv/cauchy/loss"][k], rtol=1e-5, atol=1e-20)
+        np.testing.assert_allclose(net.pose.detach().numpy(), g["poseinv/cauchy/poses"][k], atol=1e-9)

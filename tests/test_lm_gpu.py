@@ -29,14 +29,14 @@ def test_poseinv_trial_vs_oracle(dt, rtol, ptol):
     P = rand_group(rng, "SE3", n, tmax=2.0)
     X = rand_group(rng, "SE3", n, tmax=2.0)
     Pd, Xd = cu(P, dt), cu(X, dt)
-    Pt, sums = ops.lm_poseinv_trial(Pd, Xd, 1.0001, 1e-6, 1e32)
+    Pt, sums = ops.lm_poseinv_trial(Pd, Xd, 1.0001, 1e-6, 1e32, 0, 1.0)
     Pt_o, sums_o = L.poseinv_trial(Pd.double().cpu().numpy(), Xd.double().cpu().numpy(), 1.0001, 1e-6, 1e32)
     assert np.abs(Pt.double().cpu().numpy() - Pt_o).max() <= ptol * 20
     s = sums.cpu().numpy()
     np.testing.assert_allclose(s[0], sums_o[0], rtol=rtol)
     np.testing.assert_allclose(s[2], sums_o[2], rtol=rtol * 10)
     assert s[1] <= max(10 * sums_o[1], 1e-6 * s[0]) and s[3] == 0
-    loss = ops.lm_poseinv_loss(Pd, Xd).cpu().numpy()
+    loss = ops.lm_poseinv_loss(Pd, Xd, 0, 1.0).cpu().numpy()
     np.testing.assert_allclose(loss[0], sums_o[0], rtol=rtol)
 
 
@@ -60,7 +60,7 @@ def test_reproj_accum_solve_loss_vs_oracle(dt, rtol, ptol):
     seg = np.concatenate([[0], np.cumsum(np.bincount(cidx, minlength=C))]).astype(np.int32)
     pd, td, xd = cu(init, dt), cu(pts[order], dt), cu(pix[order], dt)
     segd, cd = torch.from_numpy(seg).cuda(), torch.from_numpy(cidx[order].astype(np.int32)).cuda()
-    H, g, s = ops.lm_reproj_accum(pd, td, xd, segd)
+    H, g, s = ops.lm_reproj_accum(pd, td, xd, segd, 0, 1.0)
     H_o, g_o, s_o = L.reproj_accum(pd.double().cpu().numpy(), td.double().cpu().numpy(), xd.double().cpu().numpy(), seg)
     scaleH = np.abs(H_o).max()
     assert np.abs(H.double().cpu().numpy() - H_o).max() <= rtol * scaleH
@@ -72,7 +72,7 @@ def test_reproj_accum_solve_loss_vs_oracle(dt, rtol, ptol):
     assert np.abs(D.double().cpu().numpy() - D_o).max() <= ptol * 100
     assert np.abs(Pt.double().cpu().numpy() - Pt_o).max() <= ptol * 100
     np.testing.assert_allclose(s2.cpu().numpy()[0], s2_o[0], rtol=rtol * 50)
-    lo = ops.lm_reproj_loss(Pt, td, xd, cd).cpu().numpy()[0]
+    lo = ops.lm_reproj_loss(Pt, td, xd, cd, 0, 1.0).cpu().numpy()[0]
     np.testing.assert_allclose(lo, L.reproj_loss(Pt.double().cpu().numpy(), td.double().cpu().numpy(),
                                                  xd.double().cpu().numpy(), cidx[order])[0], rtol=rtol * 10, atol=1e-12)
     r = ops.lm_reproj_residual(pd, td, xd, cd)
@@ -164,3 +164,42 @@ def test_config5_small_fp64_pose_error():
         opt.step(inp)
     d = (pp.SE3(cu(gt, torch.float64)).Inv() @ net.poses).Log().tensor().abs().max().item()
     assert d <= 1e-5, d
+
+
+@pytest.mark.parametrize("kname,kern", [("huber", lambda: pp.optim.kernel.Huber(delta=0.05)),
+                                        ("cauchy", lambda: pp.optim.kernel.Cauchy(delta=0.1)),
+                                        ("pseudohuber", lambda: pp.optim.kernel.PseudoHuber(delta=0.05)),
+                                        ("softlone", lambda: pp.optim.kernel.SoftLOne(delta=0.1)),
+                                        ("arctan", lambda: pp.optim.kernel.Arctan(delta=0.3))])
+def test_lm_robust_kernels_reference_trajectory_on_gpu(golden_lm, kname, kern):
+    g = golden_lm
+    net = pp.module.PoseReproj(pp.SE3(torch.from_numpy(g["robust_reproj/poses0"].copy()).cuda()))
+    inp = tuple(torch.from_numpy(g[f"robust_reproj/{k}"]).cuda() for k in ("pts", "pix", "cidx"))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), kernel=kern())
+    for k in range(5):
+        loss = opt.step(inp)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g[f"robust_reproj/{kname}/loss"][k], rtol=1e-6)
+        np.testing.assert_allclose(net.poses.detach().cpu().numpy(), g[f"robust_reproj/{kname}/poses"][k], atol=1e-8)
+        assert opt.reject_count == g[f"robust_reproj/{kname}/reject"][k]
+
+
+@pytest.mark.parametrize("kind,delta", [(1, 0.05), (2, 0.05), (3, 0.1), (4, 0.1), (5, 0.3), (6, 0.5)])
+def test_robust_accum_and_poseinv_vs_oracle(kind, delta):
+    rng = np.random.default_rng(kind)
+    C, M = 101, 9001
+    gt, init, pts, pix, cidx = _reproj_problem(rng, C, M, pix_noise=0.05)
+    order = np.argsort(cidx, kind="stable")
+    seg = np.concatenate([[0], np.cumsum(np.bincount(cidx, minlength=C))]).astype(np.int32)
+    dt = torch.float64
+    pd, td, xd = cu(init, dt), cu(pts[order], dt), cu(pix[order], dt)
+    H, g, s = ops.lm_reproj_accum(pd, td, xd, torch.from_numpy(seg).cuda(), kind, delta)
+    H_o, g_o, s_o = L.reproj_accum(init, pts[order], pix[order], seg, kind, delta)
+    assert np.abs(H.cpu().numpy() - H_o).max() <= 1e-9 * np.abs(H_o).max()
+    assert np.abs(g.cpu().numpy() - g_o).max() <= 1e-9 * np.abs(g_o).max()
+    np.testing.assert_allclose(s.cpu().numpy()[0], s_o[0], rtol=1e-10)
+    P, X = rand_group(rng, "SE3", 2001, tmax=2.0), rand_group(rng, "SE3", 2001, tmax=2.0)
+    Pt, sums = ops.lm_poseinv_trial(cu(P, dt), cu(X, dt), 1.0001, 1e-6, 1e32, kind, delta)
+    Pt_o, sums_o = L.poseinv_trial(P, X, 1.0001, 1e-6, 1e32, kind, delta)
+    assert np.abs(Pt.cpu().numpy() - Pt_o).max() <= 1e-9
+    np.testing.assert_allclose(sums.cpu().numpy()[:3], sums_o[:3], rtol=1e-8)
