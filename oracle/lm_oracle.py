@@ -140,6 +140,57 @@ def reproj_loss(poses, pts, pix, cidx, kind=0, delta=1.0):
     return np.array([robust(kind, delta, (reproj_residual(poses, pts, pix, cidx) ** 2).sum(-1))[0].sum()])
 
 
+# ------------------------------------------------------------------ PGO: r = Log(Z^-1 A^-1 B)
+def pgo_residual(nodes, Z, ei, ej):
+    """examples/module/pgo/pgo.py:21-25."""
+    S = O.mul("SE3", O.inv("SE3", Z), O.inv("SE3", nodes[ei]))
+    return O.log("SE3", O.mul("SE3", S, nodes[ej])), S
+
+
+def pgo_jac_blocks(nodes, Z, ei, ej):
+    """d r / d B = Jl^-1(r) Adj(Z^-1 A^-1) (SE3_Log.backward op.py:389-395 chained with SE3_Mul.backward wrt Y
+    op.py:870-877); d r / d A = -(that) (SE3_Inv.backward op.py:968-973 + SE3_Mul.backward wrt X)."""
+    r, S = pgo_residual(nodes, Z, ei, ej)
+    return r, O.se3_Jl_inv(r) @ O.SE3_Adj(S)
+
+
+def pgo_linearize(nodes, Z, ei, ej, kind=0, delta=1.0):
+    r, J = pgo_jac_blocks(nodes, Z, ei, ej)
+    rho, w = robust(kind, delta, (r ** 2).sum(-1))
+    M = np.swapaxes(J, -1, -2) @ J * w[:, None, None]
+    u = (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0] * w[:, None]
+    return _triu_pack(M), u, np.array([rho.sum()])
+
+
+def pgo_scatter(M21, u, ei, ej, n):
+    Hd, g = np.zeros((n, 21)), np.zeros((n, 6))
+    np.add.at(Hd, ei, M21); np.add.at(Hd, ej, M21)
+    np.add.at(g, ei, -u); np.add.at(g, ej, u)
+    return Hd, g
+
+
+def pgo_spmv(M21, ei, ej, x, y0):
+    v = (_triu_unpack(M21) @ (x[ei] - x[ej])[..., None])[..., 0]
+    y = y0.copy()
+    np.add.at(y, ei, v); np.add.at(y, ej, -v)
+    return y
+
+
+def pgo_loss(nodes, Z, ei, ej, kind=0, delta=1.0):
+    return np.array([robust(kind, delta, (pgo_residual(nodes, Z, ei, ej)[0] ** 2).sum(-1))[0].sum()])
+
+
+def pgo_dense_jac(nodes, Z, ei, ej):
+    """The reference's dense (6E, 7N) Jacobian of the PoseGraph model."""
+    _, J = pgo_jac_blocks(nodes, Z, ei, ej)
+    E, N = len(ei), nodes.shape[0]
+    D = np.zeros((6 * E, 7 * N))
+    for e in range(E):
+        D[6 * e:6 * e + 6, 7 * ei[e]:7 * ei[e] + 6] -= J[e]
+        D[6 * e:6 * e + 6, 7 * ej[e]:7 * ej[e] + 6] += J[e]
+    return D
+
+
 # ------------------------------------------------------------------ the dense reference algorithm
 def dense_lm_step(residual_fn, jac_fn, P, damping, dmin=1e-6, dmax=1e32, reject=16, last=None, update=None):
     """One LevenbergMarquardt.step with a constant damping (optimizer.py:645-680) on parameters P (N,7).

@@ -38,6 +38,17 @@ class Reproj(nn.Module):
         return -y[..., :2] / y[..., 2:] - pixels
 
 
+class PoseGraph(nn.Module):                 # examples/module/pgo/pgo.py:15-25
+    def __init__(self, nodes):
+        super().__init__()
+        self.nodes = ref.Parameter(nodes)
+
+    def forward(self, edges, poses):
+        node1 = self.nodes[edges[..., 0]]
+        node2 = self.nodes[edges[..., 1]]
+        return (poses.Inv() @ node1.Inv() @ node2).Log().tensor()
+
+
 def run(model, input, strategy, steps, pname):
     opt = ref.optim.LM(model, strategy=strategy)
     losses, poses, rejects = [], [], []
@@ -86,6 +97,21 @@ def main():
         init.numpy().copy(), pts.numpy().copy(), pix.numpy().copy(), cidx.numpy().copy())
     losses, poses, rej = run(Reproj(init.clone()), (pts, pix, cidx), ref.optim.strategy.TrustRegion(), 6, "poses")
     g["reproj_hard/trustregion/loss"], g["reproj_hard/trustregion/poses"], g["reproj_hard/trustregion/reject"] = losses, poses, rej
+    # pose graph: 10 nodes on a noisy loop, odometry + loop-closure edges, dense reference LM (Cholesky)
+    torch.manual_seed(21)
+    N = 10
+    gtn = ref.se3(torch.cat([torch.tensor([[1.0, 0.2, 0.0, 0.0, 0.0, 0.35]], dtype=torch.float64)] * N)).Exp().cumprod(dim=0, left=False)
+    pairs = [(i, i + 1) for i in range(N - 1)] + [(0, 5), (2, 7), (3, 9), (1, 8), (9, 0)]
+    edges = torch.tensor(pairs)
+    Zm = gtn[edges[:, 0]].Inv() @ gtn[edges[:, 1]]
+    Zm = ref.se3(0.02 * torch.randn(len(pairs), 6, dtype=torch.float64)).Exp() @ Zm
+    init = ref.se3(0.15 * torch.randn(N, 6, dtype=torch.float64)).Exp() @ gtn
+    g["pgo/nodes0"], g["pgo/edges"], g["pgo/Z"] = init.numpy().copy(), edges.numpy().copy(), Zm.numpy().copy()
+    for name, strat in (("trustregion", lambda: ref.optim.strategy.TrustRegion()),
+                        ("constant", lambda: ref.optim.strategy.Constant(damping=1e-4))):
+        losses, poses, rej = run(PoseGraph(init.clone()), (edges, Zm), strat(), 5, "nodes")
+        g[f"pgo/{name}/loss"], g[f"pgo/{name}/poses"], g[f"pgo/{name}/reject"] = losses, poses, rej
+
     # robust kernels (default FastTriggs corrector): reprojection with 10 % gross outliers under Huber,
     # PoseInv under Cauchy (optimizer.py:474-480, corrector.py:73-95, kernel.py)
     torch.manual_seed(3)

@@ -114,6 +114,26 @@ LM_OPS = [
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),
       ("const int*", "cidx", "(m) camera of each row"), ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale (optim/kernel.py) with FastTriggs scaling"), ("double", "delta", "kernel parameter")],
      "model.loss after the update, optimizer.py:673"),
+    ("b200_lm_pgo_linearize",
+     [("const REAL*", "nodes", "(N,7) SE3 parameters"), ("const REAL*", "Z", "(E,7) relative-pose measurements"),
+      ("const int*", "ei", "(E) first node of each edge"), ("const int*", "ej", "(E) second node"),
+      ("REAL*", "M", "(E,21) upper triangle of J^T J per edge"), ("REAL*", "u", "(E,6) J^T r per edge"),
+      ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "see b200_lm_reproj_accum"), ("double", "delta", "")],
+     "modjac + J^T J of optimizer.py:645-656 for r = Log(Z^-1 A^-1 B) (examples/module/pgo/pgo.py:15-25); the sparse "
+     "counterpart is bae.autograd.graph.jacobian + J.mT @ J, optimizer.py:637-642"),
+    ("b200_lm_pgo_scatter",
+     [("const REAL*", "M", "(E,21)"), ("const REAL*", "u", "(E,6)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
+      ("REAL*", "Hd", "(N,21) diagonal blocks, accumulated with atomics (zero-initialised by the caller)"),
+      ("REAL*", "g", "(N,6) J^T R, accumulated")],
+     "diagonal of A = J^T J (optimizer.py:642-643 diagonal_op_) and b = J^T R (optimizer.py:668)"),
+    ("b200_lm_pgo_spmv",
+     [("const REAL*", "M", "(E,21)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"), ("const REAL*", "x", "(N,6)"),
+      ("REAL*", "y", "(N,6) y += H x (atomics)")],
+     "A @ p inside the (P)CG loop, optim/solver.py:319-336 (bae PCG: solver.py:343-363)"),
+    ("b200_lm_pgo_loss",
+     [("const REAL*", "nodes", "(N,7)"), ("const REAL*", "Z", "(E,7)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
+      ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", ""), ("double", "delta", "")],
+     "model.loss after the update, optimizer.py:673"),
     ("b200_lm_reproj_residual",
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),
       ("const int*", "cidx", "(m)"), ("REAL*", "r", "(m,2)")],

@@ -276,6 +276,99 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_residual_kernel(const T*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pose-graph optimisation, two-pose residuals r_e = Log(Z_e^-1 A^-1 B), A = nodes[ei], B = nodes[ej]
+// (examples/module/pgo/pgo.py:15-25).  H is block-sparse: the edge's M_e = J^T J goes to (i,i), (j,j) and -M_e to
+// (i,j), (j,i).  M_e (21) and u_e = J^T r (6) are stored per edge; H is never assembled — the PCG multiplies with it
+// edge by edge (what the reference delegates to the external `bae` package, optimizer.py:629-643).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_pgo_linearize_kernel(const T* __restrict__ nodes, const T* __restrict__ Z,
+                                                                       const int* __restrict__ ei, const int* __restrict__ ej,
+                                                                       T* __restrict__ M, T* __restrict__ u, double* ws, int rk,
+                                                                       T rdelta, long long E) {
+  double acc[1] = {0.0};
+  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
+    T a[7], b[7], z[7];
+    const long long i = ei[e], j = ej[e];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a[k] = __ldg(nodes + i * 7 + k); b[k] = __ldg(nodes + j * 7 + k); z[k] = Z[e * 7 + k]; }
+    Tang<T> r;
+    Sys6<T> s;
+    pgo_linearize(load_se3(a), load_se3(b), load_se3(z), r, s);
+    T rho, w;
+    robust_eval(rk, rdelta, tang6_sqnorm(r), rho, w);
+    if (rk) sys6_scale(s, w);
+    int q = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      u[e * 6 + p] = s.g[p];
+#pragma unroll
+      for (int c = p; c < 6; ++c) M[e * 21 + q++] = s.A[p][c];
+    }
+    acc[0] += (double)rho;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+// Hd[i] += M_e, Hd[j] += M_e (diagonal blocks, packed 21);  g[i] -= u_e, g[j] += u_e   (J_A = -J, J_B = +J)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_pgo_scatter_kernel(const T* __restrict__ M, const T* __restrict__ u,
+                                                                     const int* __restrict__ ei, const int* __restrict__ ej,
+                                                                     T* __restrict__ Hd, T* __restrict__ g, long long E) {
+  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
+    const long long i = ei[e], j = ej[e];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) { const T m = M[e * 21 + k]; atomicAdd(Hd + i * 21 + k, m); atomicAdd(Hd + j * 21 + k, m); }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const T v = u[e * 6 + k]; atomicAdd(g + i * 6 + k, -v); atomicAdd(g + j * 6 + k, v); }
+  }
+}
+
+// y += H x edge by edge: v = M_e (x_i - x_j); y_i += v; y_j -= v      (y pre-initialised by the caller)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_pgo_spmv_kernel(const T* __restrict__ M, const int* __restrict__ ei,
+                                                                  const int* __restrict__ ej, const T* __restrict__ x,
+                                                                  T* __restrict__ y, long long E) {
+  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
+    const long long i = ei[e], j = ej[e];
+    T d[6], A[6][6];
+    int q = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      d[p] = __ldg(x + i * 6 + p) - __ldg(x + j * 6 + p);
+#pragma unroll
+      for (int c = p; c < 6; ++c) { A[p][c] = M[e * 21 + q]; A[c][p] = A[p][c]; ++q; }
+    }
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      T v = T(0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) v += A[p][c] * d[c];
+      atomicAdd(y + i * 6 + p, v);
+      atomicAdd(y + j * 6 + p, -v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_pgo_loss_kernel(const T* __restrict__ nodes, const T* __restrict__ Z,
+                                                                  const int* __restrict__ ei, const int* __restrict__ ej,
+                                                                  double* ws, int rk, T rdelta, long long E) {
+  double acc[1] = {0.0};
+  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
+    T a[7], b[7], z[7];
+    const long long i = ei[e], j = ej[e];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a[k] = __ldg(nodes + i * 7 + k); b[k] = __ldg(nodes + j * 7 + k); z[k] = Z[e * 7 + k]; }
+    Elem<T> S;
+    T rho, w;
+    robust_eval(rk, rdelta, tang6_sqnorm(pgo_residual(load_se3(a), load_se3(b), load_se3(z), S)), rho, w);
+    acc[0] += (double)rho;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
 inline unsigned lm_grid(long long work_items, int per_block) {
   long long need = (work_items + per_block - 1) / per_block;
   long long cap = (long long)lm_sms() * 8;
@@ -337,5 +430,37 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
     return (int)cudaGetLastError();                                                                                   \
   }
 
+#define PGO_ABI(SFX, CT)                                                                                              \
+  B200_EXPORT int b200_lm_pgo_linearize_##SFX(const CT* nodes, const CT* Z, const int* ei, const int* ej, CT* M,      \
+                                              CT* u, double* ws, int robust, double delta, long long E,               \
+                                              void* stream) {                                                         \
+    if (E <= 0) return 0;                                                                                             \
+    lm_pgo_linearize_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                     \
+        nodes, Z, ei, ej, M, u, ws, robust, (CT)delta, E);                                                            \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_scatter_##SFX(const CT* M, const CT* u, const int* ei, const int* ej, CT* Hd, CT* g,    \
+                                            long long E, void* stream) {                                              \
+    if (E <= 0) return 0;                                                                                             \
+    lm_pgo_scatter_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(M, u, ei, ej, Hd, g,   \
+                                                                                               E);                    \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_spmv_##SFX(const CT* M, const int* ei, const int* ej, const CT* x, CT* y, long long E,  \
+                                         void* stream) {                                                              \
+    if (E <= 0) return 0;                                                                                             \
+    lm_pgo_spmv_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(M, ei, ej, x, y, E);      \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_loss_##SFX(const CT* nodes, const CT* Z, const int* ei, const int* ej, double* ws,      \
+                                         int robust, double delta, long long E, void* stream) {                       \
+    if (E <= 0) return 0;                                                                                             \
+    lm_pgo_loss_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(nodes, Z, ei, ej, ws,     \
+                                                                                            robust, (CT)delta, E);    \
+    return (int)cudaGetLastError();                                                                                   \
+  }
+
 LM_ABI(f32, float)
 LM_ABI(f64, double)
+PGO_ABI(f32, float)
+PGO_ABI(f64, double)

@@ -215,6 +215,42 @@ template <typename T> LM_HD Elem<T> se3_retract(const T (&D)[6], const Elem<T>& 
   return g_mul<SE3g, T>(g_exp<SE3g, T>(d), P);
 }
 
+// ---------------------------------------------------------------- PGO edge: r = Log(Z^-1 A^-1 B)
+// (examples/module/pgo/pgo.py:15-25).  With S = Z^-1 A^-1:  dr/dB = Jl^-1(r) Adj(S) =: J,  dr/dA = -J
+// (left perturbations), so the edge contributes M = J^T J to H_ii, H_jj and -M to H_ij, H_ji.
+template <typename T> LM_HD Tang<T> pgo_residual(const Elem<T>& A, const Elem<T>& B, const Elem<T>& Z, Elem<T>& S) {
+  S = g_mul<SE3g, T>(g_inv<SE3g, T>(Z), g_inv<SE3g, T>(A));
+  return g_log<SE3g, T>(g_mul<SE3g, T>(S, B));
+}
+template <typename T> LM_HD void pgo_linearize(const Elem<T>& A, const Elem<T>& B, const Elem<T>& Z, Tang<T>& r, Sys6<T>& s) {
+  Elem<T> S;
+  r = pgo_residual(A, B, Z, S);
+  M3<T> Ji, Bm;
+  se3_jlinv_blocks(r, Ji, Bm);
+  // R(S) as a matrix, and t^ R
+  M3<T> R;
+  {
+    const V3<T> c0 = qrot(S.q, mk(T(1), T(0), T(0))), c1 = qrot(S.q, mk(T(0), T(1), T(0))), c2 = qrot(S.q, mk(T(0), T(0), T(1)));
+    R.m[0][0] = c0.x; R.m[1][0] = c0.y; R.m[2][0] = c0.z;
+    R.m[0][1] = c1.x; R.m[1][1] = c1.y; R.m[2][1] = c1.z;
+    R.m[0][2] = c2.x; R.m[1][2] = c2.y; R.m[2][2] = c2.z;
+  }
+  const M3<T> tR = m3_mul(m3_skew(S.t), R);
+  // J = [[Ji, Bm],[0, Ji]] [[R, tR],[0, R]] = [[Ji R, Ji tR + Bm R],[0, Ji R]]
+  const M3<T> JR = m3_mul(Ji, R);
+  const M3<T> JtR = m3_mul(Ji, tR), BR = m3_mul(Bm, R);
+  sys6_zero(s);
+  const T rr[6] = {r.tau.x, r.tau.y, r.tau.z, r.phi.x, r.phi.y, r.phi.z};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const T top[6] = {JR.m[i][0], JR.m[i][1], JR.m[i][2], JtR.m[i][0] + BR.m[i][0], JtR.m[i][1] + BR.m[i][1],
+                      JtR.m[i][2] + BR.m[i][2]};
+    const T bot[6] = {T(0), T(0), T(0), JR.m[i][0], JR.m[i][1], JR.m[i][2]};
+    sys6_add_row(s, top, rr[i]);
+    sys6_add_row(s, bot, rr[i + 3]);
+  }
+}
+
 // ---------------------------------------------------------------- Reprojection: r = pi(T p) - z, pi(y) = -y[:2]/y[2]
 // (README.md:170-178 `project`; the Jacobian of T p w.r.t. T is [I, -y^], operation.py:225-227)
 template <typename T> LM_HD void reproj_residual(const Elem<T>& Tc, const V3<T>& p, T zx, T zy, T& rx, T& ry, V3<T>& y) {

@@ -58,6 +58,46 @@ torch.library.define(f"{NS}::lm_reproj_loss",
 torch.library.define(f"{NS}::lm_reproj_residual", "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx) -> Tensor")
 
 
+torch.library.define(f"{NS}::lm_pgo_linearize",
+                     "(Tensor nodes, Tensor Z, Tensor ei, Tensor ej, int robust, float delta) -> (Tensor, Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_pgo_scatter", "(Tensor M, Tensor u, Tensor ei, Tensor ej, int n) -> (Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_pgo_spmv", "(Tensor M, Tensor ei, Tensor ej, Tensor x, Tensor y0) -> Tensor")
+torch.library.define(f"{NS}::lm_pgo_loss", "(Tensor nodes, Tensor Z, Tensor ei, Tensor ej, int robust, float delta) -> Tensor")
+
+
+def _pgo_linearize(nodes, Z, ei, ej, robust=0, delta=1.0):
+    nodes, Z = _same(nodes, Z)
+    E = Z.shape[0]
+    ws = _workspace(nodes.device)
+    M = torch.empty(E, 21, dtype=nodes.dtype, device=nodes.device)
+    u = torch.empty(E, 6, dtype=nodes.dtype, device=nodes.device)
+    _launch("b200_lm_pgo_linearize", nodes, [_p(nodes), _p(Z), _p(ei), _p(ej), _p(M), _p(u), _p(ws), int(robust),
+                                             float(delta)], E)
+    return M, u, ws[:1].clone()
+
+
+def _pgo_scatter(M, u, ei, ej, n):
+    Hd = torch.zeros(n, 21, dtype=M.dtype, device=M.device)
+    g = torch.zeros(n, 6, dtype=M.dtype, device=M.device)
+    _launch("b200_lm_pgo_scatter", M, [_p(M), _p(u), _p(ei), _p(ej), _p(Hd), _p(g)], M.shape[0])
+    return Hd, g
+
+
+def _pgo_spmv(M, ei, ej, x, y0):
+    """returns y0 + H x."""
+    y = y0.clone()
+    x = x.contiguous()
+    _launch("b200_lm_pgo_spmv", M, [_p(M), _p(ei), _p(ej), _p(x), _p(y)], M.shape[0])
+    return y
+
+
+def _pgo_loss(nodes, Z, ei, ej, robust=0, delta=1.0):
+    nodes, Z = _same(nodes, Z)
+    ws = _workspace(nodes.device)
+    _launch("b200_lm_pgo_loss", nodes, [_p(nodes), _p(Z), _p(ei), _p(ej), _p(ws), int(robust), float(delta)], Z.shape[0])
+    return ws[:1].clone()
+
+
 def _poseinv_loss(P, X, robust=0, delta=1.0):
     P, X = _same(P, X)
     ws = _workspace(P.device)
@@ -111,6 +151,10 @@ def _reproj_residual(poses, pts, pix, cidx):
     return r
 
 
+torch.library.impl(f"{NS}::lm_pgo_linearize", "CUDA")(_pgo_linearize)
+torch.library.impl(f"{NS}::lm_pgo_scatter", "CUDA")(_pgo_scatter)
+torch.library.impl(f"{NS}::lm_pgo_spmv", "CUDA")(_pgo_spmv)
+torch.library.impl(f"{NS}::lm_pgo_loss", "CUDA")(_pgo_loss)
 torch.library.impl(f"{NS}::lm_poseinv_loss", "CUDA")(_poseinv_loss)
 torch.library.impl(f"{NS}::lm_poseinv_trial", "CUDA")(_poseinv_trial)
 torch.library.impl(f"{NS}::lm_reproj_accum", "CUDA")(_reproj_accum)
@@ -132,7 +176,9 @@ def call(name, *args):
 
 
 _DIRECT = {"lm_poseinv_loss": _poseinv_loss, "lm_poseinv_trial": _poseinv_trial, "lm_reproj_accum": _reproj_accum,
-           "lm_solve6_retract": _solve6_retract, "lm_reproj_loss": _reproj_loss, "lm_reproj_residual": _reproj_residual}
+           "lm_solve6_retract": _solve6_retract, "lm_reproj_loss": _reproj_loss, "lm_reproj_residual": _reproj_residual,
+           "lm_pgo_linearize": _pgo_linearize, "lm_pgo_scatter": _pgo_scatter, "lm_pgo_spmv": _pgo_spmv,
+           "lm_pgo_loss": _pgo_loss}
 
 LM_OPS = ["lm_poseinv_loss", "lm_poseinv_trial", "lm_reproj_accum", "lm_solve6_retract", "lm_reproj_loss",
           "lm_reproj_residual"]

@@ -116,6 +116,104 @@ class ReprojProblem(_Problem):
         self.param.copy_(self._trial.view(self.param.shape))
 
 
+_DIAG21 = [0, 6, 11, 15, 18, 20]          # positions of the 6 diagonal entries inside a packed upper triangle
+
+
+def _unpack21(Hd):
+    iu = torch.triu_indices(6, 6, device=Hd.device)
+    A = Hd.new_zeros(Hd.shape[0], 6, 6)
+    A[:, iu[0], iu[1]] = Hd
+    A[:, iu[1], iu[0]] = Hd
+    return A
+
+
+class PGOProblem(_Problem):
+    """Two-pose residuals r_e = Log(Z_e^-1 A^-1 B): block-sparse H, never assembled.
+
+    linearize: per-edge M_e = J^T J and u_e = J^T r (one kernel), diagonal blocks + gradient by atomics.
+    trial:     (H + extra diagonal) D = -g by block-Jacobi preconditioned CG whose matvec walks the edges
+               (csrc/lm.cu lm_pgo_spmv_kernel); the extra diagonal is clamp(diag H) * scale - diag H, i.e. the
+               reference's clamp (optimizer.py:643/657) + cumulative damping (:664/666).
+    Edges may be sharded over a process group: Hd, g, every matvec and the scalars are all-reduced."""
+
+    def __init__(self, model, edges, Z, key, group, robust, tol, maxiter):
+        self.model, self.key, self.group, self.robust = model, key, group, robust
+        self.param = model.nodes
+        self.dtype = self.param.dtype
+        self.ei = edges[..., 0].to(torch.int32).contiguous()
+        self.ej = edges[..., 1].to(torch.int32).contiguous()
+        self.Z = Z.tensor().to(self.dtype).reshape(-1, 7).contiguous()
+        self.tol, self.maxiter = tol, maxiter
+        self._trial = None
+        self.cg_iters = 0
+
+    def matches(self, model, input):
+        return model is self.model and _input_key(input) == self.key
+
+    def _nodes(self):
+        return self.param.tensor().reshape(-1, 7)
+
+    def loss(self):
+        s = _fused.call("lm_pgo_loss", self._nodes(), self.Z, self.ei, self.ej, *self.robust)
+        return _allreduce(s, self.group)[0].to(self.dtype)
+
+    def linearize(self):
+        nodes = self._nodes()
+        M, u, cur = _fused.call("lm_pgo_linearize", nodes, self.Z, self.ei, self.ej, *self.robust)
+        Hd, g = _fused.call("lm_pgo_scatter", M, u, self.ei, self.ej, nodes.shape[0])
+        if self.group is not None:
+            packed = torch.cat([Hd.reshape(-1), g.reshape(-1)])
+            _allreduce(packed, self.group)
+            n = Hd.numel()
+            Hd, g = packed[:n].view_as(Hd), packed[n:].view_as(g)
+        return M, Hd, g, cur
+
+    def _matvec(self, M, extra, x):
+        y = _fused.call("lm_pgo_spmv", M, self.ei, self.ej, x, torch.zeros_like(x))
+        return _allreduce(y, self.group) + extra * x
+
+    def trial(self, lin, scale, dmin, dmax):
+        M, Hd, g, cur = lin
+        d = Hd[:, _DIAG21]
+        extra = d.clamp(dmin, dmax) * scale - d                       # added to the diagonal of H
+        blocks = _unpack21(Hd) + torch.diag_embed(extra)
+        Minv = torch.linalg.inv(blocks)                               # block-Jacobi preconditioner
+        b = -g
+        x = torch.zeros_like(b)
+        r = b.clone()
+        z = torch.einsum('nij,nj->ni', Minv, r)
+        p = z.clone()
+        rz = (r * z).sum()
+        bnorm = b.norm()
+        maxiter = self.maxiter if self.maxiter is not None else 10 * b.numel()
+        it = 0
+        while it < maxiter and float(r.norm()) > self.tol * float(bnorm):
+            q = self._matvec(M, extra, p)
+            alpha = rz / (p * q).sum()
+            x = x + alpha * p
+            r = r - alpha * q
+            z = torch.einsum('nij,nj->ni', Minv, r)
+            rz_new = (r * z).sum()
+            p = z + (rz_new / rz) * p
+            rz = rz_new
+            it += 1
+        self.cg_iters = it
+        D = x
+        Hx = _fused.call("lm_pgo_spmv", M, self.ei, self.ej, D, torch.zeros_like(D))
+        Hx = _allreduce(Hx, self.group)
+        predicted = ((D * Hx).sum() + 2 * (D * g).sum()).to(torch.float64).reshape(1)
+        nodes = self._nodes()
+        delta = LieTensor(D, ltype=_lt.se3_type)
+        self._trial = (delta.Exp() * LieTensor(nodes, ltype=SE3_type)).tensor()
+        tl = _fused.call("lm_pgo_loss", self._trial, self.Z, self.ei, self.ej, *self.robust)
+        shard = _allreduce(torch.cat([cur, tl]), self.group)
+        return self._result(torch.cat([shard, predicted, predicted.new_zeros(1)]),
+                            {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
+
+    def accept(self):
+        self.param.copy_(self._trial.view(self.param.shape))
+
+
 def _input_key(input):
     items = input if isinstance(input, (tuple, list)) else (input,)
     return tuple((t.data_ptr(), tuple(t.shape), t.dtype, t._version) if torch.is_tensor(t) else id(t) for t in items)
@@ -125,13 +223,28 @@ def _is_se3_param(p):
     return isinstance(p, Parameter) and getattr(p, 'ltype', None) is SE3_type and p.requires_grad and p.is_cuda is not None
 
 
-def recognize(model, input, params, group=None, robust=(0, 1.0)):
+def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sparse=False):
     """Return a structured problem for (model, input) or None (-> generic dense route)."""
     params = [p for p in params if p.requires_grad]
     if len(params) != 1 or not _is_se3_param(params[0]) or params[0].dtype not in (torch.float32, torch.float64):
         return None
     param = params[0]
     from ..module.reproj import PoseReproj
+    from ..module.pgo import PoseGraph
+    from .solver import CG
+    if isinstance(model, PoseGraph):
+        # block-sparse H needs an iterative solver: taken only when the user asked for one (solver=PCG()/CG(),
+        # or sparse=True as in the reference's bae route); otherwise the generic dense Cholesky route runs.
+        if param is not model.nodes or not (isinstance(solver, CG) or sparse):
+            return None
+        edges, Z = input
+        if not isinstance(Z, LieTensor) or Z.ltype is not SE3_type:
+            return None
+        tol = solver.tol if isinstance(solver, CG) else 1e-8
+        maxiter = solver.maxiter if isinstance(solver, CG) else None
+        return PGOProblem(model, edges, Z, _input_key(input), group, robust, tol, maxiter)
+    if solver is not None and isinstance(solver, CG):
+        return None
     if isinstance(model, PoseReproj):
         if param is not model.poses:
             return None

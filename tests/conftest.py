@@ -99,6 +99,24 @@ def _install_cpu_oracle_lm_kernels():
     def reproj_residual(poses, pts, pix, cidx):
         return t(L.reproj_residual(n(poses), n(pts), n(pix), cidx.numpy()), poses)
 
+    def pgo_linearize(nodes, Z, ei, ej, robust, delta):
+        M, u, c = L.pgo_linearize(n(nodes), n(Z), ei.numpy(), ej.numpy(), robust, delta)
+        return t(M, nodes), t(u, nodes), f64(c)
+
+    def pgo_scatter(M, u, ei, ej, nn):
+        Hd, g = L.pgo_scatter(n(M), n(u), ei.numpy(), ej.numpy(), nn)
+        return t(Hd, M), t(g, M)
+
+    def pgo_spmv(M, ei, ej, x, y0):
+        return t(L.pgo_spmv(n(M), ei.numpy(), ej.numpy(), n(x), n(y0)), M)
+
+    def pgo_loss(nodes, Z, ei, ej, robust, delta):
+        return f64(L.pgo_loss(n(nodes), n(Z), ei.numpy(), ej.numpy(), robust, delta))
+
+    for name, fn in (("lm_pgo_linearize", pgo_linearize), ("lm_pgo_scatter", pgo_scatter), ("lm_pgo_spmv", pgo_spmv),
+                     ("lm_pgo_loss", pgo_loss)):
+        torch.library.impl(f"b200pose::{name}", "CPU")(fn)
+
     for name, fn in (("lm_poseinv_loss", poseinv_loss), ("lm_poseinv_trial", poseinv_trial),
                      ("lm_reproj_accum", reproj_accum), ("lm_solve6_retract", solve6_retract),
                      ("lm_reproj_loss", reproj_loss), ("lm_reproj_residual", reproj_residual)):
