@@ -13,7 +13,7 @@ _lib = None
 
 def build():
     src = os.path.join(HERE, "hostmath.cpp")
-    hdrs = [os.path.join(ROOT, "pypose_b200", "csrc", h) for h in ("lie_math.cuh", "lie_ops.cuh")]
+    hdrs = [os.path.join(ROOT, "pypose_b200", "csrc", h) for h in ("lie_math.cuh", "lie_ops.cuh", "lm_math.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-x", "c++", "-shared", "-fPIC",
@@ -41,3 +41,36 @@ def run(group, op, ins, out_widths):
     if rc != 0:
         raise RuntimeError(f"hostmath_run({group},{op}) -> {rc}")
     return outs
+
+
+def _vp(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def poseinv_trial(P, X, scale, dmin, dmax, kind=0, delta=1.0):
+    P, X = np.ascontiguousarray(P), np.ascontiguousarray(X)
+    Pt, sums = np.empty_like(P), np.zeros(4)
+    lib().hostmath_poseinv_trial(int(P.dtype == np.float64), _vp(P), _vp(X), _vp(Pt), _vp(sums), ctypes.c_double(scale),
+                                 ctypes.c_double(dmin), ctypes.c_double(dmax), int(kind), ctypes.c_double(delta),
+                                 ctypes.c_longlong(P.shape[0]))
+    return Pt, sums
+
+
+def pgo_linearize(nodes, Z, ei, ej, kind=0, delta=1.0):
+    nodes, Z = np.ascontiguousarray(nodes), np.ascontiguousarray(Z)
+    ei, ej = np.ascontiguousarray(ei, dtype=np.int32), np.ascontiguousarray(ej, dtype=np.int32)
+    E = Z.shape[0]
+    M, u, loss = np.empty((E, 21), nodes.dtype), np.empty((E, 6), nodes.dtype), np.zeros(1)
+    lib().hostmath_pgo_linearize(int(nodes.dtype == np.float64), _vp(nodes), _vp(Z), _vp(ei), _vp(ej), _vp(M), _vp(u),
+                                 _vp(loss), int(kind), ctypes.c_double(delta), ctypes.c_longlong(E))
+    return M, u, loss
+
+
+def reproj_rows(poses, pts, pix, cidx):
+    poses, pts, pix = (np.ascontiguousarray(a) for a in (poses, pts, pix))
+    cidx = np.ascontiguousarray(cidx, dtype=np.int32)
+    m = pts.shape[0]
+    r, J = np.empty((m, 2), poses.dtype), np.empty((m, 2, 6), poses.dtype)
+    lib().hostmath_reproj_rows(int(poses.dtype == np.float64), _vp(poses), _vp(pts), _vp(pix), _vp(cidx), _vp(r), _vp(J),
+                               ctypes.c_longlong(m))
+    return r, J

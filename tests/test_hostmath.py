@@ -91,3 +91,34 @@ def test_exp_log_roundtrip_tolerance(grp):
         x2 = hostmath.run(grp, "log_fwd", [X], [K])[0]
         err = np.abs(x2.astype(np.float64) - x.astype(dt).astype(np.float64)) / (1 + np.abs(x))
         assert err.max() <= tol, f"{grp} {dt.__name__}: {err.max():.3e}"
+
+
+# ---- LM per-block math (csrc/lm_math.cuh) vs the LM oracle --------------------------------------------------
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-10), (np.float32, 5e-5)], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind,delta", [(0, 1.0), (1, 0.3), (3, 0.5)])
+def test_lm_poseinv_trial_functor(dt, tol, kind, delta):
+    from oracle import lm_oracle as L
+    from tests.util import rand_group
+    rng = np.random.default_rng(12)
+    P, X = rand_group(rng, "SE3", 500, tmax=2.0).astype(dt), rand_group(rng, "SE3", 500, tmax=2.0).astype(dt)
+    Pt, sums = hostmath.poseinv_trial(P, X, 1.0001, 1e-6, 1e32, kind, delta)
+    Pt_o, sums_o = L.poseinv_trial(P.astype(np.float64), X.astype(np.float64), 1.0001, 1e-6, 1e32, kind, delta)
+    assert np.abs(Pt - Pt_o).max() <= tol * 10
+    np.testing.assert_allclose(sums[0], sums_o[0], rtol=max(tol, 1e-9))
+    np.testing.assert_allclose(sums[2], sums_o[2], rtol=max(tol * 50, 1e-8))
+    assert sums[3] == 0
+
+
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-10), (np.float32, 2e-4)], ids=["f64", "f32"])
+def test_lm_pgo_and_reproj_functors(golden_lm, dt, tol):
+    from oracle import lm_oracle as L
+    g = golden_lm
+    nodes, edges, Z = g["pgo/nodes0"].astype(dt), g["pgo/edges"], g["pgo/Z"].astype(dt)
+    M, u, loss = hostmath.pgo_linearize(nodes, Z, edges[:, 0], edges[:, 1])
+    M_o, u_o, loss_o = L.pgo_linearize(nodes.astype(np.float64), Z.astype(np.float64), edges[:, 0], edges[:, 1])
+    assert np.abs(M - M_o).max() <= tol * np.abs(M_o).max() and np.abs(u - u_o).max() <= tol * max(1, np.abs(u_o).max())
+    np.testing.assert_allclose(loss[0], loss_o[0], rtol=max(tol, 1e-9))
+    poses, pts, pix, cidx = (g[f"reproj/{k}"] for k in ("poses0", "pts", "pix", "cidx"))
+    r, J = hostmath.reproj_rows(poses.astype(dt), pts.astype(dt), pix.astype(dt), cidx)
+    assert np.abs(r - L.reproj_residual(poses, pts, pix, cidx)).max() <= tol
+    assert np.abs(J - L.reproj_jac_rows(poses, pts, cidx)).max() <= tol * 10
