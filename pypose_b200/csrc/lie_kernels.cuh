@@ -146,18 +146,19 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <class Op, int S, int OS> struct TmaLayout {
+template <class Op, int S, int OS, int THREADS = kThreads, int EPT = 1> struct TmaLayout {
   using T = typename Op::T;
-  static constexpr int TILE = kThreads;
+  static constexpr int TILE = THREADS * EPT;
   static constexpr int IN_WORDS = TILE * (Op::DI0 + (Op::NIN > 1 ? Op::DI1 : 0) + (Op::NIN > 2 ? Op::DI2 : 0));
   static constexpr int OUT_WORDS = TILE * (Op::DO0 + (Op::NOUT > 1 ? Op::DO1 : 0));
   static constexpr int BYTES = (S * IN_WORDS + OS * OUT_WORDS) * (int)sizeof(T) + 8 * S;
 };
 
-template <class Op, int S, int OS>
-__global__ void __launch_bounds__(kThreads) stream_kernel_tma(StreamParams<typename Op::T, Op::NIN, Op::NOUT> p) {
+// THREADS threads per CTA, EPT rows per thread per tile (rows tid, tid + THREADS, ...), S input / OS output stages.
+template <class Op, int S, int OS, int THREADS = kThreads, int EPT = 1>
+__global__ void __launch_bounds__(THREADS) stream_kernel_tma(StreamParams<typename Op::T, Op::NIN, Op::NOUT> p) {
   using T = typename Op::T;
-  using L = TmaLayout<Op, S, OS>;
+  using L = TmaLayout<Op, S, OS, THREADS, EPT>;
   constexpr int TILE = L::TILE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T* s_in = reinterpret_cast<T*>(smem_raw);
@@ -212,14 +213,18 @@ __global__ void __launch_bounds__(kThreads) stream_kernel_tma(StreamParams<typen
     T* out1 = out0 + TILE * Op::DO0;
 
     mbar_wait(&full[s], parity);
-    if (tid < cnt) {
-      T i0[Op::DI0], i1[Op::DI1], i2[Op::DI2], o0[Op::DO0], o1[Op::DO1];
-      row_get<Op::DI0>(in0, tid, i0);
-      if (Op::NIN > 1) row_get<Op::DI1>(in1, tid, i1);
-      if (Op::NIN > 2) row_get<Op::DI2>(in2, tid, i2);
-      Op::apply(i0, i1, i2, o0, o1);
-      row_put<Op::DO0>(out0, tid, o0);
-      if (Op::NOUT > 1) row_put<Op::DO1>(out1, tid, o1);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int row = tid + e * THREADS;
+      if (row < cnt) {
+        T i0[Op::DI0], i1[Op::DI1], i2[Op::DI2], o0[Op::DO0], o1[Op::DO1];
+        row_get<Op::DI0>(in0, row, i0);
+        if (Op::NIN > 1) row_get<Op::DI1>(in1, row, i1);
+        if (Op::NIN > 2) row_get<Op::DI2>(in2, row, i2);
+        Op::apply(i0, i1, i2, o0, o1);
+        row_put<Op::DO0>(out0, row, o0);
+        if (Op::NOUT > 1) row_put<Op::DO1>(out1, row, o1);
+      }
     }
     // out[(i+1) % OS] is written next iteration: its previous store (tile i+1-OS) must have been read
     // out of shared memory.  Stores pending now: tiles <= i-1; allow the newest OS-2 of them to stay.
@@ -300,15 +305,15 @@ inline int stream_max_ctas_per_sm() {
   return v;
 }
 
-template <class Op, int S, int OS>
+template <class Op, int S, int OS, int THREADS = kThreads, int EPT = 1>
 int launch_stream_tma(const typename Op::T* const* in, typename Op::T* const* out, long long n, cudaStream_t stream) {
   using T = typename Op::T;
-  using L = TmaLayout<Op, S, OS>;
-  auto kern = stream_kernel_tma<Op, S, OS>;
+  using L = TmaLayout<Op, S, OS, THREADS, EPT>;
+  auto kern = stream_kernel_tma<Op, S, OS, THREADS, EPT>;
   static thread_local int occ = 0;
   if (occ == 0) {
     if (L::BYTES > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, L::BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, L::BYTES);
     if (occ < 1) occ = 1;
     if (occ > stream_max_ctas_per_sm()) occ = stream_max_ctas_per_sm();
   }
@@ -324,8 +329,18 @@ int launch_stream_tma(const typename Op::T* const* in, typename Op::T* const* ou
   chunk = (chunk + 3) & ~3LL;
   grid = (n + chunk - 1) / chunk;
   p.chunk = chunk;
-  kern<<<(unsigned)grid, kThreads, L::BYTES, stream>>>(p);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = L::BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = stream_pdl() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 template <class Op>
