@@ -52,6 +52,16 @@ def main():
             l2.append(float(opt2.step(inp)))
             rej.append(opt2.reject_count)
         res[f"{case}_loss"], res[f"{case}_poses"], res[f"{case}_reject"] = np.array(l2), net2.poses.detach().numpy(), np.array(rej)
+    # PGO: edges sharded, nodes replicated; Hd | g, every PCG matvec and the scalars all-reduced
+    edges, Z = g["pgo/edges"], g["pgo/Z"]
+    E = len(edges)
+    sl = slice(rank * E // world, (rank + 1) * E // world)
+    net3 = pp.module.PoseGraph(pp.SE3(torch.from_numpy(g["pgo/nodes0"].copy())))
+    opt3 = pp.optim.LM(net3, strategy=pp.optim.strategy.TrustRegion(), solver=pp.optim.solver.PCG(tol=1e-12), sparse=True,
+                       group=True)
+    inp3 = (torch.from_numpy(edges[sl]), pp.SE3(torch.from_numpy(Z[sl].copy())))
+    res["pgo_loss"] = np.array([float(opt3.step(inp3)) for _ in range(5)])
+    res["pgo_poses"] = net3.nodes.detach().numpy()
     if rank == 0:
         np.savez(out, **res)
     dist.barrier()

@@ -36,3 +36,5 @@ def test_sharded_lm_world2_matches_reference(tmp_path, golden_lm):
         np.testing.assert_allclose(r[f"{case}_loss"], g[f"{case}/trustregion/loss"], rtol=1e-6)
         np.testing.assert_allclose(r[f"{case}_poses"], g[f"{case}/trustregion/poses"][-1], atol=1e-8)
         np.testing.assert_array_equal(r[f"{case}_reject"], g[f"{case}/trustregion/reject"])
+    np.testing.assert_allclose(r["pgo_loss"], g["pgo/trustregion/loss"], rtol=1e-6)
+    np.testing.assert_allclose(r["pgo_poses"], g["pgo/trustregion/poses"][-1], atol=1e-7)
