@@ -364,6 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-large", dest="no_large", action="store_true", help="skip the 2e8-residual LM leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

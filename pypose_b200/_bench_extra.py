@@ -93,6 +93,38 @@ def run(args, rank, world, dev):
                         "residuals_total": M, "residuals_per_gpu": hi - lo, "scaling": "strong", "dtype": "f32",
                         "config": "1e4 SE3 poses, 1e6 reprojection residuals, block-diagonal JtJ, TrustRegion "
                                   "(BASELINE.json configs[4], single-pose form)"}
+    # ---- the same reprojection problem where the residual passes dominate latency: 1e5 poses, 2e8 residuals in total
+    # (strong scaling; each rank generates only its shard).  This is the size at which residual sharding pays.
+    if not getattr(args, "no_large", False):
+        CL, ML = 100_000, 200_000_000
+        mloc = ML // world
+        gl = torch.Generator(device=dev).manual_seed(77)         # same poses on every rank
+        gtL = pp.se3(0.3 * torch.randn(CL, 6, device=dev, generator=gl)).Exp()
+        initL = pp.se3(0.05 * torch.randn(CL, 6, device=dev, generator=gl)).Exp() * gtL
+        gs = torch.Generator(device=dev).manual_seed(1000 + rank)
+        cidxL = torch.randint(0, CL, (mloc,), device=dev, generator=gs)
+        pcL = torch.rand(mloc, 3, device=dev, generator=gs) * 4 + torch.tensor([-2.0, -2.0, 2.0], device=dev)
+        ptsL = gtL[cidxL].Inv().Act(pcL)
+        pixL = -pcL[:, :2] / pcL[:, 2:]
+        del pcL
+        netL = pp.module.PoseReproj(initL.clone())
+        optL = pp.optim.LM(netL, strategy=pp.optim.strategy.TrustRegion(), group=group)
+        inpL = (ptsL, pixL, cidxL)
+
+        def resetL():
+            with torch.no_grad():
+                netL.poses.copy_(initL)
+            if hasattr(optL, 'loss'):
+                del optL.loss
+            optL.param_groups[0]['damping'] = 1e-6
+        msL = _max(_time_steps(lambda: optL.step(inpL), resetL, 6, 2), world, dev)
+        out["lm_reproj_2e8"] = {"steps_per_s": round(1e3 / msL, 2), "ms_per_step": round(msL, 3), "poses": CL,
+                                "residuals_total": ML, "residuals_per_gpu": mloc, "scaling": "strong", "dtype": "f32",
+                                "streamed_gbs_per_gpu": round(mloc * 2 * 24 / (msL * 1e-3) / 1e9, 1),
+                                "config": "1e5 SE3 poses, 2e8 reprojection residuals, TrustRegion; two residual passes per step"}
+        del netL, optL, inpL, ptsL, pixL, cidxL
+        torch.cuda.empty_cache()
+
     # ---- block-sparse pose graph (two-pose residuals), edges sharded over ranks
     N, extra = 100_000, 200_000
     step = pp.se3(torch.tensor([[1.0, 0.1, 0.0, 0.0, 0.0, 0.2]], device=dev).repeat(N, 1)
