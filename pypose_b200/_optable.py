@@ -112,7 +112,7 @@ LM_OPS = [
      "diag clamp (optimizer.py:657) + damping (:666) + Cholesky solve (solver.py:213-216) + p.add_ (:139-140)"),
     ("b200_lm_reproj_loss",
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),
-      ("const int*", "cidx", "(m) camera of each row"), ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale (optim/kernel.py) with FastTriggs scaling"), ("double", "delta", "kernel parameter")],
+      ("const int*", "seg", "(ncam+1) row offsets per camera"), ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "0 none, 1 Huber, 2 PseudoHuber, 3 Cauchy, 4 SoftLOne, 5 Arctan, 6 Scale (optim/kernel.py) with FastTriggs scaling"), ("double", "delta", "kernel parameter")],
      "model.loss after the update, optimizer.py:673"),
     ("b200_lm_pgo_linearize",
      [("const REAL*", "nodes", "(N,7) SE3 parameters"), ("const REAL*", "Z", "(E,7) relative-pose measurements"),

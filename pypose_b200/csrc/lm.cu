@@ -156,11 +156,10 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __
     sys6_zero(s);
     T loss = T(0);
     const int b = seg[c], e = seg[c + 1];
-    for (int k = b + lane; k < e; k += 32) {
-      const V3<T> p = mk(pts[(long long)k * 3], pts[(long long)k * 3 + 1], pts[(long long)k * 3 + 2]);
+    auto accumulate = [&](const V3<T>& p, T zx, T zy) {
       T rx, ry;
       V3<T> y;
-      reproj_residual(Tc, p, pix[(long long)k * 2], pix[(long long)k * 2 + 1], rx, ry, y);
+      reproj_residual(Tc, p, zx, zy, rx, ry, y);
       T j0[6], j1[6];
       reproj_rows(y, j0, j1);
       T rho, w;
@@ -174,6 +173,21 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __
       sys6_add_row(s, j0, rx);
       sys6_add_row(s, j1, ry);
       loss += rho;
+    };
+    // two observations per lane per iteration, all ten loads issued before the math (memory-level parallelism:
+    // ncu showed the one-at-a-time loop stalled on long_scoreboard with 46 % issue utilisation)
+    int k = b + lane;
+    for (; k + 32 < e; k += 64) {
+      const long long k0 = k, k1 = k + 32;
+      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
+      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
+      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
+      accumulate(p0, z0x, z0y);
+      accumulate(p1, z1x, z1y);
+    }
+    if (k < e) {
+      const long long k0 = k;
+      accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
     }
     // warp reduction of 21 + 6 + 1 values
 #pragma unroll
@@ -235,24 +249,43 @@ __global__ void __launch_bounds__(kLmThreads) lm_solve6_retract_kernel(const T* 
   reduce_sums<2>(acc, ws);
 }
 
-// trial loss over a shard of observations (flat, one thread per observation, pose gathered through L2)
+// trial loss over a shard of observations: one warp per camera (pose in registers), lanes stride over the camera's
+// rows two at a time — the same access pattern as the accumulate kernel without the Jacobian work.
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_reproj_loss_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
-                                                                     const T* __restrict__ pix, const int* __restrict__ cidx,
-                                                                     double* ws, int rk, T rdelta, long long m) {
+                                                                     const T* __restrict__ pix, const int* __restrict__ seg,
+                                                                     double* ws, int rk, T rdelta, int ncam) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
   double acc[1] = {0.0};
-  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
-    const int c = cidx[k];
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
     T pr[7];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) pr[q] = __ldg(poses + (long long)c * 7 + q);
-    const V3<T> p = mk(pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]);
-    T rx, ry;
-    V3<T> y;
-    reproj_residual(load_se3(pr), p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
-    T rho, w;
-    robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
-    acc[0] += (double)rho;
+    for (int q = 0; q < 7; ++q) pr[q] = poses[(long long)c * 7 + q];
+    const Elem<T> Tc = load_se3(pr);
+    const int b = seg[c], e = seg[c + 1];
+    T loss = T(0);
+    auto one = [&](const V3<T>& p, T zx, T zy) {
+      T rx, ry, rho, w;
+      V3<T> y;
+      reproj_residual(Tc, p, zx, zy, rx, ry, y);
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      loss += rho;
+    };
+    int k = b + lane;
+    for (; k + 32 < e; k += 64) {
+      const long long k0 = k, k1 = k + 32;
+      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
+      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
+      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
+      one(p0, z0x, z0y);
+      one(p1, z1x, z1y);
+    }
+    if (k < e) {
+      const long long k0 = k;
+      one(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
+    }
+    acc[0] += (double)loss;
   }
   reduce_sums<1>(acc, ws);
 }
@@ -415,11 +448,11 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
         H, g, P, P_trial, D, ws, (CT)scale, (CT)dmin, (CT)dmax, n);                                                   \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_reproj_loss_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* cidx,           \
-                                            double* ws, int robust, double delta, long long m, void* stream) {        \
-    if (m <= 0) return 0;                                                                                             \
-    lm_reproj_loss_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                       \
-        poses, pts, pix, cidx, ws, robust, (CT)delta, m);                                                             \
+  B200_EXPORT int b200_lm_reproj_loss_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* seg,            \
+                                            double* ws, int robust, double delta, long long ncam, void* stream) {     \
+    if (ncam <= 0) return 0;                                                                                          \
+    lm_reproj_loss_kernel<CT><<<lm_grid(ncam, kLmThreads / 32), kLmThreads, 0, (cudaStream_t)stream>>>(               \
+        poses, pts, pix, seg, ws, robust, (CT)delta, (int)ncam);                                                      \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_reproj_residual_##SFX(const CT* poses, const CT* pts, const CT* pix, const int* cidx,       \

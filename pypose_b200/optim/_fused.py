@@ -54,7 +54,7 @@ torch.library.define(f"{NS}::lm_reproj_accum",
 torch.library.define(f"{NS}::lm_solve6_retract",
                      "(Tensor H, Tensor g, Tensor P, float scale, float dmin, float dmax) -> (Tensor, Tensor, Tensor)")
 torch.library.define(f"{NS}::lm_reproj_loss",
-                     "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx, int robust, float delta) -> Tensor")
+                     "(Tensor poses, Tensor pts, Tensor pix, Tensor seg, int robust, float delta) -> Tensor")
 torch.library.define(f"{NS}::lm_reproj_residual", "(Tensor poses, Tensor pts, Tensor pix, Tensor cidx) -> Tensor")
 
 
@@ -134,12 +134,12 @@ def _solve6_retract(H, g, P, scale, dmin, dmax):
     return Pt, D, ws[:2].clone()
 
 
-def _reproj_loss(poses, pts, pix, cidx, robust=0, delta=1.0):
+def _reproj_loss(poses, pts, pix, seg, robust=0, delta=1.0):
     poses, pts, pix = _same(poses, pts, pix)
-    assert cidx.dtype == torch.int32
+    assert seg.dtype == torch.int32 and seg.numel() == poses.shape[0] + 1
     ws = _workspace(poses.device)
-    _launch("b200_lm_reproj_loss", poses, [_p(poses), _p(pts), _p(pix), _p(cidx), _p(ws), int(robust), float(delta)],
-            pts.shape[0])
+    _launch("b200_lm_reproj_loss", poses, [_p(poses), _p(pts), _p(pix), _p(seg), _p(ws), int(robust), float(delta)],
+            poses.shape[0])
     return ws[:1].clone()
 
 

@@ -93,7 +93,7 @@ class ReprojProblem(_Problem):
         return self.param.tensor().reshape(-1, 7)
 
     def loss(self):
-        s = _fused.call("lm_reproj_loss", self._poses(), self.pts, self.pix, self.cidx, *self.robust)
+        s = _fused.call("lm_reproj_loss", self._poses(), self.pts, self.pix, self.seg, *self.robust)
         return _allreduce(s, self.group)[0].to(self.dtype)
 
     def linearize(self):
@@ -108,7 +108,7 @@ class ReprojProblem(_Problem):
     def trial(self, lin, scale, dmin, dmax):
         H, g, cur = lin
         self._trial, _, sums = _fused.call("lm_solve6_retract", H, g, self._poses(), float(scale), float(dmin), float(dmax))
-        tl = _fused.call("lm_reproj_loss", self._trial, self.pts, self.pix, self.cidx, *self.robust)
+        tl = _fused.call("lm_reproj_loss", self._trial, self.pts, self.pix, self.seg, *self.robust)
         shard = torch.cat([cur, tl])                 # [current loss, trial loss] of this rank's residuals
         shard = _allreduce(shard, self.group)
         return self._result(torch.cat([shard, sums]), {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})

@@ -93,8 +93,9 @@ def _install_cpu_oracle_lm_kernels():
         Pt, D, s = L.solve6_retract(n(H), n(g), n(P), scale, dmin, dmax)
         return t(Pt, P), t(D, P), f64(s)
 
-    def reproj_loss(poses, pts, pix, cidx, robust, delta):
-        return f64(L.reproj_loss(n(poses), n(pts), n(pix), cidx.numpy(), robust, delta))
+    def reproj_loss(poses, pts, pix, seg, robust, delta):
+        cidx = np.repeat(np.arange(poses.shape[0]), np.diff(seg.numpy()))
+        return f64(L.reproj_loss(n(poses), n(pts), n(pix), cidx, robust, delta))
 
     def reproj_residual(poses, pts, pix, cidx):
         return t(L.reproj_residual(n(poses), n(pts), n(pix), cidx.numpy()), poses)

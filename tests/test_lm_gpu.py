@@ -72,7 +72,7 @@ def test_reproj_accum_solve_loss_vs_oracle(dt, rtol, ptol):
     assert np.abs(D.double().cpu().numpy() - D_o).max() <= ptol * 100
     assert np.abs(Pt.double().cpu().numpy() - Pt_o).max() <= ptol * 100
     np.testing.assert_allclose(s2.cpu().numpy()[0], s2_o[0], rtol=rtol * 50)
-    lo = ops.lm_reproj_loss(Pt, td, xd, cd, 0, 1.0).cpu().numpy()[0]
+    lo = ops.lm_reproj_loss(Pt, td, xd, segd, 0, 1.0).cpu().numpy()[0]
     np.testing.assert_allclose(lo, L.reproj_loss(Pt.double().cpu().numpy(), td.double().cpu().numpy(),
                                                  xd.double().cpu().numpy(), cidx[order])[0], rtol=rtol * 10, atol=1e-12)
     r = ops.lm_reproj_residual(pd, td, xd, cd)
