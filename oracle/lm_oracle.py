@@ -191,6 +191,90 @@ def pgo_dense_jac(nodes, Z, ei, ej):
     return D
 
 
+# ------------------------------------------------------------------ bundle adjustment: poses AND points are parameters
+def ba_residual(poses, points, pix, cidx, pidx):
+    """README.md:170-178: project(points[pidx], poses[cidx]) - observations."""
+    y = O.act("SE3", poses[cidx], points[pidx])
+    return -y[:, :2] / y[:, 2:] - pix
+
+
+def ba_jac_rows(poses, points, cidx, pidx):
+    """Jc (m,2,6) as reproj_jac_rows; Jp (m,2,3) = d pi/dy @ R(T) (SE3_Act.backward wrt p, op.py:560-568)."""
+    y = O.act("SE3", poses[cidx], points[pidx])
+    m = y.shape[0]
+    dpi = np.zeros((m, 2, 3))
+    dpi[:, 0, 0] = -1 / y[:, 2]
+    dpi[:, 1, 1] = -1 / y[:, 2]
+    dpi[:, 0, 2] = y[:, 0] / y[:, 2] ** 2
+    dpi[:, 1, 2] = y[:, 1] / y[:, 2] ** 2
+    dy = np.concatenate([np.broadcast_to(np.eye(3), (m, 3, 3)), O.vec2skew(-y)], -1)
+    return dpi @ dy, dpi @ O.SO3_Adj(poses[cidx][:, 3:])
+
+
+def ba_linearize(poses, points, pix, cidx, pidx, kind=0, delta=1.0):
+    r = ba_residual(poses, points, pix, cidx, pidx)
+    Jc, Jp = ba_jac_rows(poses, points, cidx, pidx)
+    rho, w = robust(kind, delta, (r ** 2).sum(-1))
+    sw = np.sqrt(w)
+    Jc, Jp, rs = Jc * sw[:, None, None], Jp * sw[:, None, None], r * sw[:, None]
+    C, P = poses.shape[0], points.shape[0]
+    Hcc, Hpp, gc, gp = np.zeros((C, 6, 6)), np.zeros((P, 3, 3)), np.zeros((C, 6)), np.zeros((P, 3))
+    np.add.at(Hcc, cidx, np.swapaxes(Jc, -1, -2) @ Jc)
+    np.add.at(Hpp, pidx, np.swapaxes(Jp, -1, -2) @ Jp)
+    np.add.at(gc, cidx, (np.swapaxes(Jc, -1, -2) @ rs[..., None])[..., 0])
+    np.add.at(gp, pidx, (np.swapaxes(Jp, -1, -2) @ rs[..., None])[..., 0])
+    iu = np.triu_indices(3)
+    return (Jc.reshape(-1, 12), Jp.reshape(-1, 6), rs, _triu_pack(Hcc), Hpp[:, iu[0], iu[1]], gc, gp,
+            np.array([rho.sum()]))
+
+
+def ba_wtx(Jc, Jp, cidx, pidx, x, npts):
+    v = (Jc.reshape(-1, 2, 6) @ x[cidx][..., None])
+    t = np.zeros((npts, 3))
+    np.add.at(t, pidx, (np.swapaxes(Jp.reshape(-1, 2, 3), -1, -2) @ v)[..., 0])
+    return t
+
+
+def ba_wv(Jc, Jp, cidx, pidx, v, ncam):
+    u = (Jp.reshape(-1, 2, 3) @ v[pidx][..., None])
+    y = np.zeros((ncam, 6))
+    np.add.at(y, cidx, (np.swapaxes(Jc.reshape(-1, 2, 6), -1, -2) @ u)[..., 0])
+    return y
+
+
+def ba_loss(poses, points, pix, cidx, pidx, kind=0, delta=1.0):
+    return np.array([robust(kind, delta, (ba_residual(poses, points, pix, cidx, pidx) ** 2).sum(-1))[0].sum()])
+
+
+def ba_dense_lm_step(poses, points, pix, cidx, pidx, damping, dmin=1e-6, dmax=1e32, reject=16, last=None):
+    """optimizer.py:645-680 on the dense (2m, 7C + 3P) Jacobian, parameters ordered [poses, points_3d]."""
+    C, P, m = poses.shape[0], points.shape[0], len(cidx)
+    R = ba_residual(poses, points, pix, cidx, pidx).reshape(-1)
+    Jc, Jp = ba_jac_rows(poses, points, cidx, pidx)
+    J = np.zeros((2 * m, 7 * C + 3 * P))
+    for k in range(m):
+        J[2 * k:2 * k + 2, 7 * cidx[k]:7 * cidx[k] + 6] = Jc[k]
+        J[2 * k:2 * k + 2, 7 * C + 3 * pidx[k]:7 * C + 3 * pidx[k] + 3] = Jp[k]
+    A = J.T @ J
+    d = np.arange(A.shape[0])
+    A[d, d] = np.clip(A[d, d], dmin, dmax)
+    loss = last = (R ** 2).sum() if last is None else last
+    rej = 0
+    while last <= loss:
+        A[d, d] += A[d, d] * damping
+        L_ = np.linalg.cholesky(A)
+        D = np.linalg.solve(L_.T, np.linalg.solve(L_, -(J.T @ R)))
+        Pn = retract(D[:7 * C].reshape(C, 7)[:, :6], poses)
+        pn = points + D[7 * C:].reshape(P, 3)
+        loss = (ba_residual(Pn, pn, pix, cidx, pidx) ** 2).sum()
+        if last < loss and rej < reject:
+            loss, rej = last, rej + 1
+        else:
+            poses, points = Pn, pn
+            break
+    return poses, points, loss, last, rej
+
+
 # ------------------------------------------------------------------ the dense reference algorithm
 def dense_lm_step(residual_fn, jac_fn, P, damping, dmin=1e-6, dmax=1e32, reject=16, last=None, update=None):
     """One LevenbergMarquardt.step with a constant damping (optimizer.py:645-680) on parameters P (N,7).

@@ -49,6 +49,17 @@ class PoseGraph(nn.Module):                 # examples/module/pgo/pgo.py:15-25
         return (poses.Inv() @ node1.Inv() @ node2).Log().tensor()
 
 
+class BA(nn.Module):                        # README.md:163-198 (without the bae-only sjac / psjac markers)
+    def __init__(self, poses, points_3d):
+        super().__init__()
+        self.poses = ref.Parameter(poses)
+        self.points_3d = ref.Parameter(points_3d)
+
+    def forward(self, observations, camera_indices, point_indices):
+        pts = self.poses[camera_indices].Act(self.points_3d[point_indices])
+        return -pts[..., :2] / pts[..., 2].unsqueeze(-1) - observations
+
+
 def run(model, input, strategy, steps, pname):
     opt = ref.optim.LM(model, strategy=strategy)
     losses, poses, rejects = [], [], []
@@ -111,6 +122,31 @@ def main():
                         ("constant", lambda: ref.optim.strategy.Constant(damping=1e-4))):
         losses, poses, rej = run(PoseGraph(init.clone()), (edges, Zm), strat(), 5, "nodes")
         g[f"pgo/{name}/loss"], g[f"pgo/{name}/poses"], g[f"pgo/{name}/reject"] = losses, poses, rej
+
+    # bundle adjustment: 5 cameras x 16 points, every point seen by 3 cameras, poses AND points optimised
+    torch.manual_seed(31)
+    Cb, Pb = 5, 16
+    gtb = ref.randn_SE3(Cb, sigma=0.15, dtype=torch.float64)
+    ptsw = torch.rand(Pb, 3, dtype=torch.float64) * torch.tensor([4.0, 4.0, 3.0]) + torch.tensor([-2.0, -2.0, 3.0])
+    cb = torch.tensor([(j + o) % Cb for j in range(Pb) for o in range(3)])
+    pb = torch.tensor([j for j in range(Pb) for _ in range(3)])
+    yb = gtb[cb].Act(ptsw[pb])
+    pixb = -yb[:, :2] / yb[:, 2:] + 1e-3 * torch.randn(len(cb), 2, dtype=torch.float64)
+    poses0 = ref.se3(0.03 * torch.randn(Cb, 6, dtype=torch.float64)).Exp() * gtb
+    pts0 = ptsw + 0.05 * torch.randn(Pb, 3, dtype=torch.float64)
+    g["ba/poses0"], g["ba/points0"], g["ba/pix"], g["ba/cidx"], g["ba/pidx"] = (poses0.numpy().copy(), pts0.numpy().copy(),
+                                                                                pixb.numpy().copy(), cb.numpy().copy(), pb.numpy().copy())
+    for name, strat in (("trustregion", lambda: ref.optim.strategy.TrustRegion()),
+                        ("constant", lambda: ref.optim.strategy.Constant(damping=1e-4))):
+        model = BA(poses0.clone(), pts0.clone())
+        opt = ref.optim.LM(model, strategy=strat())
+        losses, ps, qs, rej = [], [], [], []
+        for _ in range(5):
+            losses.append(float(opt.step((pixb, cb, pb))))
+            ps.append(model.poses.detach().clone().numpy()); qs.append(model.points_3d.detach().clone().numpy())
+            rej.append(opt.reject_count)
+        g[f"ba/{name}/loss"], g[f"ba/{name}/poses"], g[f"ba/{name}/points"], g[f"ba/{name}/reject"] = (
+            np.array(losses), np.stack(ps), np.stack(qs), np.array(rej))
 
     # robust kernels (default FastTriggs corrector): reprojection with 10 % gross outliers under Huber,
     # PoseInv under Cauchy (optimizer.py:474-480, corrector.py:73-95, kernel.py)

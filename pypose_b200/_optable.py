@@ -134,6 +134,28 @@ LM_OPS = [
      [("const REAL*", "nodes", "(N,7)"), ("const REAL*", "Z", "(E,7)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
       ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", ""), ("double", "delta", "")],
      "model.loss after the update, optimizer.py:673"),
+    ("b200_lm_ba_linearize",
+     [("const REAL*", "poses", "(C,7)"), ("const REAL*", "points", "(P,3)"), ("const REAL*", "pix", "(m,2)"),
+      ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"), ("REAL*", "Jc", "(m,12) rows of d r/d pose"),
+      ("REAL*", "Jp", "(m,6) rows of d r/d point"), ("REAL*", "rs", "(m,2) (scaled) residual"),
+      ("REAL*", "Hcc", "(C,21) accumulated (zero-initialised by the caller)"), ("REAL*", "Hpp", "(P,6) accumulated"),
+      ("REAL*", "gc", "(C,6) accumulated"), ("REAL*", "gp", "(P,3) accumulated"), ("double*", "ws", "ws[0] = sum rho"),
+      ("int", "robust", ""), ("double", "delta", "")],
+     "modjac + J^T J for the two-parameter reprojection model, README.md:163-198; sparse counterpart "
+     "bae.autograd.graph.jacobian, optimizer.py:637-642"),
+    ("b200_lm_ba_wtx",
+     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+      ("const REAL*", "x", "(C,6)"), ("REAL*", "t", "(P,3) t += W^T x (atomics)")],
+     "off-diagonal block product inside A @ p of the (P)CG loop, optim/solver.py:319-336"),
+    ("b200_lm_ba_wv",
+     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+      ("const REAL*", "v", "(P,3)"), ("REAL*", "y", "(C,6) y += W v (atomics)")],
+     "off-diagonal block product inside A @ p of the (P)CG loop, optim/solver.py:319-336"),
+    ("b200_lm_ba_loss",
+     [("const REAL*", "poses", "(C,7)"), ("const REAL*", "points", "(P,3)"), ("const REAL*", "pix", "(m,2)"),
+      ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"), ("double*", "ws", "ws[0] = sum rho(|r|^2)"),
+      ("int", "robust", ""), ("double", "delta", "")],
+     "model.loss after the update, optimizer.py:673"),
     ("b200_lm_reproj_residual",
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),
       ("const int*", "cidx", "(m)"), ("REAL*", "r", "(m,2)")],

@@ -402,6 +402,114 @@ __global__ void __launch_bounds__(kLmThreads) lm_pgo_loss_kernel(const T* __rest
   reduce_sums<1>(acc, ws);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bundle adjustment: r_k = pi(T_{c_k} p_{j_k}) - z_k with BOTH the poses and the points as parameters
+// (README.md:153-198 sparse example; examples/module/ba).  Per observation: Jc (2x6) and Jp (2x3), stored (already
+// scaled by sqrt(rho')) together with the scaled residual so that the Schur-complement PCG can multiply with
+// W = sum Jc^T Jp and W^T observation by observation without ever forming the reduced camera matrix.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_ba_linearize_kernel(
+    const T* __restrict__ poses, const T* __restrict__ points, const T* __restrict__ pix, const int* __restrict__ cidx,
+    const int* __restrict__ pidx, T* __restrict__ Jc, T* __restrict__ Jp, T* __restrict__ rs, T* __restrict__ Hcc,
+    T* __restrict__ Hpp, T* __restrict__ gc, T* __restrict__ gp, double* ws, int rk, T rdelta, long long m) {
+  double acc[1] = {0.0};
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const long long c = cidx[k], j = pidx[k];
+    T pr[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) pr[q] = __ldg(poses + c * 7 + q);
+    const Elem<T> Tc = load_se3(pr);
+    const V3<T> p = mk(__ldg(points + j * 3), __ldg(points + j * 3 + 1), __ldg(points + j * 3 + 2));
+    T rx, ry;
+    V3<T> y;
+    reproj_residual(Tc, p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
+    T j0[6], j1[6], p0[3], p1[3];
+    reproj_rows(y, j0, j1);
+    reproj_point_rows(Tc, y, p0, p1);
+    T rho, w;
+    robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+    if (rk) {
+      const T sw = m_sqrt(w);
+      rx *= sw; ry *= sw;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { p0[a] *= sw; p1[a] *= sw; }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { Jc[k * 12 + a] = j0[a]; Jc[k * 12 + 6 + a] = j1[a]; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { Jp[k * 6 + a] = p0[a]; Jp[k * 6 + 3 + a] = p1[a]; }
+    rs[k * 2] = rx; rs[k * 2 + 1] = ry;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      atomicAdd(gc + c * 6 + a, j0[a] * rx + j1[a] * ry);
+#pragma unroll
+      for (int b = a; b < 6; ++b) atomicAdd(Hcc + c * 21 + q++, j0[a] * j0[b] + j1[a] * j1[b]);
+    }
+    q = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      atomicAdd(gp + j * 3 + a, p0[a] * rx + p1[a] * ry);
+#pragma unroll
+      for (int b = a; b < 3; ++b) atomicAdd(Hpp + j * 6 + q++, p0[a] * p0[b] + p1[a] * p1[b]);
+    }
+    acc[0] += (double)rho;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+// t[j] += Jp_k^T (Jc_k x[c_k])      (W^T x, cameras -> points)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_ba_wtx_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+                                                                const int* __restrict__ cidx, const int* __restrict__ pidx,
+                                                                const T* __restrict__ x, T* __restrict__ t, long long m) {
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const long long c = cidx[k], j = pidx[k];
+    T v0 = T(0), v1 = T(0);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += Jc[k * 12 + a] * xa; v1 += Jc[k * 12 + 6 + a] * xa; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomicAdd(t + j * 3 + a, Jp[k * 6 + a] * v0 + Jp[k * 6 + 3 + a] * v1);
+  }
+}
+// y[c] += Jc_k^T (Jp_k v[j_k])      (W v, points -> cameras)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_ba_wv_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+                                                               const int* __restrict__ cidx, const int* __restrict__ pidx,
+                                                               const T* __restrict__ v, T* __restrict__ y, long long m) {
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const long long c = cidx[k], j = pidx[k];
+    T u0 = T(0), u1 = T(0);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { const T va = __ldg(v + j * 3 + a); u0 += Jp[k * 6 + a] * va; u1 += Jp[k * 6 + 3 + a] * va; }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) atomicAdd(y + c * 6 + a, Jc[k * 12 + a] * u0 + Jc[k * 12 + 6 + a] * u1);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_ba_loss_kernel(const T* __restrict__ poses, const T* __restrict__ points,
+                                                                 const T* __restrict__ pix, const int* __restrict__ cidx,
+                                                                 const int* __restrict__ pidx, double* ws, int rk, T rdelta,
+                                                                 long long m) {
+  double acc[1] = {0.0};
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const long long c = cidx[k], j = pidx[k];
+    T pr[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) pr[q] = __ldg(poses + c * 7 + q);
+    const V3<T> p = mk(__ldg(points + j * 3), __ldg(points + j * 3 + 1), __ldg(points + j * 3 + 2));
+    T rx, ry, rho, w;
+    V3<T> y;
+    reproj_residual(load_se3(pr), p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
+    robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+    acc[0] += (double)rho;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
 inline unsigned lm_grid(long long work_items, int per_block) {
   long long need = (work_items + per_block - 1) / per_block;
   long long cap = (long long)lm_sms() * 8;
@@ -493,7 +601,42 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
     return (int)cudaGetLastError();                                                                                   \
   }
 
+#define BA_ABI(SFX, CT)                                                                                               \
+  B200_EXPORT int b200_lm_ba_linearize_##SFX(const CT* poses, const CT* points, const CT* pix, const int* cidx,       \
+                                             const int* pidx, CT* Jc, CT* Jp, CT* rs, CT* Hcc, CT* Hpp, CT* gc,       \
+                                             CT* gp, double* ws, int robust, double delta, long long m,               \
+                                             void* stream) {                                                          \
+    if (m <= 0) return 0;                                                                                             \
+    lm_ba_linearize_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                      \
+        poses, points, pix, cidx, pidx, Jc, Jp, rs, Hcc, Hpp, gc, gp, ws, robust, (CT)delta, m);                      \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_wtx_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx, const CT* x,     \
+                                       CT* t, long long m, void* stream) {                                            \
+    if (m <= 0) return 0;                                                                                             \
+    lm_ba_wtx_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(Jc, Jp, cidx, pidx, x, t,   \
+                                                                                          m);                         \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_wv_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx, const CT* v,      \
+                                      CT* y, long long m, void* stream) {                                             \
+    if (m <= 0) return 0;                                                                                             \
+    lm_ba_wv_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(Jc, Jp, cidx, pidx, v, y,    \
+                                                                                         m);                          \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_loss_##SFX(const CT* poses, const CT* points, const CT* pix, const int* cidx,            \
+                                        const int* pidx, double* ws, int robust, double delta, long long m,           \
+                                        void* stream) {                                                               \
+    if (m <= 0) return 0;                                                                                             \
+    lm_ba_loss_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                           \
+        poses, points, pix, cidx, pidx, ws, robust, (CT)delta, m);                                                    \
+    return (int)cudaGetLastError();                                                                                   \
+  }
+
 LM_ABI(f32, float)
 LM_ABI(f64, double)
+BA_ABI(f32, float)
+BA_ABI(f64, double)
 PGO_ABI(f32, float)
 PGO_ABI(f64, double)

@@ -274,4 +274,15 @@ template <typename T> LM_HD void reproj_rows(const V3<T>& y, T (&j0)[6], T (&j1)
   j1[5] = a0 * y.x;              // a0*x
 }
 
+// d pi / d p = d pi/dy R(T)  (2x3): Jacobian of the projection w.r.t. a world point (SE3_Act.backward gp = g @ R,
+// operation.py:560-568)
+template <typename T> LM_HD void reproj_point_rows(const Elem<T>& Tc, const V3<T>& y, T (&p0)[3], T (&p1)[3]) {
+  const T iz = m_rcp(y.z), iz2 = iz * iz;
+  const T a0 = -iz, c0 = y.x * iz2, c1 = y.y * iz2;
+  // rows of dpi/dy: [a0, 0, c0], [0, a0, c1];  row @ R = R^T row
+  const V3<T> r0 = qrot_t(Tc.q, mk(a0, T(0), c0)), r1 = qrot_t(Tc.q, mk(T(0), a0, c1));
+  p0[0] = r0.x; p0[1] = r0.y; p0[2] = r0.z;
+  p1[0] = r1.x; p1[1] = r1.y; p1[2] = r1.z;
+}
+
 }  // namespace b200pose

@@ -1,3 +1,4 @@
 from .reproj import PoseReproj
 from .pgo import PoseGraph
+from .ba import BundleAdjustment
 from .imu_preintegrator import IMUPreintegrator

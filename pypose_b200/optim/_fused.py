@@ -98,6 +98,50 @@ def _pgo_loss(nodes, Z, ei, ej, robust=0, delta=1.0):
     return ws[:1].clone()
 
 
+torch.library.define(f"{NS}::lm_ba_linearize",
+                     "(Tensor poses, Tensor points, Tensor pix, Tensor cidx, Tensor pidx, int robust, float delta) -> "
+                     "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_ba_wtx", "(Tensor Jc, Tensor Jp, Tensor cidx, Tensor pidx, Tensor x, int npts) -> Tensor")
+torch.library.define(f"{NS}::lm_ba_wv", "(Tensor Jc, Tensor Jp, Tensor cidx, Tensor pidx, Tensor v, int ncam) -> Tensor")
+torch.library.define(f"{NS}::lm_ba_loss",
+                     "(Tensor poses, Tensor points, Tensor pix, Tensor cidx, Tensor pidx, int robust, float delta) -> Tensor")
+
+
+def _ba_linearize(poses, points, pix, cidx, pidx, robust=0, delta=1.0):
+    poses, points, pix = _same(poses, points, pix)
+    m, C, P = pix.shape[0], poses.shape[0], points.shape[0]
+    dt, dev = poses.dtype, poses.device
+    ws = _workspace(dev)
+    Jc, Jp, rs = (torch.empty(m, w, dtype=dt, device=dev) for w in (12, 6, 2))
+    Hcc, Hpp = torch.zeros(C, 21, dtype=dt, device=dev), torch.zeros(P, 6, dtype=dt, device=dev)
+    gc, gp = torch.zeros(C, 6, dtype=dt, device=dev), torch.zeros(P, 3, dtype=dt, device=dev)
+    _launch("b200_lm_ba_linearize", poses, [_p(poses), _p(points), _p(pix), _p(cidx), _p(pidx), _p(Jc), _p(Jp), _p(rs),
+                                            _p(Hcc), _p(Hpp), _p(gc), _p(gp), _p(ws), int(robust), float(delta)], m)
+    return Jc, Jp, rs, Hcc, Hpp, gc, gp, ws[:1].clone()
+
+
+def _ba_wtx(Jc, Jp, cidx, pidx, x, npts):
+    t = torch.zeros(npts, 3, dtype=Jc.dtype, device=Jc.device)
+    x = x.contiguous()
+    _launch("b200_lm_ba_wtx", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(x), _p(t)], Jc.shape[0])
+    return t
+
+
+def _ba_wv(Jc, Jp, cidx, pidx, v, ncam):
+    y = torch.zeros(ncam, 6, dtype=Jc.dtype, device=Jc.device)
+    v = v.contiguous()
+    _launch("b200_lm_ba_wv", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(v), _p(y)], Jc.shape[0])
+    return y
+
+
+def _ba_loss(poses, points, pix, cidx, pidx, robust=0, delta=1.0):
+    poses, points, pix = _same(poses, points, pix)
+    ws = _workspace(poses.device)
+    _launch("b200_lm_ba_loss", poses, [_p(poses), _p(points), _p(pix), _p(cidx), _p(pidx), _p(ws), int(robust),
+                                       float(delta)], pix.shape[0])
+    return ws[:1].clone()
+
+
 def _poseinv_loss(P, X, robust=0, delta=1.0):
     P, X = _same(P, X)
     ws = _workspace(P.device)
@@ -151,6 +195,10 @@ def _reproj_residual(poses, pts, pix, cidx):
     return r
 
 
+torch.library.impl(f"{NS}::lm_ba_linearize", "CUDA")(_ba_linearize)
+torch.library.impl(f"{NS}::lm_ba_wtx", "CUDA")(_ba_wtx)
+torch.library.impl(f"{NS}::lm_ba_wv", "CUDA")(_ba_wv)
+torch.library.impl(f"{NS}::lm_ba_loss", "CUDA")(_ba_loss)
 torch.library.impl(f"{NS}::lm_pgo_linearize", "CUDA")(_pgo_linearize)
 torch.library.impl(f"{NS}::lm_pgo_scatter", "CUDA")(_pgo_scatter)
 torch.library.impl(f"{NS}::lm_pgo_spmv", "CUDA")(_pgo_spmv)
@@ -178,7 +226,8 @@ def call(name, *args):
 _DIRECT = {"lm_poseinv_loss": _poseinv_loss, "lm_poseinv_trial": _poseinv_trial, "lm_reproj_accum": _reproj_accum,
            "lm_solve6_retract": _solve6_retract, "lm_reproj_loss": _reproj_loss, "lm_reproj_residual": _reproj_residual,
            "lm_pgo_linearize": _pgo_linearize, "lm_pgo_scatter": _pgo_scatter, "lm_pgo_spmv": _pgo_spmv,
-           "lm_pgo_loss": _pgo_loss}
+           "lm_pgo_loss": _pgo_loss, "lm_ba_linearize": _ba_linearize, "lm_ba_wtx": _ba_wtx, "lm_ba_wv": _ba_wv,
+           "lm_ba_loss": _ba_loss}
 
 LM_OPS = ["lm_poseinv_loss", "lm_poseinv_trial", "lm_reproj_accum", "lm_solve6_retract", "lm_reproj_loss",
           "lm_reproj_residual"]

@@ -215,6 +215,122 @@ class PGOProblem(_Problem):
         self.param.copy_(self._trial.view(self.param.shape))
 
 
+def _unpack6(Hp):
+    """(P, 6) packed upper triangles of 3x3 blocks -> (P, 3, 3)."""
+    iu = torch.triu_indices(3, 3, device=Hp.device)
+    A = Hp.new_zeros(Hp.shape[0], 3, 3)
+    A[:, iu[0], iu[1]] = Hp
+    A[:, iu[1], iu[0]] = Hp
+    return A
+
+
+class BAProblem(_Problem):
+    """Bundle adjustment with poses (C,7) and points (P,3) as parameters, in the reference's parameter order.
+
+    The normal equations [[Hcc, W], [W^T, Hpp]] [dc; dp] = -[gc; gp] (diagonal clamped + damped like the dense
+    branch, optimizer.py:657/666) are solved by eliminating the 3x3 point blocks:
+        (Hcc - W Hpp^-1 W^T) dc = -gc + W Hpp^-1 gp,     dp = Hpp^-1 (-gp - W^T dc)
+    with a block-Jacobi preconditioned CG whose W / W^T products walk the observations (csrc/lm.cu lm_ba_wv / wtx).
+    Observations may be sharded over a process group (blocks, gradients and every product all-reduced)."""
+
+    def __init__(self, model, pix, cidx, pidx, key, group, robust, tol, maxiter):
+        self.model, self.key, self.group, self.robust = model, key, group, robust
+        self.poses, self.points = model.poses, model.points_3d
+        self.dtype = self.poses.dtype
+        self.pix = pix.to(self.dtype).contiguous()
+        self.cidx, self.pidx = cidx.to(torch.int32).contiguous(), pidx.to(torch.int32).contiguous()
+        self.cl, self.pl = cidx.long(), pidx.long()
+        self.tol, self.maxiter = tol, maxiter
+        self._trial = None
+        self.cg_iters = 0
+
+    def matches(self, model, input):
+        return model is self.model and _input_key(input) == self.key
+
+    def _params(self):
+        return self.poses.tensor().reshape(-1, 7), self.points.reshape(-1, 3)
+
+    def loss(self):
+        T, p = self._params()
+        s = _fused.call("lm_ba_loss", T, p, self.pix, self.cidx, self.pidx, *self.robust)
+        return _allreduce(s, self.group)[0].to(self.dtype)
+
+    def linearize(self):
+        T, p = self._params()
+        Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = _fused.call("lm_ba_linearize", T, p, self.pix, self.cidx, self.pidx, *self.robust)
+        if self.group is not None:
+            packed = torch.cat([t.reshape(-1) for t in (Hcc, Hpp, gc, gp)])
+            _allreduce(packed, self.group)
+            outs, o = [], 0
+            for t in (Hcc, Hpp, gc, gp):
+                outs.append(packed[o:o + t.numel()].view_as(t)); o += t.numel()
+            Hcc, Hpp, gc, gp = outs
+        return Jc, Jp, rs, Hcc, Hpp, gc, gp, cur
+
+    def trial(self, lin, scale, dmin, dmax):
+        Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = lin
+        C, P = Hcc.shape[0], Hpp.shape[0]
+        dc, dp = Hcc[:, _DIAG21], Hpp[:, [0, 3, 5]]
+        Hc = _unpack21(Hcc) + torch.diag_embed(dc.clamp(dmin, dmax) * scale - dc)
+        Hp_inv = torch.linalg.inv(_unpack6(Hpp) + torch.diag_embed(dp.clamp(dmin, dmax) * scale - dp))
+
+        def WTx(x):
+            return _allreduce(_fused.call("lm_ba_wtx", Jc, Jp, self.cidx, self.pidx, x, P), self.group)
+
+        def Wv(v):
+            return _allreduce(_fused.call("lm_ba_wv", Jc, Jp, self.cidx, self.pidx, v, C), self.group)
+
+        def pinv(t):
+            return torch.einsum('nij,nj->ni', Hp_inv, t)
+
+        def S(x):                                     # reduced camera system
+            return torch.einsum('nij,nj->ni', Hc, x) - Wv(pinv(WTx(x)))
+
+        # block-Jacobi preconditioner on the Schur diagonal: Hc - sum_k (Jc^T Jp) Hp^-1 (Jp^T Jc)
+        Wk = torch.einsum('kri,krj->kij', Jc.view(-1, 2, 6), Jp.view(-1, 2, 3))
+        Tk = torch.einsum('kia,kab,kjb->kij', Wk, Hp_inv[self.pl], Wk)
+        Sd = Hc.clone().index_add_(0, self.cl, -Tk)
+        if self.group is not None:       # every rank added its local -Tk to the already reduced Hc
+            Sd = Hc + _allreduce(Sd - Hc, self.group)
+        Minv = torch.linalg.inv(Sd)
+        b = -gc + Wv(pinv(gp))
+        x = torch.zeros_like(b)
+        r = b.clone()
+        z = torch.einsum('nij,nj->ni', Minv, r)
+        p = z.clone()
+        rz = (r * z).sum()
+        bnorm = float(b.norm())
+        maxiter = self.maxiter if self.maxiter is not None else 10 * b.numel()
+        it = 0
+        while it < maxiter and float(r.norm()) > self.tol * bnorm:
+            q = S(p)
+            alpha = rz / (p * q).sum()
+            x = x + alpha * p
+            r = r - alpha * q
+            z = torch.einsum('nij,nj->ni', Minv, r)
+            rz_new = (r * z).sum()
+            p = z + (rz_new / rz) * p
+            rz = rz_new
+            it += 1
+        self.cg_iters = it
+        xc = x
+        xp = pinv(-gp - WTx(xc))
+        # predicted = (J D)^T (2 R + J D), per observation (corrected J and R)
+        Jd = torch.einsum('kri,ki->kr', Jc.view(-1, 2, 6), xc[self.cl]) + torch.einsum('kri,ki->kr', Jp.view(-1, 2, 3), xp[self.pl])
+        pred = ((Jd * Jd).sum() + 2 * (rs * Jd).sum()).to(torch.float64).reshape(1)
+        T, pts = self._params()
+        Tn = (LieTensor(xc, ltype=_lt.se3_type).Exp() * LieTensor(T, ltype=SE3_type)).tensor()
+        pn = pts + xp
+        self._trial = (Tn, pn)
+        tl = _fused.call("lm_ba_loss", Tn, pn, self.pix, self.cidx, self.pidx, *self.robust)
+        shard = _allreduce(torch.cat([cur, tl, pred]), self.group)
+        return self._result(torch.cat([shard, shard.new_zeros(1)]), {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
+
+    def accept(self):
+        self.poses.copy_(self._trial[0].view(self.poses.shape))
+        self.points.copy_(self._trial[1].view(self.points.shape))
+
+
 def _input_key(input):
     items = input if isinstance(input, (tuple, list)) else (input,)
     return tuple((t.data_ptr(), tuple(t.shape), t.dtype, t._version) if torch.is_tensor(t) else id(t) for t in items)
@@ -227,6 +343,18 @@ def _is_se3_param(p):
 def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sparse=False):
     """Return a structured problem for (model, input) or None (-> generic dense route)."""
     params = [p for p in params if p.requires_grad]
+    from ..module.ba import BundleAdjustment
+    from .solver import CG
+    if isinstance(model, BundleAdjustment):
+        ok = (len(params) == 2 and params[0] is model.poses and params[1] is model.points_3d
+              and _is_se3_param(model.poses) and (isinstance(solver, CG) or sparse)
+              and model.poses.dtype in (torch.float32, torch.float64))
+        if not ok:
+            return None
+        pix, cidx, pidx = input
+        tol = solver.tol if isinstance(solver, CG) else 1e-8
+        maxiter = solver.maxiter if isinstance(solver, CG) else None
+        return BAProblem(model, pix, cidx, pidx, _input_key(input), group, robust, tol, maxiter)
     if len(params) != 1 or not _is_se3_param(params[0]) or params[0].dtype not in (torch.float32, torch.float64):
         return None
     param = params[0]

@@ -114,6 +114,22 @@ def _install_cpu_oracle_lm_kernels():
     def pgo_loss(nodes, Z, ei, ej, robust, delta):
         return f64(L.pgo_loss(n(nodes), n(Z), ei.numpy(), ej.numpy(), robust, delta))
 
+    def ba_linearize(poses, points, pix, cidx, pidx, robust, delta):
+        outs = L.ba_linearize(n(poses), n(points), n(pix), cidx.numpy(), pidx.numpy(), robust, delta)
+        return tuple(t(o, poses) for o in outs[:7]) + (f64(outs[7]),)
+
+    def ba_wtx(Jc, Jp, cidx, pidx, x, npts):
+        return t(L.ba_wtx(n(Jc), n(Jp), cidx.numpy(), pidx.numpy(), n(x), npts), Jc)
+
+    def ba_wv(Jc, Jp, cidx, pidx, v, ncam):
+        return t(L.ba_wv(n(Jc), n(Jp), cidx.numpy(), pidx.numpy(), n(v), ncam), Jc)
+
+    def ba_loss(poses, points, pix, cidx, pidx, robust, delta):
+        return f64(L.ba_loss(n(poses), n(points), n(pix), cidx.numpy(), pidx.numpy(), robust, delta))
+
+    for name, fn in (("lm_ba_linearize", ba_linearize), ("lm_ba_wtx", ba_wtx), ("lm_ba_wv", ba_wv), ("lm_ba_loss", ba_loss)):
+        torch.library.impl(f"b200pose::{name}", "CPU")(fn)
+
     for name, fn in (("lm_pgo_linearize", pgo_linearize), ("lm_pgo_scatter", pgo_scatter), ("lm_pgo_spmv", pgo_spmv),
                      ("lm_pgo_loss", pgo_loss)):
         torch.library.impl(f"b200pose::{name}", "CPU")(fn)

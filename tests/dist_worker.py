@@ -62,6 +62,16 @@ def main():
     inp3 = (torch.from_numpy(edges[sl]), pp.SE3(torch.from_numpy(Z[sl].copy())))
     res["pgo_loss"] = np.array([float(opt3.step(inp3)) for _ in range(5)])
     res["pgo_poses"] = net3.nodes.detach().numpy()
+    # BA: observations sharded, poses and points replicated
+    pixb, cb, pb = g["ba/pix"], g["ba/cidx"], g["ba/pidx"]
+    Mb = len(cb)
+    sl = slice(rank * Mb // world, (rank + 1) * Mb // world)
+    net4 = pp.module.BundleAdjustment(pp.SE3(torch.from_numpy(g["ba/poses0"].copy())), torch.from_numpy(g["ba/points0"].copy()))
+    opt4 = pp.optim.LM(net4, strategy=pp.optim.strategy.TrustRegion(), solver=pp.optim.solver.PCG(tol=1e-12), sparse=True,
+                       group=True)
+    inp4 = (torch.from_numpy(pixb[sl]), torch.from_numpy(cb[sl]), torch.from_numpy(pb[sl]))
+    res["ba_loss"] = np.array([float(opt4.step(inp4)) for _ in range(5)])
+    res["ba_poses"], res["ba_points"] = net4.poses.detach().numpy(), net4.points_3d.detach().numpy()
     if rank == 0:
         np.savez(out, **res)
     dist.barrier()

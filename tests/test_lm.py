@@ -257,3 +257,33 @@ def test_lm_pgo_matches_reference_trajectory(golden_lm, strategy, route):
         np.testing.assert_allclose(float(loss), g[f"pgo/{strategy}/loss"][k], rtol=1e-6)
         np.testing.assert_allclose(net.nodes.detach().numpy(), g[f"pgo/{strategy}/poses"][k], atol=1e-7)
         assert opt.reject_count == g[f"pgo/{strategy}/reject"][k]
+
+
+def test_oracle_dense_lm_reproduces_reference_ba(golden_lm):
+    g = golden_lm
+    T, p = g["ba/poses0"].copy(), g["ba/points0"].copy()
+    last = None
+    for k in range(5):
+        T, p, loss, last, rej = L.ba_dense_lm_step(T, p, g["ba/pix"], g["ba/cidx"], g["ba/pidx"], damping=1e-4, last=last)
+        last = loss
+        np.testing.assert_allclose(loss, g["ba/constant/loss"][k], rtol=1e-6)
+        np.testing.assert_allclose(T, g["ba/constant/poses"][k], atol=1e-8)
+        np.testing.assert_allclose(p, g["ba/constant/points"][k], atol=1e-8)
+
+
+@pytest.mark.parametrize("strategy", ["constant", "trustregion"])
+@pytest.mark.parametrize("route", ["structured", "generic"])
+def test_lm_bundle_adjustment_matches_reference_trajectory(golden_lm, strategy, route):
+    """Poses + points optimised together: Schur-complement PCG route (tol 1e-12) vs the reference's dense Cholesky LM."""
+    g = golden_lm
+    net = pp.module.BundleAdjustment(pp.SE3(torch.from_numpy(g["ba/poses0"].copy())), torch.from_numpy(g["ba/points0"].copy()))
+    inp = tuple(torch.from_numpy(g[f"ba/{k}"]) for k in ("pix", "cidx", "pidx"))
+    kw = dict(solver=pp.optim.solver.PCG(tol=1e-12), sparse=True) if route == "structured" else {}
+    opt = pp.optim.LM(net, strategy=STRATS[strategy](), **kw)
+    for k in range(5):
+        loss = opt.step(inp)
+        assert (opt._problem is not None) == (route == "structured")
+        np.testing.assert_allclose(float(loss), g[f"ba/{strategy}/loss"][k], rtol=1e-5)
+        np.testing.assert_allclose(net.poses.detach().numpy(), g[f"ba/{strategy}/poses"][k], atol=1e-6)
+        np.testing.assert_allclose(net.points_3d.detach().numpy(), g[f"ba/{strategy}/points"][k], atol=1e-6)
+        assert opt.reject_count == g[f"ba/{strategy}/reject"][k]

@@ -274,3 +274,63 @@ def test_pgo_large_graph_fp32_converges():
     losses = [float(opt.step(inp)) for _ in range(8)]
     assert losses[-1] < 1e-3 * losses[0] or losses[-1] < 1e-4, losses
     assert net(*inp).abs().max().item() < 1e-2
+
+
+def _ba_problem(rng, C, P, per_point, noise_T=0.02, noise_p=0.05, pix_noise=0.0):
+    gt = rand_group(rng, "SE3", C, tmax=0.3, t_sigma=0.3)
+    ptsw = rng.uniform([-2, -2, 3], [2, 2, 6], (P, 3))
+    cidx = (np.repeat(np.arange(P), per_point) * 7 + np.tile(np.arange(per_point), P) * 3) % C
+    pidx = np.repeat(np.arange(P), per_point)
+    y = O.act("SE3", gt[cidx], ptsw[pidx])
+    pix = -y[:, :2] / y[:, 2:] + pix_noise * rng.standard_normal((len(cidx), 2))
+    T0 = O.mul("SE3", O.exp("SE3", noise_T * rng.standard_normal((C, 6))), gt)
+    p0 = ptsw + noise_p * rng.standard_normal((P, 3))
+    return gt, ptsw, T0, p0, pix, cidx, pidx
+
+
+def test_ba_kernels_vs_oracle():
+    rng = np.random.default_rng(15)
+    gt, ptsw, T0, p0, pix, cidx, pidx = _ba_problem(rng, 40, 900, 4, pix_noise=0.01)
+    dt = torch.float64
+    ci, pi_ = torch.from_numpy(cidx.astype(np.int32)).cuda(), torch.from_numpy(pidx.astype(np.int32)).cuda()
+    for kind, delta in ((0, 1.0), (1, 0.02)):
+        outs = ops.lm_ba_linearize(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, kind, delta)
+        outs_o = L.ba_linearize(T0, p0, pix, cidx, pidx, kind, delta)
+        for a, b, nm in zip(outs, outs_o, ("Jc", "Jp", "rs", "Hcc", "Hpp", "gc", "gp", "loss")):
+            assert np.abs(a.cpu().numpy() - b).max() <= 1e-9 * max(1.0, np.abs(b).max()), nm
+    Jc, Jp = outs[0], outs[1]
+    x, v = rng.standard_normal((40, 6)), rng.standard_normal((900, 3))
+    t = ops.lm_ba_wtx(Jc, Jp, ci, pi_, cu(x, dt), 900).cpu().numpy()
+    y = ops.lm_ba_wv(Jc, Jp, ci, pi_, cu(v, dt), 40).cpu().numpy()
+    assert np.abs(t - L.ba_wtx(outs_o[0], outs_o[1], cidx, pidx, x, 900)).max() <= 1e-9 * np.abs(t).max()
+    assert np.abs(y - L.ba_wv(outs_o[0], outs_o[1], cidx, pidx, v, 40)).max() <= 1e-9 * np.abs(y).max()
+    lo = ops.lm_ba_loss(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, 0, 1.0).cpu().numpy()[0]
+    np.testing.assert_allclose(lo, L.ba_loss(T0, p0, pix, cidx, pidx)[0], rtol=1e-10)
+
+
+@pytest.mark.parametrize("strategy", ["constant", "trustregion"])
+def test_lm_bundle_adjustment_reference_trajectory_on_gpu(golden_lm, strategy):
+    g = golden_lm
+    st = {"constant": lambda: pp.optim.strategy.Constant(damping=1e-4), "trustregion": lambda: pp.optim.strategy.TrustRegion()}[strategy]()
+    net = pp.module.BundleAdjustment(pp.SE3(torch.from_numpy(g["ba/poses0"].copy()).cuda()),
+                                     torch.from_numpy(g["ba/points0"].copy()).cuda())
+    inp = tuple(torch.from_numpy(g[f"ba/{k}"]).cuda() for k in ("pix", "cidx", "pidx"))
+    opt = pp.optim.LM(net, strategy=st, solver=pp.optim.solver.PCG(tol=1e-12), sparse=True)
+    for k in range(5):
+        loss = opt.step(inp)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g[f"ba/{strategy}/loss"][k], rtol=1e-5)
+        np.testing.assert_allclose(net.poses.detach().cpu().numpy(), g[f"ba/{strategy}/poses"][k], atol=1e-6)
+        np.testing.assert_allclose(net.points_3d.detach().cpu().numpy(), g[f"ba/{strategy}/points"][k], atol=1e-6)
+        assert opt.reject_count == g[f"ba/{strategy}/reject"][k]
+
+
+def test_ba_large_fp32_converges():
+    """300 cameras, 60 k points, 4.8e5 observations, fp32, Schur PCG(tol 1e-4): loss drops > 1e3x."""
+    rng = np.random.default_rng(16)
+    gt, ptsw, T0, p0, pix, cidx, pidx = _ba_problem(rng, 300, 60_000, 8)
+    net = pp.module.BundleAdjustment(pp.SE3(cu(T0, torch.float32)), cu(p0, torch.float32))
+    inp = (cu(pix, torch.float32), torch.from_numpy(cidx).cuda(), torch.from_numpy(pidx).cuda())
+    opt = pp.optim.LM(net, solver=pp.optim.solver.PCG(tol=1e-4, maxiter=100), sparse=True)
+    losses = [float(opt.step(inp)) for _ in range(8)]
+    assert losses[-1] < 1e-3 * losses[0], losses
