@@ -41,3 +41,31 @@ def imu_integrate(dt, gyro, acc, rot=None, init_rot=None, gravity=(0.0, 0.0, flo
     incre_p = np.cumsum(dp, 1)
     incre_t = np.cumsum(dt, 1)
     return a, incre_p[:, 1:], incre_v[:, 1:], incre_r[:, 1:], incre_t, w[:, 1:]
+
+
+def imu_cov(Rk, Rij, a, dt, gyro_cov, acc_cov, init_cov):
+    """pypose/module/imu_preintegrator.py:428-465, materialising A (B,F+1,9,9) like the reference does."""
+    B, F = dt.shape[:2]
+    dtp = dt.dtype
+    Ha = O.vec2skew(a)
+    Rkm, Rijm = O.SO3_Adj(Rk), O.SO3_Adj(Rij)
+    A = np.broadcast_to(np.eye(9, dtype=dtp), (B, F + 1, 9, 9)).copy()
+    dt1, dt2 = dt[..., None], (dt ** 2)[..., None]
+    A[:, :-1, 0:3, 0:3] = np.swapaxes(Rkm, -1, -2)
+    RH = Rijm @ Ha
+    A[:, :-1, 3:6, 0:3] = -RH * dt1
+    A[:, :-1, 6:9, 0:3] = -0.5 * RH * dt2
+    A[:, :-1, 6:9, 3:6] = np.eye(3, dtype=dtp) * dt1
+    Bg, Ba = np.zeros((B, F, 9, 3), dtp), np.zeros((B, F, 9, 3), dtp)
+    Bg[..., 0:3, :] = O.so3_jr(O.SO3_log(Rk)) * dt1
+    Ba[..., 3:6, :] = Rijm * dt1
+    Ba[..., 6:9, :] = 0.5 * Rijm * dt2
+    Cg = gyro_cov[..., None] * np.eye(3, dtype=dtp)
+    Ca = acc_cov[..., None] * np.eye(3, dtype=dtp)
+    Bc = (Bg @ Cg @ np.swapaxes(Bg, -1, -2) + Ba @ Ca @ np.swapaxes(Ba, -1, -2)) / dt1
+    Bc = np.concatenate([np.broadcast_to(init_cov.reshape(-1, 1, 9, 9), (B, 1, 9, 9)), Bc], 1)
+    L = np.empty_like(A)
+    L[:, F] = A[:, F]
+    for k in range(F - 1, -1, -1):                      # L_k = A_k L_{k+1}   (cumprod(A.flip).flip, left=True)
+        L[:, k] = A[:, k] @ L[:, k + 1]
+    return (L @ Bc @ np.swapaxes(L, -1, -2)).sum(1)

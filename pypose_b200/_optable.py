@@ -194,6 +194,16 @@ SCAN_OPS = [
       ("REAL*", "vel_out", "(B,F,3)"), ("REAL*", "pos_out", "(B,F,3)"), ("long long", "B", "trajectories"),
       ("long long", "F", "samples per trajectory")],
      "IMUPreintegrator.integrate + .predict, pypose/module/imu_preintegrator.py:314-384, 386-426"),
+    ("b200_imu_cov",
+     [("const REAL*", "Rk", "(B,F,4) per-sample rotation increments (w)"), ("const REAL*", "Rij", "(B,F,4) accumulated rotations"),
+      ("const REAL*", "a", "(B,F,3) gravity-compensated accelerations"), ("const REAL*", "dt", "(B,F,1)"),
+      ("const REAL*", "gyro_cov", "(B,1|F,3) diagonal"), ("const REAL*", "acc_cov", "(B,1|F,3) diagonal"),
+      ("long long", "cov_stride_b", "elements between trajectories in gyro/acc_cov"),
+      ("long long", "cov_stride_f", "3 if per-sample, 0 if one per trajectory"),
+      ("const REAL*", "init_cov", "(B,9,9) / (1,9,9)"), ("long long", "init_stride", "81 or 0"),
+      ("REAL*", "cov", "(B,9,9)"), ("REAL*", "work", "B*(3*NC+1)*81 elements, NC = ceil(F/chunk)"),
+      ("long long", "chunk", "time steps per chunk"), ("long long", "B", ""), ("long long", "F", "")],
+     "IMUPreintegrator.propagate_cov, pypose/module/imu_preintegrator.py:428-465"),
 ]
 
 

@@ -15,6 +15,10 @@ torch.library.define(f"{NS}::imu_predict",
                      "float[] gravity) -> (Tensor, Tensor, Tensor)")
 
 
+torch.library.define(f"{NS}::imu_cov",
+                     "(Tensor Rk, Tensor Rij, Tensor a, Tensor dt, Tensor gyro_cov, Tensor acc_cov, Tensor init_cov) -> Tensor")
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -77,6 +81,33 @@ def _imu_predict_cuda(dt, gyro, acc, rot, init_rot, init_pos, init_vel, gravity)
 
 torch.library.impl(f"{NS}::imu_integrate", "CUDA")(_imu_cuda)
 torch.library.impl(f"{NS}::imu_predict", "CUDA")(_imu_predict_cuda)
+
+
+def _imu_cov_cuda(Rk, Rij, a, dt, gyro_cov, acc_cov, init_cov, chunk=128):
+    """(B,F,4), (B,F,4), (B,F,3), (B,F,1), (B,1|F,3), (B,1|F,3), (B|1,9,9) -> (B,9,9)."""
+    B, F = dt.shape[:2]
+    dtype, dev = dt.dtype, dt.device
+    Rk, Rij, a, dt = (t.to(dtype).contiguous() for t in (Rk, Rij, a, dt))
+    gyro_cov = gyro_cov.to(dtype).expand(B, gyro_cov.shape[1], 3).contiguous()
+    acc_cov = acc_cov.to(dtype).expand(B, acc_cov.shape[1], 3).contiguous()
+    assert gyro_cov.shape[1] == acc_cov.shape[1] and gyro_cov.shape[1] in (1, F)
+    init_cov = init_cov.to(dtype).reshape(-1, 9, 9).contiguous()
+    assert init_cov.shape[0] in (1, B)
+    cov = torch.empty(B, 9, 9, dtype=dtype, device=dev)
+    if B * F == 0:
+        return init_cov.expand(B, 9, 9).clone()
+    NC = (F + chunk - 1) // chunk
+    work = torch.empty(B * (3 * NC + 1) * 81, dtype=dtype, device=dev)
+    sym = f"b200_imu_cov_{_C.suffix(dtype)}"
+    with torch.cuda.device(dev):
+        _C.check(_C.fn(sym)(_p(Rk), _p(Rij), _p(a), _p(dt), _p(gyro_cov), _p(acc_cov), gyro_cov.shape[1] * 3,
+                            3 if gyro_cov.shape[1] == F and F > 1 else 0, _p(init_cov),
+                            81 if init_cov.shape[0] == B and B > 1 else 0, _p(cov), _p(work), chunk, B, F,
+                            _C.stream_ptr(dev)), sym)
+    return cov
+
+
+torch.library.impl(f"{NS}::imu_cov", "CUDA")(_imu_cov_cuda)
 
 
 def try_cumprod(input, dim, left):

@@ -176,7 +176,15 @@ def _install_cpu_oracle_scan_kernels():
 
     torch.library.impl("b200pose::cumprod", "CPU")(cumprod)
     torch.library.impl("b200pose::imu_integrate", "CPU")(imu)
+    def imu_cov(Rk, Rij, a, dt, gyro_cov, acc_cov, init_cov):
+        n = lambda t: t.detach().double().numpy()
+        B = dt.shape[0]
+        gc = np.broadcast_to(n(gyro_cov), (B,) + tuple(gyro_cov.shape[1:]))
+        ac = np.broadcast_to(n(acc_cov), (B,) + tuple(acc_cov.shape[1:]))
+        return torch.from_numpy(S.imu_cov(n(Rk), n(Rij), n(a), n(dt), gc, ac, n(init_cov))).to(dt.dtype)
+
     torch.library.impl("b200pose::imu_predict", "CPU")(imu_predict)
+    torch.library.impl("b200pose::imu_cov", "CPU")(imu_cov)
 
 
 _install_cpu_oracle_scan_kernels()

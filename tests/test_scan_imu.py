@@ -145,3 +145,50 @@ def test_imu_config4_size_vs_oracle_subset():
     assert np.abs(out["vel"][:4].cpu().numpy() - Dv).max() <= 1e-9 * (1 + np.abs(Dv).max())
     assert np.abs(out["pos"][:4].cpu().numpy() - Dp).max() <= 1e-9 * (1 + np.abs(Dp).max())
     assert torch.isfinite(out["pos"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("F", [1, 5, 127, 128, 129, 1000])
+def test_imu_cov_kernel_vs_oracle(F):
+    from tests.util import rand_group
+    rng = np.random.default_rng(F)
+    B = 5
+    Rk = rand_group(rng, "SO3", B * F, tmax=0.05).reshape(B, F, 4)
+    Rij = rand_group(rng, "SO3", B * F, tmax=2.0).reshape(B, F, 4)
+    a = rng.standard_normal((B, F, 3)) * 3
+    dt = 0.005 * (1 + 0.2 * rng.random((B, F, 1)))
+    gc, ac = np.abs(rng.standard_normal((B, 1, 3))) * 1e-4, np.abs(rng.standard_normal((B, 1, 3))) * 1e-2
+    A0 = rng.standard_normal((B, 9, 9)) * 1e-3
+    init = A0 @ np.swapaxes(A0, -1, -2)
+    c = lambda x: torch.from_numpy(x).cuda()
+    cov = torch.ops.b200pose.imu_cov(c(Rk), c(Rij), c(a), c(dt), c(gc), c(ac), c(init)).cpu().numpy()
+    ref = S.imu_cov(Rk, Rij, a, dt, gc, ac, init)
+    assert np.abs(cov - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), np.abs(cov - ref).max()
+    # per-sample covariances
+    gcf, acf = np.abs(rng.standard_normal((B, F, 3))) * 1e-4, np.abs(rng.standard_normal((B, F, 3))) * 1e-2
+    cov = torch.ops.b200pose.imu_cov(c(Rk), c(Rij), c(a), c(dt), c(gcf), c(acf), c(init[:1])).cpu().numpy()
+    ref = S.imu_cov(Rk, Rij, a, dt, gcf, acf, init[:1])
+    assert np.abs(cov - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+def test_imu_config4_with_covariance_runs_at_full_size():
+    """BASELINE.json configs[3], second run: prop_cov=True at B=1e3, F=1e4 fp64 (the reference needs 6.5 GB for A alone
+    and was measured at B <= 100); covariance symmetric PSD-ish and finite; first trajectories vs oracle."""
+    torch.manual_seed(1)
+    B, F = 1000, 10_000
+    dt = torch.full((B, F, 1), 0.005, dtype=torch.float64, device="cuda")
+    gyro = 0.1 * torch.randn(B, F, 3, dtype=torch.float64, device="cuda")
+    acc = torch.randn(B, F, 3, dtype=torch.float64, device="cuda") + torch.tensor([0, 0, 9.81], dtype=torch.float64, device="cuda")
+    m = pp.module.IMUPreintegrator(prop_cov=True, reset=True).double().cuda()
+    out = m(dt, gyro, acc)
+    cov = out["cov"]
+    assert cov.shape == (B, 9, 9) and torch.isfinite(cov).all()
+    assert (cov - cov.mT).abs().max() <= 1e-9 * cov.abs().max()
+    inte = S.imu_integrate(dt[:2].cpu().numpy(), gyro[:2].cpu().numpy(), acc[:2].cpu().numpy())
+    a_, Dr, w = inte[0], inte[3], inte[5]
+    gcv = np.full((2, 1, 3), (3.2e-3) ** 2)
+    acv = np.full((2, 1, 3), (8e-2) ** 2)
+    ref = S.imu_cov(w, Dr, a_, dt[:2].cpu().numpy(), gcv.astype(np.float32).astype(np.float64), acv.astype(np.float32).astype(np.float64),
+                    np.zeros((1, 9, 9)))
+    assert np.abs(cov[:2].cpu().numpy() - ref).max() <= 1e-8 * np.abs(ref).max()
