@@ -153,6 +153,34 @@ def run(args, rank, world, dev):
                      "residuals_total": int(6 * E), "cg_iters_last": int(opt3._problem.cg_iters), "scaling": "strong",
                      "dtype": "f32", "config": "PoseGraph Log(Z^-1 A^-1 B), block-sparse H, block-Jacobi PCG(tol=1e-3, maxiter=30)"}
 
+    # ---- bundle adjustment (poses + points), observations sharded over ranks
+    Cb, Pb, per = 1000, 125_000, 8
+    gb = torch.Generator(device=dev).manual_seed(99)
+    gtb = pp.se3(0.2 * torch.randn(Cb, 6, device=dev, generator=gb)).Exp()
+    ptw = torch.rand(Pb, 3, device=dev, generator=gb) * torch.tensor([4.0, 4.0, 3.0], device=dev) + torch.tensor([-2.0, -2.0, 3.0], device=dev)
+    pidx_all = torch.arange(Pb, device=dev).repeat_interleave(per)
+    cidx_all = (pidx_all * 7 + torch.arange(per, device=dev).repeat(Pb) * 3) % Cb
+    yb = gtb[cidx_all].Act(ptw[pidx_all])
+    pixb = -yb[:, :2] / yb[:, 2:]
+    T0 = pp.se3(0.02 * torch.randn(Cb, 6, device=dev, generator=gb)).Exp() * gtb
+    p0 = ptw + 0.05 * torch.randn(Pb, 3, device=dev, generator=gb)
+    Mb = pidx_all.shape[0]
+    slb = slice(rank * Mb // world, (rank + 1) * Mb // world)
+    inp5 = (pixb[slb].contiguous(), cidx_all[slb].contiguous(), pidx_all[slb].contiguous())
+    net5 = pp.module.BundleAdjustment(T0.clone(), p0.clone())
+    opt5 = pp.optim.LM(net5, solver=pp.optim.solver.PCG(tol=1e-3, maxiter=30), sparse=True, group=group)
+
+    def reset5():
+        with torch.no_grad():
+            net5.poses.copy_(T0); net5.points_3d.copy_(p0)
+        if hasattr(opt5, 'loss'):
+            del opt5.loss
+        opt5.param_groups[0]['damping'] = 1e-6
+    ms6 = _max(_time_steps(lambda: opt5.step(inp5), reset5, max(5, steps // 5), 2), world, dev)
+    out["lm_ba"] = {"steps_per_s": round(1e3 / ms6, 1), "ms_per_step": round(ms6, 3), "cameras": Cb, "points": Pb,
+                    "residuals_total": int(2 * Mb), "cg_iters_last": int(opt5._problem.cg_iters), "scaling": "strong",
+                    "dtype": "f32", "config": "bundle adjustment, poses + points, Schur complement + block-Jacobi PCG(tol=1e-3, maxiter=30)"}
+
     # ---- IMU preintegration (trajectories sharded: weak scaling, 1e3 x 1e4 fp64 samples per GPU)
     B, F = 1000, 10_000
     dt = torch.full((B, F, 1), 0.005, dtype=torch.float64, device=dev)
