@@ -127,3 +127,21 @@ def test_quat2unit_and_euler():
     torch.testing.assert_close(u.tensor().norm(dim=-1), torch.ones(1))
     e = pp.SO3(torch.tensor([0.0, 0.0, np.sin(0.25), np.cos(0.25)], dtype=torch.float32)).euler()
     torch.testing.assert_close(e, torch.tensor([0.0, 0.0, 0.5]), atol=1e-6, rtol=0)
+
+
+def test_converters_match_reference_golden():
+    """mat2SO3/SE3/Sim3/RxSO3, from_matrix, euler2SO3, euler (goldens from the reference, incl. quaternion sign)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "convert.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    torch.testing.assert_close(pp.mat2SO3(t("R")).tensor(), t("SO3"), atol=1e-12, rtol=0)
+    torch.testing.assert_close(pp.mat2SE3(t("T")).tensor(), t("SE3"), atol=1e-12, rtol=0)
+    torch.testing.assert_close(pp.mat2SE3(t("T34")).tensor(), t("SE3_34"), atol=1e-12, rtol=0)
+    torch.testing.assert_close(pp.mat2Sim3(t("M")).tensor(), t("Sim3"), atol=1e-11, rtol=0)
+    torch.testing.assert_close(pp.mat2RxSO3(t("M")[:, :3, :3]).tensor(), t("RxSO3"), atol=1e-11, rtol=0)
+    torch.testing.assert_close(pp.from_matrix(t("T"), pp.SE3_type).tensor(), t("SE3"), atol=1e-12, rtol=0)
+    torch.testing.assert_close(pp.euler2SO3(t("euler")).tensor(), t("euler2SO3"), atol=1e-14, rtol=0)
+    torch.testing.assert_close(pp.SO3(t("SO3")).euler(), t("SO3_euler"), atol=1e-12, rtol=0)
+    assert pp.mat2SE3(t("T")).ltype is pp.SE3_type
+    with pytest.raises(ValueError):
+        pp.mat2SO3(2 * t("R"))
