@@ -79,9 +79,9 @@ class PoseInvProblem(_Problem):
 
 
 class ReprojProblem(_Problem):
-    def __init__(self, model, data, key, group, robust=(0, 1.0)):
+    def __init__(self, model, data, key, group, robust=(0, 1.0), param=None):
         self.model, self.key, self.group, self.robust = model, key, group, robust
-        self.param = model.poses
+        self.param = model.poses if param is None else param
         self.dtype = self.param.dtype
         self.pts, self.pix, self.cidx, self.seg = data
         self._trial = None
@@ -137,9 +137,9 @@ class PGOProblem(_Problem):
                reference's clamp (optimizer.py:643/657) + cumulative damping (:664/666).
     Edges may be sharded over a process group: Hd, g, every matvec and the scalars are all-reduced."""
 
-    def __init__(self, model, edges, Z, key, group, robust, tol, maxiter):
+    def __init__(self, model, edges, Z, key, group, robust, tol, maxiter, param=None):
         self.model, self.key, self.group, self.robust = model, key, group, robust
-        self.param = model.nodes
+        self.param = model.nodes if param is None else param
         self.dtype = self.param.dtype
         self.ei = edges[..., 0].to(torch.int32).contiguous()
         self.ej = edges[..., 1].to(torch.int32).contiguous()
@@ -233,9 +233,9 @@ class BAProblem(_Problem):
     with a block-Jacobi preconditioned CG whose W / W^T products walk the observations (csrc/lm.cu lm_ba_wv / wtx).
     Observations may be sharded over a process group (blocks, gradients and every product all-reduced)."""
 
-    def __init__(self, model, pix, cidx, pidx, key, group, robust, tol, maxiter):
+    def __init__(self, model, pix, cidx, pidx, key, group, robust, tol, maxiter, params=None):
         self.model, self.key, self.group, self.robust = model, key, group, robust
-        self.poses, self.points = model.poses, model.points_3d
+        self.poses, self.points = (model.poses, model.points_3d) if params is None else params
         self.dtype = self.poses.dtype
         self.pix = pix.to(self.dtype).contiguous()
         self.cidx, self.pidx = cidx.to(torch.int32).contiguous(), pidx.to(torch.int32).contiguous()
@@ -340,6 +340,67 @@ def _is_se3_param(p):
     return isinstance(p, Parameter) and getattr(p, 'ltype', None) is SE3_type and p.requires_grad and p.is_cuda is not None
 
 
+def _prepare_reproj(param, points, pixels, cidx):
+    """Sort observations by camera and build per-camera row offsets (same as PoseReproj.prepare)."""
+    C = param.shape[0]
+    order = torch.argsort(cidx, stable=True)
+    c_sorted = cidx[order]
+    seg = torch.zeros(C + 1, dtype=torch.int32, device=cidx.device)
+    seg[1:] = torch.cumsum(torch.bincount(c_sorted, minlength=C), 0).to(torch.int32)
+    dt = param.dtype
+    return points[order].to(dt).contiguous(), pixels[order].to(dt).contiguous(), c_sorted.to(torch.int32).contiguous(), seg
+
+
+def _is_index(t, n=None):
+    return torch.is_tensor(t) and t.dtype in (torch.int64, torch.int32) and t.dim() == 1 and (n is None or t.shape[0] == n)
+
+
+def _recognize_by_signature(model, input, params, group, robust, solver, sparse):
+    """User-written modules (e.g. README.md:163-198 `Reproj`, examples/module/pgo `PoseGraph`) reach a fused family
+    when (i) their parameters and inputs have the family's types and shapes and (ii) the output of ONE eager forward
+    pass has the family's shape and the same sum of squares as the family's residual kernel on the same data
+    (relative 1e-4).  Anything else falls through to the generic dense route."""
+    from .solver import CG
+    if not isinstance(input, (tuple, list)) or len(params) not in (1, 2) or not _is_se3_param(params[0]):
+        return None
+    if params[0].dim() != 2 or params[0].dtype not in (torch.float32, torch.float64):
+        return None
+    iterative = isinstance(solver, CG) or sparse
+    tol = solver.tol if isinstance(solver, CG) else 1e-8
+    maxiter = solver.maxiter if isinstance(solver, CG) else None
+    key, cand, M, d = _input_key(input), None, None, None
+    if len(params) == 2 and iterative and len(input) == 3:                           # bundle adjustment
+        pts, (obs, ci, pi_) = params[1], input
+        if (torch.is_tensor(pts) and not isinstance(pts, LieTensor) and pts.dim() == 2 and pts.shape[1] == 3
+                and torch.is_tensor(obs) and obs.dim() == 2 and obs.shape[1] == 2 and _is_index(ci, obs.shape[0])
+                and _is_index(pi_, obs.shape[0])):
+            cand = BAProblem(model, obs, ci, pi_, key, group, (0, 1.0), tol, maxiter, params=(params[0], pts))
+            M, d = obs.shape[0], 2
+    elif len(params) == 1 and len(input) == 2 and iterative:                         # pose graph
+        edges, Z = input
+        if (torch.is_tensor(edges) and edges.dtype in (torch.int64, torch.int32) and edges.dim() == 2 and edges.shape[1] == 2
+                and isinstance(Z, LieTensor) and Z.ltype is SE3_type and Z.shape == (edges.shape[0], 7)):
+            cand = PGOProblem(model, edges, Z, key, group, (0, 1.0), tol, maxiter, param=params[0])
+            M, d = edges.shape[0], 6
+    elif len(params) == 1 and len(input) == 3 and not isinstance(solver, CG):        # single-pose reprojection
+        points, pixels, ci = input
+        if (torch.is_tensor(points) and points.dim() == 2 and points.shape[1] == 3 and torch.is_tensor(pixels)
+                and pixels.shape == (points.shape[0], 2) and _is_index(ci, points.shape[0])):
+            cand = ReprojProblem(model, _prepare_reproj(params[0], points, pixels, ci), key, group, (0, 1.0), param=params[0])
+            M, d = points.shape[0], 2
+    if cand is None:
+        return None
+    with torch.no_grad():
+        out = model(*input)
+    if not torch.is_tensor(out) or tuple(out.shape) != (M, d):
+        return None
+    ours, theirs = float(cand.loss()), float(_allreduce(out.double().square().sum().reshape(1), group)[0])
+    if abs(ours - theirs) > 1e-4 * (1e-12 + abs(theirs)):
+        return None
+    cand.robust = robust
+    return cand
+
+
 def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sparse=False):
     """Return a structured problem for (model, input) or None (-> generic dense route)."""
     params = [p for p in params if p.requires_grad]
@@ -355,6 +416,9 @@ def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sp
         tol = solver.tol if isinstance(solver, CG) else 1e-8
         maxiter = solver.maxiter if isinstance(solver, CG) else None
         return BAProblem(model, pix, cidx, pidx, _input_key(input), group, robust, tol, maxiter)
+    duck = _recognize_by_signature(model, input, params, group, robust, solver, sparse)
+    if duck is not None:
+        return duck
     if len(params) != 1 or not _is_se3_param(params[0]) or params[0].dtype not in (torch.float32, torch.float64):
         return None
     param = params[0]

@@ -287,3 +287,76 @@ def test_lm_bundle_adjustment_matches_reference_trajectory(golden_lm, strategy, 
         np.testing.assert_allclose(net.poses.detach().numpy(), g[f"ba/{strategy}/poses"][k], atol=1e-6)
         np.testing.assert_allclose(net.points_3d.detach().numpy(), g[f"ba/{strategy}/points"][k], atol=1e-6)
         assert opt.reject_count == g[f"ba/{strategy}/reject"][k]
+
+
+# ---- user-written modules reach the fused routes unchanged (recognition by signature + numeric verification) --------
+class UserReproj(nn.Module):                    # README.md:163-198, verbatim structure
+    def __init__(self, poses, points_3d):
+        super().__init__()
+        self.poses = pp.Parameter(poses, sjac=True)
+        self.points_3d = pp.Parameter(points_3d, sjac=True)
+
+    @pp.autograd.function.psjac
+    def project(points, poses):
+        points = poses.Act(points)
+        return -points[..., :2] / points[..., 2].unsqueeze(-1)
+
+    def forward(self, observations, camera_indices, point_indices):
+        poses = self.poses[camera_indices]
+        points = self.points_3d[point_indices]
+        return UserReproj.project(points, poses) - observations
+
+
+class UserPoseGraph(nn.Module):                 # examples/module/pgo/pgo.py:15-25
+    def __init__(self, nodes):
+        super().__init__()
+        self.nodes = pp.Parameter(nodes)
+
+    def forward(self, edges, poses):
+        node1 = self.nodes[edges[..., 0]]
+        node2 = self.nodes[edges[..., 1]]
+        error = poses.Inv() @ node1.Inv() @ node2
+        return error.Log().tensor()
+
+
+class UserOneParamReproj(nn.Module):
+    def __init__(self, cams):
+        super().__init__()
+        self.cams = pp.Parameter(cams)
+
+    def forward(self, points, pixels, cidx):
+        y = self.cams[cidx] @ points
+        return -y[:, :2] / y[:, 2:] - pixels
+
+
+class AlmostReproj(UserOneParamReproj):         # same signature, different residual -> must NOT be recognised
+    def forward(self, points, pixels, cidx):
+        y = self.cams[cidx] @ points
+        return -y[:, :2] / y[:, 2:] - 1.01 * pixels
+
+
+def test_user_written_models_take_the_fused_routes(golden_lm):
+    g = golden_lm
+    t = lambda k: torch.from_numpy(g[k].copy())
+    net = UserReproj(pp.SE3(t("ba/poses0")), t("ba/points0"))
+    opt = pp.optim.LM(net, strategy=STRATS["trustregion"](), solver=pp.optim.solver.PCG(tol=1e-12), sparse=True)
+    for k in range(5):
+        loss = opt.step((t("ba/pix"), t("ba/cidx"), t("ba/pidx")))
+        assert type(opt._problem).__name__ == "BAProblem"
+        np.testing.assert_allclose(float(loss), g["ba/trustregion/loss"][k], rtol=1e-5)
+    net = UserPoseGraph(pp.SE3(t("pgo/nodes0")))
+    opt = pp.optim.LM(net, strategy=STRATS["trustregion"](), solver=pp.optim.solver.PCG(tol=1e-12), sparse=True)
+    for k in range(5):
+        loss = opt.step((t("pgo/edges"), pp.SE3(t("pgo/Z"))))
+        assert type(opt._problem).__name__ == "PGOProblem"
+        np.testing.assert_allclose(float(loss), g["pgo/trustregion/loss"][k], rtol=1e-6)
+    net = UserOneParamReproj(pp.SE3(t("reproj/poses0")))
+    opt = pp.optim.LM(net, strategy=STRATS["trustregion"]())
+    for k in range(4):
+        loss = opt.step((t("reproj/pts"), t("reproj/pix"), t("reproj/cidx")))
+        assert type(opt._problem).__name__ == "ReprojProblem"
+        np.testing.assert_allclose(float(loss), g["reproj/trustregion/loss"][k], rtol=1e-6)
+    net = AlmostReproj(pp.SE3(t("reproj/poses0")))
+    opt = pp.optim.LM(net, strategy=STRATS["trustregion"]())
+    opt.step((t("reproj/pts"), t("reproj/pix"), t("reproj/cidx")))
+    assert opt._problem is None                 # numeric verification rejected it -> generic dense route
