@@ -121,6 +121,8 @@ def run(args, rank, world, dev):
         out["lm_reproj_2e8"] = {"steps_per_s": round(1e3 / msL, 2), "ms_per_step": round(msL, 3), "poses": CL,
                                 "residuals_total": ML, "residuals_per_gpu": mloc, "scaling": "strong", "dtype": "f32",
                                 "streamed_gbs_per_gpu": round(mloc * 2 * 24 / (msL * 1e-3) / 1e9, 1),
+                                "hbm_frac_of_measured_6540": round(mloc * 2 * 24 / (msL * 1e-3) / 1e9 / 6540.5, 3),
+                                "alg_bytes_per_residual_per_pass": 24,
                                 "config": "1e5 SE3 poses, 2e8 reprojection residuals, TrustRegion; two residual passes per step"}
         del netL, optL, inpL, ptsL, pixL, cidxL
         torch.cuda.empty_cache()
