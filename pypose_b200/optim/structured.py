@@ -117,6 +117,33 @@ class ReprojProblem(_Problem):
         self.param.copy_(self._trial.view(self.param.shape))
 
 
+def _pcg(matvec, Minv, b, tol, maxiter, check_every=4):
+    """Block-Jacobi preconditioned CG on (n, 6) block vectors (the algorithm of optim/solver.py:276-340 with
+    M = blockdiag(Minv)).  In-place vector updates with device-side scalars; the residual norm is read back only
+    every `check_every` iterations (each read is a host sync), so up to check_every-1 extra iterations may run."""
+    x = torch.zeros_like(b)
+    r = b.clone()
+    z = torch.einsum('nij,nj->ni', Minv, r)
+    p = z.clone()
+    rz = (r * z).sum()
+    stop = tol * float(b.norm())
+    maxiter = maxiter if maxiter is not None else 10 * b.numel()
+    it = 0
+    while it < maxiter:
+        if it % check_every == 0 and float(r.norm()) <= stop:
+            break
+        q = matvec(p)
+        alpha = rz / (p * q).sum()
+        x.addcmul_(p, alpha)
+        r.addcmul_(q, -alpha)
+        z = torch.einsum('nij,nj->ni', Minv, r)
+        rz_new = (r * z).sum()
+        p.mul_(rz_new / rz).add_(z)
+        rz = rz_new
+        it += 1
+    return x, it
+
+
 _DIAG21 = [0, 6, 11, 15, 18, 20]          # positions of the 6 diagonal entries inside a packed upper triangle
 
 
@@ -179,25 +206,7 @@ class PGOProblem(_Problem):
         extra = d.clamp(dmin, dmax) * scale - d                       # added to the diagonal of H
         blocks = _unpack21(Hd) + torch.diag_embed(extra)
         Minv = torch.linalg.inv(blocks)                               # block-Jacobi preconditioner
-        b = -g
-        x = torch.zeros_like(b)
-        r = b.clone()
-        z = torch.einsum('nij,nj->ni', Minv, r)
-        p = z.clone()
-        rz = (r * z).sum()
-        bnorm = b.norm()
-        maxiter = self.maxiter if self.maxiter is not None else 10 * b.numel()
-        it = 0
-        while it < maxiter and float(r.norm()) > self.tol * float(bnorm):
-            q = self._matvec(M, extra, p)
-            alpha = rz / (p * q).sum()
-            x = x + alpha * p
-            r = r - alpha * q
-            z = torch.einsum('nij,nj->ni', Minv, r)
-            rz_new = (r * z).sum()
-            p = z + (rz_new / rz) * p
-            rz = rz_new
-            it += 1
+        x, it = _pcg(lambda v: self._matvec(M, extra, v), Minv, -g, self.tol, self.maxiter)
         self.cg_iters = it
         D = x
         Hx = _fused.call("lm_pgo_spmv", M, self.ei, self.ej, D, torch.zeros_like(D))
@@ -293,25 +302,7 @@ class BAProblem(_Problem):
         if self.group is not None:       # every rank added its local -Tk to the already reduced Hc
             Sd = Hc + _allreduce(Sd - Hc, self.group)
         Minv = torch.linalg.inv(Sd)
-        b = -gc + Wv(pinv(gp))
-        x = torch.zeros_like(b)
-        r = b.clone()
-        z = torch.einsum('nij,nj->ni', Minv, r)
-        p = z.clone()
-        rz = (r * z).sum()
-        bnorm = float(b.norm())
-        maxiter = self.maxiter if self.maxiter is not None else 10 * b.numel()
-        it = 0
-        while it < maxiter and float(r.norm()) > self.tol * bnorm:
-            q = S(p)
-            alpha = rz / (p * q).sum()
-            x = x + alpha * p
-            r = r - alpha * q
-            z = torch.einsum('nij,nj->ni', Minv, r)
-            rz_new = (r * z).sum()
-            p = z + (rz_new / rz) * p
-            rz = rz_new
-            it += 1
+        x, it = _pcg(S, Minv, -gc + Wv(pinv(gp)), self.tol, self.maxiter)
         self.cg_iters = it
         xc = x
         xp = pinv(-gp - WTx(xc))
