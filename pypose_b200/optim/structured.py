@@ -117,13 +117,19 @@ class ReprojProblem(_Problem):
         self.param.copy_(self._trial.view(self.param.shape))
 
 
+def _bmv(A, x):
+    """Batched tiny mat-vec (n,k,m) @ (n,m) as one fused multiply + reduce: torch.einsum / bmm dispatches these to
+    per-batch GEMV kernels that took 60-70 % of a PGO / BA step (torch.profiler, tools/prof_pgo_ba.py)."""
+    return (A * x.unsqueeze(-2)).sum(-1)
+
+
 def _pcg(matvec, Minv, b, tol, maxiter, check_every=4):
     """Block-Jacobi preconditioned CG on (n, 6) block vectors (the algorithm of optim/solver.py:276-340 with
     M = blockdiag(Minv)).  In-place vector updates with device-side scalars; the residual norm is read back only
     every `check_every` iterations (each read is a host sync), so up to check_every-1 extra iterations may run."""
     x = torch.zeros_like(b)
     r = b.clone()
-    z = torch.einsum('nij,nj->ni', Minv, r)
+    z = _bmv(Minv, r)
     p = z.clone()
     rz = (r * z).sum()
     stop = tol * float(b.norm())
@@ -136,7 +142,7 @@ def _pcg(matvec, Minv, b, tol, maxiter, check_every=4):
         alpha = rz / (p * q).sum()
         x.addcmul_(p, alpha)
         r.addcmul_(q, -alpha)
-        z = torch.einsum('nij,nj->ni', Minv, r)
+        z = _bmv(Minv, r)
         rz_new = (r * z).sum()
         p.mul_(rz_new / rz).add_(z)
         rz = rz_new
@@ -290,14 +296,16 @@ class BAProblem(_Problem):
             return _allreduce(_fused.call("lm_ba_wv", Jc, Jp, self.cidx, self.pidx, v, C), self.group)
 
         def pinv(t):
-            return torch.einsum('nij,nj->ni', Hp_inv, t)
+            return _bmv(Hp_inv, t)
 
         def S(x):                                     # reduced camera system
-            return torch.einsum('nij,nj->ni', Hc, x) - Wv(pinv(WTx(x)))
+            return _bmv(Hc, x) - Wv(pinv(WTx(x)))
 
         # block-Jacobi preconditioner on the Schur diagonal: Hc - sum_k (Jc^T Jp) Hp^-1 (Jp^T Jc)
-        Wk = torch.einsum('kri,krj->kij', Jc.view(-1, 2, 6), Jp.view(-1, 2, 3))
-        Tk = torch.einsum('kia,kab,kjb->kij', Wk, Hp_inv[self.pl], Wk)
+        Jc3, Jp3 = Jc.view(-1, 2, 6), Jp.view(-1, 2, 3)
+        Wk = Jc3[:, 0, :, None] * Jp3[:, 0, None, :] + Jc3[:, 1, :, None] * Jp3[:, 1, None, :]          # (m,6,3) = Jc^T Jp
+        WH = (Wk.unsqueeze(-1) * Hp_inv[self.pl].unsqueeze(1)).sum(-2)                                  # (m,6,3) = Wk Hp^-1
+        Tk = (WH.unsqueeze(2) * Wk.unsqueeze(1)).sum(-1)                                                # (m,6,6)
         Sd = Hc.clone().index_add_(0, self.cl, -Tk)
         if self.group is not None:       # every rank added its local -Tk to the already reduced Hc
             Sd = Hc + _allreduce(Sd - Hc, self.group)
@@ -307,7 +315,7 @@ class BAProblem(_Problem):
         xc = x
         xp = pinv(-gp - WTx(xc))
         # predicted = (J D)^T (2 R + J D), per observation (corrected J and R)
-        Jd = torch.einsum('kri,ki->kr', Jc.view(-1, 2, 6), xc[self.cl]) + torch.einsum('kri,ki->kr', Jp.view(-1, 2, 3), xp[self.pl])
+        Jd = _bmv(Jc3, xc[self.cl]) + _bmv(Jp3, xp[self.pl])
         pred = ((Jd * Jd).sum() + 2 * (rs * Jd).sum()).to(torch.float64).reshape(1)
         T, pts = self._params()
         Tn = (LieTensor(xc, ltype=_lt.se3_type).Exp() * LieTensor(T, ltype=SE3_type)).tensor()
