@@ -160,6 +160,58 @@ LM_OPS = [
      [("const REAL*", "poses", "(ncam,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),
       ("const int*", "cidx", "(m)"), ("REAL*", "r", "(m,2)")],
      "model.forward of the reprojection model, README.md:170-178"),
+    ("b200_lm_blk6_damp_inv",
+     [("const REAL*", "H", "(n,21) packed upper triangles of symmetric 6x6 blocks"), ("double", "scale", "prod(1+damping)"),
+      ("double", "dmin", "diag clamp min"), ("double", "dmax", "diag clamp max"),
+      ("REAL*", "Hd", "(n,21) block with diag <- clamp(diag)*scale, or NULL"),
+      ("REAL*", "extra", "(n,6) amount added to the diagonal, or NULL"),
+      ("REAL*", "Minv", "(n,21) inverse of the damped block (block-Jacobi preconditioner), or NULL")],
+     "A.diagonal().clamp_ + cumulative damping, optimizer.py:657/666; block-Jacobi preconditioner of the PCG, solver.py:276-340"),
+    ("b200_lm_pt3_damp_inv",
+     [("const REAL*", "H", "(P,6) packed symmetric 3x3 point blocks"), ("double", "scale", ""), ("double", "dmin", ""),
+      ("double", "dmax", ""), ("REAL*", "Hinv", "(P,6) inverse of the clamped + damped block")],
+     "point-block elimination of the Schur complement (the reference solves the full sparse system, optimizer.py:637-643)"),
+    ("b200_lm_pt3_apply",
+     [("const REAL*", "A6", "(P,6) packed symmetric 3x3"), ("const REAL*", "t", "(P,3)"), ("double", "alpha", ""),
+      ("REAL*", "out", "(P,3) alpha * A t")],
+     "back-substitution dp = Hpp^-1 (-gp - W^T dc)"),
+    ("b200_lm_pgo_pcg",
+     [("const REAL*", "M", "(E,21) per-edge J^T J"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
+      ("long long", "E", "edges"), ("const REAL*", "Minv", "(n,21) preconditioner blocks"),
+      ("const REAL*", "extra", "(n,6) clamp/damping added to diag H"), ("const REAL*", "g", "(n,6) J^T R; solves (H+extra) x = -g"),
+      ("REAL*", "x", "(n,6) solution"), ("REAL*", "r", "(n,6) work"), ("REAL*", "z", "(n,6) work"), ("REAL*", "p", "(n,6) work"),
+      ("REAL*", "q", "(n,6) work"),
+      ("double*", "cg", "(8) state: rz[2], p.Ap, |r|^2, stop^2, done flag, iterations, maxiter"),
+      ("double*", "ws", "reduction workspace"), ("double", "tol", "stop when |r| <= tol |b|"),
+      ("long long", "maxiter", ""), ("long long", "first_iter", "0 initialises the state; otherwise continue"),
+      ("long long", "iters", "iterations to enqueue (no-ops once the done flag is set)")],
+     "PCG.forward loop, optim/solver.py:312-340, with M = block-Jacobi; enqueues `iters` iterations without a host sync"),
+    ("b200_lm_pgo_predicted",
+     [("const REAL*", "M", "(E,21)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"), ("long long", "E", ""),
+      ("const REAL*", "D", "(n,6) step"), ("const REAL*", "g", "(n,6) J^T R"), ("double*", "ws", "ws[0] = D^T H D + 2 D^T g")],
+     "TrustRegion 'predicted' reduction (J D)^T (2 R + J D), optim/strategy.py:143"),
+    ("b200_lm_ba_schur_diag",
+     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+      ("const REAL*", "Hpinv", "(P,6)"), ("REAL*", "Sd", "(C,21) in: damped Hcc; out: minus sum_k W_k Hpp^-1 W_k^T (atomics)")],
+     "diagonal blocks of the reduced camera system (preconditioner of the Schur PCG)"),
+    ("b200_lm_ba_wv_pinv",
+     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+      ("const REAL*", "Hpinv", "(P,6)"), ("const REAL*", "t", "(P,3)"), ("REAL*", "y", "(C,6) y -= W Hpp^-1 t (warp-aggregated atomics)")],
+     "off-diagonal product of the reduced camera system, optim/solver.py:319-336"),
+    ("b200_lm_ba_pcg",
+     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+      ("long long", "m", "observations"), ("const REAL*", "Hc", "(C,21) damped camera blocks"), ("const REAL*", "Hpinv", "(P,6)"),
+      ("const REAL*", "Minv", "(C,21) preconditioner blocks"), ("const REAL*", "bneg", "(C,6) minus the right-hand side"),
+      ("REAL*", "x", "(C,6) solution"), ("REAL*", "r", "(C,6)"), ("REAL*", "z", "(C,6)"), ("REAL*", "p", "(C,6)"), ("REAL*", "q", "(C,6)"),
+      ("REAL*", "t", "(P,3) work"), ("double*", "cg", "(8) state, see b200_lm_pgo_pcg"), ("double*", "ws", "reduction workspace"),
+      ("double", "tol", ""), ("long long", "maxiter", ""), ("long long", "P", "points"), ("long long", "first_iter", ""),
+      ("long long", "iters", "")],
+     "PCG on the Schur complement (Hcc - W Hpp^-1 W^T) dc = rhs; optim/solver.py:312-340"),
+    ("b200_lm_ba_predicted",
+     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const REAL*", "rs", "(m,2)"), ("const int*", "cidx", "(m)"),
+      ("const int*", "pidx", "(m)"), ("const REAL*", "xc", "(C,6)"), ("const REAL*", "xp", "(P,3)"),
+      ("double*", "ws", "ws[0] = sum (J d)^T (2 r + J d)")],
+     "TrustRegion 'predicted' reduction, optim/strategy.py:143"),
 ]
 
 

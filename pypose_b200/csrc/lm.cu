@@ -7,76 +7,9 @@
 // Scalars that the host control flow reads (loss, trial loss, predicted reduction) are reduced on the
 // device in fp64: per-CTA partials, then the last CTA to finish folds them in a fixed order, so results
 // are deterministic for a given grid.  Work is enqueued on the caller's stream; nothing synchronises.
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include "lm_math.cuh"
+#include "lm_common.cuh"
 
 namespace b200pose {
-
-#define B200_EXPORT extern "C" __attribute__((visibility("default")))
-constexpr int kLmThreads = 128;
-constexpr int kMaxSums = 4;
-
-inline int lm_sms() {
-  static thread_local int dev_cached = -1, sms = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev != dev_cached) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
-  return sms;
-}
-
-// Block-reduce NS doubles per thread, store the CTA partial, and let the last CTA produce the totals.
-// workspace layout (doubles): [0 .. NS) totals | [7] ticket (as unsigned) | [8 ..) partials[grid][NS]
-template <int NS>
-__device__ __forceinline__ void reduce_sums(double (&v)[NS], double* ws) {
-  __shared__ double sh[kLmThreads / 32][NS];
-  __shared__ bool is_last;
-#pragma unroll
-  for (int k = 0; k < NS; ++k)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0)
-#pragma unroll
-    for (int k = 0; k < NS; ++k) sh[warp][k] = v[k];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double* part = ws + 8 + (size_t)blockIdx.x * NS;
-#pragma unroll
-    for (int k = 0; k < NS; ++k) {
-      double t = 0;
-      for (int w = 0; w < kLmThreads / 32; ++w) t += sh[w][k];
-      part[k] = t;
-    }
-    __threadfence();
-    unsigned* ticket = reinterpret_cast<unsigned*>(ws + 7);
-    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    // fixed-order fold by one warp: lane-strided partial sums, then a shuffle tree
-    if (threadIdx.x < 32) {
-      double t[NS];
-#pragma unroll
-      for (int k = 0; k < NS; ++k) t[k] = 0;
-      for (unsigned b = threadIdx.x; b < gridDim.x; b += 32)
-#pragma unroll
-        for (int k = 0; k < NS; ++k) t[k] += ws[8 + (size_t)b * NS + k];
-#pragma unroll
-      for (int k = 0; k < NS; ++k)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
-      if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NS; ++k) ws[k] = t[k];
-        *reinterpret_cast<unsigned*>(ws + 7) = 0u;   // re-arm the ticket for the next launch
-      }
-    }
-  }
-}
-
-template <typename T> __device__ __forceinline__ Elem<T> load_se3(const T* p) { return load_elem<SE3g, T>(p); }
 
 // ------------------------------------------------------------------------------------------------
 // PoseInv (BASELINE.json configs[2], README.md:120-135 InvNet): residual Log(P_i X_i), one 6x6 system per pose.
@@ -414,49 +347,68 @@ __global__ void __launch_bounds__(kLmThreads) lm_ba_linearize_kernel(
     const int* __restrict__ pidx, T* __restrict__ Jc, T* __restrict__ Jp, T* __restrict__ rs, T* __restrict__ Hcc,
     T* __restrict__ Hpp, T* __restrict__ gc, T* __restrict__ gp, double* ws, int rk, T rdelta, long long m) {
   double acc[1] = {0.0};
-  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
-    const long long c = cidx[k], j = pidx[k];
-    T pr[7];
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: the camera-side sums are combined across the warp before the atomics (seg_atomic_add)
+  for (long long k0 = (long long)blockIdx.x * kLmThreads + (threadIdx.x - lane); k0 < m; k0 += (long long)gridDim.x * kLmThreads) {
+    const long long k = k0 + lane;
+    const bool active = k < m;
+    long long c = 0;
+    T cam[27];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) pr[q] = __ldg(poses + c * 7 + q);
-    const Elem<T> Tc = load_se3(pr);
-    const V3<T> p = mk(__ldg(points + j * 3), __ldg(points + j * 3 + 1), __ldg(points + j * 3 + 2));
-    T rx, ry;
-    V3<T> y;
-    reproj_residual(Tc, p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
-    T j0[6], j1[6], p0[3], p1[3];
-    reproj_rows(y, j0, j1);
-    reproj_point_rows(Tc, y, p0, p1);
-    T rho, w;
-    robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
-    if (rk) {
-      const T sw = m_sqrt(w);
-      rx *= sw; ry *= sw;
+    for (int a = 0; a < 27; ++a) cam[a] = T(0);
+    if (active) {
+      c = cidx[k];
+      const long long j = pidx[k];
+      T pr[7];
 #pragma unroll
-      for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+      for (int q = 0; q < 7; ++q) pr[q] = __ldg(poses + c * 7 + q);
+      const Elem<T> Tc = load_se3(pr);
+      const V3<T> p = mk(__ldg(points + j * 3), __ldg(points + j * 3 + 1), __ldg(points + j * 3 + 2));
+      T rx, ry;
+      V3<T> y;
+      reproj_residual(Tc, p, pix[k * 2], pix[k * 2 + 1], rx, ry, y);
+      T j0[6], j1[6], p0[3], p1[3];
+      reproj_rows(y, j0, j1);
+      reproj_point_rows(Tc, y, p0, p1);
+      T rho, w;
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      if (rk) {
+        const T sw = m_sqrt(w);
+        rx *= sw; ry *= sw;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { p0[a] *= sw; p1[a] *= sw; }
+        for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { p0[a] *= sw; p1[a] *= sw; }
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { Jc[k * 12 + a] = j0[a]; Jc[k * 12 + 6 + a] = j1[a]; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { Jp[k * 6 + a] = p0[a]; Jp[k * 6 + 3 + a] = p1[a]; }
+      rs[k * 2] = rx; rs[k * 2 + 1] = ry;
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        cam[21 + a] = j0[a] * rx + j1[a] * ry;
+#pragma unroll
+        for (int b = a; b < 6; ++b) cam[q++] = j0[a] * j0[b] + j1[a] * j1[b];
+      }
+      q = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        atomicAdd(gp + j * 3 + a, p0[a] * rx + p1[a] * ry);
+#pragma unroll
+        for (int b = a; b < 3; ++b) atomicAdd(Hpp + j * 6 + q++, p0[a] * p0[b] + p1[a] * p1[b]);
+      }
+      acc[0] += (double)rho;
     }
+    // Hcc (21) and gc (6) live in different arrays: two segmented adds with the same key
+    T hc[21], g6[6];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { Jc[k * 12 + a] = j0[a]; Jc[k * 12 + 6 + a] = j1[a]; }
+    for (int a = 0; a < 21; ++a) hc[a] = cam[a];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { Jp[k * 6 + a] = p0[a]; Jp[k * 6 + 3 + a] = p1[a]; }
-    rs[k * 2] = rx; rs[k * 2 + 1] = ry;
-    int q = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      atomicAdd(gc + c * 6 + a, j0[a] * rx + j1[a] * ry);
-#pragma unroll
-      for (int b = a; b < 6; ++b) atomicAdd(Hcc + c * 21 + q++, j0[a] * j0[b] + j1[a] * j1[b]);
-    }
-    q = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      atomicAdd(gp + j * 3 + a, p0[a] * rx + p1[a] * ry);
-#pragma unroll
-      for (int b = a; b < 3; ++b) atomicAdd(Hpp + j * 6 + q++, p0[a] * p0[b] + p1[a] * p1[b]);
-    }
-    acc[0] += (double)rho;
+    for (int a = 0; a < 6; ++a) g6[a] = cam[21 + a];
+    seg_atomic_add<T, 21>(Hcc + c * 21, c, hc, active);
+    seg_atomic_add<T, 6>(gc + c * 6, c, g6, active);
   }
   reduce_sums<1>(acc, ws);
 }
@@ -480,13 +432,22 @@ template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_ba_wv_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
                                                                const int* __restrict__ cidx, const int* __restrict__ pidx,
                                                                const T* __restrict__ v, T* __restrict__ y, long long m) {
-  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
-    const long long c = cidx[k], j = pidx[k];
-    T u0 = T(0), u1 = T(0);
+  const int lane = threadIdx.x & 31;
+  for (long long k0 = (long long)blockIdx.x * kLmThreads + (threadIdx.x - lane); k0 < m; k0 += (long long)gridDim.x * kLmThreads) {
+    const long long k = k0 + lane;
+    const bool active = k < m;
+    long long c = 0;
+    T out[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    if (active) {
+      c = cidx[k];
+      const long long j = pidx[k];
+      T u0 = T(0), u1 = T(0);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { const T va = __ldg(v + j * 3 + a); u0 += Jp[k * 6 + a] * va; u1 += Jp[k * 6 + 3 + a] * va; }
+      for (int a = 0; a < 3; ++a) { const T va = __ldg(v + j * 3 + a); u0 += Jp[k * 6 + a] * va; u1 += Jp[k * 6 + 3 + a] * va; }
 #pragma unroll
-    for (int a = 0; a < 6; ++a) atomicAdd(y + c * 6 + a, Jc[k * 12 + a] * u0 + Jc[k * 12 + 6 + a] * u1);
+      for (int a = 0; a < 6; ++a) out[a] = Jc[k * 12 + a] * u0 + Jc[k * 12 + 6 + a] * u1;
+    }
+    seg_atomic_add<T, 6>(y + c * 6, c, out, active);
   }
 }
 template <typename T>
@@ -508,13 +469,6 @@ __global__ void __launch_bounds__(kLmThreads) lm_ba_loss_kernel(const T* __restr
     acc[0] += (double)rho;
   }
   reduce_sums<1>(acc, ws);
-}
-
-inline unsigned lm_grid(long long work_items, int per_block) {
-  long long need = (work_items + per_block - 1) / per_block;
-  long long cap = (long long)lm_sms() * 8;
-  if (need < 1) need = 1;
-  return (unsigned)(need < cap ? need : cap);
 }
 
 }  // namespace b200pose

@@ -1,0 +1,185 @@
+// lm_common.cuh — shared by lm.cu and pcg.cu: launch geometry and the deterministic fp64 last-block reduction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lm_math.cuh"
+
+namespace b200pose {
+
+#define B200_EXPORT extern "C" __attribute__((visibility("default")))
+constexpr int kLmThreads = 128;
+constexpr int kMaxSums = 4;
+
+static inline int lm_sms() {
+  static thread_local int dev_cached = -1, sms = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != dev_cached) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+  return sms;
+}
+
+// Block-reduce NS doubles per thread, store the CTA partial, and let the last CTA produce the totals.
+// workspace layout (doubles): [0 .. NS) totals | [7] ticket (as unsigned) | [8 ..) partials[grid][NS]
+template <int NS>
+__device__ __forceinline__ bool reduce_sums(double (&v)[NS], double* ws) {
+  __shared__ double sh[kLmThreads / 32][NS];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int k = 0; k < NS; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sh[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* part = ws + 8 + (size_t)blockIdx.x * NS;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double t = 0;
+      for (int w = 0; w < kLmThreads / 32; ++w) t += sh[w][k];
+      part[k] = t;
+    }
+    __threadfence();
+    unsigned* ticket = reinterpret_cast<unsigned*>(ws + 7);
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    // fixed-order fold by one warp: lane-strided partial sums, then a shuffle tree
+    if (threadIdx.x < 32) {
+      double t[NS];
+#pragma unroll
+      for (int k = 0; k < NS; ++k) t[k] = 0;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += 32)
+#pragma unroll
+        for (int k = 0; k < NS; ++k) t[k] += ws[8 + (size_t)b * NS + k];
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) ws[k] = t[k];
+        *reinterpret_cast<unsigned*>(ws + 7) = 0u;   // re-arm the ticket for the next launch
+        return true;                                 // thread 0 of the last CTA: totals are in ws[0..NS)
+      }
+    }
+  }
+  return false;
+}
+
+template <typename T> __device__ __forceinline__ Elem<T> load_se3(const T* p) { return load_elem<SE3g, T>(p); }
+
+static inline unsigned lm_grid(long long work_items, int per_block) {
+  long long need = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)lm_sms() * 8;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+}  // namespace b200pose
+
+namespace b200pose {
+
+// Scatter-add K values per lane to dst (already offset by the lane's key) with as few atomics as the key layout allows:
+// lanes holding the same key are found with match.any; if every such group is a contiguous lane range (keys sorted, the
+// usual case for observations grouped by camera) a segmented shuffle reduction leaves the group's sum in its first lane,
+// which issues the K atomics.  Any other layout falls back to per-lane atomics.  Must be called by all 32 lanes.
+template <typename T, int K>
+__device__ __forceinline__ void seg_atomic_add(T* dst, long long key, T (&v)[K], bool active) {
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(0xffffffffu, active ? key : (long long)(-1 - lane));
+  const int lo = __ffs(peers) - 1, hi = 31 - __clz(peers);
+  const bool contig = __popc(peers) == hi - lo + 1;
+  if (__all_sync(0xffffffffu, contig)) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const bool take = lane + o <= hi;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const T other = __shfl_down_sync(0xffffffffu, v[k], o);
+        if (take) v[k] += other;
+      }
+    }
+    if (active && lane == lo)
+#pragma unroll
+      for (int k = 0; k < K; ++k) atomicAdd(dst + k, v[k]);
+  } else if (active) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) atomicAdd(dst + k, v[k]);
+  }
+}
+
+// ---- packed symmetric blocks: 6x6 as 21 (row-major upper triangle), 3x3 as 6 ----
+template <typename T> LM_HD void sym6_unpack(const T* a, T (&A)[6][6]) {
+  int q = 0;
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int c = p; c < 6; ++c) { A[p][c] = a[q]; A[c][p] = a[q]; ++q; }
+}
+template <typename T> LM_HD void sym6_pack(const T (&A)[6][6], T* a) {
+  int q = 0;
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int c = p; c < 6; ++c) a[q++] = A[p][c];
+}
+template <typename T> LM_HD void sym6_mv(const T (&A)[6][6], const T (&x)[6], T (&y)[6]) {
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    T v = T(0);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) v += A[p][c] * x[c];
+    y[p] = v;
+  }
+}
+// A^-1 of a symmetric positive definite NxN block through its Cholesky factor: A = L L^T, A^-1 = L^-T L^-1.
+// Non-positive pivots (only reachable with a numerically singular block) are replaced by a tiny positive number.
+template <typename T, int N> LM_HD void spd_inverse(const T (&A)[N][N], T (&Ai)[N][N]) {
+  T L[N][N], R[N][N];      // R = L^-1 (lower)
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    T s = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    s = s > T(0) ? s : T(1e-30);
+    const T inv = m_rsqrt(s);
+    L[j][j] = s * inv;
+    R[j][j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      T v = A[j][i];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      T v = T(0);
+#pragma unroll
+      for (int k = j; k < i; ++k) v += L[i][k] * R[k][j];
+      R[i][j] = -v * R[i][i];
+    }
+#pragma unroll
+  for (int a = 0; a < N; ++a)
+#pragma unroll
+    for (int b = a; b < N; ++b) {
+      T v = T(0);
+#pragma unroll
+      for (int k = b; k < N; ++k) v += R[k][a] * R[k][b];
+      Ai[a][b] = v; Ai[b][a] = v;
+    }
+}
+template <typename T> LM_HD void sym3_unpack(const T* a, T (&A)[3][3]) {
+  A[0][0] = a[0]; A[0][1] = A[1][0] = a[1]; A[0][2] = A[2][0] = a[2];
+  A[1][1] = a[3]; A[1][2] = A[2][1] = a[4]; A[2][2] = a[5];
+}
+
+}  // namespace b200pose

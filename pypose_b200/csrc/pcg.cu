@@ -1,0 +1,422 @@
+// pcg.cu — device-resident block-Jacobi preconditioned conjugate gradients for the block-sparse LM routes
+// (C-ABI: include/b200pose.h, section LM; reference algorithm: pypose/optim/solver.py:276-340 PCG/CG, and the
+// `bae` PCG the sparse branch delegates to, solver.py:343-363 / optimizer.py:629-643).
+//
+// The vectors are (n,6) block rows (one SE3 tangent per pose / camera).  Every scalar of the iteration (r.z, p.Ap,
+// |r|^2, the stop threshold, the iteration counter and the "done" flag) lives in a small fp64 state array on the
+// device, so a whole chunk of iterations is enqueued by ONE host call without any synchronisation; once the flag is
+// set all remaining kernels of the chunk return immediately.  Per iteration: operator kernel(s) + 3 vector kernels
+//   dot     pq = p.q
+//   update  alpha = rz/pq; x += alpha p; r -= alpha q; z = Minv r; rz' = r.z; rr = r.r; converged / maxiter -> done
+//   dir     beta = rz'/rz; p = z + beta p; q = D p          (D: the block-diagonal part of the operator)
+// Reductions are the deterministic last-block fp64 folds of lm_common.cuh.
+#include "lm_common.cuh"
+
+namespace b200pose {
+
+enum { CG_RZ0 = 0, CG_RZ1 = 1, CG_PQ = 2, CG_RR = 3, CG_STOP2 = 4, CG_DONE = 5, CG_ITERS = 6, CG_MAXIT = 7 };
+
+template <typename T> __device__ __forceinline__ void ld6(const T* p, long long i, T (&v)[6]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) v[k] = p[i * 6 + k];
+}
+template <typename T> __device__ __forceinline__ void st6(T* p, long long i, const T (&v)[6]) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p[i * 6 + k] = v[k];
+}
+template <typename T> __device__ __forceinline__ void sym6_mv_packed(const T* a21, const T (&x)[6], T (&y)[6]) {
+  T A[6][6];
+  sym6_unpack(a21, A);
+  sym6_mv(A, x, y);
+}
+// q = D p with D none (0), diagonal (n,6) (1) or packed symmetric blocks (n,21) (2)
+template <typename T> __device__ __forceinline__ void apply_D(const T* D, int dmode, long long i, const T (&p)[6], T (&q)[6]) {
+  if (dmode == 2) {
+    sym6_mv_packed(D + i * 21, p, q);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) q[k] = dmode == 1 ? D[i * 6 + k] * p[k] : T(0);
+  }
+}
+
+// diag <- clamp(diag, dmin, dmax) * scale (optimizer.py:657 + cumulative :666); optional outputs: the damped block,
+// the amount added to the diagonal, the inverse of the damped block.
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) blk6_damp_inv_kernel(const T* __restrict__ H, T scale, T dmin, T dmax,
+                                                                    T* __restrict__ Hd, T* __restrict__ extra,
+                                                                    T* __restrict__ Minv, long long n) {
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T A[6][6], Ai[6][6];
+    sym6_unpack(H + i * 21, A);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const T d = A[k][k];
+      const T c = (d < dmin ? dmin : (d > dmax ? dmax : d)) * scale;
+      if (extra) extra[i * 6 + k] = c - d;
+      A[k][k] = c;
+    }
+    if (Hd) sym6_pack(A, Hd + i * 21);
+    if (Minv) { spd_inverse<T, 6>(A, Ai); sym6_pack(Ai, Minv + i * 21); }
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pt3_damp_inv_kernel(const T* __restrict__ H, T scale, T dmin, T dmax,
+                                                                   T* __restrict__ Hinv, long long n) {
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T A[3][3], Ai[3][3];
+    sym3_unpack(H + i * 6, A);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { const T d = A[k][k]; A[k][k] = (d < dmin ? dmin : (d > dmax ? dmax : d)) * scale; }
+    spd_inverse<T, 3>(A, Ai);
+    T* o = Hinv + i * 6;
+    o[0] = Ai[0][0]; o[1] = Ai[0][1]; o[2] = Ai[0][2]; o[3] = Ai[1][1]; o[4] = Ai[1][2]; o[5] = Ai[2][2];
+  }
+}
+// out = alpha * A t for packed 3x3 blocks
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pt3_apply_kernel(const T* __restrict__ A6, const T* __restrict__ t, T alpha,
+                                                                T* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T A[3][3];
+    sym3_unpack(A6 + i * 6, A);
+    const T a = t[i * 3], b = t[i * 3 + 1], c = t[i * 3 + 2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[i * 3 + k] = alpha * (A[k][0] * a + A[k][1] * b + A[k][2] * c);
+  }
+}
+
+// ---- CG vector kernels -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) cg_init_kernel(const T* __restrict__ Minv, const T* __restrict__ b, T sign,
+                                                              const T* __restrict__ D, int dmode, T* __restrict__ x,
+                                                              T* __restrict__ r, T* __restrict__ p, T* __restrict__ q,
+                                                              double* cg, double* ws, double tol, double maxiter,
+                                                              long long n) {
+  double acc[2] = {0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T rv[6], z[6], qv[6], zero[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    ld6(b, i, rv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rv[k] *= sign;
+    sym6_mv_packed(Minv + i * 21, rv, z);
+    apply_D(D, dmode, i, z, qv);
+    st6(x, i, zero); st6(r, i, rv); st6(p, i, z); st6(q, i, qv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { acc[0] += (double)rv[k] * (double)z[k]; acc[1] += (double)rv[k] * (double)rv[k]; }
+  }
+  if (reduce_sums<2>(acc, ws)) {
+    const double rz = ws[0], rr = ws[1];
+    cg[CG_RZ0] = rz; cg[CG_RZ1] = 0.0; cg[CG_PQ] = 0.0; cg[CG_RR] = rr; cg[CG_STOP2] = tol * tol * rr;
+    cg[CG_ITERS] = 0.0; cg[CG_MAXIT] = maxiter;
+    cg[CG_DONE] = (!(rr > tol * tol * rr) || maxiter <= 0.0) ? 1.0 : 0.0;      // |r| <= tol |b| (also NaN) -> nothing to do
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) cg_dot_kernel(const T* __restrict__ p, const T* __restrict__ q, double* cg,
+                                                             double* ws, long long n) {
+  if (cg[CG_DONE] != 0.0) return;
+  double acc[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[0] += (double)p[i * 6 + k] * (double)q[i * 6 + k];
+  }
+  if (reduce_sums<1>(acc, ws)) cg[CG_PQ] = ws[0];
+}
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) cg_update_kernel(const T* __restrict__ Minv, const T* __restrict__ p,
+                                                                const T* __restrict__ q, T* __restrict__ x,
+                                                                T* __restrict__ r, T* __restrict__ z, double* cg,
+                                                                double* ws, int par, long long n) {
+  if (cg[CG_DONE] != 0.0) return;
+  const double pq = cg[CG_PQ];
+  if (!(pq > 0.0)) {                       // breakdown (operator not positive definite along p): stop with the current x
+    if (blockIdx.x == 0 && threadIdx.x == 0) cg[CG_DONE] = 2.0;
+    return;
+  }
+  const T alpha = (T)(cg[par] / pq);
+  double acc[2] = {0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T pv[6], qv[6], xv[6], rv[6], zv[6];
+    ld6(p, i, pv); ld6(q, i, qv); ld6(x, i, xv); ld6(r, i, rv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { xv[k] += alpha * pv[k]; rv[k] -= alpha * qv[k]; }
+    sym6_mv_packed(Minv + i * 21, rv, zv);
+    st6(x, i, xv); st6(r, i, rv); st6(z, i, zv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { acc[0] += (double)rv[k] * (double)zv[k]; acc[1] += (double)rv[k] * (double)rv[k]; }
+  }
+  if (reduce_sums<2>(acc, ws)) {
+    cg[par ^ 1] = ws[0];
+    cg[CG_RR] = ws[1];
+    const double it = cg[CG_ITERS] + 1.0;
+    cg[CG_ITERS] = it;
+    if (!(ws[1] > cg[CG_STOP2]) || it >= cg[CG_MAXIT]) cg[CG_DONE] = 1.0;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) cg_dir_kernel(const T* __restrict__ z, const T* __restrict__ D, int dmode,
+                                                             T* __restrict__ p, T* __restrict__ q, const double* cg, int par,
+                                                             long long n) {
+  if (cg[CG_DONE] != 0.0) return;
+  const T beta = (T)(cg[par ^ 1] / cg[par]);
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T pv[6], zv[6], qv[6];
+    ld6(p, i, pv); ld6(z, i, zv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pv[k] = zv[k] + beta * pv[k];
+    apply_D(D, dmode, i, pv, qv);
+    st6(p, i, pv); st6(q, i, qv);
+  }
+}
+
+// ---- operators ---------------------------------------------------------------------------------------------------
+// pose graph: q += H p edge by edge (lm.cu lm_pgo_spmv_kernel), skipped once the CG has finished
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pcg_pgo_spmv_kernel(const T* __restrict__ M, const int* __restrict__ ei,
+                                                                   const int* __restrict__ ej, const T* __restrict__ x,
+                                                                   T* __restrict__ y, const double* cg, long long E) {
+  if (cg[CG_DONE] != 0.0) return;
+  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
+    const long long i = ei[e], j = ej[e];
+    T d[6], v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = __ldg(x + i * 6 + k) - __ldg(x + j * 6 + k);
+    sym6_mv_packed(M + e * 21, d, v);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { atomicAdd(y + i * 6 + k, v[k]); atomicAdd(y + j * 6 + k, -v[k]); }
+  }
+}
+// bundle adjustment: t[j] += Jp^T (Jc x[c])
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+                                                                 const int* __restrict__ cidx, const int* __restrict__ pidx,
+                                                                 const T* __restrict__ x, T* __restrict__ t, const double* cg,
+                                                                 long long m) {
+  if (cg && cg[CG_DONE] != 0.0) return;
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const long long c = cidx[k], j = pidx[k];
+    T v0 = T(0), v1 = T(0);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += Jc[k * 12 + a] * xa; v1 += Jc[k * 12 + 6 + a] * xa; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomicAdd(t + j * 3 + a, Jp[k * 6 + a] * v0 + Jp[k * 6 + 3 + a] * v1);
+  }
+}
+// y[c] -= Jc^T Jp Hp^-1 t[j]   (W Hpp^-1 t; the point-block inverse is applied per observation: 9 cached loads
+// instead of a separate (P,3) pass)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pcg_ba_wv_pinv_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+                                                                     const int* __restrict__ cidx,
+                                                                     const int* __restrict__ pidx, const T* __restrict__ Hpinv,
+                                                                     const T* __restrict__ t, T* __restrict__ y,
+                                                                     const double* cg, long long m) {
+  if (cg && cg[CG_DONE] != 0.0) return;
+  const int lane = threadIdx.x & 31;
+  for (long long k0 = (long long)blockIdx.x * kLmThreads + (threadIdx.x - lane); k0 < m; k0 += (long long)gridDim.x * kLmThreads) {
+    const long long k = k0 + lane;
+    const bool active = k < m;
+    long long c = 0;
+    T out[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    if (active) {
+      c = cidx[k];
+      const long long j = pidx[k];
+      T A[3][3];
+      T h[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) h[a] = __ldg(Hpinv + j * 6 + a);
+      sym3_unpack(h, A);
+      const T t0 = __ldg(t + j * 3), t1 = __ldg(t + j * 3 + 1), t2 = __ldg(t + j * 3 + 2);
+      T v[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) v[a] = A[a][0] * t0 + A[a][1] * t1 + A[a][2] * t2;
+      T u0 = T(0), u1 = T(0);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { u0 += Jp[k * 6 + a] * v[a]; u1 += Jp[k * 6 + 3 + a] * v[a]; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) out[a] = -(Jc[k * 12 + a] * u0 + Jc[k * 12 + 6 + a] * u1);
+    }
+    seg_atomic_add<T, 6>(y + c * 6, c, out, active);
+  }
+}
+// Sd[c] -= (Jc^T Jp) Hp^-1 (Jp^T Jc)   (diagonal blocks of the Schur complement, packed 21; Sd pre-set to damped Hcc)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) ba_schur_diag_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+                                                                    const int* __restrict__ cidx, const int* __restrict__ pidx,
+                                                                    const T* __restrict__ Hpinv, T* __restrict__ Sd,
+                                                                    long long m) {
+  const int lane = threadIdx.x & 31;
+  for (long long k0 = (long long)blockIdx.x * kLmThreads + (threadIdx.x - lane); k0 < m; k0 += (long long)gridDim.x * kLmThreads) {
+    const long long k = k0 + lane;
+    const bool active = k < m;
+    long long c = 0;
+    T out[21];
+#pragma unroll
+    for (int a = 0; a < 21; ++a) out[a] = T(0);
+    if (active) {
+      c = cidx[k];
+      const long long j = pidx[k];
+      T A[3][3], h[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) h[a] = __ldg(Hpinv + j * 6 + a);
+      sym3_unpack(h, A);
+      // G = Jp Hp^-1 Jp^T (2x2), then T_k = Jc^T G Jc
+      T jp[2][3], jc[2][6], B[2][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { jp[0][a] = Jp[k * 6 + a]; jp[1][a] = Jp[k * 6 + 3 + a]; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { jc[0][a] = Jc[k * 12 + a]; jc[1][a] = Jc[k * 12 + 6 + a]; }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) B[r][a] = jp[r][0] * A[0][a] + jp[r][1] * A[1][a] + jp[r][2] * A[2][a];
+      const T g00 = B[0][0] * jp[0][0] + B[0][1] * jp[0][1] + B[0][2] * jp[0][2];
+      const T g01 = B[0][0] * jp[1][0] + B[0][1] * jp[1][1] + B[0][2] * jp[1][2];
+      const T g11 = B[1][0] * jp[1][0] + B[1][1] * jp[1][1] + B[1][2] * jp[1][2];
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const T l0 = jc[0][a] * g00 + jc[1][a] * g01, l1 = jc[0][a] * g01 + jc[1][a] * g11;
+#pragma unroll
+        for (int b = a; b < 6; ++b) out[q++] = -(l0 * jc[0][b] + l1 * jc[1][b]);
+      }
+    }
+    seg_atomic_add<T, 21>(Sd + c * 21, c, out, active);
+  }
+}
+// ws[0] = sum_k (J_k d)^T (2 r_k + J_k d) with J_k d = Jc x_c + Jp x_p    (strategy.py:143 'predicted')
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) ba_predicted_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+                                                                   const T* __restrict__ rs, const int* __restrict__ cidx,
+                                                                   const int* __restrict__ pidx, const T* __restrict__ xc,
+                                                                   const T* __restrict__ xp, double* ws, long long m) {
+  double acc[1] = {0.0};
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    const long long c = cidx[k], j = pidx[k];
+    T d0 = T(0), d1 = T(0);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { const T v = __ldg(xc + c * 6 + a); d0 += Jc[k * 12 + a] * v; d1 += Jc[k * 12 + 6 + a] * v; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { const T v = __ldg(xp + j * 3 + a); d0 += Jp[k * 6 + a] * v; d1 += Jp[k * 6 + 3 + a] * v; }
+    acc[0] += (double)(d0 * (T(2) * rs[k * 2] + d0) + d1 * (T(2) * rs[k * 2 + 1] + d1));
+  }
+  reduce_sums<1>(acc, ws);
+}
+// ws[0] = D^T H D + 2 D^T g for the pose graph: sum over edges of d^T M_e d (d = D_i - D_j) plus the linear term
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pgo_predicted_kernel(const T* __restrict__ M, const int* __restrict__ ei,
+                                                                    const int* __restrict__ ej, const T* __restrict__ D,
+                                                                    const T* __restrict__ g, double* ws, long long E,
+                                                                    long long n) {
+  double acc[1] = {0.0};
+  const long long tid = (long long)blockIdx.x * kLmThreads + threadIdx.x, nth = (long long)gridDim.x * kLmThreads;
+  for (long long e = tid; e < E; e += nth) {
+    const long long i = ei[e], j = ej[e];
+    T d[6], v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = __ldg(D + i * 6 + k) - __ldg(D + j * 6 + k);
+    sym6_mv_packed(M + e * 21, d, v);
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += d[k] * v[k];
+    acc[0] += (double)s;
+  }
+  for (long long i = tid; i < n; i += nth) {
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += D[i * 6 + k] * g[i * 6 + k];
+    acc[0] += 2.0 * (double)s;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+}  // namespace b200pose
+
+using namespace b200pose;
+
+#define LM_LAUNCH(kern, work, st, ...) kern<<<lm_grid(work, kLmThreads), kLmThreads, 0, (cudaStream_t)(st)>>>(__VA_ARGS__)
+
+#define PCG_ABI(SFX, CT)                                                                                              \
+  B200_EXPORT int b200_lm_blk6_damp_inv_##SFX(const CT* H, double scale, double dmin, double dmax, CT* Hd, CT* extra, \
+                                              CT* Minv, long long n, void* stream) {                                  \
+    if (n <= 0) return 0;                                                                                             \
+    LM_LAUNCH(blk6_damp_inv_kernel<CT>, n, stream, H, (CT)scale, (CT)dmin, (CT)dmax, Hd, extra, Minv, n);             \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pt3_damp_inv_##SFX(const CT* H, double scale, double dmin, double dmax, CT* Hinv,           \
+                                             long long n, void* stream) {                                             \
+    if (n <= 0) return 0;                                                                                             \
+    LM_LAUNCH(pt3_damp_inv_kernel<CT>, n, stream, H, (CT)scale, (CT)dmin, (CT)dmax, Hinv, n);                         \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pt3_apply_##SFX(const CT* A6, const CT* t, double alpha, CT* out, long long n,              \
+                                          void* stream) {                                                             \
+    if (n <= 0) return 0;                                                                                             \
+    LM_LAUNCH(pt3_apply_kernel<CT>, n, stream, A6, t, (CT)alpha, out, n);                                             \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_pcg_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* Minv,       \
+                                        const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q, double* cg,  \
+                                        double* ws, double tol, long long maxiter, long long first_iter,              \
+                                        long long iters, long long n, void* stream) {                                 \
+    if (n <= 0) return 0;                                                                                             \
+    if (first_iter == 0)                                                                                              \
+      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, g, (CT)-1, extra, 1, x, r, p, q, cg, ws, tol, (double)maxiter, n); \
+    for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
+      const int par = (int)(it & 1);                                                                                  \
+      if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, M, ei, ej, p, q, cg, E);                               \
+      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);                                \
+      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, 1, p, q, cg, par, n);                                         \
+    }                                                                                                                 \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_predicted_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* D,    \
+                                              const CT* g, double* ws, long long n, void* stream) {                   \
+    if (n <= 0) return 0;                                                                                             \
+    LM_LAUNCH(pgo_predicted_kernel<CT>, (E > n ? E : n), stream, M, ei, ej, D, g, ws, E, n);                          \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_schur_diag_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx,           \
+                                              const CT* Hpinv, CT* Sd, long long m, void* stream) {                   \
+    if (m <= 0) return 0;                                                                                             \
+    LM_LAUNCH(ba_schur_diag_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, Hpinv, Sd, m);                                 \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_wv_pinv_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx,              \
+                                           const CT* Hpinv, const CT* t, CT* y, long long m, void* stream) {          \
+    if (m <= 0) return 0;                                                                                             \
+    LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, Hpinv, t, y, (const double*)nullptr, m);      \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx, long long m,     \
+                                       const CT* Hc, const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r,   \
+                                       CT* z, CT* p, CT* q, CT* t, double* cg, double* ws, double tol,                \
+                                       long long maxiter, long long P, long long first_iter, long long iters,         \
+                                       long long n, void* stream) {                                                   \
+    if (n <= 0) return 0;                                                                                             \
+    cudaStream_t st = (cudaStream_t)stream;                                                                           \
+    if (first_iter == 0)                                                                                              \
+      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, bneg, (CT)-1, Hc, 2, x, r, p, q, cg, ws, tol, (double)maxiter, n); \
+    for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
+      const int par = (int)(it & 1);                                                                                  \
+      cudaMemsetAsync(t, 0, sizeof(CT) * 3 * (size_t)P, st);                                                          \
+      if (m > 0) {                                                                                                    \
+        LM_LAUNCH(pcg_ba_wtx_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, p, t, cg, m);                                 \
+        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, Hpinv, t, q, cg, m);                      \
+      }                                                                                                               \
+      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);                                \
+      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, Hc, 2, p, q, cg, par, n);                                            \
+    }                                                                                                                 \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_predicted_##SFX(const CT* Jc, const CT* Jp, const CT* rs, const int* cidx,               \
+                                             const int* pidx, const CT* xc, const CT* xp, double* ws, long long m,    \
+                                             void* stream) {                                                          \
+    if (m <= 0) return 0;                                                                                             \
+    LM_LAUNCH(ba_predicted_kernel<CT>, m, stream, Jc, Jp, rs, cidx, pidx, xc, xp, ws, m);                             \
+    return (int)cudaGetLastError();                                                                                   \
+  }
+
+PCG_ABI(f32, float)
+PCG_ABI(f64, double)

@@ -232,3 +232,77 @@ _DIRECT = {"lm_poseinv_loss": _poseinv_loss, "lm_poseinv_trial": _poseinv_trial,
 LM_OPS = ["lm_poseinv_loss", "lm_poseinv_trial", "lm_reproj_accum", "lm_solve6_retract", "lm_reproj_loss",
           "lm_reproj_residual"]
 ops = torch.ops.b200pose
+
+
+# ----------------------------------------------------------------------------------------------------
+# Device-resident PCG (csrc/pcg.cu), CUDA only and single-rank only: the multi-rank route all-reduces every
+# operator product on the host side (optim/structured.py:_pcg).
+# ----------------------------------------------------------------------------------------------------
+CG_CHUNK = 8            # iterations enqueued per host call / per read of the done flag
+_cg_state = {}
+
+
+def _cg(device):
+    key = (device.type, device.index)
+    s = _cg_state.get(key)
+    if s is None:
+        s = _cg_state[key] = torch.zeros(8, dtype=torch.float64, device=device)
+    return s
+
+
+def _run_chunks(enqueue, cg, maxiter):
+    """enqueue(first_iter, iters) until the device reports done; returns the iteration count."""
+    it = 0
+    while True:
+        n = max(1, min(CG_CHUNK, maxiter - it))
+        enqueue(it, n)
+        it += n
+        st = cg.tolist()                                  # the one host sync per chunk
+        if st[5] != 0.0 or it >= maxiter:
+            return int(st[6])
+
+
+def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter):
+    """(H + clamp/damping) x = -g by device PCG.  Returns x (n,6), iterations, predicted (1,) fp64 on device."""
+    dev, dt, n, E = M.device, M.dtype, Hd.shape[0], M.shape[0]
+    ws, cg = _workspace(dev), _cg(dev)
+    extra = torch.empty(n, 6, dtype=dt, device=dev)
+    Minv = torch.empty(n, 21, dtype=dt, device=dev)
+    _launch("b200_lm_blk6_damp_inv", M, [_p(Hd), float(scale), float(dmin), float(dmax), _p(None), _p(extra), _p(Minv)], n)
+    x, r, z, p, q = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(5))
+    maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
+    iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg", M, [
+        _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg), _p(ws),
+        float(tol), maxiter, it0, k], n), cg, maxiter)
+    _launch("b200_lm_pgo_predicted", M, [_p(M), _p(ei), _p(ej), E, _p(x), _p(g), _p(ws)], n)
+    return x, iters, ws[:1].clone()
+
+
+def ba_solve(Jc, Jp, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter):
+    """Schur-complement solve of the damped BA normal equations by device PCG.
+    Returns xc (C,6), xp (P,3), iterations, predicted (1,) fp64 on device."""
+    dev, dt = Jc.device, Jc.dtype
+    m, C, P = Jc.shape[0], Hcc.shape[0], Hpp.shape[0]
+    ws, cg = _workspace(dev), _cg(dev)
+    Hc = torch.empty(C, 21, dtype=dt, device=dev)
+    Hpinv = torch.empty(P, 6, dtype=dt, device=dev)
+    Minv = torch.empty(C, 21, dtype=dt, device=dev)
+    _launch("b200_lm_blk6_damp_inv", Jc, [_p(Hcc), float(scale), float(dmin), float(dmax), _p(Hc), _p(None), _p(None)], C)
+    _launch("b200_lm_pt3_damp_inv", Jc, [_p(Hpp), float(scale), float(dmin), float(dmax), _p(Hpinv)], P)
+    Sd = Hc.clone()
+    _launch("b200_lm_ba_schur_diag", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(Hpinv), _p(Sd)], m)
+    _launch("b200_lm_blk6_damp_inv", Jc, [_p(Sd), 1.0, -3.0e38, 3.0e38, _p(None), _p(None), _p(Minv)], C)
+    bneg = gc.clone()                                     # -(rhs) = gc - W Hpp^-1 gp
+    _launch("b200_lm_ba_wv_pinv", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(Hpinv), _p(gp), _p(bneg)], m)
+    x, r, z, p, q = (torch.empty(C, 6, dtype=dt, device=dev) for _ in range(5))
+    t = torch.empty(P, 3, dtype=dt, device=dev)
+    maxiter = int(maxiter) if maxiter is not None else 10 * 6 * C
+    iters = _run_chunks(lambda it0, k: _launch("b200_lm_ba_pcg", Jc, [
+        _p(Jc), _p(Jp), _p(cidx), _p(pidx), m, _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
+        _p(t), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter)
+    t.copy_(gp)                                           # dp = -Hpp^-1 (gp + W^T dc)
+    _launch("b200_lm_ba_wtx", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(x), _p(t)], m)
+    xp = torch.empty(P, 3, dtype=dt, device=dev)
+    _launch("b200_lm_pt3_apply", Jc, [_p(Hpinv), _p(t), -1.0, _p(xp)], P)
+    _launch("b200_lm_ba_predicted", Jc, [_p(Jc), _p(Jp), _p(rs), _p(cidx), _p(pidx), _p(x), _p(xp), _p(ws)], m)
+    return x, xp, iters, ws[:1].clone()

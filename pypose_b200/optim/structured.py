@@ -208,6 +208,10 @@ class PGOProblem(_Problem):
 
     def trial(self, lin, scale, dmin, dmax):
         M, Hd, g, cur = lin
+        if M.is_cuda and self.group is None:          # device-resident PCG: one host read per 8 iterations
+            D, self.cg_iters, predicted = _fused.pgo_solve(M, self.ei, self.ej, Hd, g, scale, dmin, dmax, self.tol,
+                                                           self.maxiter)
+            return self._finish_trial(D, predicted, cur)
         d = Hd[:, _DIAG21]
         extra = d.clamp(dmin, dmax) * scale - d                       # added to the diagonal of H
         blocks = _unpack21(Hd) + torch.diag_embed(extra)
@@ -218,6 +222,9 @@ class PGOProblem(_Problem):
         Hx = _fused.call("lm_pgo_spmv", M, self.ei, self.ej, D, torch.zeros_like(D))
         Hx = _allreduce(Hx, self.group)
         predicted = ((D * Hx).sum() + 2 * (D * g).sum()).to(torch.float64).reshape(1)
+        return self._finish_trial(D, predicted, cur)
+
+    def _finish_trial(self, D, predicted, cur):
         nodes = self._nodes()
         delta = LieTensor(D, ltype=_lt.se3_type)
         self._trial = (delta.Exp() * LieTensor(nodes, ltype=SE3_type)).tensor()
@@ -252,6 +259,10 @@ class BAProblem(_Problem):
         self.model, self.key, self.group, self.robust = model, key, group, robust
         self.poses, self.points = (model.poses, model.points_3d) if params is None else params
         self.dtype = self.poses.dtype
+        # observations are regrouped by camera once (the LM sums do not depend on their order): the camera-side
+        # scatter-adds of the kernels then collapse to one atomic per warp and value (csrc/lm_common.cuh seg_atomic_add)
+        order = torch.sort(cidx.reshape(-1), stable=True)[1]
+        pix, cidx, pidx = pix.reshape(-1, 2)[order], cidx.reshape(-1)[order], pidx.reshape(-1)[order]
         self.pix = pix.to(self.dtype).contiguous()
         self.cidx, self.pidx = cidx.to(torch.int32).contiguous(), pidx.to(torch.int32).contiguous()
         self.cl, self.pl = cidx.long(), pidx.long()
@@ -285,6 +296,10 @@ class BAProblem(_Problem):
     def trial(self, lin, scale, dmin, dmax):
         Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = lin
         C, P = Hcc.shape[0], Hpp.shape[0]
+        if Jc.is_cuda and self.group is None:         # device-resident Schur PCG
+            xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, Hcc, Hpp, gc, gp, scale, dmin,
+                                                          dmax, self.tol, self.maxiter)
+            return self._finish_trial(xc, xp, pred, cur)
         dc, dp = Hcc[:, _DIAG21], Hpp[:, [0, 3, 5]]
         Hc = _unpack21(Hcc) + torch.diag_embed(dc.clamp(dmin, dmax) * scale - dc)
         Hp_inv = torch.linalg.inv(_unpack6(Hpp) + torch.diag_embed(dp.clamp(dmin, dmax) * scale - dp))
@@ -317,6 +332,9 @@ class BAProblem(_Problem):
         # predicted = (J D)^T (2 R + J D), per observation (corrected J and R)
         Jd = _bmv(Jc3, xc[self.cl]) + _bmv(Jp3, xp[self.pl])
         pred = ((Jd * Jd).sum() + 2 * (rs * Jd).sum()).to(torch.float64).reshape(1)
+        return self._finish_trial(xc, xp, pred, cur)
+
+    def _finish_trial(self, xc, xp, pred, cur):
         T, pts = self._params()
         Tn = (LieTensor(xc, ltype=_lt.se3_type).Exp() * LieTensor(T, ltype=SE3_type)).tensor()
         pn = pts + xp

@@ -334,3 +334,123 @@ def test_ba_large_fp32_converges():
     opt = pp.optim.LM(net, solver=pp.optim.solver.PCG(tol=1e-4, maxiter=100), sparse=True)
     losses = [float(opt.step(inp)) for _ in range(8)]
     assert losses[-1] < 1e-3 * losses[0], losses
+
+
+def _dense_sym(packed, n, k):
+    """(n, k(k+1)/2) packed upper triangles -> (n,k,k)."""
+    iu = np.triu_indices(k)
+    A = np.zeros((n, k, k))
+    A[:, iu[0], iu[1]] = packed
+    A[:, iu[1], iu[0]] = packed
+    return A
+
+
+def test_block_damp_inverse_kernels():
+    """b200_lm_blk6_damp_inv / pt3_damp_inv / pt3_apply against numpy (clamp + damping of optimizer.py:657/666)."""
+    import ctypes
+    from pypose_b200.optim import _fused as F
+    rng = np.random.default_rng(21)
+    n = 1037
+    for dt, tol in ((torch.float64, 1e-9), (torch.float32, 2e-3)):
+        B = rng.standard_normal((n, 6, 8))
+        A = B @ B.transpose(0, 2, 1)
+        A[::7, 2, 2] = 1e-9                                   # below the clamp
+        iu = np.triu_indices(6)
+        H = cu(A[:, iu[0], iu[1]], dt)
+        Hd, ex, Mi = (torch.empty(n, w, dtype=dt, device="cuda") for w in (21, 6, 21))
+        F._launch("b200_lm_blk6_damp_inv", H, [F._p(H), 1.5, 1e-6, 1e32, F._p(Hd), F._p(ex), F._p(Mi)], n)
+        Ad = _dense_sym(H.double().cpu().numpy(), n, 6)
+        d = np.einsum('nii->ni', Ad).copy()
+        dd = np.clip(d, 1e-6, 1e32) * 1.5
+        Ad[:, np.arange(6), np.arange(6)] = dd
+        np.testing.assert_allclose(ex.double().cpu().numpy(), dd - d, rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(_dense_sym(Hd.double().cpu().numpy(), n, 6), Ad, rtol=1e-6, atol=1e-12)
+        I = _dense_sym(Mi.double().cpu().numpy(), n, 6) @ Ad
+        assert np.abs(I - np.eye(6)).max() <= tol * np.linalg.cond(Ad).max() ** 0.5
+        B3 = rng.standard_normal((n, 3, 5))
+        A3 = B3 @ B3.transpose(0, 2, 1)
+        iu3 = np.triu_indices(3)
+        H3 = cu(A3[:, iu3[0], iu3[1]], dt)
+        Hi3 = torch.empty(n, 6, dtype=dt, device="cuda")
+        F._launch("b200_lm_pt3_damp_inv", H3, [F._p(H3), 1.25, 1e-6, 1e32, F._p(Hi3)], n)
+        A3d = _dense_sym(H3.double().cpu().numpy(), n, 3)
+        A3d[:, np.arange(3), np.arange(3)] *= 1.25
+        I3 = _dense_sym(Hi3.double().cpu().numpy(), n, 3) @ A3d
+        assert np.abs(I3 - np.eye(3)).max() <= tol * 10
+        t = rng.standard_normal((n, 3))
+        out = torch.empty(n, 3, dtype=dt, device="cuda")
+        F._launch("b200_lm_pt3_apply", H3, [F._p(Hi3), F._p(cu(t, dt)), -2.0, F._p(out)], n)
+        ref = -2.0 * np.einsum('nij,nj->ni', _dense_sym(Hi3.double().cpu().numpy(), n, 3), cu(t, dt).double().cpu().numpy())
+        np.testing.assert_allclose(out.double().cpu().numpy(), ref, rtol=1e-5 if dt == torch.float32 else 1e-12, atol=1e-6 if dt == torch.float32 else 1e-12)
+
+
+@pytest.mark.parametrize("maxiter", [500, 3])
+def test_pgo_device_pcg_vs_dense_solve(maxiter):
+    """b200_lm_pgo_pcg (device-resident block-Jacobi PCG) against a dense numpy solve of (H + clamp/damp) x = -g."""
+    from pypose_b200.optim import _fused as F
+    rng = np.random.default_rng(22)
+    N = 90
+    gt, init, edges, Z = _pgo_problem(rng, N, 120, meas_noise=0.02)
+    dt = torch.float64
+    ei, ej = (torch.from_numpy(edges[:, k].astype(np.int32)).cuda() for k in (0, 1))
+    M, u, c = ops.lm_pgo_linearize(cu(init, dt), cu(Z, dt), ei, ej, 0, 1.0)
+    Hd, g = ops.lm_pgo_scatter(M, u, ei, ej, N)
+    scale, dmin, dmax = 1.0 + 1e-3, 1e-6, 1e32
+    x, iters, pred = F.pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, 1e-13, maxiter)
+    # dense H from the per-edge blocks
+    Mb = _dense_sym(M.cpu().numpy(), M.shape[0], 6)
+    H = np.zeros((N * 6, N * 6))
+    for e, (i, j) in enumerate(edges):
+        for (a, b, s) in ((i, i, 1), (j, j, 1), (i, j, -1), (j, i, -1)):
+            H[a * 6:a * 6 + 6, b * 6:b * 6 + 6] += s * Mb[e]
+    d = np.diag(H).copy()
+    Hdamp = H + np.diag(np.clip(d, dmin, dmax) * scale - d)
+    gv = g.cpu().numpy().reshape(-1)
+    xv = x.cpu().numpy().reshape(-1)
+    if maxiter == 3:                       # maxiter honoured exactly; the partial solution still decreases the model
+        assert iters == 3
+        assert xv @ Hdamp @ xv + 2 * xv @ gv < 0
+    else:
+        ref = np.linalg.solve(Hdamp, -gv)
+        assert 0 < iters < maxiter
+        assert np.abs(xv - ref).max() <= 1e-8 * np.abs(ref).max()
+    np.testing.assert_allclose(pred.cpu().numpy()[0], xv @ H @ xv + 2 * xv @ gv, rtol=1e-9)
+
+
+@pytest.mark.parametrize("sort_by_camera", [False, True])
+def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera):
+    """b200_lm_ba_pcg & co. against a dense numpy solve of the full damped normal equations; with observations
+    grouped by camera the warp-aggregated scatter path runs, otherwise the per-lane fallback."""
+    from pypose_b200.optim import _fused as F
+    rng = np.random.default_rng(23)
+    C, P = 12, 150
+    gt, ptsw, T0, p0, pix, cidx, pidx = _ba_problem(rng, C, P, 5, pix_noise=0.01)
+    if sort_by_camera:
+        o = np.argsort(cidx, kind="stable")
+        pix, cidx, pidx = pix[o], cidx[o], pidx[o]
+    dt = torch.float64
+    ci, pi_ = torch.from_numpy(cidx.astype(np.int32)).cuda(), torch.from_numpy(pidx.astype(np.int32)).cuda()
+    Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = ops.lm_ba_linearize(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, 0, 1.0)
+    outs_o = L.ba_linearize(T0, p0, pix, cidx, pidx, 0, 1.0)
+    for a, b in zip((Jc, Jp, rs, Hcc, Hpp, gc, gp), outs_o):
+        assert np.abs(a.cpu().numpy() - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
+    scale, dmin, dmax = 1.0 + 1e-4, 1e-6, 1e32
+    xc, xp, iters, pred = F.ba_solve(Jc, Jp, rs, ci, pi_, Hcc, Hpp, gc, gp, scale, dmin, dmax, 1e-13, 400)
+    m = len(cidx)
+    J = np.zeros((2 * m, 6 * C + 3 * P))
+    Jcn, Jpn = Jc.cpu().numpy().reshape(m, 2, 6), Jp.cpu().numpy().reshape(m, 2, 3)
+    for k in range(m):
+        J[2 * k:2 * k + 2, 6 * cidx[k]:6 * cidx[k] + 6] = Jcn[k]
+        J[2 * k:2 * k + 2, 6 * C + 3 * pidx[k]:6 * C + 3 * pidx[k] + 3] = Jpn[k]
+    R = rs.cpu().numpy().reshape(-1)
+    A = J.T @ J
+    d = np.diag(A).copy()
+    A_d = A + np.diag(np.clip(d, dmin, dmax) * scale - d)
+    ref = np.linalg.solve(A_d, -J.T @ R)
+    got = np.concatenate([xc.cpu().numpy().reshape(-1), xp.cpu().numpy().reshape(-1)])
+    assert 0 < iters < 400
+    assert np.abs(got - ref).max() <= 1e-7 * np.abs(ref).max()
+    Jd = J @ got
+    np.testing.assert_allclose(pred.cpu().numpy()[0], Jd @ (2 * R + Jd), rtol=1e-9)
+    y = ops.lm_ba_wv(Jc, Jp, ci, pi_, cu(rng.standard_normal((P, 3)), dt) * 0 + 1.0, C).cpu().numpy()
+    np.testing.assert_allclose(y, L.ba_wv(outs_o[0], outs_o[1], cidx, pidx, np.ones((P, 3)), C), rtol=1e-9, atol=1e-9)
