@@ -354,7 +354,8 @@ def test_block_damp_inverse_kernels():
     for dt, tol in ((torch.float64, 1e-9), (torch.float32, 2e-3)):
         B = rng.standard_normal((n, 6, 8))
         A = B @ B.transpose(0, 2, 1)
-        A[::7, 2, 2] = 1e-9                                   # below the clamp
+        A[::7, 2, :] = 0.0                                    # an unobserved direction: diagonal below the clamp,
+        A[::7, :, 2] = 0.0                                    # block stays positive semi-definite
         iu = np.triu_indices(6)
         H = cu(A[:, iu[0], iu[1]], dt)
         Hd, ex, Mi = (torch.empty(n, w, dtype=dt, device="cuda") for w in (21, 6, 21))
@@ -366,7 +367,9 @@ def test_block_damp_inverse_kernels():
         np.testing.assert_allclose(ex.double().cpu().numpy(), dd - d, rtol=1e-6, atol=1e-12)
         np.testing.assert_allclose(_dense_sym(Hd.double().cpu().numpy(), n, 6), Ad, rtol=1e-6, atol=1e-12)
         I = _dense_sym(Mi.double().cpu().numpy(), n, 6) @ Ad
-        assert np.abs(I - np.eye(6)).max() <= tol * np.linalg.cond(Ad).max() ** 0.5
+        assert np.isfinite(I).all()
+        well = np.ones(n, bool) if dt == torch.float64 else (np.arange(n) % 7 != 0)     # cond ~1e7 blocks: fp64 only
+        assert np.abs(I[well] - np.eye(6)).max() <= tol * 10
         B3 = rng.standard_normal((n, 3, 5))
         A3 = B3 @ B3.transpose(0, 2, 1)
         iu3 = np.triu_indices(3)
