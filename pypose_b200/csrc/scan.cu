@@ -257,178 +257,237 @@ __global__ void __launch_bounds__(kScanThreads) imu_integrate_kernel(
 // ------------------------------------------------------------------------------------------------
 // IMU covariance propagation (imu_preintegrator.py:428-465) without materialising (B, F+1, 9, 9):
 //   cov = sum_{k=0..F} L_k B_k L_k^T,  L_k = A_k A_{k+1} ... A_{F-1},  B_0 = init_cov, B_{j+1} = N_j (noise of sample j)
-// exactly the reference's `cumprod(A.flip).flip` ordering.  Three passes over chunks of the time axis, A_j and N_j
-// rebuilt on the fly from (Rk = dr_j, Rij_j, a_j, dt_j):
+// exactly the reference's `cumprod(A.flip).flip` ordering, with
+//   A_j = [[Rk^T,0,0],[M1, I, 0],[M1 dt/2, dt I, I]],  M1 = -Rij a^ dt;   N_j = (Bg Cg Bg^T + Ba Ca Ba^T)/dt,
+//   Bg = [Jr(dr) dt; 0; 0],  Ba = [0; Rij dt; Rij dt^2/2].
+// Products of such A keep the shape  L = [[X,0,0],[Y,I,0],[Z,tau I,I]]  (X,Y,Z 3x3, tau = sum of dt), so a 9x9 matrix
+// is 28 numbers and one step A_j L costs two 3x3 products; the noise term needs only the first block column:
+//   L Bg = [X;Y;Z] Jr dt,   L Ba = [0; R dt; (tau + dt/2) R dt]
+//   L N L^T = [X;Y;Z] Q [X;Y;Z]^T + [[0,0,0],[0,K,sK],[0,sK,s^2 K]],  Q = Jr diag(cg dt) Jr^T, K = R diag(ca dt) R^T, s = tau+dt/2.
+// Everything lives in registers (the first version kept dense 9x9 matrices in local memory: 17.7 ms for 1e3 x 1e4
+// samples; this form: see DESIGN.md §3.2).  Three passes over chunks of the time axis:
 //   1. P_c = product of the A_j of chunk c                        (one thread per (trajectory, chunk))
 //   2. S_c = P_c S_{c+1}: suffix products over chunks              (one thread per trajectory, NC steps)
-//   3. T_c = sum_{j in c} L_{j+1} N_j L_{j+1}^T walking the chunk backwards from L = S_{c+1}; cov = sum_c T_c + L_0 init L_0^T
-// A_j = [[Rk^T,0,0],[-Rij a^ dt, I, 0],[-Rij a^ dt^2/2, dt I, I]];  N_j = (Bg Cg Bg^T + Ba Ca Ba^T)/dt,
-// Bg = [Jr(dr) dt; 0; 0], Ba = [0; Rij dt; Rij dt^2/2].
+//   3. T_c = sum_{j in c} L_{j+1} N_j L_{j+1}^T walking the chunk backwards from L = S_{c+1} (symmetric, 45 numbers);
+//      cov = sum_c T_c + L_0 init L_0^T                            (81 threads per trajectory)
 // ------------------------------------------------------------------------------------------------
-template <typename T> struct CovStep {
-  T Rt[3][3];   // Rk^T
-  T M1[3][3];   // -Rij a^ dt
-  T dt;
-  T Jr[3][3];   // Jr(Log dr)
-  T R[3][3];    // Rij
-};
+template <typename T> struct CovL { T X[3][3], Y[3][3], Z[3][3], tau; };
+constexpr int kCovL = 28;       // stored size of a CovL
+constexpr int kCovT = 45;       // packed upper triangle of a symmetric 9x9 (row-major)
+
+template <typename T> __device__ __forceinline__ void covl_identity(CovL<T>& L) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { L.X[r][c] = r == c ? T(1) : T(0); L.Y[r][c] = T(0); L.Z[r][c] = T(0); }
+  L.tau = T(0);
+}
+template <typename T> __device__ __forceinline__ void covl_store(const CovL<T>& L, T* p) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { p[r * 3 + c] = L.X[r][c]; p[9 + r * 3 + c] = L.Y[r][c]; p[18 + r * 3 + c] = L.Z[r][c]; }
+  p[27] = L.tau;
+}
+template <typename T> __device__ __forceinline__ void covl_load(CovL<T>& L, const T* p) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { L.X[r][c] = p[r * 3 + c]; L.Y[r][c] = p[9 + r * 3 + c]; L.Z[r][c] = p[18 + r * 3 + c]; }
+  L.tau = p[27];
+}
+template <typename T> __device__ __forceinline__ void m3mul(const T (&A)[3][3], const T (&B)[3][3], T (&C)[3][3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) C[r][c] = A[r][0] * B[0][c] + A[r][1] * B[1][c] + A[r][2] * B[2][c];
+}
 template <typename T> __device__ __forceinline__ void quat_matrix(const Q4<T>& q, T (&R)[3][3]) {
   const V3<T> c0 = qrot(q, mk(T(1), T(0), T(0))), c1 = qrot(q, mk(T(0), T(1), T(0))), c2 = qrot(q, mk(T(0), T(0), T(1)));
   R[0][0] = c0.x; R[1][0] = c0.y; R[2][0] = c0.z;
   R[0][1] = c1.x; R[1][1] = c1.y; R[2][1] = c1.z;
   R[0][2] = c2.x; R[1][2] = c2.y; R[2][2] = c2.z;
 }
+// L <- A_j L.  R = matrix of Rij_j (returned for the noise term), qk = Rk_j.
 template <typename T>
-__device__ __forceinline__ void cov_step_load(CovStep<T>& s, const T* Rk, const T* Rij, const T* a, const T* dt, long long j,
-                                              bool need_noise) {
-  const Q4<T> qk = ldq(Rk + j * 4), qi = ldq(Rij + j * 4);
-  T Rkm[3][3];
-  quat_matrix(qk, Rkm);
-  quat_matrix(qi, s.R);
-  s.dt = dt[j];
-  const V3<T> av = ld3(a + j * 3);
+__device__ __forceinline__ void covl_apply_A(CovL<T>& L, const Q4<T>& qk, const T (&R)[3][3], const V3<T>& av, T dt) {
+  T Rk[3][3], M1[3][3], MX[3][3], Xn[3][3];
+  quat_matrix(qk, Rk);
   const T H[3][3] = {{T(0), -av.z, av.y}, {av.z, T(0), -av.x}, {-av.y, av.x, T(0)}};
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
+    for (int c = 0; c < 3; ++c) M1[r][c] = -(R[r][0] * H[0][c] + R[r][1] * H[1][c] + R[r][2] * H[2][c]) * dt;
+  m3mul(M1, L.X, MX);
+  const T hdt = T(0.5) * dt;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
-      s.Rt[r][c] = Rkm[c][r];
-      s.M1[r][c] = -(s.R[r][0] * H[0][c] + s.R[r][1] * H[1][c] + s.R[r][2] * H[2][c]) * s.dt;
-    }
-  if (need_noise) {
-    T jc;
-    const V3<T> phi = so3_log(qk, jc);
-    const RotCoef<T> rc = rot_coef(phi);
-    T c1 = rc.c1, c2 = rc.c2;
-    if (!(rc.theta > num<T>::eps)) { c1 = T(0); c2 = T(0); }
-    const T xx = phi.x * phi.x, yy = phi.y * phi.y, zz = phi.z * phi.z, xy = phi.x * phi.y, xz = phi.x * phi.z, yz = phi.y * phi.z;
-    s.Jr[0][0] = T(1) - c2 * (yy + zz); s.Jr[0][1] = c1 * phi.z + c2 * xy;   s.Jr[0][2] = -c1 * phi.y + c2 * xz;
-    s.Jr[1][0] = -c1 * phi.z + c2 * xy;  s.Jr[1][1] = T(1) - c2 * (xx + zz); s.Jr[1][2] = c1 * phi.x + c2 * yz;
-    s.Jr[2][0] = c1 * phi.y + c2 * xz;   s.Jr[2][1] = -c1 * phi.x + c2 * yz;  s.Jr[2][2] = T(1) - c2 * (xx + yy);
-  }
-}
-// L <- A_j L  (L is 9x9 row-major in local memory)
-template <typename T> __device__ __forceinline__ void cov_apply_A(const CovStep<T>& s, T* L) {
-  const T hdt = T(0.5) * s.dt;
-#pragma unroll 1
-  for (int c = 0; c < 9; ++c) {
-    const T l0 = L[0 * 9 + c], l1 = L[1 * 9 + c], l2 = L[2 * 9 + c];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const T m = s.M1[r][0] * l0 + s.M1[r][1] * l1 + s.M1[r][2] * l2;
-      const T mid = L[(3 + r) * 9 + c];
-      L[(6 + r) * 9 + c] += hdt * m + s.dt * mid;      // M2 = M1 dt / 2
-      L[(3 + r) * 9 + c] = mid + m;
+      L.Z[r][c] += hdt * MX[r][c] + dt * L.Y[r][c];
+      L.Y[r][c] += MX[r][c];
+      Xn[r][c] = Rk[0][r] * L.X[0][c] + Rk[1][r] * L.X[1][c] + Rk[2][r] * L.X[2][c];      // Rk^T X
     }
 #pragma unroll
-    for (int r = 0; r < 3; ++r) L[r * 9 + c] = s.Rt[r][0] * l0 + s.Rt[r][1] * l1 + s.Rt[r][2] * l2;
-  }
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) L.X[r][c] = Xn[r][c];
+  L.tau += dt;
 }
-// Tm += L N_j L^T,  N_j = (Bg Cg Bg^T + Ba Ca Ba^T)/dt
+// C = P S for two structured matrices
+template <typename T> __device__ __forceinline__ void covl_mul(const CovL<T>& P, const CovL<T>& S, CovL<T>& C) {
+  T YX[3][3], ZX[3][3];
+  m3mul(P.X, S.X, C.X);
+  m3mul(P.Y, S.X, YX);
+  m3mul(P.Z, S.X, ZX);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { C.Y[r][c] = YX[r][c] + S.Y[r][c]; C.Z[r][c] = ZX[r][c] + P.tau * S.Y[r][c] + S.Z[r][c]; }
+  C.tau = P.tau + S.tau;
+}
+// packed index of (i,j), i <= j, in a row-major upper triangle of a 9x9
+__host__ __device__ constexpr int tri9(int i, int j) { return i * 9 - i * (i - 1) / 2 + (j - i); }
+
+// Tm += L N_j L^T (upper triangle)
 template <typename T>
-__device__ __forceinline__ void cov_accum_noise(const CovStep<T>& s, const T* L, T* Tm, const T* cg, const T* ca) {
-  const T hdt = T(0.5) * s.dt;
-  T U[9][6];     // columns 0-2: L Bg, 3-5: L Ba
-#pragma unroll 1
-  for (int i = 0; i < 9; ++i) {
-    const T g0 = L[i * 9 + 0], g1 = L[i * 9 + 1], g2 = L[i * 9 + 2];
-    const T b0 = L[i * 9 + 3] + hdt * L[i * 9 + 6], b1 = L[i * 9 + 4] + hdt * L[i * 9 + 7], b2 = L[i * 9 + 5] + hdt * L[i * 9 + 8];
+__device__ __forceinline__ void covl_accum_noise(const CovL<T>& L, const Q4<T>& qk, const T (&R)[3][3], T dt, const T* cg,
+                                                 const T* ca, T (&Tm)[kCovT]) {
+  // Jr(Log dr)
+  T jc;
+  const V3<T> phi = so3_log(qk, jc);
+  const RotCoef<T> rc = rot_coef(phi);
+  T c1 = rc.c1, c2 = rc.c2;
+  if (!(rc.theta > num<T>::eps)) { c1 = T(0); c2 = T(0); }
+  const T xx = phi.x * phi.x, yy = phi.y * phi.y, zz = phi.z * phi.z, xy = phi.x * phi.y, xz = phi.x * phi.z, yz = phi.y * phi.z;
+  T Jr[3][3];
+  Jr[0][0] = T(1) - c2 * (yy + zz); Jr[0][1] = c1 * phi.z + c2 * xy;   Jr[0][2] = -c1 * phi.y + c2 * xz;
+  Jr[1][0] = -c1 * phi.z + c2 * xy;  Jr[1][1] = T(1) - c2 * (xx + zz); Jr[1][2] = c1 * phi.x + c2 * yz;
+  Jr[2][0] = c1 * phi.y + c2 * xz;   Jr[2][1] = -c1 * phi.x + c2 * yz;  Jr[2][2] = T(1) - c2 * (xx + yy);
+  const T wg[3] = {cg[0] * dt, cg[1] * dt, cg[2] * dt}, wa[3] = {ca[0] * dt, ca[1] * dt, ca[2] * dt};
+  T Q[3][3], K[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      U[i][c] = (g0 * s.Jr[0][c] + g1 * s.Jr[1][c] + g2 * s.Jr[2][c]) * s.dt;
-      U[i][3 + c] = (b0 * s.R[0][c] + b1 * s.R[1][c] + b2 * s.R[2][c]) * s.dt;
+      Q[r][c] = Jr[r][0] * wg[0] * Jr[c][0] + Jr[r][1] * wg[1] * Jr[c][1] + Jr[r][2] * wg[2] * Jr[c][2];
+      K[r][c] = R[r][0] * wa[0] * R[c][0] + R[r][1] * wa[1] * R[c][1] + R[r][2] * wa[2] * R[c][2];
     }
-  }
-  const T idt = T(1) / s.dt;
-  const T w[6] = {cg[0] * idt, cg[1] * idt, cg[2] * idt, ca[0] * idt, ca[1] * idt, ca[2] * idt};
-#pragma unroll 1
-  for (int i = 0; i < 9; ++i)
-#pragma unroll 1
-    for (int jj = 0; jj < 9; ++jj) {
-      T acc = T(0);
+  T V[9][3];      // [X;Y;Z] Q
+  m3mul(L.X, Q, *reinterpret_cast<T(*)[3][3]>(&V[0]));
+  m3mul(L.Y, Q, *reinterpret_cast<T(*)[3][3]>(&V[3]));
+  m3mul(L.Z, Q, *reinterpret_cast<T(*)[3][3]>(&V[6]));
+  const T s = L.tau + T(0.5) * dt;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) acc += U[i][c] * w[c] * U[jj][c];
-      Tm[i * 9 + jj] += acc;
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = i; j < 9; ++j) {
+      const T(&Bj)[3][3] = j < 3 ? L.X : (j < 6 ? L.Y : L.Z);
+      const int jr = j % 3;
+      T acc = V[i][0] * Bj[jr][0] + V[i][1] * Bj[jr][1] + V[i][2] * Bj[jr][2];
+      if (i >= 3) {                                            // accelerometer part: blocks (1,1), (1,2), (2,2)
+        const T k = K[i % 3][jr];
+        acc += (i < 6 ? (j < 6 ? k : s * k) : s * s * k);
+      }
+      Tm[tri9(i, j)] += acc;
     }
-}
-template <typename T> __device__ __forceinline__ void mat9_identity(T* L) {
-  for (int i = 0; i < 81; ++i) L[i] = (i % 10 == 0) ? T(1) : T(0);
 }
 
+constexpr int kCovThreads = 64;
+
 template <typename T>
-__global__ void imu_cov_chunk_prod_kernel(const T* Rk, const T* Rij, const T* a, const T* dt, T* P, long long F, long long chunk,
-                                          long long NC, long long total) {
+__global__ void __launch_bounds__(kCovThreads) imu_cov_chunk_prod_kernel(const T* Rk, const T* Rij, const T* a, const T* dt, T* P,
+                                                                        long long F, long long chunk, long long NC,
+                                                                        long long total) {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= total) return;
   const long long b = id / NC, c = id % NC;
   Rk += b * F * 4; Rij += b * F * 4; a += b * F * 3; dt += b * F;
-  T L[81];
-  mat9_identity(L);
+  CovL<T> L;
+  covl_identity(L);
   const long long lo = c * chunk, hi = (lo + chunk < F) ? lo + chunk : F;
-  CovStep<T> s;
-  for (long long j = hi - 1; j >= lo; --j) { cov_step_load(s, Rk, Rij, a, dt, j, false); cov_apply_A(s, L); }
-  for (int i = 0; i < 81; ++i) P[id * 81 + i] = L[i];
+  for (long long j = hi - 1; j >= lo; --j) {
+    T R[3][3];
+    quat_matrix(ldq(Rij + j * 4), R);
+    covl_apply_A(L, ldq(Rk + j * 4), R, ld3(a + j * 3), dt[j]);
+  }
+  covl_store(L, P + id * kCovL);
 }
-// S[c] = P_c P_{c+1} ... P_{NC-1};  S[NC] = I     (P and S share storage layout (B, NC+1, 81); in-place backwards)
+// S[c] = P_c P_{c+1} ... P_{NC-1};  S[NC] = I     (S: (B, NC+1, 28))
 template <typename T> __global__ void imu_cov_suffix_kernel(const T* P, T* S, long long NC, long long B) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  T acc[81], tmp[81];
-  mat9_identity(acc);
-  for (int i = 0; i < 81; ++i) S[(b * (NC + 1) + NC) * 81 + i] = acc[i];
+  CovL<T> acc, Pc, nx;
+  covl_identity(acc);
+  covl_store(acc, S + (b * (NC + 1) + NC) * kCovL);
   for (long long c = NC - 1; c >= 0; --c) {
-    const T* Pc = P + (b * NC + c) * 81;
-    for (int i = 0; i < 9; ++i)
-      for (int jj = 0; jj < 9; ++jj) {
-        T v = T(0);
-        for (int k = 0; k < 9; ++k) v += Pc[i * 9 + k] * acc[k * 9 + jj];
-        tmp[i * 9 + jj] = v;
-      }
-    for (int i = 0; i < 81; ++i) { acc[i] = tmp[i]; S[(b * (NC + 1) + c) * 81 + i] = tmp[i]; }
+    covl_load(Pc, P + (b * NC + c) * kCovL);
+    covl_mul(Pc, acc, nx);
+    acc = nx;
+    covl_store(acc, S + (b * (NC + 1) + c) * kCovL);
   }
 }
 template <typename T>
-__global__ void imu_cov_accum_kernel(const T* Rk, const T* Rij, const T* a, const T* dt, const T* gcov, const T* acov,
-                                     long long cov_stride_b, long long cov_stride_f, const T* S, T* Tc, long long F, long long chunk,
-                                     long long NC, long long total) {
+__global__ void __launch_bounds__(kCovThreads) imu_cov_accum_kernel(const T* Rk, const T* Rij, const T* a, const T* dt,
+                                                                   const T* gcov, const T* acov, long long cov_stride_b,
+                                                                   long long cov_stride_f, const T* S, T* Tc, long long F,
+                                                                   long long chunk, long long NC, long long total) {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= total) return;
   const long long b = id / NC, c = id % NC;
   Rk += b * F * 4; Rij += b * F * 4; a += b * F * 3; dt += b * F;
   gcov += b * cov_stride_b; acov += b * cov_stride_b;
-  T L[81], Tm[81];
-  for (int i = 0; i < 81; ++i) { L[i] = S[(b * (NC + 1) + c + 1) * 81 + i]; Tm[i] = T(0); }
+  CovL<T> L;
+  covl_load(L, S + (b * (NC + 1) + c + 1) * kCovL);
+  T Tm[kCovT];
+#pragma unroll
+  for (int i = 0; i < kCovT; ++i) Tm[i] = T(0);
   const long long lo = c * chunk, hi = (lo + chunk < F) ? lo + chunk : F;
-  CovStep<T> s;
   for (long long j = hi - 1; j >= lo; --j) {
-    cov_step_load(s, Rk, Rij, a, dt, j, true);
-    cov_accum_noise(s, L, Tm, gcov + j * cov_stride_f, acov + j * cov_stride_f);   // uses L_{j+1}
-    cov_apply_A(s, L);                                                              // L_j = A_j L_{j+1}
+    const Q4<T> qk = ldq(Rk + j * 4);
+    T R[3][3];
+    quat_matrix(ldq(Rij + j * 4), R);
+    const T d = dt[j];
+    covl_accum_noise(L, qk, R, d, gcov + j * cov_stride_f, acov + j * cov_stride_f, Tm);   // uses L_{j+1}
+    covl_apply_A(L, qk, R, ld3(a + j * 3), d);                                              // L_j = A_j L_{j+1}
   }
-  for (int i = 0; i < 81; ++i) Tc[id * 81 + i] = Tm[i];
+#pragma unroll
+  for (int i = 0; i < kCovT; ++i) Tc[id * kCovT + i] = Tm[i];
 }
-// cov[b] = sum_c T_c + S_0 init_cov S_0^T
+// cov[b] = sum_c T_c + S_0 init_cov S_0^T: one CTA of 81 threads per trajectory, thread e owns entry (e/9, e%9)
 template <typename T>
-__global__ void imu_cov_finish_kernel(const T* S, const T* Tc, const T* init_cov, long long init_stride, T* cov, long long NC,
-                                      long long B) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const T* L0 = S + b * (NC + 1) * 81;
-  const T* C0 = init_cov + b * init_stride;
-  T tmp[81];
-  for (int i = 0; i < 9; ++i)
-    for (int jj = 0; jj < 9; ++jj) {
-      T v = T(0);
-      for (int k = 0; k < 9; ++k) v += L0[i * 9 + k] * C0[k * 9 + jj];
-      tmp[i * 9 + jj] = v;
-    }
-  for (int i = 0; i < 9; ++i)
-    for (int jj = 0; jj < 9; ++jj) {
-      T v = T(0);
-      for (int k = 0; k < 9; ++k) v += tmp[i * 9 + k] * L0[jj * 9 + k];
-      for (long long c = 0; c < NC; ++c) v += Tc[(b * NC + c) * 81 + i * 9 + jj];
-      cov[b * 81 + i * 9 + jj] = v;
-    }
+__global__ void __launch_bounds__(96) imu_cov_finish_kernel(const T* S, const T* Tc, const T* init_cov, long long init_stride,
+                                                           T* cov, long long NC) {
+  const long long b = blockIdx.x;
+  __shared__ T L0[81], C0[81], tmp[81];
+  const int e = threadIdx.x;
+  if (e < 81) {
+    const T* s = S + b * (NC + 1) * kCovL;
+    const int r = e / 9, c = e % 9, br = r / 3, bc = c / 3, rr = r % 3, cc = c % 3;
+    T v = T(0);
+    if (bc == 0) v = s[br * 9 + rr * 3 + cc];                         // X, Y, Z
+    else if (br == bc) v = rr == cc ? T(1) : T(0);                    // identity blocks
+    else if (br == 2 && bc == 1) v = rr == cc ? s[27] : T(0);         // tau I
+    L0[e] = v;
+    C0[e] = init_cov[b * init_stride + e];
+  }
+  __syncthreads();
+  if (e < 81) {
+    const int i = e / 9, jj = e % 9;
+    T v = T(0);
+    for (int k = 0; k < 9; ++k) v += L0[i * 9 + k] * C0[k * 9 + jj];
+    tmp[e] = v;
+  }
+  __syncthreads();
+  if (e < 81) {
+    const int i = e / 9, jj = e % 9;
+    T v = T(0);
+    for (int k = 0; k < 9; ++k) v += tmp[i * 9 + k] * L0[jj * 9 + k];
+    const int q = i <= jj ? tri9(i, jj) : tri9(jj, i);
+    const T* t = Tc + b * NC * kCovT + q;
+    for (long long c = 0; c < NC; ++c) v += t[c * kCovT];
+    cov[b * 81 + e] = v;
+  }
 }
 
 }  // namespace b200pose
@@ -462,7 +521,8 @@ SCAN_ABI(Sim3, Sim3g)
 IMU_ABI(f32, float, 4)
 IMU_ABI(f64, double, 2)
 
-// work: B * ((NC + 1) + 2 * NC) * 81 elements, NC = ceil(F / chunk)
+// work: at least B * ((NC + 1) * 28 + NC * (28 + 45)) elements, NC = ceil(F / chunk)  (callers may keep the older,
+// larger B * (3 NC + 1) * 81 sizing)
 #define IMU_COV_ABI(SFX, CT)                                                                                           \
   B200_EXPORT int b200_imu_cov_##SFX(const CT* Rk, const CT* Rij, const CT* a, const CT* dt, const CT* gyro_cov,       \
                                      const CT* acc_cov, long long cov_stride_b, long long cov_stride_f,                \
@@ -471,15 +531,15 @@ IMU_ABI(f64, double, 2)
     if (B <= 0 || F <= 0 || chunk <= 0) return 0;                                                                      \
     const long long NC = (F + chunk - 1) / chunk, total = B * NC;                                                      \
     CT* P = work;                                                                                                      \
-    CT* S = P + total * 81;                                                                                            \
-    CT* Tc = S + B * (NC + 1) * 81;                                                                                    \
+    CT* S = P + total * kCovL;                                                                                         \
+    CT* Tc = S + B * (NC + 1) * kCovL;                                                                                 \
     cudaStream_t st = (cudaStream_t)stream;                                                                            \
-    imu_cov_chunk_prod_kernel<CT><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(Rk, Rij, a, dt, P, F, chunk, NC, total); \
+    const unsigned gb = (unsigned)((total + kCovThreads - 1) / kCovThreads);                                           \
+    imu_cov_chunk_prod_kernel<CT><<<gb, kCovThreads, 0, st>>>(Rk, Rij, a, dt, P, F, chunk, NC, total);                 \
     imu_cov_suffix_kernel<CT><<<(unsigned)((B + 31) / 32), 32, 0, st>>>(P, S, NC, B);                                  \
-    imu_cov_accum_kernel<CT><<<(unsigned)((total + 63) / 64), 64, 0, st>>>(Rk, Rij, a, dt, gyro_cov, acc_cov,          \
-                                                                           cov_stride_b, cov_stride_f, S, Tc, F, chunk, \
-                                                                           NC, total);                                 \
-    imu_cov_finish_kernel<CT><<<(unsigned)((B + 31) / 32), 32, 0, st>>>(S, Tc, init_cov, init_stride, cov, NC, B);     \
+    imu_cov_accum_kernel<CT><<<gb, kCovThreads, 0, st>>>(Rk, Rij, a, dt, gyro_cov, acc_cov, cov_stride_b,              \
+                                                         cov_stride_f, S, Tc, F, chunk, NC, total);                    \
+    imu_cov_finish_kernel<CT><<<(unsigned)B, 96, 0, st>>>(S, Tc, init_cov, init_stride, cov, NC);                      \
     return (int)cudaGetLastError();                                                                                    \
   }
 IMU_COV_ABI(f32, float)

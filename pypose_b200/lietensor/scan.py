@@ -83,7 +83,7 @@ torch.library.impl(f"{NS}::imu_integrate", "CUDA")(_imu_cuda)
 torch.library.impl(f"{NS}::imu_predict", "CUDA")(_imu_predict_cuda)
 
 
-def _imu_cov_cuda(Rk, Rij, a, dt, gyro_cov, acc_cov, init_cov, chunk=128):
+def _imu_cov_cuda(Rk, Rij, a, dt, gyro_cov, acc_cov, init_cov, chunk=None):
     """(B,F,4), (B,F,4), (B,F,3), (B,F,1), (B,1|F,3), (B,1|F,3), (B|1,9,9) -> (B,9,9)."""
     B, F = dt.shape[:2]
     dtype, dev = dt.dtype, dt.device
@@ -96,8 +96,10 @@ def _imu_cov_cuda(Rk, Rij, a, dt, gyro_cov, acc_cov, init_cov, chunk=128):
     cov = torch.empty(B, 9, 9, dtype=dtype, device=dev)
     if B * F == 0:
         return init_cov.expand(B, 9, 9).clone()
+    if chunk is None:                     # one thread per (trajectory, chunk): keep >= ~64k threads in flight
+        chunk = min(256, max(16, (B * F) // 65536))
     NC = (F + chunk - 1) // chunk
-    work = torch.empty(B * (3 * NC + 1) * 81, dtype=dtype, device=dev)
+    work = torch.empty(B * ((NC + 1) * 28 + NC * (28 + 45)), dtype=dtype, device=dev)
     sym = f"b200_imu_cov_{_C.suffix(dtype)}"
     with torch.cuda.device(dev):
         _C.check(_C.fn(sym)(_p(Rk), _p(Rij), _p(a), _p(dt), _p(gyro_cov), _p(acc_cov), gyro_cov.shape[1] * 3,
