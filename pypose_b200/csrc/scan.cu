@@ -302,22 +302,27 @@ template <typename T> __device__ __forceinline__ void m3mul(const T (&A)[3][3], 
 #pragma unroll
     for (int c = 0; c < 3; ++c) C[r][c] = A[r][0] * B[0][c] + A[r][1] * B[1][c] + A[r][2] * B[2][c];
 }
+// R = I + 2 w [v]x + 2 [v]x^2 (same polynomial in q as qrot, lie_math.cuh)
 template <typename T> __device__ __forceinline__ void quat_matrix(const Q4<T>& q, T (&R)[3][3]) {
-  const V3<T> c0 = qrot(q, mk(T(1), T(0), T(0))), c1 = qrot(q, mk(T(0), T(1), T(0))), c2 = qrot(q, mk(T(0), T(0), T(1)));
-  R[0][0] = c0.x; R[1][0] = c0.y; R[2][0] = c0.z;
-  R[0][1] = c1.x; R[1][1] = c1.y; R[2][1] = c1.z;
-  R[0][2] = c2.x; R[1][2] = c2.y; R[2][2] = c2.z;
+  const T x2 = q.v.x + q.v.x, y2 = q.v.y + q.v.y, z2 = q.v.z + q.v.z;
+  const T xx = q.v.x * x2, yy = q.v.y * y2, zz = q.v.z * z2, xy = q.v.x * y2, xz = q.v.x * z2, yz = q.v.y * z2;
+  const T wx = q.w * x2, wy = q.w * y2, wz = q.w * z2;
+  R[0][0] = T(1) - yy - zz; R[0][1] = xy - wz;        R[0][2] = xz + wy;
+  R[1][0] = xy + wz;        R[1][1] = T(1) - xx - zz; R[1][2] = yz - wx;
+  R[2][0] = xz - wy;        R[2][1] = yz + wx;        R[2][2] = T(1) - xx - yy;
 }
 // L <- A_j L.  R = matrix of Rij_j (returned for the noise term), qk = Rk_j.
 template <typename T>
 __device__ __forceinline__ void covl_apply_A(CovL<T>& L, const Q4<T>& qk, const T (&R)[3][3], const V3<T>& av, T dt) {
   T Rk[3][3], M1[3][3], MX[3][3], Xn[3][3];
   quat_matrix(qk, Rk);
-  const T H[3][3] = {{T(0), -av.z, av.y}, {av.z, T(0), -av.x}, {-av.y, av.x, T(0)}};
+  const T ax = av.x * dt, ay = av.y * dt, az = av.z * dt;        // M1 = -R a^ dt, column c = -R (a x e_c) dt
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) M1[r][c] = -(R[r][0] * H[0][c] + R[r][1] * H[1][c] + R[r][2] * H[2][c]) * dt;
+  for (int r = 0; r < 3; ++r) {
+    M1[r][0] = R[r][2] * ay - R[r][1] * az;
+    M1[r][1] = R[r][0] * az - R[r][2] * ax;
+    M1[r][2] = R[r][1] * ax - R[r][0] * ay;
+  }
   m3mul(M1, L.X, MX);
   const T hdt = T(0.5) * dt;
 #pragma unroll
@@ -354,11 +359,18 @@ template <typename T>
 __device__ __forceinline__ void covl_accum_noise(const CovL<T>& L, const Q4<T>& qk, const T (&R)[3][3], T dt, const T* cg,
                                                  const T* ca, T (&Tm)[kCovT]) {
   // Jr(Log dr)
+  // Jr(Log dr) = I - c1 K + c2 K^2.  theta/2 = atan(|v|/w), so sin^2(theta/2) = |v|^2/|q|^2 and
+  // sin(theta) = 2 |v| w / |q|^2 come from the quaternion itself: no sincos (the closed forms are those of rot_coef).
   T jc;
   const V3<T> phi = so3_log(qk, jc);
-  const RotCoef<T> rc = rot_coef(phi);
-  T c1 = rc.c1, c2 = rc.c2;
-  if (!(rc.theta > num<T>::eps)) { c1 = T(0); c2 = T(0); }
+  const T x = dot(phi, phi), n2 = dot(qk.v, qk.v), iq = m_rcp(n2 + qk.w * qk.w);
+  const T inv_th = m_rsqrt(x), th = x * inv_th, ix = inv_th * inv_th;
+  const bool small = x < num<T>::small2;
+  const T imag_s = T(0.5) + x * (T(-1.0 / 48) + x * (T(1.0 / 3840) + x * (T(-1.0 / 645120) + x * T(1.0 / 185794560))));
+  const T c2_s = T(1.0 / 6) + x * (T(-1.0 / 120) + x * (T(1.0 / 5040) + x * (T(-1.0 / 362880) + x * T(1.0 / 39916800))));
+  T c1 = small ? T(2) * imag_s * imag_s : T(2) * n2 * iq * ix;
+  T c2 = small ? c2_s : (th - T(2) * m_sqrt(n2) * m_abs(qk.w) * iq) * ix * inv_th;
+  if (!(x > num<T>::eps * num<T>::eps)) { c1 = T(0); c2 = T(0); }
   const T xx = phi.x * phi.x, yy = phi.y * phi.y, zz = phi.z * phi.z, xy = phi.x * phi.y, xz = phi.x * phi.z, yz = phi.y * phi.z;
   T Jr[3][3];
   Jr[0][0] = T(1) - c2 * (yy + zz); Jr[0][1] = c1 * phi.z + c2 * xy;   Jr[0][2] = -c1 * phi.y + c2 * xz;
@@ -406,25 +418,70 @@ __global__ void __launch_bounds__(kCovThreads) imu_cov_chunk_prod_kernel(const T
   CovL<T> L;
   covl_identity(L);
   const long long lo = c * chunk, hi = (lo + chunk < F) ? lo + chunk : F;
+  // the loads of step j-1 are issued before the arithmetic of step j (each thread walks its own stream: the only
+  // latency hiding inside a thread is this one-step software pipeline)
+  Q4<T> qk = ldq(Rk + (hi - 1) * 4), qi = ldq(Rij + (hi - 1) * 4);
+  V3<T> av = ld3(a + (hi - 1) * 3);
+  T d = dt[hi - 1];
   for (long long j = hi - 1; j >= lo; --j) {
+    const long long jn = j > lo ? j - 1 : j;
+    const Q4<T> qk_n = ldq(Rk + jn * 4), qi_n = ldq(Rij + jn * 4);
+    const V3<T> av_n = ld3(a + jn * 3);
+    const T d_n = dt[jn];
     T R[3][3];
-    quat_matrix(ldq(Rij + j * 4), R);
-    covl_apply_A(L, ldq(Rk + j * 4), R, ld3(a + j * 3), dt[j]);
+    quat_matrix(qi, R);
+    covl_apply_A(L, qk, R, av, d);
+    qk = qk_n; qi = qi_n; av = av_n; d = d_n;
   }
   covl_store(L, P + id * kCovL);
 }
-// S[c] = P_c P_{c+1} ... P_{NC-1};  S[NC] = I     (S: (B, NC+1, 28))
-template <typename T> __global__ void imu_cov_suffix_kernel(const T* P, T* S, long long NC, long long B) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  CovL<T> acc, Pc, nx;
-  covl_identity(acc);
-  covl_store(acc, S + (b * (NC + 1) + NC) * kCovL);
-  for (long long c = NC - 1; c >= 0; --c) {
-    covl_load(Pc, P + (b * NC + c) * kCovL);
-    covl_mul(Pc, acc, nx);
-    acc = nx;
-    covl_store(acc, S + (b * (NC + 1) + c) * kCovL);
+// S[c] = P_c P_{c+1} ... P_{NC-1};  S[NC] = I     (S: (B, NC+1, 28)).  One warp per trajectory: tiles of 32 chunks from
+// the right, order-preserving suffix scan by shuffles (the product is associative, not commutative), carry = S of the
+// tile to the right.
+template <typename T> __device__ __forceinline__ CovL<T> covl_shfl_down(const CovL<T>& v, int o) {
+  CovL<T> r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      r.X[i][j] = __shfl_down_sync(0xffffffffu, v.X[i][j], o);
+      r.Y[i][j] = __shfl_down_sync(0xffffffffu, v.Y[i][j], o);
+      r.Z[i][j] = __shfl_down_sync(0xffffffffu, v.Z[i][j], o);
+    }
+  r.tau = __shfl_down_sync(0xffffffffu, v.tau, o);
+  return r;
+}
+template <typename T> __device__ __forceinline__ CovL<T> covl_bcast0(const CovL<T>& v) {
+  CovL<T> r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      r.X[i][j] = __shfl_sync(0xffffffffu, v.X[i][j], 0);
+      r.Y[i][j] = __shfl_sync(0xffffffffu, v.Y[i][j], 0);
+      r.Z[i][j] = __shfl_sync(0xffffffffu, v.Z[i][j], 0);
+    }
+  r.tau = __shfl_sync(0xffffffffu, v.tau, 0);
+  return r;
+}
+template <typename T> __global__ void __launch_bounds__(128) imu_cov_suffix_kernel(const T* P, T* S, long long NC, long long B) {
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;                                    // whole warps leave together
+  const int lane = threadIdx.x & 31;
+  CovL<T> carry, v, o, nx;
+  covl_identity(carry);
+  if (lane == 0) covl_store(carry, S + (b * (NC + 1) + NC) * kCovL);
+  for (long long base = ((NC - 1) / 32) * 32; base >= 0; base -= 32) {
+    const long long c = base + lane;
+    if (c < NC) covl_load(v, P + (b * NC + c) * kCovL); else covl_identity(v);
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+      o = covl_shfl_down(v, off);
+      if (lane + off < 32) { covl_mul(v, o, nx); v = nx; }
+    }
+    covl_mul(v, carry, nx);
+    if (c < NC) covl_store(nx, S + (b * (NC + 1) + c) * kCovL);
+    carry = covl_bcast0(nx);
   }
 }
 template <typename T>
@@ -536,7 +593,7 @@ IMU_ABI(f64, double, 2)
     cudaStream_t st = (cudaStream_t)stream;                                                                            \
     const unsigned gb = (unsigned)((total + kCovThreads - 1) / kCovThreads);                                           \
     imu_cov_chunk_prod_kernel<CT><<<gb, kCovThreads, 0, st>>>(Rk, Rij, a, dt, P, F, chunk, NC, total);                 \
-    imu_cov_suffix_kernel<CT><<<(unsigned)((B + 31) / 32), 32, 0, st>>>(P, S, NC, B);                                  \
+    imu_cov_suffix_kernel<CT><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(P, S, NC, B);                                       \
     imu_cov_accum_kernel<CT><<<gb, kCovThreads, 0, st>>>(Rk, Rij, a, dt, gyro_cov, acc_cov, cov_stride_b,              \
                                                          cov_stride_f, S, Tc, F, chunk, NC, total);                    \
     imu_cov_finish_kernel<CT><<<(unsigned)B, 96, 0, st>>>(S, Tc, init_cov, init_stride, cov, NC);                      \

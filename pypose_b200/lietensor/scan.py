@@ -15,6 +15,9 @@ torch.library.define(f"{NS}::imu_predict",
                      "float[] gravity) -> (Tensor, Tensor, Tensor)")
 
 
+torch.library.define(f"{NS}::imu_full",
+                     "(Tensor dt, Tensor gyro, Tensor acc, Tensor? rot, Tensor init_rot, Tensor init_pos, Tensor init_vel, "
+                     "float[] gravity) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
 torch.library.define(f"{NS}::imu_cov",
                      "(Tensor Rk, Tensor Rij, Tensor a, Tensor dt, Tensor gyro_cov, Tensor acc_cov, Tensor init_cov) -> Tensor")
 
@@ -79,7 +82,15 @@ def _imu_predict_cuda(dt, gyro, acc, rot, init_rot, init_pos, init_vel, gravity)
     return _imu_launch(dt, gyro, acc, rot, init_rot, gravity, False, init_pos, init_vel)[1]
 
 
+def _imu_full_cuda(dt, gyro, acc, rot, init_rot, init_pos, init_vel, gravity):
+    """integrate + predict in one launch, all nine outputs (a, Dp, Dv, Dr, Dt, w, rot, vel, pos): the prop_cov=True
+    forward needs a / Dr / w for the covariance and the predicted states."""
+    inte, pred = _imu_launch(dt, gyro, acc, rot, init_rot, gravity, True, init_pos, init_vel)
+    return (*inte, *pred)
+
+
 torch.library.impl(f"{NS}::imu_integrate", "CUDA")(_imu_cuda)
+torch.library.impl(f"{NS}::imu_full", "CUDA")(_imu_full_cuda)
 torch.library.impl(f"{NS}::imu_predict", "CUDA")(_imu_predict_cuda)
 
 

@@ -59,8 +59,14 @@ class IMUPreintegrator(nn.Module):
                 self.pos, self.rot, self.vel = p[..., -1:, :], predict['rot'][..., -1:, :], v[..., -1:, :]
                 self.cov = None
             return {**predict, 'cov': None}
-        inte = self.integrate(dt, gyro, acc, rot=rot, init_rot=init_state['rot'])
-        predict = self.predict(init_state, inte)
+        # integrate + predict in one launch; a / Dr / w feed the covariance kernels directly (the reference's
+        # vec2skew(a) (B,F,3,3) detour is only kept in the public propagate_cov signature)
+        rot_t = rot.tensor() if isinstance(rot, LieTensor) else None
+        a, Dp, Dv, Dr, Dt, w, r, v, p = torch.ops.b200pose.imu_full(
+            dt, gyro.to(dt.dtype), acc.to(dt.dtype), rot_t, init_state['rot'].tensor(), init_state['pos'],
+            init_state['vel'], [0.0, 0.0, self._g])
+        inte = {'a': a, 'Dp': Dp, 'Dv': Dv, 'Dr': SO3(Dr), 'Dt': Dt, 'w': SO3(w)}
+        predict = {'rot': SO3(r), 'vel': v, 'pos': p}
         if self.prop_cov:
             gyro_cov = self.gyro_cov.repeat([B, 1, 1]) if gyro_cov is None else gyro_cov
             acc_cov = self.acc_cov.repeat([B, 1, 1]) if acc_cov is None else acc_cov
@@ -70,9 +76,9 @@ class IMUPreintegrator(nn.Module):
                 init_cov = init_state['cov']
             Rij = init_state['Rij'] if 'Rij' in init_state else self.Rij
             Rij = Rij * inte['Dr'] if Rij is not None else inte['Dr']
-            cov_in = {'Rij': Rij.detach(), 'Rk': inte['w'].detach(), 'Ha': vec2skew(inte['a'].detach()),
-                      'dt': dt.detach()}
-            cov = self.propagate_cov(cov_input=cov_in, init_cov=init_cov, gyro_cov=gyro_cov, acc_cov=acc_cov)
+            cov = {'cov': torch.ops.b200pose.imu_cov(inte['w'].tensor().detach(), Rij.tensor().detach(), a.detach(),
+                                                     dt.detach(), gyro_cov, acc_cov, init_cov),
+                   'Rij': Rij[..., -1:, :]}
         else:
             cov = {'cov': None}
         if not self.reset:      # carry the last state over to the next call (imu_preintegrator.py:305-310)

@@ -184,6 +184,9 @@ def _install_cpu_oracle_scan_kernels():
         return torch.from_numpy(S.imu_cov(n(Rk), n(Rij), n(a), n(dt), gc, ac, n(init_cov))).to(dt.dtype)
 
     torch.library.impl("b200pose::imu_predict", "CPU")(imu_predict)
+    torch.library.impl("b200pose::imu_full", "CPU")(
+        lambda dt, gyro, acc, rot, init_rot, init_pos, init_vel, gravity:
+        (*imu(dt, gyro, acc, rot, init_rot, gravity), *imu_predict(dt, gyro, acc, rot, init_rot, init_pos, init_vel, gravity)))
     torch.library.impl("b200pose::imu_cov", "CPU")(imu_cov)
 
 
