@@ -9,6 +9,7 @@
 // elements in registers, thread totals are scanned with order-preserving warp shuffles, warp totals through
 // shared memory.  The group operation is not commutative: every combine keeps (earlier, later) order.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include "lie_math.cuh"
 
@@ -188,19 +189,20 @@ __global__ void __launch_bounds__(kScanThreads) imu_integrate_kernel(
   for (long long base = 0; base < F; base += TILE) {
     const long long first = base + (long long)threadIdx.x * CH;
     // ---- rotation part: dr_k and the thread-local running product
-    Elem<T> drs[CH], loc[CH];
+    Elem<T> loc[CH];
     T dts[CH];
     Elem<T> run = elem_identity<T>();
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      drs[c] = elem_identity<T>();
       dts[c] = T(0);
       if (first + c < F) {
         const long long k = first + c;
         dts[c] = dt[k];
         const V3<T> phi = dts[c] * mk(gyro[k * 3], gyro[k * 3 + 1], gyro[k * 3 + 2]);
-        drs[c].q = so3_exp(phi, rot_coef(phi));
-        run = g_mul<SO3g, T>(run, drs[c]);
+        Elem<T> dr = elem_identity<T>();
+        dr.q = so3_exp(phi, rot_coef(phi));
+        if (a_out) stq(w_out + k * 4, dr.q);        // written here so that the increments need not stay in registers
+        run = g_mul<SO3g, T>(run, dr);
       }
       loc[c] = run;
     }
@@ -225,7 +227,6 @@ __global__ void __launch_bounds__(kScanThreads) imu_integrate_kernel(
         if (a_out) {
           st3(a_out + k * 3, ak);
           stq(Dr + k * 4, Rafter.q);
-          stq(w_out + k * 4, drs[c].q);
         }
         if (rot_o) stq(rot_o + k * 4, qmul(R0.q, Rafter.q));
       }
@@ -563,20 +564,34 @@ SCAN_ABI(SE3, SE3g)
 SCAN_ABI(RxSO3, RxSO3g)
 SCAN_ABI(Sim3, Sim3g)
 
-#define IMU_ABI(SFX, CT, CH)                                                                                           \
+// Samples per thread (CH) trades scan overhead (amortised over CH) against coalescing (a thread's CH consecutive
+// samples make every warp access CH-strided).  Measured on B200 at 1e3 x 1e4 samples (tools/ab_imu.py): fp64 predict-only
+// 0.61 ms at CH=2 vs 0.72 (CH=1) / 0.74 (CH=4); fp64 with the six integrate outputs 0.74 ms at CH=1 vs 0.79 / 1.14;
+// fp32 predict-only 0.29 ms at CH=2 vs 0.48 (CH=4) / 0.60 (CH=8).  B200POSE_IMU_CH overrides for A/B runs.
+template <typename T, int CH>
+static void imu_launch(const T* dt, const T* gyro, const T* acc, const T* rot, const T* init_rot, long long init_stride,
+                       const T* g, T* a, T* Dp, T* Dv, T* Dr, T* Dt, T* w, const T* init_pos, const T* init_vel,
+                       long long pv_stride, T* rot_out, T* vel_out, T* pos_out, long long B, long long F, cudaStream_t s) {
+  imu_integrate_kernel<T, CH><<<(unsigned)B, kScanThreads, 0, s>>>(dt, gyro, acc, rot, init_rot, init_stride, g[0], g[1], g[2],
+                                                                   a, Dp, Dv, Dr, Dt, w, init_pos, init_vel, pv_stride,
+                                                                   rot_out, vel_out, pos_out, F);
+}
+#define IMU_ABI(SFX, CT, CH_PREDICT, CH_FULL)                                                                          \
   B200_EXPORT int b200_imu_integrate_##SFX(const CT* dt, const CT* gyro, const CT* acc, const CT* rot,                 \
                                            const CT* init_rot, long long init_stride, const CT* gravity3_host, CT* a,  \
                                            CT* Dp, CT* Dv, CT* Dr, CT* Dt, CT* w, const CT* init_pos,                  \
                                            const CT* init_vel, long long pv_stride, CT* rot_out, CT* vel_out,          \
                                            CT* pos_out, long long B, long long F, void* s) {                           \
     if (B <= 0 || F <= 0) return 0;                                                                                    \
-    imu_integrate_kernel<CT, CH><<<(unsigned)B, kScanThreads, 0, (cudaStream_t)s>>>(                                   \
-        dt, gyro, acc, rot, init_rot, init_stride, gravity3_host[0], gravity3_host[1], gravity3_host[2], a, Dp, Dv,    \
-        Dr, Dt, w, init_pos, init_vel, pv_stride, rot_out, vel_out, pos_out, F);                                       \
+    static const int ch_env = getenv("B200POSE_IMU_CH") ? atoi(getenv("B200POSE_IMU_CH")) : 0;                         \
+    const int ch = ch_env ? ch_env : (a ? CH_FULL : CH_PREDICT);                                                       \
+    auto go = ch == 1 ? imu_launch<CT, 1> : (ch == 4 ? imu_launch<CT, 4> : imu_launch<CT, 2>);                         \
+    go(dt, gyro, acc, rot, init_rot, init_stride, gravity3_host, a, Dp, Dv, Dr, Dt, w, init_pos, init_vel, pv_stride,  \
+       rot_out, vel_out, pos_out, B, F, (cudaStream_t)s);                                                              \
     return (int)cudaGetLastError();                                                                                    \
   }
-IMU_ABI(f32, float, 4)
-IMU_ABI(f64, double, 2)
+IMU_ABI(f32, float, 2, 2)
+IMU_ABI(f64, double, 2, 1)
 
 // work: at least B * ((NC + 1) * 28 + NC * (28 + 45)) elements, NC = ceil(F / chunk)  (callers may keep the older,
 // larger B * (3 NC + 1) * 81 sizing)
