@@ -197,10 +197,12 @@ def run(args, rank, world, dev):
                   "trajectories_per_gpu": B, "samples": F, "dtype": "f64", "scaling": "weak",
                   "config": "IMUPreintegrator(prop_cov=False), 1e3 x 1e4 samples fp64 (BASELINE.json configs[3])"}
     imuc = pp.module.IMUPreintegrator(prop_cov=True, reset=True).double().to(dev)
-    ms5 = _max(_time_steps(lambda: imuc(dt, gyro, acc), lambda: None, 3, 1), world, dev)
+    ms5 = _max(_time_steps(lambda: imuc(dt, gyro, acc), lambda: None, max(5, steps // 4), 2), world, dev)
     out["imu_cov"] = {"msamples_per_s": round(world * B * F / (ms5 * 1e-3) / 1e6, 1), "ms_per_call": round(ms5, 3),
                       "trajectories_per_gpu": B, "samples": F, "dtype": "f64",
-                      "config": "IMUPreintegrator(prop_cov=True): integrate + predict + chunked 9x9 covariance propagation"}
+                      "hbm_gbs": round(B * F * (304 + 2 * 96) / (ms5 * 1e-3) / 1e9, 1), "alg_bytes_per_sample": 304 + 2 * 96,
+                      "config": "IMUPreintegrator(prop_cov=True), the reference default: integrate + predict (9 outputs, 304 B/sample) + "
+                                "block-triangular covariance propagation (two passes over Rk, Rij, a, dt: 2 x 96 B/sample)"}
     return out
 
 
