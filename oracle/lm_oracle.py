@@ -154,12 +154,21 @@ def pgo_jac_blocks(nodes, Z, ei, ej):
     return r, O.se3_Jl_inv(r) @ O.SE3_Adj(S)
 
 
-def pgo_linearize(nodes, Z, ei, ej, kind=0, delta=1.0):
+def pgo_linearize(nodes, Z, ei, ej, kind=0, delta=1.0, W=None):
+    """Per-edge J^T J / J^T r (optimizer.py:654-656).  With information matrices W ((E,6,6) or (1,6,6); `weight` of
+    LM.step, normalize_RWJ optimizer.py:80-95) returns (J^T W J, J^T W r, J^T J, J^T r, cost): the unweighted pair is
+    what the step-quality term uses (strategy.py:143 receives J and R, not the weight)."""
     r, J = pgo_jac_blocks(nodes, Z, ei, ej)
     rho, w = robust(kind, delta, (r ** 2).sum(-1))
-    M = np.swapaxes(J, -1, -2) @ J * w[:, None, None]
-    u = (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0] * w[:, None]
-    return _triu_pack(M), u, np.array([rho.sum()])
+    Jt = np.swapaxes(J, -1, -2)
+    M = Jt @ J * w[:, None, None]
+    u = (Jt @ r[..., None])[..., 0] * w[:, None]
+    if W is None:
+        return _triu_pack(M), u, np.array([rho.sum()])
+    W = np.broadcast_to(W.reshape(-1, 6, 6), J.shape)
+    Mw = Jt @ W @ J * w[:, None, None]
+    uw = (Jt @ W @ r[..., None])[..., 0] * w[:, None]
+    return _triu_pack(Mw), uw, _triu_pack(M), u, np.array([rho.sum()])
 
 
 def pgo_scatter(M21, u, ei, ej, n):

@@ -176,6 +176,23 @@ def main():
     for _ in range(4):
         losses.append(float(opt.step(X))); poses.append(net.pose.detach().clone().numpy())
     g["poseinv/cauchy/loss"], g["poseinv/cauchy/poses"] = np.array(losses), np.stack(poses)
+    # pose graph with information matrices (examples/module/pgo/pgo.py:75: optimizer.step(input, weight=infos)):
+    # per-edge SPD (E,6,6) and one shared (6,6)
+    torch.manual_seed(77)
+    edges_t, Z_t = torch.from_numpy(g["pgo/edges"]), ref.SE3(torch.from_numpy(g["pgo/Z"].copy()))
+    Bw = torch.randn(edges_t.shape[0], 6, 6, dtype=torch.float64)
+    infos = Bw @ Bw.mT / 6 + 0.5 * torch.eye(6, dtype=torch.float64)
+    g["pgo_w/infos"] = infos.numpy().copy()
+    for name, strat, W in (("trustregion", lambda: ref.optim.strategy.TrustRegion(), infos),
+                           ("constant", lambda: ref.optim.strategy.Constant(damping=1e-4), infos),
+                           ("shared", lambda: ref.optim.strategy.TrustRegion(), infos[3])):
+        model = PoseGraph(ref.SE3(torch.from_numpy(g["pgo/nodes0"].copy())))
+        opt = ref.optim.LM(model, strategy=strat())
+        losses, poses, rej = [], [], []
+        for _ in range(5):
+            losses.append(float(opt.step((edges_t, Z_t), weight=W)))
+            poses.append(model.nodes.detach().clone().numpy()); rej.append(opt.reject_count)
+        g[f"pgo_w/{name}/loss"], g[f"pgo_w/{name}/poses"], g[f"pgo_w/{name}/reject"] = np.array(losses), np.stack(poses), np.array(rej)
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, {k: (v if v.ndim == 1 and v.size <= 4 else v.shape) for k, v in g.items() if "loss" in k or "reject" in k})
 

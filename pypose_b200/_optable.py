@@ -121,6 +121,15 @@ LM_OPS = [
       ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "see b200_lm_reproj_accum"), ("double", "delta", "")],
      "modjac + J^T J of optimizer.py:645-656 for r = Log(Z^-1 A^-1 B) (examples/module/pgo/pgo.py:15-25); the sparse "
      "counterpart is bae.autograd.graph.jacobian + J.mT @ J, optimizer.py:637-642"),
+    ("b200_lm_pgo_linearize_w",
+     [("const REAL*", "nodes", "(N,7)"), ("const REAL*", "Z", "(E,7)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
+      ("const REAL*", "W", "(E,36) or (1,36) symmetric information matrices, row-major"),
+      ("long long", "w_stride", "36 per-edge, 0 one matrix for all edges"),
+      ("REAL*", "M", "(E,21) upper triangle of J^T W J"), ("REAL*", "u", "(E,6) J^T W r"),
+      ("REAL*", "M0", "(E,21) upper triangle of J^T J"), ("REAL*", "u0", "(E,6) J^T r"),
+      ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", "see b200_lm_reproj_accum"), ("double", "delta", "")],
+     "J^T W J / J^T W R with `weight` (optimizer.py:654-656, normalize_RWJ :80-95; examples/module/pgo/pgo.py:75 infos); the "
+     "unweighted blocks feed the step quality (strategy.py:143)"),
     ("b200_lm_pgo_scatter",
      [("const REAL*", "M", "(E,21)"), ("const REAL*", "u", "(E,6)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
       ("REAL*", "Hd", "(N,21) diagonal blocks, accumulated with atomics (zero-initialised by the caller)"),
@@ -190,6 +199,10 @@ LM_OPS = [
      [("const REAL*", "M", "(E,21)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"), ("long long", "E", ""),
       ("const REAL*", "D", "(n,6) step"), ("const REAL*", "g", "(n,6) J^T R"), ("double*", "ws", "ws[0] = D^T H D + 2 D^T g")],
      "TrustRegion 'predicted' reduction (J D)^T (2 R + J D), optim/strategy.py:143"),
+    ("b200_lm_pgo_predicted_edge",
+     [("const REAL*", "M0", "(E,21)"), ("const REAL*", "u0", "(E,6)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
+      ("const REAL*", "D", "(N,6) step"), ("double*", "ws", "ws[0] = sum_e d^T M0 d + 2 d^T u0, d = D_j - D_i")],
+     "TrustRegion 'predicted' reduction from per-edge blocks, optim/strategy.py:143"),
     ("b200_lm_ba_schur_diag",
      [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
       ("const REAL*", "Hpinv", "(P,6)"), ("REAL*", "Sd", "(C,21) in: damped Hcc; out: minus sum_k W_k Hpp^-1 W_k^T (atomics)")],

@@ -277,6 +277,42 @@ __global__ void __launch_bounds__(kLmThreads) lm_pgo_linearize_kernel(const T* _
   reduce_sums<1>(acc, ws);
 }
 
+// The same with per-edge information matrices W_e (examples/module/pgo/pgo.py:75 `weight=infos`): M = w J^T W J,
+// u = w J^T W r for the solve, M0 = w J^T J and u0 = w J^T r for the step-quality term (w = robust weight).
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_pgo_linearize_w_kernel(const T* __restrict__ nodes, const T* __restrict__ Z,
+                                                                         const int* __restrict__ ei, const int* __restrict__ ej,
+                                                                         const T* __restrict__ W, long long w_stride,
+                                                                         T* __restrict__ M, T* __restrict__ u, T* __restrict__ M0,
+                                                                         T* __restrict__ u0, double* ws, int rk, T rdelta,
+                                                                         long long E) {
+  double acc[1] = {0.0};
+  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
+    T a[7], b[7], z[7], w36[36];
+    const long long i = ei[e], j = ej[e];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a[k] = __ldg(nodes + i * 7 + k); b[k] = __ldg(nodes + j * 7 + k); z[k] = Z[e * 7 + k]; }
+#pragma unroll
+    for (int k = 0; k < 36; ++k) w36[k] = W[e * w_stride + k];
+    Tang<T> r;
+    Sys6<T> sw, s0;
+    pgo_linearize_w(load_se3(a), load_se3(b), load_se3(z), w36, r, sw, s0);
+    T rho, w;
+    robust_eval(rk, rdelta, tang6_sqnorm(r), rho, w);
+    if (rk) { sys6_scale(sw, w); sys6_scale(s0, w); }
+    int q = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      u[e * 6 + p] = sw.g[p];
+      u0[e * 6 + p] = s0.g[p];
+#pragma unroll
+      for (int c = p; c < 6; ++c) { M[e * 21 + q] = sw.A[p][c]; M0[e * 21 + q] = s0.A[p][c]; ++q; }
+    }
+    acc[0] += (double)rho;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
 // Hd[i] += M_e, Hd[j] += M_e (diagonal blocks, packed 21);  g[i] -= u_e, g[j] += u_e   (J_A = -J, J_B = +J)
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_pgo_scatter_kernel(const T* __restrict__ M, const T* __restrict__ u,
@@ -532,6 +568,14 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
     if (E <= 0) return 0;                                                                                             \
     lm_pgo_linearize_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                     \
         nodes, Z, ei, ej, M, u, ws, robust, (CT)delta, E);                                                            \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_linearize_w_##SFX(const CT* nodes, const CT* Z, const int* ei, const int* ej, const CT* W, \
+                                                long long w_stride, CT* M, CT* u, CT* M0, CT* u0, double* ws,          \
+                                                int robust, double delta, long long E, void* stream) {                 \
+    if (E <= 0) return 0;                                                                                             \
+    lm_pgo_linearize_w_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                   \
+        nodes, Z, ei, ej, W, w_stride, M, u, M0, u0, ws, robust, (CT)delta, E);                                       \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_scatter_##SFX(const CT* M, const CT* u, const int* ei, const int* ej, CT* Hd, CT* g,    \

@@ -222,7 +222,8 @@ template <typename T> LM_HD Tang<T> pgo_residual(const Elem<T>& A, const Elem<T>
   S = g_mul<SE3g, T>(g_inv<SE3g, T>(Z), g_inv<SE3g, T>(A));
   return g_log<SE3g, T>(g_mul<SE3g, T>(S, B));
 }
-template <typename T> LM_HD void pgo_linearize(const Elem<T>& A, const Elem<T>& B, const Elem<T>& Z, Tang<T>& r, Sys6<T>& s) {
+// rows of J = dr/dB (6x6) for one edge
+template <typename T> LM_HD void pgo_jacobian(const Elem<T>& A, const Elem<T>& B, const Elem<T>& Z, Tang<T>& r, T (&J)[6][6]) {
   Elem<T> S;
   r = pgo_residual(A, B, Z, S);
   M3<T> Ji, Bm;
@@ -239,15 +240,62 @@ template <typename T> LM_HD void pgo_linearize(const Elem<T>& A, const Elem<T>& 
   // J = [[Ji, Bm],[0, Ji]] [[R, tR],[0, R]] = [[Ji R, Ji tR + Bm R],[0, Ji R]]
   const M3<T> JR = m3_mul(Ji, R);
   const M3<T> JtR = m3_mul(Ji, tR), BR = m3_mul(Bm, R);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      J[i][c] = JR.m[i][c];
+      J[i][3 + c] = JtR.m[i][c] + BR.m[i][c];
+      J[3 + i][c] = T(0);
+      J[3 + i][3 + c] = JR.m[i][c];
+    }
+}
+template <typename T> LM_HD void pgo_linearize(const Elem<T>& A, const Elem<T>& B, const Elem<T>& Z, Tang<T>& r, Sys6<T>& s) {
+  T J[6][6];
+  pgo_jacobian(A, B, Z, r, J);
   sys6_zero(s);
   const T rr[6] = {r.tau.x, r.tau.y, r.tau.z, r.phi.x, r.phi.y, r.phi.z};
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const T top[6] = {JR.m[i][0], JR.m[i][1], JR.m[i][2], JtR.m[i][0] + BR.m[i][0], JtR.m[i][1] + BR.m[i][1],
-                      JtR.m[i][2] + BR.m[i][2]};
-    const T bot[6] = {T(0), T(0), T(0), JR.m[i][0], JR.m[i][1], JR.m[i][2]};
-    sys6_add_row(s, top, rr[i]);
-    sys6_add_row(s, bot, rr[i + 3]);
+  for (int i = 0; i < 6; ++i) sys6_add_row(s, J[i], rr[i]);
+}
+// with a per-edge information matrix W (6x6, row-major): sw.A = J^T W J, sw.g = J^T W r (optimizer.py:654-656 with
+// `weight`), next to the unweighted s0 (the TrustRegion quality uses J and R without the weight, strategy.py:143)
+template <typename T>
+LM_HD void pgo_linearize_w(const Elem<T>& A, const Elem<T>& B, const Elem<T>& Z, const T* W, Tang<T>& r, Sys6<T>& sw, Sys6<T>& s0) {
+  T J[6][6];
+  pgo_jacobian(A, B, Z, r, J);
+  sys6_zero(s0);
+  const T rr[6] = {r.tau.x, r.tau.y, r.tau.z, r.phi.x, r.phi.y, r.phi.z};
+#pragma unroll
+  for (int i = 0; i < 6; ++i) sys6_add_row(s0, J[i], rr[i]);
+  T WJ[6][6], Wr[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    T a = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a += W[i * 6 + k] * rr[k];
+    Wr[i] = a;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      T v = T(0);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v += W[i * 6 + k] * J[k][c];
+      WJ[i][c] = v;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    T g = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g += J[k][a] * Wr[k];
+    sw.g[a] = g;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      T v = T(0);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v += J[k][a] * WJ[k][b];
+      sw.A[a][b] = v;
+    }
   }
 }
 

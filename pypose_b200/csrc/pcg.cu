@@ -329,6 +329,27 @@ __global__ void __launch_bounds__(kLmThreads) pgo_predicted_kernel(const T* __re
   reduce_sums<1>(acc, ws);
 }
 
+// ws[0] = sum_e d^T M0_e d + 2 d^T u0_e, d = D_j - D_i: the same quantity from per-edge blocks (used when M0 / u0 differ
+// from the blocks of the solve, i.e. with information-matrix weights)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pgo_predicted_edge_kernel(const T* __restrict__ M0, const T* __restrict__ u0,
+                                                                         const int* __restrict__ ei, const int* __restrict__ ej,
+                                                                         const T* __restrict__ D, double* ws, long long E) {
+  double acc[1] = {0.0};
+  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
+    const long long i = ei[e], j = ej[e];
+    T d[6], v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = __ldg(D + j * 6 + k) - __ldg(D + i * 6 + k);
+    sym6_mv_packed(M0 + e * 21, d, v);
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s += d[k] * (v[k] + T(2) * u0[e * 6 + k]);
+    acc[0] += (double)s;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
 }  // namespace b200pose
 
 using namespace b200pose;
@@ -374,6 +395,12 @@ using namespace b200pose;
                                               const CT* g, double* ws, long long n, void* stream) {                   \
     if (n <= 0) return 0;                                                                                             \
     LM_LAUNCH(pgo_predicted_kernel<CT>, (E > n ? E : n), stream, M, ei, ej, D, g, ws, E, n);                          \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_predicted_edge_##SFX(const CT* M0, const CT* u0, const int* ei, const int* ej,          \
+                                                   const CT* D, double* ws, long long E, void* stream) {              \
+    if (E <= 0) return 0;                                                                                             \
+    LM_LAUNCH(pgo_predicted_edge_kernel<CT>, E, stream, M0, u0, ei, ej, D, ws, E);                                    \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_schur_diag_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx,           \

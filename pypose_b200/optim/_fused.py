@@ -60,6 +60,9 @@ torch.library.define(f"{NS}::lm_reproj_residual", "(Tensor poses, Tensor pts, Te
 
 torch.library.define(f"{NS}::lm_pgo_linearize",
                      "(Tensor nodes, Tensor Z, Tensor ei, Tensor ej, int robust, float delta) -> (Tensor, Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_pgo_linearize_w",
+                     "(Tensor nodes, Tensor Z, Tensor ei, Tensor ej, Tensor W, int robust, float delta) -> "
+                     "(Tensor, Tensor, Tensor, Tensor, Tensor)")
 torch.library.define(f"{NS}::lm_pgo_scatter", "(Tensor M, Tensor u, Tensor ei, Tensor ej, int n) -> (Tensor, Tensor)")
 torch.library.define(f"{NS}::lm_pgo_spmv", "(Tensor M, Tensor ei, Tensor ej, Tensor x, Tensor y0) -> Tensor")
 torch.library.define(f"{NS}::lm_pgo_loss", "(Tensor nodes, Tensor Z, Tensor ei, Tensor ej, int robust, float delta) -> Tensor")
@@ -74,6 +77,18 @@ def _pgo_linearize(nodes, Z, ei, ej, robust=0, delta=1.0):
     _launch("b200_lm_pgo_linearize", nodes, [_p(nodes), _p(Z), _p(ei), _p(ej), _p(M), _p(u), _p(ws), int(robust),
                                              float(delta)], E)
     return M, u, ws[:1].clone()
+
+
+def _pgo_linearize_w(nodes, Z, ei, ej, W, robust=0, delta=1.0):
+    """W: (E,6,6) or (1,6,6) symmetric information matrices -> weighted (M, u), unweighted (M0, u0), cost."""
+    nodes, Z, W = _same(nodes, Z, W)
+    E = Z.shape[0]
+    ws = _workspace(nodes.device)
+    M, M0 = (torch.empty(E, 21, dtype=nodes.dtype, device=nodes.device) for _ in range(2))
+    u, u0 = (torch.empty(E, 6, dtype=nodes.dtype, device=nodes.device) for _ in range(2))
+    _launch("b200_lm_pgo_linearize_w", nodes, [_p(nodes), _p(Z), _p(ei), _p(ej), _p(W), 36 if W.shape[0] == E and E > 1 else 0,
+                                               _p(M), _p(u), _p(M0), _p(u0), _p(ws), int(robust), float(delta)], E)
+    return M, u, M0, u0, ws[:1].clone()
 
 
 def _pgo_scatter(M, u, ei, ej, n):
@@ -200,6 +215,7 @@ torch.library.impl(f"{NS}::lm_ba_wtx", "CUDA")(_ba_wtx)
 torch.library.impl(f"{NS}::lm_ba_wv", "CUDA")(_ba_wv)
 torch.library.impl(f"{NS}::lm_ba_loss", "CUDA")(_ba_loss)
 torch.library.impl(f"{NS}::lm_pgo_linearize", "CUDA")(_pgo_linearize)
+torch.library.impl(f"{NS}::lm_pgo_linearize_w", "CUDA")(_pgo_linearize_w)
 torch.library.impl(f"{NS}::lm_pgo_scatter", "CUDA")(_pgo_scatter)
 torch.library.impl(f"{NS}::lm_pgo_spmv", "CUDA")(_pgo_spmv)
 torch.library.impl(f"{NS}::lm_pgo_loss", "CUDA")(_pgo_loss)
@@ -225,7 +241,7 @@ def call(name, *args):
 
 _DIRECT = {"lm_poseinv_loss": _poseinv_loss, "lm_poseinv_trial": _poseinv_trial, "lm_reproj_accum": _reproj_accum,
            "lm_solve6_retract": _solve6_retract, "lm_reproj_loss": _reproj_loss, "lm_reproj_residual": _reproj_residual,
-           "lm_pgo_linearize": _pgo_linearize, "lm_pgo_scatter": _pgo_scatter, "lm_pgo_spmv": _pgo_spmv,
+           "lm_pgo_linearize": _pgo_linearize, "lm_pgo_linearize_w": _pgo_linearize_w, "lm_pgo_scatter": _pgo_scatter, "lm_pgo_spmv": _pgo_spmv,
            "lm_pgo_loss": _pgo_loss, "lm_ba_linearize": _ba_linearize, "lm_ba_wtx": _ba_wtx, "lm_ba_wv": _ba_wv,
            "lm_ba_loss": _ba_loss}
 
@@ -250,11 +266,13 @@ def _cg(device):
     return s
 
 
-def _run_chunks(enqueue, cg, maxiter):
-    """enqueue(first_iter, iters) until the device reports done; returns the iteration count."""
+def _run_chunks(enqueue, cg, maxiter, hint=0):
+    """enqueue(first_iter, iters) until the device reports done; returns the iteration count.  `hint` (the iteration
+    count of the previous solve of this problem) sizes the first chunk: consecutive LM trials need about the same
+    number of iterations, so most solves cost exactly one host read."""
     it = 0
     while True:
-        n = max(1, min(CG_CHUNK, maxiter - it))
+        n = max(1, min(hint if (it == 0 and hint > 0) else CG_CHUNK, maxiter - it))
         enqueue(it, n)
         it += n
         st = cg.tolist()                                  # the one host sync per chunk
@@ -262,8 +280,9 @@ def _run_chunks(enqueue, cg, maxiter):
             return int(st[6])
 
 
-def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter):
-    """(H + clamp/damping) x = -g by device PCG.  Returns x (n,6), iterations, predicted (1,) fp64 on device."""
+def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None):
+    """(H + clamp/damping) x = -g by device PCG.  Returns x (n,6), iterations, predicted (1,) fp64 on device.
+    `unweighted` = (M0, u0): per-edge blocks without the information matrices, for the predicted reduction."""
     dev, dt, n, E = M.device, M.dtype, Hd.shape[0], M.shape[0]
     ws, cg = _workspace(dev), _cg(dev)
     extra = torch.empty(n, 6, dtype=dt, device=dev)
@@ -273,12 +292,15 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter):
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
     iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg", M, [
         _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg), _p(ws),
-        float(tol), maxiter, it0, k], n), cg, maxiter)
-    _launch("b200_lm_pgo_predicted", M, [_p(M), _p(ei), _p(ej), E, _p(x), _p(g), _p(ws)], n)
+        float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+    if unweighted is None:
+        _launch("b200_lm_pgo_predicted", M, [_p(M), _p(ei), _p(ej), E, _p(x), _p(g), _p(ws)], n)
+    else:
+        _launch("b200_lm_pgo_predicted_edge", M, [_p(unweighted[0]), _p(unweighted[1]), _p(ei), _p(ej), _p(x), _p(ws)], E)
     return x, iters, ws[:1].clone()
 
 
-def ba_solve(Jc, Jp, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter):
+def ba_solve(Jc, Jp, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
     """Schur-complement solve of the damped BA normal equations by device PCG.
     Returns xc (C,6), xp (P,3), iterations, predicted (1,) fp64 on device."""
     dev, dt = Jc.device, Jc.dtype
@@ -299,7 +321,7 @@ def ba_solve(Jc, Jp, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, m
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * C
     iters = _run_chunks(lambda it0, k: _launch("b200_lm_ba_pcg", Jc, [
         _p(Jc), _p(Jp), _p(cidx), _p(pidx), m, _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
-        _p(t), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter)
+        _p(t), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter, hint)
     t.copy_(gp)                                           # dp = -Hpp^-1 (gp + W^T dc)
     _launch("b200_lm_ba_wtx", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(x), _p(t)], m)
     xp = torch.empty(P, 3, dtype=dt, device=dev)

@@ -187,17 +187,18 @@ class LevenbergMarquardt(_SecondOrder):
 
     # -- structured route ------------------------------------------------------------------------------
     def _structured(self, input, target, weight):
-        if not (self._robust is not None and weight is None and self.weight is None and target is None):
+        weight = self.weight if weight is None else weight
+        if not (self._robust is not None and target is None):
             return None
         from .solver import CG
         if not (isinstance(self.solver, CG) or (isinstance(self.solver, Cholesky) and not self.solver.upper)):
             return None
         if len(self.param_groups) != 1:
             return None
-        if self._problem is not None and self._problem.matches(self.model.model, input):
+        if self._problem is not None and self._problem.matches(self.model.model, input, weight):
             return self._problem
         self._problem = structured.recognize(self.model.model, input, self.param_groups[0]['params'], self.group,
-                                             self._robust, self.solver, self.sparse)
+                                             self._robust, self.solver, self.sparse, weight)
         return self._problem
 
     def _step_structured(self, prob, pg):

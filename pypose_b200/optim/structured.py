@@ -55,8 +55,8 @@ class PoseInvProblem(_Problem):
         self.dtype = param.dtype
         self._trial = None
 
-    def matches(self, model, input):
-        return model is self.model and _input_key(input) == self.key
+    def matches(self, model, input, weight=None):
+        return weight is None and model is self.model and _input_key(input) == self.key
 
     def _rows(self):
         return self.param.tensor().reshape(-1, 7), self.X.tensor().reshape(-1, 7)
@@ -86,8 +86,8 @@ class ReprojProblem(_Problem):
         self.pts, self.pix, self.cidx, self.seg = data
         self._trial = None
 
-    def matches(self, model, input):
-        return model is self.model and _input_key(input) == self.key
+    def matches(self, model, input, weight=None):
+        return weight is None and model is self.model and _input_key(input) == self.key
 
     def _poses(self):
         return self.param.tensor().reshape(-1, 7)
@@ -170,19 +170,23 @@ class PGOProblem(_Problem):
                reference's clamp (optimizer.py:643/657) + cumulative damping (:664/666).
     Edges may be sharded over a process group: Hd, g, every matvec and the scalars are all-reduced."""
 
-    def __init__(self, model, edges, Z, key, group, robust, tol, maxiter, param=None):
+    def __init__(self, model, edges, Z, key, group, robust, tol, maxiter, param=None, weight=None):
         self.model, self.key, self.group, self.robust = model, key, group, robust
+        self.weight_key = None if weight is None else _input_key(weight)
         self.param = model.nodes if param is None else param
         self.dtype = self.param.dtype
         self.ei = edges[..., 0].to(torch.int32).contiguous()
         self.ej = edges[..., 1].to(torch.int32).contiguous()
         self.Z = Z.tensor().to(self.dtype).reshape(-1, 7).contiguous()
+        # information matrices (examples/module/pgo/pgo.py:75 `weight=infos`): (E,6,6) or one (6,6) for all edges
+        self.W = None if weight is None else weight.to(self.dtype).reshape(-1, 36).contiguous()
         self.tol, self.maxiter = tol, maxiter
         self._trial = None
         self.cg_iters = 0
 
-    def matches(self, model, input):
-        return model is self.model and _input_key(input) == self.key
+    def matches(self, model, input, weight=None):
+        return (model is self.model and _input_key(input) == self.key
+                and self.weight_key == (None if weight is None else _input_key(weight)))
 
     def _nodes(self):
         return self.param.tensor().reshape(-1, 7)
@@ -193,24 +197,30 @@ class PGOProblem(_Problem):
 
     def linearize(self):
         nodes = self._nodes()
-        M, u, cur = _fused.call("lm_pgo_linearize", nodes, self.Z, self.ei, self.ej, *self.robust)
+        unw = None
+        if self.W is None:
+            M, u, cur = _fused.call("lm_pgo_linearize", nodes, self.Z, self.ei, self.ej, *self.robust)
+        else:
+            M, u, M0, u0, cur = _fused.call("lm_pgo_linearize_w", nodes, self.Z, self.ei, self.ej, self.W, *self.robust)
+            unw = (M0, u0)
         Hd, g = _fused.call("lm_pgo_scatter", M, u, self.ei, self.ej, nodes.shape[0])
         if self.group is not None:
             packed = torch.cat([Hd.reshape(-1), g.reshape(-1)])
             _allreduce(packed, self.group)
             n = Hd.numel()
             Hd, g = packed[:n].view_as(Hd), packed[n:].view_as(g)
-        return M, Hd, g, cur
+        return M, Hd, g, cur, unw
 
     def _matvec(self, M, extra, x):
         y = _fused.call("lm_pgo_spmv", M, self.ei, self.ej, x, torch.zeros_like(x))
         return _allreduce(y, self.group) + extra * x
 
     def trial(self, lin, scale, dmin, dmax):
-        M, Hd, g, cur = lin
+        M, Hd, g, cur, unw = lin
         if M.is_cuda and self.group is None:          # device-resident PCG: one host read per 8 iterations
             D, self.cg_iters, predicted = _fused.pgo_solve(M, self.ei, self.ej, Hd, g, scale, dmin, dmax, self.tol,
-                                                           self.maxiter)
+                                                           self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0,
+                                                           unweighted=unw)
             return self._finish_trial(D, predicted, cur)
         d = Hd[:, _DIAG21]
         extra = d.clamp(dmin, dmax) * scale - d                       # added to the diagonal of H
@@ -219,9 +229,14 @@ class PGOProblem(_Problem):
         x, it = _pcg(lambda v: self._matvec(M, extra, v), Minv, -g, self.tol, self.maxiter)
         self.cg_iters = it
         D = x
-        Hx = _fused.call("lm_pgo_spmv", M, self.ei, self.ej, D, torch.zeros_like(D))
-        Hx = _allreduce(Hx, self.group)
-        predicted = ((D * Hx).sum() + 2 * (D * g).sum()).to(torch.float64).reshape(1)
+        if unw is None:
+            Hx = _fused.call("lm_pgo_spmv", M, self.ei, self.ej, D, torch.zeros_like(D))
+            Hx = _allreduce(Hx, self.group)
+            predicted = ((D * Hx).sum() + 2 * (D * g).sum()).to(torch.float64).reshape(1)
+        else:     # (J D)^T (2 R + J D) without the weights (strategy.py:143): per-edge sum over this rank's edges
+            d = D[self.ej.long()] - D[self.ei.long()]
+            predicted = ((d * _bmv(_unpack21(unw[0]), d)).sum() + 2 * (d * unw[1]).sum()).to(torch.float64).reshape(1)
+            predicted = _allreduce(predicted, self.group)
         return self._finish_trial(D, predicted, cur)
 
     def _finish_trial(self, D, predicted, cur):
@@ -270,8 +285,8 @@ class BAProblem(_Problem):
         self._trial = None
         self.cg_iters = 0
 
-    def matches(self, model, input):
-        return model is self.model and _input_key(input) == self.key
+    def matches(self, model, input, weight=None):
+        return weight is None and model is self.model and _input_key(input) == self.key
 
     def _params(self):
         return self.poses.tensor().reshape(-1, 7), self.points.reshape(-1, 3)
@@ -298,7 +313,7 @@ class BAProblem(_Problem):
         C, P = Hcc.shape[0], Hpp.shape[0]
         if Jc.is_cuda and self.group is None:         # device-resident Schur PCG
             xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, Hcc, Hpp, gc, gp, scale, dmin,
-                                                          dmax, self.tol, self.maxiter)
+                                                          dmax, self.tol, self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0)
             return self._finish_trial(xc, xp, pred, cur)
         dc, dp = Hcc[:, _DIAG21], Hpp[:, [0, 3, 5]]
         Hc = _unpack21(Hcc) + torch.diag_embed(dc.clamp(dmin, dmax) * scale - dc)
@@ -372,7 +387,7 @@ def _is_index(t, n=None):
     return torch.is_tensor(t) and t.dtype in (torch.int64, torch.int32) and t.dim() == 1 and (n is None or t.shape[0] == n)
 
 
-def _recognize_by_signature(model, input, params, group, robust, solver, sparse):
+def _recognize_by_signature(model, input, params, group, robust, solver, sparse, weight=None):
     """User-written modules (e.g. README.md:163-198 `Reproj`, examples/module/pgo `PoseGraph`) reach a fused family
     when (i) their parameters and inputs have the family's types and shapes and (ii) the output of ONE eager forward
     pass has the family's shape and the same sum of squares as the family's residual kernel on the same data
@@ -397,7 +412,7 @@ def _recognize_by_signature(model, input, params, group, robust, solver, sparse)
         edges, Z = input
         if (torch.is_tensor(edges) and edges.dtype in (torch.int64, torch.int32) and edges.dim() == 2 and edges.shape[1] == 2
                 and isinstance(Z, LieTensor) and Z.ltype is SE3_type and Z.shape == (edges.shape[0], 7)):
-            cand = PGOProblem(model, edges, Z, key, group, (0, 1.0), tol, maxiter, param=params[0])
+            cand = PGOProblem(model, edges, Z, key, group, (0, 1.0), tol, maxiter, param=params[0], weight=weight)
             M, d = edges.shape[0], 6
     elif len(params) == 1 and len(input) == 3 and not isinstance(solver, CG):        # single-pose reprojection
         points, pixels, ci = input
@@ -405,7 +420,7 @@ def _recognize_by_signature(model, input, params, group, robust, solver, sparse)
                 and pixels.shape == (points.shape[0], 2) and _is_index(ci, points.shape[0])):
             cand = ReprojProblem(model, _prepare_reproj(params[0], points, pixels, ci), key, group, (0, 1.0), param=params[0])
             M, d = points.shape[0], 2
-    if cand is None:
+    if cand is None or (weight is not None and not isinstance(cand, PGOProblem)):
         return None
     with torch.no_grad():
         out = model(*input)
@@ -418,9 +433,21 @@ def _recognize_by_signature(model, input, params, group, robust, solver, sparse)
     return cand
 
 
-def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sparse=False):
+def _pgo_weight(weight, input):
+    """`weight` usable by the pose-graph route: one symmetric (6,6) / (1,6,6) or per-edge (E,6,6) tensor."""
+    if not (torch.is_tensor(weight) and isinstance(input, (tuple, list)) and len(input) == 2 and torch.is_tensor(input[0])):
+        return False
+    E = input[0].shape[0]
+    if weight.dim() not in (2, 3) or tuple(weight.shape[-2:]) != (6, 6) or (weight.dim() == 3 and weight.shape[0] not in (1, E)):
+        return False
+    return bool(torch.allclose(weight, weight.mT))
+
+
+def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sparse=False, weight=None):
     """Return a structured problem for (model, input) or None (-> generic dense route)."""
     params = [p for p in params if p.requires_grad]
+    if weight is not None and not _pgo_weight(weight, input):
+        return None
     from ..module.ba import BundleAdjustment
     from .solver import CG
     if isinstance(model, BundleAdjustment):
@@ -432,8 +459,8 @@ def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sp
         pix, cidx, pidx = input
         tol = solver.tol if isinstance(solver, CG) else 1e-8
         maxiter = solver.maxiter if isinstance(solver, CG) else None
-        return BAProblem(model, pix, cidx, pidx, _input_key(input), group, robust, tol, maxiter)
-    duck = _recognize_by_signature(model, input, params, group, robust, solver, sparse)
+        return None if weight is not None else BAProblem(model, pix, cidx, pidx, _input_key(input), group, robust, tol, maxiter)
+    duck = _recognize_by_signature(model, input, params, group, robust, solver, sparse, weight)
     if duck is not None:
         return duck
     if len(params) != 1 or not _is_se3_param(params[0]) or params[0].dtype not in (torch.float32, torch.float64):
@@ -452,8 +479,8 @@ def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sp
             return None
         tol = solver.tol if isinstance(solver, CG) else 1e-8
         maxiter = solver.maxiter if isinstance(solver, CG) else None
-        return PGOProblem(model, edges, Z, _input_key(input), group, robust, tol, maxiter)
-    if solver is not None and isinstance(solver, CG):
+        return PGOProblem(model, edges, Z, _input_key(input), group, robust, tol, maxiter, weight=weight)
+    if weight is not None or (solver is not None and isinstance(solver, CG)):
         return None
     if isinstance(model, PoseReproj):
         if param is not model.poses:

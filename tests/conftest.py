@@ -104,6 +104,10 @@ def _install_cpu_oracle_lm_kernels():
         M, u, c = L.pgo_linearize(n(nodes), n(Z), ei.numpy(), ej.numpy(), robust, delta)
         return t(M, nodes), t(u, nodes), f64(c)
 
+    def pgo_linearize_w(nodes, Z, ei, ej, W, robust, delta):
+        outs = L.pgo_linearize(n(nodes), n(Z), ei.numpy(), ej.numpy(), robust, delta, W=n(W))
+        return (*[t(o, nodes) for o in outs[:4]], f64(outs[4]))
+
     def pgo_scatter(M, u, ei, ej, nn):
         Hd, g = L.pgo_scatter(n(M), n(u), ei.numpy(), ej.numpy(), nn)
         return t(Hd, M), t(g, M)
@@ -130,7 +134,7 @@ def _install_cpu_oracle_lm_kernels():
     for name, fn in (("lm_ba_linearize", ba_linearize), ("lm_ba_wtx", ba_wtx), ("lm_ba_wv", ba_wv), ("lm_ba_loss", ba_loss)):
         torch.library.impl(f"b200pose::{name}", "CPU")(fn)
 
-    for name, fn in (("lm_pgo_linearize", pgo_linearize), ("lm_pgo_scatter", pgo_scatter), ("lm_pgo_spmv", pgo_spmv),
+    for name, fn in (("lm_pgo_linearize", pgo_linearize), ("lm_pgo_linearize_w", pgo_linearize_w), ("lm_pgo_scatter", pgo_scatter), ("lm_pgo_spmv", pgo_spmv),
                      ("lm_pgo_loss", pgo_loss)):
         torch.library.impl(f"b200pose::{name}", "CPU")(fn)
 
