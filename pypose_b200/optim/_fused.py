@@ -14,28 +14,35 @@ NS = "b200pose"
 _ws = {}
 
 
-def _workspace(device):
-    """Per-device fp64 reduction workspace, zeroed once (the kernels re-arm it)."""
+_WS_SLOTS = 4
+
+
+def _workspaces(device):
+    """Per-device fp64 reduction workspaces (_WS_SLOTS, doubles), zeroed once (the kernels re-arm them).  Kernels of one
+    LM trial that the host reads together use different slots, so their totals sit at [k, 0:4] and ONE strided copy
+    brings them to the host."""
     key = (device.type, device.index)
     w = _ws.get(key)
     if w is None:
         n = _C.lib().b200_lm_workspace_doubles
         n.restype = ctypes.c_longlong
-        w = torch.zeros(int(n()), dtype=torch.float64, device=device)
+        w = torch.zeros(_WS_SLOTS, int(n()), dtype=torch.float64, device=device)
         _ws[key] = w
     return w
 
 
+def _workspace(device):
+    return _workspaces(device)[0]
+
+
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    return t.data_ptr() if t is not None else None        # c_void_p argtypes take ints / None
 
 
 def _launch(base, ref: Tensor, args, n):
     if not ref.is_cuda:
         raise _C.B200PoseError(f"{base}: expected CUDA tensors (no CPU path), got {ref.device}")
-    sym = f"{base}_{_C.suffix(ref.dtype)}"
-    with torch.cuda.device(ref.device):
-        _C.check(_C.fn(sym)(*args, n, _C.stream_ptr(ref.device)), sym)
+    _C.enqueue(base + ("_f32" if ref.dtype is torch.float32 else "_" + _C.suffix(ref.dtype)), ref, *args, n)
 
 
 def _same(*ts):
@@ -328,3 +335,25 @@ def ba_solve(Jc, Jp, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, m
     _launch("b200_lm_pt3_apply", Jc, [_p(Hpinv), _p(t), -1.0, _p(xp)], P)
     _launch("b200_lm_ba_predicted", Jc, [_p(Jc), _p(Jp), _p(rs), _p(cidx), _p(pidx), _p(x), _p(xp), _p(ws)], m)
     return x, xp, iters, ws[:1].clone()
+
+
+# ----------------------------------------------------------------------------------------------------
+# Reprojection LM trial with the fewest host operations (the step is host-bound: ~30 us of kernels, see
+# tools/prof_lm_host.py): outputs are caller-owned buffers, the three kernels reduce into three workspace
+# slots and one strided 4x4 copy returns [cur | trial loss | predicted, failed].
+# ----------------------------------------------------------------------------------------------------
+def reproj_linearize(poses, pts, pix, seg, robust, delta, H, g):
+    W = _workspaces(poses.device)
+    _launch("b200_lm_reproj_accum", poses, [poses.data_ptr(), pts.data_ptr(), pix.data_ptr(), seg.data_ptr(), H.data_ptr(),
+                                            g.data_ptr(), W[0].data_ptr(), int(robust), float(delta)], poses.shape[0])
+
+
+def reproj_trial(H, g, poses, pts, pix, seg, scale, dmin, dmax, robust, delta, Pt):
+    """-> (16,) fp64 device tensor: [0] current loss (from reproj_linearize), [4] trial loss, [8] predicted, [9] failed."""
+    W = _workspaces(poses.device)
+    n = poses.shape[0]
+    _launch("b200_lm_solve6_retract", poses, [H.data_ptr(), g.data_ptr(), poses.data_ptr(), Pt.data_ptr(), None, W[2].data_ptr(),
+                                              float(scale), float(dmin), float(dmax)], n)
+    _launch("b200_lm_reproj_loss", poses, [Pt.data_ptr(), pts.data_ptr(), pix.data_ptr(), seg.data_ptr(), W[1].data_ptr(),
+                                           int(robust), float(delta)], n)
+    return W[:, :4].reshape(-1)              # non-contiguous view -> reshape copies (one small kernel)
