@@ -152,6 +152,14 @@ LM_OPS = [
       ("int", "robust", ""), ("double", "delta", "")],
      "modjac + J^T J for the two-parameter reprojection model, README.md:163-198; sparse counterpart "
      "bae.autograd.graph.jacobian, optimizer.py:637-642"),
+    ("b200_lm_ba_linearize_y",
+     [("const REAL*", "poses", "(C,7)"), ("const REAL*", "points", "(P,3)"), ("const REAL*", "pix", "(m,2)"),
+      ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+      ("REAL*", "Y4", "(m,4): camera-frame point y = T p and sqrt(rho') — the PCG kernels rebuild the 2x6 / 2x3 rows from it"),
+      ("REAL*", "rs", "(m,2) (scaled) residual"), ("REAL*", "Hcc", "(C,21) accumulated (zero-initialised by the caller)"),
+      ("REAL*", "Hpp", "(P,6) accumulated"), ("REAL*", "gc", "(C,6) accumulated"), ("REAL*", "gp", "(P,3) accumulated"),
+      ("double*", "ws", "ws[0] = sum rho"), ("int", "robust", ""), ("double", "delta", "")],
+     "as b200_lm_ba_linearize, storing 16 B per observation instead of the 72 B of Jacobian rows"),
     ("b200_lm_ba_wtx",
      [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
       ("const REAL*", "x", "(C,6)"), ("REAL*", "t", "(P,3) t += W^T x (atomics)")],
@@ -204,15 +212,19 @@ LM_OPS = [
       ("const REAL*", "D", "(N,6) step"), ("double*", "ws", "ws[0] = sum_e d^T M0 d + 2 d^T u0, d = D_j - D_i")],
      "TrustRegion 'predicted' reduction from per-edge blocks, optim/strategy.py:143"),
     ("b200_lm_ba_schur_diag",
-     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+     [("const REAL*", "Y4", "(m,4) from b200_lm_ba_linearize_y"), ("const REAL*", "poses", "(C,7) the poses it was linearised at"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
       ("const REAL*", "Hpinv", "(P,6)"), ("REAL*", "Sd", "(C,21) in: damped Hcc; out: minus sum_k W_k Hpp^-1 W_k^T (atomics)")],
      "diagonal blocks of the reduced camera system (preconditioner of the Schur PCG)"),
+    ("b200_lm_ba_wtx_y",
+     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+      ("const REAL*", "x", "(C,6)"), ("REAL*", "t", "(P,3) t += W^T x (atomics)")],
+     "off-diagonal block product, optim/solver.py:319-336 (rows rebuilt from Y4)"),
     ("b200_lm_ba_wv_pinv",
-     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
       ("const REAL*", "Hpinv", "(P,6)"), ("const REAL*", "t", "(P,3)"), ("REAL*", "y", "(C,6) y -= W Hpp^-1 t (warp-aggregated atomics)")],
      "off-diagonal product of the reduced camera system, optim/solver.py:319-336"),
     ("b200_lm_ba_pcg",
-     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
       ("long long", "m", "observations"), ("const REAL*", "Hc", "(C,21) damped camera blocks"), ("const REAL*", "Hpinv", "(P,6)"),
       ("const REAL*", "Minv", "(C,21) preconditioner blocks"), ("const REAL*", "bneg", "(C,6) minus the right-hand side"),
       ("REAL*", "x", "(C,6) solution"), ("REAL*", "r", "(C,6)"), ("REAL*", "z", "(C,6)"), ("REAL*", "p", "(C,6)"), ("REAL*", "q", "(C,6)"),
@@ -221,7 +233,7 @@ LM_OPS = [
       ("long long", "iters", "")],
      "PCG on the Schur complement (Hcc - W Hpp^-1 W^T) dc = rhs; optim/solver.py:312-340"),
     ("b200_lm_ba_predicted",
-     [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const REAL*", "rs", "(m,2)"), ("const int*", "cidx", "(m)"),
+     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const REAL*", "rs", "(m,2)"), ("const int*", "cidx", "(m)"),
       ("const int*", "pidx", "(m)"), ("const REAL*", "xc", "(C,6)"), ("const REAL*", "xp", "(P,3)"),
       ("double*", "ws", "ws[0] = sum (J d)^T (2 r + J d)")],
      "TrustRegion 'predicted' reduction, optim/strategy.py:143"),

@@ -169,7 +169,106 @@ __global__ void __launch_bounds__(kLmThreads) cg_dir_kernel(const T* __restrict_
   }
 }
 
+// dot + update + dir of one iteration in ONE single-CTA launch, for systems small enough that a grid is only latency
+// (bundle adjustment: a few thousand cameras; the three separate kernels cost ~28 us at 1e3 rows, this one ~8 us).
+// Fixed-order block reductions (warp shuffles, then warp 0 over the 32 warp partials): deterministic.
+constexpr int kVecThreads = 1024;
+constexpr long long kVecSmallRows = 4096;
+template <int NS> __device__ __forceinline__ void block_sums(double (&v)[NS], double (*sh)[NS], double (&out)[NS]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sh[warp][k] = v[k];
+  __syncthreads();
+  if (warp == 0) {
+    double t[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      t[k] = sh[lane][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+    }
+    if (lane == 0)
+#pragma unroll
+      for (int k = 0; k < NS; ++k) sh[0][k] = t[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NS; ++k) out[k] = sh[0][k];
+  __syncthreads();
+}
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads) cg_vec_small_kernel(const T* __restrict__ Minv, const T* __restrict__ D, int dmode,
+                                                                    T* __restrict__ x, T* __restrict__ r, T* __restrict__ z,
+                                                                    T* __restrict__ p, T* __restrict__ q, double* cg, int par,
+                                                                    long long n) {
+  __shared__ double sh[kVecThreads / 32][2];
+  if (cg[CG_DONE] != 0.0) return;
+  const double rz_old = cg[par], stop2 = cg[CG_STOP2], it = cg[CG_ITERS] + 1.0, maxit = cg[CG_MAXIT];
+  double a1[2] = {0.0, 0.0}, s1[2];
+  for (long long i = threadIdx.x; i < n; i += kVecThreads)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a1[0] += (double)p[i * 6 + k] * (double)q[i * 6 + k];
+  block_sums<2>(a1, sh, s1);
+  const double pq = s1[0];
+  if (!(pq > 0.0)) {                       // breakdown: stop with the current x
+    if (threadIdx.x == 0) cg[CG_DONE] = 2.0;
+    return;
+  }
+  const T alpha = (T)(rz_old / pq);
+  double a2[2] = {0.0, 0.0}, s2[2];
+  for (long long i = threadIdx.x; i < n; i += kVecThreads) {
+    T pv[6], qv[6], xv[6], rv[6], zv[6];
+    ld6(p, i, pv); ld6(q, i, qv); ld6(x, i, xv); ld6(r, i, rv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { xv[k] += alpha * pv[k]; rv[k] -= alpha * qv[k]; }
+    sym6_mv_packed(Minv + i * 21, rv, zv);
+    st6(x, i, xv); st6(r, i, rv); st6(z, i, zv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a2[0] += (double)rv[k] * (double)zv[k]; a2[1] += (double)rv[k] * (double)rv[k]; }
+  }
+  block_sums<2>(a2, sh, s2);
+  const bool done = !(s2[1] > stop2) || it >= maxit;
+  if (threadIdx.x == 0) {
+    cg[CG_PQ] = pq; cg[par ^ 1] = s2[0]; cg[CG_RR] = s2[1]; cg[CG_ITERS] = it;
+    if (done) cg[CG_DONE] = 1.0;
+  }
+  if (done) return;
+  const T beta = (T)(s2[0] / rz_old);
+  for (long long i = threadIdx.x; i < n; i += kVecThreads) {     // the same thread wrote z[i] above
+    T pv[6], zv[6], qv[6];
+    ld6(p, i, pv); ld6(z, i, zv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pv[k] = zv[k] + beta * pv[k];
+    apply_D(D, dmode, i, pv, qv);
+    st6(p, i, pv); st6(q, i, qv);
+  }
+}
+
 // ---- operators ---------------------------------------------------------------------------------------------------
+// Rows of one observation rebuilt from 16 B: Y4[k] = (y = T_c p, sqrt(rho')) and the camera quaternion (gathered, the
+// observations are grouped by camera so a warp mostly shares it).  jc0/jc1 = d r / d xi_c (2x6), jp0/jp1 = d r / d p (2x3).
+template <typename T> struct ObsRows { T jc0[6], jc1[6], jp0[3], jp1[3]; };
+template <typename T>
+__device__ __forceinline__ void obs_rows(const T* __restrict__ Y4, const T* __restrict__ poses, long long k, long long c,
+                                         ObsRows<T>& R) {
+  const T yx = Y4[k * 4], yy = Y4[k * 4 + 1], yz = Y4[k * 4 + 2], sw = Y4[k * 4 + 3];
+  Elem<T> Tc;
+  Tc.q.v = mk(__ldg(poses + c * 7 + 3), __ldg(poses + c * 7 + 4), __ldg(poses + c * 7 + 5));
+  Tc.q.w = __ldg(poses + c * 7 + 6);
+  const V3<T> y = mk(yx, yy, yz);
+  reproj_rows(y, R.jc0, R.jc1);
+  reproj_point_rows(Tc, y, R.jp0, R.jp1);
+#pragma unroll
+  for (int a = 0; a < 6; ++a) { R.jc0[a] *= sw; R.jc1[a] *= sw; }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { R.jp0[a] *= sw; R.jp1[a] *= sw; }
+}
+
 // pose graph: q += H p edge by edge (lm.cu lm_pgo_spmv_kernel), skipped once the CG has finished
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) pcg_pgo_spmv_kernel(const T* __restrict__ M, const int* __restrict__ ei,
@@ -188,24 +287,26 @@ __global__ void __launch_bounds__(kLmThreads) pcg_pgo_spmv_kernel(const T* __res
 }
 // bundle adjustment: t[j] += Jp^T (Jc x[c])
 template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+__global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
                                                                  const int* __restrict__ cidx, const int* __restrict__ pidx,
                                                                  const T* __restrict__ x, T* __restrict__ t, const double* cg,
                                                                  long long m) {
   if (cg && cg[CG_DONE] != 0.0) return;
   for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
     const long long c = cidx[k], j = pidx[k];
+    ObsRows<T> R;
+    obs_rows(Y4, poses, k, c, R);
     T v0 = T(0), v1 = T(0);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += Jc[k * 12 + a] * xa; v1 += Jc[k * 12 + 6 + a] * xa; }
+    for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += R.jc0[a] * xa; v1 += R.jc1[a] * xa; }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) atomicAdd(t + j * 3 + a, Jp[k * 6 + a] * v0 + Jp[k * 6 + 3 + a] * v1);
+    for (int a = 0; a < 3; ++a) atomicAdd(t + j * 3 + a, R.jp0[a] * v0 + R.jp1[a] * v1);
   }
 }
 // y[c] -= Jc^T Jp Hp^-1 t[j]   (W Hpp^-1 t; the point-block inverse is applied per observation: 9 cached loads
 // instead of a separate (P,3) pass)
 template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pcg_ba_wv_pinv_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+__global__ void __launch_bounds__(kLmThreads) pcg_ba_wv_pinv_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
                                                                      const int* __restrict__ cidx,
                                                                      const int* __restrict__ pidx, const T* __restrict__ Hpinv,
                                                                      const T* __restrict__ t, T* __restrict__ y,
@@ -229,18 +330,20 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wv_pinv_kernel(const T* __r
       T v[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) v[a] = A[a][0] * t0 + A[a][1] * t1 + A[a][2] * t2;
+      ObsRows<T> R;
+      obs_rows(Y4, poses, k, c, R);
       T u0 = T(0), u1 = T(0);
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { u0 += Jp[k * 6 + a] * v[a]; u1 += Jp[k * 6 + 3 + a] * v[a]; }
+      for (int a = 0; a < 3; ++a) { u0 += R.jp0[a] * v[a]; u1 += R.jp1[a] * v[a]; }
 #pragma unroll
-      for (int a = 0; a < 6; ++a) out[a] = -(Jc[k * 12 + a] * u0 + Jc[k * 12 + 6 + a] * u1);
+      for (int a = 0; a < 6; ++a) out[a] = -(R.jc0[a] * u0 + R.jc1[a] * u1);
     }
     seg_atomic_add<T, 6>(y + c * 6, c, out, active);
   }
 }
 // Sd[c] -= (Jc^T Jp) Hp^-1 (Jp^T Jc)   (diagonal blocks of the Schur complement, packed 21; Sd pre-set to damped Hcc)
 template <typename T>
-__global__ void __launch_bounds__(kLmThreads) ba_schur_diag_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+__global__ void __launch_bounds__(kLmThreads) ba_schur_diag_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
                                                                     const int* __restrict__ cidx, const int* __restrict__ pidx,
                                                                     const T* __restrict__ Hpinv, T* __restrict__ Sd,
                                                                     long long m) {
@@ -261,10 +364,12 @@ __global__ void __launch_bounds__(kLmThreads) ba_schur_diag_kernel(const T* __re
       sym3_unpack(h, A);
       // G = Jp Hp^-1 Jp^T (2x2), then T_k = Jc^T G Jc
       T jp[2][3], jc[2][6], B[2][3];
+      ObsRows<T> R;
+      obs_rows(Y4, poses, k, c, R);
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { jp[0][a] = Jp[k * 6 + a]; jp[1][a] = Jp[k * 6 + 3 + a]; }
+      for (int a = 0; a < 3; ++a) { jp[0][a] = R.jp0[a]; jp[1][a] = R.jp1[a]; }
 #pragma unroll
-      for (int a = 0; a < 6; ++a) { jc[0][a] = Jc[k * 12 + a]; jc[1][a] = Jc[k * 12 + 6 + a]; }
+      for (int a = 0; a < 6; ++a) { jc[0][a] = R.jc0[a]; jc[1][a] = R.jc1[a]; }
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -285,18 +390,20 @@ __global__ void __launch_bounds__(kLmThreads) ba_schur_diag_kernel(const T* __re
 }
 // ws[0] = sum_k (J_k d)^T (2 r_k + J_k d) with J_k d = Jc x_c + Jp x_p    (strategy.py:143 'predicted')
 template <typename T>
-__global__ void __launch_bounds__(kLmThreads) ba_predicted_kernel(const T* __restrict__ Jc, const T* __restrict__ Jp,
+__global__ void __launch_bounds__(kLmThreads) ba_predicted_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
                                                                    const T* __restrict__ rs, const int* __restrict__ cidx,
                                                                    const int* __restrict__ pidx, const T* __restrict__ xc,
                                                                    const T* __restrict__ xp, double* ws, long long m) {
   double acc[1] = {0.0};
   for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
     const long long c = cidx[k], j = pidx[k];
+    ObsRows<T> R;
+    obs_rows(Y4, poses, k, c, R);
     T d0 = T(0), d1 = T(0);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { const T v = __ldg(xc + c * 6 + a); d0 += Jc[k * 12 + a] * v; d1 += Jc[k * 12 + 6 + a] * v; }
+    for (int a = 0; a < 6; ++a) { const T v = __ldg(xc + c * 6 + a); d0 += R.jc0[a] * v; d1 += R.jc1[a] * v; }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { const T v = __ldg(xp + j * 3 + a); d0 += Jp[k * 6 + a] * v; d1 += Jp[k * 6 + 3 + a] * v; }
+    for (int a = 0; a < 3; ++a) { const T v = __ldg(xp + j * 3 + a); d0 += R.jp0[a] * v; d1 += R.jp1[a] * v; }
     acc[0] += (double)(d0 * (T(2) * rs[k * 2] + d0) + d1 * (T(2) * rs[k * 2 + 1] + d1));
   }
   reduce_sums<1>(acc, ws);
@@ -385,6 +492,10 @@ using namespace b200pose;
     for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
       const int par = (int)(it & 1);                                                                                  \
       if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, M, ei, ej, p, q, cg, E);                               \
+      if (n <= kVecSmallRows) {                                                                                       \
+        cg_vec_small_kernel<CT><<<1, kVecThreads, 0, (cudaStream_t)stream>>>(Minv, extra, 1, x, r, z, p, q, cg, par, n); \
+        continue;                                                                                                     \
+      }                                                                                                               \
       LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \
       LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);                                \
       LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, 1, p, q, cg, par, n);                                         \
@@ -403,19 +514,25 @@ using namespace b200pose;
     LM_LAUNCH(pgo_predicted_edge_kernel<CT>, E, stream, M0, u0, ei, ej, D, ws, E);                                    \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_schur_diag_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx,           \
+  B200_EXPORT int b200_lm_ba_schur_diag_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,        \
                                               const CT* Hpinv, CT* Sd, long long m, void* stream) {                   \
     if (m <= 0) return 0;                                                                                             \
-    LM_LAUNCH(ba_schur_diag_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, Hpinv, Sd, m);                                 \
+    LM_LAUNCH(ba_schur_diag_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, Sd, m);                              \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_wv_pinv_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx,              \
+  B200_EXPORT int b200_lm_ba_wv_pinv_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,           \
                                            const CT* Hpinv, const CT* t, CT* y, long long m, void* stream) {          \
     if (m <= 0) return 0;                                                                                             \
-    LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, Hpinv, t, y, (const double*)nullptr, m);      \
+    LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, t, y, (const double*)nullptr, m);   \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx, long long m,     \
+  B200_EXPORT int b200_lm_ba_wtx_y_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,             \
+                                         const CT* x, CT* t, long long m, void* stream) {                             \
+    if (m <= 0) return 0;                                                                                             \
+    LM_LAUNCH(pcg_ba_wtx_kernel<CT>, m, stream, Y4, poses, cidx, pidx, x, t, (const double*)nullptr, m);              \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx, long long m,  \
                                        const CT* Hc, const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r,   \
                                        CT* z, CT* p, CT* q, CT* t, double* cg, double* ws, double tol,                \
                                        long long maxiter, long long P, long long first_iter, long long iters,         \
@@ -428,8 +545,12 @@ using namespace b200pose;
       const int par = (int)(it & 1);                                                                                  \
       cudaMemsetAsync(t, 0, sizeof(CT) * 3 * (size_t)P, st);                                                          \
       if (m > 0) {                                                                                                    \
-        LM_LAUNCH(pcg_ba_wtx_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, p, t, cg, m);                                 \
-        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Jc, Jp, cidx, pidx, Hpinv, t, q, cg, m);                      \
+        LM_LAUNCH(pcg_ba_wtx_kernel<CT>, m, stream, Y4, poses, cidx, pidx, p, t, cg, m);                              \
+        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, t, q, cg, m);                   \
+      }                                                                                                               \
+      if (n <= kVecSmallRows) {                                                                                       \
+        cg_vec_small_kernel<CT><<<1, kVecThreads, 0, (cudaStream_t)stream>>>(Minv, Hc, 2, x, r, z, p, q, cg, par, n); \
+        continue;                                                                                                     \
       }                                                                                                               \
       LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \
       LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);                                \
@@ -437,11 +558,11 @@ using namespace b200pose;
     }                                                                                                                 \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_predicted_##SFX(const CT* Jc, const CT* Jp, const CT* rs, const int* cidx,               \
+  B200_EXPORT int b200_lm_ba_predicted_##SFX(const CT* Y4, const CT* poses, const CT* rs, const int* cidx,            \
                                              const int* pidx, const CT* xc, const CT* xp, double* ws, long long m,    \
                                              void* stream) {                                                          \
     if (m <= 0) return 0;                                                                                             \
-    LM_LAUNCH(ba_predicted_kernel<CT>, m, stream, Jc, Jp, rs, cidx, pidx, xc, xp, ws, m);                             \
+    LM_LAUNCH(ba_predicted_kernel<CT>, m, stream, Y4, poses, rs, cidx, pidx, xc, xp, ws, m);                          \
     return (int)cudaGetLastError();                                                                                   \
   }
 

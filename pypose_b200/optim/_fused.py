@@ -142,6 +142,20 @@ def _ba_linearize(poses, points, pix, cidx, pidx, robust=0, delta=1.0):
     return Jc, Jp, rs, Hcc, Hpp, gc, gp, ws[:1].clone()
 
 
+def ba_linearize_y(poses, points, pix, cidx, pidx, robust=0, delta=1.0):
+    """As _ba_linearize, storing Y4 (m,4) = (T p, sqrt(rho')) instead of the Jacobian rows (device PCG route)."""
+    poses, points, pix = _same(poses, points, pix)
+    m, C, P = pix.shape[0], poses.shape[0], points.shape[0]
+    dt, dev = poses.dtype, poses.device
+    ws = _workspace(dev)
+    Y4, rs = torch.empty(m, 4, dtype=dt, device=dev), torch.empty(m, 2, dtype=dt, device=dev)
+    Hcc, Hpp = torch.zeros(C, 21, dtype=dt, device=dev), torch.zeros(P, 6, dtype=dt, device=dev)
+    gc, gp = torch.zeros(C, 6, dtype=dt, device=dev), torch.zeros(P, 3, dtype=dt, device=dev)
+    _launch("b200_lm_ba_linearize_y", poses, [_p(poses), _p(points), _p(pix), _p(cidx), _p(pidx), _p(Y4), _p(rs), _p(Hcc),
+                                              _p(Hpp), _p(gc), _p(gp), _p(ws), int(robust), float(delta)], m)
+    return Y4, rs, Hcc, Hpp, gc, gp, ws[:1].clone()
+
+
 def _ba_wtx(Jc, Jp, cidx, pidx, x, npts):
     t = torch.zeros(npts, 3, dtype=Jc.dtype, device=Jc.device)
     x = x.contiguous()
@@ -307,33 +321,35 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     return x, iters, ws[:1].clone()
 
 
-def ba_solve(Jc, Jp, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
-    """Schur-complement solve of the damped BA normal equations by device PCG.
+def ba_solve(Y4, poses, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
+    """Schur-complement solve of the damped BA normal equations by device PCG; the Jacobian rows are rebuilt from
+    Y4 (ba_linearize_y) and the poses it was linearised at.
     Returns xc (C,6), xp (P,3), iterations, predicted (1,) fp64 on device."""
-    dev, dt = Jc.device, Jc.dtype
-    m, C, P = Jc.shape[0], Hcc.shape[0], Hpp.shape[0]
+    dev, dt = Y4.device, Y4.dtype
+    m, C, P = Y4.shape[0], Hcc.shape[0], Hpp.shape[0]
     ws, cg = _workspace(dev), _cg(dev)
     Hc = torch.empty(C, 21, dtype=dt, device=dev)
     Hpinv = torch.empty(P, 6, dtype=dt, device=dev)
     Minv = torch.empty(C, 21, dtype=dt, device=dev)
-    _launch("b200_lm_blk6_damp_inv", Jc, [_p(Hcc), float(scale), float(dmin), float(dmax), _p(Hc), _p(None), _p(None)], C)
-    _launch("b200_lm_pt3_damp_inv", Jc, [_p(Hpp), float(scale), float(dmin), float(dmax), _p(Hpinv)], P)
+    J = [_p(Y4), _p(poses), _p(cidx), _p(pidx)]
+    _launch("b200_lm_blk6_damp_inv", Y4, [_p(Hcc), float(scale), float(dmin), float(dmax), _p(Hc), _p(None), _p(None)], C)
+    _launch("b200_lm_pt3_damp_inv", Y4, [_p(Hpp), float(scale), float(dmin), float(dmax), _p(Hpinv)], P)
     Sd = Hc.clone()
-    _launch("b200_lm_ba_schur_diag", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(Hpinv), _p(Sd)], m)
-    _launch("b200_lm_blk6_damp_inv", Jc, [_p(Sd), 1.0, -3.0e38, 3.0e38, _p(None), _p(None), _p(Minv)], C)
+    _launch("b200_lm_ba_schur_diag", Y4, [*J, _p(Hpinv), _p(Sd)], m)
+    _launch("b200_lm_blk6_damp_inv", Y4, [_p(Sd), 1.0, -3.0e38, 3.0e38, _p(None), _p(None), _p(Minv)], C)
     bneg = gc.clone()                                     # -(rhs) = gc - W Hpp^-1 gp
-    _launch("b200_lm_ba_wv_pinv", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(Hpinv), _p(gp), _p(bneg)], m)
+    _launch("b200_lm_ba_wv_pinv", Y4, [*J, _p(Hpinv), _p(gp), _p(bneg)], m)
     x, r, z, p, q = (torch.empty(C, 6, dtype=dt, device=dev) for _ in range(5))
     t = torch.empty(P, 3, dtype=dt, device=dev)
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * C
-    iters = _run_chunks(lambda it0, k: _launch("b200_lm_ba_pcg", Jc, [
-        _p(Jc), _p(Jp), _p(cidx), _p(pidx), m, _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
+    iters = _run_chunks(lambda it0, k: _launch("b200_lm_ba_pcg", Y4, [
+        *J, m, _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
         _p(t), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter, hint)
     t.copy_(gp)                                           # dp = -Hpp^-1 (gp + W^T dc)
-    _launch("b200_lm_ba_wtx", Jc, [_p(Jc), _p(Jp), _p(cidx), _p(pidx), _p(x), _p(t)], m)
+    _launch("b200_lm_ba_wtx_y", Y4, [*J, _p(x), _p(t)], m)
     xp = torch.empty(P, 3, dtype=dt, device=dev)
-    _launch("b200_lm_pt3_apply", Jc, [_p(Hpinv), _p(t), -1.0, _p(xp)], P)
-    _launch("b200_lm_ba_predicted", Jc, [_p(Jc), _p(Jp), _p(rs), _p(cidx), _p(pidx), _p(x), _p(xp), _p(ws)], m)
+    _launch("b200_lm_pt3_apply", Y4, [_p(Hpinv), _p(t), -1.0, _p(xp)], P)
+    _launch("b200_lm_ba_predicted", Y4, [*J, _p(rs), _p(x), _p(xp), _p(ws)], m)
     return x, xp, iters, ws[:1].clone()
 
 

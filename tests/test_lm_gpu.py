@@ -420,8 +420,9 @@ def test_pgo_device_pcg_vs_dense_solve(maxiter):
     np.testing.assert_allclose(pred.cpu().numpy()[0], xv @ H @ xv + 2 * xv @ gv, rtol=1e-9)
 
 
+@pytest.mark.parametrize("kind,delta", [(0, 1.0), (1, 0.02)])
 @pytest.mark.parametrize("sort_by_camera", [False, True])
-def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera):
+def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera, kind, delta):
     """b200_lm_ba_pcg & co. against a dense numpy solve of the full damped normal equations; with observations
     grouped by camera the warp-aggregated scatter path runs, otherwise the per-lane fallback."""
     from pypose_b200.optim import _fused as F
@@ -433,12 +434,15 @@ def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera):
         pix, cidx, pidx = pix[o], cidx[o], pidx[o]
     dt = torch.float64
     ci, pi_ = torch.from_numpy(cidx.astype(np.int32)).cuda(), torch.from_numpy(pidx.astype(np.int32)).cuda()
-    Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = ops.lm_ba_linearize(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, 0, 1.0)
-    outs_o = L.ba_linearize(T0, p0, pix, cidx, pidx, 0, 1.0)
+    Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = ops.lm_ba_linearize(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, kind, delta)
+    outs_o = L.ba_linearize(T0, p0, pix, cidx, pidx, kind, delta)
     for a, b in zip((Jc, Jp, rs, Hcc, Hpp, gc, gp), outs_o):
         assert np.abs(a.cpu().numpy() - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
     scale, dmin, dmax = 1.0 + 1e-4, 1e-6, 1e32
-    xc, xp, iters, pred = F.ba_solve(Jc, Jp, rs, ci, pi_, Hcc, Hpp, gc, gp, scale, dmin, dmax, 1e-13, 400)
+    Y4, rs_y, Hcc_y, Hpp_y, gc_y, gp_y, cur_y = F.ba_linearize_y(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, kind, delta)
+    for a, b in ((rs_y, rs), (Hcc_y, Hcc), (Hpp_y, Hpp), (gc_y, gc), (gp_y, gp), (cur_y, cur)):
+        assert (a - b).abs().max().item() <= 1e-9 * max(1.0, b.abs().max().item())
+    xc, xp, iters, pred = F.ba_solve(Y4, cu(T0, dt), rs, ci, pi_, Hcc, Hpp, gc, gp, scale, dmin, dmax, 1e-13, 400)
     m = len(cidx)
     J = np.zeros((2 * m, 6 * C + 3 * P))
     Jcn, Jpn = Jc.cpu().numpy().reshape(m, 2, 6), Jp.cpu().numpy().reshape(m, 2, 3)
