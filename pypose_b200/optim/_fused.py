@@ -349,7 +349,7 @@ def ba_solve(Y4, poses, rs, cidx, pidx, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol
     _launch("b200_lm_ba_wtx_y", Y4, [*J, _p(x), _p(t)], m)
     xp = torch.empty(P, 3, dtype=dt, device=dev)
     _launch("b200_lm_pt3_apply", Y4, [_p(Hpinv), _p(t), -1.0, _p(xp)], P)
-    _launch("b200_lm_ba_predicted", Y4, [*J, _p(rs), _p(x), _p(xp), _p(ws)], m)
+    _launch("b200_lm_ba_predicted", Y4, [_p(Y4), _p(poses), _p(rs), _p(cidx), _p(pidx), _p(x), _p(xp), _p(ws)], m)
     return x, xp, iters, ws[:1].clone()
 
 
