@@ -243,6 +243,8 @@ def run_ours(args):
     a.record()
     for i in range(e2e_steps):
         e2e_step(i)
+    for ev in ev_out:                      # the timed region ends when the last results have reached the host
+        s_c.wait_event(ev)
     b.record()
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks(a.elapsed_time(b), world, dev) / e2e_steps
