@@ -447,6 +447,14 @@ class LieTensor(Tensor):
         return self.ltype.cumprod_(self, dim, left)
 
 
+class _TensorParameter(nn.Parameter):
+    """Plain-tensor parameter created by `pp.Parameter(tensor, sjac=True)`: like the reference's tracked parameter
+    (lt.py:1308-1323) it answers `.tensor()` (used e.g. by tests/optim/test_sparse_lm.py:86 of the reference)."""
+
+    def tensor(self):
+        return Tensor.as_subclass(self, Tensor)
+
+
 class Parameter(LieTensor, nn.Parameter):
     """nn.Parameter that is also a LieTensor (lt.py:1236-1337).
 
@@ -467,7 +475,7 @@ class Parameter(LieTensor, nn.Parameter):
             param.ltype = data.ltype
             param._is_param = True
         else:
-            param = nn.Parameter(data, requires_grad)
+            param = _TensorParameter(data, requires_grad) if sjac else nn.Parameter(data, requires_grad)
         param.sjac = bool(sjac)
         return param
 

@@ -408,6 +408,11 @@ def _prepare_reproj(param, points, pixels, cidx):
     return points[order].to(dt).contiguous(), pixels[order].to(dt).contiguous(), c_sorted.to(torch.int32).contiguous(), seg
 
 
+def _in_range(idx, n):
+    """All indices in [0, n) — the fused kernels gather without bounds checks (one host read, at recognition only)."""
+    return idx.numel() == 0 or bool(((idx >= 0) & (idx < n)).all())
+
+
 def _is_index(t, n=None):
     return torch.is_tensor(t) and t.dtype in (torch.int64, torch.int32) and t.dim() == 1 and (n is None or t.shape[0] == n)
 
@@ -430,19 +435,21 @@ def _recognize_by_signature(model, input, params, group, robust, solver, sparse,
         pts, (obs, ci, pi_) = params[1], input
         if (torch.is_tensor(pts) and not isinstance(pts, LieTensor) and pts.dim() == 2 and pts.shape[1] == 3
                 and torch.is_tensor(obs) and obs.dim() == 2 and obs.shape[1] == 2 and _is_index(ci, obs.shape[0])
-                and _is_index(pi_, obs.shape[0])):
+                and _is_index(pi_, obs.shape[0]) and _in_range(ci, params[0].shape[0]) and _in_range(pi_, pts.shape[0])):
             cand = BAProblem(model, obs, ci, pi_, key, group, (0, 1.0), tol, maxiter, params=(params[0], pts))
             M, d = obs.shape[0], 2
     elif len(params) == 1 and len(input) == 2 and iterative:                         # pose graph
         edges, Z = input
         if (torch.is_tensor(edges) and edges.dtype in (torch.int64, torch.int32) and edges.dim() == 2 and edges.shape[1] == 2
-                and isinstance(Z, LieTensor) and Z.ltype is SE3_type and Z.shape == (edges.shape[0], 7)):
+                and isinstance(Z, LieTensor) and Z.ltype is SE3_type and Z.shape == (edges.shape[0], 7)
+                and _in_range(edges, params[0].shape[0])):
             cand = PGOProblem(model, edges, Z, key, group, (0, 1.0), tol, maxiter, param=params[0], weight=weight)
             M, d = edges.shape[0], 6
     elif len(params) == 1 and len(input) == 3 and not isinstance(solver, CG):        # single-pose reprojection
         points, pixels, ci = input
         if (torch.is_tensor(points) and points.dim() == 2 and points.shape[1] == 3 and torch.is_tensor(pixels)
-                and pixels.shape == (points.shape[0], 2) and _is_index(ci, points.shape[0])):
+                and pixels.shape == (points.shape[0], 2) and _is_index(ci, points.shape[0])
+                and _in_range(ci, params[0].shape[0])):
             cand = ReprojProblem(model, _prepare_reproj(params[0], points, pixels, ci), key, group, (0, 1.0), param=params[0])
             M, d = points.shape[0], 2
     if cand is None or (weight is not None and not isinstance(cand, PGOProblem)):
@@ -482,6 +489,8 @@ def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sp
         if not ok:
             return None
         pix, cidx, pidx = input
+        if not (_in_range(cidx, model.poses.shape[0]) and _in_range(pidx, model.points_3d.shape[0])):
+            raise IndexError("BundleAdjustment: camera / point index out of range")
         tol = solver.tol if isinstance(solver, CG) else 1e-8
         maxiter = solver.maxiter if isinstance(solver, CG) else None
         return None if weight is not None else BAProblem(model, pix, cidx, pidx, _input_key(input), group, robust, tol, maxiter)
@@ -502,6 +511,8 @@ def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sp
         edges, Z = input
         if not isinstance(Z, LieTensor) or Z.ltype is not SE3_type:
             return None
+        if not _in_range(edges, param.shape[0]):
+            raise IndexError("PoseGraph: edge index out of range")
         tol = solver.tol if isinstance(solver, CG) else 1e-8
         maxiter = solver.maxiter if isinstance(solver, CG) else None
         return PGOProblem(model, edges, Z, _input_key(input), group, robust, tol, maxiter, weight=weight)

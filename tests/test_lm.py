@@ -396,3 +396,77 @@ def test_user_written_models_take_the_fused_routes(golden_lm):
     opt = pp.optim.LM(net, strategy=STRATS["trustregion"]())
     opt.step((t("reproj/pts"), t("reproj/pix"), t("reproj/cidx")))
     assert opt._problem is None                 # numeric verification rejected it -> generic dense route
+
+
+# ---- the two scenarios of the reference's tests/optim/test_sparse_lm.py (which needs CUDA + `bae` there), CPU edition
+def _sparse_models():
+    from pypose_b200.autograd.function import psjac
+
+    @psjac
+    def edge_error(node1, node2, relpose):
+        return (relpose.Inv() @ node1.Inv() @ node2).Log().tensor()
+
+    class Identity(nn.Module):
+        def __init__(self, x0):
+            super().__init__()
+            self.x = pp.Parameter(x0, sjac=True)
+
+        def forward(self):
+            return self.x
+
+    class ChainPGO(nn.Module):            # a fixed root node concatenated in front of the optimised ones
+        def __init__(self, root, nodes):
+            super().__init__()
+            self.register_buffer("root", root)
+            self.nodes = pp.Parameter(nodes, sjac=True)
+
+        def forward(self, edges, relposes):
+            nodes = torch.cat((self.root, self.nodes), dim=0)
+            return edge_error(nodes[edges[:, 0]], nodes[edges[:, 1]], relposes)
+
+    return Identity, ChainPGO
+
+
+def run_sparse_lm_scenarios(device):
+    Identity, ChainPGO = _sparse_models()
+    torch.manual_seed(0)
+    dt = torch.float64
+    x_true = torch.randn(8, 1, device=device, dtype=dt)
+    model = Identity(x_true + 0.1 * torch.randn_like(x_true))
+    opt = pp.optim.LM(model, solver=pp.optim.solver.PCG(), strategy=pp.optim.strategy.Constant(damping=1e-6), sparse=True)
+    loss0 = opt.model.loss(input=(), target=x_true).item()
+    for _ in range(6):
+        loss = opt.step(input=(), target=x_true).item()
+    assert loss < loss0
+    torch.testing.assert_close(model.x.tensor(), x_true, rtol=1e-4, atol=1e-4)
+
+    gt = pp.SE3(torch.tensor([[0.0, 0, 0, 0, 0, 0, 1], [1.0, 0, 0, 0, 0, 0, 1], [2.0, 0, 0, 0, 0, 0, 1]], device=device, dtype=dt))
+    edges = torch.tensor([[0, 1], [1, 2]], device=device)
+    rel = gt[edges[:, 0]].Inv() @ gt[edges[:, 1]]
+    init = gt[1:] * pp.randn_SE3(2, sigma=0.1, device=device, dtype=dt)
+    model = ChainPGO(gt[:1], init)
+    opt = pp.optim.LM(model, solver=pp.optim.solver.PCG(), strategy=pp.optim.strategy.Constant(damping=1e-4), sparse=True)
+    loss0 = opt.model.loss(input=(edges, rel), target=None).item()
+    for _ in range(5):
+        loss = opt.step(input=(edges, rel)).item()
+        # edge indices address cat(root, nodes): out of range for the parameter alone, so the fused pose-graph
+        # kernels (which gather without bounds checks) must not be chosen
+        assert opt._problem is None
+        if loss < 1e-5:
+            break
+    assert loss < loss0 and loss < 1e-5
+    torch.testing.assert_close(pp.SE3(model.nodes).translation(), gt[1:].translation(), rtol=1e-4, atol=2e-4)
+
+
+def test_reference_sparse_lm_scenarios_cpu():
+    run_sparse_lm_scenarios(torch.device("cpu"))
+
+
+def test_named_pose_graph_rejects_out_of_range_edges(golden_lm):
+    g = golden_lm
+    net = pp.module.PoseGraph(pp.SE3(torch.from_numpy(g["pgo/nodes0"].copy())))
+    edges = torch.from_numpy(g["pgo/edges"]).clone()
+    edges[0, 1] = 10 ** 6
+    opt = pp.optim.LM(net, solver=pp.optim.solver.PCG(), sparse=True)
+    with pytest.raises(IndexError):
+        opt.step((edges, pp.SE3(torch.from_numpy(g["pgo/Z"].copy()))))

@@ -506,3 +506,9 @@ def test_lm_pgo_information_matrices_reference_trajectory_on_gpu(golden_lm, case
         np.testing.assert_allclose(net.nodes.detach().cpu().numpy(), g[f"pgo_w/{case}/poses"][k],
                                    atol=2e-7 if not (case == "shared" and k >= 3) else 2e-5)   # see docstring / note below
         assert opt.reject_count == g[f"pgo_w/{case}/reject"][k]
+
+
+def test_reference_sparse_lm_scenarios_gpu():
+    """tests/optim/test_sparse_lm.py of the reference (identity model with a target; chain pose graph with a fixed root)."""
+    from tests.test_lm import run_sparse_lm_scenarios
+    run_sparse_lm_scenarios(torch.device("cuda"))
