@@ -303,6 +303,37 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_kernel(const T* __restr
     for (int a = 0; a < 3; ++a) atomicAdd(t + j * 3 + a, R.jp0[a] * v0 + R.jp1[a] * v1);
   }
 }
+// u[j] = alpha * Hp^-1_j (t0[j] + sum_{k in obs(j)} Jp_k^T Jc_k x[c_k])   — W^T x by GATHER: one thread per point walks
+// the point's observations (padj / pptr: observation ids grouped by point), so there are no atomics, no zero-fill of
+// a (P,3) buffer, the result is deterministic, and the 3x3 point-block inverse is applied while the sum is in registers.
+// With t0 = gp, alpha = -1 and x = dc this is the back-substitution dp = -Hpp^-1 (gp + W^T dc).
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_gather_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
+                                                                        const int* __restrict__ cidx, const int* __restrict__ padj,
+                                                                        const int* __restrict__ pptr, const T* __restrict__ Hpinv,
+                                                                        const T* __restrict__ x, const T* __restrict__ t0, T alpha,
+                                                                        T* __restrict__ u, const double* cg, long long P) {
+  if (cg && cg[CG_DONE] != 0.0) return;
+  for (long long j = (long long)blockIdx.x * kLmThreads + threadIdx.x; j < P; j += (long long)gridDim.x * kLmThreads) {
+    T t[3] = {T(0), T(0), T(0)};
+    if (t0) { t[0] = t0[j * 3]; t[1] = t0[j * 3 + 1]; t[2] = t0[j * 3 + 2]; }
+    const int lo = pptr[j], hi = pptr[j + 1];
+    for (int s = lo; s < hi; ++s) {
+      const long long k = padj[s], c = cidx[k];
+      ObsRows<T> R;
+      obs_rows(Y4, poses, k, c, R);
+      T v0 = T(0), v1 = T(0);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += R.jc0[a] * xa; v1 += R.jc1[a] * xa; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) t[a] += R.jp0[a] * v0 + R.jp1[a] * v1;
+    }
+    T A[3][3];
+    sym3_unpack(Hpinv + j * 6, A);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) u[j * 3 + a] = alpha * (A[a][0] * t[0] + A[a][1] * t[1] + A[a][2] * t[2]);
+  }
+}
 // y[c] -= Jc^T Jp Hp^-1 t[j]   (W Hpp^-1 t; the point-block inverse is applied per observation: 9 cached loads
 // instead of a separate (P,3) pass)
 template <typename T>
@@ -321,15 +352,17 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wv_pinv_kernel(const T* __r
     if (active) {
       c = cidx[k];
       const long long j = pidx[k];
-      T A[3][3];
-      T h[6];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) h[a] = __ldg(Hpinv + j * 6 + a);
-      sym3_unpack(h, A);
       const T t0 = __ldg(t + j * 3), t1 = __ldg(t + j * 3 + 1), t2 = __ldg(t + j * 3 + 2);
-      T v[3];
+      T v[3] = {t0, t1, t2};
+      if (Hpinv) {                       // NULL: t already holds Hp^-1 t (pcg_ba_wtx_gather_kernel)
+        T A[3][3];
+        T h[6];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) v[a] = A[a][0] * t0 + A[a][1] * t1 + A[a][2] * t2;
+        for (int a = 0; a < 6; ++a) h[a] = __ldg(Hpinv + j * 6 + a);
+        sym3_unpack(h, A);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) v[a] = A[a][0] * t0 + A[a][1] * t1 + A[a][2] * t2;
+      }
       ObsRows<T> R;
       obs_rows(Y4, poses, k, c, R);
       T u0 = T(0), u1 = T(0);
@@ -526,6 +559,14 @@ using namespace b200pose;
     LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, t, y, (const double*)nullptr, m);   \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
+  B200_EXPORT int b200_lm_ba_wtx_gather_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* padj,        \
+                                              const int* pptr, const CT* Hpinv, const CT* x, const CT* t0,            \
+                                              double alpha, CT* u, long long P, void* stream) {                       \
+    if (P <= 0) return 0;                                                                                             \
+    LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P, stream, Y4, poses, cidx, padj, pptr, Hpinv, x, t0, (CT)alpha, u,       \
+              (const double*)nullptr, P);                                                                             \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_wtx_y_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,             \
                                          const CT* x, CT* t, long long m, void* stream) {                             \
     if (m <= 0) return 0;                                                                                             \
@@ -533,7 +574,7 @@ using namespace b200pose;
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx, long long m,  \
-                                       const CT* Hc, const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r,   \
+                                       const int* padj, const int* pptr, const CT* Hc, const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r,   \
                                        CT* z, CT* p, CT* q, CT* t, double* cg, double* ws, double tol,                \
                                        long long maxiter, long long P, long long first_iter, long long iters,         \
                                        long long n, void* stream) {                                                   \
@@ -543,10 +584,10 @@ using namespace b200pose;
       LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, bneg, (CT)-1, Hc, 2, x, r, p, q, cg, ws, tol, (double)maxiter, n); \
     for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
       const int par = (int)(it & 1);                                                                                  \
-      cudaMemsetAsync(t, 0, sizeof(CT) * 3 * (size_t)P, st);                                                          \
       if (m > 0) {                                                                                                    \
-        LM_LAUNCH(pcg_ba_wtx_kernel<CT>, m, stream, Y4, poses, cidx, pidx, p, t, cg, m);                              \
-        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, t, q, cg, m);                   \
+        LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P, stream, Y4, poses, cidx, padj, pptr, Hpinv, p, (const CT*)nullptr, \
+                  (CT)1, t, cg, P);                                                                                   \
+        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, (const CT*)nullptr, t, q, cg, m);      \
       }                                                                                                               \
       if (n <= kVecSmallRows) {                                                                                       \
         cg_vec_small_kernel<CT><<<1, kVecThreads, 0, (cudaStream_t)stream>>>(Minv, Hc, 2, x, r, z, p, q, cg, par, n); \

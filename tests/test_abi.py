@@ -58,3 +58,24 @@ def test_package_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_fused_launch_sites_pass_as_many_arguments_as_the_abi_declares():
+    """Every `_launch("b200_lm_*", ref, [args...], n)` in optim/_fused.py is checked against the op table (ctypes would
+    only notice a wrong count at call time, on a GPU box)."""
+    import re
+    from pypose_b200._optable import LM_OPS
+    arity = {base: len(args) for base, args, _ in LM_OPS}
+    src = open(os.path.join(ROOT, "pypose_b200", "optim", "_fused.py")).read()
+    seen = 0
+    for m in re.finditer(r'_launch\("(b200_lm_\w+)",\s*\w+,\s*\[(.*?)\],\s*[\w\.\[\]\(\) ]+\)', src, re.S):
+        name, args = m.group(1), m.group(2)
+        depth, n = 0, 1
+        for ch in args:
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            n += ch == "," and depth == 0
+        n += 3 * args.count("*J")          # J = [Y4, poses, cidx, pidx]
+        assert n == arity[name], (name, n, arity[name])
+        seen += 1
+    assert seen >= 30
