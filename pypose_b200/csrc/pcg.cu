@@ -307,6 +307,9 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_kernel(const T* __restr
 // the point's observations (padj / pptr: observation ids grouped by point), so there are no atomics, no zero-fill of
 // a (P,3) buffer, the result is deterministic, and the 3x3 point-block inverse is applied while the sum is in registers.
 // With t0 = gp, alpha = -1 and x = dc this is the back-substitution dp = -Hpp^-1 (gp + W^T dc).
+// LPP lanes cooperate on one point (a point has ~2-20 observations; one thread per point was latency-bound on the
+// dependent padj -> cidx/Y4 -> pose/x gathers: 28 us at 1e6 observations, this form: see DESIGN.md).
+constexpr int kLanesPerPoint = 8;
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_gather_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
                                                                         const int* __restrict__ cidx, const int* __restrict__ padj,
@@ -314,24 +317,37 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_gather_kernel(const T* 
                                                                         const T* __restrict__ x, const T* __restrict__ t0, T alpha,
                                                                         T* __restrict__ u, const double* cg, long long P) {
   if (cg && cg[CG_DONE] != 0.0) return;
-  for (long long j = (long long)blockIdx.x * kLmThreads + threadIdx.x; j < P; j += (long long)gridDim.x * kLmThreads) {
+  constexpr int LPP = kLanesPerPoint, PPB = kLmThreads / LPP;           // points per CTA and sweep
+  const int sub = threadIdx.x % LPP;
+  // warp-uniform trip count (the shuffles below need all 32 lanes): iterate over groups of PPB points
+  const long long groups = (P + PPB - 1) / PPB;
+  for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+    const long long j = g * PPB + threadIdx.x / LPP;
     T t[3] = {T(0), T(0), T(0)};
-    if (t0) { t[0] = t0[j * 3]; t[1] = t0[j * 3 + 1]; t[2] = t0[j * 3 + 2]; }
-    const int lo = pptr[j], hi = pptr[j + 1];
-    for (int s = lo; s < hi; ++s) {
-      const long long k = padj[s], c = cidx[k];
-      ObsRows<T> R;
-      obs_rows(Y4, poses, k, c, R);
-      T v0 = T(0), v1 = T(0);
+    if (j < P) {
+      const int lo = pptr[j], hi = pptr[j + 1];
+      for (int s = lo + sub; s < hi; s += LPP) {
+        const long long k = padj[s], c = cidx[k];
+        ObsRows<T> R;
+        obs_rows(Y4, poses, k, c, R);
+        T v0 = T(0), v1 = T(0);
 #pragma unroll
-      for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += R.jc0[a] * xa; v1 += R.jc1[a] * xa; }
+        for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += R.jc0[a] * xa; v1 += R.jc1[a] * xa; }
 #pragma unroll
-      for (int a = 0; a < 3; ++a) t[a] += R.jp0[a] * v0 + R.jp1[a] * v1;
+        for (int a = 0; a < 3; ++a) t[a] += R.jp0[a] * v0 + R.jp1[a] * v1;
+      }
     }
-    T A[3][3];
-    sym3_unpack(Hpinv + j * 6, A);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) u[j * 3 + a] = alpha * (A[a][0] * t[0] + A[a][1] * t[1] + A[a][2] * t[2]);
+    for (int o = LPP / 2; o > 0; o >>= 1)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) t[a] += __shfl_xor_sync(0xffffffffu, t[a], o);      // stays inside the LPP-lane group
+    if (j < P && sub == 0) {
+      if (t0) { t[0] += t0[j * 3]; t[1] += t0[j * 3 + 1]; t[2] += t0[j * 3 + 2]; }
+      T A[3][3];
+      sym3_unpack(Hpinv + j * 6, A);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) u[j * 3 + a] = alpha * (A[a][0] * t[0] + A[a][1] * t[1] + A[a][2] * t[2]);
+    }
   }
 }
 // y[c] -= Jc^T Jp Hp^-1 t[j]   (W Hpp^-1 t; the point-block inverse is applied per observation: 9 cached loads
@@ -563,8 +579,8 @@ using namespace b200pose;
                                               const int* pptr, const CT* Hpinv, const CT* x, const CT* t0,            \
                                               double alpha, CT* u, long long P, void* stream) {                       \
     if (P <= 0) return 0;                                                                                             \
-    LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P, stream, Y4, poses, cidx, padj, pptr, Hpinv, x, t0, (CT)alpha, u,       \
-              (const double*)nullptr, P);                                                                             \
+    LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4, poses, cidx, padj, pptr, Hpinv, x, t0,    \
+              (CT)alpha, u, (const double*)nullptr, P);                                                                             \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_wtx_y_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,             \
@@ -585,8 +601,8 @@ using namespace b200pose;
     for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
       const int par = (int)(it & 1);                                                                                  \
       if (m > 0) {                                                                                                    \
-        LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P, stream, Y4, poses, cidx, padj, pptr, Hpinv, p, (const CT*)nullptr, \
-                  (CT)1, t, cg, P);                                                                                   \
+        LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4, poses, cidx, padj, pptr, Hpinv, p,    \
+                  (const CT*)nullptr, (CT)1, t, cg, P);                                                                                   \
         LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, (const CT*)nullptr, t, q, cg, m);      \
       }                                                                                                               \
       if (n <= kVecSmallRows) {                                                                                       \
