@@ -216,8 +216,9 @@ LM_OPS = [
       ("const REAL*", "Hpinv", "(P,6)"), ("REAL*", "Sd", "(C,21) in: damped Hcc; out: minus sum_k W_k Hpp^-1 W_k^T (atomics)")],
      "diagonal blocks of the reduced camera system (preconditioner of the Schur PCG)"),
     ("b200_lm_ba_wtx_gather",
-     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"),
-      ("const int*", "padj", "(m) observation ids grouped by point"), ("const int*", "pptr", "(P+1) offsets into padj"),
+     [("const REAL*", "Y4p", "(m,4) Y4 reordered so that each point's observations are contiguous"),
+      ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx_p", "(m) camera index in the same order"),
+      ("const int*", "pptr", "(P+1) offsets per point"),
       ("const REAL*", "Hpinv", "(P,6)"), ("const REAL*", "x", "(C,6)"), ("const REAL*", "t0", "(P,3) or NULL"),
       ("double", "alpha", ""), ("REAL*", "u", "(P,3) alpha * Hpp^-1 (t0 + W^T x), no atomics")],
      "W^T x of the Schur PCG by gather + the point-block solve; with t0 = gp, alpha = -1 the back-substitution "
@@ -232,8 +233,8 @@ LM_OPS = [
      "off-diagonal product of the reduced camera system, optim/solver.py:319-336"),
     ("b200_lm_ba_pcg",
      [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
-      ("long long", "m", "observations"), ("const int*", "padj", "(m) observation ids grouped by point"),
-      ("const int*", "pptr", "(P+1)"), ("const REAL*", "Hc", "(C,21) damped camera blocks"), ("const REAL*", "Hpinv", "(P,6)"),
+      ("long long", "m", "observations"), ("const REAL*", "Y4p", "(m,4) point-ordered copy of Y4"),
+      ("const int*", "cidx_p", "(m) point-ordered camera indices"), ("const int*", "pptr", "(P+1)"), ("const REAL*", "Hc", "(C,21) damped camera blocks"), ("const REAL*", "Hpinv", "(P,6)"),
       ("const REAL*", "Minv", "(C,21) preconditioner blocks"), ("const REAL*", "bneg", "(C,6) minus the right-hand side"),
       ("REAL*", "x", "(C,6) solution"), ("REAL*", "r", "(C,6)"), ("REAL*", "z", "(C,6)"), ("REAL*", "p", "(C,6)"), ("REAL*", "q", "(C,6)"),
       ("REAL*", "t", "(P,3) work"), ("double*", "cg", "(8) state, see b200_lm_pgo_pcg"), ("double*", "ws", "reduction workspace"),

@@ -10,6 +10,7 @@
 //   update  alpha = rz/pq; x += alpha p; r -= alpha q; z = Minv r; rz' = r.z; rr = r.r; converged / maxiter -> done
 //   dir     beta = rz'/rz; p = z + beta p; q = D p          (D: the block-diagonal part of the operator)
 // Reductions are the deterministic last-block fp64 folds of lm_common.cuh.
+#include <stdlib.h>
 #include "lm_common.cuh"
 
 namespace b200pose {
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kLmThreads) cg_dir_kernel(const T* __restrict_
 // Fixed-order block reductions (warp shuffles, then warp 0 over the 32 warp partials): deterministic.
 constexpr int kVecThreads = 1024;
 constexpr long long kVecSmallRows = 4096;
-template <int NS> __device__ __forceinline__ void block_sums(double (&v)[NS], double (*sh)[NS], double (&out)[NS]) {
+template <int NS, int THREADS> __device__ __forceinline__ void block_sums(double (&v)[NS], double (*sh)[NS], double (&out)[NS]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NS; ++k)
@@ -188,7 +189,7 @@ template <int NS> __device__ __forceinline__ void block_sums(double (&v)[NS], do
     double t[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-      t[k] = sh[lane][k];
+      t[k] = lane < THREADS / 32 ? sh[lane][k] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
     }
@@ -201,19 +202,19 @@ template <int NS> __device__ __forceinline__ void block_sums(double (&v)[NS], do
   for (int k = 0; k < NS; ++k) out[k] = sh[0][k];
   __syncthreads();
 }
-template <typename T>
-__global__ void __launch_bounds__(kVecThreads) cg_vec_small_kernel(const T* __restrict__ Minv, const T* __restrict__ D, int dmode,
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) cg_vec_small_kernel(const T* __restrict__ Minv, const T* __restrict__ D, int dmode,
                                                                     T* __restrict__ x, T* __restrict__ r, T* __restrict__ z,
                                                                     T* __restrict__ p, T* __restrict__ q, double* cg, int par,
                                                                     long long n) {
-  __shared__ double sh[kVecThreads / 32][2];
+  __shared__ double sh[32][2];
   if (cg[CG_DONE] != 0.0) return;
   const double rz_old = cg[par], stop2 = cg[CG_STOP2], it = cg[CG_ITERS] + 1.0, maxit = cg[CG_MAXIT];
   double a1[2] = {0.0, 0.0}, s1[2];
-  for (long long i = threadIdx.x; i < n; i += kVecThreads)
+  for (long long i = threadIdx.x; i < n; i += THREADS)
 #pragma unroll
     for (int k = 0; k < 6; ++k) a1[0] += (double)p[i * 6 + k] * (double)q[i * 6 + k];
-  block_sums<2>(a1, sh, s1);
+  block_sums<2, THREADS>(a1, sh, s1);
   const double pq = s1[0];
   if (!(pq > 0.0)) {                       // breakdown: stop with the current x
     if (threadIdx.x == 0) cg[CG_DONE] = 2.0;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_vec_small_kernel(const T* __re
   }
   const T alpha = (T)(rz_old / pq);
   double a2[2] = {0.0, 0.0}, s2[2];
-  for (long long i = threadIdx.x; i < n; i += kVecThreads) {
+  for (long long i = threadIdx.x; i < n; i += THREADS) {
     T pv[6], qv[6], xv[6], rv[6], zv[6];
     ld6(p, i, pv); ld6(q, i, qv); ld6(x, i, xv); ld6(r, i, rv);
 #pragma unroll
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_vec_small_kernel(const T* __re
 #pragma unroll
     for (int k = 0; k < 6; ++k) { a2[0] += (double)rv[k] * (double)zv[k]; a2[1] += (double)rv[k] * (double)rv[k]; }
   }
-  block_sums<2>(a2, sh, s2);
+  block_sums<2, THREADS>(a2, sh, s2);
   const bool done = !(s2[1] > stop2) || it >= maxit;
   if (threadIdx.x == 0) {
     cg[CG_PQ] = pq; cg[par ^ 1] = s2[0]; cg[CG_RR] = s2[1]; cg[CG_ITERS] = it;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kVecThreads) cg_vec_small_kernel(const T* __re
   }
   if (done) return;
   const T beta = (T)(s2[0] / rz_old);
-  for (long long i = threadIdx.x; i < n; i += kVecThreads) {     // the same thread wrote z[i] above
+  for (long long i = threadIdx.x; i < n; i += THREADS) {     // the same thread wrote z[i] above
     T pv[6], zv[6], qv[6];
     ld6(p, i, pv); ld6(z, i, zv);
 #pragma unroll
@@ -247,6 +248,16 @@ __global__ void __launch_bounds__(kVecThreads) cg_vec_small_kernel(const T* __re
     apply_D(D, dmode, i, pv, qv);
     st6(p, i, pv); st6(q, i, qv);
   }
+}
+
+template <typename T>
+static void launch_cg_vec_small(const T* Minv, const T* D, int dmode, T* x, T* r, T* z, T* p, T* q, double* cg, int par,
+                                long long n, cudaStream_t st) {
+  static const int env = getenv("B200POSE_CG_VEC_THREADS") ? atoi(getenv("B200POSE_CG_VEC_THREADS")) : 0;
+  const int th = env ? env : (n <= 256 ? 256 : (n <= 512 ? 512 : 1024));
+  if (th == 256) cg_vec_small_kernel<T, 256><<<1, 256, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
+  else if (th == 512) cg_vec_small_kernel<T, 512><<<1, 512, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
+  else cg_vec_small_kernel<T, 1024><<<1, 1024, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
 }
 
 // ---- operators ---------------------------------------------------------------------------------------------------
@@ -303,16 +314,16 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_kernel(const T* __restr
     for (int a = 0; a < 3; ++a) atomicAdd(t + j * 3 + a, R.jp0[a] * v0 + R.jp1[a] * v1);
   }
 }
-// u[j] = alpha * Hp^-1_j (t0[j] + sum_{k in obs(j)} Jp_k^T Jc_k x[c_k])   — W^T x by GATHER: one thread per point walks
-// the point's observations (padj / pptr: observation ids grouped by point), so there are no atomics, no zero-fill of
+// u[j] = alpha * Hp^-1_j (t0[j] + sum_{k in obs(j)} Jp_k^T Jc_k x[c_k])   — W^T x by GATHER over a point-ordered copy
+// of the per-observation data (Y4p, cidx_p; pptr = offsets per point), so there are no atomics, no zero-fill of
 // a (P,3) buffer, the result is deterministic, and the 3x3 point-block inverse is applied while the sum is in registers.
 // With t0 = gp, alpha = -1 and x = dc this is the back-substitution dp = -Hpp^-1 (gp + W^T dc).
 // LPP lanes cooperate on one point (a point has ~2-20 observations; one thread per point was latency-bound on the
 // dependent padj -> cidx/Y4 -> pose/x gathers: 28 us at 1e6 observations, this form: see DESIGN.md).
 constexpr int kLanesPerPoint = 8;
 template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_gather_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
-                                                                        const int* __restrict__ cidx, const int* __restrict__ padj,
+__global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_gather_kernel(const T* __restrict__ Y4p, const T* __restrict__ poses,
+                                                                        const int* __restrict__ cidx_p,
                                                                         const int* __restrict__ pptr, const T* __restrict__ Hpinv,
                                                                         const T* __restrict__ x, const T* __restrict__ t0, T alpha,
                                                                         T* __restrict__ u, const double* cg, long long P) {
@@ -326,10 +337,10 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_gather_kernel(const T* 
     T t[3] = {T(0), T(0), T(0)};
     if (j < P) {
       const int lo = pptr[j], hi = pptr[j + 1];
-      for (int s = lo + sub; s < hi; s += LPP) {
-        const long long k = padj[s], c = cidx[k];
+      for (int s = lo + sub; s < hi; s += LPP) {        // Y4p / cidx_p are stored in point order: coalesced
+        const long long c = cidx_p[s];
         ObsRows<T> R;
-        obs_rows(Y4, poses, k, c, R);
+        obs_rows(Y4p, poses, s, c, R);
         T v0 = T(0), v1 = T(0);
 #pragma unroll
         for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += R.jc0[a] * xa; v1 += R.jc1[a] * xa; }
@@ -542,7 +553,7 @@ using namespace b200pose;
       const int par = (int)(it & 1);                                                                                  \
       if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, M, ei, ej, p, q, cg, E);                               \
       if (n <= kVecSmallRows) {                                                                                       \
-        cg_vec_small_kernel<CT><<<1, kVecThreads, 0, (cudaStream_t)stream>>>(Minv, extra, 1, x, r, z, p, q, cg, par, n); \
+        launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, cg, par, n, (cudaStream_t)stream);                      \
         continue;                                                                                                     \
       }                                                                                                               \
       LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \
@@ -575,11 +586,11 @@ using namespace b200pose;
     LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, t, y, (const double*)nullptr, m);   \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_wtx_gather_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* padj,        \
-                                              const int* pptr, const CT* Hpinv, const CT* x, const CT* t0,            \
-                                              double alpha, CT* u, long long P, void* stream) {                       \
+  B200_EXPORT int b200_lm_ba_wtx_gather_##SFX(const CT* Y4p, const CT* poses, const int* cidx_p, const int* pptr,     \
+                                              const CT* Hpinv, const CT* x, const CT* t0, double alpha, CT* u,        \
+                                              long long P, void* stream) {                                            \
     if (P <= 0) return 0;                                                                                             \
-    LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4, poses, cidx, padj, pptr, Hpinv, x, t0,    \
+    LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4p, poses, cidx_p, pptr, Hpinv, x, t0,       \
               (CT)alpha, u, (const double*)nullptr, P);                                                                             \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
@@ -590,7 +601,8 @@ using namespace b200pose;
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx, long long m,  \
-                                       const int* padj, const int* pptr, const CT* Hc, const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r,   \
+                                       const CT* Y4p, const int* cidx_p, const int* pptr, const CT* Hc,             \
+                                       const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r,   \
                                        CT* z, CT* p, CT* q, CT* t, double* cg, double* ws, double tol,                \
                                        long long maxiter, long long P, long long first_iter, long long iters,         \
                                        long long n, void* stream) {                                                   \
@@ -601,12 +613,12 @@ using namespace b200pose;
     for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
       const int par = (int)(it & 1);                                                                                  \
       if (m > 0) {                                                                                                    \
-        LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4, poses, cidx, padj, pptr, Hpinv, p,    \
+        LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4p, poses, cidx_p, pptr, Hpinv, p,       \
                   (const CT*)nullptr, (CT)1, t, cg, P);                                                                                   \
         LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, (const CT*)nullptr, t, q, cg, m);      \
       }                                                                                                               \
       if (n <= kVecSmallRows) {                                                                                       \
-        cg_vec_small_kernel<CT><<<1, kVecThreads, 0, (cudaStream_t)stream>>>(Minv, Hc, 2, x, r, z, p, q, cg, par, n); \
+        launch_cg_vec_small<CT>(Minv, Hc, 2, x, r, z, p, q, cg, par, n, (cudaStream_t)stream);                         \
         continue;                                                                                                     \
       }                                                                                                               \
       LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \

@@ -321,7 +321,7 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     return x, iters, ws[:1].clone()
 
 
-def ba_solve(Y4, poses, rs, cidx, pidx, padj, pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
+def ba_solve(Y4, poses, rs, cidx, pidx, padj, cidx_p, pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
     """Schur-complement solve of the damped BA normal equations by device PCG; the Jacobian rows are rebuilt from
     Y4 (ba_linearize_y) and the poses it was linearised at.
     Returns xc (C,6), xp (P,3), iterations, predicted (1,) fp64 on device."""
@@ -332,6 +332,7 @@ def ba_solve(Y4, poses, rs, cidx, pidx, padj, pptr, Hcc, Hpp, gc, gp, scale, dmi
     Hpinv = torch.empty(P, 6, dtype=dt, device=dev)
     Minv = torch.empty(C, 21, dtype=dt, device=dev)
     J = [_p(Y4), _p(poses), _p(cidx), _p(pidx)]
+    Y4p = Y4.index_select(0, padj)                        # point-ordered copy for the gather side (once per linearisation)
     _launch("b200_lm_blk6_damp_inv", Y4, [_p(Hcc), float(scale), float(dmin), float(dmax), _p(Hc), _p(None), _p(None)], C)
     _launch("b200_lm_pt3_damp_inv", Y4, [_p(Hpp), float(scale), float(dmin), float(dmax), _p(Hpinv)], P)
     Sd = Hc.clone()
@@ -343,11 +344,10 @@ def ba_solve(Y4, poses, rs, cidx, pidx, padj, pptr, Hcc, Hpp, gc, gp, scale, dmi
     t = torch.empty(P, 3, dtype=dt, device=dev)
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * C
     iters = _run_chunks(lambda it0, k: _launch("b200_lm_ba_pcg", Y4, [
-        *J, m, _p(padj), _p(pptr), _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
+        *J, m, _p(Y4p), _p(cidx_p), _p(pptr), _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
         _p(t), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter, hint)
     xp = torch.empty(P, 3, dtype=dt, device=dev)          # dp = -Hpp^-1 (gp + W^T dc)
-    _launch("b200_lm_ba_wtx_gather", Y4, [_p(Y4), _p(poses), _p(cidx), _p(padj), _p(pptr), _p(Hpinv), _p(x), _p(gp), -1.0,
-                                          _p(xp)], P)
+    _launch("b200_lm_ba_wtx_gather", Y4, [_p(Y4p), _p(poses), _p(cidx_p), _p(pptr), _p(Hpinv), _p(x), _p(gp), -1.0, _p(xp)], P)
     _launch("b200_lm_ba_predicted", Y4, [_p(Y4), _p(poses), _p(rs), _p(cidx), _p(pidx), _p(x), _p(xp), _p(ws)], m)
     return x, xp, iters, ws[:1].clone()
 

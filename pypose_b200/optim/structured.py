@@ -305,7 +305,8 @@ class BAProblem(_Problem):
         self.cl, self.pl = cidx.long(), pidx.long()
         # observation ids grouped by point (CSR): W^T x of the device PCG gathers along it instead of scatter-adding
         P = self.points.reshape(-1, 3).shape[0]
-        self.padj = torch.sort(self.pl, stable=True)[1].to(torch.int32).contiguous()
+        self.padj = torch.sort(self.pl, stable=True)[1].contiguous()
+        self.cidx_p = self.cidx[self.padj].contiguous()
         self.pptr = torch.zeros(P + 1, dtype=torch.int32, device=self.pl.device)
         self.pptr[1:] = torch.cumsum(torch.bincount(self.pl, minlength=P), 0).to(torch.int32)
         self.tol, self.maxiter = tol, maxiter
@@ -342,7 +343,7 @@ class BAProblem(_Problem):
         Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = lin
         C, P = Hcc.shape[0], Hpp.shape[0]
         if Jc.is_cuda and self.group is None:         # device-resident Schur PCG; (Jc, Jp) are (Y4, poses) here
-            xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, self.padj, self.pptr, Hcc, Hpp,
+            xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, self.padj, self.cidx_p, self.pptr, Hcc, Hpp,
                                                           gc, gp, scale, dmin,
                                                           dmax, self.tol, self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0)
             return self._finish_trial(xc, xp, pred, cur)
