@@ -156,6 +156,8 @@ LM_OPS = [
      [("const REAL*", "poses", "(C,7)"), ("const REAL*", "points", "(P,3)"), ("const REAL*", "pix", "(m,2)"),
       ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
       ("REAL*", "Y4", "(m,4): camera-frame point y = T p and sqrt(rho') — the PCG kernels rebuild the 2x6 / 2x3 rows from it"),
+      ("const int*", "ppos", "(m) position of each observation in point order, or NULL"),
+      ("REAL*", "Y4p", "(m,4) the same rows in point order (for b200_lm_ba_wtx_gather), or NULL"),
       ("REAL*", "rs", "(m,2) (scaled) residual"), ("REAL*", "Hcc", "(C,21) accumulated (zero-initialised by the caller)"),
       ("REAL*", "Hpp", "(P,6) accumulated"), ("REAL*", "gc", "(C,6) accumulated"), ("REAL*", "gp", "(P,3) accumulated"),
       ("double*", "ws", "ws[0] = sum rho"), ("int", "robust", ""), ("double", "delta", "")],

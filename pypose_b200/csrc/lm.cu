@@ -382,9 +382,9 @@ __global__ void __launch_bounds__(kLmThreads) lm_pgo_loss_kernel(const T* __rest
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_ba_linearize_kernel(
     const T* __restrict__ poses, const T* __restrict__ points, const T* __restrict__ pix, const int* __restrict__ cidx,
-    const int* __restrict__ pidx, T* __restrict__ Jc, T* __restrict__ Jp, T* __restrict__ Y4, T* __restrict__ rs,
-    T* __restrict__ Hcc, T* __restrict__ Hpp, T* __restrict__ gc, T* __restrict__ gp, double* ws, int rk, T rdelta,
-    long long m) {
+    const int* __restrict__ pidx, T* __restrict__ Jc, T* __restrict__ Jp, T* __restrict__ Y4, const int* __restrict__ ppos,
+    T* __restrict__ Y4p, T* __restrict__ rs, T* __restrict__ Hcc, T* __restrict__ Hpp, T* __restrict__ gc,
+    T* __restrict__ gp, double* ws, int rk, T rdelta, long long m) {
   double acc[1] = {0.0};
   const int lane = threadIdx.x & 31;
   // warp-uniform trip count: the camera-side sums are combined across the warp before the atomics (seg_atomic_add)
@@ -427,6 +427,10 @@ __global__ void __launch_bounds__(kLmThreads) lm_ba_linearize_kernel(
         for (int a = 0; a < 3; ++a) { Jp[k * 6 + a] = p0[a]; Jp[k * 6 + 3 + a] = p1[a]; }
       }
       if (Y4) { Y4[k * 4] = y.x; Y4[k * 4 + 1] = y.y; Y4[k * 4 + 2] = y.z; Y4[k * 4 + 3] = sw; }
+      if (Y4p) {                          // the same 16 B at the observation's position in point order
+        const long long s = ppos[k];
+        Y4p[s * 4] = y.x; Y4p[s * 4 + 1] = y.y; Y4p[s * 4 + 2] = y.z; Y4p[s * 4 + 3] = sw;
+      }
       rs[k * 2] = rx; rs[k * 2 + 1] = ry;
       int q = 0;
 #pragma unroll
@@ -613,16 +617,18 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
                                              void* stream) {                                                          \
     if (m <= 0) return 0;                                                                                             \
     lm_ba_linearize_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                      \
-        poses, points, pix, cidx, pidx, Jc, Jp, (CT*)nullptr, rs, Hcc, Hpp, gc, gp, ws, robust, (CT)delta, m);        \
+        poses, points, pix, cidx, pidx, Jc, Jp, (CT*)nullptr, (const int*)nullptr, (CT*)nullptr, rs, Hcc, Hpp, gc,    \
+        gp, ws, robust, (CT)delta, m);                                                                                \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_linearize_y_##SFX(const CT* poses, const CT* points, const CT* pix, const int* cidx,     \
-                                               const int* pidx, CT* Y4, CT* rs, CT* Hcc, CT* Hpp, CT* gc, CT* gp,     \
-                                               double* ws, int robust, double delta, long long m, void* stream) {     \
+                                               const int* pidx, CT* Y4, const int* ppos, CT* Y4p, CT* rs, CT* Hcc,    \
+                                               CT* Hpp, CT* gc, CT* gp, double* ws, int robust, double delta,         \
+                                               long long m, void* stream) {                                           \
     if (m <= 0) return 0;                                                                                             \
     lm_ba_linearize_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                      \
-        poses, points, pix, cidx, pidx, (CT*)nullptr, (CT*)nullptr, Y4, rs, Hcc, Hpp, gc, gp, ws, robust, (CT)delta,  \
-        m);                                                                                                           \
+        poses, points, pix, cidx, pidx, (CT*)nullptr, (CT*)nullptr, Y4, ppos, Y4p, rs, Hcc, Hpp, gc, gp, ws, robust,  \
+        (CT)delta, m);                                                                                                \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_wtx_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx, const CT* x,     \

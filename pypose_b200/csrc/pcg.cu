@@ -254,7 +254,7 @@ template <typename T>
 static void launch_cg_vec_small(const T* Minv, const T* D, int dmode, T* x, T* r, T* z, T* p, T* q, double* cg, int par,
                                 long long n, cudaStream_t st) {
   static const int env = getenv("B200POSE_CG_VEC_THREADS") ? atoi(getenv("B200POSE_CG_VEC_THREADS")) : 0;
-  const int th = env ? env : (n <= 256 ? 256 : (n <= 512 ? 512 : 1024));
+  const int th = env ? env : (n <= 2048 ? 256 : (n <= 3072 ? 512 : 1024));     // measured: 256 beats 1024 at 1e3 rows
   if (th == 256) cg_vec_small_kernel<T, 256><<<1, 256, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
   else if (th == 512) cg_vec_small_kernel<T, 512><<<1, 512, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
   else cg_vec_small_kernel<T, 1024><<<1, 1024, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);

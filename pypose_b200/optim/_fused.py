@@ -142,18 +142,20 @@ def _ba_linearize(poses, points, pix, cidx, pidx, robust=0, delta=1.0):
     return Jc, Jp, rs, Hcc, Hpp, gc, gp, ws[:1].clone()
 
 
-def ba_linearize_y(poses, points, pix, cidx, pidx, robust=0, delta=1.0):
-    """As _ba_linearize, storing Y4 (m,4) = (T p, sqrt(rho')) instead of the Jacobian rows (device PCG route)."""
+def ba_linearize_y(poses, points, pix, cidx, pidx, robust=0, delta=1.0, ppos=None):
+    """As _ba_linearize, storing Y4 (m,4) = (T p, sqrt(rho')) instead of the Jacobian rows (device PCG route); with
+    `ppos` (position of each observation in point order) also the point-ordered copy Y4p."""
     poses, points, pix = _same(poses, points, pix)
     m, C, P = pix.shape[0], poses.shape[0], points.shape[0]
     dt, dev = poses.dtype, poses.device
     ws = _workspace(dev)
     Y4, rs = torch.empty(m, 4, dtype=dt, device=dev), torch.empty(m, 2, dtype=dt, device=dev)
+    Y4p = torch.empty(m, 4, dtype=dt, device=dev) if ppos is not None else None
     Hcc, Hpp = torch.zeros(C, 21, dtype=dt, device=dev), torch.zeros(P, 6, dtype=dt, device=dev)
     gc, gp = torch.zeros(C, 6, dtype=dt, device=dev), torch.zeros(P, 3, dtype=dt, device=dev)
-    _launch("b200_lm_ba_linearize_y", poses, [_p(poses), _p(points), _p(pix), _p(cidx), _p(pidx), _p(Y4), _p(rs), _p(Hcc),
-                                              _p(Hpp), _p(gc), _p(gp), _p(ws), int(robust), float(delta)], m)
-    return Y4, rs, Hcc, Hpp, gc, gp, ws[:1].clone()
+    _launch("b200_lm_ba_linearize_y", poses, [_p(poses), _p(points), _p(pix), _p(cidx), _p(pidx), _p(Y4), _p(ppos), _p(Y4p),
+                                              _p(rs), _p(Hcc), _p(Hpp), _p(gc), _p(gp), _p(ws), int(robust), float(delta)], m)
+    return (Y4, Y4p), rs, Hcc, Hpp, gc, gp, ws[:1].clone()
 
 
 def _ba_wtx(Jc, Jp, cidx, pidx, x, npts):
@@ -321,10 +323,11 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     return x, iters, ws[:1].clone()
 
 
-def ba_solve(Y4, poses, rs, cidx, pidx, padj, cidx_p, pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
+def ba_solve(Y4s, poses, rs, cidx, pidx, cidx_p, pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
     """Schur-complement solve of the damped BA normal equations by device PCG; the Jacobian rows are rebuilt from
     Y4 (ba_linearize_y) and the poses it was linearised at.
     Returns xc (C,6), xp (P,3), iterations, predicted (1,) fp64 on device."""
+    Y4, Y4p = Y4s                                         # camera-ordered and point-ordered rows (ba_linearize_y)
     dev, dt = Y4.device, Y4.dtype
     m, C, P = Y4.shape[0], Hcc.shape[0], Hpp.shape[0]
     ws, cg = _workspace(dev), _cg(dev)
@@ -332,7 +335,6 @@ def ba_solve(Y4, poses, rs, cidx, pidx, padj, cidx_p, pptr, Hcc, Hpp, gc, gp, sc
     Hpinv = torch.empty(P, 6, dtype=dt, device=dev)
     Minv = torch.empty(C, 21, dtype=dt, device=dev)
     J = [_p(Y4), _p(poses), _p(cidx), _p(pidx)]
-    Y4p = Y4.index_select(0, padj)                        # point-ordered copy for the gather side (once per linearisation)
     _launch("b200_lm_blk6_damp_inv", Y4, [_p(Hcc), float(scale), float(dmin), float(dmax), _p(Hc), _p(None), _p(None)], C)
     _launch("b200_lm_pt3_damp_inv", Y4, [_p(Hpp), float(scale), float(dmin), float(dmax), _p(Hpinv)], P)
     Sd = Hc.clone()

@@ -307,6 +307,8 @@ class BAProblem(_Problem):
         P = self.points.reshape(-1, 3).shape[0]
         self.padj = torch.sort(self.pl, stable=True)[1].contiguous()
         self.cidx_p = self.cidx[self.padj].contiguous()
+        self.ppos = torch.empty_like(self.padj, dtype=torch.int32)          # inverse permutation: position in point order
+        self.ppos[self.padj] = torch.arange(self.padj.numel(), dtype=torch.int32, device=self.padj.device)
         self.pptr = torch.zeros(P + 1, dtype=torch.int32, device=self.pl.device)
         self.pptr[1:] = torch.cumsum(torch.bincount(self.pl, minlength=P), 0).to(torch.int32)
         self.tol, self.maxiter = tol, maxiter
@@ -327,8 +329,9 @@ class BAProblem(_Problem):
     def linearize(self):
         T, p = self._params()
         if T.is_cuda and self.group is None:          # device PCG route: 16 B per observation instead of the rows
-            Y4, rs, Hcc, Hpp, gc, gp, cur = _fused.ba_linearize_y(T, p, self.pix, self.cidx, self.pidx, *self.robust)
-            return Y4, T, rs, Hcc, Hpp, gc, gp, cur
+            Y4s, rs, Hcc, Hpp, gc, gp, cur = _fused.ba_linearize_y(T, p, self.pix, self.cidx, self.pidx, *self.robust,
+                                                                    ppos=self.ppos)
+            return Y4s, T, rs, Hcc, Hpp, gc, gp, cur
         Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = _fused.call("lm_ba_linearize", T, p, self.pix, self.cidx, self.pidx, *self.robust)
         if self.group is not None:
             packed = torch.cat([t.reshape(-1) for t in (Hcc, Hpp, gc, gp)])
@@ -342,8 +345,8 @@ class BAProblem(_Problem):
     def trial(self, lin, scale, dmin, dmax):
         Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = lin
         C, P = Hcc.shape[0], Hpp.shape[0]
-        if Jc.is_cuda and self.group is None:         # device-resident Schur PCG; (Jc, Jp) are (Y4, poses) here
-            xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, self.padj, self.cidx_p, self.pptr, Hcc, Hpp,
+        if isinstance(Jc, tuple):                     # device-resident Schur PCG; (Jc, Jp) are ((Y4, Y4p), poses) here
+            xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, self.cidx_p, self.pptr, Hcc, Hpp,
                                                           gc, gp, scale, dmin,
                                                           dmax, self.tol, self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0)
             return self._finish_trial(xc, xp, pred, cur)

@@ -439,12 +439,15 @@ def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera, kind, delta):
     for a, b in zip((Jc, Jp, rs, Hcc, Hpp, gc, gp), outs_o):
         assert np.abs(a.cpu().numpy() - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
     scale, dmin, dmax = 1.0 + 1e-4, 1e-6, 1e32
-    Y4, rs_y, Hcc_y, Hpp_y, gc_y, gp_y, cur_y = F.ba_linearize_y(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, kind, delta)
+    padj = torch.from_numpy(np.argsort(pidx, kind="stable")).cuda()
+    ppos = torch.empty(len(pidx), dtype=torch.int32, device="cuda")
+    ppos[padj] = torch.arange(len(pidx), dtype=torch.int32, device="cuda")
+    Y4s, rs_y, Hcc_y, Hpp_y, gc_y, gp_y, cur_y = F.ba_linearize_y(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, kind, delta, ppos=ppos)
+    assert torch.equal(Y4s[1], Y4s[0][padj])
     for a, b in ((rs_y, rs), (Hcc_y, Hcc), (Hpp_y, Hpp), (gc_y, gc), (gp_y, gp), (cur_y, cur)):
         assert (a - b).abs().max().item() <= 1e-9 * max(1.0, b.abs().max().item())
-    padj = torch.from_numpy(np.argsort(pidx, kind="stable")).cuda()
     pptr = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(pidx, minlength=P))]).astype(np.int32)).cuda()
-    xc, xp, iters, pred = F.ba_solve(Y4, cu(T0, dt), rs, ci, pi_, padj, ci[padj].contiguous(), pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, 1e-13, 400)
+    xc, xp, iters, pred = F.ba_solve(Y4s, cu(T0, dt), rs, ci, pi_, ci[padj].contiguous(), pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, 1e-13, 400)
     m = len(cidx)
     J = np.zeros((2 * m, 6 * C + 3 * P))
     Jcn, Jpn = Jc.cpu().numpy().reshape(m, 2, 6), Jp.cpu().numpy().reshape(m, 2, 3)
