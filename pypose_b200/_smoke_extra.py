@@ -20,3 +20,43 @@ def run(dev):
     l0 = float(opt.step(X))
     l1 = float(opt.step(X))
     assert opt._problem is not None and l1 <= l0 and l1 < 1e-6, (l0, l1)
+
+    # IMU preintegration with covariance propagation (scan.cu), checked against the oracle
+    import numpy as np
+    from oracle import scan_oracle as S
+    B, F = 2, 300
+    g = torch.Generator().manual_seed(3)
+    dt = torch.full((B, F, 1), 0.01, dtype=torch.float64)
+    gyro = 0.2 * torch.randn(B, F, 3, dtype=torch.float64, generator=g)
+    acc = torch.randn(B, F, 3, dtype=torch.float64, generator=g) + torch.tensor([0.0, 0.0, 9.81], dtype=torch.float64)
+    imu = pp.module.IMUPreintegrator(prop_cov=True, reset=True).double().to(dev)
+    out = imu(dt.to(dev), gyro.to(dev), acc.to(dev))
+    a, Dp, Dv, Dr, Dt, w = S.imu_integrate(dt.numpy(), gyro.numpy(), acc.numpy(), None, np.array([[0.0, 0, 0, 1]]), [0.0, 0.0, imu._g])
+    assert np.abs(out['pos'].cpu().numpy() - Dp).max() < 1e-9 and np.abs(out['vel'].cpu().numpy() - Dv).max() < 1e-9
+    gc = np.broadcast_to(imu.gyro_cov.double().cpu().numpy(), (B, 1, 3))
+    ac = np.broadcast_to(imu.acc_cov.double().cpu().numpy(), (B, 1, 3))
+    cov = S.imu_cov(w, Dr, a, dt.numpy(), gc, ac, np.zeros((1, 9, 9)))
+    assert np.abs(out['cov'].cpu().numpy() - cov).max() < 1e-12 + 1e-9 * np.abs(cov).max()
+
+    # block-sparse routes: a pose graph and a bundle adjustment step through the device-resident PCG (pcg.cu)
+    N = 64
+    gt = pp.se3(torch.tensor([[1.0, 0.1, 0.0, 0.0, 0.0, 0.2]], device=dev).repeat(N, 1)).Exp().cumprod(dim=0, left=False)
+    edges = torch.stack([torch.arange(N - 1), torch.arange(1, N)], 1).to(dev)
+    Z = gt[edges[:, 0]].Inv() @ gt[edges[:, 1]]
+    pg = pp.module.PoseGraph(pp.se3(0.05 * torch.randn(N, 6, device=dev)).Exp() @ gt)
+    opt = pp.optim.LM(pg, solver=pp.optim.solver.PCG(tol=1e-6), sparse=True)
+    l0 = float(opt.step((edges, Z)))
+    l1 = float(opt.step((edges, Z)))
+    assert opt._problem is not None and l1 < 1e-2 * l0 + 1e-8, (l0, l1)
+    Cb, Pb, per = 6, 80, 3
+    gtb = pp.se3(0.2 * torch.randn(Cb, 6, device=dev)).Exp()
+    ptw = torch.rand(Pb, 3, device=dev) * torch.tensor([4.0, 4.0, 3.0], device=dev) + torch.tensor([-2.0, -2.0, 3.0], device=dev)
+    pidx = torch.arange(Pb, device=dev).repeat_interleave(per)
+    cidx = (pidx + torch.arange(per, device=dev).repeat(Pb) * 2) % Cb
+    yb = gtb[cidx].Act(ptw[pidx])
+    ba = pp.module.BundleAdjustment(pp.se3(0.02 * torch.randn(Cb, 6, device=dev)).Exp() * gtb, ptw + 0.03 * torch.randn(Pb, 3, device=dev))
+    opt = pp.optim.LM(ba, solver=pp.optim.solver.PCG(tol=1e-6), sparse=True)
+    inp = (-yb[:, :2] / yb[:, 2:], cidx, pidx)
+    l0 = float(opt.step(inp))
+    l1 = float(opt.step(inp))
+    assert opt._problem is not None and l1 < 0.1 * l0 + 1e-8, (l0, l1)
