@@ -128,19 +128,46 @@ class _SecondOrder(_Optimizer):
 
 
 class GaussNewton(_SecondOrder):
-    """Gauss-Newton (optimizer.py:143-328): D = solver(W J, -W R), default solver PINV."""
+    """Gauss-Newton (optimizer.py:143-328): D = solver(W J, -W R), default solver PINV.
 
-    def __init__(self, model, solver=None, kernel=None, corrector=None, weight=None, vectorize=True):
+    With the default solver, no kernel / weight / target and a model of a block-diagonal family (PoseInv, single-pose
+    reprojection; optim/structured.py) the step is the fused LM trial without damping: the normal equations of a
+    full-rank J have the pseudo-inverse's solution, so the batched 6x6 Cholesky solve replaces the dense `pinv`."""
+
+    def __init__(self, model, solver=None, kernel=None, corrector=None, weight=None, vectorize=True, group=None):
         super().__init__(model.parameters(), defaults={})
         self.jackwargs = {'vectorize': vectorize}
+        self._default_solver = solver is None
         self.solver = PINV() if solver is None else solver
-        self.weight = weight
+        self.weight, self.group = weight, group
+        self._plain = kernel is None and corrector is None
         kernel, self.corrector = _setup_correctors(kernel, corrector)
         self.model = RobustModel(model, kernel)
+        self._problem = None
+
+    def _structured(self, input, target, weight):
+        if not (self._default_solver and self._plain and target is None and weight is None and self.weight is None
+                and len(self.param_groups) == 1):
+            return None
+        if self._problem is not None and self._problem.matches(self.model.model, input):
+            return self._problem
+        prob = structured.recognize(self.model.model, input, self.param_groups[0]['params'], self.group, (0, 1.0), None, False)
+        # only the families whose step is an exact batched 6x6 solve (the PCG families need a tolerance)
+        self._problem = prob if isinstance(prob, (structured.PoseInvProblem, structured.ReprojProblem)) else None
+        return self._problem
 
     @torch.no_grad()
     def step(self, input, target=None, weight=None):
         for pg in self.param_groups:
+            prob = self._structured(input, target, weight)
+            if prob is not None:
+                r = prob.trial(prob.linearize(), 1.0, 1e-30, 1e38)       # no damping; clamp is a no-op on a PSD diagonal
+                if r["failed"] == 0:
+                    self.last = self.loss if hasattr(self, 'loss') else r["cur_t"]
+                    prob.accept()
+                    self.loss = r["loss_t"]
+                    continue
+                self._problem = None                                      # rank-deficient block: let PINV handle it
             R, weight, J = self._linearize(input, target, weight)
             A, b = (J, -R) if weight is None else (weight @ J, -weight @ R)
             D = self.solver(A=A, b=b.view(-1, 1))

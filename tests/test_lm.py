@@ -470,3 +470,29 @@ def test_named_pose_graph_rejects_out_of_range_edges(golden_lm):
     opt = pp.optim.LM(net, solver=pp.optim.solver.PCG(), sparse=True)
     with pytest.raises(IndexError):
         opt.step((edges, pp.SE3(torch.from_numpy(g["pgo/Z"].copy()))))
+
+
+def _reproj_small(dtype=torch.float64, C=5, M=60, seed=4):
+    g = torch.Generator().manual_seed(seed)
+    gt = pp.se3(0.3 * torch.randn(C, 6, generator=g, dtype=dtype)).Exp()
+    cidx = torch.sort(torch.randint(0, C, (M,), generator=g))[0]
+    pc = torch.rand(M, 3, generator=g, dtype=dtype) * 4 + torch.tensor([-2.0, -2.0, 2.0], dtype=dtype)
+    pts, pix = gt[cidx].Inv().Act(pc), -pc[:, :2] / pc[:, 2:]
+    init = pp.se3(0.05 * torch.randn(C, 6, generator=g, dtype=dtype)).Exp() * gt
+    return init, (pts, pix, cidx)
+
+
+def test_gauss_newton_structured_route_equals_generic_pinv():
+    """GaussNewton with its default solver takes the fused block route for block-diagonal families (exact 6x6 solves
+    = the pseudo-inverse solution of a full-rank J); an explicit PINV() solver keeps the reference's dense route."""
+    init, inp = _reproj_small()
+    traj = {}
+    for route in ("structured", "generic"):
+        net = pp.module.PoseReproj(init.clone())
+        opt = pp.optim.GN(net) if route == "structured" else pp.optim.GN(net, solver=pp.optim.solver.PINV())
+        losses = [float(opt.step(inp)) for _ in range(4)]
+        assert (opt._problem is not None) == (route == "structured")
+        traj[route] = (losses, net.poses.detach().clone())
+    np.testing.assert_allclose(traj["structured"][0], traj["generic"][0], rtol=1e-6, atol=1e-24)
+    assert (traj["structured"][1] - traj["generic"][1]).abs().max().item() < 1e-9
+    assert traj["structured"][0][-1] < 1e-20

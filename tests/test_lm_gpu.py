@@ -517,3 +517,15 @@ def test_reference_sparse_lm_scenarios_gpu():
     """tests/optim/test_sparse_lm.py of the reference (identity model with a target; chain pose graph with a fixed root)."""
     from tests.test_lm import run_sparse_lm_scenarios
     run_sparse_lm_scenarios(torch.device("cuda"))
+
+
+def test_gauss_newton_structured_route_on_gpu_at_scale():
+    """GN on 1e4 poses / 1e6 reprojection residuals (the reference's dense pinv would need a 2e6 x 7e4 matrix)."""
+    rng = np.random.default_rng(41)
+    gt, init, pts, pix, cidx = _reproj_problem(rng, 10_000, 1_000_000, noise=0.03)
+    net = pp.module.PoseReproj(pp.SE3(cu(init, torch.float32)))
+    inp = (cu(pts, torch.float32), cu(pix, torch.float32), torch.from_numpy(cidx).cuda())
+    opt = pp.optim.GN(net)
+    losses = [float(opt.step(inp)) for _ in range(5)]
+    assert opt._problem is not None
+    assert losses[-1] < 1e-6 * losses[0] + 1e-4, losses
