@@ -21,23 +21,6 @@ def run(dev):
     l1 = float(opt.step(X))
     assert opt._problem is not None and l1 <= l0 and l1 < 1e-6, (l0, l1)
 
-    # IMU preintegration with covariance propagation (scan.cu), checked against the oracle
-    import numpy as np
-    from oracle import scan_oracle as S
-    B, F = 2, 300
-    g = torch.Generator().manual_seed(3)
-    dt = torch.full((B, F, 1), 0.01, dtype=torch.float64)
-    gyro = 0.2 * torch.randn(B, F, 3, dtype=torch.float64, generator=g)
-    acc = torch.randn(B, F, 3, dtype=torch.float64, generator=g) + torch.tensor([0.0, 0.0, 9.81], dtype=torch.float64)
-    imu = pp.module.IMUPreintegrator(prop_cov=True, reset=True).double().to(dev)
-    out = imu(dt.to(dev), gyro.to(dev), acc.to(dev))
-    a, Dp, Dv, Dr, Dt, w = S.imu_integrate(dt.numpy(), gyro.numpy(), acc.numpy(), None, np.array([[0.0, 0, 0, 1]]), [0.0, 0.0, imu._g])
-    assert np.abs(out['pos'].cpu().numpy() - Dp).max() < 1e-9 and np.abs(out['vel'].cpu().numpy() - Dv).max() < 1e-9
-    gc = np.broadcast_to(imu.gyro_cov.double().cpu().numpy(), (B, 1, 3))
-    ac = np.broadcast_to(imu.acc_cov.double().cpu().numpy(), (B, 1, 3))
-    cov = S.imu_cov(w, Dr, a, dt.numpy(), gc, ac, np.zeros((1, 9, 9)))
-    assert np.abs(out['cov'].cpu().numpy() - cov).max() < 1e-12 + 1e-9 * np.abs(cov).max()
-
     # block-sparse routes: a pose graph and a bundle adjustment step through the device-resident PCG (pcg.cu)
     N = 64
     gt = pp.se3(torch.tensor([[1.0, 0.1, 0.0, 0.0, 0.0, 0.2]], device=dev).repeat(N, 1)).Exp().cumprod(dim=0, left=False)
