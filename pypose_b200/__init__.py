@@ -25,5 +25,6 @@ from .function import *
 from .basics import *
 from . import autograd
 from . import module
+from .module.loss import geodesic_loss
 from . import optim
 from . import testing

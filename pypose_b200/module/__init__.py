@@ -2,3 +2,4 @@ from .reproj import PoseReproj
 from .pgo import PoseGraph
 from .ba import BundleAdjustment
 from .imu_preintegrator import IMUPreintegrator
+from .loss import GeodesicLoss, geodesic_loss

@@ -145,3 +145,15 @@ def test_converters_match_reference_golden():
     assert pp.mat2SE3(t("T")).ltype is pp.SE3_type
     with pytest.raises(ValueError):
         pp.mat2SO3(2 * t("R"))
+
+
+def test_geodesic_loss_matches_trace_formula():
+    """tests/module/test_loss.py of the reference: |Log(R_x R_y^-1)| == arccos((trace - 1) / 2)."""
+    torch.manual_seed(5)
+    x, y = pp.randn_SE3(6, dtype=torch.float64), pp.randn_SE3(6, dtype=torch.float64)
+    e1 = pp.module.GeodesicLoss(reduction='none')(x, y)
+    R = (x.rotation() * y.rotation().Inv()).matrix()
+    e2 = ((R.diagonal(dim1=-1, dim2=-2).sum(-1) - 1) / 2).arccos()
+    torch.testing.assert_close(e1, e2, rtol=1e-9, atol=1e-9)
+    torch.testing.assert_close(pp.geodesic_loss(x, y), e2.mean())
+    torch.testing.assert_close(pp.geodesic_loss(x, y, reduction='sum'), e2.sum())

@@ -1,5 +1,6 @@
 #!/bin/bash
-# API conformance: run the REFERENCE's own tests (tests/lietensor, tests/basics, tests/optim) against pypose_b200.
+# API conformance: run the REFERENCE's own tests (tests/lietensor, tests/basics, tests/optim, tests/module/test_loss.py)
+# against pypose_b200.
 # Build-container only (needs /root/reference); the tests are copied to a scratch dir, never into the repo.
 # Deselected: test_sparse_lm.py (needs CUDA + the external `bae` package), test_parameter_dispatch (monkeypatches
 # the reference's private bae loader).  Known remaining failure: test_quat2unit before convert.quat2unit existed.
@@ -7,5 +8,6 @@ set -e
 D=$(mktemp -d)
 cp /root/repo/tools/conformance_conftest.py $D/conftest.py
 cp -r /root/reference/tests/lietensor /root/reference/tests/basics /root/reference/tests/optim $D/
-cd $D && PYTHONDONTWRITEBYTECODE=1 python -m pytest lietensor basics optim -q -p no:cacheprovider \
+mkdir -p $D/module && cp /root/reference/tests/module/test_loss.py $D/module/
+cd $D && PYTHONDONTWRITEBYTECODE=1 python -m pytest lietensor basics optim module -q -p no:cacheprovider \
     --deselect optim/test_sparse_lm.py --deselect lietensor/test_lietensor.py::test_parameter_dispatch "$@"
