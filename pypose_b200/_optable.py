@@ -194,9 +194,18 @@ LM_OPS = [
      [("const REAL*", "A6", "(P,6) packed symmetric 3x3"), ("const REAL*", "t", "(P,3)"), ("double", "alpha", ""),
       ("REAL*", "out", "(P,3) alpha * A t")],
      "back-substitution dp = Hpp^-1 (-gp - W^T dc)"),
+    ("b200_lm_pgo_node_order",
+     [("const REAL*", "M", "(E,21)"), ("const REAL*", "u", "(E,6)"), ("const int*", "epos_i", "(E) position of the edge in its first node's list"),
+      ("const int*", "epos_j", "(E) position in its second node's list"), ("REAL*", "Mn", "(2E,21) M_e at both positions"),
+      ("REAL*", "un", "(2E,6) -u_e at the first node's position, +u_e at the second's")],
+     "node-ordered copy of the per-edge blocks so that H products and block sums are gathers (no atomics)"),
+    ("b200_lm_pgo_node_sums",
+     [("const REAL*", "Mn", "(2E,21)"), ("const REAL*", "un", "(2E,6)"), ("const int*", "nptr", "(N+1) offsets per node"),
+      ("REAL*", "Hd", "(N,21) diagonal blocks of J^T J"), ("REAL*", "g", "(N,6) J^T R")],
+     "diagonal of A = J^T J (optimizer.py:642-643) and b = J^T R (optimizer.py:668), deterministic"),
     ("b200_lm_pgo_pcg",
-     [("const REAL*", "M", "(E,21) per-edge J^T J"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
-      ("long long", "E", "edges"), ("const REAL*", "Minv", "(n,21) preconditioner blocks"),
+     [("const REAL*", "Mn", "(2E,21) node-ordered per-edge blocks"), ("const int*", "nother", "(2E) opposite node of each entry"),
+      ("const int*", "nptr", "(n+1) offsets per node"), ("const REAL*", "Minv", "(n,21) preconditioner blocks"),
       ("const REAL*", "extra", "(n,6) clamp/damping added to diag H"), ("const REAL*", "g", "(n,6) J^T R; solves (H+extra) x = -g"),
       ("REAL*", "x", "(n,6) solution"), ("REAL*", "r", "(n,6) work"), ("REAL*", "z", "(n,6) work"), ("REAL*", "p", "(n,6) work"),
       ("REAL*", "q", "(n,6) work"),

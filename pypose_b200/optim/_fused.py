@@ -303,9 +303,20 @@ def _run_chunks(enqueue, cg, maxiter, hint=0):
             return int(st[6])
 
 
-def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None):
-    """(H + clamp/damping) x = -g by device PCG.  Returns x (n,6), iterations, predicted (1,) fp64 on device.
-    `unweighted` = (M0, u0): per-edge blocks without the information matrices, for the predicted reduction."""
+def pgo_node_order(M, u, epos_i, epos_j, nptr):
+    """Node-ordered copies (Mn, un) of the per-edge blocks and, from them, the diagonal blocks Hd and J^T R (gathers)."""
+    E, N = M.shape[0], nptr.shape[0] - 1
+    Mn, un = M.new_empty(2 * E, 21), M.new_empty(2 * E, 6)
+    Hd, g = M.new_empty(N, 21), M.new_empty(N, 6)
+    _launch("b200_lm_pgo_node_order", M, [_p(M), _p(u), _p(epos_i), _p(epos_j), _p(Mn), _p(un)], E)
+    _launch("b200_lm_pgo_node_sums", M, [_p(Mn), _p(un), _p(nptr), _p(Hd), _p(g)], N)
+    return Mn, Hd, g
+
+
+def pgo_solve(M, ei, ej, Mn, nother, nptr, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None):
+    """(H + clamp/damping) x = -g by device PCG over the node-ordered blocks.  Returns x (n,6), iterations, predicted
+    (1,) fp64 on device.  `unweighted` = (M0, u0): per-edge blocks without the information matrices, for the predicted
+    reduction."""
     dev, dt, n, E = M.device, M.dtype, Hd.shape[0], M.shape[0]
     ws, cg = _workspace(dev), _cg(dev)
     extra = torch.empty(n, 6, dtype=dt, device=dev)
@@ -314,7 +325,7 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     x, r, z, p, q = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(5))
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
     iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg", M, [
-        _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg), _p(ws),
+        _p(Mn), _p(nother), _p(nptr), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg), _p(ws),
         float(tol), maxiter, it0, k], n), cg, maxiter, hint)
     if unweighted is None:
         _launch("b200_lm_pgo_predicted", M, [_p(M), _p(ei), _p(ej), E, _p(x), _p(g), _p(ws)], n)

@@ -202,6 +202,18 @@ class PGOProblem(_Problem):
         self.Z = Z.tensor().to(self.dtype).reshape(-1, 7).contiguous()
         # information matrices (examples/module/pgo/pgo.py:75 `weight=infos`): (E,6,6) or one (6,6) for all edges
         self.W = None if weight is None else weight.to(self.dtype).reshape(-1, 36).contiguous()
+        # node adjacency (single-rank device route): every edge sits once in each endpoint's list, so H products and
+        # the block sums are gathers over node-ordered copies of the per-edge blocks
+        E = self.ei.shape[0]
+        keys = torch.cat([self.ei, self.ej]).long()
+        order = torch.sort(keys, stable=True)[1]
+        self.nother = torch.cat([self.ej, self.ei])[order].contiguous()
+        N = self.param.tensor().reshape(-1, 7).shape[0]
+        self.nptr = torch.zeros(N + 1, dtype=torch.int32, device=keys.device)
+        self.nptr[1:] = torch.cumsum(torch.bincount(keys, minlength=N), 0).to(torch.int32)
+        pos = torch.empty(2 * E, dtype=torch.int32, device=keys.device)
+        pos[order] = torch.arange(2 * E, dtype=torch.int32, device=keys.device)
+        self.epos_i, self.epos_j = pos[:E].contiguous(), pos[E:].contiguous()
         self.tol, self.maxiter = tol, maxiter
         self._trial = None
         self.cg_iters = 0
@@ -225,6 +237,9 @@ class PGOProblem(_Problem):
         else:
             M, u, M0, u0, cur = _fused.call("lm_pgo_linearize_w", nodes, self.Z, self.ei, self.ej, self.W, *self.robust)
             unw = (M0, u0)
+        if M.is_cuda and self.group is None:           # gathers over node-ordered copies, no atomics
+            Mn, Hd, g = _fused.pgo_node_order(M, u, self.epos_i, self.epos_j, self.nptr)
+            return (M, Mn), Hd, g, cur, unw
         Hd, g = _fused.call("lm_pgo_scatter", M, u, self.ei, self.ej, nodes.shape[0])
         if self.group is not None:
             packed = torch.cat([Hd.reshape(-1), g.reshape(-1)])
@@ -239,8 +254,9 @@ class PGOProblem(_Problem):
 
     def trial(self, lin, scale, dmin, dmax):
         M, Hd, g, cur, unw = lin
-        if M.is_cuda and self.group is None:          # device-resident PCG: one host read per 8 iterations
-            D, self.cg_iters, predicted = _fused.pgo_solve(M, self.ei, self.ej, Hd, g, scale, dmin, dmax, self.tol,
+        if isinstance(M, tuple):                      # device-resident PCG: (edge-ordered, node-ordered) blocks
+            D, self.cg_iters, predicted = _fused.pgo_solve(M[0], self.ei, self.ej, M[1], self.nother, self.nptr, Hd, g,
+                                                           scale, dmin, dmax, self.tol,
                                                            self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0,
                                                            unweighted=unw)
             return self._finish_trial(D, predicted, cur)

@@ -398,8 +398,19 @@ def test_pgo_device_pcg_vs_dense_solve(maxiter):
     ei, ej = (torch.from_numpy(edges[:, k].astype(np.int32)).cuda() for k in (0, 1))
     M, u, c = ops.lm_pgo_linearize(cu(init, dt), cu(Z, dt), ei, ej, 0, 1.0)
     Hd, g = ops.lm_pgo_scatter(M, u, ei, ej, N)
+    # node-ordered copies and the gathered block sums (no atomics) must agree with the scatter kernel
+    keys = torch.cat([ei, ej]).long()
+    order = torch.sort(keys, stable=True)[1]
+    nother = torch.cat([ej, ei])[order].contiguous()
+    nptr = torch.zeros(N + 1, dtype=torch.int32, device="cuda")
+    nptr[1:] = torch.cumsum(torch.bincount(keys, minlength=N), 0).to(torch.int32)
+    pos = torch.empty(2 * len(ei), dtype=torch.int32, device="cuda")
+    pos[order] = torch.arange(2 * len(ei), dtype=torch.int32, device="cuda")
+    Mn, Hd_n, g_n = F.pgo_node_order(M, u, pos[:len(ei)].contiguous(), pos[len(ei):].contiguous(), nptr)
+    assert (Hd_n - Hd).abs().max().item() <= 1e-10 * Hd.abs().max().item()
+    assert (g_n - g).abs().max().item() <= 1e-10 * max(1.0, g.abs().max().item())
     scale, dmin, dmax = 1.0 + 1e-3, 1e-6, 1e32
-    x, iters, pred = F.pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, 1e-13, maxiter)
+    x, iters, pred = F.pgo_solve(M, ei, ej, Mn, nother, nptr, Hd_n, g_n, scale, dmin, dmax, 1e-13, maxiter)
     # dense H from the per-edge blocks
     Mb = _dense_sym(M.cpu().numpy(), M.shape[0], 6)
     H = np.zeros((N * 6, N * 6))
