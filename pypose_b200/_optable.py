@@ -204,8 +204,8 @@ LM_OPS = [
       ("REAL*", "Hd", "(N,21) diagonal blocks of J^T J"), ("REAL*", "g", "(N,6) J^T R")],
      "diagonal of A = J^T J (optimizer.py:642-643) and b = J^T R (optimizer.py:668), deterministic"),
     ("b200_lm_pgo_pcg",
-     [("const REAL*", "Mn", "(2E,21) node-ordered per-edge blocks"), ("const int*", "nother", "(2E) opposite node of each entry"),
-      ("const int*", "nptr", "(n+1) offsets per node"), ("const REAL*", "Minv", "(n,21) preconditioner blocks"),
+     [("const REAL*", "M", "(E,21) per-edge J^T J"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
+      ("long long", "E", "edges"), ("const REAL*", "Minv", "(n,21) preconditioner blocks"),
       ("const REAL*", "extra", "(n,6) clamp/damping added to diag H"), ("const REAL*", "g", "(n,6) J^T R; solves (H+extra) x = -g"),
       ("REAL*", "x", "(n,6) solution"), ("REAL*", "r", "(n,6) work"), ("REAL*", "z", "(n,6) work"), ("REAL*", "p", "(n,6) work"),
       ("REAL*", "q", "(n,6) work"),
@@ -214,6 +214,13 @@ LM_OPS = [
       ("long long", "maxiter", ""), ("long long", "first_iter", "0 initialises the state; otherwise continue"),
       ("long long", "iters", "iterations to enqueue (no-ops once the done flag is set)")],
      "PCG.forward loop, optim/solver.py:312-340, with M = block-Jacobi; enqueues `iters` iterations without a host sync"),
+    ("b200_lm_pgo_pcg_gather",
+     [("const REAL*", "Mn", "(2E,21) node-ordered per-edge blocks"), ("const int*", "nother", "(2E) opposite node of each entry"),
+      ("const int*", "nptr", "(n+1) offsets per node"), ("const REAL*", "Minv", "(n,21)"), ("const REAL*", "extra", "(n,6)"),
+      ("const REAL*", "g", "(n,6)"), ("REAL*", "x", "(n,6)"), ("REAL*", "r", "(n,6)"), ("REAL*", "z", "(n,6)"), ("REAL*", "p", "(n,6)"),
+      ("REAL*", "q", "(n,6)"), ("double*", "cg", "(8) state"), ("double*", "ws", ""), ("double", "tol", ""),
+      ("long long", "maxiter", ""), ("long long", "first_iter", ""), ("long long", "iters", "")],
+     "as b200_lm_pgo_pcg with the H product as a gather over node-ordered blocks: no atomics, bit-reproducible"),
     ("b200_lm_pgo_predicted",
      [("const REAL*", "M", "(E,21)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"), ("long long", "E", ""),
       ("const REAL*", "D", "(n,6) step"), ("const REAL*", "g", "(n,6) J^T R"), ("double*", "ws", "ws[0] = D^T H D + 2 D^T g")],

@@ -608,6 +608,32 @@ using namespace b200pose;
 
 #define LM_LAUNCH(kern, work, st, ...) kern<<<lm_grid(work, kLmThreads), kLmThreads, 0, (cudaStream_t)(st)>>>(__VA_ARGS__)
 
+// One chunk of PCG iterations for the pose graph.  GATHER = false: the operator walks the edges and scatter-adds
+// (A = per-edge M, ia/ib = ei/ej, E edges) — the faster variant on B200 (20.5 us per product at 3e5 edges, and no
+// node-ordered copy to build: 1.35 vs 1.44 ms per LM step).  GATHER = true: node-ordered blocks (A = Mn, ia = nother,
+// ib = nptr), no atomics, bit-reproducible; selected with B200POSE_DETERMINISTIC=1.
+template <typename CT, bool GATHER>
+static int pgo_pcg_run(const CT* A, const int* ia, const int* ib, long long E, const CT* Minv, const CT* extra, const CT* g,
+                       CT* x, CT* r, CT* z, CT* p, CT* q, double* cg, double* ws, double tol, long long maxiter,
+                       long long first_iter, long long iters, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (first_iter == 0)
+    LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, g, (CT)-1, extra, 1, x, r, p, q, cg, ws, tol, (double)maxiter, n);
+  for (long long it = first_iter; it < first_iter + iters; ++it) {
+    const int par = (int)(it & 1);
+    if (GATHER) LM_LAUNCH(pcg_pgo_spmv_gather_kernel<CT>, n * kLanesPerNode, stream, A, ia, ib, extra, p, q, cg, n);
+    else if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, A, ia, ib, p, q, cg, E);
+    if (n <= kVecSmallRows) {
+      launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, cg, par, n, stream);
+      continue;
+    }
+    LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
+    LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);
+    LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, 1, p, q, cg, par, n);
+  }
+  return (int)cudaGetLastError();
+}
+
 #define PCG_ABI(SFX, CT)                                                                                              \
   B200_EXPORT int b200_lm_blk6_damp_inv_##SFX(const CT* H, double scale, double dmin, double dmax, CT* Hd, CT* extra, \
                                               CT* Minv, long long n, void* stream) {                                  \
@@ -639,25 +665,19 @@ using namespace b200pose;
     LM_LAUNCH(pgo_node_sums_kernel<CT>, N * kLanesPerNode, stream, Mn, un, nptr, Hd, g, N);                           \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_pgo_pcg_##SFX(const CT* Mn, const int* nother, const int* nptr, const CT* Minv,             \
+  B200_EXPORT int b200_lm_pgo_pcg_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* Minv,       \
                                         const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q, double* cg,  \
                                         double* ws, double tol, long long maxiter, long long first_iter,              \
                                         long long iters, long long n, void* stream) {                                 \
-    if (n <= 0) return 0;                                                                                             \
-    if (first_iter == 0)                                                                                              \
-      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, g, (CT)-1, extra, 1, x, r, p, q, cg, ws, tol, (double)maxiter, n); \
-    for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
-      const int par = (int)(it & 1);                                                                                  \
-      LM_LAUNCH(pcg_pgo_spmv_gather_kernel<CT>, n * kLanesPerNode, stream, Mn, nother, nptr, extra, p, q, cg, n);     \
-      if (n <= kVecSmallRows) {                                                                                       \
-        launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, cg, par, n, (cudaStream_t)stream);                      \
-        continue;                                                                                                     \
-      }                                                                                                               \
-      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \
-      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);                                \
-      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, 1, p, q, cg, par, n);                                         \
-    }                                                                                                                 \
-    return (int)cudaGetLastError();                                                                                   \
+    return pgo_pcg_run<CT, false>(M, ei, ej, E, Minv, extra, g, x, r, z, p, q, cg, ws, tol, maxiter, first_iter,      \
+                                  iters, n, (cudaStream_t)stream);                                                    \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_pcg_gather_##SFX(const CT* Mn, const int* nother, const int* nptr, const CT* Minv,      \
+                                               const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q,       \
+                                               double* cg, double* ws, double tol, long long maxiter,                 \
+                                               long long first_iter, long long iters, long long n, void* stream) {    \
+    return pgo_pcg_run<CT, true>(Mn, nother, nptr, 0, Minv, extra, g, x, r, z, p, q, cg, ws, tol, maxiter,            \
+                                 first_iter, iters, n, (cudaStream_t)stream);                                         \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_predicted_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* D,    \
                                               const CT* g, double* ws, long long n, void* stream) {                   \

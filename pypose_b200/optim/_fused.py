@@ -313,10 +313,10 @@ def pgo_node_order(M, u, epos_i, epos_j, nptr):
     return Mn, Hd, g
 
 
-def pgo_solve(M, ei, ej, Mn, nother, nptr, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None):
-    """(H + clamp/damping) x = -g by device PCG over the node-ordered blocks.  Returns x (n,6), iterations, predicted
-    (1,) fp64 on device.  `unweighted` = (M0, u0): per-edge blocks without the information matrices, for the predicted
-    reduction."""
+def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None, node=None):
+    """(H + clamp/damping) x = -g by device PCG.  Returns x (n,6), iterations, predicted (1,) fp64 on device.
+    `unweighted` = (M0, u0): per-edge blocks without the information matrices, for the predicted reduction.
+    `node` = (Mn, nother, nptr): node-ordered blocks -> the H product is a gather (deterministic) instead of a scatter."""
     dev, dt, n, E = M.device, M.dtype, Hd.shape[0], M.shape[0]
     ws, cg = _workspace(dev), _cg(dev)
     extra = torch.empty(n, 6, dtype=dt, device=dev)
@@ -324,9 +324,14 @@ def pgo_solve(M, ei, ej, Mn, nother, nptr, Hd, g, scale, dmin, dmax, tol, maxite
     _launch("b200_lm_blk6_damp_inv", M, [_p(Hd), float(scale), float(dmin), float(dmax), _p(None), _p(extra), _p(Minv)], n)
     x, r, z, p, q = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(5))
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
-    iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg", M, [
-        _p(Mn), _p(nother), _p(nptr), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg), _p(ws),
-        float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+    if node is None:
+        iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg", M, [
+            _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg), _p(ws),
+            float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+    else:
+        iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg_gather", M, [
+            _p(node[0]), _p(node[1]), _p(node[2]), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg),
+            _p(ws), float(tol), maxiter, it0, k], n), cg, maxiter, hint)
     if unweighted is None:
         _launch("b200_lm_pgo_predicted", M, [_p(M), _p(ei), _p(ej), E, _p(x), _p(g), _p(ws)], n)
     else:

@@ -15,6 +15,8 @@ Multi-GPU (`group`): PoseInv shards poses (each rank owns its rows; only the sca
 all-reduced).  Reproj shards residuals (each rank accumulates H/g for its rows; H, g and the
 scalars are all-reduced; the 6x6 solves run redundantly on every rank).
 """
+import os
+
 import torch
 
 from ..lietensor import lietensor as _lt
@@ -202,8 +204,10 @@ class PGOProblem(_Problem):
         self.Z = Z.tensor().to(self.dtype).reshape(-1, 7).contiguous()
         # information matrices (examples/module/pgo/pgo.py:75 `weight=infos`): (E,6,6) or one (6,6) for all edges
         self.W = None if weight is None else weight.to(self.dtype).reshape(-1, 36).contiguous()
-        # node adjacency (single-rank device route): every edge sits once in each endpoint's list, so H products and
-        # the block sums are gathers over node-ordered copies of the per-edge blocks
+        # B200POSE_DETERMINISTIC=1: node adjacency (single-rank device route) — every edge sits once in each endpoint's
+        # list, so H products and the block sums are gathers over node-ordered copies of the per-edge blocks: no
+        # atomics, bit-reproducible, ~7 % slower per LM step than the scatter kernels
+        self.deterministic = os.environ.get("B200POSE_DETERMINISTIC", "0") == "1"
         E = self.ei.shape[0]
         keys = torch.cat([self.ei, self.ej]).long()
         order = torch.sort(keys, stable=True)[1]
@@ -237,7 +241,7 @@ class PGOProblem(_Problem):
         else:
             M, u, M0, u0, cur = _fused.call("lm_pgo_linearize_w", nodes, self.Z, self.ei, self.ej, self.W, *self.robust)
             unw = (M0, u0)
-        if M.is_cuda and self.group is None:           # gathers over node-ordered copies, no atomics
+        if M.is_cuda and self.group is None and self.deterministic:      # gathers over node-ordered copies, no atomics
             Mn, Hd, g = _fused.pgo_node_order(M, u, self.epos_i, self.epos_j, self.nptr)
             return (M, Mn), Hd, g, cur, unw
         Hd, g = _fused.call("lm_pgo_scatter", M, u, self.ei, self.ej, nodes.shape[0])
@@ -254,11 +258,12 @@ class PGOProblem(_Problem):
 
     def trial(self, lin, scale, dmin, dmax):
         M, Hd, g, cur, unw = lin
-        if isinstance(M, tuple):                      # device-resident PCG: (edge-ordered, node-ordered) blocks
-            D, self.cg_iters, predicted = _fused.pgo_solve(M[0], self.ei, self.ej, M[1], self.nother, self.nptr, Hd, g,
-                                                           scale, dmin, dmax, self.tol,
+        if isinstance(M, tuple) or (M.is_cuda and self.group is None):   # device-resident PCG
+            node = (M[1], self.nother, self.nptr) if isinstance(M, tuple) else None
+            M = M[0] if isinstance(M, tuple) else M
+            D, self.cg_iters, predicted = _fused.pgo_solve(M, self.ei, self.ej, Hd, g, scale, dmin, dmax, self.tol,
                                                            self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0,
-                                                           unweighted=unw)
+                                                           unweighted=unw, node=node)
             return self._finish_trial(D, predicted, cur)
         d = Hd[:, _DIAG21]
         extra = d.clamp(dmin, dmax) * scale - d                       # added to the diagonal of H

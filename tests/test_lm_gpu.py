@@ -410,7 +410,9 @@ def test_pgo_device_pcg_vs_dense_solve(maxiter):
     assert (Hd_n - Hd).abs().max().item() <= 1e-10 * Hd.abs().max().item()
     assert (g_n - g).abs().max().item() <= 1e-10 * max(1.0, g.abs().max().item())
     scale, dmin, dmax = 1.0 + 1e-3, 1e-6, 1e32
-    x, iters, pred = F.pgo_solve(M, ei, ej, Mn, nother, nptr, Hd_n, g_n, scale, dmin, dmax, 1e-13, maxiter)
+    x, iters, pred = F.pgo_solve(M, ei, ej, Hd_n, g_n, scale, dmin, dmax, 1e-13, maxiter, node=(Mn, nother, nptr))
+    x2, iters2, pred2 = F.pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, 1e-13, maxiter)        # scatter operator
+    assert iters2 == iters and (x2 - x).abs().max().item() <= 1e-9 * x.abs().max().item()
     # dense H from the per-edge blocks
     Mb = _dense_sym(M.cpu().numpy(), M.shape[0], 6)
     H = np.zeros((N * 6, N * 6))
@@ -540,3 +542,22 @@ def test_gauss_newton_structured_route_on_gpu_at_scale():
     losses = [float(opt.step(inp)) for _ in range(5)]
     assert opt._problem is not None
     assert losses[-1] < 1e-6 * losses[0] + 1e-4, losses
+
+
+def test_lm_pgo_deterministic_gather_route(golden_lm, monkeypatch):
+    """B200POSE_DETERMINISTIC=1: node-ordered gathers instead of scatter atomics — same reference trajectory, and two
+    runs give bit-identical parameters."""
+    monkeypatch.setenv("B200POSE_DETERMINISTIC", "1")
+    g = golden_lm
+    finals = []
+    for _ in range(2):
+        net = pp.module.PoseGraph(pp.SE3(torch.from_numpy(g["pgo/nodes0"].copy()).cuda()))
+        inp = (torch.from_numpy(g["pgo/edges"]).cuda(), pp.SE3(torch.from_numpy(g["pgo/Z"].copy()).cuda()))
+        opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), solver=pp.optim.solver.PCG(tol=1e-12), sparse=True)
+        for k in range(5):
+            loss = opt.step(inp)
+            assert opt._problem is not None and opt._problem.deterministic
+            np.testing.assert_allclose(float(loss), g["pgo/trustregion/loss"][k], rtol=1e-6)
+            np.testing.assert_allclose(net.nodes.detach().cpu().numpy(), g["pgo/trustregion/poses"][k], atol=1e-7)
+        finals.append(net.nodes.detach().clone())
+    assert torch.equal(finals[0], finals[1])
