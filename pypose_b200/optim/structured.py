@@ -19,6 +19,7 @@ import os
 
 import torch
 
+from .. import _C
 from ..lietensor import lietensor as _lt
 from ..lietensor.lietensor import LieTensor, Parameter, SE3_type
 from . import _fused  # noqa: F401  (registers the ops)
@@ -36,6 +37,15 @@ def _copy_param(param, value):
     """param <- value without the LieTensor `__torch_function__` round trip (35 us per call, measured)."""
     with torch._C.DisableTorchFunctionSubclass():
         param.copy_(value.view(param.shape))
+
+
+def _retract_se3(D, poses):
+    """Exp(D) * poses for (n,6) steps and (n,7) SE3 rows.  On the GPU the two C-ABI entry points are called directly
+    (the LieTensor / autograd.Function path costs ~50 us of Python per op and no graph is needed here)."""
+    if D.is_cuda:
+        X = _C.launch_rows("b200_se3_exp_fwd", [D.contiguous()], [7])[0]
+        return _C.launch_rows("b200_SE3_mul_fwd", [X, poses.contiguous()], [7])[0]
+    return (LieTensor(D, ltype=_lt.se3_type).Exp() * LieTensor(poses, ltype=SE3_type)).tensor()
 
 
 class _Problem:
@@ -283,16 +293,14 @@ class PGOProblem(_Problem):
         return self._finish_trial(D, predicted, cur)
 
     def _finish_trial(self, D, predicted, cur):
-        nodes = self._nodes()
-        delta = LieTensor(D, ltype=_lt.se3_type)
-        self._trial = (delta.Exp() * LieTensor(nodes, ltype=SE3_type)).tensor()
+        self._trial = _retract_se3(D, self._nodes())
         tl = _fused.call("lm_pgo_loss", self._trial, self.Z, self.ei, self.ej, *self.robust)
         shard = _allreduce(torch.cat([cur, tl]), self.group)
         return self._result(torch.cat([shard, predicted, predicted.new_zeros(1)]),
                             {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
 
     def accept(self):
-        self.param.copy_(self._trial.view(self.param.shape))
+        _copy_param(self.param, self._trial)
 
 
 def _unpack6(Hp):
@@ -407,7 +415,7 @@ class BAProblem(_Problem):
 
     def _finish_trial(self, xc, xp, pred, cur):
         T, pts = self._params()
-        Tn = (LieTensor(xc, ltype=_lt.se3_type).Exp() * LieTensor(T, ltype=SE3_type)).tensor()
+        Tn = _retract_se3(xc, T)
         pn = pts + xp
         self._trial = (Tn, pn)
         tl = _fused.call("lm_ba_loss", Tn, pn, self.pix, self.cidx, self.pidx, *self.robust)
@@ -415,8 +423,8 @@ class BAProblem(_Problem):
         return self._result(torch.cat([shard, shard.new_zeros(1)]), {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
 
     def accept(self):
-        self.poses.copy_(self._trial[0].view(self.poses.shape))
-        self.points.copy_(self._trial[1].view(self.points.shape))
+        _copy_param(self.poses, self._trial[0])
+        _copy_param(self.points, self._trial[1])
 
 
 def _input_key(input):
