@@ -11,6 +11,9 @@
 //   dir     beta = rz'/rz; p = z + beta p; q = D p          (D: the block-diagonal part of the operator)
 // Reductions are the deterministic last-block fp64 folds of lm_common.cuh.
 #include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <unordered_map>
 #include "lm_common.cuh"
 
 namespace b200pose {
@@ -608,6 +611,60 @@ using namespace b200pose;
 
 #define LM_LAUNCH(kern, work, st, ...) kern<<<lm_grid(work, kLmThreads), kLmThreads, 0, (cudaStream_t)(st)>>>(__VA_ARGS__)
 
+// ---- CUDA-graph replay of a chunk of iterations --------------------------------------------------------------------
+// A chunk is 45-90 kernels of 4-20 us each; enqueued one by one the GPU front end leaves ~4 us between them (30 % of a
+// pose-graph LM step, measured).  The chunk is therefore captured once per distinct argument tuple (on a private
+// stream: the caller's stream may be the legacy default stream, which cannot be captured) and replayed with
+// cudaGraphLaunch into the caller's stream.  PyTorch's caching allocator hands the same addresses to the same
+// allocation sequence, so consecutive LM trials hit the cache.  Any failure of the capture API disables graphs for the
+// process and falls back to plain launches.  B200POSE_CG_GRAPH=0 turns it off.
+struct GraphCache {
+  std::unordered_map<std::string, cudaGraphExec_t> map;
+  cudaStream_t cap = nullptr;
+  bool disabled = false;
+};
+static GraphCache& graph_cache() {
+  static thread_local GraphCache c;
+  return c;
+}
+template <typename Key, typename F> static int replay_or_launch(const Key& key, cudaStream_t user, F&& enqueue) {
+  static const bool on = !(getenv("B200POSE_CG_GRAPH") && atoi(getenv("B200POSE_CG_GRAPH")) == 0);
+  GraphCache& gc = graph_cache();
+  if (!on || gc.disabled) { enqueue(user); return (int)cudaGetLastError(); }
+  const std::string k(reinterpret_cast<const char*>(&key), sizeof(Key));
+  auto it = gc.map.find(k);
+  if (it == gc.map.end()) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = gc.cap || cudaStreamCreateWithFlags(&gc.cap, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamBeginCapture(gc.cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      enqueue(gc.cap);
+      ok = cudaStreamEndCapture(gc.cap, &graph) == cudaSuccess && graph != nullptr;
+    }
+    ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {                                   // never seen in practice; keep the solver working regardless
+      gc.disabled = true;
+      cudaGetLastError();
+      enqueue(user);
+      return (int)cudaGetLastError();
+    }
+    if (gc.map.size() >= 64) {                   // bounded: drop everything (addresses changed for good)
+      for (auto& e : gc.map) cudaGraphExecDestroy(e.second);
+      gc.map.clear();
+    }
+    it = gc.map.emplace(k, exec).first;
+  }
+  return (int)cudaGraphLaunch(it->second, user);
+}
+struct PcgKey {                                   // every launch argument of a chunk (padding zeroed by the caller)
+  const void* ptr[20];
+  long long num[8];
+  double tol;
+  int tag, dev;
+};
+
 // One chunk of PCG iterations for the pose graph.  GATHER = false: the operator walks the edges and scatter-adds
 // (A = per-edge M, ia/ib = ei/ej, E edges) — the faster variant on B200 (20.5 us per product at 3e5 edges, and no
 // node-ordered copy to build: 1.35 vs 1.44 ms per LM step).  GATHER = true: node-ordered blocks (A = Mn, ia = nother,
@@ -615,23 +672,64 @@ using namespace b200pose;
 template <typename CT, bool GATHER>
 static int pgo_pcg_run(const CT* A, const int* ia, const int* ib, long long E, const CT* Minv, const CT* extra, const CT* g,
                        CT* x, CT* r, CT* z, CT* p, CT* q, double* cg, double* ws, double tol, long long maxiter,
-                       long long first_iter, long long iters, long long n, cudaStream_t stream) {
+                       long long first_iter, long long iters, long long n, cudaStream_t user) {
   if (n <= 0) return 0;
-  if (first_iter == 0)
-    LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, g, (CT)-1, extra, 1, x, r, p, q, cg, ws, tol, (double)maxiter, n);
-  for (long long it = first_iter; it < first_iter + iters; ++it) {
-    const int par = (int)(it & 1);
-    if (GATHER) LM_LAUNCH(pcg_pgo_spmv_gather_kernel<CT>, n * kLanesPerNode, stream, A, ia, ib, extra, p, q, cg, n);
-    else if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, A, ia, ib, p, q, cg, E);
-    if (n <= kVecSmallRows) {
-      launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, cg, par, n, stream);
-      continue;
+  PcgKey key;
+  memset(&key, 0, sizeof(key));
+  const void* ptrs[] = {A, ia, ib, Minv, extra, g, x, r, z, p, q, cg, ws};
+  for (int i = 0; i < 13; ++i) key.ptr[i] = ptrs[i];
+  key.num[0] = E; key.num[1] = maxiter; key.num[2] = first_iter; key.num[3] = iters; key.num[4] = n;
+  key.tol = tol; key.tag = (GATHER ? 2 : 1) + 16 * (int)sizeof(CT);
+  cudaGetDevice(&key.dev);
+  return replay_or_launch(key, user, [&](cudaStream_t stream) {
+    if (first_iter == 0)
+      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, g, (CT)-1, extra, 1, x, r, p, q, cg, ws, tol, (double)maxiter, n);
+    for (long long it = first_iter; it < first_iter + iters; ++it) {
+      const int par = (int)(it & 1);
+      if (GATHER) LM_LAUNCH(pcg_pgo_spmv_gather_kernel<CT>, n * kLanesPerNode, stream, A, ia, ib, extra, p, q, cg, n);
+      else if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, A, ia, ib, p, q, cg, E);
+      if (n <= kVecSmallRows) {
+        launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, cg, par, n, stream);
+        continue;
+      }
+      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);
+      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, 1, p, q, cg, par, n);
     }
-    LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
-    LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);
-    LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, 1, p, q, cg, par, n);
-  }
-  return (int)cudaGetLastError();
+  });
+}
+template <typename CT>
+static int ba_pcg_run(const CT* Y4, const CT* poses, const int* cidx, const int* pidx, long long m, const CT* Y4p,
+                      const int* cidx_p, const int* pptr, const CT* Hc, const CT* Hpinv, const CT* Minv, const CT* bneg,
+                      CT* x, CT* r, CT* z, CT* p, CT* q, CT* t, double* cg, double* ws, double tol, long long maxiter,
+                      long long P, long long first_iter, long long iters, long long n, cudaStream_t user) {
+  if (n <= 0) return 0;
+  PcgKey key;
+  memset(&key, 0, sizeof(key));
+  const void* ptrs[] = {Y4, poses, cidx, pidx, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, q, t, cg, ws};
+  for (int i = 0; i < 19; ++i) key.ptr[i] = ptrs[i];
+  key.num[0] = m; key.num[1] = maxiter; key.num[2] = first_iter; key.num[3] = iters; key.num[4] = n; key.num[5] = P;
+  key.tol = tol; key.tag = 3 + 16 * (int)sizeof(CT);
+  cudaGetDevice(&key.dev);
+  return replay_or_launch(key, user, [&](cudaStream_t stream) {
+    if (first_iter == 0)
+      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, bneg, (CT)-1, Hc, 2, x, r, p, q, cg, ws, tol, (double)maxiter, n);
+    for (long long it = first_iter; it < first_iter + iters; ++it) {
+      const int par = (int)(it & 1);
+      if (m > 0) {
+        LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4p, poses, cidx_p, pptr, Hpinv, p,
+                  (const CT*)nullptr, (CT)1, t, cg, P);
+        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, (const CT*)nullptr, t, q, cg, m);
+      }
+      if (n <= kVecSmallRows) {
+        launch_cg_vec_small<CT>(Minv, Hc, 2, x, r, z, p, q, cg, par, n, stream);
+        continue;
+      }
+      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);
+      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, Hc, 2, p, q, cg, par, n);
+    }
+  });
 }
 
 #define PCG_ABI(SFX, CT)                                                                                              \
@@ -718,31 +816,13 @@ static int pgo_pcg_run(const CT* A, const int* ia, const int* ib, long long E, c
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx, long long m,  \
-                                       const CT* Y4p, const int* cidx_p, const int* pptr, const CT* Hc,             \
-                                       const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r,   \
-                                       CT* z, CT* p, CT* q, CT* t, double* cg, double* ws, double tol,                \
-                                       long long maxiter, long long P, long long first_iter, long long iters,         \
-                                       long long n, void* stream) {                                                   \
-    if (n <= 0) return 0;                                                                                             \
-    cudaStream_t st = (cudaStream_t)stream;                                                                           \
-    if (first_iter == 0)                                                                                              \
-      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, bneg, (CT)-1, Hc, 2, x, r, p, q, cg, ws, tol, (double)maxiter, n); \
-    for (long long it = first_iter; it < first_iter + iters; ++it) {                                                  \
-      const int par = (int)(it & 1);                                                                                  \
-      if (m > 0) {                                                                                                    \
-        LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4p, poses, cidx_p, pptr, Hpinv, p,       \
-                  (const CT*)nullptr, (CT)1, t, cg, P);                                                                                   \
-        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, (const CT*)nullptr, t, q, cg, m);      \
-      }                                                                                                               \
-      if (n <= kVecSmallRows) {                                                                                       \
-        launch_cg_vec_small<CT>(Minv, Hc, 2, x, r, z, p, q, cg, par, n, (cudaStream_t)stream);                         \
-        continue;                                                                                                     \
-      }                                                                                                               \
-      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);                                                       \
-      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);                                \
-      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, Hc, 2, p, q, cg, par, n);                                            \
-    }                                                                                                                 \
-    return (int)cudaGetLastError();                                                                                   \
+                                       const CT* Y4p, const int* cidx_p, const int* pptr, const CT* Hc,               \
+                                       const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r, CT* z, CT* p,   \
+                                       CT* q, CT* t, double* cg, double* ws, double tol, long long maxiter,           \
+                                       long long P, long long first_iter, long long iters, long long n,               \
+                                       void* stream) {                                                                \
+    return ba_pcg_run<CT>(Y4, poses, cidx, pidx, m, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, q, t, cg,   \
+                          ws, tol, maxiter, P, first_iter, iters, n, (cudaStream_t)stream);                           \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_predicted_##SFX(const CT* Y4, const CT* poses, const CT* rs, const int* cidx,            \
                                              const int* pidx, const CT* xc, const CT* xp, double* ws, long long m,    \
