@@ -611,13 +611,12 @@ using namespace b200pose;
 
 #define LM_LAUNCH(kern, work, st, ...) kern<<<lm_grid(work, kLmThreads), kLmThreads, 0, (cudaStream_t)(st)>>>(__VA_ARGS__)
 
-// ---- CUDA-graph replay of a chunk of iterations --------------------------------------------------------------------
-// A chunk is 45-90 kernels of 4-20 us each; enqueued one by one the GPU front end leaves ~4 us between them (30 % of a
-// pose-graph LM step, measured).  The chunk is therefore captured once per distinct argument tuple (on a private
-// stream: the caller's stream may be the legacy default stream, which cannot be captured) and replayed with
-// cudaGraphLaunch into the caller's stream.  PyTorch's caching allocator hands the same addresses to the same
-// allocation sequence, so consecutive LM trials hit the cache.  Any failure of the capture API disables graphs for the
-// process and falls back to plain launches.  B200POSE_CG_GRAPH=0 turns it off.
+// ---- optional CUDA-graph replay of a chunk of iterations (B200POSE_CG_GRAPH=1; off by default) -----------------------
+// A chunk is 45-90 kernels of 4-20 us each with ~4 us between dependent kernels.  Capturing the chunk once per distinct
+// argument tuple (on a private stream: the caller's stream may be the legacy default stream, which cannot be captured)
+// and replaying it with cudaGraphLaunch was measured on B200 and does NOT help: bundle adjustment 1.63 ms/step with the
+// graph vs 1.58 ms without — the gaps are dependency (drain + launch) latency on the device, not host enqueue cost.
+// Kept as an opt-in because it costs nothing when off.  Any failure of the capture API disables it for the process.
 struct GraphCache {
   std::unordered_map<std::string, cudaGraphExec_t> map;
   cudaStream_t cap = nullptr;
@@ -628,7 +627,7 @@ static GraphCache& graph_cache() {
   return c;
 }
 template <typename Key, typename F> static int replay_or_launch(const Key& key, cudaStream_t user, F&& enqueue) {
-  static const bool on = !(getenv("B200POSE_CG_GRAPH") && atoi(getenv("B200POSE_CG_GRAPH")) == 0);
+  static const bool on = getenv("B200POSE_CG_GRAPH") && atoi(getenv("B200POSE_CG_GRAPH")) != 0;
   GraphCache& gc = graph_cache();
   if (!on || gc.disabled) { enqueue(user); return (int)cudaGetLastError(); }
   const std::string k(reinterpret_cast<const char*>(&key), sizeof(Key));
