@@ -333,4 +333,74 @@ template <typename T> LM_HD void reproj_point_rows(const Elem<T>& Tc, const V3<T
   p1[0] = r1.x; p1[1] = r1.y; p1[2] = r1.z;
 }
 
+// ---- packed symmetric blocks: 6x6 as 21 (row-major upper triangle), 3x3 as 6 ----
+template <typename T> LM_HD void sym6_unpack(const T* a, T (&A)[6][6]) {
+  int q = 0;
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int c = p; c < 6; ++c) { A[p][c] = a[q]; A[c][p] = a[q]; ++q; }
+}
+template <typename T> LM_HD void sym6_pack(const T (&A)[6][6], T* a) {
+  int q = 0;
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int c = p; c < 6; ++c) a[q++] = A[p][c];
+}
+template <typename T> LM_HD void sym6_mv(const T (&A)[6][6], const T (&x)[6], T (&y)[6]) {
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    T v = T(0);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) v += A[p][c] * x[c];
+    y[p] = v;
+  }
+}
+// A^-1 of a symmetric positive definite NxN block through its Cholesky factor: A = L L^T, A^-1 = L^-T L^-1.
+// Non-positive pivots (only reachable with a numerically singular block) are replaced by a tiny positive number.
+template <typename T, int N> LM_HD void spd_inverse(const T (&A)[N][N], T (&Ai)[N][N]) {
+  T L[N][N], R[N][N];      // R = L^-1 (lower)
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    T s = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    s = s > T(0) ? s : T(1e-30);
+    const T inv = m_rsqrt(s);
+    L[j][j] = s * inv;
+    R[j][j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      T v = A[j][i];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      T v = T(0);
+#pragma unroll
+      for (int k = j; k < i; ++k) v += L[i][k] * R[k][j];
+      R[i][j] = -v * R[i][i];
+    }
+#pragma unroll
+  for (int a = 0; a < N; ++a)
+#pragma unroll
+    for (int b = a; b < N; ++b) {
+      T v = T(0);
+#pragma unroll
+      for (int k = b; k < N; ++k) v += R[k][a] * R[k][b];
+      Ai[a][b] = v; Ai[b][a] = v;
+    }
+}
+template <typename T> LM_HD void sym3_unpack(const T* a, T (&A)[3][3]) {
+  A[0][0] = a[0]; A[0][1] = A[1][0] = a[1]; A[0][2] = A[2][0] = a[2];
+  A[1][1] = a[3]; A[1][2] = A[2][1] = a[4]; A[2][2] = a[5];
+}
+
+
 }  // namespace b200pose

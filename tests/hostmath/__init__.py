@@ -13,7 +13,7 @@ _lib = None
 
 def build():
     src = os.path.join(HERE, "hostmath.cpp")
-    hdrs = [os.path.join(ROOT, "pypose_b200", "csrc", h) for h in ("lie_math.cuh", "lie_ops.cuh", "lm_math.cuh")]
+    hdrs = [os.path.join(ROOT, "pypose_b200", "csrc", h) for h in ("lie_math.cuh", "lie_ops.cuh", "lm_math.cuh", "imu_cov_math.cuh")]
     newest = max(os.path.getmtime(p) for p in [src] + hdrs)
     if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-x", "c++", "-shared", "-fPIC",
@@ -74,3 +74,43 @@ def reproj_rows(poses, pts, pix, cidx):
     lib().hostmath_reproj_rows(int(poses.dtype == np.float64), _vp(poses), _vp(pts), _vp(pix), _vp(cidx), _vp(r), _vp(J),
                                ctypes.c_longlong(m))
     return r, J
+
+
+def spd_inverse(A_packed, k):
+    A = np.ascontiguousarray(A_packed)
+    out = np.empty_like(A)
+    lib().hostmath_spd_inverse(int(A.dtype == np.float64), int(k), _vp(A), _vp(out), ctypes.c_longlong(A.shape[0]))
+    return out
+
+
+def pgo_linearize_w(nodes, Z, ei, ej, W):
+    nodes, Z, W = (np.ascontiguousarray(x) for x in (nodes, Z, W.reshape(-1, 36)))
+    ei, ej = np.ascontiguousarray(ei, dtype=np.int32), np.ascontiguousarray(ej, dtype=np.int32)
+    E = Z.shape[0]
+    M, M0 = np.empty((E, 21), nodes.dtype), np.empty((E, 21), nodes.dtype)
+    u, u0 = np.empty((E, 6), nodes.dtype), np.empty((E, 6), nodes.dtype)
+    lib().hostmath_pgo_linearize_w(int(nodes.dtype == np.float64), _vp(nodes), _vp(Z), _vp(ei), _vp(ej), _vp(W),
+                                   ctypes.c_longlong(36 if W.shape[0] == E and E > 1 else 0), _vp(M), _vp(u), _vp(M0), _vp(u0),
+                                   ctypes.c_longlong(E))
+    return M, u, M0, u0
+
+
+def ba_rows(poses, points, cidx, pidx):
+    poses, points = np.ascontiguousarray(poses), np.ascontiguousarray(points)
+    cidx, pidx = np.ascontiguousarray(cidx, dtype=np.int32), np.ascontiguousarray(pidx, dtype=np.int32)
+    m = cidx.shape[0]
+    Jc, Jp = np.empty((m, 12), poses.dtype), np.empty((m, 6), poses.dtype)
+    lib().hostmath_ba_rows(int(poses.dtype == np.float64), _vp(poses), _vp(points), _vp(cidx), _vp(pidx), _vp(Jc), _vp(Jp),
+                           ctypes.c_longlong(m))
+    return Jc, Jp
+
+
+def imu_cov(Rk, Rij, a, dt, gcov, acov, init_cov, chunk):
+    """One trajectory: Rk, Rij (F,4), a (F,3), dt (F,1), gcov / acov (1|F,3), init_cov (9,9) -> (9,9)."""
+    Rk, Rij, a, dt, gcov, acov, init_cov = (np.ascontiguousarray(x) for x in (Rk, Rij, a, dt, gcov, acov, init_cov))
+    F = dt.shape[0]
+    cov = np.empty((9, 9), Rk.dtype)
+    lib().hostmath_imu_cov(int(Rk.dtype == np.float64), _vp(Rk), _vp(Rij), _vp(a), _vp(dt), _vp(gcov), _vp(acov),
+                           ctypes.c_longlong(3 if gcov.shape[0] == F and F > 1 else 0), _vp(init_cov), _vp(cov),
+                           ctypes.c_longlong(F), ctypes.c_longlong(chunk))
+    return cov

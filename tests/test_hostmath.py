@@ -122,3 +122,66 @@ def test_lm_pgo_and_reproj_functors(golden_lm, dt, tol):
     r, J = hostmath.reproj_rows(poses.astype(dt), pts.astype(dt), pix.astype(dt), cidx)
     assert np.abs(r - L.reproj_residual(poses, pts, pix, cidx)).max() <= tol
     assert np.abs(J - L.reproj_jac_rows(poses, pts, cidx)).max() <= tol * 10
+
+
+# ---- device math added with the device-resident PCG and the structured IMU covariance, checked on the CPU ----
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-10), (np.float32, 2e-3)], ids=["f64", "f32"])
+def test_spd_inverse_of_packed_blocks(dt, tol):
+    rng = np.random.default_rng(3)
+    for k in (6, 3):
+        B = rng.standard_normal((300, k, k + 2))
+        A = B @ B.transpose(0, 2, 1) + 0.1 * np.eye(k)
+        iu = np.triu_indices(k)
+        Ai = hostmath.spd_inverse(A[:, iu[0], iu[1]].astype(dt), k)
+        full = np.zeros((300, k, k))
+        full[:, iu[0], iu[1]] = Ai
+        full[:, iu[1], iu[0]] = Ai
+        assert np.abs(full @ A - np.eye(k)).max() <= tol * np.linalg.cond(A).max() ** 0.5
+
+
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-10), (np.float32, 2e-4)], ids=["f64", "f32"])
+def test_lm_pgo_weighted_functor(golden_lm, dt, tol):
+    from oracle import lm_oracle as L
+    g = golden_lm
+    nodes, edges, Z, W = g["pgo/nodes0"].astype(dt), g["pgo/edges"], g["pgo/Z"].astype(dt), g["pgo_w/infos"].astype(dt)
+    for Wc in (W, W[3:4]):
+        outs = hostmath.pgo_linearize_w(nodes, Z, edges[:, 0], edges[:, 1], Wc)
+        outs_o = L.pgo_linearize(nodes.astype(np.float64), Z.astype(np.float64), edges[:, 0], edges[:, 1], W=Wc.astype(np.float64))
+        for a, b in zip(outs, outs_o[:4]):
+            assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-11), (np.float32, 2e-5)], ids=["f64", "f32"])
+def test_ba_rows_rebuilt_from_camera_frame_point(golden_lm, dt, tol):
+    """pcg.cu obs_rows: both Jacobian row pairs from y = T p and the camera quaternion alone."""
+    from oracle import lm_oracle as L
+    g = golden_lm
+    poses, points, cidx, pidx = g["ba/poses0"], g["ba/points0"], g["ba/cidx"], g["ba/pidx"]
+    Jc, Jp = hostmath.ba_rows(poses.astype(dt), points.astype(dt), cidx, pidx)
+    Jc_o, Jp_o = L.ba_jac_rows(poses, points, cidx, pidx)
+    assert np.abs(Jc.reshape(-1, 2, 6) - Jc_o).max() <= tol * max(1.0, np.abs(Jc_o).max())
+    assert np.abs(Jp.reshape(-1, 2, 3) - Jp_o).max() <= tol * max(1.0, np.abs(Jp_o).max())
+
+
+@pytest.mark.parametrize("F,chunk", [(37, 8), (200, 16), (64, 64), (130, 1000)])
+def test_structured_imu_covariance_vs_dense_oracle(F, chunk):
+    """imu_cov_math.cuh (28-number block-triangular products, 45-number symmetric accumulator, chunked three-pass
+    order of scan.cu) against the dense 9x9 restatement of imu_preintegrator.py:428-465."""
+    from oracle import scan_oracle as S
+    rng = np.random.default_rng(F)
+    Rk = O.exp("SO3", 0.05 * rng.standard_normal((1, F, 3)).reshape(-1, 3)).reshape(1, F, 4)
+    Rk[0, 3] = [0.0, 0.0, 0.0, 1.0]                                   # an exact identity increment (theta <= eps branch)
+    Rij = rand_group_so3(rng, F).reshape(1, F, 4)
+    a = rng.standard_normal((1, F, 3))
+    dt = rng.uniform(0.002, 0.02, (1, F, 1))
+    init = rng.standard_normal((9, 9)); init = init @ init.T * 1e-3
+    for per_sample in (False, True):
+        n = F if per_sample else 1
+        gc, ac = rng.uniform(1e-5, 1e-4, (1, n, 3)), rng.uniform(1e-3, 1e-2, (1, n, 3))
+        ref = S.imu_cov(Rk, Rij, a, dt, gc, ac, init[None])[0]
+        got = hostmath.imu_cov(Rk[0], Rij[0], a[0], dt[0], gc[0], ac[0], init, chunk)
+        assert np.abs(got - ref).max() <= 1e-12 + 1e-10 * np.abs(ref).max(), (per_sample, np.abs(got - ref).max())
+
+
+def rand_group_so3(rng, n):
+    return O.exp("SO3", rng.standard_normal((n, 3)))
