@@ -193,6 +193,34 @@ def main():
             losses.append(float(opt.step((edges_t, Z_t), weight=W)))
             poses.append(model.nodes.detach().clone().numpy()); rej.append(opt.reject_count)
         g[f"pgo_w/{name}/loss"], g[f"pgo_w/{name}/poses"], g[f"pgo_w/{name}/reject"] = np.array(losses), np.stack(poses), np.array(rej)
+    # robust kernels on the block-sparse families: pose graph with outlier edges and bundle adjustment with outlier pixels
+    # (reference: dense LM, kernel + default FastTriggs corrector, TrustRegion)
+    torch.manual_seed(88)
+    Zo = Z_t.tensor().clone()
+    Zo[::4] = (ref.se3(0.4 * torch.randn(Zo[::4].shape[0], 6, dtype=torch.float64)).Exp() @ ref.SE3(Zo[::4])).tensor()
+    g["pgo_robust/Z"] = Zo.numpy().copy()
+    for kname, kern in (("huber", lambda: ref.optim.kernel.Huber(delta=0.1)), ("cauchy", lambda: ref.optim.kernel.Cauchy(delta=0.2))):
+        model = PoseGraph(ref.SE3(torch.from_numpy(g["pgo/nodes0"].copy())))
+        opt = ref.optim.LM(model, strategy=ref.optim.strategy.TrustRegion(), kernel=kern())
+        losses, poses, rej = [], [], []
+        for _ in range(5):
+            losses.append(float(opt.step((edges_t, ref.SE3(Zo)))))
+            poses.append(model.nodes.detach().clone().numpy()); rej.append(opt.reject_count)
+        g[f"pgo_robust/{kname}/loss"], g[f"pgo_robust/{kname}/poses"], g[f"pgo_robust/{kname}/reject"] = np.array(losses), np.stack(poses), np.array(rej)
+    pixo = torch.from_numpy(g["ba/pix"].copy())
+    pixo[::7] += 0.3 * torch.randn(pixo[::7].shape, dtype=torch.float64)
+    g["ba_robust/pix"] = pixo.numpy().copy()
+    cb_t, pb_t = torch.from_numpy(g["ba/cidx"]), torch.from_numpy(g["ba/pidx"])
+    for kname, kern in (("huber", lambda: ref.optim.kernel.Huber(delta=0.05)),):
+        model = BA(ref.SE3(torch.from_numpy(g["ba/poses0"].copy())), torch.from_numpy(g["ba/points0"].copy()))
+        opt = ref.optim.LM(model, strategy=ref.optim.strategy.TrustRegion(), kernel=kern())
+        losses, poses, points, rej = [], [], [], []
+        for _ in range(5):
+            losses.append(float(opt.step((pixo, cb_t, pb_t))))
+            poses.append(model.poses.detach().clone().numpy()); points.append(model.points_3d.detach().clone().numpy())
+            rej.append(opt.reject_count)
+        g[f"ba_robust/{kname}/loss"], g[f"ba_robust/{kname}/poses"] = np.array(losses), np.stack(poses)
+        g[f"ba_robust/{kname}/points"], g[f"ba_robust/{kname}/reject"] = np.stack(points), np.array(rej)
     np.savez_compressed(OUT, **g)
     print("wrote", OUT, {k: (v if v.ndim == 1 and v.size <= 4 else v.shape) for k, v in g.items() if "loss" in k or "reject" in k})
 

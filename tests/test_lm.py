@@ -496,3 +496,37 @@ def test_gauss_newton_structured_route_equals_generic_pinv():
     np.testing.assert_allclose(traj["structured"][0], traj["generic"][0], rtol=1e-6, atol=1e-24)
     assert (traj["structured"][1] - traj["generic"][1]).abs().max().item() < 1e-9
     assert traj["structured"][0][-1] < 1e-20
+
+
+@pytest.mark.parametrize("kname,kern", [("huber", lambda: pp.optim.kernel.Huber(delta=0.1)),
+                                        ("cauchy", lambda: pp.optim.kernel.Cauchy(delta=0.2))])
+def test_lm_pgo_robust_kernels_match_reference(golden_lm, kname, kern):
+    """Pose graph with outlier edges, robust kernel + FastTriggs fused into the per-edge blocks, block-Jacobi PCG
+    (tol 1e-13) vs the reference's dense LM with the same kernel."""
+    g = golden_lm
+    net = pp.module.PoseGraph(pp.SE3(torch.from_numpy(g["pgo/nodes0"].copy())))
+    inp = (torch.from_numpy(g["pgo/edges"]), pp.SE3(torch.from_numpy(g["pgo_robust/Z"].copy())))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), kernel=kern(), solver=pp.optim.solver.PCG(tol=1e-13), sparse=True)
+    for k in range(5):
+        loss = opt.step(inp)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g[f"pgo_robust/{kname}/loss"][k], rtol=1e-6)
+        np.testing.assert_allclose(net.nodes.detach().numpy(), g[f"pgo_robust/{kname}/poses"][k], atol=5e-7)
+        assert opt.reject_count == g[f"pgo_robust/{kname}/reject"][k]
+
+
+def test_lm_bundle_adjustment_huber_matches_reference(golden_lm):
+    """Bundle adjustment with outlier pixels and a Huber kernel: Schur PCG route vs the reference's dense LM,
+    including the step with five rejected trials."""
+    g = golden_lm
+    net = pp.module.BundleAdjustment(pp.SE3(torch.from_numpy(g["ba/poses0"].copy())), torch.from_numpy(g["ba/points0"].copy()))
+    inp = (torch.from_numpy(g["ba_robust/pix"].copy()), torch.from_numpy(g["ba/cidx"]), torch.from_numpy(g["ba/pidx"]))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), kernel=pp.optim.kernel.Huber(delta=0.05),
+                      solver=pp.optim.solver.PCG(tol=1e-13), sparse=True)
+    for k in range(5):
+        loss = opt.step(inp)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g["ba_robust/huber/loss"][k], rtol=1e-5)
+        np.testing.assert_allclose(net.poses.detach().numpy(), g["ba_robust/huber/poses"][k], atol=2e-6)
+        np.testing.assert_allclose(net.points_3d.detach().numpy(), g["ba_robust/huber/points"][k], atol=2e-6)
+        assert opt.reject_count == g["ba_robust/huber/reject"][k]

@@ -561,3 +561,34 @@ def test_lm_pgo_deterministic_gather_route(golden_lm, monkeypatch):
             np.testing.assert_allclose(net.nodes.detach().cpu().numpy(), g["pgo/trustregion/poses"][k], atol=1e-7)
         finals.append(net.nodes.detach().clone())
     assert torch.equal(finals[0], finals[1])
+
+
+@pytest.mark.parametrize("kname,kern", [("huber", lambda: pp.optim.kernel.Huber(delta=0.1)),
+                                        ("cauchy", lambda: pp.optim.kernel.Cauchy(delta=0.2))])
+def test_lm_pgo_robust_kernels_reference_trajectory_on_gpu(golden_lm, kname, kern):
+    g = golden_lm
+    net = pp.module.PoseGraph(pp.SE3(torch.from_numpy(g["pgo/nodes0"].copy()).cuda()))
+    inp = (torch.from_numpy(g["pgo/edges"]).cuda(), pp.SE3(torch.from_numpy(g["pgo_robust/Z"].copy()).cuda()))
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), kernel=kern(), solver=pp.optim.solver.PCG(tol=1e-13), sparse=True)
+    for k in range(5):
+        loss = opt.step(inp)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g[f"pgo_robust/{kname}/loss"][k], rtol=1e-6)
+        np.testing.assert_allclose(net.nodes.detach().cpu().numpy(), g[f"pgo_robust/{kname}/poses"][k], atol=5e-7)
+        assert opt.reject_count == g[f"pgo_robust/{kname}/reject"][k]
+
+
+def test_lm_bundle_adjustment_huber_reference_trajectory_on_gpu(golden_lm):
+    g = golden_lm
+    net = pp.module.BundleAdjustment(pp.SE3(torch.from_numpy(g["ba/poses0"].copy()).cuda()),
+                                     torch.from_numpy(g["ba/points0"].copy()).cuda())
+    inp = (torch.from_numpy(g["ba_robust/pix"].copy()).cuda(), torch.from_numpy(g["ba/cidx"]).cuda(), torch.from_numpy(g["ba/pidx"]).cuda())
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), kernel=pp.optim.kernel.Huber(delta=0.05),
+                      solver=pp.optim.solver.PCG(tol=1e-13), sparse=True)
+    for k in range(5):
+        loss = opt.step(inp)
+        assert opt._problem is not None
+        np.testing.assert_allclose(float(loss), g["ba_robust/huber/loss"][k], rtol=1e-5)
+        np.testing.assert_allclose(net.poses.detach().cpu().numpy(), g["ba_robust/huber/poses"][k], atol=2e-6)
+        np.testing.assert_allclose(net.points_3d.detach().cpu().numpy(), g["ba_robust/huber/points"][k], atol=2e-6)
+        assert opt.reject_count == g["ba_robust/huber/reject"][k]
