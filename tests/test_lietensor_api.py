@@ -157,3 +157,44 @@ def test_geodesic_loss_matches_trace_formula():
     torch.testing.assert_close(e1, e2, rtol=1e-9, atol=1e-9)
     torch.testing.assert_close(pp.geodesic_loss(x, y), e2.mean())
     torch.testing.assert_close(pp.geodesic_loss(x, y, reduction='sum'), e2.sum())
+
+
+# ---- splines (reference: pypose/function/spline.py; goldens: oracle/make_golden_spline.py) ----
+def _spline_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spline.npz"))
+
+
+def test_bspline_matches_reference_goldens():
+    g = _spline_golden()
+    poses = pp.SE3(torch.from_numpy(g["bspline/poses"].copy()))
+    for name, interval, ext in (("i02", 0.2, False), ("i03x", 0.3, True), ("i05", 0.5, False), ("i01x", 0.1, True)):
+        out = pp.bspline(poses, interval, ext)
+        assert isinstance(out, pp.LieTensor) and out.ltype == pp.SE3_type
+        np.testing.assert_allclose(out.tensor().numpy(), g[f"bspline/{name}"], rtol=0, atol=1e-12)
+    two = pp.SE3(torch.from_numpy(g["bspline/two"].copy()))
+    np.testing.assert_allclose(pp.bspline(two, 0.1, True).tensor().numpy(), g["bspline/two_i01x"], rtol=0, atol=1e-12)
+
+
+def test_bspline_properties_of_the_reference_tests():
+    """tests/function/test_spline.py: sample counts, and with extrapolation the curve starts / ends at the data."""
+    torch.manual_seed(3)
+    data = pp.randn_SE3(2, 3, 6, dtype=torch.float64)
+    for interval, k in ((0.5, 2), (0.2, 5), (0.3, 4)):
+        assert pp.bspline(data, interval).lshape[-1] == k * (data.lshape[-1] - 3) + 1
+        ends = pp.bspline(data, interval, True)[..., [0, -1], :]
+        pp.testing.assert_close(ends, data[..., [0, -1], :])
+    with pytest.raises(AssertionError):
+        pp.bspline(pp.randn_SE3(3), 0.1)              # fewer than four poses without extrapolation
+    with pytest.raises(AssertionError):
+        pp.bspline(pp.randn_SO3(5), 0.1)              # SE3 only
+
+
+def test_chspline_matches_reference_goldens_and_interpolates():
+    g = _spline_golden()
+    pts = torch.from_numpy(g["chspline/points"].copy())
+    for name, interval in (("i01", 0.1), ("i04", 0.4), ("i05", 0.5)):
+        out = pp.chspline(pts, interval=interval)
+        np.testing.assert_allclose(out.numpy(), g[f"chspline/{name}"], rtol=0, atol=1e-12)
+        k = int(np.ceil(1.0 / interval))
+        torch.testing.assert_close(out[..., ::k, :], pts)          # passes through the data points

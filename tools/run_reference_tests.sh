@@ -8,6 +8,6 @@ set -e
 D=$(mktemp -d)
 cp /root/repo/tools/conformance_conftest.py $D/conftest.py
 cp -r /root/reference/tests/lietensor /root/reference/tests/basics /root/reference/tests/optim $D/
-mkdir -p $D/module && cp /root/reference/tests/module/test_loss.py $D/module/
-cd $D && PYTHONDONTWRITEBYTECODE=1 python -m pytest lietensor basics optim module -q -p no:cacheprovider \
+mkdir -p $D/module $D/function && cp /root/reference/tests/module/test_loss.py $D/module/ && cp /root/reference/tests/function/test_spline.py /root/reference/tests/function/test_checking.py $D/function/
+cd $D && PYTHONDONTWRITEBYTECODE=1 python -m pytest lietensor basics optim module function -q -p no:cacheprovider \
     --deselect optim/test_sparse_lm.py --deselect lietensor/test_lietensor.py::test_parameter_dispatch "$@"
