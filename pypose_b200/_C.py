@@ -106,6 +106,9 @@ def launch_rows(base, ins, out_widths):
     x0 = ins[0]
     if not x0.is_cuda:
         raise B200PoseError(f"{base}: expected CUDA tensors (no CPU path), got device {x0.device}")
+    for t in ins[1:]:       # every operand reaches the kernel as a raw pointer: same device and dtype or a clean error
+        if t.device != x0.device or t.dtype != x0.dtype:
+            raise B200PoseError(f"{base}: all operands must be on {x0.device} with dtype {x0.dtype}, got {t.device} / {t.dtype}")
     n = x0.shape[0]
     sym = f"{base}_{suffix(x0.dtype)}"
     outs = [torch.empty((n, w), dtype=x0.dtype, device=x0.device) for w in out_widths]

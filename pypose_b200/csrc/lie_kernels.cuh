@@ -244,6 +244,12 @@ __global__ void __launch_bounds__(THREADS) stream_kernel_tma(StreamParams<typena
   if (tid == 0) bulk_wait_all();
 }
 
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 struct DeviceInfo { int sms; };
 inline const DeviceInfo& device_info() {
   static thread_local int cached_dev = -1;
@@ -265,7 +271,9 @@ int launch_stream_ept(const typename Op::T* const* in, typename Op::T* const* ou
                                 (Op::NOUT > 1 ? Op::DO1 : 0));
   constexpr int smem = words * (int)sizeof(T);
   auto kern = stream_kernel<Op, EPT>;
-  static thread_local int occ = 0;
+  // the dynamic-smem attribute is per device: cache the occupancy per (kernel instantiation, device)
+  static thread_local int occ_dev[kMaxDevices] = {};
+  int& occ = occ_dev[current_device_slot()];
   if (occ == 0) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem);
@@ -310,7 +318,8 @@ int launch_stream_tma(const typename Op::T* const* in, typename Op::T* const* ou
   using T = typename Op::T;
   using L = TmaLayout<Op, S, OS, THREADS, EPT>;
   auto kern = stream_kernel_tma<Op, S, OS, THREADS, EPT>;
-  static thread_local int occ = 0;
+  static thread_local int occ_dev[kMaxDevices] = {};
+  int& occ = occ_dev[current_device_slot()];
   if (occ == 0) {
     if (L::BYTES > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, L::BYTES);

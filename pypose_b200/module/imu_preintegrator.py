@@ -12,6 +12,20 @@ from torch import nn
 from ..lietensor import LieTensor, SO3, identity_SO3, so3, vec2skew
 
 
+def _needs_grad(*objs):
+    """True when autograd has to see through the integration: the fused scan kernels have no backward, so a call
+    with any differentiable signal / state takes the op-by-op LieTensor route (every op there has a backward kernel)."""
+    if not torch.is_grad_enabled():
+        return False
+    for o in objs:
+        if isinstance(o, dict):
+            if _needs_grad(*o.values()):
+                return True
+        elif torch.is_tensor(o) and o.requires_grad:
+            return True
+    return False
+
+
 class IMUPreintegrator(nn.Module):
     def __init__(self, pos=torch.zeros(3), rot=identity_SO3(), vel=torch.zeros(3), gravity=9.81007,
                  gyro_cov=(3.2e-3) ** 2, acc_cov=(8e-2) ** 2, prop_cov=True, reset=False):
@@ -48,12 +62,14 @@ class IMUPreintegrator(nn.Module):
         B = dt.shape[0]
         if init_state is None:
             init_state = {'pos': self.pos, 'rot': self.rot, 'vel': self.vel}
+        if _needs_grad(dt, gyro, acc, rot, init_state):
+            return self._forward_differentiable(dt, gyro, acc, rot, gyro_cov, acc_cov, init_state)
         if not self.prop_cov:
             # integrate + predict fused: nothing but the predicted states leaves the kernel
             rot_t = rot.tensor() if isinstance(rot, LieTensor) else None
             r, v, p = torch.ops.b200pose.imu_predict(
                 dt, gyro.to(dt.dtype), acc.to(dt.dtype), rot_t, init_state['rot'].tensor(), init_state['pos'],
-                init_state['vel'], [0.0, 0.0, self._g])
+                init_state['vel'], self._gvec())
             predict = {'rot': SO3(r), 'vel': v, 'pos': p}
             if not self.reset:
                 self.pos, self.rot, self.vel = p[..., -1:, :], predict['rot'][..., -1:, :], v[..., -1:, :]
@@ -64,7 +80,7 @@ class IMUPreintegrator(nn.Module):
         rot_t = rot.tensor() if isinstance(rot, LieTensor) else None
         a, Dp, Dv, Dr, Dt, w, r, v, p = torch.ops.b200pose.imu_full(
             dt, gyro.to(dt.dtype), acc.to(dt.dtype), rot_t, init_state['rot'].tensor(), init_state['pos'],
-            init_state['vel'], [0.0, 0.0, self._g])
+            init_state['vel'], self._gvec())
         inte = {'a': a, 'Dp': Dp, 'Dv': Dv, 'Dr': SO3(Dr), 'Dt': Dt, 'w': SO3(w)}
         predict = {'rot': SO3(r), 'vel': v, 'pos': p}
         if self.prop_cov:
@@ -89,13 +105,66 @@ class IMUPreintegrator(nn.Module):
             self.Rij = Rij[..., -1:, :]
         return {**predict, **cov}
 
+    def _gvec(self):
+        """Gravity as the kernels take it (three host floats), read from the `gravity` buffer so that a user who
+        replaces / moves the buffer is honoured; the host copy is refreshed only when the buffer changes."""
+        g = self.gravity
+        key = (g.data_ptr(), g._version, g.device)
+        if getattr(self, '_gkey', None) != key:
+            self._gkey, self._ghost = key, [float(v) for v in g.detach().reshape(-1)[-3:].tolist()]
+        return self._ghost
+
+    def _forward_differentiable(self, dt, gyro, acc, rot, gyro_cov, acc_cov, init_state):
+        """The same outputs through differentiable LieTensor ops (autograd reaches dt / gyro / acc / rot / init_state,
+        e.g. the IMU-corrector training of the reference's examples); the covariance sees detached inputs exactly
+        like imu_preintegrator.py:291-296."""
+        B = dt.shape[0]
+        inte = self._integrate_ops(dt, gyro, acc, rot, init_state['rot'])
+        predict = self.predict(init_state, inte)
+        cov, Rij = {'cov': None}, None
+        if self.prop_cov:
+            gyro_cov = self.gyro_cov.repeat([B, 1, 1]) if gyro_cov is None else gyro_cov
+            acc_cov = self.acc_cov.repeat([B, 1, 1]) if acc_cov is None else acc_cov
+            init_cov = self.cov.expand(B, 9, 9) if init_state.get('cov') is None else init_state['cov']
+            Rij = init_state['Rij'] if 'Rij' in init_state else self.Rij
+            Rij = Rij * inte['Dr'] if Rij is not None else inte['Dr']
+            cov = {'cov': torch.ops.b200pose.imu_cov(inte['w'].tensor().detach(), Rij.tensor().detach(), inte['a'].detach(),
+                                                     dt.detach(), gyro_cov, acc_cov, init_cov),
+                   'Rij': Rij[..., -1:, :]}
+        if not self.reset:
+            self.pos, self.rot, self.vel = predict['pos'][..., -1:, :], predict['rot'][..., -1:, :], predict['vel'][..., -1:, :]
+            self.cov = cov['cov']
+            self.Rij = Rij[..., -1:, :] if Rij is not None else None
+        return {**predict, **cov}
+
+    def _integrate_ops(self, dt, gyro, acc, rot, init_rot):
+        """imu_preintegrator.py:360-384 with LieTensor ops: rotation increments by an SO3 product scan, gravity removed
+        with R_{k+1} (or the known `rot`), velocity / position increments by prefix sums."""
+        B, F = dt.shape[:2]
+        kw = {'dtype': dt.dtype, 'device': dt.device}
+        gravity = self.gravity.to(**kw)
+        w = so3(gyro * dt).Exp()
+        R = torch.cat([identity_SO3(B, 1, **kw), w], dim=1).cumprod(dim=1, left=False)          # R_0 .. R_F
+        if isinstance(rot, LieTensor):
+            a = acc - rot.Inv() @ gravity
+        else:
+            init_rot = identity_SO3(B, 1, **kw) if init_rot is None else init_rot
+            a = acc - (init_rot * R)[:, 1:, :].Inv() @ gravity
+        Ra = R[:, :F, :] @ a
+        zero3 = torch.zeros(B, 1, 3, **kw)
+        V = torch.cumsum(torch.cat([zero3, Ra * dt], dim=1), dim=1)                               # Dv_0 .. Dv_F
+        Pm = torch.cumsum(torch.cat([zero3, V[:, :F, :] * dt + Ra * (0.5 * dt ** 2)], dim=1), dim=1)
+        return {'a': a, 'Dp': Pm[:, 1:, :], 'Dv': V[:, 1:, :], 'Dr': R[:, 1:, :], 'Dt': torch.cumsum(dt, dim=1), 'w': w}
+
     def integrate(self, dt, gyro, acc, rot: SO3 = None, init_rot: SO3 = None):
         """Fused preintegration: returns a, Dp, Dv, Dr, Dt, w exactly as imu_preintegrator.py:383-384."""
         dtype = dt.dtype
+        if _needs_grad(dt, gyro, acc, rot, init_rot):
+            return self._integrate_ops(dt, gyro.to(dtype), acc.to(dtype), rot, init_rot)
         rot_t = rot.tensor() if isinstance(rot, LieTensor) else None
         init_t = init_rot.tensor() if (rot_t is None and init_rot is not None) else None
         a, Dp, Dv, Dr, Dt, w = torch.ops.b200pose.imu_integrate(
-            dt, gyro.to(dtype), acc.to(dtype), rot_t, init_t, [0.0, 0.0, self._g])
+            dt, gyro.to(dtype), acc.to(dtype), rot_t, init_t, self._gvec())
         return {'a': a, 'Dp': Dp, 'Dv': Dv, 'Dr': SO3(Dr), 'Dt': Dt, 'w': SO3(w)}
 
     @classmethod

@@ -49,7 +49,8 @@ def _same(*ts):
     dt, dev = ts[0].dtype, ts[0].device
     for t in ts:
         if t.dtype != dt or t.device != dev:
-            raise TypeError("b200pose LM ops need one dtype/device for all floating inputs")
+            raise TypeError(f"b200pose LM ops need one dtype/device for all floating inputs (got {t.dtype} on {t.device}, "
+                            f"expected {dt} on {dev})")
     return [t.contiguous() for t in ts]
 
 

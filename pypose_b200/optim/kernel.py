@@ -21,8 +21,12 @@ class Huber(nn.Module):
 
     def forward(self, input: Tensor) -> Tensor:
         _nonneg(input)
-        root = input.sqrt()
-        return torch.where(root < self.delta, input, 2 * self.delta * root - self.delta2)
+        # sqrt only on the outer branch: d sqrt / d s is inf at s = 0 and torch.where would turn the unselected
+        # branch's 0 * inf into NaN in the backward (FastTriggs differentiates this kernel); rho'(0) = 1 like the
+        # reference's masked assignment (kernel.py:38-44)
+        inner = input < self.delta2
+        root = torch.where(inner, torch.ones_like(input), input).sqrt()
+        return torch.where(inner, input, 2 * self.delta * root - self.delta2)
 
 
 class PseudoHuber(nn.Module):

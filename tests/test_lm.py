@@ -530,3 +530,75 @@ def test_lm_bundle_adjustment_huber_matches_reference(golden_lm):
         np.testing.assert_allclose(net.poses.detach().numpy(), g["ba_robust/huber/poses"][k], atol=2e-6)
         np.testing.assert_allclose(net.points_3d.detach().numpy(), g["ba_robust/huber/points"][k], atol=2e-6)
         assert opt.reject_count == g["ba_robust/huber/reject"][k]
+
+
+def test_huber_fasttriggs_zero_residual_row_is_finite():
+    """an exactly zero residual row under Huber + FastTriggs must not poison R / J with NaN (the
+    reference's masked assignment gives rho'(0) = 1, kernel.py:38-44 / corrector.py:73-95)."""
+    R = torch.tensor([[0.0, 0.0], [0.3, -0.4], [3.0, 4.0]], dtype=torch.float64)
+    J = torch.arange(6 * 5, dtype=torch.float64).reshape(6, 5) / 7
+    for k in (pp.optim.kernel.Huber(1.0), pp.optim.kernel.PseudoHuber(1.0), pp.optim.kernel.Cauchy(1.0),
+              pp.optim.kernel.SoftLOne(1.0), pp.optim.kernel.Arctan(1.0)):
+        Rc, Jc = pp.optim.corrector.FastTriggs(k)(R=R.clone(), J=J.clone())
+        assert torch.isfinite(Rc).all() and torch.isfinite(Jc).all(), type(k).__name__
+    Rc, Jc = pp.optim.corrector.FastTriggs(pp.optim.kernel.Huber(1.0))(R=R.clone(), J=J.clone())
+    torch.testing.assert_close(Rc[:2], R[:2])                       # inliers (and the zero row): rho' = 1
+    torch.testing.assert_close(Rc[2], R[2] * (1.0 / 5.0) ** 0.5)     # rho'(25) = delta / sqrt(s) = 1/5
+    # and end to end: a generic-route LM step on a model with a zero residual row keeps the parameters finite
+    class Lin(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = nn.Parameter(torch.tensor([1.0, 2.0], dtype=torch.float64))
+
+        def forward(self, x):
+            return x * self.w
+    net = Lin()
+    x = torch.tensor([[0.0, 0.0], [1.0, 1.0]], dtype=torch.float64)
+    opt = pp.optim.LM(net, kernel=pp.optim.kernel.Huber(1.0))
+    opt.step(x)
+    assert torch.isfinite(net.w).all()
+
+
+def test_recognition_needs_row_wise_agreement_not_one_scalar(golden_lm):
+    """same sum of squares at the start (rows rolled; all-zero residuals; a subclass overriding forward) must
+    not reach the fused kernels — the module is verified row by row at the current AND at perturbed parameters."""
+    g = golden_lm
+    t = lambda k: torch.from_numpy(g[k].copy())
+
+    class RolledReproj(UserOneParamReproj):            # identical norm, different residual <-> parameter coupling
+        def forward(self, points, pixels, cidx):
+            return super().forward(points, pixels, cidx).roll(1, 0)
+
+    inp = (t("reproj/pts"), t("reproj/pix"), t("reproj/cidx"))
+    opt = pp.optim.LM(RolledReproj(pp.SE3(t("reproj/poses0"))), strategy=STRATS["trustregion"]())
+    opt.step(inp)
+    assert opt._problem is None
+
+    class ZeroAtStart(nn.Module):                      # 0 == 0 at the initial point, unrelated elsewhere
+        def __init__(self, poses):
+            super().__init__()
+            self.poses = pp.Parameter(poses)
+            self.register_buffer("start", poses.tensor().clone())
+
+        def forward(self, points, pixels, cidx):
+            d = (self.poses.tensor() - self.start)[cidx]
+            return d[:, :2] * points[:, :2]
+
+    P0 = pp.SE3(t("reproj/poses0"))
+    net = ZeroAtStart(P0)
+    y = P0[inp[2]].Act(inp[0])
+    exact = (inp[0], -y[..., :2] / y[..., 2:], inp[2])  # pixels that make the reprojection residual exactly zero too
+    opt = pp.optim.LM(net, strategy=STRATS["trustregion"]())
+    opt.step(exact)
+    assert opt._problem is None
+    torch.testing.assert_close(net.poses.tensor(), P0.tensor())          # verification restored the parameters (and a zero
+    #                                                                      residual gives a zero step)
+
+    class Overridden(pp.module.PoseGraph):             # subclass of a built-in module with another forward
+        def forward(self, edges, poses):
+            return 2.0 * super().forward(edges, poses)
+
+    net = Overridden(pp.SE3(t("pgo/nodes0")))
+    opt = pp.optim.LM(net, solver=pp.optim.solver.PCG(tol=1e-12), sparse=True)
+    opt.step((t("pgo/edges"), pp.SE3(t("pgo/Z"))))
+    assert opt._problem is None

@@ -1,4 +1,6 @@
 """Scans and IMU preintegration: oracle pinned to the reference goldens; host logic on CPU; kernels on GPU."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -192,3 +194,48 @@ def test_imu_config4_with_covariance_runs_at_full_size():
     ref = S.imu_cov(w, Dr, a_, dt[:2].cpu().numpy(), gcv.astype(np.float32).astype(np.float64), acv.astype(np.float32).astype(np.float64),
                     np.zeros((1, 9, 9)))
     assert np.abs(cov[:2].cpu().numpy() - ref).max() <= 1e-8 * np.abs(ref).max()
+
+
+def _check_imu_gradients(dev, tol):
+    """the integrator is differentiable in the signals and the initial state like the reference
+    (goldens: oracle/make_golden_imu_grad.py, reference fp64)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "scan_imu.npz"))
+    gg = np.load(os.path.join(os.path.dirname(__file__), "golden", "imu_grad.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    for tag in ("free", "rot"):
+        for cov in (False, True):
+            dt, gyro, acc = (t(k).requires_grad_() for k in ("imu/dt", "imu/gyro", "imu/acc"))
+            pos, vel = t("imu/init_pos").requires_grad_(), t("imu/init_vel").requires_grad_()
+            init = {"pos": pos, "rot": pp.SO3(t("imu/init_rot")), "vel": vel}
+            kw = {"rot": pp.SO3(t("imu/rot"))} if tag == "rot" else {}
+            m = pp.module.IMUPreintegrator(prop_cov=cov, reset=True).double().to(dev)
+            out = m(dt, gyro, acc, init_state=init, **kw)
+            s = (out["pos"] ** 2).sum() + (out["vel"] ** 2).sum() + (out["rot"].Log().tensor() ** 2).sum()
+            s.backward()
+            key = f"{tag}/{'cov' if cov else 'nocov'}"
+            np.testing.assert_allclose(float(s), gg[f"{key}/scalar"], rtol=tol)
+            for name, v in (("dt", dt), ("gyro", gyro), ("acc", acc), ("pos", pos), ("vel", vel)):
+                ref = gg[f"{key}/grad_{name}"]
+                np.testing.assert_allclose(v.grad.cpu().numpy(), ref, atol=tol * (1 + np.abs(ref).max()), err_msg=f"{key}/{name}")
+            # integrate() alone is differentiable too
+            d = m.integrate(dt, gyro, acc, init_rot=init["rot"], **kw)
+            assert d["Dp"].requires_grad and d["Dr"].requires_grad
+
+
+def test_imu_gradients_cpu():
+    _check_imu_gradients("cpu", 1e-9)
+
+
+@pytest.mark.gpu
+def test_imu_gradients_gpu():
+    _check_imu_gradients("cuda", 1e-9)
+
+
+def test_imu_gravity_buffer_is_honoured():
+    m = pp.module.IMUPreintegrator(prop_cov=False, reset=True).double()
+    dt = torch.full((1, 5, 1), 0.01, dtype=torch.float64)
+    z = torch.zeros(1, 5, 3, dtype=torch.float64)
+    a = m(dt, z, z)["vel"][0, -1]
+    m.gravity = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64)
+    b = m(dt, z, z)["vel"][0, -1]
+    assert abs(float(a[2]) + 0.05 * 9.81007) < 1e-6 and abs(float(b[2]) + 0.05) < 1e-12
