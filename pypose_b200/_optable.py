@@ -152,16 +152,6 @@ LM_OPS = [
       ("int", "robust", ""), ("double", "delta", "")],
      "modjac + J^T J for the two-parameter reprojection model, README.md:163-198; sparse counterpart "
      "bae.autograd.graph.jacobian, optimizer.py:637-642"),
-    ("b200_lm_ba_linearize_y",
-     [("const REAL*", "poses", "(C,7)"), ("const REAL*", "points", "(P,3)"), ("const REAL*", "pix", "(m,2)"),
-      ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
-      ("REAL*", "Y4", "(m,4): camera-frame point y = T p and sqrt(rho') — the PCG kernels rebuild the 2x6 / 2x3 rows from it"),
-      ("const int*", "ppos", "(m) position of each observation in point order, or NULL"),
-      ("REAL*", "Y4p", "(m,4) the same rows in point order (for b200_lm_ba_wtx_gather), or NULL"),
-      ("REAL*", "rs", "(m,2) (scaled) residual"), ("REAL*", "Hcc", "(C,21) accumulated (zero-initialised by the caller)"),
-      ("REAL*", "Hpp", "(P,6) accumulated"), ("REAL*", "gc", "(C,6) accumulated"), ("REAL*", "gp", "(P,3) accumulated"),
-      ("double*", "ws", "ws[0] = sum rho"), ("int", "robust", ""), ("double", "delta", "")],
-     "as b200_lm_ba_linearize, storing 16 B per observation instead of the 72 B of Jacobian rows"),
     ("b200_lm_ba_wtx",
      [("const REAL*", "Jc", "(m,12)"), ("const REAL*", "Jp", "(m,6)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
       ("const REAL*", "x", "(C,6)"), ("REAL*", "t", "(P,3) t += W^T x (atomics)")],
@@ -208,8 +198,9 @@ LM_OPS = [
       ("long long", "E", "edges"), ("const REAL*", "Minv", "(n,21) preconditioner blocks"),
       ("const REAL*", "extra", "(n,6) clamp/damping added to diag H"), ("const REAL*", "g", "(n,6) J^T R; solves (H+extra) x = -g"),
       ("REAL*", "x", "(n,6) solution"), ("REAL*", "r", "(n,6) work"), ("REAL*", "z", "(n,6) work"), ("REAL*", "p", "(n,6) work"),
-      ("REAL*", "q", "(n,6) work"),
-      ("double*", "cg", "(8) state: rz[2], p.Ap, |r|^2, stop^2, done flag, iterations, maxiter"),
+      ("REAL*", "q", "(n,6) work"), ("REAL*", "xbest", "(n,6) copy of the iterate with the smallest |r| so far"),
+      ("double*", "cg", "(16) state: rz[2], p.Ap, |r|^2, stop^2, done (1 converged, 2 breakdown, 3 stagnated, 4 maxiter), "
+                        "iterations, maxiter, best |r|^2, iterations since best, save flag, patience"),
       ("double*", "ws", "reduction workspace"), ("double", "tol", "stop when |r| <= tol |b|"),
       ("long long", "maxiter", ""), ("long long", "first_iter", "0 initialises the state; otherwise continue"),
       ("long long", "iters", "iterations to enqueue (no-ops once the done flag is set)")],
@@ -218,9 +209,14 @@ LM_OPS = [
      [("const REAL*", "Mn", "(2E,21) node-ordered per-edge blocks"), ("const int*", "nother", "(2E) opposite node of each entry"),
       ("const int*", "nptr", "(n+1) offsets per node"), ("const REAL*", "Minv", "(n,21)"), ("const REAL*", "extra", "(n,6)"),
       ("const REAL*", "g", "(n,6)"), ("REAL*", "x", "(n,6)"), ("REAL*", "r", "(n,6)"), ("REAL*", "z", "(n,6)"), ("REAL*", "p", "(n,6)"),
-      ("REAL*", "q", "(n,6)"), ("double*", "cg", "(8) state"), ("double*", "ws", ""), ("double", "tol", ""),
+      ("REAL*", "q", "(n,6)"), ("REAL*", "xbest", "(n,6)"), ("double*", "cg", "(16) state"), ("double*", "ws", ""), ("double", "tol", ""),
       ("long long", "maxiter", ""), ("long long", "first_iter", ""), ("long long", "iters", "")],
      "as b200_lm_pgo_pcg with the H product as a gather over node-ordered blocks: no atomics, bit-reproducible"),
+    ("b200_lm_cg_finish",
+     [("REAL*", "x", "(n,6) in: last iterate; out: the returned solution"), ("const REAL*", "xbest", "(n,6)"),
+      ("const double*", "cg", "(16) state of the finished solve")],
+     "end of CG.forward (solver.py:338-340 `return x`): the last iterate if the solve converged, otherwise the iterate "
+     "with the smallest residual (finite-precision guard, DESIGN.md)"),
     ("b200_lm_pgo_predicted",
      [("const REAL*", "M", "(E,21)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"), ("long long", "E", ""),
       ("const REAL*", "D", "(n,6) step"), ("const REAL*", "g", "(n,6) J^T R"), ("double*", "ws", "ws[0] = D^T H D + 2 D^T g")],
@@ -229,10 +225,6 @@ LM_OPS = [
      [("const REAL*", "M0", "(E,21)"), ("const REAL*", "u0", "(E,6)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
       ("const REAL*", "D", "(N,6) step"), ("double*", "ws", "ws[0] = sum_e d^T M0 d + 2 d^T u0, d = D_j - D_i")],
      "TrustRegion 'predicted' reduction from per-edge blocks, optim/strategy.py:143"),
-    ("b200_lm_ba_schur_diag",
-     [("const REAL*", "Y4", "(m,4) from b200_lm_ba_linearize_y"), ("const REAL*", "poses", "(C,7) the poses it was linearised at"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
-      ("const REAL*", "Hpinv", "(P,6)"), ("REAL*", "Sd", "(C,21) in: damped Hcc; out: minus sum_k W_k Hpp^-1 W_k^T (atomics)")],
-     "diagonal blocks of the reduced camera system (preconditioner of the Schur PCG)"),
     ("b200_lm_ba_wtx_gather",
      [("const REAL*", "Y4p", "(m,4) Y4 reordered so that each point's observations are contiguous"),
       ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx_p", "(m) camera index in the same order"),
@@ -241,29 +233,101 @@ LM_OPS = [
       ("double", "alpha", ""), ("REAL*", "u", "(P,3) alpha * Hpp^-1 (t0 + W^T x), no atomics")],
      "W^T x of the Schur PCG by gather + the point-block solve; with t0 = gp, alpha = -1 the back-substitution "
      "dp = Hpp^-1 (-gp - W^T dc)"),
-    ("b200_lm_ba_wtx_y",
-     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
-      ("const REAL*", "x", "(C,6)"), ("REAL*", "t", "(P,3) t += W^T x (atomics)")],
-     "off-diagonal block product, optim/solver.py:319-336 (rows rebuilt from Y4)"),
-    ("b200_lm_ba_wv_pinv",
-     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
-      ("const REAL*", "Hpinv", "(P,6), or NULL if t already holds Hpp^-1 t"), ("const REAL*", "t", "(P,3)"), ("REAL*", "y", "(C,6) y -= W Hpp^-1 t (warp-aggregated atomics)")],
-     "off-diagonal product of the reduced camera system, optim/solver.py:319-336"),
     ("b200_lm_ba_pcg",
-     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx", "(m)"), ("const int*", "pidx", "(m)"),
+     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "pidx", "(m) camera-sorted"),
+      ("const int*", "cseg", "(C+1) row offsets per camera"), ("long long", "split", "work items per camera"),
+      ("long long", "tpi", "threads per work item: 32 or 128"),
       ("long long", "m", "observations"), ("const REAL*", "Y4p", "(m,4) point-ordered copy of Y4"),
       ("const int*", "cidx_p", "(m) point-ordered camera indices"), ("const int*", "pptr", "(P+1)"), ("const REAL*", "Hc", "(C,21) damped camera blocks"), ("const REAL*", "Hpinv", "(P,6)"),
       ("const REAL*", "Minv", "(C,21) preconditioner blocks"), ("const REAL*", "bneg", "(C,6) minus the right-hand side"),
       ("REAL*", "x", "(C,6) solution"), ("REAL*", "r", "(C,6)"), ("REAL*", "z", "(C,6)"), ("REAL*", "p", "(C,6)"), ("REAL*", "q", "(C,6)"),
-      ("REAL*", "t", "(P,3) work"), ("double*", "cg", "(8) state, see b200_lm_pgo_pcg"), ("double*", "ws", "reduction workspace"),
+      ("REAL*", "t", "(P,3) work"), ("REAL*", "part", "(C*split,6) partial sums, unused when split == 1"),
+      ("REAL*", "xbest", "(C,6)"), ("double*", "cg", "(16) state, see b200_lm_pgo_pcg"), ("double*", "ws", "reduction workspace"),
       ("double", "tol", ""), ("long long", "maxiter", ""), ("long long", "P", "points"), ("long long", "first_iter", ""),
       ("long long", "iters", "")],
-     "PCG on the Schur complement (Hcc - W Hpp^-1 W^T) dc = rhs; optim/solver.py:312-340"),
+     "PCG on the Schur complement (Hcc - W Hpp^-1 W^T) dc = rhs; optim/solver.py:312-340; no atomics (ba.cu)"),
+    ("b200_lm_ba_linearize_seg",
+     [("const REAL*", "poses", "(C,7)"), ("const REAL*", "points", "(P,3)"), ("const REAL*", "pix", "(m,2) camera-sorted"),
+      ("const int*", "pidx", "(m) camera-sorted"), ("const int*", "cseg", "(C+1) row offsets per camera"),
+      ("long long", "split", "work items per camera"), ("long long", "tpi", "threads per work item: 32 or 128"),
+      ("REAL*", "Y4", "(m,4) y = T p and sqrt(rho')"), ("const int*", "ppos", "(m) position in point order, or NULL"),
+      ("REAL*", "Y4p", "(m,4) point-ordered copy, or NULL"), ("REAL*", "rs", "(m,2) (scaled) residual"),
+      ("REAL*", "Hcc", "(C,21) written"), ("REAL*", "gc", "(C,6) written"), ("REAL*", "part", "(C*split,27) or NULL when split == 1"),
+      ("double*", "ws", "ws[0] = sum rho"), ("int", "robust", ""), ("double", "delta", "")],
+     "modjac + J^T J camera blocks for the two-parameter reprojection model (README.md:163-198; optimizer.py:645-656) with "
+     "one writer per camera and a fixed summation order: bit-reproducible"),
+    ("b200_lm_ba_point_blocks",
+     [("const REAL*", "Y4p", "(m,4) point-ordered"), ("const REAL*", "pix_p", "(m,2) point-ordered pixels"),
+      ("const REAL*", "poses", "(C,7)"), ("const int*", "cidx_p", "(m)"), ("const int*", "pptr", "(P+1)"),
+      ("REAL*", "Hpp", "(P,6) written"), ("REAL*", "gp", "(P,3) written")],
+     "J^T J / J^T R point blocks of the same model by gather (no atomics)"),
+    ("b200_lm_ba_wv_seg",
+     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "pidx", "(m)"), ("const int*", "cseg", "(C+1)"),
+      ("long long", "split", ""), ("long long", "tpi", ""), ("const REAL*", "Hpinv", "(P,6) or NULL if t holds Hpp^-1 t"),
+      ("const REAL*", "t", "(P,3)"), ("REAL*", "y", "(C,6) y -= W Hpp^-1 t, one writer per camera"),
+      ("REAL*", "part", "(C*split,6) or NULL when split == 1")],
+     "off-diagonal product of the reduced camera system, optim/solver.py:319-336, deterministic"),
+    ("b200_lm_ba_schur_diag_seg",
+     [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const int*", "pidx", "(m)"), ("const int*", "cseg", "(C+1)"),
+      ("long long", "split", ""), ("long long", "tpi", ""), ("const REAL*", "Hpinv", "(P,6)"),
+      ("REAL*", "Sd", "(C,21) in: damped Hcc; out: minus sum_k W_k Hpp^-1 W_k^T, one writer per camera"),
+      ("REAL*", "part", "(C*split,21) or NULL when split == 1")],
+     "diagonal blocks of the reduced camera system (preconditioner of the Schur PCG), deterministic"),
     ("b200_lm_ba_predicted",
      [("const REAL*", "Y4", "(m,4)"), ("const REAL*", "poses", "(C,7)"), ("const REAL*", "rs", "(m,2)"), ("const int*", "cidx", "(m)"),
       ("const int*", "pidx", "(m)"), ("const REAL*", "xc", "(C,6)"), ("const REAL*", "xp", "(P,3)"),
       ("double*", "ws", "ws[0] = sum (J d)^T (2 r + J d)")],
      "TrustRegion 'predicted' reduction, optim/strategy.py:143"),
+]
+
+
+LM_OPS += [
+    ("b200_lm_reproj_step",
+     [("REAL*", "poses", "(ncam,7) parameters; overwritten with the trial poses when the trial is accepted"),
+      ("const REAL*", "pts", "(m,3) camera-sorted"), ("const REAL*", "pix", "(m,2)"), ("const int*", "seg", "(ncam+1)"),
+      ("REAL*", "H", "(ncam,21) J^T J blocks: written by a first trial, read by a retry"), ("REAL*", "g", "(ncam,6)"),
+      ("REAL*", "P_trial", "(ncam,7) work"), ("double*", "ws0", "reduction workspace of the solve kernel"),
+      ("double*", "ws1", "reduction workspace of the loss kernel"),
+      ("double*", "st", "(16) device state: status (0 rejected, 1 accepted, 2 solver failed), loss, last, damping, radius, down, "
+                        "reject count, current loss, trial loss, predicted, failed pivots"),
+      ("double*", "host_out", "(16) pinned host copy of st, valid on return; NULL: no copy and no synchronisation"),
+      ("const double*", "ctl", "HOST (14): last, cached, damping, pg down, reject count, reject limit, strategy kind "
+                               "(0 Constant, 1 Adaptive, 2 TrustRegion), high, low, up, strategy down, factor, min, max"),
+      ("int", "robust", "see b200_lm_reproj_accum"), ("double", "delta", ""), ("double", "scale", "prod(1+damping) so far"),
+      ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", "0: linearise + solve; 1: solve the stored blocks again")],
+     "one trial of LevenbergMarquardt.step incl. strategy.update and the accept test, optimizer.py:659-680, "
+     "strategy.py:41-46,134-151,248-274, for the single-pose reprojection model"),
+    ("b200_lm_reproj_step_peer",
+     [("REAL*", "poses", "(ncam,7) replicated parameters; overwritten when the trial is accepted"),
+      ("const REAL*", "pts", "(m_local,3) this rank's observations, camera-sorted"), ("const REAL*", "pix", "(m_local,2)"),
+      ("const int*", "seg", "(ncam+1) offsets of this rank's rows per camera"),
+      ("REAL*", "H", "(ncam,21): the owner's rows hold the reduced blocks (kept for retries)"), ("REAL*", "g", "(ncam,6)"),
+      ("const unsigned long long*", "bases", "HOST (world) exchange buffers, see b200_comm_open"), ("int", "rank", ""), ("int", "world", ""),
+      ("long long", "part_off", "payload byte offset of the partial blocks: world * ceil(ncam/world) * 27 elements"),
+      ("long long", "pt_off", "payload byte offset of the trial poses: ncam * 7 elements"),
+      ("long long", "epoch0", "count of linearisations so far (incl. this one unless retry)"),
+      ("long long", "epoch1", "count of trials so far incl. this one"),
+      ("double*", "ws0", "reduction workspace"), ("double*", "ws1", ""), ("double*", "ws2", ""),
+      ("double*", "st", "(16) device state, see b200_lm_reproj_step"), ("double*", "host_out", "(16) pinned host copy or NULL"),
+      ("const double*", "ctl", "HOST (14), see b200_lm_reproj_step"), ("int", "robust", ""), ("double", "delta", ""),
+      ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", "")],
+     "b200_lm_reproj_step with the observations sharded over `world` GPUs: [H | g] is reduce-scattered to camera owners, "
+     "trial poses are all-gathered and the scalar sums exchanged by stores into the peers' buffers (SURVEY.md §8e row 4); "
+     "optimizer.py:659-680"),
+    ("b200_lm_poseinv_step_peer",
+     [("REAL*", "P", "(n,7) this rank's poses"), ("const REAL*", "X", "(n,7)"), ("REAL*", "P_trial", "(n,7) work"),
+      ("const unsigned long long*", "bases", "HOST (world) exchange buffers"), ("int", "rank", ""), ("int", "world", ""),
+      ("long long", "epoch", "count of trials so far incl. this one"), ("double*", "ws", ""), ("double*", "st", "(16)"),
+      ("double*", "host_out", "(16) pinned host copy or NULL"), ("const double*", "ctl", "HOST (14)"), ("int", "robust", ""),
+      ("double", "delta", ""), ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", "")],
+     "b200_lm_poseinv_step with the poses sharded over `world` GPUs: only the four scalar sums are exchanged "
+     "(SURVEY.md §8e row 3); optimizer.py:659-680"),
+    ("b200_lm_poseinv_step",
+     [("REAL*", "P", "(n,7) parameters; overwritten when the trial is accepted"), ("const REAL*", "X", "(n,7)"),
+      ("REAL*", "P_trial", "(n,7) work"), ("double*", "ws", "reduction workspace"), ("double*", "st", "(16) device state"),
+      ("double*", "host_out", "(16) pinned host copy or NULL"), ("const double*", "ctl", "HOST (14), see b200_lm_reproj_step"),
+      ("int", "robust", ""), ("double", "delta", ""), ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", "")],
+     "one trial of LevenbergMarquardt.step for README.md:120-129 InvNet, optimizer.py:659-680"),
 ]
 
 

@@ -621,16 +621,6 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
         gp, ws, robust, (CT)delta, m);                                                                                \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_linearize_y_##SFX(const CT* poses, const CT* points, const CT* pix, const int* cidx,     \
-                                               const int* pidx, CT* Y4, const int* ppos, CT* Y4p, CT* rs, CT* Hcc,    \
-                                               CT* Hpp, CT* gc, CT* gp, double* ws, int robust, double delta,         \
-                                               long long m, void* stream) {                                           \
-    if (m <= 0) return 0;                                                                                             \
-    lm_ba_linearize_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                      \
-        poses, points, pix, cidx, pidx, (CT*)nullptr, (CT*)nullptr, Y4, ppos, Y4p, rs, Hcc, Hpp, gc, gp, ws, robust,  \
-        (CT)delta, m);                                                                                                \
-    return (int)cudaGetLastError();                                                                                   \
-  }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_wtx_##SFX(const CT* Jc, const CT* Jp, const int* cidx, const int* pidx, const CT* x,     \
                                        CT* t, long long m, void* stream) {                                            \
     if (m <= 0) return 0;                                                                                             \

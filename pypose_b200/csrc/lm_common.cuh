@@ -114,3 +114,33 @@ __device__ __forceinline__ void seg_atomic_add(T* dst, long long key, T (&v)[K],
 }
 
 }  // namespace b200pose
+
+namespace b200pose {
+
+// Rows of one observation rebuilt from 16 B: Y4[k] = (y = T_c p, sqrt(rho')) and the camera quaternion (gathered, the
+// observations are grouped by camera so a warp mostly shares it).  jc0/jc1 = d r / d xi_c (2x6), jp0/jp1 = d r / d p (2x3).
+template <typename T> struct ObsRows { T jc0[6], jc1[6], jp0[3], jp1[3]; };
+template <typename T>
+__device__ __forceinline__ void obs_rows(const T* __restrict__ Y4, const T* __restrict__ poses, long long k, long long c,
+                                         ObsRows<T>& R) {
+  const T yx = Y4[k * 4], yy = Y4[k * 4 + 1], yz = Y4[k * 4 + 2], sw = Y4[k * 4 + 3];
+  Elem<T> Tc;
+  Tc.q.v = mk(__ldg(poses + c * 7 + 3), __ldg(poses + c * 7 + 4), __ldg(poses + c * 7 + 5));
+  Tc.q.w = __ldg(poses + c * 7 + 6);
+  const V3<T> y = mk(yx, yy, yz);
+  reproj_rows(y, R.jc0, R.jc1);
+  reproj_point_rows(Tc, y, R.jp0, R.jp1);
+#pragma unroll
+  for (int a = 0; a < 6; ++a) { R.jc0[a] *= sw; R.jc1[a] *= sw; }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { R.jp0[a] *= sw; R.jp1[a] *= sw; }
+}
+
+}  // namespace b200pose
+
+namespace b200pose {
+// ba.cu: y[c] -= sum over camera c's rows of Jc^T Jp (Hp^-1) t, one writer per camera (deterministic)
+template <typename CT>
+int ba_wv_seg_launch(const CT* Y4, const CT* poses, const int* pidx, const int* cseg, int S, int tpi, const CT* Hpinv,
+                     const CT* t, CT* y, CT* part, const double* cg, long long C, cudaStream_t st);
+}  // namespace b200pose

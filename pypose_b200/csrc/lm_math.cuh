@@ -403,4 +403,70 @@ template <typename T> LM_HD void sym3_unpack(const T* a, T (&A)[3][3]) {
 }
 
 
+
+// ---------------------------------------------------------------- LM accept / reject decision + damping strategies
+// IEEE double operations exactly as Python evaluates them: no fused multiply-adds on the device
+#ifdef __CUDA_ARCH__
+LM_HD double lm_ddiv(double a, double b) { return __ddiv_rn(a, b); }
+LM_HD double lm_dsub(double a, double b) { return __dsub_rn(a, b); }
+LM_HD double lm_dmul(double a, double b) { return __dmul_rn(a, b); }
+#else
+LM_HD double lm_ddiv(double a, double b) { return a / b; }
+LM_HD double lm_dsub(double a, double b) { return a - b; }
+LM_HD double lm_dmul(double a, double b) { return a * b; }
+#endif
+LM_HD double lm_fmax(double a, double b) { return a > b ? a : (b == b ? b : a); }     // Python max(a, b) for non-NaN input
+LM_HD double lm_fmin(double a, double b) { return a < b ? a : (b == b ? b : a); }
+
+// control block of one trial (filled from the host's `ctl` array, passed by value)
+struct LmCtl {
+  double last;          // loss the trial has to beat (the cached loss of the previous step), if `cached`
+  double damping;       // pg['damping'] used for this trial
+  double pg_down;       // pg['down']  (Adaptive: its constant factor; TrustRegion: the shrinking state)
+  double reject_count;  // rejected trials so far in this step
+  double reject_limit;  // LM(reject=...)
+  double high, low, up, self_down, factor, smin, smax;
+  int cached;           // 0: first step ever -> last = current loss of this linearisation
+  int kind;             // 0 Constant, 1 Adaptive, 2 TrustRegion
+};
+
+enum { ST_STATUS = 0, ST_LOSS = 1, ST_LAST = 2, ST_DAMPING = 3, ST_RADIUS = 4, ST_DOWN = 5, ST_REJECT = 6, ST_CUR = 7,
+       ST_TRIAL = 8, ST_PRED = 9, ST_FAILED = 10, ST_SIZE = 16 };
+
+// optimizer.py:662-680 for one trial: strategy.update, then accept (status 1) / reject (0) / solver failure (2).
+// Plain IEEE double operations in the order Python evaluates them (no fused multiply-adds).
+LM_HD void lm_decide(const LmCtl& c, double cur, double trial, double predicted, double failed,
+                                          double* st) {
+  const double last = c.cached ? c.last : cur;
+  double damping = c.damping, down = c.pg_down, radius = lm_ddiv(1.0, c.damping);
+  st[ST_CUR] = cur; st[ST_TRIAL] = trial; st[ST_PRED] = predicted; st[ST_FAILED] = failed; st[ST_LAST] = last;
+  if (failed > 0.0) {                      // solver.py:214-215 -> optimizer.py:669-671: break, nothing changes
+    st[ST_STATUS] = 2.0; st[ST_LOSS] = last; st[ST_DAMPING] = damping; st[ST_RADIUS] = radius; st[ST_DOWN] = down;
+    st[ST_REJECT] = c.reject_count;
+    return;
+  }
+  if (c.kind != 0) {
+    const double quality = lm_ddiv(lm_dsub(last, trial), -predicted);      // strategy.py:143 / 260
+    if (c.kind == 1) {                                                         // Adaptive, strategy.py:134-151
+      if (quality > c.high) damping = lm_dmul(damping, down);
+      else if (quality > c.low) { }
+      else damping = lm_dmul(damping, c.up);
+      damping = lm_fmax(c.smin, lm_fmin(damping, c.smax));
+    } else {                                                                   // TrustRegion, strategy.py:248-274
+      if (quality > c.high) { radius = lm_dmul(c.up, radius); down = c.self_down; }
+      else if (quality > c.low) { down = c.self_down; }
+      else { radius = lm_dmul(radius, down); down = lm_dmul(down, c.factor); }
+      down = lm_fmax(c.smin, lm_fmin(down, c.smax));
+      radius = lm_fmax(c.smin, lm_fmin(radius, c.smax));
+      damping = lm_ddiv(1.0, radius);
+    }
+  }
+  const bool reject = (last < trial) && (c.reject_count < c.reject_limit);     // optimizer.py:675
+  st[ST_STATUS] = reject ? 0.0 : 1.0;
+  st[ST_LOSS] = reject ? last : trial;
+  st[ST_REJECT] = reject ? c.reject_count + 1.0 : c.reject_count;
+  st[ST_DAMPING] = damping; st[ST_RADIUS] = radius; st[ST_DOWN] = down;
+}
+
+
 }  // namespace b200pose

@@ -1,0 +1,608 @@
+// lmstep.cu — one Levenberg-Marquardt trial per host call, decided on the device (C-ABI: include/b200pose.h, section LM).
+//
+// Round 1 drove every trial from Python: three launches, a gather kernel, a blocking read, the damping strategy in
+// Python, then the parameter copy — 125 us per step for ~35 us of kernels (VERDICT r1 "What's weak").
+// Here ONE C call enqueues the whole trial and the control flow of optimizer.py:659-680 runs on the device:
+//
+//   reprojection (block-diagonal H):  K1 linearise + accumulate + damped 6x6 solve + retraction  (warp per camera)
+//                                     K2 trial loss; its last CTA takes the accept / reject decision and updates the
+//                                        damping state (Constant / Adaptive / TrustRegion, strategy.py:41-46,134-151,248-274)
+//                                     K3 parameters <- trial parameters, if accepted
+//   PoseInv (independent poses):      K1 whole trial per pose in registers + decision in its last CTA;  K3 as above
+//
+// and the 16-double state comes back with one asynchronous copy + one stream synchronisation (the single host read of
+// the step).  A rejected trial (rare) is retried by the host with the state it just read: K1 is then only the damped
+// solve on the stored blocks.  All scalars the decision needs are arguments of that call — the host stays the owner of
+// `param_groups` (users edit the damping between steps), the device computes the update.
+#include "lm_common.cuh"
+#include "comm.cuh"
+
+namespace b200pose {
+
+// K1 (first trial of a step): one warp per camera — accumulate the camera's 6x6 system over its sorted observations,
+// keep it (H, g) for retries, solve the damped system and retract, all in registers.
+// sums (ws): [0] sum rho(|r|^2) (current loss), [1] predicted reduction, [2] failed pivots
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
+                                                                      const T* __restrict__ pix, const int* __restrict__ seg,
+                                                                      T* __restrict__ H, T* __restrict__ g,
+                                                                      T* __restrict__ Pt, double* ws, T scale, T dmin,
+                                                                      T dmax, int rk, T rdelta, int ncam) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+    T pr[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
+    const Elem<T> Tc = load_se3(pr);
+    Sys6<T> s;
+    sys6_zero(s);
+    T loss = T(0);
+    const int b = seg[c], e = seg[c + 1];
+    auto accumulate = [&](const V3<T>& p, T zx, T zy) {
+      T rx, ry;
+      V3<T> y;
+      reproj_residual(Tc, p, zx, zy, rx, ry, y);
+      T j0[6], j1[6];
+      reproj_rows(y, j0, j1);
+      T rho, w;
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      if (rk) {
+        const T sw = m_sqrt(w);
+        rx *= sw; ry *= sw;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+      }
+      sys6_add_row(s, j0, rx);
+      sys6_add_row(s, j1, ry);
+      loss += rho;
+    };
+    int k = b + lane;
+    for (; k + 32 < e; k += 64) {
+      const long long k0 = k, k1 = k + 32;
+      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
+      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
+      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
+      accumulate(p0, z0x, z0y);
+      accumulate(p1, z1x, z1y);
+    }
+    if (k < e) {
+      const long long k0 = k;
+      accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
+#pragma unroll
+        for (int bb = a; bb < 6; ++bb) s.A[a][bb] += __shfl_xor_sync(0xffffffffu, s.A[a][bb], o);
+      }
+      loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    }
+    // every lane holds the camera's totals (xor tree): the solve runs redundantly, lane 0 stores
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    if (lane == 0) {
+      T o7[7];
+      store_elem<SE3g, T>(o7, se3_retract(D, Tc));
+#pragma unroll
+      for (int q = 0; q < 7; ++q) Pt[(long long)c * 7 + q] = o7[q];
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        g[(long long)c * 6 + a] = s.g[a];
+#pragma unroll
+        for (int bb = a; bb < 6; ++bb) H[(long long)c * 21 + q++] = s.A[a][bb];
+      }
+      acc[0] += (double)loss;
+      acc[1] += (double)pred;
+      acc[2] += ok ? 0.0 : 1.0;
+    }
+  }
+  reduce_sums<3>(acc, ws);
+}
+
+// K1 (retry): damped solve + retraction from the stored blocks; same sums layout ([0] is not used by a retry)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) reproj_resolve_kernel(const T* __restrict__ H, const T* __restrict__ g,
+                                                                     const T* __restrict__ P, T* __restrict__ Pt, double* ws,
+                                                                     T scale, T dmin, T dmax, long long n) {
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (long long c = (long long)blockIdx.x * kLmThreads + threadIdx.x; c < n; c += (long long)gridDim.x * kLmThreads) {
+    Sys6<T> s;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      s.g[a] = g[c * 6 + a];
+#pragma unroll
+      for (int b = a; b < 6; ++b) s.A[a][b] = H[c * 21 + q++];
+    }
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    T pr[7], o[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = P[c * 7 + k];
+    store_elem<SE3g, T>(o, se3_retract(D, load_se3(pr)));
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Pt[c * 7 + k] = o[k];
+    acc[1] += (double)pred;
+    acc[2] += ok ? 0.0 : 1.0;
+  }
+  reduce_sums<3>(acc, ws);
+}
+
+// K2: trial loss (warp per camera, trial pose in registers); the last CTA decides.  ws1: this kernel's reduction slot,
+// ws0: K1's totals.
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) reproj_loss_decide_kernel(const T* __restrict__ Pt, const T* __restrict__ pts,
+                                                                         const T* __restrict__ pix, const int* __restrict__ seg,
+                                                                         double* ws1, const double* ws0, double* st, LmCtl ctl,
+                                                                         int rk, T rdelta, int ncam) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
+  double acc[1] = {0.0};
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+    T pr[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) pr[q] = Pt[(long long)c * 7 + q];
+    const Elem<T> Tc = load_se3(pr);
+    const int b = seg[c], e = seg[c + 1];
+    T loss = T(0);
+    auto one = [&](const V3<T>& p, T zx, T zy) {
+      T rx, ry, rho, w;
+      V3<T> y;
+      reproj_residual(Tc, p, zx, zy, rx, ry, y);
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      loss += rho;
+    };
+    int k = b + lane;
+    for (; k + 32 < e; k += 64) {
+      const long long k0 = k, k1 = k + 32;
+      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
+      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
+      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
+      one(p0, z0x, z0y);
+      one(p1, z1x, z1y);
+    }
+    if (k < e) {
+      const long long k0 = k;
+      one(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
+    }
+    acc[0] += (double)loss;
+  }
+  if (reduce_sums<1>(acc, ws1)) lm_decide(ctl, ws0[0], ws1[0], ws0[1], ws0[2], st);
+}
+
+// K1 of the PoseInv family: the whole trial per pose in registers (lm.cu lm_poseinv_trial_kernel) + the decision
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) poseinv_trial_decide_kernel(const T* __restrict__ P, const T* __restrict__ X,
+                                                                           T* __restrict__ Pt, double* ws, double* st,
+                                                                           LmCtl ctl, T scale, T dmin, T dmax, int rk,
+                                                                           T rdelta, long long n) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T p[7], x[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { p[k] = P[i * 7 + k]; x[k] = X[i * 7 + k]; }
+    const Elem<T> Pe = load_se3(p), Xe = load_se3(x);
+    Tang<T> r;
+    Sys6<T> s;
+    poseinv_linearize(Pe, Xe, r, s);
+    T rho0, w0, rho1, w1;
+    robust_eval(rk, rdelta, tang6_sqnorm(r), rho0, w0);
+    if (rk) sys6_scale(s, w0);
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    const Elem<T> Pn = se3_retract(D, Pe);
+    T o[7];
+    store_elem<SE3g, T>(o, Pn);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Pt[i * 7 + k] = o[k];
+    robust_eval(rk, rdelta, tang6_sqnorm(poseinv_residual(Pn, Xe)), rho1, w1);
+    acc[0] += (double)rho0;
+    acc[1] += (double)rho1;
+    acc[2] += (double)pred;
+    acc[3] += ok ? 0.0 : 1.0;
+  }
+  if (reduce_sums<4>(acc, ws)) lm_decide(ctl, ws[0], ws[1], ws[2], ws[3], st);
+}
+
+// K3: parameters <- trial parameters when the decision was "accept" (update_parameter, optimizer.py:135-140)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_commit_kernel(const double* __restrict__ st, const T* __restrict__ src,
+                                                                T* __restrict__ dst, long long count) {
+  if (st[ST_STATUS] != 1.0) return;
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < count; i += (long long)gridDim.x * kLmThreads)
+    dst[i] = src[i];
+}
+
+// ================================================================================================================
+// Multi-GPU trials over NVLink peer memory (comm.cuh): residual-sharded reprojection and pose-sharded PoseInv.
+// No collective library call: producers store partial results into the consumer's exchange buffer and publish an epoch.
+//
+// Reprojection (cameras replicated, observations sharded; SURVEY.md §8e "residuals sharded, one packed reduction of
+// [H | g | loss] per iteration, small reduction per trial") as a reduce-scatter / all-gather pair fused into the kernels:
+//   K1p  every rank accumulates its observations' 27 sums per camera and stores them into the OWNER of that camera
+//        (owner k holds cameras [k q, (k+1) q), q = ceil(C / world));                       signal channel 0
+//   K2p  the owner adds the `world` partials in rank order, keeps the reduced block for retries, solves, retracts and
+//        stores the trial pose (7 numbers instead of 27) into every rank's copy;             signal channel 1
+//   K3p  trial loss of the local observations -> scalar to every rank;                      signal channel 2
+//   K4p  every rank adds the scalars in rank order (bit-identical decisions), decides, commits.
+// Scalars whose producer may run ahead of a slow consumer (current loss, PoseInv sums) are double-buffered by epoch parity.
+constexpr int CH_PART = 0, CH_TRIAL = 1, CH_LOSS = 2, CH_POSEINV = 3;
+
+struct PeerRegions { long long part, pt; };     // byte offsets inside the payload: partial blocks, trial poses
+
+__device__ __forceinline__ bool cta_ticket_last(unsigned* ticket) {     // call after __threadfence_system + __syncthreads
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (last) *ticket = 0u;
+  }
+  __syncthreads();
+  return last;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
+                                                                        const T* __restrict__ pix, const int* __restrict__ seg,
+                                                                        Peers P, PeerRegions R, double* ws,
+                                                                        unsigned long long epoch, int rk, T rdelta, int ncam) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
+  const int q = (ncam + P.world - 1) / P.world;
+  double acc[1] = {0.0};
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+    T pr[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
+    const Elem<T> Tc = load_se3(pr);
+    Sys6<T> s;
+    sys6_zero(s);
+    T loss = T(0);
+    const int b = seg[c], e = seg[c + 1];
+    for (int k = b + lane; k < e; k += 32) {
+      const long long k0 = k;
+      T rx, ry;
+      V3<T> y;
+      reproj_residual(Tc, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1], rx, ry, y);
+      T j0[6], j1[6];
+      reproj_rows(y, j0, j1);
+      T rho, w;
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      if (rk) {
+        const T sw = m_sqrt(w);
+        rx *= sw; ry *= sw;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+      }
+      sys6_add_row(s, j0, rx);
+      sys6_add_row(s, j1, ry);
+      loss += rho;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
+#pragma unroll
+        for (int bb = a; bb < 6; ++bb) s.A[a][bb] += __shfl_xor_sync(0xffffffffu, s.A[a][bb], o);
+      }
+      loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    }
+    if (lane == 0) {
+      const int owner = c / q;
+      T* dst = reinterpret_cast<T*>(P.base[owner] + kDataOffset + R.part) + ((long long)P.rank * q + (c - owner * q)) * 27;
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int bb = a; bb < 6; ++bb) dst[t++] = s.A[a][bb];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) dst[21 + a] = s.g[a];
+      acc[0] += (double)loss;
+      __threadfence_system();
+    }
+  }
+  if (reduce_sums<1>(acc, ws)) {           // thread 0 of the last CTA: every CTA's stores are ordered before its ticket
+    for (int r = 0; r < P.world; ++r) comm_scalars(P.base[r], CH_PART, P.rank)[(epoch & 1) * 4] = ws[0];
+    comm_signal_all(P, CH_PART, epoch);
+  }
+}
+
+// owner: reduce (or, on a retry, reuse) its cameras' blocks, solve, retract, broadcast the trial poses
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) reproj_reduce_solve_push_kernel(const T* __restrict__ poses, T* __restrict__ H,
+                                                                               T* __restrict__ g, Peers P, PeerRegions R,
+                                                                               double* ws, unsigned long long epoch0,
+                                                                               unsigned long long epoch1, int retry, T scale,
+                                                                               T dmin, T dmax, int ncam) {
+  const int q = (ncam + P.world - 1) / P.world;
+  const int c0 = P.rank * q, c1 = min(ncam, c0 + q);
+  if (!retry) {
+    if (threadIdx.x == 0) comm_wait_all(P, CH_PART, epoch0);
+    __syncthreads();
+  }
+  double acc[2] = {0.0, 0.0};
+  const T* part = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.part);
+  for (int c = c0 + blockIdx.x * kLmThreads + threadIdx.x; c < c1; c += gridDim.x * kLmThreads) {
+    Sys6<T> s;
+    if (!retry) {
+      T v[27];
+#pragma unroll
+      for (int t = 0; t < 27; ++t) v[t] = part[(long long)(c - c0) * 27 + t];
+      for (int r = 1; r < P.world; ++r)
+#pragma unroll
+        for (int t = 0; t < 27; ++t) v[t] += part[((long long)r * q + (c - c0)) * 27 + t];
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) { s.A[a][b] = v[t]; H[(long long)c * 21 + t] = v[t]; ++t; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { s.g[a] = v[21 + a]; g[(long long)c * 6 + a] = v[21 + a]; }
+    } else {
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        s.g[a] = g[(long long)c * 6 + a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) s.A[a][b] = H[(long long)c * 21 + t++];
+      }
+    }
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    T pr[7], o[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
+    store_elem<SE3g, T>(o, se3_retract(D, load_se3(pr)));
+    for (int r = 0; r < P.world; ++r) {
+      T* dst = reinterpret_cast<T*>(P.base[r] + kDataOffset + R.pt) + (long long)c * 7;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) dst[k] = o[k];
+    }
+    acc[0] += (double)pred;
+    acc[1] += ok ? 0.0 : 1.0;
+    __threadfence_system();
+  }
+  if (reduce_sums<2>(acc, ws)) {
+    for (int r = 0; r < P.world; ++r) {
+      double* sc = comm_scalars(P.base[r], CH_TRIAL, P.rank);
+      sc[0] = ws[0]; sc[1] = ws[1];
+    }
+    comm_signal_all(P, CH_TRIAL, epoch1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) reproj_loss_push_kernel(const T* __restrict__ pts, const T* __restrict__ pix,
+                                                                       const int* __restrict__ seg, Peers P, PeerRegions R,
+                                                                       double* ws, unsigned long long epoch1, int rk, T rdelta,
+                                                                       int ncam) {
+  if (threadIdx.x == 0) comm_wait_all(P, CH_TRIAL, epoch1);
+  __syncthreads();
+  const T* Pt = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.pt);
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
+  double acc[1] = {0.0};
+  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+    const int b = seg[c], e = seg[c + 1];
+    if (b == e) continue;
+    T pr[7];
+#pragma unroll
+    for (int qk = 0; qk < 7; ++qk) pr[qk] = Pt[(long long)c * 7 + qk];
+    const Elem<T> Tc = load_se3(pr);
+    T loss = T(0);
+    for (int k = b + lane; k < e; k += 32) {
+      const long long k0 = k;
+      T rx, ry, rho, w;
+      V3<T> y;
+      reproj_residual(Tc, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1], rx, ry, y);
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      loss += rho;
+    }
+    acc[0] += (double)loss;
+  }
+  if (reduce_sums<1>(acc, ws)) {
+    for (int r = 0; r < P.world; ++r) comm_scalars(P.base[r], CH_LOSS, P.rank)[0] = ws[0];
+    comm_signal_all(P, CH_LOSS, epoch1);
+  }
+}
+
+// every rank: add the scalars in rank order, decide (identical everywhere), commit the trial poses
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) reproj_decide_commit_kernel(Peers P, PeerRegions R, double* st, LmCtl ctl,
+                                                                           unsigned long long epoch0, unsigned long long epoch1,
+                                                                           T* __restrict__ poses, long long count) {
+  __shared__ double sh[ST_SIZE];
+  if (threadIdx.x == 0) {
+    comm_wait_all(P, CH_LOSS, epoch1);
+    double cur = 0.0, trial = 0.0, pred = 0.0, failed = 0.0;
+    for (int r = 0; r < P.world; ++r) {
+      cur += comm_scalars(P.base[P.rank], CH_PART, r)[(epoch0 & 1) * 4];
+      pred += comm_scalars(P.base[P.rank], CH_TRIAL, r)[0];
+      failed += comm_scalars(P.base[P.rank], CH_TRIAL, r)[1];
+      trial += comm_scalars(P.base[P.rank], CH_LOSS, r)[0];
+    }
+    lm_decide(ctl, cur, trial, pred, failed, sh);
+    if (blockIdx.x == 0)
+      for (int k = 0; k < ST_SIZE; ++k) st[k] = k <= ST_FAILED ? sh[k] : 0.0;
+  }
+  __syncthreads();
+  if (sh[ST_STATUS] != 1.0) return;
+  const T* Pt = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.pt);
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < count; i += (long long)gridDim.x * kLmThreads)
+    poses[i] = Pt[i];
+}
+
+// PoseInv, poses sharded: the trial kernel of each rank pushes its four sums; decide + commit after one exchange
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) poseinv_trial_push_kernel(const T* __restrict__ Pm, const T* __restrict__ X,
+                                                                         T* __restrict__ Pt, double* ws, Peers P,
+                                                                         unsigned long long epoch, T scale, T dmin, T dmax,
+                                                                         int rk, T rdelta, long long n) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+    T p[7], x[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { p[k] = Pm[i * 7 + k]; x[k] = X[i * 7 + k]; }
+    const Elem<T> Pe = load_se3(p), Xe = load_se3(x);
+    Tang<T> r;
+    Sys6<T> s;
+    poseinv_linearize(Pe, Xe, r, s);
+    T rho0, w0, rho1, w1;
+    robust_eval(rk, rdelta, tang6_sqnorm(r), rho0, w0);
+    if (rk) sys6_scale(s, w0);
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    const Elem<T> Pn = se3_retract(D, Pe);
+    T o[7];
+    store_elem<SE3g, T>(o, Pn);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Pt[i * 7 + k] = o[k];
+    robust_eval(rk, rdelta, tang6_sqnorm(poseinv_residual(Pn, Xe)), rho1, w1);
+    acc[0] += (double)rho0;
+    acc[1] += (double)rho1;
+    acc[2] += (double)pred;
+    acc[3] += ok ? 0.0 : 1.0;
+  }
+  if (reduce_sums<4>(acc, ws)) {
+    for (int r = 0; r < P.world; ++r) {
+      double* sc = comm_scalars(P.base[r], CH_POSEINV, P.rank) + (epoch & 1) * 4;
+      sc[0] = ws[0]; sc[1] = ws[1]; sc[2] = ws[2]; sc[3] = ws[3];
+    }
+    comm_signal_all(P, CH_POSEINV, epoch);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) poseinv_decide_commit_kernel(Peers P, double* st, LmCtl ctl,
+                                                                            unsigned long long epoch,
+                                                                            const T* __restrict__ Pt, T* __restrict__ Pm,
+                                                                            long long count) {
+  __shared__ double sh[ST_SIZE];
+  if (threadIdx.x == 0) {
+    comm_wait_all(P, CH_POSEINV, epoch);
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < P.world; ++r) {
+      const double* sc = comm_scalars(P.base[P.rank], CH_POSEINV, r) + (epoch & 1) * 4;
+      v[0] += sc[0]; v[1] += sc[1]; v[2] += sc[2]; v[3] += sc[3];
+    }
+    lm_decide(ctl, v[0], v[1], v[2], v[3], sh);
+    if (blockIdx.x == 0)
+      for (int k = 0; k < ST_SIZE; ++k) st[k] = k <= ST_FAILED ? sh[k] : 0.0;
+  }
+  __syncthreads();
+  if (sh[ST_STATUS] != 1.0) return;
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < count; i += (long long)gridDim.x * kLmThreads)
+    Pm[i] = Pt[i];
+}
+
+static Peers make_peers(const unsigned long long* bases, int rank, int world) {
+  Peers P;
+  for (int r = 0; r < kMaxRanks; ++r) P.base[r] = r < world ? reinterpret_cast<char*>(bases[r]) : nullptr;
+  P.rank = rank; P.world = world;
+  return P;
+}
+
+static LmCtl make_ctl(const double* c) {
+  LmCtl k;
+  k.last = c[0]; k.cached = c[1] != 0.0; k.damping = c[2]; k.pg_down = c[3]; k.reject_count = c[4]; k.reject_limit = c[5];
+  k.kind = (int)c[6]; k.high = c[7]; k.low = c[8]; k.up = c[9]; k.self_down = c[10]; k.factor = c[11]; k.smin = c[12];
+  k.smax = c[13];
+  return k;
+}
+
+static int finish_step(double* st, double* host_out, cudaStream_t s) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (!host_out) return 0;
+  e = cudaMemcpyAsync(host_out, st, ST_SIZE * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(s);
+}
+
+}  // namespace b200pose
+
+using namespace b200pose;
+
+#define LMSTEP_ABI(SFX, CT)                                                                                           \
+  B200_EXPORT int b200_lm_reproj_step_##SFX(CT* poses, const CT* pts, const CT* pix, const int* seg, CT* H, CT* g,    \
+                                            CT* P_trial, double* ws0, double* ws1, double* st, double* host_out,      \
+                                            const double* ctl, int robust, double delta, double scale, double dmin,   \
+                                            double dmax, int retry, long long ncam, void* stream) {                   \
+    if (ncam <= 0) return 0;                                                                                          \
+    cudaStream_t s = (cudaStream_t)stream;                                                                            \
+    const LmCtl k = make_ctl(ctl);                                                                                    \
+    const unsigned wgrid = lm_grid(ncam, kLmThreads / 32);                                                            \
+    if (!retry)                                                                                                       \
+      reproj_linsolve_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, (CT)scale,    \
+                                                              (CT)dmin, (CT)dmax, robust, (CT)delta, (int)ncam);      \
+    else                                                                                                              \
+      reproj_resolve_kernel<CT><<<lm_grid(ncam, kLmThreads), kLmThreads, 0, s>>>(H, g, poses, P_trial, ws0,           \
+                                                                                 (CT)scale, (CT)dmin, (CT)dmax, ncam);\
+    reproj_loss_decide_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(P_trial, pts, pix, seg, ws1, ws0, st, k, robust,       \
+                                                               (CT)delta, (int)ncam);                                 \
+    lm_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(st, P_trial, poses, ncam * 7);          \
+    return finish_step(st, host_out, s);                                                                              \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_poseinv_step_##SFX(CT* P, const CT* X, CT* P_trial, double* ws, double* st,                 \
+                                             double* host_out, const double* ctl, int robust, double delta,           \
+                                             double scale, double dmin, double dmax, long long n, void* stream) {     \
+    if (n <= 0) return 0;                                                                                             \
+    cudaStream_t s = (cudaStream_t)stream;                                                                            \
+    const LmCtl k = make_ctl(ctl);                                                                                    \
+    poseinv_trial_decide_kernel<CT><<<lm_grid(n, kLmThreads), kLmThreads, 0, s>>>(                                    \
+        P, X, P_trial, ws, st, k, (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta, n);                               \
+    lm_commit_kernel<CT><<<lm_grid(n * 7, kLmThreads), kLmThreads, 0, s>>>(st, P_trial, P, n * 7);                    \
+    return finish_step(st, host_out, s);                                                                              \
+  }
+
+#define LMSTEP_PEER_ABI(SFX, CT)                                                                                      \
+  B200_EXPORT int b200_lm_reproj_step_peer_##SFX(CT* poses, const CT* pts, const CT* pix, const int* seg, CT* H,      \
+                                                 CT* g, const unsigned long long* bases, int rank, int world,         \
+                                                 long long part_off, long long pt_off, long long epoch0,              \
+                                                 long long epoch1, double* ws0, double* ws1, double* ws2, double* st, \
+                                                 double* host_out, const double* ctl, int robust, double delta,       \
+                                                 double scale, double dmin, double dmax, int retry, long long ncam,   \
+                                                 void* stream) {                                                      \
+    if (ncam <= 0) return 0;                                                                                          \
+    cudaStream_t s = (cudaStream_t)stream;                                                                            \
+    const LmCtl k = make_ctl(ctl);                                                                                    \
+    const Peers P = make_peers(bases, rank, world);                                                                   \
+    const PeerRegions R = {part_off, pt_off};                                                                         \
+    const unsigned wgrid = lm_grid(ncam, kLmThreads / 32);                                                            \
+    const long long q = (ncam + world - 1) / world;                                                                   \
+    if (!retry)                                                                                                       \
+      reproj_accum_push_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0,                      \
+                                                                (unsigned long long)epoch0, robust, (CT)delta,        \
+                                                                (int)ncam);                                           \
+    reproj_reduce_solve_push_kernel<CT><<<lm_grid(q, kLmThreads), kLmThreads, 0, s>>>(                                \
+        poses, H, g, P, R, ws1, (unsigned long long)epoch0, (unsigned long long)epoch1, retry, (CT)scale, (CT)dmin,   \
+        (CT)dmax, (int)ncam);                                                                                         \
+    reproj_loss_push_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2, (unsigned long long)epoch1,    \
+                                                             robust, (CT)delta, (int)ncam);                           \
+    reproj_decide_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(                             \
+        P, R, st, k, (unsigned long long)epoch0, (unsigned long long)epoch1, poses, ncam * 7);                        \
+    return finish_step(st, host_out, s);                                                                              \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_poseinv_step_peer_##SFX(CT* P_, const CT* X, CT* P_trial, const unsigned long long* bases,  \
+                                                  int rank, int world, long long epoch, double* ws, double* st,       \
+                                                  double* host_out, const double* ctl, int robust, double delta,      \
+                                                  double scale, double dmin, double dmax, long long n,                \
+                                                  void* stream) {                                                     \
+    cudaStream_t s = (cudaStream_t)stream;                                                                            \
+    const LmCtl k = make_ctl(ctl);                                                                                    \
+    const Peers P = make_peers(bases, rank, world);                                                                   \
+    poseinv_trial_push_kernel<CT><<<lm_grid(n > 0 ? n : 1, kLmThreads), kLmThreads, 0, s>>>(                          \
+        P_, X, P_trial, ws, P, (unsigned long long)epoch, (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta, n);       \
+    poseinv_decide_commit_kernel<CT><<<lm_grid(n > 0 ? n * 7 : 1, kLmThreads), kLmThreads, 0, s>>>(                   \
+        P, st, k, (unsigned long long)epoch, P_trial, P_, n * 7);                                                     \
+    return finish_step(st, host_out, s);                                                                              \
+  }
+
+LMSTEP_ABI(f32, float)
+LMSTEP_ABI(f64, double)
+LMSTEP_PEER_ABI(f32, float)
+LMSTEP_PEER_ABI(f64, double)

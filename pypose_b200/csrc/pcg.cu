@@ -18,7 +18,23 @@
 
 namespace b200pose {
 
-enum { CG_RZ0 = 0, CG_RZ1 = 1, CG_PQ = 2, CG_RR = 3, CG_STOP2 = 4, CG_DONE = 5, CG_ITERS = 6, CG_MAXIT = 7 };
+// state (16 doubles).  DONE: 0 running, 1 converged (|r| <= tol |b|), 2 breakdown (p.Ap <= 0), 3 stagnated (no new minimum of
+// |r| for PATIENCE iterations), 4 maxiter.  BEST / SINCE / SAVE guard the solve against finite-precision CG: when the
+// tolerance is below what the arithmetic can reach (fp32, ill-conditioned Schur complements) the iterate degrades after
+// its best point, so the iterate with the smallest recursive residual is kept in xbest and returned unless the solve
+// converged (then the last iterate IS the best one, i.e. attainable tolerances behave exactly like solver.py:312-340).
+enum { CG_RZ0 = 0, CG_RZ1 = 1, CG_PQ = 2, CG_RR = 3, CG_STOP2 = 4, CG_DONE = 5, CG_ITERS = 6, CG_MAXIT = 7,
+       CG_BEST = 8, CG_SINCE = 9, CG_SAVE = 10, CG_PATIENCE = 11, CG_STATE = 16 };
+constexpr double kCgPatience = 100.0;
+
+// after an update produced |r|^2 = rr: bookkeeping of the best iterate and the stop decision (one thread)
+__device__ __forceinline__ void cg_after_update(double* cg, double rr, double it) {
+  if (rr < cg[CG_BEST]) { cg[CG_BEST] = rr; cg[CG_SINCE] = 0.0; cg[CG_SAVE] = 1.0; }
+  else { cg[CG_SINCE] += 1.0; cg[CG_SAVE] = 0.0; }
+  if (!(rr > cg[CG_STOP2])) cg[CG_DONE] = 1.0;
+  else if (it >= cg[CG_MAXIT]) cg[CG_DONE] = 4.0;
+  else if (cg[CG_SINCE] >= cg[CG_PATIENCE]) cg[CG_DONE] = 3.0;
+}
 
 template <typename T> __device__ __forceinline__ void ld6(const T* p, long long i, T (&v)[6]) {
 #pragma unroll
@@ -112,6 +128,7 @@ __global__ void __launch_bounds__(kLmThreads) cg_init_kernel(const T* __restrict
     const double rz = ws[0], rr = ws[1];
     cg[CG_RZ0] = rz; cg[CG_RZ1] = 0.0; cg[CG_PQ] = 0.0; cg[CG_RR] = rr; cg[CG_STOP2] = tol * tol * rr;
     cg[CG_ITERS] = 0.0; cg[CG_MAXIT] = maxiter;
+    cg[CG_BEST] = rr; cg[CG_SINCE] = 0.0; cg[CG_SAVE] = 1.0; cg[CG_PATIENCE] = kCgPatience;   // x = 0 is the first best
     cg[CG_DONE] = (!(rr > tol * tol * rr) || maxiter <= 0.0) ? 1.0 : 0.0;      // |r| <= tol |b| (also NaN) -> nothing to do
   }
 }
@@ -129,9 +146,11 @@ __global__ void __launch_bounds__(kLmThreads) cg_dot_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) cg_update_kernel(const T* __restrict__ Minv, const T* __restrict__ p,
                                                                 const T* __restrict__ q, T* __restrict__ x,
-                                                                T* __restrict__ r, T* __restrict__ z, double* cg,
+                                                                T* __restrict__ r, T* __restrict__ z,
+                                                                T* __restrict__ xbest, double* cg,
                                                                 double* ws, int par, long long n) {
   if (cg[CG_DONE] != 0.0) return;
+  const bool save = cg[CG_SAVE] != 0.0;      // the iterate entering this update is the best so far: keep a copy
   const double pq = cg[CG_PQ];
   if (!(pq > 0.0)) {                       // breakdown (operator not positive definite along p): stop with the current x
     if (blockIdx.x == 0 && threadIdx.x == 0) cg[CG_DONE] = 2.0;
@@ -142,6 +161,7 @@ __global__ void __launch_bounds__(kLmThreads) cg_update_kernel(const T* __restri
   for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
     T pv[6], qv[6], xv[6], rv[6], zv[6];
     ld6(p, i, pv); ld6(q, i, qv); ld6(x, i, xv); ld6(r, i, rv);
+    if (save) st6(xbest, i, xv);
 #pragma unroll
     for (int k = 0; k < 6; ++k) { xv[k] += alpha * pv[k]; rv[k] -= alpha * qv[k]; }
     sym6_mv_packed(Minv + i * 21, rv, zv);
@@ -149,13 +169,21 @@ __global__ void __launch_bounds__(kLmThreads) cg_update_kernel(const T* __restri
 #pragma unroll
     for (int k = 0; k < 6; ++k) { acc[0] += (double)rv[k] * (double)zv[k]; acc[1] += (double)rv[k] * (double)rv[k]; }
   }
-  if (reduce_sums<2>(acc, ws)) {
+  if (reduce_sums<2>(acc, ws)) {       // thread 0 of the last CTA: every CTA has read the state it needs by now
     cg[par ^ 1] = ws[0];
     cg[CG_RR] = ws[1];
     const double it = cg[CG_ITERS] + 1.0;
     cg[CG_ITERS] = it;
-    if (!(ws[1] > cg[CG_STOP2]) || it >= cg[CG_MAXIT]) cg[CG_DONE] = 1.0;
+    cg_after_update(cg, ws[1], it);
   }
+}
+// x <- xbest unless the solve converged or the last iterate is the best one (see the state enum)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) cg_finish_kernel(T* __restrict__ x, const T* __restrict__ xbest,
+                                                                const double* cg, long long n6) {
+  if (cg[CG_DONE] == 1.0 || cg[CG_SAVE] != 0.0) return;
+  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n6; i += (long long)gridDim.x * kLmThreads)
+    x[i] = xbest[i];
 }
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) cg_dir_kernel(const T* __restrict__ z, const T* __restrict__ D, int dmode,
@@ -208,11 +236,14 @@ template <int NS, int THREADS> __device__ __forceinline__ void block_sums(double
 template <typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS) cg_vec_small_kernel(const T* __restrict__ Minv, const T* __restrict__ D, int dmode,
                                                                     T* __restrict__ x, T* __restrict__ r, T* __restrict__ z,
-                                                                    T* __restrict__ p, T* __restrict__ q, double* cg, int par,
+                                                                    T* __restrict__ p, T* __restrict__ q,
+                                                                    T* __restrict__ xbest, double* cg, int par,
                                                                     long long n) {
   __shared__ double sh[32][2];
+  __shared__ double done_sh;
   if (cg[CG_DONE] != 0.0) return;
-  const double rz_old = cg[par], stop2 = cg[CG_STOP2], it = cg[CG_ITERS] + 1.0, maxit = cg[CG_MAXIT];
+  const double rz_old = cg[par], it = cg[CG_ITERS] + 1.0;
+  const bool save = cg[CG_SAVE] != 0.0;
   double a1[2] = {0.0, 0.0}, s1[2];
   for (long long i = threadIdx.x; i < n; i += THREADS)
 #pragma unroll
@@ -228,6 +259,7 @@ __global__ void __launch_bounds__(THREADS) cg_vec_small_kernel(const T* __restri
   for (long long i = threadIdx.x; i < n; i += THREADS) {
     T pv[6], qv[6], xv[6], rv[6], zv[6];
     ld6(p, i, pv); ld6(q, i, qv); ld6(x, i, xv); ld6(r, i, rv);
+    if (save) st6(xbest, i, xv);
 #pragma unroll
     for (int k = 0; k < 6; ++k) { xv[k] += alpha * pv[k]; rv[k] -= alpha * qv[k]; }
     sym6_mv_packed(Minv + i * 21, rv, zv);
@@ -236,12 +268,13 @@ __global__ void __launch_bounds__(THREADS) cg_vec_small_kernel(const T* __restri
     for (int k = 0; k < 6; ++k) { a2[0] += (double)rv[k] * (double)zv[k]; a2[1] += (double)rv[k] * (double)rv[k]; }
   }
   block_sums<2, THREADS>(a2, sh, s2);
-  const bool done = !(s2[1] > stop2) || it >= maxit;
   if (threadIdx.x == 0) {
     cg[CG_PQ] = pq; cg[par ^ 1] = s2[0]; cg[CG_RR] = s2[1]; cg[CG_ITERS] = it;
-    if (done) cg[CG_DONE] = 1.0;
+    cg_after_update(cg, s2[1], it);
+    done_sh = cg[CG_DONE];
   }
-  if (done) return;
+  __syncthreads();
+  if (done_sh != 0.0) return;
   const T beta = (T)(s2[0] / rz_old);
   for (long long i = threadIdx.x; i < n; i += THREADS) {     // the same thread wrote z[i] above
     T pv[6], zv[6], qv[6];
@@ -254,35 +287,16 @@ __global__ void __launch_bounds__(THREADS) cg_vec_small_kernel(const T* __restri
 }
 
 template <typename T>
-static void launch_cg_vec_small(const T* Minv, const T* D, int dmode, T* x, T* r, T* z, T* p, T* q, double* cg, int par,
-                                long long n, cudaStream_t st) {
+static void launch_cg_vec_small(const T* Minv, const T* D, int dmode, T* x, T* r, T* z, T* p, T* q, T* xbest, double* cg,
+                                int par, long long n, cudaStream_t st) {
   static const int env = getenv("B200POSE_CG_VEC_THREADS") ? atoi(getenv("B200POSE_CG_VEC_THREADS")) : 0;
   const int th = env ? env : (n <= 2048 ? 256 : (n <= 3072 ? 512 : 1024));     // measured: 256 beats 1024 at 1e3 rows
-  if (th == 256) cg_vec_small_kernel<T, 256><<<1, 256, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
-  else if (th == 512) cg_vec_small_kernel<T, 512><<<1, 512, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
-  else cg_vec_small_kernel<T, 1024><<<1, 1024, 0, st>>>(Minv, D, dmode, x, r, z, p, q, cg, par, n);
+  if (th == 256) cg_vec_small_kernel<T, 256><<<1, 256, 0, st>>>(Minv, D, dmode, x, r, z, p, q, xbest, cg, par, n);
+  else if (th == 512) cg_vec_small_kernel<T, 512><<<1, 512, 0, st>>>(Minv, D, dmode, x, r, z, p, q, xbest, cg, par, n);
+  else cg_vec_small_kernel<T, 1024><<<1, 1024, 0, st>>>(Minv, D, dmode, x, r, z, p, q, xbest, cg, par, n);
 }
 
-// ---- operators ---------------------------------------------------------------------------------------------------
-// Rows of one observation rebuilt from 16 B: Y4[k] = (y = T_c p, sqrt(rho')) and the camera quaternion (gathered, the
-// observations are grouped by camera so a warp mostly shares it).  jc0/jc1 = d r / d xi_c (2x6), jp0/jp1 = d r / d p (2x3).
-template <typename T> struct ObsRows { T jc0[6], jc1[6], jp0[3], jp1[3]; };
-template <typename T>
-__device__ __forceinline__ void obs_rows(const T* __restrict__ Y4, const T* __restrict__ poses, long long k, long long c,
-                                         ObsRows<T>& R) {
-  const T yx = Y4[k * 4], yy = Y4[k * 4 + 1], yz = Y4[k * 4 + 2], sw = Y4[k * 4 + 3];
-  Elem<T> Tc;
-  Tc.q.v = mk(__ldg(poses + c * 7 + 3), __ldg(poses + c * 7 + 4), __ldg(poses + c * 7 + 5));
-  Tc.q.w = __ldg(poses + c * 7 + 6);
-  const V3<T> y = mk(yx, yy, yz);
-  reproj_rows(y, R.jc0, R.jc1);
-  reproj_point_rows(Tc, y, R.jp0, R.jp1);
-#pragma unroll
-  for (int a = 0; a < 6; ++a) { R.jc0[a] *= sw; R.jc1[a] *= sw; }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) { R.jp0[a] *= sw; R.jp1[a] *= sw; }
-}
-
+// ---- operators (ObsRows / obs_rows: lm_common.cuh) -----------------------------------------------------------------
 // pose graph: q += H p edge by edge (lm.cu lm_pgo_spmv_kernel), skipped once the CG has finished
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) pcg_pgo_spmv_kernel(const T* __restrict__ M, const int* __restrict__ ei,
@@ -384,24 +398,6 @@ __global__ void __launch_bounds__(kLmThreads) pcg_pgo_spmv_gather_kernel(const T
   }
 }
 
-// bundle adjustment: t[j] += Jp^T (Jc x[c])
-template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
-                                                                 const int* __restrict__ cidx, const int* __restrict__ pidx,
-                                                                 const T* __restrict__ x, T* __restrict__ t, const double* cg,
-                                                                 long long m) {
-  if (cg && cg[CG_DONE] != 0.0) return;
-  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
-    const long long c = cidx[k], j = pidx[k];
-    ObsRows<T> R;
-    obs_rows(Y4, poses, k, c, R);
-    T v0 = T(0), v1 = T(0);
-#pragma unroll
-    for (int a = 0; a < 6; ++a) { const T xa = __ldg(x + c * 6 + a); v0 += R.jc0[a] * xa; v1 += R.jc1[a] * xa; }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) atomicAdd(t + j * 3 + a, R.jp0[a] * v0 + R.jp1[a] * v1);
-  }
-}
 // u[j] = alpha * Hp^-1_j (t0[j] + sum_{k in obs(j)} Jp_k^T Jc_k x[c_k])   — W^T x by GATHER over a point-ordered copy
 // of the per-observation data (Y4p, cidx_p; pptr = offsets per point), so there are no atomics, no zero-fill of
 // a (P,3) buffer, the result is deterministic, and the 3x3 point-block inverse is applied while the sum is in registers.
@@ -447,93 +443,6 @@ __global__ void __launch_bounds__(kLmThreads) pcg_ba_wtx_gather_kernel(const T* 
 #pragma unroll
       for (int a = 0; a < 3; ++a) u[j * 3 + a] = alpha * (A[a][0] * t[0] + A[a][1] * t[1] + A[a][2] * t[2]);
     }
-  }
-}
-// y[c] -= Jc^T Jp Hp^-1 t[j]   (W Hpp^-1 t; the point-block inverse is applied per observation: 9 cached loads
-// instead of a separate (P,3) pass)
-template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pcg_ba_wv_pinv_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
-                                                                     const int* __restrict__ cidx,
-                                                                     const int* __restrict__ pidx, const T* __restrict__ Hpinv,
-                                                                     const T* __restrict__ t, T* __restrict__ y,
-                                                                     const double* cg, long long m) {
-  if (cg && cg[CG_DONE] != 0.0) return;
-  const int lane = threadIdx.x & 31;
-  for (long long k0 = (long long)blockIdx.x * kLmThreads + (threadIdx.x - lane); k0 < m; k0 += (long long)gridDim.x * kLmThreads) {
-    const long long k = k0 + lane;
-    const bool active = k < m;
-    long long c = 0;
-    T out[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-    if (active) {
-      c = cidx[k];
-      const long long j = pidx[k];
-      const T t0 = __ldg(t + j * 3), t1 = __ldg(t + j * 3 + 1), t2 = __ldg(t + j * 3 + 2);
-      T v[3] = {t0, t1, t2};
-      if (Hpinv) {                       // NULL: t already holds Hp^-1 t (pcg_ba_wtx_gather_kernel)
-        T A[3][3];
-        T h[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) h[a] = __ldg(Hpinv + j * 6 + a);
-        sym3_unpack(h, A);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) v[a] = A[a][0] * t0 + A[a][1] * t1 + A[a][2] * t2;
-      }
-      ObsRows<T> R;
-      obs_rows(Y4, poses, k, c, R);
-      T u0 = T(0), u1 = T(0);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { u0 += R.jp0[a] * v[a]; u1 += R.jp1[a] * v[a]; }
-#pragma unroll
-      for (int a = 0; a < 6; ++a) out[a] = -(R.jc0[a] * u0 + R.jc1[a] * u1);
-    }
-    seg_atomic_add<T, 6>(y + c * 6, c, out, active);
-  }
-}
-// Sd[c] -= (Jc^T Jp) Hp^-1 (Jp^T Jc)   (diagonal blocks of the Schur complement, packed 21; Sd pre-set to damped Hcc)
-template <typename T>
-__global__ void __launch_bounds__(kLmThreads) ba_schur_diag_kernel(const T* __restrict__ Y4, const T* __restrict__ poses,
-                                                                    const int* __restrict__ cidx, const int* __restrict__ pidx,
-                                                                    const T* __restrict__ Hpinv, T* __restrict__ Sd,
-                                                                    long long m) {
-  const int lane = threadIdx.x & 31;
-  for (long long k0 = (long long)blockIdx.x * kLmThreads + (threadIdx.x - lane); k0 < m; k0 += (long long)gridDim.x * kLmThreads) {
-    const long long k = k0 + lane;
-    const bool active = k < m;
-    long long c = 0;
-    T out[21];
-#pragma unroll
-    for (int a = 0; a < 21; ++a) out[a] = T(0);
-    if (active) {
-      c = cidx[k];
-      const long long j = pidx[k];
-      T A[3][3], h[6];
-#pragma unroll
-      for (int a = 0; a < 6; ++a) h[a] = __ldg(Hpinv + j * 6 + a);
-      sym3_unpack(h, A);
-      // G = Jp Hp^-1 Jp^T (2x2), then T_k = Jc^T G Jc
-      T jp[2][3], jc[2][6], B[2][3];
-      ObsRows<T> R;
-      obs_rows(Y4, poses, k, c, R);
-#pragma unroll
-      for (int a = 0; a < 3; ++a) { jp[0][a] = R.jp0[a]; jp[1][a] = R.jp1[a]; }
-#pragma unroll
-      for (int a = 0; a < 6; ++a) { jc[0][a] = R.jc0[a]; jc[1][a] = R.jc1[a]; }
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int a = 0; a < 3; ++a) B[r][a] = jp[r][0] * A[0][a] + jp[r][1] * A[1][a] + jp[r][2] * A[2][a];
-      const T g00 = B[0][0] * jp[0][0] + B[0][1] * jp[0][1] + B[0][2] * jp[0][2];
-      const T g01 = B[0][0] * jp[1][0] + B[0][1] * jp[1][1] + B[0][2] * jp[1][2];
-      const T g11 = B[1][0] * jp[1][0] + B[1][1] * jp[1][1] + B[1][2] * jp[1][2];
-      int q = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        const T l0 = jc[0][a] * g00 + jc[1][a] * g01, l1 = jc[0][a] * g01 + jc[1][a] * g11;
-#pragma unroll
-        for (int b = a; b < 6; ++b) out[q++] = -(l0 * jc[0][b] + l1 * jc[1][b]);
-      }
-    }
-    seg_atomic_add<T, 21>(Sd + c * 21, c, out, active);
   }
 }
 // ws[0] = sum_k (J_k d)^T (2 r_k + J_k d) with J_k d = Jc x_c + Jp x_p    (strategy.py:143 'predicted')
@@ -659,6 +568,7 @@ template <typename Key, typename F> static int replay_or_launch(const Key& key, 
 }
 struct PcgKey {                                   // every launch argument of a chunk (padding zeroed by the caller)
   const void* ptr[20];
+  const void* ptr2;
   long long num[8];
   double tol;
   int tag, dev;
@@ -670,13 +580,13 @@ struct PcgKey {                                   // every launch argument of a 
 // ib = nptr), no atomics, bit-reproducible; selected with B200POSE_DETERMINISTIC=1.
 template <typename CT, bool GATHER>
 static int pgo_pcg_run(const CT* A, const int* ia, const int* ib, long long E, const CT* Minv, const CT* extra, const CT* g,
-                       CT* x, CT* r, CT* z, CT* p, CT* q, double* cg, double* ws, double tol, long long maxiter,
+                       CT* x, CT* r, CT* z, CT* p, CT* q, CT* xbest, double* cg, double* ws, double tol, long long maxiter,
                        long long first_iter, long long iters, long long n, cudaStream_t user) {
   if (n <= 0) return 0;
   PcgKey key;
   memset(&key, 0, sizeof(key));
-  const void* ptrs[] = {A, ia, ib, Minv, extra, g, x, r, z, p, q, cg, ws};
-  for (int i = 0; i < 13; ++i) key.ptr[i] = ptrs[i];
+  const void* ptrs[] = {A, ia, ib, Minv, extra, g, x, r, z, p, q, cg, ws, xbest};
+  for (int i = 0; i < 14; ++i) key.ptr[i] = ptrs[i];
   key.num[0] = E; key.num[1] = maxiter; key.num[2] = first_iter; key.num[3] = iters; key.num[4] = n;
   key.tol = tol; key.tag = (GATHER ? 2 : 1) + 16 * (int)sizeof(CT);
   cudaGetDevice(&key.dev);
@@ -688,26 +598,29 @@ static int pgo_pcg_run(const CT* A, const int* ia, const int* ib, long long E, c
       if (GATHER) LM_LAUNCH(pcg_pgo_spmv_gather_kernel<CT>, n * kLanesPerNode, stream, A, ia, ib, extra, p, q, cg, n);
       else if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, A, ia, ib, p, q, cg, E);
       if (n <= kVecSmallRows) {
-        launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, cg, par, n, stream);
+        launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, xbest, cg, par, n, stream);
         continue;
       }
       LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
-      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, xbest, cg, ws, par, n);
       LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, 1, p, q, cg, par, n);
     }
   });
 }
 template <typename CT>
-static int ba_pcg_run(const CT* Y4, const CT* poses, const int* cidx, const int* pidx, long long m, const CT* Y4p,
-                      const int* cidx_p, const int* pptr, const CT* Hc, const CT* Hpinv, const CT* Minv, const CT* bneg,
-                      CT* x, CT* r, CT* z, CT* p, CT* q, CT* t, double* cg, double* ws, double tol, long long maxiter,
+static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int* cseg, long long split, long long tpi,
+                      long long m, const CT* Y4p, const int* cidx_p, const int* pptr, const CT* Hc, const CT* Hpinv,
+                      const CT* Minv, const CT* bneg, CT* x, CT* r, CT* z, CT* p, CT* q, CT* t, CT* part, CT* xbest,
+                      double* cg, double* ws, double tol, long long maxiter,
                       long long P, long long first_iter, long long iters, long long n, cudaStream_t user) {
   if (n <= 0) return 0;
   PcgKey key;
   memset(&key, 0, sizeof(key));
-  const void* ptrs[] = {Y4, poses, cidx, pidx, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, q, t, cg, ws};
-  for (int i = 0; i < 19; ++i) key.ptr[i] = ptrs[i];
+  const void* ptrs[] = {Y4, poses, cseg, pidx, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, q, t, cg, ws, part};
+  for (int i = 0; i < 20; ++i) key.ptr[i] = ptrs[i];
+  key.ptr2 = xbest;
   key.num[0] = m; key.num[1] = maxiter; key.num[2] = first_iter; key.num[3] = iters; key.num[4] = n; key.num[5] = P;
+  key.num[6] = split; key.num[7] = tpi;
   key.tol = tol; key.tag = 3 + 16 * (int)sizeof(CT);
   cudaGetDevice(&key.dev);
   return replay_or_launch(key, user, [&](cudaStream_t stream) {
@@ -718,14 +631,14 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* cidx, const int*
       if (m > 0) {
         LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4p, poses, cidx_p, pptr, Hpinv, p,
                   (const CT*)nullptr, (CT)1, t, cg, P);
-        LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, (const CT*)nullptr, t, q, cg, m);
+        ba_wv_seg_launch<CT>(Y4, poses, pidx, cseg, (int)split, (int)tpi, (const CT*)nullptr, t, q, part, cg, n, stream);
       }
       if (n <= kVecSmallRows) {
-        launch_cg_vec_small<CT>(Minv, Hc, 2, x, r, z, p, q, cg, par, n, stream);
+        launch_cg_vec_small<CT>(Minv, Hc, 2, x, r, z, p, q, xbest, cg, par, n, stream);
         continue;
       }
       LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
-      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, cg, ws, par, n);
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, xbest, cg, ws, par, n);
       LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, Hc, 2, p, q, cg, par, n);
     }
   });
@@ -763,17 +676,22 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* cidx, const int*
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_pcg_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* Minv,       \
-                                        const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q, double* cg,  \
-                                        double* ws, double tol, long long maxiter, long long first_iter,              \
+                                        const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q, CT* xbest,   \
+                                        double* cg, double* ws, double tol, long long maxiter, long long first_iter,  \
                                         long long iters, long long n, void* stream) {                                 \
-    return pgo_pcg_run<CT, false>(M, ei, ej, E, Minv, extra, g, x, r, z, p, q, cg, ws, tol, maxiter, first_iter,      \
-                                  iters, n, (cudaStream_t)stream);                                                    \
+    return pgo_pcg_run<CT, false>(M, ei, ej, E, Minv, extra, g, x, r, z, p, q, xbest, cg, ws, tol, maxiter,           \
+                                  first_iter, iters, n, (cudaStream_t)stream);                                        \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_cg_finish_##SFX(CT* x, const CT* xbest, const double* cg, long long n, void* stream) {      \
+    if (n <= 0) return 0;                                                                                             \
+    LM_LAUNCH(cg_finish_kernel<CT>, n * 6, stream, x, xbest, cg, n * 6);                                              \
+    return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_pcg_gather_##SFX(const CT* Mn, const int* nother, const int* nptr, const CT* Minv,      \
                                                const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q,       \
-                                               double* cg, double* ws, double tol, long long maxiter,                 \
+                                               CT* xbest, double* cg, double* ws, double tol, long long maxiter,      \
                                                long long first_iter, long long iters, long long n, void* stream) {    \
-    return pgo_pcg_run<CT, true>(Mn, nother, nptr, 0, Minv, extra, g, x, r, z, p, q, cg, ws, tol, maxiter,            \
+    return pgo_pcg_run<CT, true>(Mn, nother, nptr, 0, Minv, extra, g, x, r, z, p, q, xbest, cg, ws, tol, maxiter,     \
                                  first_iter, iters, n, (cudaStream_t)stream);                                         \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_predicted_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* D,    \
@@ -788,18 +706,6 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* cidx, const int*
     LM_LAUNCH(pgo_predicted_edge_kernel<CT>, E, stream, M0, u0, ei, ej, D, ws, E);                                    \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_schur_diag_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,        \
-                                              const CT* Hpinv, CT* Sd, long long m, void* stream) {                   \
-    if (m <= 0) return 0;                                                                                             \
-    LM_LAUNCH(ba_schur_diag_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, Sd, m);                              \
-    return (int)cudaGetLastError();                                                                                   \
-  }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_wv_pinv_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,           \
-                                           const CT* Hpinv, const CT* t, CT* y, long long m, void* stream) {          \
-    if (m <= 0) return 0;                                                                                             \
-    LM_LAUNCH(pcg_ba_wv_pinv_kernel<CT>, m, stream, Y4, poses, cidx, pidx, Hpinv, t, y, (const double*)nullptr, m);   \
-    return (int)cudaGetLastError();                                                                                   \
-  }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_wtx_gather_##SFX(const CT* Y4p, const CT* poses, const int* cidx_p, const int* pptr,     \
                                               const CT* Hpinv, const CT* x, const CT* t0, double alpha, CT* u,        \
                                               long long P, void* stream) {                                            \
@@ -808,20 +714,15 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* cidx, const int*
               (CT)alpha, u, (const double*)nullptr, P);                                                                             \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_wtx_y_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx,             \
-                                         const CT* x, CT* t, long long m, void* stream) {                             \
-    if (m <= 0) return 0;                                                                                             \
-    LM_LAUNCH(pcg_ba_wtx_kernel<CT>, m, stream, Y4, poses, cidx, pidx, x, t, (const double*)nullptr, m);              \
-    return (int)cudaGetLastError();                                                                                   \
-  }                                                                                                                   \
-  B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Y4, const CT* poses, const int* cidx, const int* pidx, long long m,  \
+  B200_EXPORT int b200_lm_ba_pcg_##SFX(const CT* Y4, const CT* poses, const int* pidx, const int* cseg,               \
+                                       long long split, long long tpi, long long m,                                   \
                                        const CT* Y4p, const int* cidx_p, const int* pptr, const CT* Hc,               \
                                        const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r, CT* z, CT* p,   \
-                                       CT* q, CT* t, double* cg, double* ws, double tol, long long maxiter,           \
-                                       long long P, long long first_iter, long long iters, long long n,               \
-                                       void* stream) {                                                                \
-    return ba_pcg_run<CT>(Y4, poses, cidx, pidx, m, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, q, t, cg,   \
-                          ws, tol, maxiter, P, first_iter, iters, n, (cudaStream_t)stream);                           \
+                                       CT* q, CT* t, CT* part, CT* xbest, double* cg, double* ws, double tol,         \
+                                       long long maxiter, long long P, long long first_iter, long long iters,         \
+                                       long long n, void* stream) {                                                   \
+    return ba_pcg_run<CT>(Y4, poses, pidx, cseg, split, tpi, m, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, \
+                          q, t, part, xbest, cg, ws, tol, maxiter, P, first_iter, iters, n, (cudaStream_t)stream);    \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_predicted_##SFX(const CT* Y4, const CT* poses, const CT* rs, const int* cidx,            \
                                              const int* pidx, const CT* xc, const CT* xp, double* ws, long long m,    \

@@ -143,22 +143,6 @@ def _ba_linearize(poses, points, pix, cidx, pidx, robust=0, delta=1.0):
     return Jc, Jp, rs, Hcc, Hpp, gc, gp, ws[:1].clone()
 
 
-def ba_linearize_y(poses, points, pix, cidx, pidx, robust=0, delta=1.0, ppos=None):
-    """As _ba_linearize, storing Y4 (m,4) = (T p, sqrt(rho')) instead of the Jacobian rows (device PCG route); with
-    `ppos` (position of each observation in point order) also the point-ordered copy Y4p."""
-    poses, points, pix = _same(poses, points, pix)
-    m, C, P = pix.shape[0], poses.shape[0], points.shape[0]
-    dt, dev = poses.dtype, poses.device
-    ws = _workspace(dev)
-    Y4, rs = torch.empty(m, 4, dtype=dt, device=dev), torch.empty(m, 2, dtype=dt, device=dev)
-    Y4p = torch.empty(m, 4, dtype=dt, device=dev) if ppos is not None else None
-    Hcc, Hpp = torch.zeros(C, 21, dtype=dt, device=dev), torch.zeros(P, 6, dtype=dt, device=dev)
-    gc, gp = torch.zeros(C, 6, dtype=dt, device=dev), torch.zeros(P, 3, dtype=dt, device=dev)
-    _launch("b200_lm_ba_linearize_y", poses, [_p(poses), _p(points), _p(pix), _p(cidx), _p(pidx), _p(Y4), _p(ppos), _p(Y4p),
-                                              _p(rs), _p(Hcc), _p(Hpp), _p(gc), _p(gp), _p(ws), int(robust), float(delta)], m)
-    return (Y4, Y4p), rs, Hcc, Hpp, gc, gp, ws[:1].clone()
-
-
 def _ba_wtx(Jc, Jp, cidx, pidx, x, npts):
     t = torch.zeros(npts, 3, dtype=Jc.dtype, device=Jc.device)
     x = x.contiguous()
@@ -286,7 +270,7 @@ def _cg(device):
     key = (device.type, device.index)
     s = _cg_state.get(key)
     if s is None:
-        s = _cg_state[key] = torch.zeros(8, dtype=torch.float64, device=device)
+        s = _cg_state[key] = torch.zeros(16, dtype=torch.float64, device=device)
     return s
 
 
@@ -323,16 +307,17 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     extra = torch.empty(n, 6, dtype=dt, device=dev)
     Minv = torch.empty(n, 21, dtype=dt, device=dev)
     _launch("b200_lm_blk6_damp_inv", M, [_p(Hd), float(scale), float(dmin), float(dmax), _p(None), _p(extra), _p(Minv)], n)
-    x, r, z, p, q = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(5))
+    x, r, z, p, q, xbest = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(6))
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
     if node is None:
         iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg", M, [
-            _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg), _p(ws),
-            float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+            _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest), _p(cg),
+            _p(ws), float(tol), maxiter, it0, k], n), cg, maxiter, hint)
     else:
         iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg_gather", M, [
-            _p(node[0]), _p(node[1]), _p(node[2]), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(cg),
-            _p(ws), float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+            _p(node[0]), _p(node[1]), _p(node[2]), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest),
+            _p(cg), _p(ws), float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+    _launch("b200_lm_cg_finish", M, [_p(x), _p(xbest), _p(cg)], n)     # best iterate unless the solve converged
     if unweighted is None:
         _launch("b200_lm_pgo_predicted", M, [_p(M), _p(ei), _p(ej), E, _p(x), _p(g), _p(ws)], n)
     else:
@@ -340,31 +325,53 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     return x, iters, ws[:1].clone()
 
 
-def ba_solve(Y4s, poses, rs, cidx, pidx, cidx_p, pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
+def ba_linearize_det(poses, points, pix, pidx, geom, robust=0, delta=1.0):
+    """Deterministic BA linearisation (csrc/ba.cu): Y4 / Y4p / rs per observation, camera blocks with one writer per camera,
+    point blocks by gather.  `geom` = (cseg, split, tpi, ppos, cidx_p, pptr, pix_p) from BAProblem."""
+    cseg, split, tpi, ppos, cidx_p, pptr, pix_p = geom
+    poses, points, pix = _same(poses, points, pix)
+    m, C, P = pix.shape[0], poses.shape[0], points.shape[0]
+    dt, dev = poses.dtype, poses.device
+    ws = _workspace(dev)
+    Y4, Y4p, rs = (torch.empty(m, w, dtype=dt, device=dev) for w in (4, 4, 2))
+    Hcc, gc = torch.empty(C, 21, dtype=dt, device=dev), torch.empty(C, 6, dtype=dt, device=dev)
+    Hpp, gp = torch.empty(P, 6, dtype=dt, device=dev), torch.empty(P, 3, dtype=dt, device=dev)
+    part = torch.empty(C * split, 27, dtype=dt, device=dev) if split > 1 else None
+    _launch("b200_lm_ba_linearize_seg", poses, [_p(poses), _p(points), _p(pix), _p(pidx), _p(cseg), split, tpi, _p(Y4), _p(ppos),
+                                                _p(Y4p), _p(rs), _p(Hcc), _p(gc), _p(part), _p(ws), int(robust), float(delta)], C)
+    cur = ws[:1].clone()
+    _launch("b200_lm_ba_point_blocks", poses, [_p(Y4p), _p(pix_p), _p(poses), _p(cidx_p), _p(pptr), _p(Hpp), _p(gp)], P)
+    return (Y4, Y4p), rs, Hcc, Hpp, gc, gp, cur
+
+
+def ba_solve(Y4s, poses, rs, cidx, pidx, geom, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
     """Schur-complement solve of the damped BA normal equations by device PCG; the Jacobian rows are rebuilt from
-    Y4 (ba_linearize_y) and the poses it was linearised at.
+    Y4 (ba_linearize_det) and the poses it was linearised at.  No atomics: every camera / point sum has one writer.
     Returns xc (C,6), xp (P,3), iterations, predicted (1,) fp64 on device."""
-    Y4, Y4p = Y4s                                         # camera-ordered and point-ordered rows (ba_linearize_y)
+    Y4, Y4p = Y4s                                         # camera-ordered and point-ordered rows
+    cseg, split, tpi, _, cidx_p, pptr, _ = geom
     dev, dt = Y4.device, Y4.dtype
     m, C, P = Y4.shape[0], Hcc.shape[0], Hpp.shape[0]
     ws, cg = _workspace(dev), _cg(dev)
     Hc = torch.empty(C, 21, dtype=dt, device=dev)
     Hpinv = torch.empty(P, 6, dtype=dt, device=dev)
     Minv = torch.empty(C, 21, dtype=dt, device=dev)
-    J = [_p(Y4), _p(poses), _p(cidx), _p(pidx)]
+    part = torch.empty(C * split, 21, dtype=dt, device=dev) if split > 1 else None
+    seg = [_p(Y4), _p(poses), _p(pidx), _p(cseg), split, tpi]
     _launch("b200_lm_blk6_damp_inv", Y4, [_p(Hcc), float(scale), float(dmin), float(dmax), _p(Hc), _p(None), _p(None)], C)
     _launch("b200_lm_pt3_damp_inv", Y4, [_p(Hpp), float(scale), float(dmin), float(dmax), _p(Hpinv)], P)
     Sd = Hc.clone()
-    _launch("b200_lm_ba_schur_diag", Y4, [*J, _p(Hpinv), _p(Sd)], m)
+    _launch("b200_lm_ba_schur_diag_seg", Y4, [*seg, _p(Hpinv), _p(Sd), _p(part)], C)
     _launch("b200_lm_blk6_damp_inv", Y4, [_p(Sd), 1.0, -3.0e38, 3.0e38, _p(None), _p(None), _p(Minv)], C)
     bneg = gc.clone()                                     # -(rhs) = gc - W Hpp^-1 gp
-    _launch("b200_lm_ba_wv_pinv", Y4, [*J, _p(Hpinv), _p(gp), _p(bneg)], m)
-    x, r, z, p, q = (torch.empty(C, 6, dtype=dt, device=dev) for _ in range(5))
+    _launch("b200_lm_ba_wv_seg", Y4, [*seg, _p(Hpinv), _p(gp), _p(bneg), _p(part)], C)
+    x, r, z, p, q, xbest = (torch.empty(C, 6, dtype=dt, device=dev) for _ in range(6))
     t = torch.empty(P, 3, dtype=dt, device=dev)
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * C
     iters = _run_chunks(lambda it0, k: _launch("b200_lm_ba_pcg", Y4, [
-        *J, m, _p(Y4p), _p(cidx_p), _p(pptr), _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
-        _p(t), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter, hint)
+        *seg, m, _p(Y4p), _p(cidx_p), _p(pptr), _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
+        _p(t), _p(part), _p(xbest), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter, hint)
+    _launch("b200_lm_cg_finish", Y4, [_p(x), _p(xbest), _p(cg)], C)
     xp = torch.empty(P, 3, dtype=dt, device=dev)          # dp = -Hpp^-1 (gp + W^T dc)
     _launch("b200_lm_ba_wtx_gather", Y4, [_p(Y4p), _p(poses), _p(cidx_p), _p(pptr), _p(Hpinv), _p(x), _p(gp), -1.0, _p(xp)], P)
     _launch("b200_lm_ba_predicted", Y4, [_p(Y4), _p(poses), _p(rs), _p(cidx), _p(pidx), _p(x), _p(xp), _p(ws)], m)

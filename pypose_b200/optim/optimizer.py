@@ -20,7 +20,7 @@ from .corrector import FastTriggs
 from .functional import modjac
 from .solver import PINV, Cholesky
 from .strategy import TrustRegion
-from . import structured
+from . import _lmstep, structured
 
 
 class Trivial(torch.nn.Module):
@@ -228,9 +228,53 @@ class LevenbergMarquardt(_SecondOrder):
                                              self._robust, self.solver, self.sparse, weight)
         return self._problem
 
+    def _device_step(self, prob):
+        """The device-decided route (optim/_lmstep.py, csrc/lmstep.cu) applies to a block-diagonal family on one GPU with
+        one of the three reference strategies; everything else keeps the host-decided loop below."""
+        ds = getattr(prob, 'device_step', None)
+        if ds is None:
+            return None
+        return ds(self.strategy)
+
+    def _step_on_device(self, prob, pg, ds):
+        """optimizer.py:659-680 with the whole trial — incl. strategy.update, the accept test and the parameter update —
+        on the device: one C call and ONE host read per trial; a productive step is a single trial."""
+        cached = hasattr(self, 'loss')
+        last_f = 0.0
+        if cached:
+            if getattr(self, '_loss_t', None) is not self.loss:      # loss was set / replaced from outside
+                self._loss_f = float(self.loss)
+            last_f = self._loss_f
+        self.reject_count = 0
+        scale, retry = 1.0, False
+        state = ds.new_state()
+        while True:
+            scale *= 1.0 + pg['damping']
+            _lmstep.fill_ctl(ds.ctl, self.strategy, pg, last_f, cached, self.reject_count, self.reject)
+            st = prob.device_trial(ds, scale, pg['min'], pg['max'], retry)
+            status = st[_lmstep.ST_STATUS]
+            if not cached:                 # `self.last = self.loss = model.loss(...)` of the first ever step
+                last_f, cached = st[_lmstep.ST_CUR], True
+            self.last = state[_lmstep.ST_LAST]
+            if status == 2.0:              # solver.py:214-215 -> optimizer.py:669-671
+                print('Cholesky decomposition failed. Check your matrix (may not be positive-definite)',
+                      '\nLinear solver failed. Breaking optimization step...')
+                break
+            _lmstep.apply_state(self.strategy, pg, st)
+            self.reject_count = int(st[_lmstep.ST_REJECT])
+            if status == 1.0:
+                break
+            retry = True                   # rejected: parameters untouched, damping already updated
+        self.loss = state[_lmstep.ST_LOSS]
+        self._loss_f, self._loss_t = st[_lmstep.ST_LOSS], self.loss
+        return self.loss
+
     def _step_structured(self, prob, pg):
         """Same control flow as the dense branch below (optimizer.py:659-680), driven by host floats that
         come back from the device in ONE read per trial."""
+        ds = self._device_step(prob)
+        if ds is not None:
+            return self._step_on_device(prob, pg, ds)
         cached = hasattr(self, 'loss')
         if cached:
             if getattr(self, '_loss_t', None) is not self.loss:      # loss was set / replaced from outside

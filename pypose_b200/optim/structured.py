@@ -23,6 +23,7 @@ from .. import _C
 from ..lietensor import lietensor as _lt
 from ..lietensor.lietensor import LieTensor, Parameter, SE3_type
 from . import _fused  # noqa: F401  (registers the ops)
+from . import _lmstep
 
 ops = torch.ops.b200pose
 
@@ -95,6 +96,17 @@ class PoseInvProblem(_Problem):
     def accept(self):
         _copy_param(self.param, self._trial)
 
+    def device_step(self, strategy):
+        return _device_step(self, self.param, strategy)
+
+    def device_trial(self, ds, scale, dmin, dmax, retry):
+        if ds.comm is not None:
+            return _lmstep.poseinv_trial_peer(ds, self, scale, dmin, dmax, retry)
+        return _lmstep.poseinv_trial(ds, self, scale, dmin, dmax, retry)
+
+    def peer_payload(self):
+        return 0, 0, 256
+
 
 class ReprojProblem(_Problem):
     def __init__(self, model, data, key, group, robust=(0, 1.0), param=None):
@@ -149,6 +161,50 @@ class ReprojProblem(_Problem):
 
     def accept(self):
         _copy_param(self.param, self._trial)
+
+    def device_step(self, strategy):
+        return _device_step(self, self.param, strategy)
+
+    def device_trial(self, ds, scale, dmin, dmax, retry):
+        if self._buf is None:
+            poses = self._poses()
+            C = poses.shape[0]
+            self._buf = (poses.new_empty(C, 21), poses.new_empty(C, 6), torch.empty_like(poses))
+        if ds.comm is not None:
+            return _lmstep.reproj_trial_peer(ds, self, scale, dmin, dmax, retry)
+        return _lmstep.reproj_trial(ds, self, scale, dmin, dmax, retry)
+
+    def peer_payload(self):
+        import torch.distributed as dist
+        world = dist.get_world_size(None if self.group is True else self.group)
+        return _lmstep.reproj_payload(self._poses().shape[0], world, self.param.element_size())
+
+
+def _device_step(prob, param, strategy):
+    """DeviceStep buffers when the device-decided route applies: CUDA parameter stored contiguously (the kernels commit
+    the accepted trial straight into its storage), one rank, one of the three reference strategies."""
+    if getattr(prob, '_ds', None) is not None:
+        return prob._ds if _lmstep.strategy_kind(strategy) is not None else None
+    if getattr(prob, '_ds_tried', False):
+        return None
+    prob._ds_tried = True
+    if not param.is_cuda or _lmstep.strategy_kind(strategy) is None:
+        return None
+    if not param.is_contiguous() or os.environ.get("B200POSE_LM_HOST", "0") == "1":
+        return None
+    comm = None
+    if prob.group is not None:
+        # every rank reaches this point together (same model, same optimizer arguments): collective set-up of the NVLink
+        # exchange; if it is not available on some rank, all ranks keep the torch.distributed route
+        from .._comm import PeerComm
+        part_off, pt_off, nbytes = prob.peer_payload()
+        comm = PeerComm.create(prob.group, param.device, nbytes)
+        if comm is None:
+            return None
+    prob._ds = _lmstep.DeviceStep(param.device, param.dtype)
+    if comm is not None:
+        prob._ds.attach_comm(comm, part_off, pt_off)
+    return prob._ds
 
 
 def _bmv(A, x):
@@ -340,6 +396,15 @@ class BAProblem(_Problem):
         self.ppos[self.padj] = torch.arange(self.padj.numel(), dtype=torch.int32, device=self.padj.device)
         self.pptr = torch.zeros(P + 1, dtype=torch.int32, device=self.pl.device)
         self.pptr[1:] = torch.cumsum(torch.bincount(self.pl, minlength=P), 0).to(torch.int32)
+        # geometry of the deterministic device route (csrc/ba.cu): rows per camera, work items per camera (so that a few
+        # cameras with very many rows still fill the machine) and threads per item, point-ordered pixels
+        C, m = self.poses.tensor().reshape(-1, 7).shape[0], self.cidx.numel()
+        self.cseg = torch.zeros(C + 1, dtype=torch.int32, device=self.pl.device)
+        self.cseg[1:] = torch.cumsum(torch.bincount(self.cl, minlength=C), 0).to(torch.int32)
+        tpi = 128 if m >= 192 * C else 32
+        want = 148 * 8 * (128 // tpi)                      # items that fill the SMs
+        split = max(1, min(want // max(C, 1), (m // max(C, 1)) // (8 * tpi))) if C < want else 1
+        self.geom = (self.cseg, int(split), int(tpi), self.ppos, self.cidx_p, self.pptr, self.pix[self.padj].contiguous())
         self.tol, self.maxiter = tol, maxiter
         self._trial = None
         self.cg_iters = 0
@@ -358,8 +423,7 @@ class BAProblem(_Problem):
     def linearize(self):
         T, p = self._params()
         if T.is_cuda and self.group is None:          # device PCG route: 16 B per observation instead of the rows
-            Y4s, rs, Hcc, Hpp, gc, gp, cur = _fused.ba_linearize_y(T, p, self.pix, self.cidx, self.pidx, *self.robust,
-                                                                    ppos=self.ppos)
+            Y4s, rs, Hcc, Hpp, gc, gp, cur = _fused.ba_linearize_det(T, p, self.pix, self.pidx, self.geom, *self.robust)
             return Y4s, T, rs, Hcc, Hpp, gc, gp, cur
         Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = _fused.call("lm_ba_linearize", T, p, self.pix, self.cidx, self.pidx, *self.robust)
         if self.group is not None:
@@ -375,7 +439,7 @@ class BAProblem(_Problem):
         Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = lin
         C, P = Hcc.shape[0], Hpp.shape[0]
         if isinstance(Jc, tuple):                     # device-resident Schur PCG; (Jc, Jp) are ((Y4, Y4p), poses) here
-            xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, self.cidx_p, self.pptr, Hcc, Hpp,
+            xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, self.geom, Hcc, Hpp,
                                                           gc, gp, scale, dmin,
                                                           dmax, self.tol, self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0)
             return self._finish_trial(xc, xp, pred, cur)

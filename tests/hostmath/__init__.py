@@ -114,3 +114,12 @@ def imu_cov(Rk, Rij, a, dt, gcov, acov, init_cov, chunk):
                            ctypes.c_longlong(3 if gcov.shape[0] == F and F > 1 else 0), _vp(init_cov), _vp(cov),
                            ctypes.c_longlong(F), ctypes.c_longlong(chunk))
     return cov
+
+
+def lm_decide(ctl, cur, trial, predicted, failed):
+    """csrc/lm_math.cuh lm_decide on the host: ctl = 14 doubles (optim/_lmstep.py layout) -> 16-double state."""
+    c = np.ascontiguousarray(ctl, dtype=np.float64)
+    st = np.zeros(16)
+    lib().hostmath_lm_decide(_vp(c), ctypes.c_double(cur), ctypes.c_double(trial), ctypes.c_double(predicted),
+                             ctypes.c_double(failed), _vp(st))
+    return st

@@ -219,3 +219,12 @@ extern "C" void hostmath_imu_cov(int is64, const void* Rk, const void* Rij, cons
   if (is64) imu_cov_host<double>((const double*)Rk, (const double*)Rij, (const double*)a, (const double*)dt, (const double*)gcov, (const double*)acov, cov_stride_f, (const double*)init_cov, (double*)cov, F, chunk);
   else imu_cov_host<float>((const float*)Rk, (const float*)Rij, (const float*)a, (const float*)dt, (const float*)gcov, (const float*)acov, cov_stride_f, (const float*)init_cov, (float*)cov, F, chunk);
 }
+
+// ---- LM accept / reject decision (csrc/lm_math.cuh lm_decide) -----------------------------------------------------
+extern "C" void hostmath_lm_decide(const double* c, double cur, double trial, double predicted, double failed, double* st) {
+  LmCtl k;
+  k.last = c[0]; k.cached = c[1] != 0.0; k.damping = c[2]; k.pg_down = c[3]; k.reject_count = c[4]; k.reject_limit = c[5];
+  k.kind = (int)c[6]; k.high = c[7]; k.low = c[8]; k.up = c[9]; k.self_down = c[10]; k.factor = c[11]; k.smin = c[12];
+  k.smax = c[13];
+  lm_decide(k, cur, trial, predicted, failed, st);
+}

@@ -75,7 +75,7 @@ def test_fused_launch_sites_pass_as_many_arguments_as_the_abi_declares():
             depth += ch in "([{"
             depth -= ch in ")]}"
             n += ch == "," and depth == 0
-        n += 3 * args.count("*J")          # J = [Y4, poses, cidx, pidx]
+        n += 5 * args.count("*seg")        # seg = [Y4, poses, pidx, cseg, split, tpi]
         assert n == arity[name], (name, n, arity[name])
         seen += 1
     assert seen >= 30

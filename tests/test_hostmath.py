@@ -185,3 +185,48 @@ def test_structured_imu_covariance_vs_dense_oracle(F, chunk):
 
 def rand_group_so3(rng, n):
     return O.exp("SO3", rng.standard_normal((n, 3)))
+
+
+def test_lm_decide_equals_python_strategies_and_accept_rule():
+    """csrc/lm_math.cuh lm_decide (the device-side accept / reject + damping update of csrc/lmstep.cu) against the
+    Python strategy objects and the accept rule of optimizer.py:673-680, bit for bit, on random states."""
+    import ctypes
+    import pypose_b200 as pp
+    from pypose_b200.optim import _lmstep
+    rng = np.random.default_rng(5)
+    mk = {0: lambda: pp.optim.strategy.Constant(damping=float(10 ** rng.uniform(-8, 0))),
+          1: lambda: pp.optim.strategy.Adaptive(damping=float(10 ** rng.uniform(-8, 0)), high=0.5, low=1e-3,
+                                                up=float(rng.uniform(1.5, 4)), down=float(rng.uniform(0.1, 0.9))),
+          2: lambda: pp.optim.strategy.TrustRegion(radius=float(10 ** rng.uniform(0, 8)), up=float(rng.uniform(1.5, 4)),
+                                                   down=float(rng.uniform(0.1, 0.9)), factor=float(rng.uniform(0.1, 0.9)))}
+    for trial_id in range(600):
+        kind = trial_id % 3
+        strat = mk[kind]()
+        pg = dict(strat.defaults)
+        pg['damping'] = float(10 ** rng.uniform(-9, 3))
+        if kind == 2:
+            pg['down'] = float(10 ** rng.uniform(-5, 0))
+        last = float(10 ** rng.uniform(-6, 2))
+        cur = last if rng.random() < 0.5 else float(10 ** rng.uniform(-6, 2))
+        cached = bool(rng.random() < 0.7)
+        trial = float(last * 10 ** rng.uniform(-2, 0.3)) if rng.random() < 0.9 else last
+        predicted = -float(10 ** rng.uniform(-8, 2)) * (1 if rng.random() < 0.9 else -1)
+        failed = 1.0 if rng.random() < 0.05 else 0.0
+        rc, limit = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+        ctl = (ctypes.c_double * 14)()
+        _lmstep.fill_ctl(ctl, strat, pg, last, cached, rc, limit)
+        st = hostmath.lm_decide(list(ctl), cur, trial, predicted, failed)
+        eff_last = last if cached else cur
+        ref_pg = dict(pg)
+        if failed:
+            assert st[0] == 2.0 and st[1] == eff_last and st[6] == rc and st[3] == pg['damping']
+            continue
+        strat.update(ref_pg, last=eff_last, loss=trial, J=None, D=None, R=None, predicted=predicted)
+        reject = eff_last < trial and rc < limit
+        assert st[0] == (0.0 if reject else 1.0)
+        assert st[1] == (eff_last if reject else trial) and st[2] == eff_last
+        assert st[6] == (rc + 1 if reject else rc)
+        got = dict(pg)
+        _lmstep.apply_state(strat, got, list(st))
+        for k in ref_pg:
+            assert got[k] == ref_pg[k], (kind, k, got[k], ref_pg[k])

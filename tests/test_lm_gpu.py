@@ -433,18 +433,29 @@ def test_pgo_device_pcg_vs_dense_solve(maxiter):
     np.testing.assert_allclose(pred.cpu().numpy()[0], xv @ H @ xv + 2 * xv @ gv, rtol=1e-9)
 
 
+def _ba_geom(cidx, pidx, pix_t, C, P, split, tpi):
+    """The BAProblem geometry for camera-sorted observations (numpy index arrays, device pixel tensor)."""
+    padj = torch.from_numpy(np.argsort(pidx, kind="stable")).cuda()
+    ppos = torch.empty(len(pidx), dtype=torch.int32, device="cuda")
+    ppos[padj] = torch.arange(len(pidx), dtype=torch.int32, device="cuda")
+    pptr = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(pidx, minlength=P))]).astype(np.int32)).cuda()
+    cseg = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(cidx, minlength=C))]).astype(np.int32)).cuda()
+    ci = torch.from_numpy(cidx.astype(np.int32)).cuda()
+    return (cseg, split, tpi, ppos, ci[padj].contiguous(), pptr, pix_t[padj].contiguous()), padj
+
+
 @pytest.mark.parametrize("kind,delta", [(0, 1.0), (1, 0.02)])
-@pytest.mark.parametrize("sort_by_camera", [False, True])
-def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera, kind, delta):
-    """b200_lm_ba_pcg & co. against a dense numpy solve of the full damped normal equations; with observations
-    grouped by camera the warp-aggregated scatter path runs, otherwise the per-lane fallback."""
+@pytest.mark.parametrize("split,tpi", [(1, 32), (1, 128), (3, 32), (2, 128)])
+def test_ba_device_schur_pcg_vs_dense_solve(split, tpi, kind, delta):
+    """b200_lm_ba_linearize_seg / point_blocks / schur_diag_seg / ba_pcg (csrc/ba.cu, no atomics) against the stored-row
+    kernels, the oracle and a dense numpy solve of the full damped normal equations; every (items per camera, threads per
+    item) layout; two runs are bit-identical."""
     from pypose_b200.optim import _fused as F
     rng = np.random.default_rng(23)
     C, P = 12, 150
     gt, ptsw, T0, p0, pix, cidx, pidx = _ba_problem(rng, C, P, 5, pix_noise=0.01)
-    if sort_by_camera:
-        o = np.argsort(cidx, kind="stable")
-        pix, cidx, pidx = pix[o], cidx[o], pidx[o]
+    o = np.argsort(cidx, kind="stable")
+    pix, cidx, pidx = pix[o], cidx[o], pidx[o]
     dt = torch.float64
     ci, pi_ = torch.from_numpy(cidx.astype(np.int32)).cuda(), torch.from_numpy(pidx.astype(np.int32)).cuda()
     Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = ops.lm_ba_linearize(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, kind, delta)
@@ -452,15 +463,15 @@ def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera, kind, delta):
     for a, b in zip((Jc, Jp, rs, Hcc, Hpp, gc, gp), outs_o):
         assert np.abs(a.cpu().numpy() - b).max() <= 1e-9 * max(1.0, np.abs(b).max())
     scale, dmin, dmax = 1.0 + 1e-4, 1e-6, 1e32
-    padj = torch.from_numpy(np.argsort(pidx, kind="stable")).cuda()
-    ppos = torch.empty(len(pidx), dtype=torch.int32, device="cuda")
-    ppos[padj] = torch.arange(len(pidx), dtype=torch.int32, device="cuda")
-    Y4s, rs_y, Hcc_y, Hpp_y, gc_y, gp_y, cur_y = F.ba_linearize_y(cu(T0, dt), cu(p0, dt), cu(pix, dt), ci, pi_, kind, delta, ppos=ppos)
+    geom, padj = _ba_geom(cidx, pidx, cu(pix, dt), C, P, split, tpi)
+    Y4s, rs_y, Hcc_y, Hpp_y, gc_y, gp_y, cur_y = F.ba_linearize_det(cu(T0, dt), cu(p0, dt), cu(pix, dt), pi_, geom, kind, delta)
     assert torch.equal(Y4s[1], Y4s[0][padj])
     for a, b in ((rs_y, rs), (Hcc_y, Hcc), (Hpp_y, Hpp), (gc_y, gc), (gp_y, gp), (cur_y, cur)):
         assert (a - b).abs().max().item() <= 1e-9 * max(1.0, b.abs().max().item())
-    pptr = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(pidx, minlength=P))]).astype(np.int32)).cuda()
-    xc, xp, iters, pred = F.ba_solve(Y4s, cu(T0, dt), rs, ci, pi_, ci[padj].contiguous(), pptr, Hcc, Hpp, gc, gp, scale, dmin, dmax, 1e-13, 400)
+    xc, xp, iters, pred = F.ba_solve(Y4s, cu(T0, dt), rs, ci, pi_, geom, Hcc_y, Hpp_y, gc_y, gp_y, scale, dmin, dmax, 1e-13, 400)
+    again = F.ba_linearize_det(cu(T0, dt), cu(p0, dt), cu(pix, dt), pi_, geom, kind, delta)
+    xc2, xp2, iters2, pred2 = F.ba_solve(again[0], cu(T0, dt), again[1], ci, pi_, geom, *again[2:6], scale, dmin, dmax, 1e-13, 400)
+    assert torch.equal(xc, xc2) and torch.equal(xp, xp2) and iters == iters2 and torch.equal(pred, pred2)   # bit-reproducible
     m = len(cidx)
     J = np.zeros((2 * m, 6 * C + 3 * P))
     Jcn, Jpn = Jc.cpu().numpy().reshape(m, 2, 6), Jp.cpu().numpy().reshape(m, 2, 3)
@@ -479,6 +490,35 @@ def test_ba_device_schur_pcg_vs_dense_solve(sort_by_camera, kind, delta):
     np.testing.assert_allclose(pred.cpu().numpy()[0], Jd @ (2 * R + Jd), rtol=1e-9)
     y = ops.lm_ba_wv(Jc, Jp, ci, pi_, cu(rng.standard_normal((P, 3)), dt) * 0 + 1.0, C).cpu().numpy()
     np.testing.assert_allclose(y, L.ba_wv(outs_o[0], outs_o[1], cidx, pidx, np.ones((P, 3)), C), rtol=1e-9, atol=1e-9)
+
+
+def _smoke_ba(dev, dtype=torch.float32, tol=1e-6):
+    """The bundle-adjustment block of smoke() (gauge-free, 6 cameras, fp32, PCG tolerance below what fp32 reaches)."""
+    torch.manual_seed(0)
+    Cb, Pb, per = 6, 80, 3
+    gtb = pp.se3(0.2 * torch.randn(Cb, 6, device=dev, dtype=dtype)).Exp()
+    ptw = (torch.rand(Pb, 3, device=dev, dtype=dtype) * torch.tensor([4.0, 4.0, 3.0], device=dev, dtype=dtype)
+           + torch.tensor([-2.0, -2.0, 3.0], device=dev, dtype=dtype))
+    pidx = torch.arange(Pb, device=dev).repeat_interleave(per)
+    cidx = (pidx + torch.arange(per, device=dev).repeat(Pb) * 2) % Cb
+    yb = gtb[cidx].Act(ptw[pidx])
+    ba = pp.module.BundleAdjustment(pp.se3(0.02 * torch.randn(Cb, 6, device=dev, dtype=dtype)).Exp() * gtb,
+                                    ptw + 0.03 * torch.randn(Pb, 3, device=dev, dtype=dtype))
+    opt = pp.optim.LM(ba, solver=pp.optim.solver.PCG(tol=tol), sparse=True)
+    inp = (-yb[:, :2] / yb[:, 2:], cidx, pidx)
+    losses = [float(opt.step(inp)) for _ in range(3)]
+    return losses, ba.poses.tensor().clone(), ba.points_3d.detach().clone()
+
+
+def test_smoke_bundle_adjustment_is_reproducible_and_converges():
+    """the smoke() BA scenario gave 30 different outcomes in 30 runs (atomics + fp32 CG run past its
+    attainable accuracy, profiles/r2a_spread.log).  Now: 20 runs are bit-identical and every one meets smoke()'s bound."""
+    ref = _smoke_ba("cuda")
+    l0, l1 = ref[0][0], ref[0][1]
+    assert l1 < 0.1 * l0 + 1e-8, ref[0]
+    for _ in range(19):
+        got = _smoke_ba("cuda")
+        assert got[0] == ref[0] and torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
 
 
 def test_pgo_weighted_kernels_vs_oracle():
