@@ -98,6 +98,34 @@ class PeerComm:
             return None
         return comm
 
+    @classmethod
+    def for_allreduce(cls, group, device, max_elems, itemsize):
+        """Communicator whose payload holds the staging + result areas of sum all-reduces of up to `max_elems` elements."""
+        import torch.distributed as dist
+        if group is None or not (dist.is_available() and dist.is_initialized()):
+            return None
+        world = dist.get_world_size(None if group is True else group)
+        q = ((max_elems + 3) // 4 + world - 1) // world * 4
+        stage = (world * q * itemsize + 255) // 256 * 256
+        result = (max_elems * itemsize + 255) // 256 * 256
+        comm = cls.create(group, device, stage + result)
+        if comm is not None:
+            comm.stage_off, comm.result_off, comm.max_elems = 0, stage, max_elems
+        return comm
+
+    def pcg_args(self):
+        """(bases, rank, world, stage, result, epoch so far, tickets) for b200_lm_*_pcg."""
+        return [self.bases_ptr, self.rank, self.world, self.stage_off, self.result_off, self.epochs.get(6, 0),
+                self.tickets.data_ptr()]
+
+    def consumed(self, count, channel=6):
+        self.epochs[channel] = self.epochs.get(channel, 0) + int(count)
+
+    def sum_(self, t):
+        """In-place sum over ranks through the areas reserved by for_allreduce."""
+        assert t.is_contiguous() and t.numel() <= self.max_elems
+        return self.allreduce_(t, self.stage_off, self.result_off)
+
     def next_epoch(self, channel):
         e = self.epochs.get(channel, 0) + 1
         self.epochs[channel] = e

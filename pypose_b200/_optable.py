@@ -203,7 +203,11 @@ LM_OPS = [
                         "iterations, maxiter, best |r|^2, iterations since best, save flag, patience"),
       ("double*", "ws", "reduction workspace"), ("double", "tol", "stop when |r| <= tol |b|"),
       ("long long", "maxiter", ""), ("long long", "first_iter", "0 initialises the state; otherwise continue"),
-      ("long long", "iters", "iterations to enqueue (no-ops once the done flag is set)")],
+      ("long long", "iters", "iterations to enqueue (no-ops once the done flag is set)"),
+      ("const unsigned long long*", "bases", "HOST (world) exchange buffers (b200_comm_open) or NULL: single GPU"),
+      ("int", "rank", ""), ("int", "world", ""), ("long long", "stage", "payload byte offset of the all-reduce staging area"),
+      ("long long", "result", "payload byte offset of the all-reduce result area"),
+      ("long long", "epoch", "all-reduce epochs consumed so far on the PCG channel"), ("unsigned*", "tickets", "(2) zeroed")],
      "PCG.forward loop, optim/solver.py:312-340, with M = block-Jacobi; enqueues `iters` iterations without a host sync"),
     ("b200_lm_pgo_pcg_gather",
      [("const REAL*", "Mn", "(2E,21) node-ordered per-edge blocks"), ("const int*", "nother", "(2E) opposite node of each entry"),
@@ -244,7 +248,11 @@ LM_OPS = [
       ("REAL*", "t", "(P,3) work"), ("REAL*", "part", "(C*split,6) partial sums, unused when split == 1"),
       ("REAL*", "xbest", "(C,6)"), ("double*", "cg", "(16) state, see b200_lm_pgo_pcg"), ("double*", "ws", "reduction workspace"),
       ("double", "tol", ""), ("long long", "maxiter", ""), ("long long", "P", "points"), ("long long", "first_iter", ""),
-      ("long long", "iters", "")],
+      ("long long", "iters", ""),
+      ("const unsigned long long*", "bases", "HOST (world) exchange buffers (b200_comm_open) or NULL: single GPU"),
+      ("int", "rank", ""), ("int", "world", ""), ("long long", "stage", "payload byte offset of the all-reduce staging area"),
+      ("long long", "result", "payload byte offset of the all-reduce result area"),
+      ("long long", "epoch", "all-reduce epochs consumed so far on the PCG channel"), ("unsigned*", "tickets", "(2) zeroed")],
      "PCG on the Schur complement (Hcc - W Hpp^-1 W^T) dc = rhs; optim/solver.py:312-340; no atomics (ba.cu)"),
     ("b200_lm_ba_linearize_seg",
      [("const REAL*", "poses", "(C,7)"), ("const REAL*", "points", "(P,3)"), ("const REAL*", "pix", "(m,2) camera-sorted"),

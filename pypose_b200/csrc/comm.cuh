@@ -64,4 +64,10 @@ __device__ __forceinline__ void comm_wait_all(const Peers& P, int channel, unsig
   }
 }
 
+// comm.cu: out = sum over ranks of in, three kernels on `s` (scatter to slice owners, reduce in rank order, gather);
+// kernels return immediately when cg != NULL and cg[5] != 0 (a finished CG solve)
+template <typename T>
+int comm_allreduce_launch(const T* in, T* out, long long n, const Peers& P, long long stage, long long result, int channel,
+                          unsigned long long epoch, unsigned* tickets, const double* cg, cudaStream_t s);
+
 }  // namespace b200pose

@@ -15,6 +15,7 @@
 #include <string>
 #include <unordered_map>
 #include "lm_common.cuh"
+#include "comm.cuh"
 
 namespace b200pose {
 
@@ -578,11 +579,52 @@ struct PcgKey {                                   // every launch argument of a 
 // (A = per-edge M, ia/ib = ei/ej, E edges) — the faster variant on B200 (20.5 us per product at 3e5 edges, and no
 // node-ordered copy to build: 1.35 vs 1.44 ms per LM step).  GATHER = true: node-ordered blocks (A = Mn, ia = nother,
 // ib = nptr), no atomics, bit-reproducible; selected with B200POSE_DETERMINISTIC=1.
+// Multi-GPU: edges / observations are sharded, the CG vectors are replicated.  Every operator product is a partial sum that
+// is all-reduced ON THE DEVICE (comm.cu: scatter to slice owners, reduce in rank order, broadcast) between the operator
+// and the vector kernels of the iteration — no host in the loop, no collective library call.  The block-diagonal part
+// D p of the operator is added by rank 0 only (dmode 0 elsewhere) so that the reduction counts it once.
+struct PcgComm {
+  bool on;
+  Peers P;
+  long long stage, result;
+  unsigned long long epoch;       // epochs epoch+1, epoch+2, ... are consumed, one per all-reduce, in enqueue order
+  unsigned* tickets;
+};
+static PcgComm make_pcg_comm(const unsigned long long* bases, int rank, int world, long long stage, long long result,
+                             long long epoch, unsigned* tickets) {
+  PcgComm c;
+  c.on = bases != nullptr && world > 1;
+  for (int r = 0; r < kMaxRanks; ++r) c.P.base[r] = (c.on && r < world) ? reinterpret_cast<char*>(bases[r]) : nullptr;
+  c.P.rank = rank; c.P.world = world;
+  c.stage = stage; c.result = result; c.epoch = (unsigned long long)epoch; c.tickets = tickets;
+  return c;
+}
+constexpr int kPcgChannel = 6;
+
 template <typename CT, bool GATHER>
 static int pgo_pcg_run(const CT* A, const int* ia, const int* ib, long long E, const CT* Minv, const CT* extra, const CT* g,
                        CT* x, CT* r, CT* z, CT* p, CT* q, CT* xbest, double* cg, double* ws, double tol, long long maxiter,
-                       long long first_iter, long long iters, long long n, cudaStream_t user) {
+                       long long first_iter, long long iters, long long n, cudaStream_t user, PcgComm cm) {
   if (n <= 0) return 0;
+  if (cm.on) {
+    const int dmode = cm.P.rank == 0 ? 1 : 0;
+    cudaStream_t stream = user;
+    if (first_iter == 0)
+      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, g, (CT)-1, extra, dmode, x, r, p, q, cg, ws, tol, (double)maxiter, n);
+    for (long long it = first_iter; it < first_iter + iters; ++it) {
+      const int par = (int)(it & 1);
+      if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, A, ia, ib, p, q, cg, E);
+      comm_allreduce_launch<CT>(q, q, n * 6, cm.P, cm.stage, cm.result, kPcgChannel, ++cm.epoch, cm.tickets, cg, stream);
+      if (n <= kVecSmallRows) {
+        launch_cg_vec_small<CT>(Minv, extra, dmode, x, r, z, p, q, xbest, cg, par, n, stream);
+        continue;
+      }
+      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, xbest, cg, ws, par, n);
+      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, extra, dmode, p, q, cg, par, n);
+    }
+    return (int)cudaGetLastError();
+  }
   PcgKey key;
   memset(&key, 0, sizeof(key));
   const void* ptrs[] = {A, ia, ib, Minv, extra, g, x, r, z, p, q, cg, ws, xbest};
@@ -612,8 +654,31 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
                       long long m, const CT* Y4p, const int* cidx_p, const int* pptr, const CT* Hc, const CT* Hpinv,
                       const CT* Minv, const CT* bneg, CT* x, CT* r, CT* z, CT* p, CT* q, CT* t, CT* part, CT* xbest,
                       double* cg, double* ws, double tol, long long maxiter,
-                      long long P, long long first_iter, long long iters, long long n, cudaStream_t user) {
+                      long long P, long long first_iter, long long iters, long long n, cudaStream_t user, PcgComm cm) {
   if (n <= 0) return 0;
+  if (cm.on) {
+    const int dmode = cm.P.rank == 0 ? 2 : 0;
+    cudaStream_t stream = user;
+    if (first_iter == 0)
+      LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, bneg, (CT)-1, Hc, dmode, x, r, p, q, cg, ws, tol, (double)maxiter, n);
+    for (long long it = first_iter; it < first_iter + iters; ++it) {
+      const int par = (int)(it & 1);
+      // t = Hpp^-1 W^T p: Hpp^-1 is replicated and linear, so the partial sums over this rank's observations are reduced
+      LM_LAUNCH(pcg_ba_wtx_gather_kernel<CT>, P * kLanesPerPoint, stream, Y4p, poses, cidx_p, pptr, Hpinv, p,
+                (const CT*)nullptr, (CT)1, t, cg, P);
+      comm_allreduce_launch<CT>(t, t, P * 3, cm.P, cm.stage, cm.result, kPcgChannel, ++cm.epoch, cm.tickets, cg, stream);
+      ba_wv_seg_launch<CT>(Y4, poses, pidx, cseg, (int)split, (int)tpi, (const CT*)nullptr, t, q, part, cg, n, stream);
+      comm_allreduce_launch<CT>(q, q, n * 6, cm.P, cm.stage, cm.result, kPcgChannel, ++cm.epoch, cm.tickets, cg, stream);
+      if (n <= kVecSmallRows) {
+        launch_cg_vec_small<CT>(Minv, Hc, dmode, x, r, z, p, q, xbest, cg, par, n, stream);
+        continue;
+      }
+      LM_LAUNCH(cg_dot_kernel<CT>, n, stream, p, q, cg, ws, n);
+      LM_LAUNCH(cg_update_kernel<CT>, n, stream, Minv, p, q, x, r, z, xbest, cg, ws, par, n);
+      LM_LAUNCH(cg_dir_kernel<CT>, n, stream, z, Hc, dmode, p, q, cg, par, n);
+    }
+    return (int)cudaGetLastError();
+  }
   PcgKey key;
   memset(&key, 0, sizeof(key));
   const void* ptrs[] = {Y4, poses, cseg, pidx, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, q, t, cg, ws, part};
@@ -678,9 +743,12 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
   B200_EXPORT int b200_lm_pgo_pcg_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* Minv,       \
                                         const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q, CT* xbest,   \
                                         double* cg, double* ws, double tol, long long maxiter, long long first_iter,  \
-                                        long long iters, long long n, void* stream) {                                 \
+                                        long long iters, const unsigned long long* bases, int rank, int world,        \
+                                        long long stage, long long result, long long epoch, unsigned* tickets,        \
+                                        long long n, void* stream) {                                                  \
     return pgo_pcg_run<CT, false>(M, ei, ej, E, Minv, extra, g, x, r, z, p, q, xbest, cg, ws, tol, maxiter,           \
-                                  first_iter, iters, n, (cudaStream_t)stream);                                        \
+                                  first_iter, iters, n, (cudaStream_t)stream,                                         \
+                                  make_pcg_comm(bases, rank, world, stage, result, epoch, tickets));                  \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_cg_finish_##SFX(CT* x, const CT* xbest, const double* cg, long long n, void* stream) {      \
     if (n <= 0) return 0;                                                                                             \
@@ -692,7 +760,8 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
                                                CT* xbest, double* cg, double* ws, double tol, long long maxiter,      \
                                                long long first_iter, long long iters, long long n, void* stream) {    \
     return pgo_pcg_run<CT, true>(Mn, nother, nptr, 0, Minv, extra, g, x, r, z, p, q, xbest, cg, ws, tol, maxiter,     \
-                                 first_iter, iters, n, (cudaStream_t)stream);                                         \
+                                 first_iter, iters, n, (cudaStream_t)stream,                                          \
+                                 make_pcg_comm(nullptr, 0, 1, 0, 0, 0, nullptr));                                     \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_predicted_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* D,    \
                                               const CT* g, double* ws, long long n, void* stream) {                   \
@@ -720,9 +789,12 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
                                        const CT* Hpinv, const CT* Minv, const CT* bneg, CT* x, CT* r, CT* z, CT* p,   \
                                        CT* q, CT* t, CT* part, CT* xbest, double* cg, double* ws, double tol,         \
                                        long long maxiter, long long P, long long first_iter, long long iters,         \
-                                       long long n, void* stream) {                                                   \
+                                       const unsigned long long* bases, int rank, int world, long long stage,         \
+                                       long long result, long long epoch, unsigned* tickets, long long n,             \
+                                       void* stream) {                                                                \
     return ba_pcg_run<CT>(Y4, poses, pidx, cseg, split, tpi, m, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, \
-                          q, t, part, xbest, cg, ws, tol, maxiter, P, first_iter, iters, n, (cudaStream_t)stream);    \
+                          q, t, part, xbest, cg, ws, tol, maxiter, P, first_iter, iters, n, (cudaStream_t)stream,     \
+                          make_pcg_comm(bases, rank, world, stage, result, epoch, tickets));                          \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_ba_predicted_##SFX(const CT* Y4, const CT* poses, const CT* rs, const int* cidx,            \
                                              const int* pidx, const CT* xc, const CT* xp, double* ws, long long m,    \

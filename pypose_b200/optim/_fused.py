@@ -298,7 +298,10 @@ def pgo_node_order(M, u, epos_i, epos_j, nptr):
     return Mn, Hd, g
 
 
-def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None, node=None):
+_NOCOMM = [None, 0, 1, 0, 0, 0, None]
+
+
+def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None, node=None, comm=None):
     """(H + clamp/damping) x = -g by device PCG.  Returns x (n,6), iterations, predicted (1,) fp64 on device.
     `unweighted` = (M0, u0): per-edge blocks without the information matrices, for the predicted reduction.
     `node` = (Mn, nother, nptr): node-ordered blocks -> the H product is a gather (deterministic) instead of a scatter."""
@@ -310,9 +313,13 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     x, r, z, p, q, xbest = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(6))
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
     if node is None:
-        iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg", M, [
-            _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest), _p(cg),
-            _p(ws), float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+        def chunk(it0, k):
+            _launch("b200_lm_pgo_pcg", M, [
+                _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest), _p(cg),
+                _p(ws), float(tol), maxiter, it0, k, *(comm.pcg_args() if comm is not None else _NOCOMM)], n)
+            if comm is not None:
+                comm.consumed(k)           # one device all-reduce of q per iteration
+        iters = _run_chunks(chunk, cg, maxiter, hint)
     else:
         iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg_gather", M, [
             _p(node[0]), _p(node[1]), _p(node[2]), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest),
@@ -344,7 +351,7 @@ def ba_linearize_det(poses, points, pix, pidx, geom, robust=0, delta=1.0):
     return (Y4, Y4p), rs, Hcc, Hpp, gc, gp, cur
 
 
-def ba_solve(Y4s, poses, rs, cidx, pidx, geom, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0):
+def ba_solve(Y4s, poses, rs, cidx, pidx, geom, Hcc, Hpp, gc, gp, scale, dmin, dmax, tol, maxiter, hint=0, comm=None):
     """Schur-complement solve of the damped BA normal equations by device PCG; the Jacobian rows are rebuilt from
     Y4 (ba_linearize_det) and the poses it was linearised at.  No atomics: every camera / point sum has one writer.
     Returns xc (C,6), xp (P,3), iterations, predicted (1,) fp64 on device."""
@@ -360,20 +367,34 @@ def ba_solve(Y4s, poses, rs, cidx, pidx, geom, Hcc, Hpp, gc, gp, scale, dmin, dm
     seg = [_p(Y4), _p(poses), _p(pidx), _p(cseg), split, tpi]
     _launch("b200_lm_blk6_damp_inv", Y4, [_p(Hcc), float(scale), float(dmin), float(dmax), _p(Hc), _p(None), _p(None)], C)
     _launch("b200_lm_pt3_damp_inv", Y4, [_p(Hpp), float(scale), float(dmin), float(dmax), _p(Hpinv)], P)
-    Sd = Hc.clone()
+    # multi-GPU: Hcc / Hpp / gc / gp are already reduced (replicated); every sum over observations below is a partial sum
+    # of this rank's shard, the replicated term is contributed by rank 0 only, then one device all-reduce
+    first = comm is None or comm.rank == 0
+    Sd = Hc.clone() if first else torch.zeros_like(Hc)
     _launch("b200_lm_ba_schur_diag_seg", Y4, [*seg, _p(Hpinv), _p(Sd), _p(part)], C)
-    _launch("b200_lm_blk6_damp_inv", Y4, [_p(Sd), 1.0, -3.0e38, 3.0e38, _p(None), _p(None), _p(Minv)], C)
-    bneg = gc.clone()                                     # -(rhs) = gc - W Hpp^-1 gp
+    bneg = gc.clone() if first else torch.zeros_like(gc)  # -(rhs) = gc - W Hpp^-1 gp
     _launch("b200_lm_ba_wv_seg", Y4, [*seg, _p(Hpinv), _p(gp), _p(bneg), _p(part)], C)
+    if comm is not None:
+        comm.sum_(Sd)
+        comm.sum_(bneg)
+    _launch("b200_lm_blk6_damp_inv", Y4, [_p(Sd), 1.0, -3.0e38, 3.0e38, _p(None), _p(None), _p(Minv)], C)
     x, r, z, p, q, xbest = (torch.empty(C, 6, dtype=dt, device=dev) for _ in range(6))
     t = torch.empty(P, 3, dtype=dt, device=dev)
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * C
-    iters = _run_chunks(lambda it0, k: _launch("b200_lm_ba_pcg", Y4, [
-        *seg, m, _p(Y4p), _p(cidx_p), _p(pptr), _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
-        _p(t), _p(part), _p(xbest), _p(cg), _p(ws), float(tol), maxiter, P, it0, k], C), cg, maxiter, hint)
+    def chunk(it0, k):
+        _launch("b200_lm_ba_pcg", Y4, [
+            *seg, m, _p(Y4p), _p(cidx_p), _p(pptr), _p(Hc), _p(Hpinv), _p(Minv), _p(bneg), _p(x), _p(r), _p(z), _p(p), _p(q),
+            _p(t), _p(part), _p(xbest), _p(cg), _p(ws), float(tol), maxiter, P, it0, k,
+            *(comm.pcg_args() if comm is not None else _NOCOMM)], C)
+        if comm is not None:
+            comm.consumed(2 * k)           # W^T p and W t are reduced in every iteration
+    iters = _run_chunks(chunk, cg, maxiter, hint)
     _launch("b200_lm_cg_finish", Y4, [_p(x), _p(xbest), _p(cg)], C)
     xp = torch.empty(P, 3, dtype=dt, device=dev)          # dp = -Hpp^-1 (gp + W^T dc)
-    _launch("b200_lm_ba_wtx_gather", Y4, [_p(Y4p), _p(poses), _p(cidx_p), _p(pptr), _p(Hpinv), _p(x), _p(gp), -1.0, _p(xp)], P)
+    _launch("b200_lm_ba_wtx_gather", Y4, [_p(Y4p), _p(poses), _p(cidx_p), _p(pptr), _p(Hpinv), _p(x), _p(gp if first else None),
+                                          -1.0, _p(xp)], P)
+    if comm is not None:
+        comm.sum_(xp)
     _launch("b200_lm_ba_predicted", Y4, [_p(Y4), _p(poses), _p(rs), _p(cidx), _p(pidx), _p(x), _p(xp), _p(ws)], m)
     return x, xp, iters, ws[:1].clone()
 

@@ -310,6 +310,15 @@ class PGOProblem(_Problem):
         if M.is_cuda and self.group is None and self.deterministic:      # gathers over node-ordered copies, no atomics
             Mn, Hd, g = _fused.pgo_node_order(M, u, self.epos_i, self.epos_j, self.nptr)
             return (M, Mn), Hd, g, cur, unw
+        comm = self._peer(27 * nodes.shape[0]) if (M.is_cuda and self.group is not None) else None
+        if comm is not None:      # multi-GPU device route: [Hd | g] of this rank's edges, one device all-reduce
+            n = nodes.shape[0]
+            packed = torch.zeros(n * 27, dtype=M.dtype, device=M.device)
+            Hd, g = packed[:n * 21].view(n, 21), packed[n * 21:].view(n, 6)
+            _fused._launch("b200_lm_pgo_scatter", M, [M.data_ptr(), u.data_ptr(), self.ei.data_ptr(), self.ej.data_ptr(),
+                                                      Hd.data_ptr(), g.data_ptr()], M.shape[0])
+            comm.sum_(packed)
+            return M, Hd, g, cur, (unw if unw is not None else (M, u))      # predicted from the per-edge blocks
         Hd, g = _fused.call("lm_pgo_scatter", M, u, self.ei, self.ej, nodes.shape[0])
         if self.group is not None:
             packed = torch.cat([Hd.reshape(-1), g.reshape(-1)])
@@ -324,12 +333,15 @@ class PGOProblem(_Problem):
 
     def trial(self, lin, scale, dmin, dmax):
         M, Hd, g, cur, unw = lin
-        if isinstance(M, tuple) or (M.is_cuda and self.group is None):   # device-resident PCG
+        comm = getattr(self, '_comm', None)
+        if isinstance(M, tuple) or (M.is_cuda and (self.group is None or comm is not None)):   # device-resident PCG
             node = (M[1], self.nother, self.nptr) if isinstance(M, tuple) else None
             M = M[0] if isinstance(M, tuple) else M
             D, self.cg_iters, predicted = _fused.pgo_solve(M, self.ei, self.ej, Hd, g, scale, dmin, dmax, self.tol,
                                                            self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0,
-                                                           unweighted=unw, node=node)
+                                                           unweighted=unw, node=node, comm=comm)
+            if comm is not None:
+                predicted = _allreduce(predicted, self.group)
             return self._finish_trial(D, predicted, cur)
         d = Hd[:, _DIAG21]
         extra = d.clamp(dmin, dmax) * scale - d                       # added to the diagonal of H
@@ -357,6 +369,19 @@ class PGOProblem(_Problem):
 
     def accept(self):
         _copy_param(self.param, self._trial)
+
+    def _peer(self, max_elems):
+        return _peer_allreduce(self, self.param, max_elems)
+
+
+def _peer_allreduce(prob, param, max_elems):
+    """NVLink exchange for the device all-reduces of a sharded block-sparse problem (collective set-up on first use; None
+    keeps the torch.distributed route)."""
+    if not getattr(prob, '_comm_tried', False):
+        prob._comm_tried = True
+        from .._comm import PeerComm
+        prob._comm = PeerComm.for_allreduce(prob.group, param.device, int(max_elems), param.element_size())
+    return prob._comm
 
 
 def _unpack6(Hp):
@@ -422,8 +447,18 @@ class BAProblem(_Problem):
 
     def linearize(self):
         T, p = self._params()
-        if T.is_cuda and self.group is None:          # device PCG route: 16 B per observation instead of the rows
+        comm = None
+        if T.is_cuda and self.group is not None:
+            comm = _peer_allreduce(self, self.poses, max(27 * T.shape[0] + 9 * p.shape[0], 3 * p.shape[0]))
+        if T.is_cuda and (self.group is None or comm is not None):   # device PCG route: 16 B per observation, no atomics
             Y4s, rs, Hcc, Hpp, gc, gp, cur = _fused.ba_linearize_det(T, p, self.pix, self.pidx, self.geom, *self.robust)
+            if comm is not None:          # block sums of this rank's observations -> one device all-reduce
+                packed = torch.cat([t.reshape(-1) for t in (Hcc, Hpp, gc, gp)])
+                comm.sum_(packed)
+                outs, o = [], 0
+                for t in (Hcc, Hpp, gc, gp):
+                    outs.append(packed[o:o + t.numel()].view_as(t)); o += t.numel()
+                Hcc, Hpp, gc, gp = outs
             return Y4s, T, rs, Hcc, Hpp, gc, gp, cur
         Jc, Jp, rs, Hcc, Hpp, gc, gp, cur = _fused.call("lm_ba_linearize", T, p, self.pix, self.cidx, self.pidx, *self.robust)
         if self.group is not None:
@@ -441,7 +476,8 @@ class BAProblem(_Problem):
         if isinstance(Jc, tuple):                     # device-resident Schur PCG; (Jc, Jp) are ((Y4, Y4p), poses) here
             xc, xp, self.cg_iters, pred = _fused.ba_solve(Jc, Jp, rs, self.cidx, self.pidx, self.geom, Hcc, Hpp,
                                                           gc, gp, scale, dmin,
-                                                          dmax, self.tol, self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0)
+                                                          dmax, self.tol, self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0,
+                                                          comm=getattr(self, '_comm', None))
             return self._finish_trial(xc, xp, pred, cur)
         dc, dp = Hcc[:, _DIAG21], Hpp[:, [0, 3, 5]]
         Hc = _unpack21(Hcc) + torch.diag_embed(dc.clamp(dmin, dmax) * scale - dc)

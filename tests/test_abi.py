@@ -31,6 +31,13 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_library_has_no_unresolved_symbols():
+    """dlopen with RTLD_NOW: a template declared in one translation unit and defined in another namespace would only fail
+    at its first call on a GPU box."""
+    from pypose_b200 import _C
+    ctypes.CDLL(_C.LIB_PATH, mode=os.RTLD_NOW)
+
+
 def test_library_exports_nothing_undeclared():
     from pypose_b200 import _C
     out = subprocess.run(["nm", "-D", "--defined-only", _C.LIB_PATH], capture_output=True, text=True).stdout
@@ -76,6 +83,7 @@ def test_fused_launch_sites_pass_as_many_arguments_as_the_abi_declares():
             depth -= ch in ")]}"
             n += ch == "," and depth == 0
         n += 5 * args.count("*seg")        # seg = [Y4, poses, pidx, cseg, split, tpi]
+        n += 6 * args.count("_NOCOMM")     # *(comm.pcg_args() if comm is not None else _NOCOMM): 7 arguments
         assert n == arity[name], (name, n, arity[name])
         seen += 1
     assert seen >= 30
