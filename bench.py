@@ -6,8 +6,11 @@
 metric  : SE3 Exp+Log Mops/s (1 op = one se3->SE3 Exp plus one SE3->se3 Log on one element)
 workload: BASELINE.json configs[1] — batch 10^6, fp32, per GPU (weak scaling, no data-path collective)
 step    : one Exp launch + one Log launch over one resident batch; batches rotate through a ring whose
-          footprint exceeds the 126 MB L2, so every step streams from / to HBM.
-value   : device-timed (CUDA events, max over ranks), inputs resident in HBM.
+          footprint exceeds the 126 MB L2 (Log reads the SE3 batch Exp just wrote, possibly still in L2; nothing else is).
+value   : device-timed (CUDA events, max over ranks), inputs resident in HBM; W warm-up steps, then exactly K steps between
+          barrier + synchronize pairs, repeated REGIONS times, median region reported.
+legs    : LM step/s (PoseInv, reprojection at 1e6 / 1e7 / 2e8 residual rows, pose graph, bundle adjustment) and IMU
+          Msamples/s through the public API, each with its own roofline object (bench_legs.py).
 e2e     : same metric through the public API (pp.se3(...).Exp().Log()) with pinned HOST buffers,
           H2D and D2H copies inside the timed region.
 The reference arm (--impl reference) times the torch-CPU port of the reference's Exp/Log op
@@ -117,98 +120,116 @@ def max_over_ranks(ms, world, dev):
     return ms
 
 
+def se3_batch(n, seed, device):
+    """One workload batch, the same code for both arms: tau ~ N(0,1)^3, phi = theta * axis, theta ~ U(0, pi - 0.01), axis
+    uniform on the sphere (SURVEY.md §8d cfg 2)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn(n, 6, generator=g, device=device, dtype=torch.float32)
+    axis = torch.randn(n, 3, generator=g, device=device, dtype=torch.float32)
+    axis = axis / axis.norm(dim=-1, keepdim=True)
+    theta = torch.rand(n, 1, generator=g, device=device, dtype=torch.float32) * (3.14159265 - 0.01)
+    x[:, 3:] = axis * theta
+    return x.contiguous()
+
+
+WORKLOAD = "SE3 Exp+Log, batch 1e6 per GPU, fp32, theta ~ U(0, pi-0.01) (BASELINE.json configs[1])"
+
+
+def base_config(world):
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "angles": "U(0, pi-0.01)",
+            "parallelism": f"dp{world} (independent batches, no collective)"}
+
+
 def run_ours(args):
     import pypose_b200 as pp
     from pypose_b200 import _C
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    torch.manual_seed(1234 + rank)
     n = BATCH
     ring = 8                                  # 8 x 76 MB = 608 MB of distinct buffers, > 4 x L2
-    xs = [pp.randn_se3(n, sigma=1.0, device=dev, dtype=torch.float32).tensor().contiguous() for _ in range(ring)]
-    for x in xs:   # rotation angle ~ U(0, pi - 0.01) (SURVEY.md §8d cfg 2)
-        phi = x[:, 3:]
-        ang = torch.rand(n, 1, device=dev) * (3.14159265 - 0.01)
-        phi.copy_(phi / phi.norm(dim=-1, keepdim=True) * ang)
+    xs = [se3_batch(n, 1234 + 100 * rank + j, dev) for j in range(ring)]
     Xs = [torch.empty(n, 7, device=dev) for _ in range(ring)]
     ys = [torch.empty(n, 6, device=dev) for _ in range(ring)]
     footprint = ring * n * (24 + 28 + 24)
     f_exp, f_log = _C.fn("b200_se3_exp_fwd_f32"), _C.fn("b200_SE3_log_fwd_f32")
-    stream = torch.cuda.current_stream(dev)
+    K, W = max(1, args.steps), max(3, args.warmup)
 
-    def step(i, sp):
-        j = i % ring
-        _C.check(f_exp(ctypes.c_void_p(xs[j].data_ptr()), ctypes.c_void_p(Xs[j].data_ptr()), n, sp), "exp")
-        _C.check(f_log(ctypes.c_void_p(Xs[j].data_ptr()), ctypes.c_void_p(ys[j].data_ptr()), n, sp), "log")
+    def step(j, sp, which=3):
+        if which & 1:
+            _C.check(f_exp(ctypes.c_void_p(xs[j].data_ptr()), ctypes.c_void_p(Xs[j].data_ptr()), n, sp), "exp")
+        if which & 2:
+            _C.check(f_log(ctypes.c_void_p(Xs[j].data_ptr()), ctypes.c_void_p(ys[j].data_ptr()), n, sp), "log")
 
     side = torch.cuda.Stream(dev)
+
+    def capture(which):
+        """one CUDA graph per ring slot = ONE step (Exp launch + Log launch), so that exactly K steps can be replayed"""
+        graphs = []
+        with torch.cuda.stream(side):
+            for j in range(ring):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    step(j, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream), which)
+                graphs.append(g)
+        torch.cuda.synchronize()
+        return graphs
+
     with torch.cuda.stream(side):
         sp = ctypes.c_void_p(side.cuda_stream)
-        for i in range(max(args.warmup, ring)):
+        for i in range(ring):
             step(i, sp)
         side.synchronize()
-        # one CUDA graph = one trip round the ring (ring steps, 2*ring kernel launches)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            spc = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            for i in range(ring):
-                step(i, spc)
+    graphs = capture(3)
+    for i in range(W):
+        graphs[i % ring].replay()
     torch.cuda.synchronize()
-    trips = max(1, args.steps // ring)
-    steps = trips * ring
-    for _ in range(3):
-        graph.replay()
+
+    def timed_region(gs, k):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(k):
+            gs[i % ring].replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(trips):
-        graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    barrier(world)
+    regions = []
+    for _ in range(REGIONS):               # each region: barrier + sync, EXACTLY K steps, sync; the median region is reported
+        barrier(world)
+        ms = timed_region(graphs, K)
+        barrier(world)
+        regions.append(max_over_ranks(ms, world, dev))
+    # keep the GPU busy long enough for nvidia-smi to see clocks under load (a 0.4 ms region is shorter than one sample)
+    t_end = time.perf_counter() + 0.35
+    while time.perf_counter() < t_end:
+        timed_region(graphs, ring * 8)
     clocks = sampler.stop() if rank == 0 else None
-    ms = max_over_ranks(ms, world, dev)
-    ms_per_step = ms / steps
+    regions.sort()
+    ms_per_step = regions[len(regions) // 2] / K
     value = world * n / (ms_per_step * 1e-3) / 1e6
 
-    # per-kernel durations (each kernel alone, same ring, same graph technique) for the roofline
-    def time_kernel(which):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(g, stream=side):
-                spc = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-                for j in range(ring):
-                    if which == "exp":
-                        f_exp(ctypes.c_void_p(xs[j].data_ptr()), ctypes.c_void_p(Xs[j].data_ptr()), n, spc)
-                    else:
-                        f_log(ctypes.c_void_p(Xs[j].data_ptr()), ctypes.c_void_p(ys[j].data_ptr()), n, spc)
-        torch.cuda.synchronize()
-        g.replay()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(trips):
-            g.replay()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / (trips * ring)
-
-    t_exp, t_log = time_kernel("exp"), time_kernel("log")
+    # per-kernel durations (each kernel alone, same ring, CUDA events on the launching stream) for the roofline
+    kk = max(K, 64)
+    g_exp, g_log = capture(1), capture(2)
+    for gs in (g_exp, g_log):
+        timed_region(gs, ring)
+    t_exp = sorted(timed_region(g_exp, kk) for _ in range(3))[1] / kk
+    t_log = sorted(timed_region(g_log, kk) for _ in range(3))[1] / kk
     peak, peak_src = peaks()
     dom, t_dom, b_dom = ("se3_exp_fwd_f32", t_exp, BYTES_EXP) if t_exp >= t_log else ("SE3_log_fwd_f32", t_log, BYTES_LOG)
     ach = n * b_dom / (t_dom * 1e-3) / 1e9
     step_gbs = n * (BYTES_EXP + BYTES_LOG) / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": f"stream_kernel<{dom}>", "achieved": round(ach, 1), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": f"stream_kernel_tma<{dom}>", "achieved": round(ach, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
-                "us_per_launch": round(t_dom * 1e3, 2), "exp_us": round(t_exp * 1e3, 2), "log_us": round(t_log * 1e3, 2),
-                "step_gbs": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4)}
+                "bytes_per_launch": n * b_dom, "us_per_launch": round(t_dom * 1e3, 2), "exp_us": round(t_exp * 1e3, 2),
+                "log_us": round(t_log * 1e3, 2), "step_gbs": round(step_gbs, 1), "step_frac": round(step_gbs / peak, 4)}
 
     # ---- e2e through the public API with pinned host buffers
-    e2e_steps = max(8, min(64, steps // 50))
+    e2e_steps = max(32, min(256, K))
     hx = [xs[j % ring].cpu().pin_memory() for j in range(2)]
     hy = [torch.empty(n, 6).pin_memory() for _ in range(2)]
     dx = [torch.empty(n, 6, device=dev) for _ in range(2)]
@@ -236,44 +257,44 @@ def run_ours(args):
             hy[k].copy_(dy[k], non_blocking=True)
             ev_out[k].record(s_out)
 
-    for i in range(3):
+    for i in range(4):
         e2e_step(i)
-    barrier(world)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    for ev in ev_out:                      # the timed region ends when the last results have reached the host
-        s_c.wait_event(ev)
-    b.record()
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks(a.elapsed_time(b), world, dev) / e2e_steps
+    e2e_regions = []
+    for _ in range(3):
+        barrier(world)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        for ev in ev_out:                      # the timed region ends when the last results have reached the host
+            s_c.wait_event(ev)
+        b.record()
+        torch.cuda.synchronize()
+        e2e_regions.append(max_over_ranks(a.elapsed_time(b), world, dev) / e2e_steps)
+    e2e_ms = sorted(e2e_regions)[1]
     e2e = {"value": round(world * n / (e2e_ms * 1e-3) / 1e6, 1), "unit": UNIT, "h2d_bytes_per_step": n * 24,
-           "d2h_bytes_per_step": n * 24, "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps,
+           "d2h_bytes_per_step": n * 24, "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps, "regions": 3,
            "api": "pp.se3(x).Exp().Log() with pinned host in/out"}
 
     cpu = cpu_baseline(sample_batches=10) if (rank == 0 and world == 1 and not args.no_cpu) else None
-    extra = {}
-    try:
-        from pypose_b200 import _bench_extra
-        extra = _bench_extra.run(args, rank, world, dev)
-    except ImportError:
-        pass
+    import bench_legs
+    legs = bench_legs.run(args, rank, world, dev, peak)
     if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": steps,
-                "warmup": max(args.warmup, ring), "ms_per_step": round(ms_per_step, 6), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "SE3 Exp+Log, batch 1e6 per GPU, fp32 (BASELINE.json configs[1])",
-                           "batch_per_gpu": n, "angles": "U(0, pi-0.01)", "launch": "CUDA graph of one ring trip",
-                           "l2": f"inputs larger than L2: ring of {ring} batches, footprint {footprint >> 20} MiB > 126 MiB L2",
-                           "parallelism": f"dp{world} (independent batches, no collective)"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * steps, "clocks": clocks}
-        line.update(extra)
+        cfg = base_config(world)
+        cfg.update({"launch": "one CUDA graph per step (Exp launch + Log launch)", "timed_regions": REGIONS,
+                    "l2": f"inputs larger than L2: ring of {ring} batches, footprint {footprint >> 20} MiB > 126 MiB L2"})
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": round(ms_per_step, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "gpu_launches": 2 * K}
+        line.update(legs)                      # LM step/s and IMU legs, each with its own roofline (before the long keys)
+        line.update({"roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks, "config": cfg})
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
+
+REGIONS = 5
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
 # (profiles/); None until measured.
@@ -313,56 +334,61 @@ def best_threads(fn, cores):
     return best
 
 
-def cpu_baseline(sample_batches):
-    """Reference's torch-CPU op sequence (oracle/torch_port.py) on the host cores (best thread count)."""
+def _cpu_explog(sample_batches, warmup):
     from oracle import torch_port
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(BATCH, 6, generator=g)
+    x = se3_batch(BATCH, 1234, torch.device("cpu"))
     cores = best_threads(lambda: torch_port.SE3_log(torch_port.se3_exp(x)), usable_cores())
-    best = float("inf")
+    for _ in range(warmup):
+        torch_port.SE3_log(torch_port.se3_exp(x))
     t_all = time.perf_counter()
+    best = float("inf")
     for _ in range(sample_batches):
         t = time.perf_counter()
         torch_port.SE3_log(torch_port.se3_exp(x))
         best = min(best, time.perf_counter() - t)
-    total = time.perf_counter() - t_all
-    return {"value": round(BATCH / (total / sample_batches) / 1e6, 3), "unit": UNIT, "cores": cores, "kind": "port",
-            "best_value": round(BATCH / best / 1e6, 3),
-            "sample": f"{sample_batches} x (Exp+Log over one 1e6-element fp32 batch), torch {torch.__version__} CPU, "
-                      f"{cores} threads (fastest of 4..{usable_cores()}); mean over the sample"}
+    mean = (time.perf_counter() - t_all) / sample_batches
+    return mean, best, cores
+
+
+def cpu_baseline(sample_batches):
+    """Reference's torch-CPU op sequence (oracle/torch_port.py) on the host cores (best thread count), plus the
+    reference-side LM step and IMU integrate at the sizes the host can run (bench_legs.run_reference)."""
+    import bench_legs
+    mean, best, cores = _cpu_explog(sample_batches, 1)
+    out = {"value": round(BATCH / mean / 1e6, 3), "unit": UNIT, "cores": cores, "kind": "port",
+           "best_value": round(BATCH / best / 1e6, 3),
+           "sample": f"{sample_batches} x (Exp+Log over one 1e6-element fp32 batch), torch {torch.__version__} CPU, "
+                     f"{cores} threads (fastest of 4..{usable_cores()}); mean over the sample"}
+    out.update(bench_legs.run_reference())
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import torch_port
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(BATCH, 6, generator=g)
-    cores = best_threads(lambda: torch_port.SE3_log(torch_port.se3_exp(x)), usable_cores())
-    steps = min(args.steps, 60)
-    for _ in range(min(args.warmup, 3)):
-        torch_port.SE3_log(torch_port.se3_exp(x))
-    t = time.perf_counter()
-    for _ in range(steps):
-        torch_port.SE3_log(torch_port.se3_exp(x))
-    ms = (time.perf_counter() - t) * 1e3 / steps
-    v = round(BATCH / (ms * 1e-3) / 1e6, 3)
+    import bench_legs
+    steps = max(1, min(args.steps, 60))
+    warm = max(1, min(args.warmup, 3))
+    mean, best, cores = _cpu_explog(steps, warm)
+    ms = mean * 1e3
+    v = round(BATCH / mean / 1e6, 3)
+    cfg = base_config(args.gpus)
+    cfg["note"] = "each step = one full 1e6-element batch on the host; step count bounded to 60"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SE3 Exp+Log, batch 1e6, fp32 (BASELINE.json configs[1])", "batch_per_gpu": BATCH,
-                       "note": "each step = one full 1e6-element batch on the host; step count bounded to 60"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{steps} x Exp+Log over a 1e6 fp32 batch (oracle/torch_port.py, torch CPU)"},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "warmup": warm, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    line.update(bench_legs.run_reference())
+    line.update({"cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                  "sample": f"{steps} x Exp+Log over a 1e6 fp32 batch (oracle/torch_port.py, torch CPU)"},
+                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "config": cfg})
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -1,0 +1,250 @@
+"""Extra legs of bench.py — the second half of BASELINE.json's metric (LM step/s) and the IMU scan, for both arms.
+
+ours      : `run(args, rank, world, dev)` times the public API (`optimizer.step`, `IMUPreintegrator.__call__`) on the GPU.
+reference : `run_reference(sample_s)` times the reference's algorithm on the host cores at the largest size that finishes in
+            a bounded time (the reference cannot run the named sizes: dense Jacobian of 1.7 TB):
+            dense LM step (oracle/lm_oracle.py dense_lm_step = optimizer.py:645-680 on a dense J), IMU integrate
+            (oracle/scan_oracle.py = imu_preintegrator.py:314-384).  Sizes are printed with the numbers.
+
+Every leg carries its own roofline object: algorithmic bytes per step (84 B/pose/trial for PoseInv,
+36 B/residual/pass for reprojection, 136 B/sample for IMU) / measured time / measured HBM peak.
+A timed LM step is one `optimizer.step()` (host control flow and its single host read included) from a freshly
+perturbed state, so every timed step linearises, solves, retracts and evaluates the trial loss; the reset is not timed.
+Each leg is timed for >= 50 ms in total and reports the median over its steps.
+"""
+import time
+
+import numpy as np
+import torch
+from torch import nn
+
+MIN_LEG_MS = 50.0
+
+
+def _time_steps(step_fn, reset_fn, warmup=3, min_ms=MIN_LEG_MS, min_steps=7, max_steps=400):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        reset_fn(); step_fn()
+    ts, tot = [], 0.0
+    while len(ts) < min_steps or (tot < min_ms and len(ts) < max_steps):
+        reset_fn()
+        e0.record()
+        step_fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+        tot += ts[-1]
+    ts.sort()
+    return ts[len(ts) // 2], len(ts)
+
+
+def _max(ms, world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def _roof(bytes_per_step, ms, peak):
+    gbs = bytes_per_step / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "bytes_per_step": int(bytes_per_step), "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(gbs / peak, 4)}
+
+
+class InvNet(nn.Module):           # README.md:120-129
+    def __init__(self, pp, pose):
+        super().__init__()
+        self.pose = pp.Parameter(pose)
+
+    def forward(self, input):
+        return (self.pose @ input).Log().tensor()
+
+
+def _reproj_problem(pp, dev, C, M, rank, world, seed, sorted_split):
+    """C poses, M reprojection residual rows in total; this rank's shard.  `sorted_split`: rows sorted by camera before the
+    split; otherwise every rank draws cameras at random (all ranks touch all cameras)."""
+    gl = torch.Generator(device=dev).manual_seed(seed)
+    gt = pp.se3(0.3 * torch.randn(C, 6, device=dev, generator=gl)).Exp()
+    init = pp.se3(0.05 * torch.randn(C, 6, device=dev, generator=gl)).Exp() * gt
+    mloc = M // world
+    gs = torch.Generator(device=dev).manual_seed(seed + 1000 + rank)
+    if sorted_split:
+        lo = rank * C // world
+        cidx = torch.sort(torch.randint(lo, (rank + 1) * C // world, (mloc,), device=dev, generator=gs))[0]
+    else:
+        cidx = torch.randint(0, C, (mloc,), device=dev, generator=gs)
+    pc = torch.rand(mloc, 3, device=dev, generator=gs) * 4 + torch.tensor([-2.0, -2.0, 2.0], device=dev)
+    pts = gt[cidx].Inv().Act(pc)
+    pix = -pc[:, :2] / pc[:, 2:]
+    return init, (pts, pix, cidx)
+
+
+def run(args, rank, world, dev, peak):
+    import pypose_b200 as pp
+    group = True if world > 1 else None
+    out = {}
+
+    # ---- BASELINE configs[2]: README InvNet, 1e5 SE3 poses per GPU (weak scaling), Constant(1e-4), Cholesky
+    torch.manual_seed(100 + rank)
+    n = 100_000
+    X = pp.randn_SE3(n, sigma=0.9, device=dev)
+    P0 = pp.randn_SE3(n, sigma=0.9, device=dev)
+    net = InvNet(pp, P0.clone())
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.Constant(damping=1e-4), group=group)
+
+    def reset():
+        with torch.no_grad():
+            net.pose.copy_(P0)
+        if hasattr(opt, 'loss'):
+            del opt.loss
+    ms, k = _time_steps(lambda: opt.step(X), reset)
+    ms = _max(ms, world, dev)
+    assert opt._problem is not None
+    out["lm_poseinv"] = {"steps_per_s": round(1e3 / ms, 1), "ms": round(ms, 4), "timed_steps": k, "poses_per_gpu": n,
+                         "scaling": "weak", "roofline": _roof(84 * n, ms, peak)}
+
+    # ---- BASELINE configs[4], single-pose form: reprojection residual rows sharded over the ranks (strong scaling)
+    sizes = [("lm_reproj_1e6", 10_000, 1_000_000), ("lm_reproj_1e7", 100_000, 10_000_000)]
+    if not args.no_large:
+        sizes.append(("lm_reproj_2e8", 100_000, 200_000_000))
+    for name, C, M in sizes:
+        init, inp = _reproj_problem(pp, dev, C, M, rank, world, 77, sorted_split=False)
+        netr = pp.module.PoseReproj(init.clone())
+        optr = pp.optim.LM(netr, strategy=pp.optim.strategy.TrustRegion(), group=group)
+
+        def resetr():
+            with torch.no_grad():
+                netr.poses.copy_(init)
+            if hasattr(optr, 'loss'):
+                del optr.loss
+            optr.param_groups[0]['damping'] = 1e-6
+        ms, k = _time_steps(lambda: optr.step(inp), resetr, min_steps=5)
+        ms = _max(ms, world, dev)
+        out[name] = {"steps_per_s": round(1e3 / ms, 2), "ms": round(ms, 4), "timed_steps": k, "poses": C, "residual_rows": M,
+                     "scaling": "strong", "rejects_last": int(optr.reject_count),
+                     "roofline": _roof(2 * 36 * (M // world), ms, peak)}
+        del netr, optr, inp, init
+        torch.cuda.empty_cache()
+
+    # ---- block-sparse pose graph (two-pose residuals Log(Z^-1 A^-1 B)), edges sharded over the ranks
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for name, N, extra in (("lm_pgo", 100_000, 200_000),) + (() if args.no_large else (("lm_pgo_1e6", 1_000_000, 2_000_000),)):
+        step = pp.se3(torch.tensor([[1.0, 0.1, 0.0, 0.0, 0.0, 0.2]], device=dev).repeat(N, 1)
+                      + 0.05 * torch.randn(N, 6, generator=g).to(dev)).Exp()
+        gtn = step.cumprod(dim=0, left=False)
+        e_i = torch.cat([torch.arange(N - 1), torch.randint(0, N, (extra,), generator=g)]).to(dev)
+        e_j = torch.cat([torch.arange(1, N), torch.randint(0, N, (extra,), generator=g)]).to(dev)
+        keep = e_i != e_j
+        edges_all = torch.stack([e_i[keep], e_j[keep]], 1)
+        Z_all = gtn[edges_all[:, 0]].Inv() @ gtn[edges_all[:, 1]]
+        init3 = pp.se3(0.05 * torch.randn(N, 6, generator=g)).to(dev).Exp() @ gtn
+        E = edges_all.shape[0]
+        sl = slice(rank * E // world, (rank + 1) * E // world)
+        inp3 = (edges_all[sl].contiguous(), pp.SE3(Z_all.tensor()[sl].contiguous()))
+        net3 = pp.module.PoseGraph(init3.clone())
+        opt3 = pp.optim.LM(net3, solver=pp.optim.solver.PCG(tol=1e-3, maxiter=30), sparse=True, group=group)
+
+        def reset3():
+            with torch.no_grad():
+                net3.nodes.copy_(init3)
+            if hasattr(opt3, 'loss'):
+                del opt3.loss
+            opt3.param_groups[0]['damping'] = 1e-6
+        ms, k = _time_steps(lambda: opt3.step(inp3), reset3, warmup=2, min_steps=5)
+        ms = _max(ms, world, dev)
+        it = int(opt3._problem.cg_iters)
+        # per CG iteration: per-edge block 84 B + indices 8 B, and ~9 (n,6) vector passes of 24 B; linearise: 28 B Z + 108 B out
+        bytes_step = (E // world) * (136 + it * 92) + it * N * 9 * 24
+        out[name] = {"steps_per_s": round(1e3 / ms, 1), "ms": round(ms, 3), "timed_steps": k, "nodes": N, "edges": int(E),
+                     "cg_iters": it, "scaling": "strong", "roofline": _roof(bytes_step, ms, peak)}
+        del net3, opt3, inp3, Z_all, edges_all, gtn, step, init3
+        torch.cuda.empty_cache()
+
+    # ---- bundle adjustment (poses + points), observations sharded over the ranks
+    Cb, Pb, per = 1000, 125_000, 8
+    gb = torch.Generator(device=dev).manual_seed(99)
+    gtb = pp.se3(0.2 * torch.randn(Cb, 6, device=dev, generator=gb)).Exp()
+    ptw = torch.rand(Pb, 3, device=dev, generator=gb) * torch.tensor([4.0, 4.0, 3.0], device=dev) + torch.tensor([-2.0, -2.0, 3.0], device=dev)
+    pidx_all = torch.arange(Pb, device=dev).repeat_interleave(per)
+    cidx_all = (pidx_all * 7 + torch.arange(per, device=dev).repeat(Pb) * 3) % Cb
+    yb = gtb[cidx_all].Act(ptw[pidx_all])
+    pixb = -yb[:, :2] / yb[:, 2:]
+    T0 = pp.se3(0.02 * torch.randn(Cb, 6, device=dev, generator=gb)).Exp() * gtb
+    p0 = ptw + 0.05 * torch.randn(Pb, 3, device=dev, generator=gb)
+    Mb = pidx_all.shape[0]
+    slb = slice(rank * Mb // world, (rank + 1) * Mb // world)
+    inp5 = (pixb[slb].contiguous(), cidx_all[slb].contiguous(), pidx_all[slb].contiguous())
+    net5 = pp.module.BundleAdjustment(T0.clone(), p0.clone())
+    opt5 = pp.optim.LM(net5, solver=pp.optim.solver.PCG(tol=1e-3, maxiter=30), sparse=True, group=group)
+
+    def reset5():
+        with torch.no_grad():
+            net5.poses.copy_(T0); net5.points_3d.copy_(p0)
+        if hasattr(opt5, 'loss'):
+            del opt5.loss
+        opt5.param_groups[0]['damping'] = 1e-6
+    ms, k = _time_steps(lambda: opt5.step(inp5), reset5, warmup=2, min_steps=5)
+    ms = _max(ms, world, dev)
+    it = int(opt5._problem.cg_iters)
+    # per observation: linearise 8 B pixel + 8 B indices + 2 x 16 B Y4 out + 8 B residual; per CG iteration two passes of 16 B + 4 B
+    out["lm_ba"] = {"steps_per_s": round(1e3 / ms, 1), "ms": round(ms, 3), "timed_steps": k, "cameras": Cb, "points": Pb,
+                    "observations": int(Mb), "cg_iters": it, "scaling": "strong",
+                    "roofline": _roof((Mb // world) * (56 + it * 40), ms, peak)}
+    del net5, opt5
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[3]: IMU preintegration, 1e3 trajectories x 1e4 samples fp64 per GPU (weak scaling)
+    B, F = 1000, 10_000
+    dt = torch.full((B, F, 1), 0.005, dtype=torch.float64, device=dev)
+    gyro = 0.1 * torch.randn(B, F, 3, dtype=torch.float64, device=dev)
+    acc = torch.randn(B, F, 3, dtype=torch.float64, device=dev) + torch.tensor([0, 0, 9.81], dtype=torch.float64, device=dev)
+    imu = pp.module.IMUPreintegrator(prop_cov=False, reset=True).double().to(dev)
+    ms, k = _time_steps(lambda: imu(dt, gyro, acc), lambda: None, warmup=2, min_steps=5)
+    ms = _max(ms, world, dev)
+    out["imu"] = {"msamples_per_s": round(world * B * F / (ms * 1e-3) / 1e6, 1), "ms": round(ms, 4), "timed_steps": k,
+                  "trajectories_per_gpu": B, "samples": F, "dtype": "f64", "scaling": "weak",
+                  "roofline": _roof(136 * B * F, ms, peak)}
+    imuc = pp.module.IMUPreintegrator(prop_cov=True, reset=True).double().to(dev)
+    ms, k = _time_steps(lambda: imuc(dt, gyro, acc), lambda: None, warmup=2, min_steps=5)
+    ms = _max(ms, world, dev)
+    out["imu_cov"] = {"msamples_per_s": round(world * B * F / (ms * 1e-3) / 1e6, 1), "ms": round(ms, 3), "timed_steps": k,
+                      "dtype": "f64", "scaling": "weak", "roofline": _roof((304 + 2 * 96) * B * F, ms, peak)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithms on the host cores (test infrastructure under oracle/, timed as the baseline)
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(budget_s=20.0):
+    from oracle import lm_oracle as L
+    from oracle import lie_oracle as O
+    from oracle import scan_oracle as S
+    out = {}
+    rng = np.random.default_rng(0)
+    # dense LM step on README InvNet (optimizer.py:645-680): J is (6N, 7N) dense, J^T J is (7N)^2, Cholesky of that
+    for N in (256, 1024):
+        P = O.exp("SE3", 0.5 * rng.standard_normal((N, 6)))
+        X = O.exp("SE3", 0.5 * rng.standard_normal((N, 6)))
+        res = lambda Pm: L.poseinv_residual(Pm, X).reshape(-1)
+        jac = lambda Pm: L.dense_jac_from_blocks(L.poseinv_jac_blocks(Pm, X)[1], np.arange(N), N)
+        t = time.perf_counter()
+        L.dense_lm_step(res, jac, P, 1e-4)
+        dt = time.perf_counter() - t
+        out[f"lm_poseinv_dense_N{N}"] = {"steps_per_s": round(1 / dt, 3), "ms": round(dt * 1e3, 1), "poses": N,
+                                         "poses_per_s": round(N / dt, 1),
+                                         "note": "dense reference algorithm (oracle/lm_oracle.py dense_lm_step); the reference "
+                                                 "cannot run 1e5 poses (dense J of 1.7 TB)"}
+        if dt > budget_s / 4:
+            break
+    # IMU integrate, fp64, F = 1e4 (imu_preintegrator.py:314-384): log-step product scan + cumsums
+    B, F = 16, 10_000
+    dtt = np.full((B, F, 1), 0.005)
+    gyro, acc = 0.1 * rng.standard_normal((B, F, 3)), rng.standard_normal((B, F, 3)) + np.array([0, 0, 9.81])
+    t = time.perf_counter()
+    S.imu_integrate(dtt, gyro, acc)
+    dt = time.perf_counter() - t
+    out["imu_integrate"] = {"msamples_per_s": round(B * F / dt / 1e6, 3), "ms": round(dt * 1e3, 1), "trajectories": B, "samples": F,
+                            "dtype": "f64", "note": "oracle/scan_oracle.py imu_integrate (numpy port of the reference's op sequence)"}
+    return out

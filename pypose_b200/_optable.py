@@ -298,7 +298,9 @@ LM_OPS += [
       ("double*", "ws1", "reduction workspace of the loss kernel"),
       ("double*", "st", "(16) device state: status (0 rejected, 1 accepted, 2 solver failed), loss, last, damping, radius, down, "
                         "reject count, current loss, trial loss, predicted, failed pivots"),
-      ("double*", "host_out", "(16) pinned host copy of st, valid on return; NULL: no copy and no synchronisation"),
+      ("double*", "host_out", "(16) PINNED host memory: the deciding thread stores the state there (zero-copy) and the call "
+                              "returns when it has arrived; NULL: nothing is waited for"),
+      ("long long", "seq", "a number different from the previous call's; appears in host_out[15] when the state is complete"),
       ("const double*", "ctl", "HOST (14): last, cached, damping, pg down, reject count, reject limit, strategy kind "
                                "(0 Constant, 1 Adaptive, 2 TrustRegion), high, low, up, strategy down, factor, min, max"),
       ("int", "robust", "see b200_lm_reproj_accum"), ("double", "delta", ""), ("double", "scale", "prod(1+damping) so far"),
@@ -316,7 +318,7 @@ LM_OPS += [
       ("long long", "epoch0", "count of linearisations so far (incl. this one unless retry)"),
       ("long long", "epoch1", "count of trials so far incl. this one"),
       ("double*", "ws0", "reduction workspace"), ("double*", "ws1", ""), ("double*", "ws2", ""),
-      ("double*", "st", "(16) device state, see b200_lm_reproj_step"), ("double*", "host_out", "(16) pinned host copy or NULL"),
+      ("double*", "st", "(16) device state, see b200_lm_reproj_step"), ("double*", "host_out", "(16) pinned host memory or NULL"), ("long long", "seq", "see b200_lm_reproj_step"),
       ("const double*", "ctl", "HOST (14), see b200_lm_reproj_step"), ("int", "robust", ""), ("double", "delta", ""),
       ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", "")],
      "b200_lm_reproj_step with the observations sharded over `world` GPUs: [H | g] is reduce-scattered to camera owners, "
@@ -326,14 +328,14 @@ LM_OPS += [
      [("REAL*", "P", "(n,7) this rank's poses"), ("const REAL*", "X", "(n,7)"), ("REAL*", "P_trial", "(n,7) work"),
       ("const unsigned long long*", "bases", "HOST (world) exchange buffers"), ("int", "rank", ""), ("int", "world", ""),
       ("long long", "epoch", "count of trials so far incl. this one"), ("double*", "ws", ""), ("double*", "st", "(16)"),
-      ("double*", "host_out", "(16) pinned host copy or NULL"), ("const double*", "ctl", "HOST (14)"), ("int", "robust", ""),
+      ("double*", "host_out", "(16) pinned host memory or NULL"), ("long long", "seq", "see b200_lm_reproj_step"), ("const double*", "ctl", "HOST (14)"), ("int", "robust", ""),
       ("double", "delta", ""), ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", "")],
      "b200_lm_poseinv_step with the poses sharded over `world` GPUs: only the four scalar sums are exchanged "
      "(SURVEY.md §8e row 3); optimizer.py:659-680"),
     ("b200_lm_poseinv_step",
      [("REAL*", "P", "(n,7) parameters; overwritten when the trial is accepted"), ("const REAL*", "X", "(n,7)"),
       ("REAL*", "P_trial", "(n,7) work"), ("double*", "ws", "reduction workspace"), ("double*", "st", "(16) device state"),
-      ("double*", "host_out", "(16) pinned host copy or NULL"), ("const double*", "ctl", "HOST (14), see b200_lm_reproj_step"),
+      ("double*", "host_out", "(16) pinned host memory or NULL"), ("long long", "seq", "see b200_lm_reproj_step"), ("const double*", "ctl", "HOST (14), see b200_lm_reproj_step"),
       ("int", "robust", ""), ("double", "delta", ""), ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", "")],
      "one trial of LevenbergMarquardt.step for README.md:120-129 InvNet, optimizer.py:659-680"),
 ]

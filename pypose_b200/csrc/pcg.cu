@@ -20,7 +20,7 @@
 namespace b200pose {
 
 // state (16 doubles).  DONE: 0 running, 1 converged (|r| <= tol |b|), 2 breakdown (p.Ap <= 0), 3 stagnated (no new minimum of
-// |r| for PATIENCE iterations), 4 maxiter.  BEST / SINCE / SAVE guard the solve against finite-precision CG: when the
+// |r| for PATIENCE = max(100, unknowns) iterations), 4 maxiter.  BEST / SINCE / SAVE guard the solve against finite-precision CG: when the
 // tolerance is below what the arithmetic can reach (fp32, ill-conditioned Schur complements) the iterate degrades after
 // its best point, so the iterate with the smallest recursive residual is kept in xbest and returned unless the solve
 // converged (then the last iterate IS the best one, i.e. attainable tolerances behave exactly like solver.py:312-340).
@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(kLmThreads) cg_init_kernel(const T* __restrict
     const double rz = ws[0], rr = ws[1];
     cg[CG_RZ0] = rz; cg[CG_RZ1] = 0.0; cg[CG_PQ] = 0.0; cg[CG_RR] = rr; cg[CG_STOP2] = tol * tol * rr;
     cg[CG_ITERS] = 0.0; cg[CG_MAXIT] = maxiter;
-    cg[CG_BEST] = rr; cg[CG_SINCE] = 0.0; cg[CG_SAVE] = 1.0; cg[CG_PATIENCE] = kCgPatience;   // x = 0 is the first best
+    cg[CG_BEST] = rr; cg[CG_SINCE] = 0.0; cg[CG_SAVE] = 1.0;       // x = 0 is the first best
+    // exact CG ends within (number of unknowns) iterations: no new minimum of |r| for that long is stagnation, not a plateau
+    cg[CG_PATIENCE] = fmax(kCgPatience, 6.0 * (double)n);
     cg[CG_DONE] = (!(rr > tol * tol * rr) || maxiter <= 0.0) ? 1.0 : 0.0;      // |r| <= tol |b| (also NaN) -> nothing to do
   }
 }

@@ -58,6 +58,11 @@ class DeviceStep:
         self.sfx = _C.suffix(dtype)
         self.state = None
         self.comm = None
+        self.seq = 0
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
 
     def attach_comm(self, comm, part_off=0, pt_off=0):
         self.comm, self.part_off, self.pt_off = comm, part_off, pt_off
@@ -78,7 +83,7 @@ def reproj_trial(ds, prob, scale, dmin, dmax, retry):
     H, g, Pt = prob._buf
     _C.enqueue("b200_lm_reproj_step_" + ds.sfx, poses, poses.data_ptr(), prob.pts.data_ptr(), prob.pix.data_ptr(),
                prob.seg.data_ptr(), H.data_ptr(), g.data_ptr(), Pt.data_ptr(), ds.W[0].data_ptr(), ds.W[1].data_ptr(),
-               ds.state.data_ptr(), ds.host_ptr, ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale),
+               ds.state.data_ptr(), ds.host_ptr, ds.next_seq(), ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale),
                float(dmin), float(dmax), 1 if retry else 0, poses.shape[0])
     return ds.read()
 
@@ -88,7 +93,7 @@ def poseinv_trial(ds, prob, scale, dmin, dmax, retry):
     if prob._trial is None or prob._trial.shape != P.shape:
         prob._trial = torch.empty_like(P)
     _C.enqueue("b200_lm_poseinv_step_" + ds.sfx, P, P.data_ptr(), X.data_ptr(), prob._trial.data_ptr(), ds.W[0].data_ptr(),
-               ds.state.data_ptr(), ds.host_ptr, ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale),
+               ds.state.data_ptr(), ds.host_ptr, ds.next_seq(), ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale),
                float(dmin), float(dmax), P.shape[0])
     return ds.read()
 
@@ -114,7 +119,7 @@ def reproj_trial_peer(ds, prob, scale, dmin, dmax, retry):
     _C.enqueue("b200_lm_reproj_step_peer_" + ds.sfx, poses, poses.data_ptr(), prob.pts.data_ptr(), prob.pix.data_ptr(),
                prob.seg.data_ptr(), H.data_ptr(), g.data_ptr(), c.bases_ptr, c.rank, c.world, ds.part_off, ds.pt_off,
                ds.epoch0, ds.epoch1, ds.W[0].data_ptr(), ds.W[1].data_ptr(), ds.W[2].data_ptr(), ds.state.data_ptr(),
-               ds.host_ptr, ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale), float(dmin), float(dmax),
+               ds.host_ptr, ds.next_seq(), ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale), float(dmin), float(dmax),
                1 if retry else 0, poses.shape[0])
     return ds.read()
 
@@ -126,6 +131,6 @@ def poseinv_trial_peer(ds, prob, scale, dmin, dmax, retry):
     c = ds.comm
     ds.epoch1 += 1
     _C.enqueue("b200_lm_poseinv_step_peer_" + ds.sfx, P, P.data_ptr(), X.data_ptr(), prob._trial.data_ptr(), c.bases_ptr,
-               c.rank, c.world, ds.epoch1, ds.W[0].data_ptr(), ds.state.data_ptr(), ds.host_ptr, ds.ctl_ptr,
+               c.rank, c.world, ds.epoch1, ds.W[0].data_ptr(), ds.state.data_ptr(), ds.host_ptr, ds.next_seq(), ds.ctl_ptr,
                int(prob.robust[0]), float(prob.robust[1]), float(scale), float(dmin), float(dmax), P.shape[0])
     return ds.read()

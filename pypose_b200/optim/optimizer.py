@@ -307,9 +307,23 @@ class LevenbergMarquardt(_SecondOrder):
         self._loss_f, self._loss_t = loss_f, self.loss
         return self.loss
 
-    # -- reference (dense) route -----------------------------------------------------------------------
-    @torch.no_grad()
     def step(self, input, target=None, weight=None):
+        """One LM step.  The structured routes never build an autograd graph (their kernels are called through the C-ABI),
+        so the fast path skips `torch.no_grad()` and torch.optim's profiling wrapper (`step.hooked` below): both together
+        cost ~15 us of Python per step, a third of a 1e6-residual step."""
+        if len(self.param_groups) == 1:
+            prob = self._structured(input, target, weight)
+            if prob is not None:
+                ds = self._device_step(prob)
+                if ds is not None:
+                    return self._step_on_device(prob, self.param_groups[0], ds)
+        with torch.no_grad():
+            return self._step_generic(input, target, weight)
+
+    step.hooked = True      # torch.optim.Optimizer._patch_step_function leaves an already "hooked" step alone
+
+    # -- reference (dense) route -----------------------------------------------------------------------
+    def _step_generic(self, input, target=None, weight=None):
         for pg in self.param_groups:
             prob = self._structured(input, target, weight)
             if prob is not None:
