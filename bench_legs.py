@@ -7,7 +7,7 @@ reference : `run_reference(sample_s)` times the reference's algorithm on the hos
             (oracle/scan_oracle.py = imu_preintegrator.py:314-384).  Sizes are printed with the numbers.
 
 Every leg carries its own roofline object: algorithmic bytes per step (84 B/pose/trial for PoseInv,
-36 B/residual/pass for reprojection, 136 B/sample for IMU) / measured time / measured HBM peak.
+20 B per residual row and pass for reprojection (SURVEY's 36 B minus the 16 B of indices that sorting removes), 136 B/sample for IMU) / measured time / measured HBM peak.
 A timed LM step is one `optimizer.step()` (host control flow and its single host read included) from a freshly
 perturbed state, so every timed step linearises, solves, retracts and evaluates the trial loss; the reset is not timed.
 Each leg is timed for >= 50 ms in total and reports the median over its steps.
@@ -19,6 +19,9 @@ import torch
 from torch import nn
 
 MIN_LEG_MS = 50.0
+# reprojection row as this implementation streams it: point 12 B + pixel 8 B.  SURVEY.md §8d counts 36 B per residual row
+# and pass because it includes 16 B of indices; rows are sorted by camera once, so the kernels read (C+1) offsets instead.
+ROW_BYTES = 20
 
 
 def _time_steps(step_fn, reset_fn, warmup=3, min_ms=MIN_LEG_MS, min_steps=7, max_steps=400):
@@ -124,9 +127,43 @@ def run(args, rank, world, dev, peak):
         ms = _max(ms, world, dev)
         out[name] = {"steps_per_s": round(1e3 / ms, 2), "ms": round(ms, 4), "timed_steps": k, "poses": C, "residual_rows": M,
                      "scaling": "strong", "rejects_last": int(optr.reject_count),
-                     "roofline": _roof(2 * 36 * (M // world), ms, peak)}
+                     "roofline": _roof(2 * ROW_BYTES * (M // world), ms, peak)}
         del netr, optr, inp, init
         torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4] as stated: two-pose reprojection r = proj(T_b^-1 T_a p) - z, 1e4 poses, 1e6 residual rows,
+    # banded covisibility b = a + U{1..5} (~5e4 off-diagonal 6x6 blocks), block-Jacobi PCG; rows sharded over the ranks
+    N2, M2 = 10_000, 1_000_000
+    g2 = torch.Generator(device=dev).manual_seed(321)
+    stp = pp.se3(torch.tensor([[0.3, 0.02, 0.0, 0.0, 0.05, 0.02]], device=dev).repeat(N2, 1)
+                 + 0.02 * torch.randn(N2, 6, device=dev, generator=g2)).Exp()
+    gt2 = stp.cumprod(dim=0, left=False)
+    ia_all = torch.randint(0, N2 - 5, (M2,), device=dev, generator=g2)
+    ib_all = ia_all + torch.randint(1, 6, (M2,), device=dev, generator=g2)
+    yb = torch.rand(M2, 3, device=dev, generator=g2) * 4 + torch.tensor([-2.0, -2.0, 2.0], device=dev)
+    pts2 = (gt2[ia_all].Inv() @ gt2[ib_all]).Act(yb)
+    pix2 = -yb[:, :2] / yb[:, 2:]
+    init2 = pp.se3(0.02 * torch.randn(N2, 6, device=dev, generator=g2)).Exp() * gt2
+    sl2 = slice(rank * M2 // world, (rank + 1) * M2 // world)
+    inp2 = (pts2[sl2].contiguous(), pix2[sl2].contiguous(), ia_all[sl2].contiguous(), ib_all[sl2].contiguous())
+    net2 = pp.module.TwoPoseReproj(init2.clone())
+    opt2 = pp.optim.LM(net2, solver=pp.optim.solver.PCG(tol=1e-3, maxiter=30), sparse=True, group=group)
+
+    def reset2():
+        with torch.no_grad():
+            net2.poses.copy_(init2)
+        if hasattr(opt2, 'loss'):
+            del opt2.loss
+        opt2.param_groups[0]['damping'] = 1e-6
+    ms, k = _time_steps(lambda: opt2.step(inp2), reset2, warmup=2, min_steps=5)
+    ms = _max(ms, world, dev)
+    it = int(opt2._problem.cg_iters)
+    E2 = int(opt2._problem.pa.numel())
+    out["lm_reproj2_1e6"] = {"steps_per_s": round(1e3 / ms, 1), "ms": round(ms, 3), "timed_steps": k, "poses": N2,
+                             "residual_rows": M2, "pose_pairs_local": E2, "cg_iters": it, "scaling": "strong",
+                             "roofline": _roof(2 * ROW_BYTES * (M2 // world) + E2 * (108 + it * 92) + it * N2 * 9 * 24, ms, peak)}
+    del net2, opt2, inp2, pts2, pix2, yb, gt2, stp
+    torch.cuda.empty_cache()
 
     # ---- block-sparse pose graph (two-pose residuals Log(Z^-1 A^-1 B)), edges sharded over the ranks
     g = torch.Generator(device="cpu").manual_seed(5)

@@ -318,3 +318,63 @@ def dense_jac_from_blocks(blocks, row_param, n_params):
     for k in range(m):
         J[k * d:(k + 1) * d, 7 * row_param[k]:7 * row_param[k] + 6] = blocks[k]
     return J
+
+
+# ------------------------------------------------------------------ two-pose reprojection: r = proj(T_b^-1 T_a p) - z
+# (README.md:170-178 project with intr = (-1, 0, 0, -1, 0); function/geometry.py:60-112,171-225 point2pixel / reprojerr
+# with K -> intr = (K00, K01, K02, K11, K12); generalises examples/module/reprojpgo/reprojpgo.py:16-28)
+README_INTR = (-1.0, 0.0, 0.0, -1.0, 0.0)
+
+
+def reproj2_residual(nodes, pts, pix, ia, ib, intr=README_INTR):
+    fx, sk, cx, fy, cy = intr
+    Trel = O.mul("SE3", O.inv("SE3", nodes[ib]), nodes[ia])
+    y = O.act("SE3", Trel, pts)
+    u = (fx * y[:, 0] + sk * y[:, 1]) / y[:, 2] + cx
+    v = fy * y[:, 1] / y[:, 2] + cy
+    return np.stack([u, v], -1) - pix, y
+
+
+def reproj2_jac_rows(nodes, pts, ia, ib, intr=README_INTR):
+    """(m, 2, 6) J = d r / d xi_a = d proj/dy @ [I, -y^] @ Adj(T_b^-1) (SE3_Act_Jacobian op.py:225-227, SE3_Mul.backward
+    wrt Y op.py:870-877); d r / d xi_b = -J (SE3_Inv.backward op.py:968-973)."""
+    fx, sk, cx, fy, cy = intr
+    _, y = reproj2_residual(nodes, pts, np.zeros((len(ia), 2)), ia, ib, intr)
+    m = y.shape[0]
+    dpi = np.zeros((m, 2, 3))
+    dpi[:, 0, 0] = fx / y[:, 2]
+    dpi[:, 0, 1] = sk / y[:, 2]
+    dpi[:, 0, 2] = -(fx * y[:, 0] + sk * y[:, 1]) / y[:, 2] ** 2
+    dpi[:, 1, 1] = fy / y[:, 2]
+    dpi[:, 1, 2] = -fy * y[:, 1] / y[:, 2] ** 2
+    dy = np.concatenate([np.broadcast_to(np.eye(3), (m, 3, 3)), O.vec2skew(-y)], -1)
+    return dpi @ dy @ O.SE3_Adj(O.inv("SE3", nodes[ib]))
+
+
+def reproj2_accum(nodes, pts, pix, pseg, pa, pb, intr=README_INTR, kind=0, delta=1.0):
+    """Per ordered pose pair: M (E,21) = sum J^T J, u (E,6) = sum J^T r, cost (1,) — the C-ABI of b200_lm_reproj2_accum."""
+    E = len(pa)
+    pe = np.repeat(np.arange(E), np.diff(pseg))
+    ia, ib = np.asarray(pa)[pe], np.asarray(pb)[pe]
+    r, _ = reproj2_residual(nodes, pts, pix, ia, ib, intr)
+    J = reproj2_jac_rows(nodes, pts, ia, ib, intr)
+    rho, w = robust(kind, delta, (r ** 2).sum(-1))
+    A, g = np.zeros((E, 6, 6)), np.zeros((E, 6))
+    np.add.at(A, pe, np.swapaxes(J, -1, -2) @ J * w[:, None, None])
+    np.add.at(g, pe, (np.swapaxes(J, -1, -2) @ r[..., None])[..., 0] * w[:, None])
+    return _triu_pack(A), g, np.array([rho.sum()])
+
+
+def reproj2_loss(nodes, pts, pix, ia, ib, intr=README_INTR, kind=0, delta=1.0):
+    return np.array([robust(kind, delta, (reproj2_residual(nodes, pts, pix, ia, ib, intr)[0] ** 2).sum(-1))[0].sum()])
+
+
+def reproj2_dense_jac(nodes, pts, ia, ib, intr=README_INTR):
+    """The reference's dense (2m, 7N) Jacobian of the model."""
+    J = reproj2_jac_rows(nodes, pts, ia, ib, intr)
+    m, N = len(ia), nodes.shape[0]
+    D = np.zeros((2 * m, 7 * N))
+    for k in range(m):
+        D[2 * k:2 * k + 2, 7 * ia[k]:7 * ia[k] + 6] += J[k]
+        D[2 * k:2 * k + 2, 7 * ib[k]:7 * ib[k] + 6] -= J[k]
+    return D

@@ -290,6 +290,26 @@ LM_OPS = [
 
 
 LM_OPS += [
+    ("b200_lm_reproj2_accum",
+     [("const REAL*", "nodes", "(N,7) SE3 poses"), ("const REAL*", "pts", "(m,3) points in the frame of pose a, rows sorted by pair"),
+      ("const REAL*", "pix", "(m,2)"), ("const int*", "pseg", "(E+1) row offsets per ordered pose pair"),
+      ("const int*", "pa", "(E) pose a of each pair"), ("const int*", "pb", "(E) pose b of each pair"),
+      ("const double*", "intr", "HOST (5): fx, skew, cx, fy, cy of proj(y); README `project` is -1, 0, 0, -1, 0"),
+      ("REAL*", "M", "(E,21) sum over the pair's rows of J^T J, J = d r / d xi_a = -d r / d xi_b"),
+      ("REAL*", "u", "(E,6) sum of J^T r"), ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", ""), ("double", "delta", "")],
+     "modjac + J^T J of optimizer.py:645-656 for r = proj(T_b^-1 T_a p) - z (README.md:170-178 project; "
+     "function/geometry.py:60-112,171-225 point2pixel / reprojerr; examples/module/reprojpgo/reprojpgo.py:16-28): the pairs "
+     "are the edges of the block-sparse system (b200_lm_pgo_pcg with ei = pb, ej = pa)"),
+    ("b200_lm_reproj2_loss",
+     [("const REAL*", "nodes", "(N,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"), ("const int*", "pseg", "(E+1)"),
+      ("const int*", "pa", "(E)"), ("const int*", "pb", "(E)"), ("const double*", "intr", "HOST (5)"),
+      ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", ""), ("double", "delta", "")],
+     "model.loss after the update, optimizer.py:673, for the two-pose reprojection model"),
+    ("b200_lm_reproj2_residual",
+     [("const REAL*", "nodes", "(N,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"),
+      ("const int*", "ia", "(m) pose a per row"), ("const int*", "ib", "(m) pose b per row"),
+      ("const double*", "intr", "HOST (5)"), ("REAL*", "r", "(m,2)")],
+     "model.forward of the two-pose reprojection model"),
     ("b200_lm_reproj_step",
      [("REAL*", "poses", "(ncam,7) parameters; overwritten with the trial poses when the trial is accepted"),
       ("const REAL*", "pts", "(m,3) camera-sorted"), ("const REAL*", "pix", "(m,2)"), ("const int*", "seg", "(ncam+1)"),

@@ -518,6 +518,129 @@ __global__ void __launch_bounds__(kLmThreads) lm_ba_loss_kernel(const T* __restr
   reduce_sums<1>(acc, ws);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two-pose reprojection (BASELINE.json configs[4] as stated: block-sparse J^T J; SURVEY.md §8d cfg 5-full):
+//   r_k = proj(T_b^-1 T_a p_k) - z_k,   proj(y) = (fx y.x / y.z + sk y.y / y.z + cx,  fy y.y / y.z + cy)
+// (README.md:170-178 `project` is fx = fy = -1, sk = cx = cy = 0; function/geometry.py:60-112,171-225 point2pixel /
+// reprojerr with intrinsics K is fx = K00, sk = K01, cx = K02, fy = K11, cy = K12; generalises
+// examples/module/reprojpgo/reprojpgo.py:16-28).  With left perturbations and w = T_a p (world point),
+// y = R_b^T (w - t_b):  d y / d xi_a = R_b^T [I, -w^],  d y / d xi_b = -R_b^T [I, -w^]  =>  J_b = -J_a =: -J.
+// All residuals of one ordered pose pair (a, b) therefore add into ONE 6x6 block M = sum J^T J that enters H at
+// (a,a), (b,b) and with a minus sign at (a,b), (b,a) — exactly the pose-graph edge structure, so the pairs are the
+// "edges" of the block-sparse PCG (pcg.cu).  Residual rows are sorted by pair: pseg[e] .. pseg[e+1] are pair e's rows.
+// ------------------------------------------------------------------------------------------------
+// one warp per pose pair: M_e (21) = sum J^T J, u_e (6) = sum J^T r over the pair's rows.  sums: ws[0] = sum rho(|r|^2)
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_reproj2_accum_kernel(const T* __restrict__ nodes, const T* __restrict__ pts,
+                                                                       const T* __restrict__ pix, const int* __restrict__ pseg,
+                                                                       const int* __restrict__ pa, const int* __restrict__ pb,
+                                                                       Intr<T> K, T* __restrict__ M, T* __restrict__ u,
+                                                                       double* ws, int rk, T rdelta, long long E) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
+  double acc[1] = {0.0};
+  for (long long e = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); e < E; e += (long long)gridDim.x * wpb) {
+    T a7[7], b7[7];
+    const long long ia = pa[e], ib = pb[e];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a7[k] = __ldg(nodes + ia * 7 + k); b7[k] = __ldg(nodes + ib * 7 + k); }
+    const Elem<T> Ta = load_se3(a7), Tb = load_se3(b7);
+    Sys6<T> s;
+    sys6_zero(s);
+    T loss = T(0);
+    for (int k = pseg[e] + lane; k < pseg[e + 1]; k += 32) {
+      const long long k0 = k;
+      V3<T> w, y;
+      reproj2_point(Ta, Tb, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), w, y);
+      T rx, ry;
+      reproj2_residual(K, y, pix[k0 * 2], pix[k0 * 2 + 1], rx, ry);
+      T j0[6], j1[6];
+      reproj2_rows(K, Tb, w, y, j0, j1);
+      T rho, wt;
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, wt);
+      if (rk) {
+        const T sw = m_sqrt(wt);
+        rx *= sw; ry *= sw;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { j0[q] *= sw; j1[q] *= sw; }
+      }
+      sys6_add_row(s, j0, rx);
+      sys6_add_row(s, j1, ry);
+      loss += rho;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        s.g[q] += __shfl_xor_sync(0xffffffffu, s.g[q], o);
+#pragma unroll
+        for (int bb = q; bb < 6; ++bb) s.A[q][bb] += __shfl_xor_sync(0xffffffffu, s.A[q][bb], o);
+      }
+      loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    }
+    if (lane == 0) {
+      int t = 0;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        u[e * 6 + q] = s.g[q];
+#pragma unroll
+        for (int bb = q; bb < 6; ++bb) M[e * 21 + t++] = s.A[q][bb];
+      }
+      acc[0] += (double)loss;
+    }
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_reproj2_loss_kernel(const T* __restrict__ nodes, const T* __restrict__ pts,
+                                                                      const T* __restrict__ pix, const int* __restrict__ pseg,
+                                                                      const int* __restrict__ pa, const int* __restrict__ pb,
+                                                                      Intr<T> K, double* ws, int rk, T rdelta, long long E) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = kLmThreads / 32;
+  double acc[1] = {0.0};
+  for (long long e = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); e < E; e += (long long)gridDim.x * wpb) {
+    T a7[7], b7[7];
+    const long long ia = pa[e], ib = pb[e];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { a7[k] = __ldg(nodes + ia * 7 + k); b7[k] = __ldg(nodes + ib * 7 + k); }
+    const Elem<T> Ta = load_se3(a7), Tb = load_se3(b7);
+    T loss = T(0);
+    for (int k = pseg[e] + lane; k < pseg[e + 1]; k += 32) {
+      const long long k0 = k;
+      V3<T> w, y;
+      reproj2_point(Ta, Tb, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), w, y);
+      T rx, ry, rho, wt;
+      reproj2_residual(K, y, pix[k0 * 2], pix[k0 * 2 + 1], rx, ry);
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, wt);
+      loss += rho;
+    }
+    acc[0] += (double)loss;
+  }
+  reduce_sums<1>(acc, ws);
+}
+
+// residual rows r (m, 2) for forward() parity; pair index per row
+template <typename T>
+__global__ void __launch_bounds__(kLmThreads) lm_reproj2_residual_kernel(const T* __restrict__ nodes, const T* __restrict__ pts,
+                                                                          const T* __restrict__ pix, const int* __restrict__ ia,
+                                                                          const int* __restrict__ ib, Intr<T> K,
+                                                                          T* __restrict__ r, long long m) {
+  for (long long k = (long long)blockIdx.x * kLmThreads + threadIdx.x; k < m; k += (long long)gridDim.x * kLmThreads) {
+    T a7[7], b7[7];
+    const long long a = ia[k], b = ib[k];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) { a7[q] = __ldg(nodes + a * 7 + q); b7[q] = __ldg(nodes + b * 7 + q); }
+    V3<T> w, y;
+    reproj2_point(load_se3(a7), load_se3(b7), mk(pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]), w, y);
+    T rx, ry;
+    reproj2_residual(K, y, pix[k * 2], pix[k * 2 + 1], rx, ry);
+    r[k * 2] = rx;
+    r[k * 2 + 1] = ry;
+  }
+}
+
 }  // namespace b200pose
 
 using namespace b200pose;
@@ -650,3 +773,35 @@ BA_ABI(f32, float)
 BA_ABI(f64, double)
 PGO_ABI(f32, float)
 PGO_ABI(f64, double)
+
+#define REPROJ2_ABI(SFX, CT)                                                                                          \
+  B200_EXPORT int b200_lm_reproj2_accum_##SFX(const CT* nodes, const CT* pts, const CT* pix, const int* pseg,         \
+                                              const int* pa, const int* pb, const double* intr, CT* M, CT* u,         \
+                                              double* ws, int robust, double delta, long long E, void* stream) {      \
+    if (E <= 0) return 0;                                                                                             \
+    const Intr<CT> K = {(CT)intr[0], (CT)intr[1], (CT)intr[2], (CT)intr[3], (CT)intr[4]};                             \
+    lm_reproj2_accum_kernel<CT><<<lm_grid(E, kLmThreads / 32), kLmThreads, 0, (cudaStream_t)stream>>>(                \
+        nodes, pts, pix, pseg, pa, pb, K, M, u, ws, robust, (CT)delta, E);                                            \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_reproj2_loss_##SFX(const CT* nodes, const CT* pts, const CT* pix, const int* pseg,          \
+                                             const int* pa, const int* pb, const double* intr, double* ws,            \
+                                             int robust, double delta, long long E, void* stream) {                   \
+    if (E <= 0) return 0;                                                                                             \
+    const Intr<CT> K = {(CT)intr[0], (CT)intr[1], (CT)intr[2], (CT)intr[3], (CT)intr[4]};                             \
+    lm_reproj2_loss_kernel<CT><<<lm_grid(E, kLmThreads / 32), kLmThreads, 0, (cudaStream_t)stream>>>(                 \
+        nodes, pts, pix, pseg, pa, pb, K, ws, robust, (CT)delta, E);                                                  \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_reproj2_residual_##SFX(const CT* nodes, const CT* pts, const CT* pix, const int* ia,        \
+                                                 const int* ib, const double* intr, CT* r, long long m,               \
+                                                 void* stream) {                                                      \
+    if (m <= 0) return 0;                                                                                             \
+    const Intr<CT> K = {(CT)intr[0], (CT)intr[1], (CT)intr[2], (CT)intr[3], (CT)intr[4]};                             \
+    lm_reproj2_residual_kernel<CT><<<lm_grid(m, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(nodes, pts, pix,  \
+                                                                                                    ia, ib, K, r, m); \
+    return (int)cudaGetLastError();                                                                                   \
+  }
+
+REPROJ2_ABI(f32, float)
+REPROJ2_ABI(f64, double)

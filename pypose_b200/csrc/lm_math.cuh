@@ -404,6 +404,31 @@ template <typename T> LM_HD void sym3_unpack(const T* a, T (&A)[3][3]) {
 
 
 
+// ---------------------------------------------------------------- two-pose reprojection (lm.cu lm_reproj2_*)
+// r = proj(T_b^-1 T_a p) - z with proj(y) = (fx y.x/y.z + sk y.y/y.z + cx, fy y.y/y.z + cy); see lm.cu for the citations
+template <typename T> struct Intr { T fx, sk, cx, fy, cy; };
+
+template <typename T> LM_HD void reproj2_point(const Elem<T>& Ta, const Elem<T>& Tb, const V3<T>& p, V3<T>& w, V3<T>& y) {
+  w = g_act<SE3g, T>(Ta, p);
+  y = qrot_t(Tb.q, w - Tb.t);
+}
+template <typename T> LM_HD void reproj2_residual(const Intr<T>& K, const V3<T>& y, T zx, T zy, T& rx, T& ry) {
+  const T iz = m_rcp(y.z);
+  rx = (K.fx * y.x + K.sk * y.y) * iz + K.cx - zx;
+  ry = K.fy * y.y * iz + K.cy - zy;
+}
+// rows of J = d r / d xi_a (2x6); d r / d xi_b = -J.  d proj / d y rotated to the world frame, then [e, w x e]
+template <typename T>
+LM_HD void reproj2_rows(const Intr<T>& K, const Elem<T>& Tb, const V3<T>& w, const V3<T>& y, T (&j0)[6], T (&j1)[6]) {
+  const T iz = m_rcp(y.z), iz2 = iz * iz;
+  const V3<T> e0 = qrot(Tb.q, mk(K.fx * iz, K.sk * iz, -(K.fx * y.x + K.sk * y.y) * iz2));
+  const V3<T> e1 = qrot(Tb.q, mk(T(0), K.fy * iz, -K.fy * y.y * iz2));
+  const V3<T> c0 = cross(w, e0), c1 = cross(w, e1);
+  j0[0] = e0.x; j0[1] = e0.y; j0[2] = e0.z; j0[3] = c0.x; j0[4] = c0.y; j0[5] = c0.z;
+  j1[0] = e1.x; j1[1] = e1.y; j1[2] = e1.z; j1[3] = c1.x; j1[4] = c1.y; j1[5] = c1.z;
+}
+
+
 // ---------------------------------------------------------------- LM accept / reject decision + damping strategies
 // IEEE double operations exactly as Python evaluates them: no fused multiply-adds on the device
 #ifdef __CUDA_ARCH__

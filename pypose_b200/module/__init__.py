@@ -1,4 +1,4 @@
-from .reproj import PoseReproj
+from .reproj import PoseReproj, TwoPoseReproj
 from .pgo import PoseGraph
 from .ba import BundleAdjustment
 from .imu_preintegrator import IMUPreintegrator

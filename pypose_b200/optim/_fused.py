@@ -218,6 +218,41 @@ def _reproj_residual(poses, pts, pix, cidx):
     return r
 
 
+torch.library.define(f"{NS}::lm_reproj2_accum",
+                     "(Tensor nodes, Tensor pts, Tensor pix, Tensor pseg, Tensor pa, Tensor pb, float[] intr, int robust, "
+                     "float delta) -> (Tensor, Tensor, Tensor)")
+torch.library.define(f"{NS}::lm_reproj2_loss",
+                     "(Tensor nodes, Tensor pts, Tensor pix, Tensor pseg, Tensor pa, Tensor pb, float[] intr, int robust, "
+                     "float delta) -> Tensor")
+
+
+def _intr(intr):
+    return ctypes.addressof((ctypes.c_double * 5)(*[float(v) for v in intr]))
+
+
+def _reproj2_accum(nodes, pts, pix, pseg, pa, pb, intr, robust=0, delta=1.0):
+    nodes, pts, pix = _same(nodes, pts, pix)
+    E = pa.shape[0]
+    ws = _workspace(nodes.device)
+    M = torch.empty(E, 21, dtype=nodes.dtype, device=nodes.device)
+    u = torch.empty(E, 6, dtype=nodes.dtype, device=nodes.device)
+    k = (ctypes.c_double * 5)(*[float(v) for v in intr])
+    _launch("b200_lm_reproj2_accum", nodes, [_p(nodes), _p(pts), _p(pix), _p(pseg), _p(pa), _p(pb), ctypes.addressof(k), _p(M),
+                                             _p(u), _p(ws), int(robust), float(delta)], E)
+    return M, u, ws[:1].clone()
+
+
+def _reproj2_loss(nodes, pts, pix, pseg, pa, pb, intr, robust=0, delta=1.0):
+    nodes, pts, pix = _same(nodes, pts, pix)
+    ws = _workspace(nodes.device)
+    k = (ctypes.c_double * 5)(*[float(v) for v in intr])
+    _launch("b200_lm_reproj2_loss", nodes, [_p(nodes), _p(pts), _p(pix), _p(pseg), _p(pa), _p(pb), ctypes.addressof(k), _p(ws),
+                                            int(robust), float(delta)], pa.shape[0])
+    return ws[:1].clone()
+
+
+torch.library.impl(f"{NS}::lm_reproj2_accum", "CUDA")(_reproj2_accum)
+torch.library.impl(f"{NS}::lm_reproj2_loss", "CUDA")(_reproj2_loss)
 torch.library.impl(f"{NS}::lm_ba_linearize", "CUDA")(_ba_linearize)
 torch.library.impl(f"{NS}::lm_ba_wtx", "CUDA")(_ba_wtx)
 torch.library.impl(f"{NS}::lm_ba_wv", "CUDA")(_ba_wv)
@@ -251,7 +286,7 @@ _DIRECT = {"lm_poseinv_loss": _poseinv_loss, "lm_poseinv_trial": _poseinv_trial,
            "lm_solve6_retract": _solve6_retract, "lm_reproj_loss": _reproj_loss, "lm_reproj_residual": _reproj_residual,
            "lm_pgo_linearize": _pgo_linearize, "lm_pgo_linearize_w": _pgo_linearize_w, "lm_pgo_scatter": _pgo_scatter, "lm_pgo_spmv": _pgo_spmv,
            "lm_pgo_loss": _pgo_loss, "lm_ba_linearize": _ba_linearize, "lm_ba_wtx": _ba_wtx, "lm_ba_wv": _ba_wv,
-           "lm_ba_loss": _ba_loss}
+           "lm_ba_loss": _ba_loss, "lm_reproj2_accum": _reproj2_accum, "lm_reproj2_loss": _reproj2_loss}
 
 LM_OPS = ["lm_poseinv_loss", "lm_poseinv_trial", "lm_reproj_accum", "lm_solve6_retract", "lm_reproj_loss",
           "lm_reproj_residual"]

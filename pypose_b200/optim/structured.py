@@ -291,7 +291,7 @@ class PGOProblem(_Problem):
         self.dtype = self.param.dtype
         self.ei = edges[..., 0].to(torch.int32).contiguous()
         self.ej = edges[..., 1].to(torch.int32).contiguous()
-        self.Z = Z.tensor().to(self.dtype).reshape(-1, 7).contiguous()
+        self.Z = None if Z is None else Z.tensor().to(self.dtype).reshape(-1, 7).contiguous()
         # information matrices (examples/module/pgo/pgo.py:75 `weight=infos`): (E,6,6) or one (6,6) for all edges
         self.W = None if weight is None else weight.to(self.dtype).reshape(-1, 36).contiguous()
         # B200POSE_DETERMINISTIC=1: node adjacency (single-rank device route) — every edge sits once in each endpoint's
@@ -319,18 +319,24 @@ class PGOProblem(_Problem):
     def _nodes(self):
         return self.param.tensor().reshape(-1, 7)
 
+    # the two family-specific pieces (overridden by Reproj2Problem): per-edge blocks and the loss at given nodes
+    def _loss_at(self, nodes):
+        return _fused.call("lm_pgo_loss", nodes, self.Z, self.ei, self.ej, *self.robust)
+
+    def _blocks(self, nodes):
+        """-> M (E,21), u (E,6), cost (1,), unweighted (M0, u0) or None"""
+        if self.W is None:
+            M, u, cur = _fused.call("lm_pgo_linearize", nodes, self.Z, self.ei, self.ej, *self.robust)
+            return M, u, cur, None
+        M, u, M0, u0, cur = _fused.call("lm_pgo_linearize_w", nodes, self.Z, self.ei, self.ej, self.W, *self.robust)
+        return M, u, cur, (M0, u0)
+
     def loss(self):
-        s = _fused.call("lm_pgo_loss", self._nodes(), self.Z, self.ei, self.ej, *self.robust)
-        return _allreduce(s, self.group)[0].to(self.dtype)
+        return _allreduce(self._loss_at(self._nodes()), self.group)[0].to(self.dtype)
 
     def linearize(self):
         nodes = self._nodes()
-        unw = None
-        if self.W is None:
-            M, u, cur = _fused.call("lm_pgo_linearize", nodes, self.Z, self.ei, self.ej, *self.robust)
-        else:
-            M, u, M0, u0, cur = _fused.call("lm_pgo_linearize_w", nodes, self.Z, self.ei, self.ej, self.W, *self.robust)
-            unw = (M0, u0)
+        M, u, cur, unw = self._blocks(nodes)
         if M.is_cuda and self.group is None and self.deterministic:      # gathers over node-ordered copies, no atomics
             Mn, Hd, g = _fused.pgo_node_order(M, u, self.epos_i, self.epos_j, self.nptr)
             return (M, Mn), Hd, g, cur, unw
@@ -386,7 +392,7 @@ class PGOProblem(_Problem):
 
     def _finish_trial(self, D, predicted, cur):
         self._trial = _retract_se3(D, self._nodes())
-        tl = _fused.call("lm_pgo_loss", self._trial, self.Z, self.ei, self.ej, *self.robust)
+        tl = self._loss_at(self._trial)
         shard = _allreduce(torch.cat([cur, tl]), self.group)
         return self._result(torch.cat([shard, predicted, predicted.new_zeros(1)]),
                             {"cur": 0, "loss": 1, "predicted": 2, "failed": 3})
@@ -396,6 +402,38 @@ class PGOProblem(_Problem):
 
     def _peer(self, max_elems):
         return _peer_allreduce(self, self.param, max_elems)
+
+
+class Reproj2Problem(PGOProblem):
+    """Two-pose reprojection r = proj(T_b^-1 T_a p) - z (module.TwoPoseReproj; BASELINE.json configs[4] as stated).
+    d r / d xi_b = -d r / d xi_a, so all rows of one ordered pair (a, b) add into one 6x6 block and the pairs are the edges
+    of the pose-graph machinery above: rows are sorted by pair once, csrc/lm.cu lm_reproj2_accum gives (M, u) per pair in
+    one warp-per-pair pass over 20 B per row, everything after that (block diagonal, device PCG, retraction, multi-GPU
+    reduction) is inherited.  Sign convention of PGOProblem: edge (ei, ej) has J_ei = -J, J_ej = +J  =>  ei = b, ej = a."""
+
+    def __init__(self, model, points, pixels, ia, ib, intr, key, group, robust, tol, maxiter, param=None):
+        param = model.poses if param is None else param
+        N = param.tensor().reshape(-1, 7).shape[0]
+        ia, ib = ia.reshape(-1).long(), ib.reshape(-1).long()
+        order = torch.sort(ia * N + ib, stable=True)[1]
+        pair_key = (ia * N + ib)[order]
+        uniq, counts = torch.unique_consecutive(pair_key, return_counts=True)
+        pa, pb = (uniq // N), (uniq % N)
+        super().__init__(model, torch.stack([pb, pa], 1), None, key, group, robust, tol, maxiter, param=param)
+        self.pa, self.pb = pa.to(torch.int32).contiguous(), pb.to(torch.int32).contiguous()
+        self.pseg = torch.zeros(uniq.numel() + 1, dtype=torch.int32, device=ia.device)
+        self.pseg[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        self.pts = points.reshape(-1, 3)[order].to(self.dtype).contiguous()
+        self.pix = pixels.reshape(-1, 2)[order].to(self.dtype).contiguous()
+        self.intr = tuple(float(v) for v in intr)
+
+    def _loss_at(self, nodes):
+        return _fused.call("lm_reproj2_loss", nodes, self.pts, self.pix, self.pseg, self.pa, self.pb, self.intr, *self.robust)
+
+    def _blocks(self, nodes):
+        M, u, cur = _fused.call("lm_reproj2_accum", nodes, self.pts, self.pix, self.pseg, self.pa, self.pb, self.intr,
+                                *self.robust)
+        return M, u, cur, None
 
 
 def _peer_allreduce(prob, param, max_elems):
@@ -746,6 +784,17 @@ def recognize(model, input, params, group=None, robust=(0, 1.0), solver=None, sp
     from ..module.reproj import PoseReproj
     from ..module.pgo import PoseGraph
     from .solver import CG
+    from ..module.reproj import TwoPoseReproj
+    if _is_builtin(model, TwoPoseReproj):
+        intr = model.intr()
+        if param is not model.poses or intr is None or not (isinstance(solver, CG) or sparse) or weight is not None:
+            return None
+        points, pixels, ia, ib = input
+        if not (_in_range(ia, param.shape[0]) and _in_range(ib, param.shape[0])):
+            raise IndexError("TwoPoseReproj: pose index out of range")
+        tol = solver.tol if isinstance(solver, CG) else 1e-8
+        maxiter = solver.maxiter if isinstance(solver, CG) else None
+        return Reproj2Problem(model, points, pixels, ia, ib, intr, _input_key(input), group, robust, tol, maxiter)
     if _is_builtin(model, PoseGraph):
         # block-sparse H needs an iterative solver: taken only when the user asked for one (solver=PCG()/CG(),
         # or sparse=True as in the reference's bae route); otherwise the generic dense Cholesky route runs.

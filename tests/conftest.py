@@ -131,6 +131,17 @@ def _install_cpu_oracle_lm_kernels():
     def ba_loss(poses, points, pix, cidx, pidx, robust, delta):
         return f64(L.ba_loss(n(poses), n(points), n(pix), cidx.numpy(), pidx.numpy(), robust, delta))
 
+    def reproj2_accum(nodes, pts, pix, pseg, pa, pb, intr, robust, delta):
+        M, u, c = L.reproj2_accum(n(nodes), n(pts), n(pix), pseg.numpy(), pa.numpy(), pb.numpy(), tuple(intr), robust, delta)
+        return t(M, nodes), t(u, nodes), f64(c)
+
+    def reproj2_loss(nodes, pts, pix, pseg, pa, pb, intr, robust, delta):
+        pe = np.repeat(np.arange(len(pa)), np.diff(pseg.numpy()))
+        return f64(L.reproj2_loss(n(nodes), n(pts), n(pix), pa.numpy()[pe], pb.numpy()[pe], tuple(intr), robust, delta))
+
+    torch.library.impl("b200pose::lm_reproj2_accum", "CPU")(reproj2_accum)
+    torch.library.impl("b200pose::lm_reproj2_loss", "CPU")(reproj2_loss)
+
     for name, fn in (("lm_ba_linearize", ba_linearize), ("lm_ba_wtx", ba_wtx), ("lm_ba_wv", ba_wv), ("lm_ba_loss", ba_loss)):
         torch.library.impl(f"b200pose::{name}", "CPU")(fn)
 

@@ -123,3 +123,14 @@ def lm_decide(ctl, cur, trial, predicted, failed):
     lib().hostmath_lm_decide(_vp(c), ctypes.c_double(cur), ctypes.c_double(trial), ctypes.c_double(predicted),
                              ctypes.c_double(failed), _vp(st))
     return st
+
+
+def reproj2_rows(nodes, pts, pix, ia, ib, intr):
+    nodes, pts, pix = (np.ascontiguousarray(a) for a in (nodes, pts, pix))
+    ia, ib = np.ascontiguousarray(ia, dtype=np.int32), np.ascontiguousarray(ib, dtype=np.int32)
+    k = np.ascontiguousarray(intr, dtype=np.float64)
+    m = pts.shape[0]
+    r, J = np.empty((m, 2), nodes.dtype), np.empty((m, 2, 6), nodes.dtype)
+    lib().hostmath_reproj2_rows(int(nodes.dtype == np.float64), _vp(nodes), _vp(pts), _vp(pix), _vp(ia), _vp(ib), _vp(k), _vp(r),
+                                _vp(J), ctypes.c_longlong(m))
+    return r, J

@@ -228,3 +228,24 @@ extern "C" void hostmath_lm_decide(const double* c, double cur, double trial, do
   k.smax = c[13];
   lm_decide(k, cur, trial, predicted, failed, st);
 }
+
+// ---- two-pose reprojection rows (csrc/lm_math.cuh reproj2_*) ------------------------------------------------------
+template <typename T>
+static void reproj2_rows_host(const T* nodes, const T* pts, const T* pix, const int* ia, const int* ib, const double* intr,
+                              T* r, T* J, long long m) {
+  const Intr<T> K = {(T)intr[0], (T)intr[1], (T)intr[2], (T)intr[3], (T)intr[4]};
+  for (long long k = 0; k < m; ++k) {
+    const Elem<T> Ta = load_elem<SE3g, T>(nodes + (long long)ia[k] * 7), Tb = load_elem<SE3g, T>(nodes + (long long)ib[k] * 7);
+    V3<T> w, y;
+    reproj2_point(Ta, Tb, mk(pts[k * 3], pts[k * 3 + 1], pts[k * 3 + 2]), w, y);
+    reproj2_residual(K, y, pix[k * 2], pix[k * 2 + 1], r[k * 2], r[k * 2 + 1]);
+    T j0[6], j1[6];
+    reproj2_rows(K, Tb, w, y, j0, j1);
+    for (int q = 0; q < 6; ++q) { J[k * 12 + q] = j0[q]; J[k * 12 + 6 + q] = j1[q]; }
+  }
+}
+extern "C" void hostmath_reproj2_rows(int is64, const void* nodes, const void* pts, const void* pix, const int* ia, const int* ib,
+                                      const double* intr, void* r, void* J, long long m) {
+  if (is64) reproj2_rows_host<double>((const double*)nodes, (const double*)pts, (const double*)pix, ia, ib, intr, (double*)r, (double*)J, m);
+  else reproj2_rows_host<float>((const float*)nodes, (const float*)pts, (const float*)pix, ia, ib, intr, (float*)r, (float*)J, m);
+}

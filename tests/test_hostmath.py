@@ -4,6 +4,7 @@ a GPU; the GPU tests (test_lie_gpu.py) then validate the kernels proper through 
 
 Tolerances: fp64 1e-12 (north_star), fp32 2e-6 relative to (1 + |truth|).
 Tiny-angle rows are compared with the oracle in wide_taylor() mode (see oracle/lie_oracle.py)."""
+import os
 import numpy as np
 import pytest
 
@@ -230,3 +231,28 @@ def test_lm_decide_equals_python_strategies_and_accept_rule():
         _lmstep.apply_state(strat, got, list(st))
         for k in ref_pg:
             assert got[k] == ref_pg[k], (kind, k, got[k], ref_pg[k])
+
+
+@pytest.mark.parametrize("intr", [(-1.0, 0.0, 0.0, -1.0, 0.0), (320.0, 0.5, 310.0, 300.0, 250.0)])
+def test_two_pose_reprojection_rows_equal_oracle_chain_rule(intr):
+    """csrc/lm_math.cuh reproj2_* ([e, w x e] form) against oracle/lm_oracle.py (d proj/dy [I, -y^] Adj(T_b^-1), the
+    reference's backward rules chained) and against the oracle's own finite differences."""
+    from oracle import lm_oracle as L
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lm2.npz"))
+    nodes, pts, ia, ib = g["poses0"], g["pts"], g["ia"], g["ib"]
+    pix = g["pix_readme"]
+    r, J = hostmath.reproj2_rows(nodes, pts, pix, ia, ib, intr)
+    r_o, _ = L.reproj2_residual(nodes, pts, pix, ia, ib, intr)
+    J_o = L.reproj2_jac_rows(nodes, pts, ia, ib, intr)
+    scale = max(1.0, abs(intr[0]))
+    assert np.abs(r - r_o).max() <= 1e-10 * scale and np.abs(J - J_o).max() <= 1e-9 * scale * max(1.0, np.abs(J_o).max() / scale)
+    # finite differences of the oracle residual w.r.t. a left perturbation of pose a / pose b of row 0
+    h = 1e-6
+    for which, sign in (("a", 1.0), ("b", -1.0)):
+        for q in range(6):
+            d = np.zeros(6); d[q] = h
+            pert = nodes.copy()
+            idx = ia[0] if which == "a" else ib[0]
+            pert[idx] = L.retract(d[None], nodes[idx][None])[0]
+            rp, _ = L.reproj2_residual(pert, pts[:1], pix[:1], ia[:1], ib[:1], intr)
+            np.testing.assert_allclose((rp[0] - r_o[0]) / h, sign * J_o[0][:, q], atol=2e-5 * scale, rtol=2e-4)

@@ -3,6 +3,7 @@ trajectories, plus convergence at the BASELINE.json sizes (configs[2] and config
 
 Tolerances: fp64 1e-9 relative on sums / 1e-10 on poses; fp32 1e-4 relative on sums, 5e-5 on poses.
 LM converged pose error <= 1e-5 (north_star)."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -11,6 +12,7 @@ from torch import nn
 import pypose_b200 as pp
 from oracle import lie_oracle as O
 from oracle import lm_oracle as L
+from oracle import scan_oracle as S
 from tests.util import rand_group
 
 pytestmark = pytest.mark.gpu
@@ -632,3 +634,70 @@ def test_lm_bundle_adjustment_huber_reference_trajectory_on_gpu(golden_lm):
         np.testing.assert_allclose(net.poses.detach().cpu().numpy(), g["ba_robust/huber/poses"][k], atol=2e-6)
         np.testing.assert_allclose(net.points_3d.detach().cpu().numpy(), g["ba_robust/huber/points"][k], atol=2e-6)
         assert opt.reject_count == g["ba_robust/huber/reject"][k]
+
+
+# ------------------------------------------------------------------ two-pose reprojection (config 5 as stated)
+def test_reproj2_kernels_vs_oracle():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lm2.npz"))
+    nodes, pts, ia, ib = g["poses0"], g["pts"], g["ia"], g["ib"]
+    N = nodes.shape[0]
+    order = np.argsort(ia * N + ib, kind="stable")
+    key = (ia * N + ib)[order]
+    uniq, counts = np.unique(key, return_counts=True)
+    pa, pb = (uniq // N).astype(np.int32), (uniq % N).astype(np.int32)
+    pseg = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    for tag, intr in (("readme", L.README_INTR), ("k", (320.0, 0.5, 310.0, 300.0, 250.0))):
+        pix = g["pix_k"] if tag == "k" else g["pix_readme"]
+        for dt, tol in ((torch.float64, 1e-10), (torch.float32, 3e-5)):
+            for kind, delta in ((0, 1.0), (1, 0.5 if tag == "k" else 0.002)):
+                M, u, c = ops.lm_reproj2_accum(cu(nodes, dt), cu(pts[order], dt), cu(pix[order], dt), torch.from_numpy(pseg).cuda(),
+                                               torch.from_numpy(pa).cuda(), torch.from_numpy(pb).cuda(), list(intr), kind, delta)
+                Mo, uo, co = L.reproj2_accum(cu(nodes, dt).double().cpu().numpy(), cu(pts[order], dt).double().cpu().numpy(),
+                                             cu(pix[order], dt).double().cpu().numpy(), pseg, pa, pb, intr, kind, delta)
+                for a, b, nm in ((M, Mo, "M"), (u, uo, "u"), (c, co, "cost")):
+                    assert np.abs(a.double().cpu().numpy() - b).max() <= tol * max(1.0, np.abs(b).max()), (tag, dt, kind, nm)
+                l = ops.lm_reproj2_loss(cu(nodes, dt), cu(pts[order], dt), cu(pix[order], dt), torch.from_numpy(pseg).cuda(),
+                                        torch.from_numpy(pa).cuda(), torch.from_numpy(pb).cuda(), list(intr), kind, delta)
+                assert abs(float(l[0]) - co[0]) <= tol * max(1.0, abs(co[0]))
+
+
+@pytest.mark.parametrize("tag,strategy", [("readme", "trustregion"), ("readme", "constant"), ("k", "trustregion"), ("hard", "trustregion")])
+def test_lm_two_pose_reprojection_matches_reference_trajectory_gpu(tag, strategy):
+    from tests.test_lm import _lm2_run
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lm2.npz"))
+    steps = 8 if tag == "hard" else 6
+    run = _lm2_run(g, tag, strategy, "structured", dev="cuda", steps=steps)
+    ref_loss = g[f"{tag}/{strategy}/loss"]
+    for k, (loss, poses, rej) in enumerate(run):
+        np.testing.assert_allclose(loss, ref_loss[k], rtol=1e-5 if tag == "hard" else 2e-6)
+        if tag != "hard":
+            np.testing.assert_allclose(poses, g[f"{tag}/{strategy}/poses"][k], atol=2e-7)
+        if k == 0 or ref_loss[k - 1] - ref_loss[k] > 1e-9 * ref_loss[k]:
+            assert rej == g[f"{tag}/{strategy}/reject"][k]
+
+
+def test_lm_two_pose_reprojection_fp32_converges_to_1e5():
+    """north_star: LM converged pose error <= 1e-5, here in fp32 on the block-sparse config: noise-free pixels, so the
+    relative poses T_b^-1 T_a of every observed pair must come back to ground truth (the absolute poses keep the gauge)."""
+    rng = np.random.default_rng(3)
+    N, per = 2000, 24
+    step = O.exp("SE3", np.tile([[0.3, 0.02, 0.0, 0.0, 0.05, 0.02]], (N, 1)) + 0.02 * rng.standard_normal((N, 6)))
+    gt = S.cumprod("SE3", step[None], False)[0]
+    ia = np.repeat(np.arange(N - 3), 3 * per)
+    ib = ia + np.tile(np.repeat([1, 2, 3], per), N - 3)
+    m = len(ia)
+    yb = rng.uniform([-2, -2, 2], [2, 2, 6], (m, 3))
+    rel = O.mul("SE3", O.inv("SE3", gt[ia]), gt[ib])
+    pts = O.act("SE3", rel, yb)
+    pix = -yb[:, :2] / yb[:, 2:]
+    init = O.mul("SE3", O.exp("SE3", 0.02 * rng.standard_normal((N, 6))), gt)
+    net = pp.module.TwoPoseReproj(pp.SE3(cu(init, torch.float32)))
+    opt = pp.optim.LM(net, solver=pp.optim.solver.PCG(tol=1e-4, maxiter=200), sparse=True)
+    inp = (cu(pts, torch.float32), cu(pix, torch.float32), torch.from_numpy(ia).cuda(), torch.from_numpy(ib).cuda())
+    for _ in range(12):
+        opt.step(inp)
+    P = net.poses.detach().double().cpu().numpy()
+    est = O.mul("SE3", O.inv("SE3", P[ib[::per]]), P[ia[::per]])
+    ref = O.mul("SE3", O.inv("SE3", gt[ib[::per]]), gt[ia[::per]])
+    err = np.abs(O.log("SE3", O.mul("SE3", O.inv("SE3", ref), est))).max()
+    assert err <= 1e-5, err
