@@ -184,15 +184,6 @@ LM_OPS = [
      [("const REAL*", "A6", "(P,6) packed symmetric 3x3"), ("const REAL*", "t", "(P,3)"), ("double", "alpha", ""),
       ("REAL*", "out", "(P,3) alpha * A t")],
      "back-substitution dp = Hpp^-1 (-gp - W^T dc)"),
-    ("b200_lm_pgo_node_order",
-     [("const REAL*", "M", "(E,21)"), ("const REAL*", "u", "(E,6)"), ("const int*", "epos_i", "(E) position of the edge in its first node's list"),
-      ("const int*", "epos_j", "(E) position in its second node's list"), ("REAL*", "Mn", "(2E,21) M_e at both positions"),
-      ("REAL*", "un", "(2E,6) -u_e at the first node's position, +u_e at the second's")],
-     "node-ordered copy of the per-edge blocks so that H products and block sums are gathers (no atomics)"),
-    ("b200_lm_pgo_node_sums",
-     [("const REAL*", "Mn", "(2E,21)"), ("const REAL*", "un", "(2E,6)"), ("const int*", "nptr", "(N+1) offsets per node"),
-      ("REAL*", "Hd", "(N,21) diagonal blocks of J^T J"), ("REAL*", "g", "(N,6) J^T R")],
-     "diagonal of A = J^T J (optimizer.py:642-643) and b = J^T R (optimizer.py:668), deterministic"),
     ("b200_lm_pgo_pcg",
      [("const REAL*", "M", "(E,21) per-edge J^T J"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
       ("long long", "E", "edges"), ("const REAL*", "Minv", "(n,21) preconditioner blocks"),
@@ -209,13 +200,6 @@ LM_OPS = [
       ("long long", "result", "payload byte offset of the all-reduce result area"),
       ("long long", "epoch", "all-reduce epochs consumed so far on the PCG channel"), ("unsigned*", "tickets", "(2) zeroed")],
      "PCG.forward loop, optim/solver.py:312-340, with M = block-Jacobi; enqueues `iters` iterations without a host sync"),
-    ("b200_lm_pgo_pcg_gather",
-     [("const REAL*", "Mn", "(2E,21) node-ordered per-edge blocks"), ("const int*", "nother", "(2E) opposite node of each entry"),
-      ("const int*", "nptr", "(n+1) offsets per node"), ("const REAL*", "Minv", "(n,21)"), ("const REAL*", "extra", "(n,6)"),
-      ("const REAL*", "g", "(n,6)"), ("REAL*", "x", "(n,6)"), ("REAL*", "r", "(n,6)"), ("REAL*", "z", "(n,6)"), ("REAL*", "p", "(n,6)"),
-      ("REAL*", "q", "(n,6)"), ("REAL*", "xbest", "(n,6)"), ("double*", "cg", "(16) state"), ("double*", "ws", ""), ("double", "tol", ""),
-      ("long long", "maxiter", ""), ("long long", "first_iter", ""), ("long long", "iters", "")],
-     "as b200_lm_pgo_pcg with the H product as a gather over node-ordered blocks: no atomics, bit-reproducible"),
     ("b200_lm_cg_finish",
      [("REAL*", "x", "(n,6) in: last iterate; out: the returned solution"), ("const REAL*", "xbest", "(n,6)"),
       ("const double*", "cg", "(16) state of the finished solve")],
@@ -290,6 +274,38 @@ LM_OPS = [
 
 
 LM_OPS += [
+    ("b200_lm_pgo_linearize_n",
+     [("const REAL*", "nodes", "(N,7)"), ("const REAL*", "Z", "(E,7)"), ("const int*", "ei", "(E)"), ("const int*", "ej", "(E)"),
+      ("const int*", "epos_i", "(E) slot of the edge in its first node's list"),
+      ("const int*", "epos_j", "(E) slot in its second node's list"),
+      ("REAL*", "Mn", "(2E,24) node-ordered blocks: upper triangle of J^T J (21) + 3 pad, written at both slots"),
+      ("REAL*", "un", "(2E,6) -J^T r at the first node's slot, +J^T r at the second's"),
+      ("double*", "ws", "ws[0] = sum rho(|r|^2)"), ("int", "robust", ""), ("double", "delta", "")],
+     "b200_lm_pgo_linearize writing its blocks directly in node order (no atomics downstream); optimizer.py:645-656"),
+    ("b200_lm_reproj2_accum_n",
+     [("const REAL*", "nodes", "(N,7)"), ("const REAL*", "pts", "(m,3)"), ("const REAL*", "pix", "(m,2)"), ("const int*", "pseg", "(E+1)"),
+      ("const int*", "pa", "(E)"), ("const int*", "pb", "(E)"), ("const double*", "intr", "HOST (5)"),
+      ("const int*", "epos_i", "(E) slot of the pair in pose b's list"), ("const int*", "epos_j", "(E) slot in pose a's list"),
+      ("REAL*", "Mn", "(2E,24)"), ("REAL*", "un", "(2E,6)"), ("double*", "ws", ""), ("int", "robust", ""), ("double", "delta", "")],
+     "b200_lm_reproj2_accum writing its blocks directly in node order"),
+    ("b200_lm_pgo2_node_sums",
+     [("const REAL*", "Mn", "(2E,24)"), ("const REAL*", "un", "(2E,6)"), ("const int*", "nptr", "(N+1) offsets per node"),
+      ("REAL*", "Hd", "(N,21) diagonal blocks of J^T J"), ("REAL*", "g", "(N,6) J^T R")],
+     "diagonal of A = J^T J (optimizer.py:642-643) and b = J^T R (optimizer.py:668) by gather: one writer per node"),
+    ("b200_lm_pgo2_pcg",
+     [("const REAL*", "Mn", "(2E,24) node-ordered blocks"), ("const int*", "nother", "(2E) opposite node of each slot"),
+      ("const int*", "nptr", "(n+1)"), ("const REAL*", "Minv", "(n,21) block-Jacobi preconditioner"),
+      ("const REAL*", "extra", "(n,6) clamp / damping added to diag H"), ("const REAL*", "g", "(n,6); solves (H+extra) x = -g"),
+      ("REAL*", "x", "(n,6)"), ("REAL*", "r", "(n,6)"), ("REAL*", "z", "(n,6)"), ("REAL*", "p0", "(n,6) direction, even iterations"),
+      ("REAL*", "p1", "(n,6) direction, odd iterations"), ("REAL*", "q", "(n,6)"), ("REAL*", "xbest", "(n,6)"),
+      ("double*", "cg", "(16) state, see b200_lm_pgo_pcg"), ("double*", "ws", ""), ("double", "tol", ""),
+      ("long long", "maxiter", ""), ("long long", "first_iter", ""), ("long long", "iters", "")],
+     "PCG.forward loop, optim/solver.py:312-340, two launches per iteration: direction update + (H + D) p + p.Ap by gather, "
+     "then the vector update with its reductions; no atomics, bit-reproducible"),
+    ("b200_lm_pgo2_predicted",
+     [("const REAL*", "Mn", "(2E,24)"), ("const int*", "nother", "(2E)"), ("const int*", "nptr", "(n+1)"), ("const REAL*", "x", "(n,6) step"),
+      ("const REAL*", "g", "(n,6)"), ("double*", "ws", "ws[0] = x^T H x + 2 x^T g")],
+     "TrustRegion 'predicted' reduction (J D)^T (2 R + J D), optim/strategy.py:143, by gather"),
     ("b200_lm_reproj2_accum",
      [("const REAL*", "nodes", "(N,7) SE3 poses"), ("const REAL*", "pts", "(m,3) points in the frame of pose a, rows sorted by pair"),
       ("const REAL*", "pix", "(m,2)"), ("const int*", "pseg", "(E+1) row offsets per ordered pose pair"),

@@ -248,10 +248,41 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_residual_kernel(const T*
 // (i,j), (j,i).  M_e (21) and u_e = J^T r (6) are stored per edge; H is never assembled — the PCG multiplies with it
 // edge by edge (what the reference delegates to the external `bae` package, optimizer.py:629-643).
 // ------------------------------------------------------------------------------------------------
+// One edge's blocks, per edge (M, u: the scatter / multi-GPU route) and / or in node order (Mn, un: 24-float slots at the
+// edge's position in its first node's list — the node whose Jacobian is -J — and in its second node's list; pcg2.cu)
+template <typename T>
+__device__ __forceinline__ void store_edge_blocks(const Sys6<T>& s, long long e, T* __restrict__ M, T* __restrict__ u,
+                                                  const int* __restrict__ epos_i, const int* __restrict__ epos_j,
+                                                  T* __restrict__ Mn, T* __restrict__ un) {
+  if (M) {
+    int q = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      u[e * 6 + p] = s.g[p];
+#pragma unroll
+      for (int c = p; c < 6; ++c) M[e * 21 + q++] = s.A[p][c];
+    }
+  }
+  if (Mn) {
+    const long long si = epos_i[e], sj = epos_j[e];
+    int q = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      un[si * 6 + p] = -s.g[p];
+      un[sj * 6 + p] = s.g[p];
+#pragma unroll
+      for (int c = p; c < 6; ++c) { Mn[si * 24 + q] = s.A[p][c]; Mn[sj * 24 + q] = s.A[p][c]; ++q; }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) lm_pgo_linearize_kernel(const T* __restrict__ nodes, const T* __restrict__ Z,
                                                                        const int* __restrict__ ei, const int* __restrict__ ej,
-                                                                       T* __restrict__ M, T* __restrict__ u, double* ws, int rk,
+                                                                       T* __restrict__ M, T* __restrict__ u,
+                                                                       const int* __restrict__ epos_i,
+                                                                       const int* __restrict__ epos_j, T* __restrict__ Mn,
+                                                                       T* __restrict__ un, double* ws, int rk,
                                                                        T rdelta, long long E) {
   double acc[1] = {0.0};
   for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
@@ -265,13 +296,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_pgo_linearize_kernel(const T* _
     T rho, w;
     robust_eval(rk, rdelta, tang6_sqnorm(r), rho, w);
     if (rk) sys6_scale(s, w);
-    int q = 0;
-#pragma unroll
-    for (int p = 0; p < 6; ++p) {
-      u[e * 6 + p] = s.g[p];
-#pragma unroll
-      for (int c = p; c < 6; ++c) M[e * 21 + q++] = s.A[p][c];
-    }
+    store_edge_blocks(s, e, M, u, epos_i, epos_j, Mn, un);
     acc[0] += (double)rho;
   }
   reduce_sums<1>(acc, ws);
@@ -535,7 +560,10 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj2_accum_kernel(const T* _
                                                                        const T* __restrict__ pix, const int* __restrict__ pseg,
                                                                        const int* __restrict__ pa, const int* __restrict__ pb,
                                                                        Intr<T> K, T* __restrict__ M, T* __restrict__ u,
-                                                                       double* ws, int rk, T rdelta, long long E) {
+                                                                       const int* __restrict__ epos_i,
+                                                                       const int* __restrict__ epos_j, T* __restrict__ Mn,
+                                                                       T* __restrict__ un, double* ws, int rk, T rdelta,
+                                                                       long long E) {
   const int lane = threadIdx.x & 31;
   const int wpb = kLmThreads / 32;
   double acc[1] = {0.0};
@@ -579,13 +607,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj2_accum_kernel(const T* _
       loss += __shfl_xor_sync(0xffffffffu, loss, o);
     }
     if (lane == 0) {
-      int t = 0;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        u[e * 6 + q] = s.g[q];
-#pragma unroll
-        for (int bb = q; bb < 6; ++bb) M[e * 21 + t++] = s.A[q][bb];
-      }
+      store_edge_blocks(s, e, M, u, epos_i, epos_j, Mn, un);
       acc[0] += (double)loss;
     }
   }
@@ -701,7 +723,16 @@ B200_EXPORT long long b200_lm_workspace_doubles(void) { return 8 + (long long)kM
                                               void* stream) {                                                         \
     if (E <= 0) return 0;                                                                                             \
     lm_pgo_linearize_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                     \
-        nodes, Z, ei, ej, M, u, ws, robust, (CT)delta, E);                                                            \
+        nodes, Z, ei, ej, M, u, (const int*)nullptr, (const int*)nullptr, (CT*)nullptr, (CT*)nullptr, ws, robust,     \
+        (CT)delta, E);                                                                                                \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_pgo_linearize_n_##SFX(const CT* nodes, const CT* Z, const int* ei, const int* ej,           \
+                                                const int* epos_i, const int* epos_j, CT* Mn, CT* un, double* ws,     \
+                                                int robust, double delta, long long E, void* stream) {                \
+    if (E <= 0) return 0;                                                                                             \
+    lm_pgo_linearize_kernel<CT><<<lm_grid(E, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(                     \
+        nodes, Z, ei, ej, (CT*)nullptr, (CT*)nullptr, epos_i, epos_j, Mn, un, ws, robust, (CT)delta, E);              \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_linearize_w_##SFX(const CT* nodes, const CT* Z, const int* ei, const int* ej, const CT* W, \
@@ -781,7 +812,19 @@ PGO_ABI(f64, double)
     if (E <= 0) return 0;                                                                                             \
     const Intr<CT> K = {(CT)intr[0], (CT)intr[1], (CT)intr[2], (CT)intr[3], (CT)intr[4]};                             \
     lm_reproj2_accum_kernel<CT><<<lm_grid(E, kLmThreads / 32), kLmThreads, 0, (cudaStream_t)stream>>>(                \
-        nodes, pts, pix, pseg, pa, pb, K, M, u, ws, robust, (CT)delta, E);                                            \
+        nodes, pts, pix, pseg, pa, pb, K, M, u, (const int*)nullptr, (const int*)nullptr, (CT*)nullptr, (CT*)nullptr, \
+        ws, robust, (CT)delta, E);                                                                                    \
+    return (int)cudaGetLastError();                                                                                   \
+  }                                                                                                                   \
+  B200_EXPORT int b200_lm_reproj2_accum_n_##SFX(const CT* nodes, const CT* pts, const CT* pix, const int* pseg,       \
+                                                const int* pa, const int* pb, const double* intr, const int* epos_i,  \
+                                                const int* epos_j, CT* Mn, CT* un, double* ws, int robust,            \
+                                                double delta, long long E, void* stream) {                            \
+    if (E <= 0) return 0;                                                                                             \
+    const Intr<CT> K = {(CT)intr[0], (CT)intr[1], (CT)intr[2], (CT)intr[3], (CT)intr[4]};                             \
+    lm_reproj2_accum_kernel<CT><<<lm_grid(E, kLmThreads / 32), kLmThreads, 0, (cudaStream_t)stream>>>(                \
+        nodes, pts, pix, pseg, pa, pb, K, (CT*)nullptr, (CT*)nullptr, epos_i, epos_j, Mn, un, ws, robust, (CT)delta,  \
+        E);                                                                                                           \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_reproj2_loss_##SFX(const CT* nodes, const CT* pts, const CT* pix, const int* pseg,          \

@@ -316,91 +316,6 @@ __global__ void __launch_bounds__(kLmThreads) pcg_pgo_spmv_kernel(const T* __res
     for (int k = 0; k < 6; ++k) { atomicAdd(y + i * 6 + k, v[k]); atomicAdd(y + j * 6 + k, -v[k]); }
   }
 }
-// ---- pose graph by GATHER over a node-ordered copy of the per-edge blocks: every edge (i,j) appears at two positions
-// (one in i's list, one in j's); Mn holds M_e at both, un holds -u_e (i side) and +u_e (j side), nother the opposite
-// node.  No atomics anywhere, results independent of scheduling.
-constexpr int kLanesPerNode = 4;
-template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pgo_node_order_kernel(const T* __restrict__ M, const T* __restrict__ u,
-                                                                     const int* __restrict__ epos_i, const int* __restrict__ epos_j,
-                                                                     T* __restrict__ Mn, T* __restrict__ un, long long E) {
-  for (long long e = (long long)blockIdx.x * kLmThreads + threadIdx.x; e < E; e += (long long)gridDim.x * kLmThreads) {
-    const long long si = epos_i[e], sj = epos_j[e];
-#pragma unroll
-    for (int k = 0; k < 21; ++k) { const T m = M[e * 21 + k]; Mn[si * 21 + k] = m; Mn[sj * 21 + k] = m; }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { const T v = u[e * 6 + k]; un[si * 6 + k] = -v; un[sj * 6 + k] = v; }
-  }
-}
-// Hd[n] = sum of the node's M blocks (diagonal block of H), g[n] = sum of its signed u (J^T R)
-template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pgo_node_sums_kernel(const T* __restrict__ Mn, const T* __restrict__ un,
-                                                                    const int* __restrict__ nptr, T* __restrict__ Hd,
-                                                                    T* __restrict__ g, long long N) {
-  constexpr int L = kLanesPerNode, NPB = kLmThreads / L;
-  const int sub = threadIdx.x % L;
-  const long long groups = (N + NPB - 1) / NPB;
-  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const long long n = grp * NPB + threadIdx.x / L;
-    T a[27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) a[k] = T(0);
-    if (n < N)
-      for (int s = nptr[n] + sub; s < nptr[n + 1]; s += L) {
-#pragma unroll
-        for (int k = 0; k < 21; ++k) a[k] += Mn[(long long)s * 21 + k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) a[21 + k] += un[(long long)s * 6 + k];
-      }
-#pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1)
-#pragma unroll
-      for (int k = 0; k < 27; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
-    if (n < N && sub == 0) {
-#pragma unroll
-      for (int k = 0; k < 21; ++k) Hd[n * 21 + k] = a[k];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) g[n * 6 + k] = a[21 + k];
-    }
-  }
-}
-// q[n] = sum_{s in n} Mn[s] (x[n] - x[nother[s]]) + extra[n] * x[n]      ((H + clamp/damping) x, written, not accumulated)
-template <typename T>
-__global__ void __launch_bounds__(kLmThreads) pcg_pgo_spmv_gather_kernel(const T* __restrict__ Mn, const int* __restrict__ nother,
-                                                                          const int* __restrict__ nptr, const T* __restrict__ extra,
-                                                                          const T* __restrict__ x, T* __restrict__ q,
-                                                                          const double* cg, long long N) {
-  if (cg && cg[CG_DONE] != 0.0) return;
-  constexpr int L = kLanesPerNode, NPB = kLmThreads / L;
-  const int sub = threadIdx.x % L;
-  const long long groups = (N + NPB - 1) / NPB;
-  for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const long long n = grp * NPB + threadIdx.x / L;
-    T v[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, xn[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-    if (n < N) {
-      ld6(x, n, xn);
-      for (int s = nptr[n] + sub; s < nptr[n + 1]; s += L) {
-        const long long o = nother[s];
-        T d[6], w[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) d[k] = xn[k] - __ldg(x + o * 6 + k);
-        sym6_mv_packed(Mn + (long long)s * 21, d, w);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) v[k] += w[k];
-      }
-    }
-#pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1)
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-    if (n < N && sub == 0) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v[k] += extra[n * 6 + k] * xn[k];
-      st6(q, n, v);
-    }
-  }
-}
-
 // u[j] = alpha * Hp^-1_j (t0[j] + sum_{k in obs(j)} Jp_k^T Jc_k x[c_k])   — W^T x by GATHER over a point-ordered copy
 // of the per-observation data (Y4p, cidx_p; pptr = offsets per point), so there are no atomics, no zero-fill of
 // a (P,3) buffer, the result is deterministic, and the 3x3 point-block inverse is applied while the sum is in registers.
@@ -517,6 +432,27 @@ __global__ void __launch_bounds__(kLmThreads) pgo_predicted_edge_kernel(const T*
   reduce_sums<1>(acc, ws);
 }
 
+// used by pcg2.cu (node-ordered two-kernel iteration): x = 0, r = -b, z = M^-1 r (stored through the `p` slot), state reset
+template <typename T>
+void pcg_launch_init(const T* Minv, const T* b, T* x, T* r, T* z, T* q, double* cg, double* ws, double tol, double maxiter,
+                     long long n, cudaStream_t st) {
+  cg_init_kernel<T><<<lm_grid(n, kLmThreads), kLmThreads, 0, st>>>(Minv, b, (T)-1, (const T*)nullptr, 0, x, r, z, q, cg, ws, tol,
+                                                                  maxiter, n);
+}
+template <typename T>
+void pcg_launch_update(const T* Minv, const T* p, const T* q, T* x, T* r, T* z, T* xbest, double* cg, double* ws, int par,
+                       long long n, cudaStream_t st) {
+  cg_update_kernel<T><<<lm_grid(n, kLmThreads), kLmThreads, 0, st>>>(Minv, p, q, x, r, z, xbest, cg, ws, par, n);
+}
+template void pcg_launch_init<float>(const float*, const float*, float*, float*, float*, float*, double*, double*, double, double,
+                                     long long, cudaStream_t);
+template void pcg_launch_init<double>(const double*, const double*, double*, double*, double*, double*, double*, double*, double,
+                                      double, long long, cudaStream_t);
+template void pcg_launch_update<float>(const float*, const float*, const float*, float*, float*, float*, float*, double*, double*,
+                                       int, long long, cudaStream_t);
+template void pcg_launch_update<double>(const double*, const double*, const double*, double*, double*, double*, double*, double*,
+                                        double*, int, long long, cudaStream_t);
+
 }  // namespace b200pose
 
 using namespace b200pose;
@@ -577,10 +513,9 @@ struct PcgKey {                                   // every launch argument of a 
   int tag, dev;
 };
 
-// One chunk of PCG iterations for the pose graph.  GATHER = false: the operator walks the edges and scatter-adds
-// (A = per-edge M, ia/ib = ei/ej, E edges) — the faster variant on B200 (20.5 us per product at 3e5 edges, and no
-// node-ordered copy to build: 1.35 vs 1.44 ms per LM step).  GATHER = true: node-ordered blocks (A = Mn, ia = nother,
-// ib = nptr), no atomics, bit-reproducible; selected with B200POSE_DETERMINISTIC=1.
+// One chunk of PCG iterations for the pose graph on per-edge blocks (A = M, ia/ib = ei/ej, E edges): the operator walks the
+// edges and scatter-adds.  Single GPU uses pcg2.cu (node-ordered gathers) by default; this is the multi-GPU operator (every
+// rank holds a shard of the edges and the partial products are all-reduced on the device) and the A/B baseline.
 // Multi-GPU: edges / observations are sharded, the CG vectors are replicated.  Every operator product is a partial sum that
 // is all-reduced ON THE DEVICE (comm.cu: scatter to slice owners, reduce in rank order, broadcast) between the operator
 // and the vector kernels of the iteration — no host in the loop, no collective library call.  The block-diagonal part
@@ -639,8 +574,7 @@ static int pgo_pcg_run(const CT* A, const int* ia, const int* ib, long long E, c
       LM_LAUNCH(cg_init_kernel<CT>, n, stream, Minv, g, (CT)-1, extra, 1, x, r, p, q, cg, ws, tol, (double)maxiter, n);
     for (long long it = first_iter; it < first_iter + iters; ++it) {
       const int par = (int)(it & 1);
-      if (GATHER) LM_LAUNCH(pcg_pgo_spmv_gather_kernel<CT>, n * kLanesPerNode, stream, A, ia, ib, extra, p, q, cg, n);
-      else if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, A, ia, ib, p, q, cg, E);
+      if (E > 0) LM_LAUNCH(pcg_pgo_spmv_kernel<CT>, E, stream, A, ia, ib, p, q, cg, E);
       if (n <= kVecSmallRows) {
         launch_cg_vec_small<CT>(Minv, extra, 1, x, r, z, p, q, xbest, cg, par, n, stream);
         continue;
@@ -730,18 +664,6 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
     LM_LAUNCH(pt3_apply_kernel<CT>, n, stream, A6, t, (CT)alpha, out, n);                                             \
     return (int)cudaGetLastError();                                                                                   \
   }                                                                                                                   \
-  B200_EXPORT int b200_lm_pgo_node_order_##SFX(const CT* M, const CT* u, const int* epos_i, const int* epos_j,        \
-                                               CT* Mn, CT* un, long long E, void* stream) {                           \
-    if (E <= 0) return 0;                                                                                             \
-    LM_LAUNCH(pgo_node_order_kernel<CT>, E, stream, M, u, epos_i, epos_j, Mn, un, E);                                 \
-    return (int)cudaGetLastError();                                                                                   \
-  }                                                                                                                   \
-  B200_EXPORT int b200_lm_pgo_node_sums_##SFX(const CT* Mn, const CT* un, const int* nptr, CT* Hd, CT* g,             \
-                                              long long N, void* stream) {                                            \
-    if (N <= 0) return 0;                                                                                             \
-    LM_LAUNCH(pgo_node_sums_kernel<CT>, N * kLanesPerNode, stream, Mn, un, nptr, Hd, g, N);                           \
-    return (int)cudaGetLastError();                                                                                   \
-  }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_pcg_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* Minv,       \
                                         const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q, CT* xbest,   \
                                         double* cg, double* ws, double tol, long long maxiter, long long first_iter,  \
@@ -756,14 +678,6 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
     if (n <= 0) return 0;                                                                                             \
     LM_LAUNCH(cg_finish_kernel<CT>, n * 6, stream, x, xbest, cg, n * 6);                                              \
     return (int)cudaGetLastError();                                                                                   \
-  }                                                                                                                   \
-  B200_EXPORT int b200_lm_pgo_pcg_gather_##SFX(const CT* Mn, const int* nother, const int* nptr, const CT* Minv,      \
-                                               const CT* extra, const CT* g, CT* x, CT* r, CT* z, CT* p, CT* q,       \
-                                               CT* xbest, double* cg, double* ws, double tol, long long maxiter,      \
-                                               long long first_iter, long long iters, long long n, void* stream) {    \
-    return pgo_pcg_run<CT, true>(Mn, nother, nptr, 0, Minv, extra, g, x, r, z, p, q, xbest, cg, ws, tol, maxiter,     \
-                                 first_iter, iters, n, (cudaStream_t)stream,                                          \
-                                 make_pcg_comm(nullptr, 0, 1, 0, 0, 0, nullptr));                                     \
   }                                                                                                                   \
   B200_EXPORT int b200_lm_pgo_predicted_##SFX(const CT* M, const int* ei, const int* ej, long long E, const CT* D,    \
                                               const CT* g, double* ws, long long n, void* stream) {                   \

@@ -323,20 +323,50 @@ def _run_chunks(enqueue, cg, maxiter, hint=0):
             return int(st[6])
 
 
-def pgo_node_order(M, u, epos_i, epos_j, nptr):
-    """Node-ordered copies (Mn, un) of the per-edge blocks and, from them, the diagonal blocks Hd and J^T R (gathers)."""
-    E, N = M.shape[0], nptr.shape[0] - 1
-    Mn, un = M.new_empty(2 * E, 21), M.new_empty(2 * E, 6)
-    Hd, g = M.new_empty(N, 21), M.new_empty(N, 6)
-    _launch("b200_lm_pgo_node_order", M, [_p(M), _p(u), _p(epos_i), _p(epos_j), _p(Mn), _p(un)], E)
-    _launch("b200_lm_pgo_node_sums", M, [_p(Mn), _p(un), _p(nptr), _p(Hd), _p(g)], N)
-    return Mn, Hd, g
+def pgo_linearize_nodes(kind, prob, nodes, robust, delta):
+    """Blocks of the current linearisation directly in node order (csrc/lm.cu store_edge_blocks) and, by gather, the
+    diagonal blocks Hd and J^T R.  kind: "pgo" (Log(Z^-1 A^-1 B) edges) or "reproj2" (pose pairs)."""
+    E, N = prob.ei.shape[0], prob.nptr.shape[0] - 1
+    E2 = 2 * E
+    dt, dev = nodes.dtype, nodes.device
+    ws = _workspace(dev)
+    Mn, un = torch.empty(E2, 24, dtype=dt, device=dev), torch.empty(E2, 6, dtype=dt, device=dev)
+    if kind == "pgo":
+        _launch("b200_lm_pgo_linearize_n", nodes, [_p(nodes), _p(prob.Z), _p(prob.ei), _p(prob.ej), _p(prob.epos_i), _p(prob.epos_j),
+                                                   _p(Mn), _p(un), _p(ws), int(robust), float(delta)], E)
+    else:
+        k = (ctypes.c_double * 5)(*prob.intr)
+        _launch("b200_lm_reproj2_accum_n", nodes, [_p(nodes), _p(prob.pts), _p(prob.pix), _p(prob.pseg), _p(prob.pa), _p(prob.pb),
+                                                   ctypes.addressof(k), _p(prob.epos_i), _p(prob.epos_j), _p(Mn), _p(un), _p(ws),
+                                                   int(robust), float(delta)], E)
+    cur = ws[:1].clone()
+    Hd, g = torch.empty(N, 21, dtype=dt, device=dev), torch.empty(N, 6, dtype=dt, device=dev)
+    _launch("b200_lm_pgo2_node_sums", nodes, [_p(Mn), _p(un), _p(prob.nptr), _p(Hd), _p(g)], N)
+    return Mn, Hd, g, cur
+
+
+def pgo_solve_nodes(Mn, nother, nptr, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0):
+    """(H + clamp/damping) x = -g on node-ordered blocks (csrc/pcg2.cu): two launches per iteration, no atomics.
+    Returns x (n,6), iterations, predicted (1,) fp64 on device."""
+    dev, dt, n = Mn.device, Mn.dtype, Hd.shape[0]
+    ws, cg = _workspace(dev), _cg(dev)
+    extra = torch.empty(n, 6, dtype=dt, device=dev)
+    Minv = torch.empty(n, 21, dtype=dt, device=dev)
+    _launch("b200_lm_blk6_damp_inv", Mn, [_p(Hd), float(scale), float(dmin), float(dmax), _p(None), _p(extra), _p(Minv)], n)
+    x, r, z, p0, p1, q, xbest = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(7))
+    maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
+    iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo2_pcg", Mn, [
+        _p(Mn), _p(nother), _p(nptr), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p0), _p(p1), _p(q), _p(xbest),
+        _p(cg), _p(ws), float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+    _launch("b200_lm_cg_finish", Mn, [_p(x), _p(xbest), _p(cg)], n)
+    _launch("b200_lm_pgo2_predicted", Mn, [_p(Mn), _p(nother), _p(nptr), _p(x), _p(g), _p(ws)], n)
+    return x, iters, ws[:1].clone()
 
 
 _NOCOMM = [None, 0, 1, 0, 0, 0, None]
 
 
-def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None, node=None, comm=None):
+def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweighted=None, comm=None):
     """(H + clamp/damping) x = -g by device PCG.  Returns x (n,6), iterations, predicted (1,) fp64 on device.
     `unweighted` = (M0, u0): per-edge blocks without the information matrices, for the predicted reduction.
     `node` = (Mn, nother, nptr): node-ordered blocks -> the H product is a gather (deterministic) instead of a scatter."""
@@ -347,18 +377,13 @@ def pgo_solve(M, ei, ej, Hd, g, scale, dmin, dmax, tol, maxiter, hint=0, unweigh
     _launch("b200_lm_blk6_damp_inv", M, [_p(Hd), float(scale), float(dmin), float(dmax), _p(None), _p(extra), _p(Minv)], n)
     x, r, z, p, q, xbest = (torch.empty(n, 6, dtype=dt, device=dev) for _ in range(6))
     maxiter = int(maxiter) if maxiter is not None else 10 * 6 * n
-    if node is None:
-        def chunk(it0, k):
-            _launch("b200_lm_pgo_pcg", M, [
-                _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest), _p(cg),
-                _p(ws), float(tol), maxiter, it0, k, *(comm.pcg_args() if comm is not None else _NOCOMM)], n)
-            if comm is not None:
-                comm.consumed(k)           # one device all-reduce of q per iteration
-        iters = _run_chunks(chunk, cg, maxiter, hint)
-    else:
-        iters = _run_chunks(lambda it0, k: _launch("b200_lm_pgo_pcg_gather", M, [
-            _p(node[0]), _p(node[1]), _p(node[2]), _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest),
-            _p(cg), _p(ws), float(tol), maxiter, it0, k], n), cg, maxiter, hint)
+    def chunk(it0, k):
+        _launch("b200_lm_pgo_pcg", M, [
+            _p(M), _p(ei), _p(ej), E, _p(Minv), _p(extra), _p(g), _p(x), _p(r), _p(z), _p(p), _p(q), _p(xbest), _p(cg),
+            _p(ws), float(tol), maxiter, it0, k, *(comm.pcg_args() if comm is not None else _NOCOMM)], n)
+        if comm is not None:
+            comm.consumed(k)           # one device all-reduce of q per iteration
+    iters = _run_chunks(chunk, cg, maxiter, hint)
     _launch("b200_lm_cg_finish", M, [_p(x), _p(xbest), _p(cg)], n)     # best iterate unless the solve converged
     if unweighted is None:
         _launch("b200_lm_pgo_predicted", M, [_p(M), _p(ei), _p(ej), E, _p(x), _p(g), _p(ws)], n)

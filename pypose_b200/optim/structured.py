@@ -294,10 +294,11 @@ class PGOProblem(_Problem):
         self.Z = None if Z is None else Z.tensor().to(self.dtype).reshape(-1, 7).contiguous()
         # information matrices (examples/module/pgo/pgo.py:75 `weight=infos`): (E,6,6) or one (6,6) for all edges
         self.W = None if weight is None else weight.to(self.dtype).reshape(-1, 36).contiguous()
-        # B200POSE_DETERMINISTIC=1: node adjacency (single-rank device route) — every edge sits once in each endpoint's
-        # list, so H products and the block sums are gathers over node-ordered copies of the per-edge blocks: no
-        # atomics, bit-reproducible, ~7 % slower per LM step than the scatter kernels
-        self.deterministic = os.environ.get("B200POSE_DETERMINISTIC", "0") == "1"
+        # node adjacency (single-GPU device route, csrc/pcg2.cu): every edge owns one slot in each endpoint's list, the
+        # linearisation writes its blocks there and block sums / H products are gathers — no atomics, bit-reproducible.
+        # B200POSE_PGO_SCATTER=1 keeps the round-1 scatter kernels (per-edge blocks + atomics) for A/B measurements.
+        self.node_order = os.environ.get("B200POSE_PGO_SCATTER", "0") != "1"
+        self.kind = "pgo"
         E = self.ei.shape[0]
         keys = torch.cat([self.ei, self.ej]).long()
         order = torch.sort(keys, stable=True)[1]
@@ -336,10 +337,10 @@ class PGOProblem(_Problem):
 
     def linearize(self):
         nodes = self._nodes()
+        if nodes.is_cuda and self.group is None and self.node_order and self.W is None:
+            Mn, Hd, g, cur = _fused.pgo_linearize_nodes(self.kind, self, nodes, *self.robust)
+            return (Mn,), Hd, g, cur, None
         M, u, cur, unw = self._blocks(nodes)
-        if M.is_cuda and self.group is None and self.deterministic:      # gathers over node-ordered copies, no atomics
-            Mn, Hd, g = _fused.pgo_node_order(M, u, self.epos_i, self.epos_j, self.nptr)
-            return (M, Mn), Hd, g, cur, unw
         comm = self._peer(27 * nodes.shape[0]) if (M.is_cuda and self.group is not None) else None
         if comm is not None:      # multi-GPU device route: [Hd | g] of this rank's edges, one device all-reduce
             n = nodes.shape[0]
@@ -364,12 +365,15 @@ class PGOProblem(_Problem):
     def trial(self, lin, scale, dmin, dmax):
         M, Hd, g, cur, unw = lin
         comm = getattr(self, '_comm', None)
-        if isinstance(M, tuple) or (M.is_cuda and (self.group is None or comm is not None)):   # device-resident PCG
-            node = (M[1], self.nother, self.nptr) if isinstance(M, tuple) else None
-            M = M[0] if isinstance(M, tuple) else M
+        if isinstance(M, tuple):                                          # node-ordered blocks: csrc/pcg2.cu
+            D, self.cg_iters, predicted = _fused.pgo_solve_nodes(M[0], self.nother, self.nptr, Hd, g, scale, dmin, dmax,
+                                                                 self.tol, self.maxiter,
+                                                                 hint=self.cg_iters + 1 if self.cg_iters else 0)
+            return self._finish_trial(D, predicted, cur)
+        if M.is_cuda and (self.group is None or comm is not None):       # device-resident PCG on per-edge blocks
             D, self.cg_iters, predicted = _fused.pgo_solve(M, self.ei, self.ej, Hd, g, scale, dmin, dmax, self.tol,
                                                            self.maxiter, hint=self.cg_iters + 1 if self.cg_iters else 0,
-                                                           unweighted=unw, node=node, comm=comm)
+                                                           unweighted=unw, comm=comm)
             if comm is not None:
                 predicted = _allreduce(predicted, self.group)
             return self._finish_trial(D, predicted, cur)
@@ -426,6 +430,7 @@ class Reproj2Problem(PGOProblem):
         self.pts = points.reshape(-1, 3)[order].to(self.dtype).contiguous()
         self.pix = pixels.reshape(-1, 2)[order].to(self.dtype).contiguous()
         self.intr = tuple(float(v) for v in intr)
+        self.kind = "reproj2"
 
     def _loss_at(self, nodes):
         return _fused.call("lm_reproj2_loss", nodes, self.pts, self.pix, self.pseg, self.pa, self.pb, self.intr, *self.robust)
