@@ -232,6 +232,14 @@ def run(args, rank, world, dev, peak):
     del net5, opt5
     torch.cuda.empty_cache()
 
+    # ---- one long SE3 product scan (B = 1, L = 1e6, fp32): the time axis is split over all SMs (decoupled look-back)
+    xs = pp.randn_SE3(1, 1_000_000, sigma=0.01, device=dev)
+    ms, k = _time_steps(lambda: xs.cumprod(dim=1, left=False), lambda: None, warmup=2, min_steps=5)
+    ms = _max(ms, world, dev)
+    out["cumprod_1e6"] = {"melems_per_s": round(world * 1e6 / (ms * 1e-3) / 1e6, 1), "ms": round(ms, 4), "timed_steps": k,
+                          "scaling": "weak", "roofline": _roof(56 * 1_000_000, ms, peak)}
+    del xs
+
     # ---- BASELINE configs[3]: IMU preintegration, 1e3 trajectories x 1e4 samples fp64 per GPU (weak scaling)
     B, F = 1000, 10_000
     dt = torch.full((B, F, 1), 0.005, dtype=torch.float64, device=dev)

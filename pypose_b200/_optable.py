@@ -395,6 +395,14 @@ SCAN_OPS = [
      "lietensor.py:171-193")
     for g, (_, d, _) in GROUPS.items()
 ] + [
+    (f"b200_{g}_cumprod_lb",
+     [("const REAL*", "in", f"(B,L,{d})"), ("REAL*", "out", f"(B,L,{d})"), ("long long", "B", "sequences"),
+      ("long long", "L", "scan length"), ("int", "left", "1: y_i = x_i y_{i-1}; 0: y_i = y_{i-1} x_i"),
+      ("void*", "ws", "b200_scan_workspace_bytes(B, L, sizeof(REAL)) bytes, zero-filled before every call")],
+     "the same scan with the time axis split over CTAs (single pass, decoupled look-back): for few long sequences; "
+     "pypose/basics/ops.py:29-58, lietensor.py:171-193")
+    for g, (_, d, _) in GROUPS.items()
+] + [
     ("b200_imu_integrate",
      [("const REAL*", "dt", "(B,F,1)"), ("const REAL*", "gyro", "(B,F,3)"), ("const REAL*", "acc", "(B,F,3)"),
       ("const REAL*", "rot", "(B,F,4) known rotations or NULL"), ("const REAL*", "init_rot", "(B,4) / (1,4) or NULL"),

@@ -106,12 +106,137 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_kernel(const T* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same scan with the TIME AXIS split over CTAs: single pass, decoupled look-back (Merrill & Garland) for a
+// non-commutative operator.  A tile (kScanThreads x CH rows) scans locally, publishes its aggregate (flag 1), looks back
+// over its predecessors of the same sequence — one warp inspects 32 of them at a time, takes everything after the nearest
+// published inclusive prefix (flag 2) and folds it with an order-preserving shuffle scan — then publishes its own
+// inclusive prefix.  Tile ids come from an atomic counter, so every predecessor of a running tile has started.
+// Used when there are too few sequences to fill the machine ((B = 1, L = 1e6) ran on ONE SM with cumprod_kernel).
+// Workspace (caller-owned, zeroed): [counter | flags (tiles) | aggregates (tiles x 8) | prefixes (tiles x 8)].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <typename T> __device__ __forceinline__ Elem<T> elem_shfl(const Elem<T>& e, int l) {
+  Elem<T> r;
+  r.t = mk(shfl_idx(e.t.x, l), shfl_idx(e.t.y, l), shfl_idx(e.t.z, l));
+  r.q.v = mk(shfl_idx(e.q.v.x, l), shfl_idx(e.q.v.y, l), shfl_idx(e.q.v.z, l));
+  r.q.w = shfl_idx(e.q.w, l);
+  r.s = shfl_idx(e.s, l);
+  return r;
+}
+
+template <class G, typename T, bool LEFT, int CH>
+__global__ void __launch_bounds__(kScanThreads) cumprod_lookback_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                         long long L, int nt, unsigned* counter,
+                                                                         int* flags, T* agg, T* pre) {
+  __shared__ T sh[(kScanThreads / 32) * 8];
+  __shared__ T excl_sh[8];
+  __shared__ unsigned tile_sh;
+  if (threadIdx.x == 0) tile_sh = atomicAdd(counter, 1u);
+  __syncthreads();
+  const long long gid = tile_sh;
+  const long long b = gid / nt;
+  const int t = (int)(gid - b * nt);
+  const T* src = in + b * L * G::D;
+  T* dst = out + b * L * G::D;
+  constexpr long long TILE = (long long)kScanThreads * CH;
+  const long long first = (long long)t * TILE + (long long)threadIdx.x * CH;
+  Elem<T> loc[CH];
+  Elem<T> run = elem_identity<T>();
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (first + c < L) {
+      T row[G::D];
+#pragma unroll
+      for (int k = 0; k < G::D; ++k) row[k] = src[(first + c) * G::D + k];
+      run = combine<G, T, LEFT>(run, load_elem<G, T>(row));
+    }
+    loc[c] = run;
+  }
+  Elem<T> total;
+  const Elem<T> pre_thread = block_exclusive<G, T, LEFT>(run, total, sh);
+  int* fl = flags + b * nt;
+  if (threadIdx.x == 0) {                              // publish: tile 0 knows its inclusive prefix already
+    store_elem<Sim3g, T>((t == 0 ? pre : agg) + gid * 8, total);
+    __threadfence();
+    st_release_gpu(fl + t, t == 0 ? 2 : 1);
+  }
+  Elem<T> excl = elem_identity<T>();
+  if (t > 0) {
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      Elem<T> acc = elem_identity<T>();
+      for (int j = t - 1;; j -= 32) {                  // window: tiles j-31 .. j, lane 31 <-> tile j (lane order = time order)
+        const int idx = j - 31 + lane;
+        int f = 2;                                     // before the sequence start: an identity prefix
+        Elem<T> v = elem_identity<T>();
+        if (idx >= 0) {
+          do { f = ld_acquire_gpu(fl + idx); } while (f == 0);
+          v = load_elem<Sim3g, T>((f == 2 ? pre : agg) + (b * nt + idx) * 8);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, f == 2);
+        const int hi = 31 - __clz(pm);                 // nearest published prefix in the window (-1: none)
+        if (lane < hi) v = elem_identity<T>();
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const Elem<T> up = elem_shfl_up(v, o);
+          if (lane >= o) v = combine<G, T, LEFT>(up, v);
+        }
+        acc = combine<G, T, LEFT>(elem_shfl(v, 31), acc);
+        if (pm) break;
+      }
+      if (lane == 0) {
+        store_elem<Sim3g, T>(excl_sh, acc);
+        store_elem<Sim3g, T>(pre + gid * 8, combine<G, T, LEFT>(acc, total));
+        __threadfence();
+        st_release_gpu(fl + t, 2);
+      }
+    }
+    __syncthreads();
+    excl = load_elem<Sim3g, T>(excl_sh);
+  }
+  const Elem<T> pfx = combine<G, T, LEFT>(excl, pre_thread);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (first + c < L) {
+      T row[G::D];
+      store_elem<G, T>(row, combine<G, T, LEFT>(pfx, loc[c]));
+#pragma unroll
+      for (int k = 0; k < G::D; ++k) dst[(first + c) * G::D + k] = row[k];
+    }
+  }
+}
+
+template <typename T> constexpr int scan_ch() { return sizeof(T) == 8 ? 4 : 8; }
+static inline long long scan_tiles(long long L, int elem) { return (L + (long long)kScanThreads * (elem == 8 ? 4 : 8) - 1) / ((long long)kScanThreads * (elem == 8 ? 4 : 8)); }
+
 template <class G, typename T>
 int launch_cumprod(const T* in, T* out, long long B, long long L, int left, cudaStream_t s) {
   if (B <= 0 || L <= 0) return 0;
-  constexpr int CH = sizeof(T) == 8 ? 4 : 8;
+  constexpr int CH = scan_ch<T>();
   if (left) cumprod_kernel<G, T, true, CH><<<(unsigned)B, kScanThreads, 0, s>>>(in, out, L);
   else cumprod_kernel<G, T, false, CH><<<(unsigned)B, kScanThreads, 0, s>>>(in, out, L);
+  return (int)cudaGetLastError();
+}
+// time-split variant; ws: b200_scan_workspace_bytes(B, L, sizeof(T)) bytes, zero-filled by the caller before every call
+template <class G, typename T>
+int launch_cumprod_lb(const T* in, T* out, long long B, long long L, int left, void* ws, cudaStream_t s) {
+  if (B <= 0 || L <= 0) return 0;
+  constexpr int CH = scan_ch<T>();
+  const long long nt = scan_tiles(L, (int)sizeof(T)), tiles = B * nt;
+  unsigned* counter = reinterpret_cast<unsigned*>(ws);
+  int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + 16);
+  T* agg = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + 16 + ((tiles * 4 + 15) / 16) * 16);
+  T* pre = agg + tiles * 8;
+  if (left) cumprod_lookback_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, counter, flags, agg, pre);
+  else cumprod_lookback_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, counter, flags, agg, pre);
   return (int)cudaGetLastError();
 }
 
@@ -421,6 +546,12 @@ __global__ void __launch_bounds__(96) imu_cov_finish_kernel(const T* S, const T*
 using namespace b200pose;
 
 #define SCAN_ABI(GRP, G)                                                                                               \
+  B200_EXPORT int b200_##GRP##_cumprod_lb_f32(const float* in, float* out, long long B, long long L, int left, void* ws, void* s) { \
+    return launch_cumprod_lb<G, float>(in, out, B, L, left, ws, (cudaStream_t)s);                                      \
+  }                                                                                                                    \
+  B200_EXPORT int b200_##GRP##_cumprod_lb_f64(const double* in, double* out, long long B, long long L, int left, void* ws, void* s) { \
+    return launch_cumprod_lb<G, double>(in, out, B, L, left, ws, (cudaStream_t)s);                                     \
+  }                                                                                                                    \
   B200_EXPORT int b200_##GRP##_cumprod_f32(const float* in, float* out, long long B, long long L, int left, void* s) { \
     return launch_cumprod<G, float>(in, out, B, L, left, (cudaStream_t)s);                                             \
   }                                                                                                                    \
@@ -484,3 +615,9 @@ IMU_ABI(f64, double, 2, 1)
   }
 IMU_COV_ABI(f32, float)
 IMU_COV_ABI(f64, double)
+
+// bytes of the (zero-filled) workspace of b200_<G>_cumprod_lb_<T>
+B200_EXPORT long long b200_scan_workspace_bytes(long long B, long long L, long long elem_size) {
+  const long long tiles = B * b200pose::scan_tiles(L, (int)elem_size);
+  return 16 + ((tiles * 4 + 15) / 16) * 16 + 2 * tiles * 8 * elem_size;
+}

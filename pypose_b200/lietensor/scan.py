@@ -26,6 +26,16 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+_sm_count = {}
+
+
+def _sms(device):
+    n = _sm_count.get(device.index)
+    if n is None:
+        n = _sm_count[device.index] = torch.cuda.get_device_properties(device).multi_processor_count
+    return n
+
+
 @torch.library.impl(f"{NS}::cumprod", "CUDA")
 def _cumprod_cuda(x, group, left):
     """x: (B, L, D) contiguous."""
@@ -34,9 +44,18 @@ def _cumprod_cuda(x, group, left):
     B, L, _ = x.shape
     if B * L == 0:
         return out
-    sym = f"b200_{group}_cumprod_{_C.suffix(x.dtype)}"
     with torch.cuda.device(x.device):
-        _C.check(_C.fn(sym)(_p(x), _p(out), B, L, int(left), _C.stream_ptr(x.device)), sym)
+        tile = 128 * (8 if x.dtype == torch.float32 else 4)
+        if B < 2 * _sms(x.device) and L >= 4 * tile:
+            # few long sequences: split the time axis over CTAs (single pass, decoupled look-back)
+            q = _C.lib().b200_scan_workspace_bytes
+            q.restype, q.argtypes = ctypes.c_longlong, [ctypes.c_longlong] * 3
+            ws = torch.zeros(int(q(B, L, x.element_size())), dtype=torch.uint8, device=x.device)
+            sym = f"b200_{group}_cumprod_lb_{_C.suffix(x.dtype)}"
+            _C.check(_C.fn(sym)(_p(x), _p(out), B, L, int(left), _p(ws), _C.stream_ptr(x.device)), sym)
+        else:
+            sym = f"b200_{group}_cumprod_{_C.suffix(x.dtype)}"
+            _C.check(_C.fn(sym)(_p(x), _p(out), B, L, int(left), _C.stream_ptr(x.device)), sym)
     return out
 
 
