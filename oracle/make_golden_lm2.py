@@ -94,6 +94,33 @@ def main():
     l, p, r = run(model, (pts, pix_readme, ia, ib), ref.optim.strategy.TrustRegion(radius=1e2), 8)
     out["hard/trustregion/loss"], out["hard/trustregion/poses"], out["hard/trustregion/reject"] = l, p, r
     print("hard", l, r)
+    # bundle adjustment with intrinsics (README.md:163-198 sparse example + an extra op: point2pixel with K) on the inputs of
+    # tests/golden/lm.npz "ba/*": not one of the fused families -> the generic block route (optim/blocks.py) must match
+    g1 = np.load(os.path.join(os.path.dirname(OUT), "lm.npz"))
+    T0, p0 = ref.SE3(torch.from_numpy(g1["ba/poses0"].copy())), torch.from_numpy(g1["ba/points0"].copy())
+    cb, pb = torch.from_numpy(g1["ba/cidx"]), torch.from_numpy(g1["ba/pidx"])
+    Kb = torch.tensor([[-1.2, 0.01, 0.05], [0.0, -0.9, -0.02], [0.0, 0.0, 1.0]], dtype=DT)
+    pixb = torch.from_numpy(g1["ba/pix"].copy()) @ Kb[:2, :2].mT * 1.0 + Kb[:2, 2]
+
+    class BAK(nn.Module):
+        def __init__(self, poses, points):
+            super().__init__()
+            self.poses = ref.Parameter(poses)
+            self.points_3d = nn.Parameter(points)
+
+        def forward(self, observations, camera_indices, point_indices):
+            y = self.poses[camera_indices].Act(self.points_3d[point_indices])
+            return ref.point2pixel(y, Kb) - observations
+
+    model = BAK(T0.clone(), p0.clone())
+    opt = ref.optim.LM(model, strategy=ref.optim.strategy.TrustRegion())
+    l, P, Q = [], [], []
+    for _ in range(5):
+        l.append(float(opt.step((pixb, cb, pb))))
+        P.append(model.poses.detach().clone().numpy()); Q.append(model.points_3d.detach().clone().numpy())
+    out["bak/K"], out["bak/pix"] = Kb.numpy(), pixb.numpy()
+    out["bak/trustregion/loss"], out["bak/trustregion/poses"], out["bak/trustregion/points"] = np.array(l), np.stack(P), np.stack(Q)
+    print("bak", l)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT)
 

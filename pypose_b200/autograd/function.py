@@ -11,6 +11,11 @@ from functools import wraps
 def parallel_for_sparse_jacobian(function):
     @wraps(function)
     def wrapped(*args, **kwargs):
+        # read by the generic block route (optim/blocks.py): while it records a forward pass, running a function carrying
+        # this marker declares the residual batch-separable, which replaces the numerical separability check
+        if wrapped.batch_separable:
+            from ..optim import blocks
+            blocks.declare_separable()
         return function(*args, **kwargs)
     wrapped.batch_separable = True
     return wrapped

@@ -454,6 +454,18 @@ class _TensorParameter(nn.Parameter):
     def tensor(self):
         return Tensor.as_subclass(self, Tensor)
 
+    def __getitem__(self, idx):
+        return _sjac_getitem(self, idx, super().__getitem__)
+
+
+def _sjac_getitem(param, idx, plain):
+    """Row gathers of an `sjac` parameter are recorded while the generic block route linearises (optim/blocks.py)."""
+    if getattr(param, 'sjac', False):
+        from ..optim import blocks
+        if blocks._REC is not None:
+            return blocks.gather(param, idx, plain)
+    return plain(idx)
+
 
 class Parameter(LieTensor, nn.Parameter):
     """nn.Parameter that is also a LieTensor (lt.py:1236-1337).
@@ -478,6 +490,9 @@ class Parameter(LieTensor, nn.Parameter):
             param = _TensorParameter(data, requires_grad) if sjac else nn.Parameter(data, requires_grad)
         param.sjac = bool(sjac)
         return param
+
+    def __getitem__(self, idx):
+        return _sjac_getitem(self, idx, super().__getitem__)
 
     def __deepcopy__(self, memo):
         if id(self) in memo:

@@ -224,8 +224,17 @@ class LevenbergMarquardt(_SecondOrder):
             return None
         if self._problem is not None and self._problem.matches(self.model.model, input, weight):
             return self._problem
-        self._problem = structured.recognize(self.model.model, input, self.param_groups[0]['params'], self.group,
+        params = self.param_groups[0]['params']
+        self._problem = structured.recognize(self.model.model, input, params, self.group,
                                              self._robust, self.solver, self.sparse, weight)
+        if self._problem is None and weight is None and (self.sparse or isinstance(self.solver, CG)):
+            # not one of the fused families: per-residual Jacobian blocks for any batch-separable model of `sjac`
+            # parameters (what the reference delegates to `bae`, optimizer.py:629-643)
+            from . import blocks
+            kernel = self.model.kernel[0] if self._robust[0] != 0 else None
+            self._problem = blocks.BlockProblem.build(self.model.model, input, [p for p in params if p.requires_grad],
+                                                      structured._input_key(input), self.group, kernel, self.solver,
+                                                      self.model)
         return self._problem
 
     def _device_step(self, prob):

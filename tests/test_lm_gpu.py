@@ -715,3 +715,36 @@ def test_lm_two_pose_reprojection_fp32_converges_to_1e5():
     ref = O.mul("SE3", O.inv("SE3", gt[ib[::per]]), gt[ia[::per]])
     err = np.abs(O.log("SE3", O.mul("SE3", O.inv("SE3", ref), est))).max()
     assert err <= 1e-5, err
+
+
+@pytest.mark.parametrize("declare", [True, False])
+def test_generic_block_route_matches_reference_dense_run_gpu(declare):
+    """The generic block route (sjac / psjac, optim/blocks.py) on CUDA: Jacobian blocks through the op-level backward
+    kernels, trajectory of the reference's dense LM (oracle/make_golden_lm2.py "bak"); then the same model at 1e6 residual
+    rows, which the dense route cannot hold (J would be 2e6 x 3.8e5)."""
+    from tests.test_lm import BAWithIntrinsics
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lm.npz"))
+    g2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "lm2.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    net = BAWithIntrinsics(pp.SE3(t(g["ba/poses0"])), t(g["ba/points0"]), t(g2["bak/K"]), declare).cuda()
+    opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(), solver=pp.optim.solver.PCG(tol=1e-12), sparse=True)
+    inp = (t(g2["bak/pix"]), t(g["ba/cidx"]), t(g["ba/pidx"]))
+    for k in range(5):
+        loss = opt.step(inp)
+        assert type(opt._problem).__name__ == "BlockProblem"
+        np.testing.assert_allclose(float(loss), g2["bak/trustregion/loss"][k], rtol=1e-5)
+        np.testing.assert_allclose(net.poses.detach().cpu().numpy(), g2["bak/trustregion/poses"][k], atol=1e-6)
+    if not declare:
+        return
+    rng = np.random.default_rng(9)
+    C, P = 1000, 125_000
+    gt, ptsw, T0, p0, pix, cidx, pidx = _ba_problem(rng, C, P, 8, pix_noise=0.0)
+    K = torch.tensor([[-1.2, 0.01, 0.05], [0.0, -0.9, -0.02], [0.0, 0.0, 1.0]], device="cuda")
+    ci_t, pi_t = torch.from_numpy(cidx).cuda(), torch.from_numpy(pidx).cuda()
+    pixk = pp.point2pixel(pp.SE3(cu(gt, torch.float32))[ci_t].Act(cu(ptsw, torch.float32)[pi_t]), K)     # exact pixels
+    big = BAWithIntrinsics(pp.SE3(cu(T0, torch.float32)), cu(p0, torch.float32), K, True).cuda()
+    opt = pp.optim.LM(big, solver=pp.optim.solver.PCG(tol=1e-3, maxiter=40), sparse=True)
+    inp = (pixk, ci_t, pi_t)
+    losses = [float(opt.step(inp)) for _ in range(4)]
+    assert type(opt._problem).__name__ == "BlockProblem" and len(cidx) == 1_000_000
+    assert losses[-1] < 1e-3 * losses[0], losses
