@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __
 #pragma unroll
     for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
     const Elem<T> Tc = load_se3(pr);
-    Sys6<T> s;
-    sys6_zero(s);
+    Acc6<T> ac;
+    ac.zero();
     T loss = T(0);
     const int b = seg[c], e = seg[c + 1];
     auto accumulate = [&](const V3<T>& p, T zx, T zy) {
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __
 #pragma unroll
         for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
       }
-      sys6_add_row(s, j0, rx);
-      sys6_add_row(s, j1, ry);
+      ac.add_row(j0, rx);
+      ac.add_row(j1, ry);
       loss += rho;
     };
     // two observations per lane per iteration, all ten loads issued before the math (memory-level parallelism:
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj_accum_kernel(const T* __
       const long long k0 = k;
       accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
     }
+    Sys6<T> s = ac.finish();
     // warp reduction of 21 + 6 + 1 values
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -573,8 +574,8 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj2_accum_kernel(const T* _
 #pragma unroll
     for (int k = 0; k < 7; ++k) { a7[k] = __ldg(nodes + ia * 7 + k); b7[k] = __ldg(nodes + ib * 7 + k); }
     const Elem<T> Ta = load_se3(a7), Tb = load_se3(b7);
-    Sys6<T> s;
-    sys6_zero(s);
+    Acc6<T> ac;
+    ac.zero();
     T loss = T(0);
     for (int k = pseg[e] + lane; k < pseg[e + 1]; k += 32) {
       const long long k0 = k;
@@ -592,10 +593,11 @@ __global__ void __launch_bounds__(kLmThreads) lm_reproj2_accum_kernel(const T* _
 #pragma unroll
         for (int q = 0; q < 6; ++q) { j0[q] *= sw; j1[q] *= sw; }
       }
-      sys6_add_row(s, j0, rx);
-      sys6_add_row(s, j1, ry);
+      ac.add_row(j0, rx);
+      ac.add_row(j1, ry);
       loss += rho;
     }
+    Sys6<T> s = ac.finish();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll

@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __
 #pragma unroll
     for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
     const Elem<T> Tc = load_se3(pr);
-    Sys6<T> s;
-    sys6_zero(s);
+    Acc6<T> ac;
+    ac.zero();
     T loss = T(0);
     const int b = seg[c], e = seg[c + 1];
     auto accumulate = [&](const V3<T>& p, T zx, T zy) {
@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __
 #pragma unroll
         for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
       }
-      sys6_add_row(s, j0, rx);
-      sys6_add_row(s, j1, ry);
+      ac.add_row(j0, rx);
+      ac.add_row(j1, ry);
       loss += rho;
     };
     int k = b + lane;
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __
       const long long k0 = k;
       accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
     }
+    Sys6<T> s = ac.finish();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
 #pragma unroll
     for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
     const Elem<T> Tc = load_se3(pr);
-    Sys6<T> s;
-    sys6_zero(s);
+    Acc6<T> ac;
+    ac.zero();
     T loss = T(0);
     const int b = seg[c], e = seg[c + 1];
     for (int k = b + lane; k < e; k += 32) {
@@ -296,10 +297,11 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
 #pragma unroll
         for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
       }
-      sys6_add_row(s, j0, rx);
-      sys6_add_row(s, j1, ry);
+      ac.add_row(j0, rx);
+      ac.add_row(j1, ry);
       loss += rho;
     }
+    Sys6<T> s = ac.finish();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
