@@ -232,7 +232,7 @@ def run(args, rank, world, dev, peak):
     del net5, opt5
     torch.cuda.empty_cache()
 
-    # ---- one long SE3 product scan (B = 1, L = 1e6, fp32): the time axis is split over all SMs (decoupled look-back)
+    # ---- one long SE3 product scan (B = 1, L = 1e6, fp32): the time axis is split over all SMs (tile reduce / prefix / apply)
     xs = pp.randn_SE3(1, 1_000_000, sigma=0.01, device=dev)
     ms, k = _time_steps(lambda: xs.cumprod(dim=1, left=False), lambda: None, warmup=2, min_steps=5)
     ms = _max(ms, world, dev)

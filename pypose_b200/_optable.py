@@ -340,7 +340,8 @@ LM_OPS += [
       ("const double*", "ctl", "HOST (14): last, cached, damping, pg down, reject count, reject limit, strategy kind "
                                "(0 Constant, 1 Adaptive, 2 TrustRegion), high, low, up, strategy down, factor, min, max"),
       ("int", "robust", "see b200_lm_reproj_accum"), ("double", "delta", ""), ("double", "scale", "prod(1+damping) so far"),
-      ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", "0: linearise + solve; 1: solve the stored blocks again")],
+      ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", "0: linearise + solve; 1: solve the stored blocks again"),
+      ("long long", "rows", "total number of observation rows (selects 8 or 32 lanes per camera)")],
      "one trial of LevenbergMarquardt.step incl. strategy.update and the accept test, optimizer.py:659-680, "
      "strategy.py:41-46,134-151,248-274, for the single-pose reprojection model"),
     ("b200_lm_reproj_step_peer",
@@ -398,8 +399,8 @@ SCAN_OPS = [
     (f"b200_{g}_cumprod_lb",
      [("const REAL*", "in", f"(B,L,{d})"), ("REAL*", "out", f"(B,L,{d})"), ("long long", "B", "sequences"),
       ("long long", "L", "scan length"), ("int", "left", "1: y_i = x_i y_{i-1}; 0: y_i = y_{i-1} x_i"),
-      ("void*", "ws", "b200_scan_workspace_bytes(B, L, sizeof(REAL)) bytes, zero-filled before every call")],
-     "the same scan with the time axis split over CTAs (single pass, decoupled look-back): for few long sequences; "
+      ("void*", "ws", "b200_scan_workspace_bytes(B, L, sizeof(REAL)) bytes of scratch")],
+     "the same scan with the time axis split over CTAs (tile products, scan of the tile products, apply): for few long sequences; "
      "pypose/basics/ops.py:29-58, lietensor.py:171-193")
     for g, (_, d, _) in GROUPS.items()
 ] + [

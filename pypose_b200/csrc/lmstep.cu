@@ -31,27 +31,32 @@ __device__ __forceinline__ void publish_state(const double* st, const HostOut& h
   o[ST_SIZE - 1] = h.seq;
 }
 
-// K1 (first trial of a step): one warp per camera — accumulate the camera's 6x6 system over its sorted observations,
-// keep it (H, g) for retries, solve the damped system and retract, all in registers.
-// sums (ws): [0] sum rho(|r|^2) (current loss), [1] predicted reduction, [2] failed pivots
-template <typename T>
+// K1 (first trial of a step): LPC lanes per camera (32 for long observation lists, 8 when a camera has ~100 rows: then a
+// warp works on four cameras at once and the 10^4 cameras of the north-star size fit in one wave) — accumulate the
+// camera's 6x6 system over its sorted observations, keep it (H, g) for retries, solve the damped system and retract, all in
+// registers.  sums (ws): [0] sum rho(|r|^2) (current loss), [1] predicted reduction, [2] failed pivots
+template <typename T, int LPC>
 __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
                                                                       const T* __restrict__ pix, const int* __restrict__ seg,
                                                                       T* __restrict__ H, T* __restrict__ g,
                                                                       T* __restrict__ Pt, double* ws, T scale, T dmin,
                                                                       T dmax, int rk, T rdelta, int ncam) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = kLmThreads / 32;
+  const int sub = threadIdx.x % LPC;
+  constexpr int cpb = kLmThreads / LPC;
+  const int rounds = (ncam + cpb - 1) / cpb;
   double acc[3] = {0.0, 0.0, 0.0};
-  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+  for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+    const int c = rd * cpb + threadIdx.x / LPC;
+    const bool valid = c < ncam;
+    const int cc = valid ? c : 0;
     T pr[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)cc * 7 + k];
     const Elem<T> Tc = load_se3(pr);
     Acc6<T> ac;
     ac.zero();
     T loss = T(0);
-    const int b = seg[c], e = seg[c + 1];
+    const int b = valid ? seg[cc] : 0, e = valid ? seg[cc + 1] : 0;
     auto accumulate = [&](const V3<T>& p, T zx, T zy) {
       T rx, ry;
       V3<T> y;
@@ -70,9 +75,9 @@ __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __
       ac.add_row(j1, ry);
       loss += rho;
     };
-    int k = b + lane;
-    for (; k + 32 < e; k += 64) {
-      const long long k0 = k, k1 = k + 32;
+    int k = b + sub;
+    for (; k + LPC < e; k += 2 * LPC) {          // two observations per lane in flight
+      const long long k0 = k, k1 = k + LPC;
       const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
       const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
       const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __
     }
     Sys6<T> s = ac.finish();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = LPC / 2; o > 0; o >>= 1) {
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
         s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
@@ -94,10 +99,10 @@ __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __
       }
       loss += __shfl_xor_sync(0xffffffffu, loss, o);
     }
-    // every lane holds the camera's totals (xor tree): the solve runs redundantly, lane 0 stores
+    // every lane of the group holds the camera's totals (xor tree): the solve runs redundantly, lane 0 stores
     T D[6], pred;
     const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
-    if (lane == 0) {
+    if (valid && sub == 0) {
       T o7[7];
       store_elem<SE3g, T>(o7, se3_retract(D, Tc));
 #pragma unroll
@@ -146,17 +151,20 @@ __global__ void __launch_bounds__(kLmThreads) reproj_resolve_kernel(const T* __r
   reduce_sums<3>(acc, ws);
 }
 
-// K2: trial loss (warp per camera, trial pose in registers); the last CTA decides.  ws1: this kernel's reduction slot,
-// ws0: K1's totals.
-template <typename T>
+// K2: trial loss (LPC lanes per camera, trial pose in registers); the last CTA decides.  ws1: this kernel's reduction
+// slot, ws0: K1's totals.
+template <typename T, int LPC>
 __global__ void __launch_bounds__(kLmThreads) reproj_loss_decide_kernel(const T* __restrict__ Pt, const T* __restrict__ pts,
                                                                          const T* __restrict__ pix, const int* __restrict__ seg,
                                                                          double* ws1, const double* ws0, double* st, LmCtl ctl,
                                                                          HostOut ho, int rk, T rdelta, int ncam) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = kLmThreads / 32;
+  const int sub = threadIdx.x % LPC;
+  constexpr int cpb = kLmThreads / LPC;
+  const int rounds = (ncam + cpb - 1) / cpb;
   double acc[1] = {0.0};
-  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+  for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+    const int c = rd * cpb + threadIdx.x / LPC;
+    if (c >= ncam) continue;
     T pr[7];
 #pragma unroll
     for (int q = 0; q < 7; ++q) pr[q] = Pt[(long long)c * 7 + q];
@@ -170,9 +178,9 @@ __global__ void __launch_bounds__(kLmThreads) reproj_loss_decide_kernel(const T*
       robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
       loss += rho;
     };
-    int k = b + lane;
-    for (; k + 32 < e; k += 64) {
-      const long long k0 = k, k1 = k + 32;
+    int k = b + sub;
+    for (; k + LPC < e; k += 2 * LPC) {
+      const long long k0 = k, k1 = k + LPC;
       const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
       const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
       const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
@@ -570,20 +578,33 @@ using namespace b200pose;
   B200_EXPORT int b200_lm_reproj_step_##SFX(CT* poses, const CT* pts, const CT* pix, const int* seg, CT* H, CT* g,    \
                                             CT* P_trial, double* ws0, double* ws1, double* st, double* host_out,      \
                                             long long seq, const double* ctl, int robust, double delta, double scale, \
-                                            double dmin, double dmax, int retry, long long ncam, void* stream) {      \
+                                            double dmin, double dmax, int retry, long long rows, long long ncam,      \
+                                            void* stream) {                                                           \
     if (ncam <= 0) return 0;                                                                                          \
     cudaStream_t s = (cudaStream_t)stream;                                                                            \
     const LmCtl k = make_ctl(ctl);                                                                                    \
     const HostOut ho = make_host_out(host_out, seq);                                                                  \
-    const unsigned wgrid = lm_grid(ncam, kLmThreads / 32);                                                            \
-    if (!retry)                                                                                                       \
-      reproj_linsolve_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, (CT)scale,    \
-                                                              (CT)dmin, (CT)dmax, robust, (CT)delta, (int)ncam);      \
-    else                                                                                                              \
+    const bool wide = rows >= 384 * ncam;                  /* lanes per camera: 32 for long lists, else 8 */          \
+    const unsigned wgrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);                                    \
+    if (!retry) {                                                                                                     \
+      if (wide)                                                                                                       \
+        reproj_linsolve_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0,         \
+                                                                    (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta, \
+                                                                    (int)ncam);                                       \
+      else                                                                                                            \
+        reproj_linsolve_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0,          \
+                                                                   (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta,  \
+                                                                   (int)ncam);                                        \
+    } else {                                                                                                          \
       reproj_resolve_kernel<CT><<<lm_grid(ncam, kLmThreads), kLmThreads, 0, s>>>(H, g, poses, P_trial, ws0,           \
                                                                                  (CT)scale, (CT)dmin, (CT)dmax, ncam);\
-    reproj_loss_decide_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(P_trial, pts, pix, seg, ws1, ws0, st, k, ho, robust,   \
-                                                               (CT)delta, (int)ncam);                                 \
+    }                                                                                                                 \
+    if (wide)                                                                                                         \
+      reproj_loss_decide_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(P_trial, pts, pix, seg, ws1, ws0, st, k, ho,     \
+                                                                     robust, (CT)delta, (int)ncam);                   \
+    else                                                                                                              \
+      reproj_loss_decide_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(P_trial, pts, pix, seg, ws1, ws0, st, k, ho,      \
+                                                                    robust, (CT)delta, (int)ncam);                    \
     lm_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(st, P_trial, poses, ncam * 7);          \
     return finish_step(host_out, seq, s);                                                                             \
   }                                                                                                                   \

@@ -107,41 +107,60 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_kernel(const T* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// The same scan with the TIME AXIS split over CTAs: single pass, decoupled look-back (Merrill & Garland) for a
-// non-commutative operator.  A tile (kScanThreads x CH rows) scans locally, publishes its aggregate (flag 1), looks back
-// over its predecessors of the same sequence — one warp inspects 32 of them at a time, takes everything after the nearest
-// published inclusive prefix (flag 2) and folds it with an order-preserving shuffle scan — then publishes its own
-// inclusive prefix.  Tile ids come from an atomic counter, so every predecessor of a running tile has started.
-// Used when there are too few sequences to fill the machine ((B = 1, L = 1e6) ran on ONE SM with cumprod_kernel).
-// Workspace (caller-owned, zeroed): [counter | flags (tiles) | aggregates (tiles x 8) | prefixes (tiles x 8)].
+// The same scan with the TIME AXIS split over CTAs, for few long sequences ((B = 1, L = 1e6) ran on ONE SM with
+// cumprod_kernel).  Reduce-then-scan in three launches, deterministic, no flags:
+//   1. every tile (kScanThreads x CH rows) multiplies its rows together              -> aggregate of the tile
+//   2. one CTA per sequence scans the tile aggregates (exclusive)                     -> prefix entering each tile
+//   3. every tile scans its rows again starting from that prefix and stores them
+// The rows are read twice, the second time mostly from L2 (a 28 MB sequence stays resident in the 126 MB L2).  A single
+// pass with decoupled look-back was measured first (r2e: 116 us at L = 1e6): with only ~1000 tiles, all resident at once,
+// every tile had to walk back over hundreds of unfinished predecessors — the look-back chain, not the bandwidth, set the
+// time.  Workspace (caller-owned, no initialisation needed): aggregates (tiles x 8) and prefixes (tiles x 8).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-template <typename T> __device__ __forceinline__ Elem<T> elem_shfl(const Elem<T>& e, int l) {
-  Elem<T> r;
-  r.t = mk(shfl_idx(e.t.x, l), shfl_idx(e.t.y, l), shfl_idx(e.t.z, l));
-  r.q.v = mk(shfl_idx(e.q.v.x, l), shfl_idx(e.q.v.y, l), shfl_idx(e.q.v.z, l));
-  r.q.w = shfl_idx(e.q.w, l);
-  r.s = shfl_idx(e.s, l);
-  return r;
-}
-
 template <class G, typename T, bool LEFT, int CH>
-__global__ void __launch_bounds__(kScanThreads) cumprod_lookback_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                                         long long L, int nt, unsigned* counter,
-                                                                         int* flags, T* agg, T* pre) {
+__global__ void __launch_bounds__(kScanThreads) cumprod_tile_reduce_kernel(const T* __restrict__ in, long long L, int nt,
+                                                                            T* __restrict__ agg) {
   __shared__ T sh[(kScanThreads / 32) * 8];
-  __shared__ T excl_sh[8];
-  __shared__ unsigned tile_sh;
-  if (threadIdx.x == 0) tile_sh = atomicAdd(counter, 1u);
-  __syncthreads();
-  const long long gid = tile_sh;
+  const long long gid = blockIdx.x;
+  const long long b = gid / nt;
+  const int t = (int)(gid - b * nt);
+  const T* src = in + b * L * G::D;
+  constexpr long long TILE = (long long)kScanThreads * CH;
+  const long long first = (long long)t * TILE + (long long)threadIdx.x * CH;
+  Elem<T> run = elem_identity<T>();
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (first + c < L) {
+      T row[G::D];
+#pragma unroll
+      for (int k = 0; k < G::D; ++k) row[k] = src[(first + c) * G::D + k];
+      run = combine<G, T, LEFT>(run, load_elem<G, T>(row));
+    }
+  }
+  Elem<T> total;
+  block_exclusive<G, T, LEFT>(run, total, sh);
+  if (threadIdx.x == 0) store_elem<Sim3g, T>(agg + gid * 8, total);
+}
+// exclusive scan of the nt tile aggregates of one sequence (one CTA per sequence, carry across rounds)
+template <class G, typename T, bool LEFT>
+__global__ void __launch_bounds__(kScanThreads) cumprod_tile_prefix_kernel(const T* __restrict__ agg, T* __restrict__ pre, int nt) {
+  __shared__ T sh[(kScanThreads / 32) * 8];
+  const long long b = blockIdx.x;
+  Elem<T> carry = elem_identity<T>();
+  for (int base = 0; base < nt; base += kScanThreads) {
+    const int t = base + threadIdx.x;
+    const Elem<T> mine = t < nt ? load_elem<Sim3g, T>(agg + (b * nt + t) * 8) : elem_identity<T>();
+    Elem<T> total;
+    const Elem<T> excl = block_exclusive<G, T, LEFT>(mine, total, sh);
+    if (t < nt) store_elem<Sim3g, T>(pre + (b * nt + t) * 8, combine<G, T, LEFT>(carry, excl));
+    carry = combine<G, T, LEFT>(carry, total);
+  }
+}
+template <class G, typename T, bool LEFT, int CH>
+__global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                           long long L, int nt, const T* __restrict__ pre) {
+  __shared__ T sh[(kScanThreads / 32) * 8];
+  const long long gid = blockIdx.x;
   const long long b = gid / nt;
   const int t = (int)(gid - b * nt);
   const T* src = in + b * L * G::D;
@@ -162,47 +181,7 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_lookback_kernel(const T*
   }
   Elem<T> total;
   const Elem<T> pre_thread = block_exclusive<G, T, LEFT>(run, total, sh);
-  int* fl = flags + b * nt;
-  if (threadIdx.x == 0) {                              // publish: tile 0 knows its inclusive prefix already
-    store_elem<Sim3g, T>((t == 0 ? pre : agg) + gid * 8, total);
-    __threadfence();
-    st_release_gpu(fl + t, t == 0 ? 2 : 1);
-  }
-  Elem<T> excl = elem_identity<T>();
-  if (t > 0) {
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      Elem<T> acc = elem_identity<T>();
-      for (int j = t - 1;; j -= 32) {                  // window: tiles j-31 .. j, lane 31 <-> tile j (lane order = time order)
-        const int idx = j - 31 + lane;
-        int f = 2;                                     // before the sequence start: an identity prefix
-        Elem<T> v = elem_identity<T>();
-        if (idx >= 0) {
-          do { f = ld_acquire_gpu(fl + idx); } while (f == 0);
-          v = load_elem<Sim3g, T>((f == 2 ? pre : agg) + (b * nt + idx) * 8);
-        }
-        const unsigned pm = __ballot_sync(0xffffffffu, f == 2);
-        const int hi = 31 - __clz(pm);                 // nearest published prefix in the window (-1: none)
-        if (lane < hi) v = elem_identity<T>();
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const Elem<T> up = elem_shfl_up(v, o);
-          if (lane >= o) v = combine<G, T, LEFT>(up, v);
-        }
-        acc = combine<G, T, LEFT>(elem_shfl(v, 31), acc);
-        if (pm) break;
-      }
-      if (lane == 0) {
-        store_elem<Sim3g, T>(excl_sh, acc);
-        store_elem<Sim3g, T>(pre + gid * 8, combine<G, T, LEFT>(acc, total));
-        __threadfence();
-        st_release_gpu(fl + t, 2);
-      }
-    }
-    __syncthreads();
-    excl = load_elem<Sim3g, T>(excl_sh);
-  }
-  const Elem<T> pfx = combine<G, T, LEFT>(excl, pre_thread);
+  const Elem<T> pfx = combine<G, T, LEFT>(load_elem<Sim3g, T>(pre + gid * 8), pre_thread);
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     if (first + c < L) {
@@ -225,18 +204,23 @@ int launch_cumprod(const T* in, T* out, long long B, long long L, int left, cuda
   else cumprod_kernel<G, T, false, CH><<<(unsigned)B, kScanThreads, 0, s>>>(in, out, L);
   return (int)cudaGetLastError();
 }
-// time-split variant; ws: b200_scan_workspace_bytes(B, L, sizeof(T)) bytes, zero-filled by the caller before every call
+// time-split variant; ws: b200_scan_workspace_bytes(B, L, sizeof(T)) bytes (no initialisation needed)
 template <class G, typename T>
 int launch_cumprod_lb(const T* in, T* out, long long B, long long L, int left, void* ws, cudaStream_t s) {
   if (B <= 0 || L <= 0) return 0;
   constexpr int CH = scan_ch<T>();
   const long long nt = scan_tiles(L, (int)sizeof(T)), tiles = B * nt;
-  unsigned* counter = reinterpret_cast<unsigned*>(ws);
-  int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + 16);
-  T* agg = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + 16 + ((tiles * 4 + 15) / 16) * 16);
+  T* agg = reinterpret_cast<T*>(ws);
   T* pre = agg + tiles * 8;
-  if (left) cumprod_lookback_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, counter, flags, agg, pre);
-  else cumprod_lookback_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, counter, flags, agg, pre);
+  if (left) {
+    cumprod_tile_reduce_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
+    cumprod_tile_prefix_kernel<G, T, true><<<(unsigned)B, kScanThreads, 0, s>>>(agg, pre, (int)nt);
+    cumprod_tile_apply_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
+  } else {
+    cumprod_tile_reduce_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
+    cumprod_tile_prefix_kernel<G, T, false><<<(unsigned)B, kScanThreads, 0, s>>>(agg, pre, (int)nt);
+    cumprod_tile_apply_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -632,8 +616,8 @@ IMU_ABI(f64, double, 2, 1)
 IMU_COV_ABI(f32, float)
 IMU_COV_ABI(f64, double)
 
-// bytes of the (zero-filled) workspace of b200_<G>_cumprod_lb_<T>
+// bytes of the workspace of b200_<G>_cumprod_lb_<T>
 B200_EXPORT long long b200_scan_workspace_bytes(long long B, long long L, long long elem_size) {
   const long long tiles = B * b200pose::scan_tiles(L, (int)elem_size);
-  return 16 + ((tiles * 4 + 15) / 16) * 16 + 2 * tiles * 8 * elem_size;
+  return 2 * tiles * 8 * elem_size;
 }

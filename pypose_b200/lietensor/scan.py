@@ -47,10 +47,10 @@ def _cumprod_cuda(x, group, left):
     with torch.cuda.device(x.device):
         tile = 128 * (8 if x.dtype == torch.float32 else 4)
         if B < 2 * _sms(x.device) and L >= 4 * tile:
-            # few long sequences: split the time axis over CTAs (single pass, decoupled look-back)
+            # few long sequences: split the time axis over CTAs (tile reduce -> prefix of the tile aggregates -> apply)
             q = _C.lib().b200_scan_workspace_bytes
             q.restype, q.argtypes = ctypes.c_longlong, [ctypes.c_longlong] * 3
-            ws = torch.zeros(int(q(B, L, x.element_size())), dtype=torch.uint8, device=x.device)
+            ws = torch.empty(int(q(B, L, x.element_size())), dtype=torch.uint8, device=x.device)
             sym = f"b200_{group}_cumprod_lb_{_C.suffix(x.dtype)}"
             _C.check(_C.fn(sym)(_p(x), _p(out), B, L, int(left), _p(ws), _C.stream_ptr(x.device)), sym)
         else:

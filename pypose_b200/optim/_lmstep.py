@@ -84,7 +84,7 @@ def reproj_trial(ds, prob, scale, dmin, dmax, retry):
     _C.enqueue("b200_lm_reproj_step_" + ds.sfx, poses, poses.data_ptr(), prob.pts.data_ptr(), prob.pix.data_ptr(),
                prob.seg.data_ptr(), H.data_ptr(), g.data_ptr(), Pt.data_ptr(), ds.W[0].data_ptr(), ds.W[1].data_ptr(),
                ds.state.data_ptr(), ds.host_ptr, ds.next_seq(), ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale),
-               float(dmin), float(dmax), 1 if retry else 0, poses.shape[0])
+               float(dmin), float(dmax), 1 if retry else 0, prob.pts.shape[0], poses.shape[0])
     return ds.read()
 
 

@@ -245,9 +245,9 @@ def test_imu_gravity_buffer_is_honoured():
 @pytest.mark.parametrize("grp", GROUPS)
 @pytest.mark.parametrize("B,L", [(1, 1_000_000), (3, 40_000), (2, 4097)])
 def test_cumprod_time_split_lookback_vs_oracle(grp, B, L):
-    """(B = 1, L = 1e6) used to run on one SM.  The time-split kernel (decoupled look-back over tiles,
-    csrc/scan.cu cumprod_lookback_kernel) against the oracle's log-step scan, fp64 1e-11, both directions; two runs are
-    bit-identical (the look-back combines predecessors in time order whatever the schedule)."""
+    """(B = 1, L = 1e6) used to run on one SM.  The time-split kernels (tile products, scan of the tile
+    products, apply; csrc/scan.cu cumprod_tile_*) against the oracle's log-step scan, fp64 1e-11, both directions; two
+    runs are bit-identical."""
     from tests.util import rand_group
     rng = np.random.default_rng(L + B)
     x = rand_group(rng, grp, B * L, tmax=0.02, t_sigma=0.01, s_sigma=1e-5).reshape(B, L, -1)
