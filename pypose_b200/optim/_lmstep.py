@@ -134,3 +134,76 @@ def poseinv_trial_peer(ds, prob, scale, dmin, dmax, retry):
                c.rank, c.world, ds.epoch1, ds.W[0].data_ptr(), ds.state.data_ptr(), ds.host_ptr, ds.next_seq(), ds.ctl_ptr,
                int(prob.robust[0]), float(prob.robust[1]), float(scale), float(dmin), float(dmax), P.shape[0])
     return ds.read()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# native step driver of the block-sparse pose families (csrc/lmdrive.cu b200_lm_pgo2_step)
+# ----------------------------------------------------------------------------------------------------------------
+class PgoStepArgs(ctypes.Structure):
+    """Mirror of `b200_pgo_step_args` (include/b200pose.h)."""
+    _vp, _ip, _dp = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p
+    _fields_ = ([(n, ctypes.c_int) for n in ("family", "is64", "robust", "retry")]
+                + [(n, ctypes.c_longlong) for n in ("N", "E", "maxiter", "hint", "seq", "iters_out")]
+                + [(n, ctypes.c_double) for n in ("delta", "scale", "dmin", "dmax", "tol")]
+                + [("intr", ctypes.c_double * 5), ("ctl", ctypes.c_double * 14)]
+                + [(n, ctypes.c_void_p) for n in ("nodes", "Z", "pts", "pix", "pseg", "pa", "pb", "ei", "ej", "epos_i", "epos_j",
+                                                  "nother", "nptr", "Mn", "un", "Hd", "g", "extra", "Minv", "x", "r", "z", "p0",
+                                                  "p1", "q", "xbest", "X7", "Pt", "ws0", "ws1", "ws2", "ws3", "cg", "st", "host")])
+
+
+class PgoDeviceStep:
+    """Buffers + argument block of one pose-graph-structured problem; `trial` is one C call."""
+
+    def __init__(self, prob, nodes):
+        dev, dt = nodes.device, nodes.dtype
+        N, E = nodes.shape[0], prob.ei.shape[0]
+        self.device, self.dtype, self.comm = dev, dt, None
+        new = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
+        self.buf = {"Mn": new(2 * E, 24), "un": new(2 * E, 6), "Hd": new(N, 21), "g": new(N, 6), "extra": new(N, 6),
+                    "Minv": new(N, 21), "x": new(N, 6), "r": new(N, 6), "z": new(N, 6), "p0": torch.zeros(N, 6, dtype=dt, device=dev),
+                    "p1": torch.zeros(N, 6, dtype=dt, device=dev), "q": new(N, 6), "xbest": new(N, 6), "X7": new(N, 7),
+                    "Pt": new(N, 7)}
+        n = _C.lib().b200_lm_workspace_doubles
+        n.restype = ctypes.c_longlong
+        self.W = torch.zeros(4, int(n()), dtype=torch.float64, device=dev)        # this problem's own reduction slots
+        self.cg = torch.zeros(16, dtype=torch.float64, device=dev)
+        self.host = torch.zeros(40, dtype=torch.float64).pin_memory()
+        self.state = None
+        a = self.args = PgoStepArgs()
+        a.family, a.is64 = (0 if prob.kind == "pgo" else 1), int(dt == torch.float64)
+        a.N, a.E = N, E
+        a.Z = prob.Z.data_ptr() if prob.Z is not None else None
+        if prob.kind == "reproj2":
+            a.pts, a.pix, a.pseg, a.pa, a.pb = (t.data_ptr() for t in (prob.pts, prob.pix, prob.pseg, prob.pa, prob.pb))
+            for i, v in enumerate(prob.intr):
+                a.intr[i] = v
+        for name in ("ei", "ej", "epos_i", "epos_j", "nother", "nptr"):
+            setattr(a, name, getattr(prob, name).data_ptr())
+        for name, t in self.buf.items():
+            setattr(a, name, t.data_ptr())
+        a.ws0, a.ws1, a.ws2, a.ws3 = (self.W[i].data_ptr() for i in range(4))
+        a.cg, a.host = self.cg.data_ptr(), self.host.data_ptr()
+        self.ctl = a.ctl
+        self.seq = 0
+        self.fn = _C.lib().b200_lm_pgo2_step
+        self.fn.restype, self.fn.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]
+
+    def new_state(self):
+        self.state = torch.empty(16, dtype=torch.float64, device=self.device)
+        self.args.st = self.state.data_ptr()
+        return self.state
+
+    def trial(self, prob, nodes, scale, dmin, dmax, retry):
+        a = self.args
+        self.seq += 1
+        a.nodes = nodes.data_ptr()
+        a.robust, a.delta = int(prob.robust[0]), float(prob.robust[1])
+        a.scale, a.dmin, a.dmax, a.tol = float(scale), float(dmin), float(dmax), float(prob.tol)
+        a.maxiter = int(prob.maxiter) if prob.maxiter is not None else 0
+        a.hint = prob.cg_iters + 1 if prob.cg_iters else 0
+        a.retry, a.seq = (1 if retry else 0), self.seq
+        rc = self.fn(ctypes.addressof(a), torch._C._cuda_getCurrentRawStream(self.device.index))
+        if rc != 0:
+            raise _C.B200PoseError(f"b200_lm_pgo2_step failed with CUDA error {rc}")
+        prob.cg_iters = int(a.iters_out)
+        return self.host[:16].tolist()

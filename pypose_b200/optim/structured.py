@@ -407,6 +407,24 @@ class PGOProblem(_Problem):
     def _peer(self, max_elems):
         return _peer_allreduce(self, self.param, max_elems)
 
+    # one C call per trial (csrc/lmdrive.cu): single GPU, node-ordered blocks, no information matrices
+    def device_step(self, strategy):
+        if getattr(self, '_pds', None) is not None:
+            return self._pds if _lmstep.strategy_kind(strategy) is not None else None
+        if getattr(self, '_pds_tried', False):
+            return None
+        self._pds_tried = True
+        nodes = self._nodes()
+        if (not nodes.is_cuda or self.group is not None or not self.node_order or self.W is not None
+                or _lmstep.strategy_kind(strategy) is None or not self.param.is_contiguous()
+                or os.environ.get("B200POSE_LM_HOST", "0") == "1" or nodes.get_device() != torch.cuda.current_device()):
+            return None
+        self._pds = _lmstep.PgoDeviceStep(self, nodes)
+        return self._pds
+
+    def device_trial(self, ds, scale, dmin, dmax, retry):
+        return ds.trial(self, self._nodes(), scale, dmin, dmax, retry)
+
 
 class Reproj2Problem(PGOProblem):
     """Two-pose reprojection r = proj(T_b^-1 T_a p) - z (module.TwoPoseReproj; BASELINE.json configs[4] as stated).

@@ -87,3 +87,13 @@ def test_fused_launch_sites_pass_as_many_arguments_as_the_abi_declares():
         assert n == arity[name], (name, n, arity[name])
         seen += 1
     assert seen >= 30
+
+
+def test_step_argument_block_mirror_has_the_c_layout():
+    """optim/_lmstep.py PgoStepArgs mirrors `b200_pgo_step_args` field by field: sizes must agree."""
+    from pypose_b200 import _C
+    from pypose_b200.optim._lmstep import PgoStepArgs
+    f = _C.lib().b200_pgo_step_args_size
+    f.restype = ctypes.c_longlong
+    assert ctypes.sizeof(PgoStepArgs) == f()
+    assert PgoStepArgs.nodes.offset == 4 * 4 + 6 * 8 + 5 * 8 + 5 * 8 + 14 * 8

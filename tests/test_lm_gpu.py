@@ -608,6 +608,7 @@ def test_lm_pgo_gather_and_scatter_routes(golden_lm, monkeypatch, scatter):
         for k in range(5):
             loss = opt.step(inp)
             assert opt._problem is not None and opt._problem.node_order == (scatter == "0")
+            assert (getattr(opt._problem, "_pds", None) is not None) == (scatter == "0")     # native step driver (lmdrive.cu)
             np.testing.assert_allclose(float(loss), g["pgo/trustregion/loss"][k], rtol=1e-6)
             np.testing.assert_allclose(net.nodes.detach().cpu().numpy(), g["pgo/trustregion/poses"][k], atol=1e-7)
         finals.append(net.nodes.detach().clone())
