@@ -11,6 +11,10 @@ cols = [("Kernel Name", "kernel"), ("gpu__time_duration.sum", "us"), ("launch__g
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
         ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+        ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
+        ("sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active", "hmma%"),
         ("smsp__inst_executed.sum", "warp_inst"), ("l1tex__t_sector_hit_rate.pct", "l1hit%"), ("lts__t_sector_hit_rate.pct", "l2hit%"),
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long"),
         ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_barrier"),
