@@ -207,3 +207,71 @@ class PgoDeviceStep:
             raise _C.B200PoseError(f"b200_lm_pgo2_step failed with CUDA error {rc}")
         prob.cg_iters = int(a.iters_out)
         return self.host[:16].tolist()
+
+
+class BaStepArgs(ctypes.Structure):
+    """Mirror of `b200_ba_step_args` (include/b200pose.h)."""
+    _fields_ = ([(n, ctypes.c_int) for n in ("is64", "robust", "retry", "tpi")]
+                + [(n, ctypes.c_longlong) for n in ("C", "P", "m", "split", "maxiter", "hint", "seq", "iters_out")]
+                + [(n, ctypes.c_double) for n in ("delta", "scale", "dmin", "dmax", "tol")]
+                + [("ctl", ctypes.c_double * 14)]
+                + [(n, ctypes.c_void_p) for n in ("poses", "points", "pix", "pidx", "cidx", "cseg", "ppos", "cidx_p", "pptr", "pix_p",
+                                                  "Y4", "Y4p", "rs", "Hcc", "gc", "Hpp", "gp", "part", "Hc", "Hpinv", "Minv", "Sd",
+                                                  "bneg", "x", "r", "z", "p", "q", "t", "xbest", "xp", "X7", "Tn", "pn",
+                                                  "ws0", "ws1", "ws2", "ws3", "cg", "st", "host")])
+
+
+class BaDeviceStep:
+    """Buffers + argument block of one bundle-adjustment problem; `trial` is one C call (csrc/lmdrive.cu b200_lm_ba_step)."""
+
+    def __init__(self, prob, T, pts):
+        dev, dt = T.device, T.dtype
+        C, P, m = T.shape[0], pts.shape[0], prob.pix.shape[0]
+        cseg, split, tpi, ppos, cidx_p, pptr, pix_p = prob.geom
+        self.device, self.dtype, self.comm = dev, dt, None
+        new = lambda *shape: torch.empty(*shape, dtype=dt, device=dev)
+        self.buf = {"Y4": new(m, 4), "Y4p": new(m, 4), "rs": new(m, 2), "Hcc": new(C, 21), "gc": new(C, 6), "Hpp": new(P, 6),
+                    "gp": new(P, 3), "part": new(max(C * split, 1), 27), "Hc": new(C, 21), "Hpinv": new(P, 6), "Minv": new(C, 21),
+                    "Sd": new(C, 21), "bneg": new(C, 6), "x": new(C, 6), "r": new(C, 6), "z": new(C, 6), "p": new(C, 6),
+                    "q": new(C, 6), "t": new(P, 3), "xbest": new(C, 6), "xp": new(P, 3), "X7": new(C, 7), "Tn": new(C, 7),
+                    "pn": new(P, 3)}
+        n = _C.lib().b200_lm_workspace_doubles
+        n.restype = ctypes.c_longlong
+        self.W = torch.zeros(4, int(n()), dtype=torch.float64, device=dev)
+        self.cg = torch.zeros(16, dtype=torch.float64, device=dev)
+        self.host = torch.zeros(40, dtype=torch.float64).pin_memory()
+        self.state = None
+        a = self.args = BaStepArgs()
+        a.is64, a.tpi = int(dt == torch.float64), int(tpi)
+        a.C, a.P, a.m, a.split = C, P, m, int(split)
+        for name, t in (("pix", prob.pix), ("pidx", prob.pidx), ("cidx", prob.cidx), ("cseg", cseg), ("ppos", ppos),
+                        ("cidx_p", cidx_p), ("pptr", pptr), ("pix_p", pix_p)):
+            setattr(a, name, t.data_ptr())
+        for name, t in self.buf.items():
+            setattr(a, name, t.data_ptr())
+        a.ws0, a.ws1, a.ws2, a.ws3 = (self.W[i].data_ptr() for i in range(4))
+        a.cg, a.host = self.cg.data_ptr(), self.host.data_ptr()
+        self.ctl = a.ctl
+        self.seq = 0
+        self.fn = _C.lib().b200_lm_ba_step
+        self.fn.restype, self.fn.argtypes = ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]
+
+    def new_state(self):
+        self.state = torch.empty(16, dtype=torch.float64, device=self.device)
+        self.args.st = self.state.data_ptr()
+        return self.state
+
+    def trial(self, prob, T, pts, scale, dmin, dmax, retry):
+        a = self.args
+        self.seq += 1
+        a.poses, a.points = T.data_ptr(), pts.data_ptr()
+        a.robust, a.delta = int(prob.robust[0]), float(prob.robust[1])
+        a.scale, a.dmin, a.dmax, a.tol = float(scale), float(dmin), float(dmax), float(prob.tol)
+        a.maxiter = int(prob.maxiter) if prob.maxiter is not None else 0
+        a.hint = prob.cg_iters + 1 if prob.cg_iters else 0
+        a.retry, a.seq = (1 if retry else 0), self.seq
+        rc = self.fn(ctypes.addressof(a), torch._C._cuda_getCurrentRawStream(self.device.index))
+        if rc != 0:
+            raise _C.B200PoseError(f"b200_lm_ba_step failed with CUDA error {rc}")
+        prob.cg_iters = int(a.iters_out)
+        return self.host[:16].tolist()

@@ -611,6 +611,25 @@ class BAProblem(_Problem):
         _copy_param(self.poses, self._trial[0])
         _copy_param(self.points, self._trial[1])
 
+    # one C call per trial (csrc/lmdrive.cu b200_lm_ba_step): single GPU
+    def device_step(self, strategy):
+        if getattr(self, '_bds', None) is not None:
+            return self._bds if _lmstep.strategy_kind(strategy) is not None else None
+        if getattr(self, '_bds_tried', False):
+            return None
+        self._bds_tried = True
+        T, p = self._params()
+        if (not T.is_cuda or self.group is not None or _lmstep.strategy_kind(strategy) is None
+                or not self.poses.is_contiguous() or not self.points.is_contiguous() or T.dtype != p.dtype
+                or os.environ.get("B200POSE_LM_HOST", "0") == "1" or T.get_device() != torch.cuda.current_device()):
+            return None
+        self._bds = _lmstep.BaDeviceStep(self, T, p)
+        return self._bds
+
+    def device_trial(self, ds, scale, dmin, dmax, retry):
+        T, p = self._params()
+        return ds.trial(self, T, p, scale, dmin, dmax, retry)
+
 
 def _input_key(input):
     items = input if isinstance(input, (tuple, list)) else (input,)

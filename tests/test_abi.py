@@ -97,3 +97,7 @@ def test_step_argument_block_mirror_has_the_c_layout():
     f.restype = ctypes.c_longlong
     assert ctypes.sizeof(PgoStepArgs) == f()
     assert PgoStepArgs.nodes.offset == 4 * 4 + 6 * 8 + 5 * 8 + 5 * 8 + 14 * 8
+    from pypose_b200.optim._lmstep import BaStepArgs
+    f = _C.lib().b200_ba_step_args_size
+    f.restype = ctypes.c_longlong
+    assert ctypes.sizeof(BaStepArgs) == f()
