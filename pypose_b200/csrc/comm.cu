@@ -3,6 +3,7 @@
 // asks for "one packed all-reduce of [H | g | loss] per LM iteration" and "one all-reduce per CG iteration".
 #include <string.h>
 #include "comm.cuh"
+#include "b200pose.h"
 #include "lm_common.cuh"
 
 namespace b200pose {

@@ -11,6 +11,7 @@
 // multiple of the SM count: each CTA gets the same number of elements (chunk), so there is no tail
 // wave.  One element per thread per tile; EPT tiles are batched per barrier to raise bytes in flight.
 #pragma once
+#include "b200pose.h"   // every definition is checked against the generated declaration
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "lm_math.cuh"
+#include "b200pose.h"   // every definition is checked against the generated declaration
 
 namespace b200pose {
 

@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <stdint.h>
 #include "lie_math.cuh"
+#include "b200pose.h"   // every definition is checked against the generated declaration
 #include "imu_cov_math.cuh"
 
 namespace b200pose {
