@@ -28,3 +28,4 @@ from . import module
 from .module.loss import geodesic_loss
 from . import optim
 from . import testing
+from . import utils

@@ -1,0 +1,84 @@
+"""Consumers of the hot path: the dataset tensor layouts and EPnP's Gauss-Newton refinement."""
+import os
+
+import numpy as np
+import torch
+from torch import nn
+
+import pypose_b200 as pp
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "consumers.npz")
+
+
+def test_g2o_layout(tmp_path):
+    """examples/module/pgo/pgo_dataset.py:8-51: nodes / edges / poses / infos, info2mat's symmetric fill."""
+    rng = np.random.default_rng(0)
+    info = rng.standard_normal(21)
+    lines = ["VERTEX_SE3:QUAT 0 0 0 0 0 0 0 1", "VERTEX_SE3:QUAT 1 1 0.5 0 0 0 0.7071067811865476 0.7071067811865476",
+             "EDGE_SE3:QUAT 0 1 1 0.5 0 0 0 0.7071067811865476 0.7071067811865476 " + " ".join(f"{v:.17g}" for v in info)]
+    p = tmp_path / "tiny.g2o"
+    p.write_text("\n".join(lines) + "\n")
+    d = pp.utils.read_g2o(str(p), dtype=torch.float64)
+    assert isinstance(d["nodes"], pp.LieTensor) and d["nodes"].shape == (2, 7) and d["edges"].tolist() == [[0, 1]]
+    assert d["poses"].shape == (1, 7) and d["infos"].shape == (1, 6, 6)
+    ref = np.zeros((6, 6))            # the reference's info2mat loop
+    ix = 0
+    for i in range(6):
+        ref[i, i:] = info[ix:ix + (6 - i)]
+        ref[i:, i] = info[ix:ix + (6 - i)]
+        ix += 6 - i
+    np.testing.assert_allclose(d["infos"][0].numpy(), ref, rtol=0, atol=0)
+    net = pp.module.PoseGraph(d["nodes"])                      # goes straight into the LM route with weights
+    assert torch.isfinite(net(d["edges"], d["poses"])).all()
+
+
+def test_bal_layout(tmp_path):
+    """examples/module/ba/bal_dataset.py:96-137: rotation vector -> quaternion, [t, q] pose, (f, k1, k2) intrinsics."""
+    cams = np.array([[0.1, -0.2, 0.3, 1.0, 2.0, 3.0, 500.0, 1e-3, -2e-6], [0.0, 0.0, 0.0, 0.5, 0.0, -1.0, 480.0, 0.0, 0.0]])
+    pts = np.array([[0.0, 1.0, 5.0], [1.0, -1.0, 4.0], [2.0, 0.5, 6.0]])
+    obs = [(0, 0, 10.5, -3.25), (0, 2, 1.0, 2.0), (1, 1, -7.0, 0.125), (1, 2, 3.0, 4.0)]
+    txt = [f"{len(cams)} {len(pts)} {len(obs)}"] + [f"{c} {p} {x} {y}" for c, p, x, y in obs]
+    txt += [f"{v:.17g}" for v in cams.reshape(-1)] + [f"{v:.17g}" for v in pts.reshape(-1)]
+    f = tmp_path / "tiny_bal.txt"
+    f.write_text("\n".join(txt) + "\n")
+    d = pp.utils.read_bal(str(f))
+    assert d["cidx"].tolist() == [0, 0, 1, 1] and d["pidx"].tolist() == [0, 2, 1, 2]
+    np.testing.assert_allclose(d["pixels"].numpy(), np.array([o[2:] for o in obs]))
+    np.testing.assert_allclose(d["points"].numpy(), pts)
+    np.testing.assert_allclose(d["intrinsics"].numpy(), cams[:, 6:])
+    np.testing.assert_allclose(d["cameras"].tensor()[:, :3].numpy(), cams[:, 3:6])
+    np.testing.assert_allclose(d["cameras"].rotation().Log().tensor().numpy(), cams[:, :3], atol=1e-12)   # same rotation
+    ba = pp.module.BundleAdjustment(d["cameras"], d["points"])
+    assert ba(d["pixels"], d["cidx"], d["pidx"]).shape == (4, 2)
+
+
+class BetaObjective(nn.Module):                    # module/pnp.py:13-27, unchanged apart from the import name
+    def __init__(self, beta):
+        super().__init__()
+        self.beta = torch.nn.Parameter(beta)
+        self.i = (0, 0, 0, 1, 1, 2)
+        self.j = (1, 2, 3, 2, 3, 3)
+
+    def forward(self, base_w, nullv):
+        base_c = (nullv.mT @ self.beta.unsqueeze(-1)).squeeze(-1).unflatten(dim=-1, sizes=(4, 3))
+        dist_c = (base_c[..., self.i, :] - base_c[..., self.j, :]).norm(dim=-1)
+        dist_w = (base_w[..., self.i, :] - base_w[..., self.j, :]).norm(dim=-1)
+        return dist_w - dist_c
+
+
+def test_epnp_gauss_newton_refinement_matches_reference():
+    """module/pnp.py:185-190 `_refine`: GaussNewton(BetaObjective, solver=LSTSQ()) under StopOnPlateau(steps=10,
+    patience=3) — loss sequence and refined beta of the reference (oracle/make_golden_consumers.py)."""
+    g = np.load(GOLD)
+    t = lambda k: torch.from_numpy(g[k].copy())
+    model = BetaObjective(t("pnp/beta0"))
+    optim = pp.optim.GaussNewton(model, solver=pp.optim.solver.LSTSQ())
+    sched = pp.optim.scheduler.StopOnPlateau(optim, steps=10, patience=3)
+    losses = []
+    while sched.continual():
+        loss = optim.step(input=(t("pnp/base_w"), t("pnp/nullv")))
+        sched.step(loss)
+        losses.append(float(loss))
+    assert len(losses) == len(g["pnp/loss"])
+    np.testing.assert_allclose(losses, g["pnp/loss"], rtol=1e-6, atol=1e-28)
+    np.testing.assert_allclose(model.beta.detach().numpy(), g["pnp/beta"], atol=1e-12)
