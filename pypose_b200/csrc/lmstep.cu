@@ -4,15 +4,15 @@
 // Python, then the parameter copy — 125 us per step for ~35 us of kernels (VERDICT r1 "What's weak").
 // Here ONE C call enqueues the whole trial and the control flow of optimizer.py:659-680 runs on the device:
 //
-//   reprojection (block-diagonal H):  K1 linearise + accumulate + damped 6x6 solve + retraction  (warp per camera)
-//                                     K2 trial loss; its last CTA takes the accept / reject decision and updates the
+//   reprojection (block-diagonal H):  K1 per camera: linearise + accumulate + damped 6x6 solve + retraction + trial loss over
+//                                        the same rows; its last CTA takes the accept / reject decision and updates the
 //                                        damping state (Constant / Adaptive / TrustRegion, strategy.py:41-46,134-151,248-274)
-//                                     K3 parameters <- trial parameters, if accepted
-//   PoseInv (independent poses):      K1 whole trial per pose in registers + decision in its last CTA;  K3 as above
+//                                     K2 parameters <- trial parameters, if accepted
+//   PoseInv (independent poses):      K1 whole trial per pose in registers + decision in its last CTA;  K2 as above
 //
 // and the 16-double state comes back with one asynchronous copy + one stream synchronisation (the single host read of
-// the step).  A rejected trial (rare) is retried by the host with the state it just read: K1 is then only the damped
-// solve on the stored blocks.  All scalars the decision needs are arguments of that call — the host stays the owner of
+// the step).  A rejected trial (rare) is retried by the host with the state it just read: K1 then starts from the stored
+// blocks instead of re-linearising.  All scalars the decision needs are arguments of that call — the host stays the owner of
 // `param_groups` (users edit the damping between steps), the device computes the update.
 #include "lm_common.cuh"
 #include "comm.cuh"
@@ -31,20 +31,21 @@ __device__ __forceinline__ void publish_state(const double* st, const HostOut& h
   o[ST_SIZE - 1] = h.seq;
 }
 
-// K1 (first trial of a step): LPC lanes per camera (32 for long observation lists, 8 when a camera has ~100 rows: then a
-// warp works on four cameras at once and the 10^4 cameras of the north-star size fit in one wave) — accumulate the
-// camera's 6x6 system over its sorted observations, keep it (H, g) for retries, solve the damped system and retract, all in
-// registers.  sums (ws): [0] sum rho(|r|^2) (current loss), [1] predicted reduction, [2] failed pivots
-template <typename T, int LPC>
-__global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
-                                                                      const T* __restrict__ pix, const int* __restrict__ seg,
-                                                                      T* __restrict__ H, T* __restrict__ g,
-                                                                      T* __restrict__ Pt, double* ws, T scale, T dmin,
-                                                                      T dmax, int rk, T rdelta, int ncam) {
+// The whole reprojection trial of ONE camera in one place (single GPU): accumulate the camera's rows -> 6x6 solve ->
+// retraction -> the camera's rows again with the trial pose (second read served by L1 / L2: a camera's rows are a few KB) ->
+// trial loss.  Nothing grid-wide separates "solve" from "trial loss" when H is block-diagonal, so K1 and K2 above fuse into
+// one launch and the decision runs in its last CTA.  FROM_BLOCKS: a retry starts from the stored blocks instead of the rows.
+// sums (ws): [0] current loss, [1] trial loss, [2] predicted reduction, [3] failed pivots
+template <typename T, int LPC, bool FROM_BLOCKS>
+__global__ void __launch_bounds__(kLmThreads) reproj_trial_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
+                                                                   const T* __restrict__ pix, const int* __restrict__ seg,
+                                                                   T* __restrict__ H, T* __restrict__ g, T* __restrict__ Pt,
+                                                                   double* ws, double* st, LmCtl ctl, HostOut ho, T scale,
+                                                                   T dmin, T dmax, int rk, T rdelta, int ncam) {
   const int sub = threadIdx.x % LPC;
   constexpr int cpb = kLmThreads / LPC;
   const int rounds = (ncam + cpb - 1) / cpb;
-  double acc[3] = {0.0, 0.0, 0.0};
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
     const int c = rd * cpb + threadIdx.x / LPC;
     const bool valid = c < ncam;
@@ -53,148 +54,99 @@ __global__ void __launch_bounds__(kLmThreads) reproj_linsolve_kernel(const T* __
 #pragma unroll
     for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)cc * 7 + k];
     const Elem<T> Tc = load_se3(pr);
-    Acc6<T> ac;
-    ac.zero();
-    T loss = T(0);
     const int b = valid ? seg[cc] : 0, e = valid ? seg[cc + 1] : 0;
-    auto accumulate = [&](const V3<T>& p, T zx, T zy) {
-      T rx, ry;
-      V3<T> y;
-      reproj_residual(Tc, p, zx, zy, rx, ry, y);
-      T j0[6], j1[6];
-      reproj_rows(y, j0, j1);
-      T rho, w;
-      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
-      if (rk) {
-        const T sw = m_sqrt(w);
-        rx *= sw; ry *= sw;
+    Sys6<T> s;
+    T loss = T(0);
+    if (!FROM_BLOCKS) {
+      Acc6<T> ac;
+      ac.zero();
+      auto accumulate = [&](const V3<T>& p, T zx, T zy) {
+        T rx, ry;
+        V3<T> y;
+        reproj_residual(Tc, p, zx, zy, rx, ry, y);
+        T j0[6], j1[6];
+        reproj_rows(y, j0, j1);
+        T rho, w;
+        robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+        if (rk) {
+          const T sw = m_sqrt(w);
+          rx *= sw; ry *= sw;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+          for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+        }
+        ac.add_row(j0, rx);
+        ac.add_row(j1, ry);
+        loss += rho;
+      };
+      int k = b + sub;
+      for (; k + LPC < e; k += 2 * LPC) {
+        const long long k0 = k, k1 = k + LPC;
+        const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
+        const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
+        const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
+        accumulate(p0, z0x, z0y);
+        accumulate(p1, z1x, z1y);
       }
-      ac.add_row(j0, rx);
-      ac.add_row(j1, ry);
-      loss += rho;
-    };
-    int k = b + sub;
-    for (; k + LPC < e; k += 2 * LPC) {          // two observations per lane in flight
-      const long long k0 = k, k1 = k + LPC;
-      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
-      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
-      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
-      accumulate(p0, z0x, z0y);
-      accumulate(p1, z1x, z1y);
-    }
-    if (k < e) {
-      const long long k0 = k;
-      accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
-    }
-    Sys6<T> s = ac.finish();
-#pragma unroll
-    for (int o = LPC / 2; o > 0; o >>= 1) {
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
-#pragma unroll
-        for (int bb = a; bb < 6; ++bb) s.A[a][bb] += __shfl_xor_sync(0xffffffffu, s.A[a][bb], o);
+      if (k < e) {
+        const long long k0 = k;
+        accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
       }
-      loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    }
-    // every lane of the group holds the camera's totals (xor tree): the solve runs redundantly, lane 0 stores
-    T D[6], pred;
-    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
-    if (valid && sub == 0) {
-      T o7[7];
-      store_elem<SE3g, T>(o7, se3_retract(D, Tc));
+      s = ac.finish();
 #pragma unroll
-      for (int q = 0; q < 7; ++q) Pt[(long long)c * 7 + q] = o7[q];
+      for (int o = LPC / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
+#pragma unroll
+          for (int bb = a; bb < 6; ++bb) s.A[a][bb] += __shfl_xor_sync(0xffffffffu, s.A[a][bb], o);
+        }
+        loss += __shfl_xor_sync(0xffffffffu, loss, o);
+      }
+    } else {
+      sys6_zero(s);
       int q = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        g[(long long)c * 6 + a] = s.g[a];
+        s.g[a] = g[(long long)cc * 6 + a];
 #pragma unroll
-        for (int bb = a; bb < 6; ++bb) H[(long long)c * 21 + q++] = s.A[a][bb];
+        for (int bb = a; bb < 6; ++bb) s.A[a][bb] = H[(long long)cc * 21 + q++];
       }
-      acc[0] += (double)loss;
-      acc[1] += (double)pred;
-      acc[2] += ok ? 0.0 : 1.0;
-    }
-  }
-  reduce_sums<3>(acc, ws);
-}
-
-// K1 (retry): damped solve + retraction from the stored blocks; same sums layout ([0] is not used by a retry)
-template <typename T>
-__global__ void __launch_bounds__(kLmThreads) reproj_resolve_kernel(const T* __restrict__ H, const T* __restrict__ g,
-                                                                     const T* __restrict__ P, T* __restrict__ Pt, double* ws,
-                                                                     T scale, T dmin, T dmax, long long n) {
-  double acc[3] = {0.0, 0.0, 0.0};
-  for (long long c = (long long)blockIdx.x * kLmThreads + threadIdx.x; c < n; c += (long long)gridDim.x * kLmThreads) {
-    Sys6<T> s;
-    int q = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      s.g[a] = g[c * 6 + a];
-#pragma unroll
-      for (int b = a; b < 6; ++b) s.A[a][b] = H[c * 21 + q++];
     }
     T D[6], pred;
     const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
-    T pr[7], o[7];
+    const Elem<T> Pn = se3_retract(D, Tc);
+    if (valid && sub == 0) {
+      T o7[7];
+      store_elem<SE3g, T>(o7, Pn);
 #pragma unroll
-    for (int k = 0; k < 7; ++k) pr[k] = P[c * 7 + k];
-    store_elem<SE3g, T>(o, se3_retract(D, load_se3(pr)));
+      for (int q = 0; q < 7; ++q) Pt[(long long)c * 7 + q] = o7[q];
+      if (!FROM_BLOCKS) {
+        int q = 0;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) Pt[c * 7 + k] = o[k];
-    acc[1] += (double)pred;
-    acc[2] += ok ? 0.0 : 1.0;
-  }
-  reduce_sums<3>(acc, ws);
-}
-
-// K2: trial loss (LPC lanes per camera, trial pose in registers); the last CTA decides.  ws1: this kernel's reduction
-// slot, ws0: K1's totals.
-template <typename T, int LPC>
-__global__ void __launch_bounds__(kLmThreads) reproj_loss_decide_kernel(const T* __restrict__ Pt, const T* __restrict__ pts,
-                                                                         const T* __restrict__ pix, const int* __restrict__ seg,
-                                                                         double* ws1, const double* ws0, double* st, LmCtl ctl,
-                                                                         HostOut ho, int rk, T rdelta, int ncam) {
-  const int sub = threadIdx.x % LPC;
-  constexpr int cpb = kLmThreads / LPC;
-  const int rounds = (ncam + cpb - 1) / cpb;
-  double acc[1] = {0.0};
-  for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
-    const int c = rd * cpb + threadIdx.x / LPC;
-    if (c >= ncam) continue;
-    T pr[7];
+        for (int a = 0; a < 6; ++a) {
+          g[(long long)c * 6 + a] = s.g[a];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) pr[q] = Pt[(long long)c * 7 + q];
-    const Elem<T> Tc = load_se3(pr);
-    const int b = seg[c], e = seg[c + 1];
-    T loss = T(0);
-    auto one = [&](const V3<T>& p, T zx, T zy) {
+          for (int bb = a; bb < 6; ++bb) H[(long long)c * 21 + q++] = s.A[a][bb];
+        }
+      }
+      acc[0] += (double)loss;
+      acc[2] += (double)pred;
+      acc[3] += ok ? 0.0 : 1.0;
+    }
+    // trial loss over the same rows with the trial pose (every lane adds its own partial)
+    T tl = T(0);
+    for (int k = b + sub; k < e; k += LPC) {
+      const long long k0 = k;
       T rx, ry, rho, w;
       V3<T> y;
-      reproj_residual(Tc, p, zx, zy, rx, ry, y);
+      reproj_residual(Pn, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1], rx, ry, y);
       robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
-      loss += rho;
-    };
-    int k = b + sub;
-    for (; k + LPC < e; k += 2 * LPC) {
-      const long long k0 = k, k1 = k + LPC;
-      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
-      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
-      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
-      one(p0, z0x, z0y);
-      one(p1, z1x, z1y);
+      tl += rho;
     }
-    if (k < e) {
-      const long long k0 = k;
-      one(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
-    }
-    acc[0] += (double)loss;
+    acc[1] += (double)tl;
   }
-  if (reduce_sums<1>(acc, ws1)) {
-    lm_decide(ctl, ws0[0], ws1[0], ws0[1], ws0[2], st);
+  if (reduce_sums<4>(acc, ws)) {
+    lm_decide(ctl, ws[0], ws[1], ws[2], ws[3], st);
     publish_state(st, ho);
   }
 }
@@ -586,25 +538,23 @@ using namespace b200pose;
     const HostOut ho = make_host_out(host_out, seq);                                                                  \
     const bool wide = rows >= 384 * ncam;                  /* lanes per camera: 32 for long lists, else 8 */          \
     const unsigned wgrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);                                    \
-    if (!retry) {                                                                                                     \
-      if (wide)                                                                                                       \
-        reproj_linsolve_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0,         \
-                                                                    (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta, \
-                                                                    (int)ncam);                                       \
-      else                                                                                                            \
-        reproj_linsolve_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0,          \
-                                                                   (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta,  \
-                                                                   (int)ncam);                                        \
-    } else {                                                                                                          \
-      reproj_resolve_kernel<CT><<<lm_grid(ncam, kLmThreads), kLmThreads, 0, s>>>(H, g, poses, P_trial, ws0,           \
-                                                                                 (CT)scale, (CT)dmin, (CT)dmax, ncam);\
-    }                                                                                                                 \
-    if (wide)                                                                                                         \
-      reproj_loss_decide_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(P_trial, pts, pix, seg, ws1, ws0, st, k, ho,     \
-                                                                     robust, (CT)delta, (int)ncam);                   \
+    (void)ws1;                                                                                                        \
+    if (wide && !retry)                                                                                               \
+      reproj_trial_kernel<CT, 32, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st,   \
+                                                                      k, ho, (CT)scale, (CT)dmin, (CT)dmax, robust,   \
+                                                                      (CT)delta, (int)ncam);                          \
+    else if (wide)                                                                                                    \
+      reproj_trial_kernel<CT, 32, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st, k, \
+                                                                     ho, (CT)scale, (CT)dmin, (CT)dmax, robust,       \
+                                                                     (CT)delta, (int)ncam);                           \
+    else if (!retry)                                                                                                  \
+      reproj_trial_kernel<CT, 8, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st, k, \
+                                                                     ho, (CT)scale, (CT)dmin, (CT)dmax, robust,       \
+                                                                     (CT)delta, (int)ncam);                           \
     else                                                                                                              \
-      reproj_loss_decide_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(P_trial, pts, pix, seg, ws1, ws0, st, k, ho,      \
-                                                                    robust, (CT)delta, (int)ncam);                    \
+      reproj_trial_kernel<CT, 8, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st, k,   \
+                                                                    ho, (CT)scale, (CT)dmin, (CT)dmax, robust,        \
+                                                                    (CT)delta, (int)ncam);                            \
     lm_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(st, P_trial, poses, ncam * 7);          \
     return finish_step(host_out, seq, s);                                                                             \
   }                                                                                                                   \
