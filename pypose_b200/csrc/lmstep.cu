@@ -14,10 +14,14 @@
 // the step).  A rejected trial (rare) is retried by the host with the state it just read: K1 then starts from the stored
 // blocks instead of re-linearising.  All scalars the decision needs are arguments of that call — the host stays the owner of
 // `param_groups` (users edit the damping between steps), the device computes the update.
+#include <stdlib.h>
 #include "lm_common.cuh"
 #include "comm.cuh"
+#include "tma.cuh"
 
 namespace b200pose {
+
+constexpr int kMaxLmDevices = 64;
 
 // The deciding thread also publishes the state in mapped pinned host memory (zero-copy): the host spins on the sequence
 // number instead of paying an asynchronous copy plus a stream synchronisation (~10 us per trial, measured).
@@ -135,13 +139,222 @@ __global__ void __launch_bounds__(kLmThreads) reproj_trial_kernel(const T* __res
     }
     // trial loss over the same rows with the trial pose (every lane adds its own partial)
     T tl = T(0);
-    for (int k = b + sub; k < e; k += LPC) {
-      const long long k0 = k;
+    {
+      auto trial = [&](const T* v) {
+        T rx, ry, rho, w;
+        V3<T> y;
+        reproj_residual(Pn, mk(v[0], v[1], v[2]), v[3], v[4], rx, ry, y);
+        robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+        tl += rho;
+      };
+      // the accumulators are dead here: keep kTrialRows rows per lane in flight (the fused kernel's occupancy is set by
+      // the accumulation loop, so the bytes in flight have to come from the unroll)
+      constexpr int kTrialRows = 4;
+      int k = b + sub;
+      for (; k + (kTrialRows - 1) * LPC < e; k += kTrialRows * LPC) {
+        T v[kTrialRows][5];
+#pragma unroll
+        for (int u = 0; u < kTrialRows; ++u) {
+          const long long ku = k + u * LPC;
+          v[u][0] = pts[ku * 3]; v[u][1] = pts[ku * 3 + 1]; v[u][2] = pts[ku * 3 + 2];
+          v[u][3] = pix[ku * 2]; v[u][4] = pix[ku * 2 + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < kTrialRows; ++u) trial(v[u]);
+      }
+      for (; k < e; k += LPC) {
+        const long long k0 = k;
+        const T v[5] = {pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2], pix[k0 * 2], pix[k0 * 2 + 1]};
+        trial(v);
+      }
+    }
+    acc[1] += (double)tl;
+  }
+  if (reduce_sums<4>(acc, ws)) {
+    lm_decide(ctl, ws[0], ws[1], ws[2], ws[3], st);
+    publish_state(st, ho);
+  }
+}
+
+// The same trial with the rows STAGED through shared memory by 1-D TMA bulk copies (tma.cuh): one warp per camera, a ring
+// of kStages tiles of kStageRows rows per warp, each tile one `cp.async.bulk` of the points and one of the pixels signalled
+// by an mbarrier.  The register-fed kernel above keeps (rows in flight per lane) x (resident warps) bytes in flight, and its
+// ~96 registers cap the warps: measured 0.61 of the HBM peak at 2e8 rows.  Here the bytes in flight are the ring
+// (kStages x 2.5 KB per warp, ~200 KB per SM), independent of the register count, and the lanes only read shared memory
+// (row stride 3 words / 2 words: conflict-free).  Both passes — accumulate, then the trial loss with the solved pose — are
+// ONE stream of 2 x tiles through the ring, so the first tiles of the second pass are already in flight while the warp
+// reduces and solves; a camera whose rows fit the ring (<= kStages tiles) is read from HBM once.
+// Tiles start at a multiple of 4 rows (16-byte alignment of both arrays); rows of the tile outside [seg[c], seg[c+1]) are
+// masked.  The one tile that would run past the end of the arrays is copied by the lanes instead.
+template <typename T> struct Staged {
+  static constexpr int kRows = 128;                               // rows per tile
+  static constexpr int kStages = sizeof(T) == 4 ? 4 : 3;
+  static constexpr int kWords = kRows * 5;                        // points (3) then pixels (2)
+  static constexpr int kWarps = kLmThreads / 32;
+  static constexpr int kBytes = kWarps * kStages * (kWords * (int)sizeof(T) + 8);
+};
+template <typename T, bool FROM_BLOCKS>
+__global__ void __launch_bounds__(kLmThreads) reproj_trial_staged_kernel(
+    const T* __restrict__ poses, const T* __restrict__ pts, const T* __restrict__ pix, const int* __restrict__ seg,
+    T* __restrict__ H, T* __restrict__ g, T* __restrict__ Pt, double* ws, double* st, LmCtl ctl, HostOut ho, T scale, T dmin,
+    T dmax, int rk, T rdelta, int ncam, long long rows_total) {
+  using L = Staged<T>;
+  constexpr int R = L::kRows, S = L::kStages;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  T* ring = reinterpret_cast<T*>(smem_raw) + warp * S * L::kWords;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L::kWarps * S * L::kWords * sizeof(T)) + warp * S;
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < S; ++q) mbar_init(&full[q], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  int sc = 0;                 // next stage to consume == next stage to fill whenever the ring is drained
+  uint32_t par = 0;           // phase parity per stage (bit q)
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int rounds = (ncam + L::kWarps - 1) / L::kWarps;
+  for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+    const int c = rd * L::kWarps + warp;
+    const bool valid = c < ncam;
+    const int cc = valid ? c : 0;
+    T pr[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)cc * 7 + k];
+    const Elem<T> Tc = load_se3(pr);
+    const int b = valid ? seg[cc] : 0, e = valid ? seg[cc + 1] : 0;
+    const long long a0 = (long long)(b / 4) * 4;
+    const int nt = e > b ? (int)((e - a0 + R - 1) / R) : 0;
+    const bool resident = !FROM_BLOCKS && nt <= S;           // second pass straight from the ring
+    const int jend = FROM_BLOCKS || resident ? nt : 2 * nt;  // tiles streamed for this camera
+    int issued = 0, si = sc;
+    auto issue = [&]() {                                      // tile (issued % nt) -> stage si
+      const int t = issued >= nt ? issued - nt : issued;
+      const long long r0 = a0 + (long long)t * R;
+      T* dst = ring + si * L::kWords;
+      if (r0 + R <= rows_total) {
+        if (lane == 0) {
+          mbar_expect_tx(&full[si], (uint32_t)(R * 5 * sizeof(T)));
+          bulk_g2s(dst, pts + r0 * 3, (uint32_t)(R * 3 * sizeof(T)), &full[si]);
+          bulk_g2s(dst + R * 3, pix + r0 * 2, (uint32_t)(R * 2 * sizeof(T)), &full[si]);
+        }
+      } else {                                                // the last tile of the arrays: plain copies by the lanes
+        const int cnt = (int)(rows_total - r0);
+        for (int i = lane; i < cnt * 3; i += 32) dst[i] = pts[r0 * 3 + i];
+        for (int i = lane; i < cnt * 2; i += 32) dst[R * 3 + i] = pix[r0 * 2 + i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[si]);
+      }
+      ++issued;
+      if (++si == S) si = 0;
+    };
+    while (issued < jend && issued < S) issue();
+
+    // consume tile t of a pass out of stage q: f(point, pixel) for this lane's rows inside [b, e)
+    auto for_rows = [&](int t, int q, auto&& f) {
+      const T* sp = ring + q * L::kWords;
+      const T* sx = sp + R * 3;
+      const long long r0 = a0 + (long long)t * R;
+#pragma unroll
+      for (int u = 0; u < R / 32; ++u) {
+        const int row = lane + 32 * u;
+        const long long k = r0 + row;
+        if (k >= b && k < e) f(mk(sp[row * 3], sp[row * 3 + 1], sp[row * 3 + 2]), sx[row * 2], sx[row * 2 + 1]);
+      }
+    };
+    auto next_tile = [&](int t, auto&& f) {                   // wait, consume, refill the stage
+      mbar_wait(&full[sc], (par >> sc) & 1u);
+      par ^= 1u << sc;
+      for_rows(t, sc, f);
+      __syncwarp();                                           // every lane has read the stage before it is overwritten
+      if (issued < jend) issue();
+      if (++sc == S) sc = 0;
+    };
+
+    Sys6<T> s;
+    T loss = T(0);
+    const int s_first = sc;
+    if (!FROM_BLOCKS) {
+      Acc6<T> ac;
+      ac.zero();
+      auto accumulate = [&](const V3<T>& p, T zx, T zy) {
+        T rx, ry;
+        V3<T> y;
+        reproj_residual(Tc, p, zx, zy, rx, ry, y);
+        T j0[6], j1[6];
+        reproj_rows(y, j0, j1);
+        T rho, w;
+        robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+        if (rk) {
+          const T sw = m_sqrt(w);
+          rx *= sw; ry *= sw;
+#pragma unroll
+          for (int a = 0; a < 6; ++a) { j0[a] *= sw; j1[a] *= sw; }
+        }
+        ac.add_row(j0, rx);
+        ac.add_row(j1, ry);
+        loss += rho;
+      };
+      for (int t = 0; t < nt; ++t) next_tile(t, accumulate);
+      s = ac.finish();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
+#pragma unroll
+          for (int bb = a; bb < 6; ++bb) s.A[a][bb] += __shfl_xor_sync(0xffffffffu, s.A[a][bb], o);
+        }
+        loss += __shfl_xor_sync(0xffffffffu, loss, o);
+      }
+    } else {
+      sys6_zero(s);
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        s.g[a] = g[(long long)cc * 6 + a];
+#pragma unroll
+        for (int bb = a; bb < 6; ++bb) s.A[a][bb] = H[(long long)cc * 21 + q++];
+      }
+    }
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    const Elem<T> Pn = se3_retract(D, Tc);
+    if (valid && lane == 0) {
+      T o7[7];
+      store_elem<SE3g, T>(o7, Pn);
+#pragma unroll
+      for (int q = 0; q < 7; ++q) Pt[(long long)c * 7 + q] = o7[q];
+      if (!FROM_BLOCKS) {
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          g[(long long)c * 6 + a] = s.g[a];
+#pragma unroll
+          for (int bb = a; bb < 6; ++bb) H[(long long)c * 21 + q++] = s.A[a][bb];
+        }
+      }
+      acc[0] += (double)loss;
+      acc[2] += (double)pred;
+      acc[3] += ok ? 0.0 : 1.0;
+    }
+    T tl = T(0);
+    auto trial = [&](const V3<T>& p, T zx, T zy) {
       T rx, ry, rho, w;
       V3<T> y;
-      reproj_residual(Pn, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1], rx, ry, y);
+      reproj_residual(Pn, p, zx, zy, rx, ry, y);
       robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
       tl += rho;
+    };
+    if (resident) {
+      int q = s_first;
+      for (int t = 0; t < nt; ++t) {
+        for_rows(t, q, trial);
+        if (++q == S) q = 0;
+      }
+      __syncwarp();                                           // the next camera refills these stages
+    } else {
+      for (int t = 0; t < nt; ++t) next_tile(t, trial);
     }
     acc[1] += (double)tl;
   }
@@ -522,9 +735,42 @@ static int finish_step(double* host_out, long long seq, cudaStream_t s) {
   }
 }
 
+// B200POSE_REPROJ_STAGED: 0 = register-fed kernels only, 1 (default) = TMA-staged kernel for long row lists,
+// 2 = TMA-staged kernel always (A/B knob for DESIGN.md §3.3)
+static int g_staged_mode = -1;
+static int staged_mode() {
+  if (g_staged_mode < 0) {
+    const char* v = getenv("B200POSE_REPROJ_STAGED");
+    g_staged_mode = v && *v ? atoi(v) : 1;
+  }
+  return g_staged_mode;
+}
+// dynamic shared memory above 48 KB needs the opt-in attribute, once per device and kernel
+template <typename T> static int staged_prepare() {
+  if (Staged<T>::kBytes <= 48 * 1024) return 0;
+  static bool done[kMaxLmDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev >= 0 && dev < kMaxLmDevices ? dev : 0;
+  if (done[slot] && dev == slot) return 0;
+  cudaError_t e = cudaFuncSetAttribute(reproj_trial_staged_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Staged<T>::kBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(reproj_trial_staged_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Staged<T>::kBytes);
+  if (e == cudaSuccess) done[slot] = true;
+  return (int)e;
+}
+
 }  // namespace b200pose
 
 using namespace b200pose;
+
+B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
+  const int prev = staged_mode();
+  if (mode >= 0) g_staged_mode = mode;
+  return prev;
+}
 
 #define LMSTEP_ABI(SFX, CT)                                                                                           \
   B200_EXPORT int b200_lm_reproj_step_##SFX(CT* poses, const CT* pts, const CT* pix, const int* seg, CT* H, CT* g,    \
@@ -539,7 +785,20 @@ using namespace b200pose;
     const bool wide = rows >= 384 * ncam;                  /* lanes per camera: 32 for long lists, else 8 */          \
     const unsigned wgrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);                                    \
     (void)ws1;                                                                                                        \
-    if (wide && !retry)                                                                                               \
+    const int staged = staged_mode();                                                                                 \
+    if ((staged == 2 || (staged == 1 && wide)) && ((((uintptr_t)pts) | ((uintptr_t)pix)) & 15) == 0) {               \
+      int rc = staged_prepare<CT>();                                                                                  \
+      if (rc) return rc;                                                                                              \
+      const unsigned sgrid = lm_grid(ncam, kLmThreads / 32);                                                          \
+      if (!retry)                                                                                                     \
+        reproj_trial_staged_kernel<CT, false><<<sgrid, kLmThreads, Staged<CT>::kBytes, s>>>(                          \
+            poses, pts, pix, seg, H, g, P_trial, ws0, st, k, ho, (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta,    \
+            (int)ncam, rows);                                                                                         \
+      else                                                                                                            \
+        reproj_trial_staged_kernel<CT, true><<<sgrid, kLmThreads, Staged<CT>::kBytes, s>>>(                           \
+            poses, pts, pix, seg, H, g, P_trial, ws0, st, k, ho, (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta,    \
+            (int)ncam, rows);                                                                                         \
+    } else if (wide && !retry)                                                                                               \
       reproj_trial_kernel<CT, 32, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st,   \
                                                                       k, ho, (CT)scale, (CT)dmin, (CT)dmax, robust,   \
                                                                       (CT)delta, (int)ncam);                          \

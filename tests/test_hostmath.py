@@ -5,6 +5,7 @@ a GPU; the GPU tests (test_lie_gpu.py) then validate the kernels proper through 
 Tolerances: fp64 1e-12 (north_star), fp32 2e-6 relative to (1 + |truth|).
 Tiny-angle rows are compared with the oracle in wide_taylor() mode (see oracle/lie_oracle.py)."""
 import os
+import zlib
 import numpy as np
 import pytest
 
@@ -17,14 +18,16 @@ OPS = all_ops()
 
 def _check(res, truth, tol):
     for r, t in zip(res, truth):
-        err = np.abs(r.astype(np.float64) - t) / (1.0 + np.abs(t))
+        # element error against the size of its ROW: a component that cancels to ~0 inside a row with large entries
+        # (Sim3 scale x translation) carries the rounding error of the large ones
+        err = np.abs(r.astype(np.float64) - t) / (1.0 + np.abs(t).reshape(t.shape[0], -1).max(axis=1).reshape((-1,) + (1,) * (t.ndim - 1)))
         assert err.max() <= tol, f"max rel err {err.max():.3e}"
 
 
 @pytest.mark.parametrize("key,grp,op,inw,outw", OPS, ids=[o[0] for o in OPS])
 @pytest.mark.parametrize("dt,tol", [(np.float64, 1e-12), (np.float32, 2e-6)], ids=["f64", "f32"])
 def test_functor_vs_oracle_random(key, grp, op, inw, outw, dt, tol):
-    rng = np.random.default_rng(abs(hash(key)) % (2 ** 31))
+    rng = np.random.default_rng(zlib.crc32(key.encode()))
     ins = [a.astype(dt) for a in make_inputs(rng, grp, op, 257)]
     with O.wide_taylor():
         truth = O.run(key, *[a.astype(np.float64) for a in ins])
@@ -35,7 +38,7 @@ def test_wide_taylor_oracle_equals_faithful_oracle_when_well_conditioned():
     """wide_taylor() only changes how the SAME formulas are evaluated: on well-conditioned inputs
     (theta in [0.05, pi-0.05], |sigma| >= 0.01) both evaluations agree to 1e-12."""
     for key, grp, op, inw, outw in OPS:
-        rng = np.random.default_rng(abs(hash(key)) % (2 ** 31))
+        rng = np.random.default_rng(zlib.crc32(key.encode()))
         ins = make_inputs(rng, grp, op, 512)
         faithful = O.run(key, *ins)
         with O.wide_taylor():

@@ -3,6 +3,7 @@ reference), called through the C-ABI (ctypes) on device buffers.
 
 Tolerances (stated per north_star): fp64 1e-12, fp32 2e-6, both relative to (1 + |truth|).
 """
+import zlib
 import numpy as np
 import pytest
 import torch
@@ -35,7 +36,7 @@ def check(res, truth, tol, what="", scale=1.0):
 @pytest.mark.parametrize("key,grp,op,inw,outw", OPS, ids=[o[0] for o in OPS])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
 def test_op_vs_oracle_random(key, grp, op, inw, outw, dtype):
-    rng = np.random.default_rng(abs(hash(key)) % (2 ** 31))
+    rng = np.random.default_rng(zlib.crc32(key.encode()))
     ins = make_inputs(rng, grp, op, 20011)      # ragged: not a multiple of 4 / of the tile
     res, dev_ins = run_abi(key, ins, outw, dtype)
     host_ins = [t.double().cpu().numpy() for t in dev_ins]

@@ -123,6 +123,51 @@ def test_lm_reproj_reference_trajectory_on_gpu(golden_lm, case, strategy, steps,
         assert opt.reject_count == g[f"{case}/{strategy}/reject"][k]
 
 
+@pytest.mark.parametrize("dt,tol", [(torch.float64, 1e-11), (torch.float32, 2e-5)], ids=["f64", "f32"])
+@pytest.mark.parametrize("kernel", [None, "huber"])
+def test_reproj_staged_route_matches_register_route(dt, tol, kernel):
+    """csrc/lmstep.cu reproj_trial_staged_kernel (rows through a TMA-fed shared-memory ring, one warp per camera) against the
+    register-fed reproj_trial_kernel on ragged per-camera row lists: empty cameras, 1 row, lists that end exactly on a
+    tile, lists shorter / longer than the ring, a total that is not a multiple of 4 (the last tile is copied by the lanes),
+    accepted and rejected trials (the retry runs from the stored blocks)."""
+    import ctypes
+    from pypose_b200 import _C
+    rng = np.random.default_rng(11)
+    counts = np.array([0, 1, 3, 127, 128, 129, 511, 512, 513, 640, 2000, 0, 5, 1537, 64, 4099, 2, 0, 777, 1023], np.int64)
+    C, M = counts.size, int(counts.sum())
+    assert M % 4 != 0
+    cidx = rng.permutation(np.repeat(np.arange(C), counts))
+    gt = rand_group(rng, "SE3", C, tmax=0.5, t_sigma=0.5)
+    pc = rng.uniform([-2, -2, 2], [2, 2, 6], (M, 3))
+    pts = O.act("SE3", O.inv("SE3", gt)[cidx], pc)
+    pix = -pc[:, :2] / pc[:, 2:] + 0.01 * rng.standard_normal((M, 2))
+    if kernel:
+        pix[rng.random(M) < 0.05] += 0.5
+    init = O.mul("SE3", O.exp("SE3", 0.1 * rng.standard_normal((C, 6))), gt)
+    inp = (cu(pts, dt), cu(pix, dt), torch.from_numpy(cidx).cuda())
+    mode = _C.lib().b200_lm_reproj_staged_mode
+    mode.restype, mode.argtypes = ctypes.c_int, [ctypes.c_int]
+    prev = mode(-1)
+    out = {}
+    try:
+        for m in (0, 2):
+            mode(m)
+            net = pp.module.PoseReproj(pp.SE3(cu(init, dt)))
+            opt = pp.optim.LM(net, strategy=pp.optim.strategy.TrustRegion(radius=1e4),
+                              kernel=pp.optim.kernel.Huber(delta=0.1) if kernel else None)
+            losses, rejects = [], []
+            for _ in range(6):
+                losses.append(float(opt.step(inp)))
+                rejects.append(opt.reject_count)
+            out[m] = (np.array(losses), rejects, net.poses.detach().double().cpu().numpy())
+    finally:
+        mode(prev)
+    np.testing.assert_allclose(out[2][0], out[0][0], rtol=tol * 10)
+    assert out[2][1] == out[0][1]
+    assert np.abs(out[2][2] - out[0][2]).max() <= tol * 10
+    assert out[0][0][-1] < out[0][0][0]
+
+
 def test_config3_invnet_1e5_fp32_converges():
     """BASELINE.json configs[2]: README InvNet, 1e5 SE3 poses, fp32, Constant(1e-4), Cholesky, 10 iterations.
     (rotations of the inputs are kept away from the Log branch cut, SURVEY.md §8d cfg 3.)"""
