@@ -14,6 +14,7 @@
 #include "lie_math.cuh"
 #include "b200pose.h"   // every definition is checked against the generated declaration
 #include "imu_cov_math.cuh"
+#include "tma.cuh"
 
 namespace b200pose {
 
@@ -564,6 +565,164 @@ SCAN_ABI(SE3, SE3g)
 SCAN_ABI(RxSO3, RxSO3g)
 SCAN_ABI(Sim3, Sim3g)
 
+// ------------------------------------------------------------------------------------------------
+// Predict-only integration with the samples STAGED through shared memory by 1-D TMA bulk copies (tma.cuh).
+// ncu of imu_integrate_kernel (profiles/r1i): 124 registers -> 16 warps per SM, and half of the stall cycles are long-
+// scoreboard waits on the tile's own loads plus LSU back-pressure from 3-word strided stores — the next tile cannot start
+// loading before this one has been scanned.  Here thread 0 queues the bulk loads of tile i+2 while the CTA scans tile i
+// out of shared memory, and the results leave through one bulk store per output array, so the LSU only sees shared memory.
+// Same arithmetic, same order of operations as imu_integrate_kernel (results are bit-identical).
+// Preconditions (checked by the launcher, which otherwise uses imu_integrate_kernel): no per-sample `rot`, no integrate
+// outputs, 16-byte aligned arrays and F * sizeof(T) a multiple of 16.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CH> struct ImuTma {
+  static constexpr int TILE = kScanThreads * CH;
+  static constexpr int S = 2;                                   // input stages
+  static constexpr int IN_WORDS = TILE * 7, OUT_WORDS = TILE * 10;
+  static constexpr int BYTES = (S * IN_WORDS + OUT_WORDS) * (int)sizeof(T) + 8 * S;
+};
+template <typename T, int CH>
+__global__ void __launch_bounds__(kScanThreads) imu_predict_tma_kernel(
+    const T* __restrict__ dt, const T* __restrict__ gyro, const T* __restrict__ acc, const T* __restrict__ init_rot,
+    long long init_stride, T gx, T gy, T gz, const T* __restrict__ init_pos, const T* __restrict__ init_vel,
+    long long pv_stride, T* __restrict__ rot_o, T* __restrict__ vel_o, T* __restrict__ pos_o, long long F) {
+  using L = ImuTma<T, CH>;
+  constexpr int TILE = L::TILE, S = L::S;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ T sh[(kScanThreads / 32) * 8];
+  T* s_in = reinterpret_cast<T*>(smem_raw);
+  T* s_out = s_in + S * L::IN_WORDS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_out + L::OUT_WORDS);
+  const long long b = blockIdx.x;
+  dt += b * F; gyro += b * F * 3; acc += b * F * 3;
+  rot_o += b * F * 4; vel_o += b * F * 3; pos_o += b * F * 3;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < S; ++q) mbar_init(&full[q], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ntiles = (int)((F + TILE - 1) / TILE);
+  auto issue_load = [&](int t, int q) {                         // thread 0 only
+    const long long base = (long long)t * TILE;
+    const uint32_t cnt = (uint32_t)(F - base < TILE ? F - base : TILE);
+    T* dst = s_in + q * L::IN_WORDS;
+    mbar_expect_tx(&full[q], cnt * 7u * (uint32_t)sizeof(T));
+    bulk_g2s(dst, dt + base, cnt * (uint32_t)sizeof(T), &full[q]);
+    bulk_g2s(dst + TILE, gyro + base * 3, cnt * 3u * (uint32_t)sizeof(T), &full[q]);
+    bulk_g2s(dst + 4 * TILE, acc + base * 3, cnt * 3u * (uint32_t)sizeof(T), &full[q]);
+  };
+  if (tid == 0)
+    for (int t = 0; t < ntiles && t < S; ++t) issue_load(t, t);
+
+  const V3<T> grav = mk(gx, gy, gz);
+  Elem<T> R0 = elem_identity<T>();
+  if (init_rot) R0.q = ldq(init_rot + b * init_stride);
+  V3<T> p0 = mk(T(0), T(0), T(0)), v0 = p0;
+  if (init_pos) p0 = ld3(init_pos + b * pv_stride);
+  if (init_vel) v0 = ld3(init_vel + b * pv_stride);
+  Elem<T> carryR = elem_identity<T>();
+  Vpt<T> carry = vpt_identity<T>();
+  T* o_rot = s_out;
+  T* o_vel = s_out + 4 * TILE;
+  T* o_pos = s_out + 7 * TILE;
+  int q = 0;
+  uint32_t parity = 0;
+  for (int i = 0; i < ntiles; ++i) {
+    const long long base = (long long)i * TILE;
+    const int cnt = (int)(F - base < TILE ? F - base : TILE);
+    const T* i_dt = s_in + q * L::IN_WORDS;
+    const T* i_gy = i_dt + TILE;
+    const T* i_ac = i_dt + 4 * TILE;
+    const int first = tid * CH;
+    mbar_wait(&full[q], parity);
+    if (tid == 0) bulk_wait_read<0>();     // the store of tile i-1 has left s_out (ordered for the CTA by the scan's barrier)
+    Elem<T> loc[CH];
+    T dts[CH];
+    Elem<T> run = elem_identity<T>();
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      dts[c] = T(0);
+      if (first + c < cnt) {
+        const int k = first + c;
+        dts[c] = i_dt[k];
+        const V3<T> phi = dts[c] * mk(i_gy[k * 3], i_gy[k * 3 + 1], i_gy[k * 3 + 2]);
+        Elem<T> dr = elem_identity<T>();
+        dr.q = so3_exp_imu(phi);
+        run = g_mul<SO3g, T>(run, dr);
+      }
+      loc[c] = run;
+    }
+    Elem<T> totR;
+    const Elem<T> preR = g_mul<SO3g, T>(carryR, block_exclusive<SO3g, T, false>(run, totR, sh));
+    Vpt<T> vloc[CH];
+    Vpt<T> vrun = vpt_identity<T>();
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      if (first + c < cnt) {
+        const int k = first + c;
+        const Elem<T> Rafter = g_mul<SO3g, T>(preR, loc[c]);
+        const Elem<T> Rbefore = c == 0 ? preR : g_mul<SO3g, T>(preR, loc[c - 1]);
+        const Q4<T> qg = qmul(R0.q, Rafter.q);
+        const V3<T> ak = mk(i_ac[k * 3], i_ac[k * 3 + 1], i_ac[k * 3 + 2]) - qrot_t(qg, grav);
+        const V3<T> Ra = qrot(Rbefore.q, ak);
+        Vpt<T> e; e.v = dts[c] * Ra; e.p = (T(0.5) * dts[c] * dts[c]) * Ra; e.t = dts[c];
+        vrun = vpt_combine(vrun, e);
+        stq(o_rot + k * 4, qmul(R0.q, Rafter.q));
+      }
+      vloc[c] = vrun;
+    }
+    Vpt<T> totV;
+    const Vpt<T> preV = vpt_combine(carry, vpt_block_exclusive(vrun, totV, sh));
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      if (first + c < cnt) {
+        const int k = first + c;
+        const Vpt<T> y = vpt_combine(preV, vloc[c]);
+        st3(o_vel + k * 3, v0 + qrot(R0.q, y.v));
+        st3(o_pos + k * 3, p0 + qrot(R0.q, y.p) + y.t * v0);
+      }
+    }
+    carryR = g_mul<SO3g, T>(carryR, totR);
+    carry = vpt_combine(carry, totV);
+    fence_async_smem();
+    __syncthreads();                       // s_out complete, stage q read by everyone
+    if (tid == 0) {
+      bulk_s2g(rot_o + base * 4, o_rot, (uint32_t)cnt * 4u * (uint32_t)sizeof(T));
+      bulk_s2g(vel_o + base * 3, o_vel, (uint32_t)cnt * 3u * (uint32_t)sizeof(T));
+      bulk_s2g(pos_o + base * 3, o_pos, (uint32_t)cnt * 3u * (uint32_t)sizeof(T));
+      bulk_commit();
+      if (i + S < ntiles) issue_load(i + S, q);
+    }
+    if (++q == S) { q = 0; parity ^= 1; }
+  }
+  if (tid == 0) bulk_wait_all();
+}
+// opt-in for > 48 KB of dynamic shared memory, once per device and instantiation
+constexpr int kMaxDevices = 64;
+template <typename T, int CH> static int imu_tma_prepare() {
+  static bool done[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+  if (done[dev]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(imu_predict_tma_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ImuTma<T, CH>::BYTES);
+  if (e == cudaSuccess) done[dev] = true;
+  return (int)e;
+}
+template <typename T, int CH>
+static int imu_tma_launch(const T* dt, const T* gyro, const T* acc, const T* init_rot, long long init_stride, const T* g,
+                          const T* init_pos, const T* init_vel, long long pv_stride, T* rot_out, T* vel_out, T* pos_out,
+                          long long B, long long F, cudaStream_t s) {
+  int rc = imu_tma_prepare<T, CH>();
+  if (rc) return rc;
+  imu_predict_tma_kernel<T, CH><<<(unsigned)B, kScanThreads, ImuTma<T, CH>::BYTES, s>>>(
+      dt, gyro, acc, init_rot, init_stride, g[0], g[1], g[2], init_pos, init_vel, pv_stride, rot_out, vel_out, pos_out, F);
+  return (int)cudaGetLastError();
+}
+
 // Samples per thread (CH) trades scan overhead (amortised over CH) against coalescing (a thread's CH consecutive
 // samples make every warp access CH-strided).  Measured on B200 at 1e3 x 1e4 samples (tools/ab_imu.py): fp64 predict-only
 // 0.61 ms at CH=2 vs 0.72 (CH=1) / 0.74 (CH=4); fp64 with the six integrate outputs 0.74 ms at CH=1 vs 0.79 / 1.14;
@@ -576,6 +735,20 @@ static void imu_launch(const T* dt, const T* gyro, const T* acc, const T* rot, c
                                                                    a, Dp, Dv, Dr, Dt, w, init_pos, init_vel, pv_stride,
                                                                    rot_out, vel_out, pos_out, F);
 }
+// B200POSE_IMU_TMA / b200_imu_tma_mode: 1 (default) predict-only calls take imu_predict_tma_kernel when they can, 0 never
+static int g_imu_tma = -1;
+static int imu_tma_mode() {
+  if (g_imu_tma < 0) {
+    const char* v = getenv("B200POSE_IMU_TMA");
+    g_imu_tma = v && *v ? atoi(v) : 1;
+  }
+  return g_imu_tma;
+}
+B200_EXPORT int b200_imu_tma_mode(int mode) {
+  const int prev = imu_tma_mode();
+  if (mode >= 0) g_imu_tma = mode;
+  return prev;
+}
 #define IMU_ABI(SFX, CT, CH_PREDICT, CH_FULL)                                                                          \
   B200_EXPORT int b200_imu_integrate_##SFX(const CT* dt, const CT* gyro, const CT* acc, const CT* rot,                 \
                                            const CT* init_rot, long long init_stride, const CT* gravity3_host, CT* a,  \
@@ -585,6 +758,14 @@ static void imu_launch(const T* dt, const T* gyro, const T* acc, const T* rot, c
     if (B <= 0 || F <= 0) return 0;                                                                                    \
     static const int ch_env = getenv("B200POSE_IMU_CH") ? atoi(getenv("B200POSE_IMU_CH")) : 0;                         \
     const int ch = ch_env ? ch_env : (a ? CH_FULL : CH_PREDICT);                                                       \
+    const int tma_env = imu_tma_mode();                                                                                \
+    const uintptr_t bits = (uintptr_t)dt | (uintptr_t)gyro | (uintptr_t)acc | (uintptr_t)rot_out | (uintptr_t)vel_out | \
+                           (uintptr_t)pos_out | (uintptr_t)(F * (long long)sizeof(CT));                                \
+    if (tma_env && !a && !rot && rot_out && (bits & 15) == 0 && ch != 4) {                                             \
+      auto tgo = ch == 1 ? imu_tma_launch<CT, 1> : imu_tma_launch<CT, 2>;                                              \
+      return tgo(dt, gyro, acc, init_rot, init_stride, gravity3_host, init_pos, init_vel, pv_stride, rot_out, vel_out, \
+                 pos_out, B, F, (cudaStream_t)s);                                                                      \
+    }                                                                                                                  \
     auto go = ch == 1 ? imu_launch<CT, 1> : (ch == 4 ? imu_launch<CT, 4> : imu_launch<CT, 2>);                         \
     go(dt, gyro, acc, rot, init_rot, init_stride, gravity3_host, a, Dp, Dv, Dr, Dt, w, init_pos, init_vel, pv_stride,  \
        rot_out, vel_out, pos_out, B, F, (cudaStream_t)s);                                                              \

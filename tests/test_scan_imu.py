@@ -128,6 +128,49 @@ def test_imu_module_gpu(golden_scan):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dt_", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("B,F", [(3, 2), (5, 254), (4, 256), (7, 258), (2, 1000), (3, 10_000), (2, 777)])
+def test_imu_tma_staged_kernel_matches_register_kernel(dt_, B, F):
+    """csrc/scan.cu imu_predict_tma_kernel (samples through a TMA-fed shared-memory ring, bulk stores) against
+    imu_integrate_kernel: same arithmetic in the same order, so the outputs are compared bit for bit; lengths below, at and
+    above the tile, several tiles, with initial states; F = 777 (rows not 16-byte multiples) must fall back and still agree.
+    The fp64 result is also checked against the oracle."""
+    import ctypes
+    from pypose_b200 import _C
+    torch.manual_seed(F + B)
+    dt = (0.004 + 0.002 * torch.rand(B, F, 1, dtype=dt_, device="cuda"))
+    gyro = 0.3 * torch.randn(B, F, 3, dtype=dt_, device="cuda")
+    acc = torch.randn(B, F, 3, dtype=dt_, device="cuda") + torch.tensor([0, 0, 9.81], dtype=dt_, device="cuda")
+    init = {"pos": torch.randn(B, 1, 3, dtype=dt_, device="cuda"), "rot": pp.randn_SO3(B, 1, dtype=dt_, device="cuda"),
+            "vel": torch.randn(B, 1, 3, dtype=dt_, device="cuda")}
+    mode = _C.lib().b200_imu_tma_mode
+    mode.restype, mode.argtypes = ctypes.c_int, [ctypes.c_int]
+    prev = mode(-1)
+    outs = {}
+    try:
+        for m in (0, 1):
+            mode(m)
+            imu = pp.module.IMUPreintegrator(prop_cov=False, reset=True).to(dt_).cuda()
+            o = imu(dt, gyro, acc, init_state=init)
+            outs[m] = {k: (o[k].tensor() if hasattr(o[k], "tensor") else o[k]).clone() for k in ("rot", "vel", "pos")}
+    finally:
+        mode(prev)
+    for k in ("rot", "vel", "pos"):
+        assert torch.isfinite(outs[1][k]).all()
+        assert torch.equal(outs[0][k], outs[1][k]), (k, (outs[0][k] - outs[1][k]).abs().max().item())
+    if dt_ == torch.float64:
+        o = S.imu_integrate(dt.cpu().numpy(), gyro.cpu().numpy(), acc.cpu().numpy(), init_rot=init["rot"].tensor().cpu().numpy())
+        Dp, Dv, Dr, Dt = o[1], o[2], o[3], o[4]
+        R0 = init["rot"].tensor().cpu().numpy().reshape(B, 1, 4).repeat(F, 1).reshape(-1, 4)
+        rot_ref = O.mul("SO3", R0, Dr.reshape(-1, 4))
+        d = O.log("SO3", O.mul("SO3", O.inv("SO3", rot_ref), outs[1]["rot"].cpu().numpy().reshape(-1, 4)))
+        assert np.abs(d).max() <= 1e-10
+        v0 = init["vel"].cpu().numpy()
+        vel_ref = v0 + O.act("SO3", R0, Dv.reshape(-1, 3)).reshape(B, F, 3)
+        assert np.abs(outs[1]["vel"].cpu().numpy() - vel_ref).max() <= 1e-10 * (1 + np.abs(vel_ref).max())
+
+
+@pytest.mark.gpu
 def test_imu_config4_size_vs_oracle_subset():
     """BASELINE.json configs[3]: 1e3 trajectories x 1e4 samples, fp64; the first 4 trajectories are
     checked against the oracle (rot via Log(a^-1 b) <= 1e-9, vel/pos relative 1e-9)."""
