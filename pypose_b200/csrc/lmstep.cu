@@ -745,6 +745,20 @@ static int staged_mode() {
   }
   return g_staged_mode;
 }
+// lanes per camera of the register-fed kernel: 0 = by row count (32 for long lists, else 8); A/B knob (b200_lm_reproj_lanes)
+static int g_reproj_lanes = 0;
+template <typename T, int LPC, typename... A>
+static void launch_reproj_trial(int retry, long long ncam, cudaStream_t s, const T* poses, const T* pts, const T* pix,
+                                const int* seg, T* H, T* g, T* Pt, double* ws, double* st, const LmCtl& k, const HostOut& ho,
+                                T scale, T dmin, T dmax, int robust, T delta) {
+  const unsigned grid = lm_grid(ncam, kLmThreads / LPC);
+  if (!retry)
+    reproj_trial_kernel<T, LPC, false><<<grid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, Pt, ws, st, k, ho, scale, dmin,
+                                                                   dmax, robust, delta, (int)ncam);
+  else
+    reproj_trial_kernel<T, LPC, true><<<grid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, Pt, ws, st, k, ho, scale, dmin,
+                                                                  dmax, robust, delta, (int)ncam);
+}
 // dynamic shared memory above 48 KB needs the opt-in attribute, once per device and kernel
 template <typename T> static int staged_prepare() {
   if (Staged<T>::kBytes <= 48 * 1024) return 0;
@@ -766,6 +780,11 @@ template <typename T> static int staged_prepare() {
 
 using namespace b200pose;
 
+B200_EXPORT int b200_lm_reproj_lanes(int lanes) {
+  const int prev = g_reproj_lanes;
+  if (lanes == 0 || lanes == 8 || lanes == 16 || lanes == 32) g_reproj_lanes = lanes;
+  return prev;
+}
 B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
   const int prev = staged_mode();
   if (mode >= 0) g_staged_mode = mode;
@@ -783,7 +802,6 @@ B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
     const LmCtl k = make_ctl(ctl);                                                                                    \
     const HostOut ho = make_host_out(host_out, seq);                                                                  \
     const bool wide = rows >= 384 * ncam;                  /* lanes per camera: 32 for long lists, else 8 */          \
-    const unsigned wgrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);                                    \
     (void)ws1;                                                                                                        \
     const int staged = staged_mode();                                                                                 \
     if ((staged == 2 || (staged == 1 && wide)) && ((((uintptr_t)pts) | ((uintptr_t)pix)) & 15) == 0) {               \
@@ -798,22 +816,15 @@ B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
         reproj_trial_staged_kernel<CT, true><<<sgrid, kLmThreads, Staged<CT>::kBytes, s>>>(                           \
             poses, pts, pix, seg, H, g, P_trial, ws0, st, k, ho, (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta,    \
             (int)ncam, rows);                                                                                         \
-    } else if (wide && !retry)                                                                                               \
-      reproj_trial_kernel<CT, 32, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st,   \
-                                                                      k, ho, (CT)scale, (CT)dmin, (CT)dmax, robust,   \
-                                                                      (CT)delta, (int)ncam);                          \
-    else if (wide)                                                                                                    \
-      reproj_trial_kernel<CT, 32, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st, k, \
-                                                                     ho, (CT)scale, (CT)dmin, (CT)dmax, robust,       \
-                                                                     (CT)delta, (int)ncam);                           \
-    else if (!retry)                                                                                                  \
-      reproj_trial_kernel<CT, 8, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st, k, \
-                                                                     ho, (CT)scale, (CT)dmin, (CT)dmax, robust,       \
-                                                                     (CT)delta, (int)ncam);                           \
-    else                                                                                                              \
-      reproj_trial_kernel<CT, 8, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P_trial, ws0, st, k,   \
-                                                                    ho, (CT)scale, (CT)dmin, (CT)dmax, robust,        \
-                                                                    (CT)delta, (int)ncam);                            \
+    } else {                                                                                                          \
+      const int lanes = g_reproj_lanes ? g_reproj_lanes : (wide ? 32 : 8);                                            \
+      if (lanes == 32) launch_reproj_trial<CT, 32>(retry, ncam, s, poses, pts, pix, seg, H, g, P_trial, ws0, st, k, ho, \
+                                                   (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta);                 \
+      else if (lanes == 16) launch_reproj_trial<CT, 16>(retry, ncam, s, poses, pts, pix, seg, H, g, P_trial, ws0, st, \
+                                                        k, ho, (CT)scale, (CT)dmin, (CT)dmax, robust, (CT)delta);     \
+      else launch_reproj_trial<CT, 8>(retry, ncam, s, poses, pts, pix, seg, H, g, P_trial, ws0, st, k, ho, (CT)scale, \
+                                      (CT)dmin, (CT)dmax, robust, (CT)delta);                                         \
+    }                                                                                                                 \
     lm_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(st, P_trial, poses, ncam * 7);          \
     return finish_step(host_out, seq, s);                                                                             \
   }                                                                                                                   \

@@ -72,23 +72,86 @@ __device__ __forceinline__ Elem<T> block_exclusive(const Elem<T>& mine, Elem<T>&
 // ------------------------------------------------------------------------------------------------
 // generic group cumprod
 // ------------------------------------------------------------------------------------------------
+// Tile staging.  A thread owns CH consecutive rows (CH * D words); read straight from global memory, every load
+// instruction of a warp touches 32 different 128-byte lines — r2g measured 79 us for the three launches at L = 1e6 (0.11 of
+// the HBM peak), the LSU wavefront count, not the bytes, set the time.  The tile therefore goes through shared memory:
+// coalesced 16-byte (or 4/8-byte, when the tile is not 16-byte aligned) global accesses, and each thread's CH * D words sit
+// at stride CH * D + 1 words — odd, so the per-thread reads and writes are bank-conflict free.
+template <typename T, int D, int CH> struct TileSmem {
+  static constexpr int PER = CH * D;                       // words owned by one thread
+  static constexpr int STRIDE = PER + 1;
+  static constexpr int WORDS = kScanThreads * STRIDE;
+};
+template <typename T, int D, int CH>
+__device__ __forceinline__ void tile_load(const T* __restrict__ src, int words, T* __restrict__ sm) {
+  constexpr int PER = TileSmem<T, D, CH>::PER, EV = 16 / (int)sizeof(T);
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int nv = words / EV;
+    const float4* v4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 4
+    for (int v = threadIdx.x; v < nv; v += kScanThreads) {
+      const float4 x = v4[v];
+      const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+      for (int k = 0; k < EV; ++k) {
+        const int w = v * EV + k;
+        sm[w + w / PER] = e[k];
+      }
+    }
+    for (int w = nv * EV + threadIdx.x; w < words; w += kScanThreads) sm[w + w / PER] = src[w];
+  } else {
+#pragma unroll 8
+    for (int w = threadIdx.x; w < words; w += kScanThreads) sm[w + w / PER] = src[w];
+  }
+  __syncthreads();
+}
+template <typename T, int D, int CH>
+__device__ __forceinline__ void tile_store(T* __restrict__ dst, int words, const T* __restrict__ sm) {
+  constexpr int PER = TileSmem<T, D, CH>::PER, EV = 16 / (int)sizeof(T);
+  __syncthreads();
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int nv = words / EV;
+    float4* v4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+    for (int v = threadIdx.x; v < nv; v += kScanThreads) {
+      float4 x;
+      T* e = reinterpret_cast<T*>(&x);
+#pragma unroll
+      for (int k = 0; k < EV; ++k) {
+        const int w = v * EV + k;
+        e[k] = sm[w + w / PER];
+      }
+      v4[v] = x;
+    }
+    for (int w = nv * EV + threadIdx.x; w < words; w += kScanThreads) dst[w] = sm[w + w / PER];
+  } else {
+#pragma unroll 8
+    for (int w = threadIdx.x; w < words; w += kScanThreads) dst[w] = sm[w + w / PER];
+  }
+}
+
 template <class G, typename T, bool LEFT, int CH>
 __global__ void __launch_bounds__(kScanThreads) cumprod_kernel(const T* __restrict__ in, T* __restrict__ out, long long L) {
+  using TS = TileSmem<T, G::D, CH>;
   __shared__ T sh[(kScanThreads / 32) * 8];
+  __shared__ __align__(16) T tile[TS::WORDS];
   const T* src = in + (long long)blockIdx.x * L * G::D;
   T* dst = out + (long long)blockIdx.x * L * G::D;
   Elem<T> carry = elem_identity<T>();
   constexpr long long TILE = (long long)kScanThreads * CH;
+  const int first = threadIdx.x * CH;
+  T* mine = tile + threadIdx.x * TS::STRIDE;
   for (long long base = 0; base < L; base += TILE) {
-    const long long first = base + (long long)threadIdx.x * CH;
+    const int rows = (int)(L - base < TILE ? L - base : TILE);
+    tile_load<T, G::D, CH>(src + base * G::D, rows * G::D, tile);        // coalesced; see TileSmem
     Elem<T> loc[CH];
     Elem<T> run = elem_identity<T>();
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      if (first + c < L) {
+      if (first + c < rows) {
         T row[G::D];
 #pragma unroll
-        for (int k = 0; k < G::D; ++k) row[k] = src[(first + c) * G::D + k];
+        for (int k = 0; k < G::D; ++k) row[k] = mine[c * G::D + k];
         run = combine<G, T, LEFT>(run, load_elem<G, T>(row));
       }
       loc[c] = run;
@@ -97,13 +160,15 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_kernel(const T* __restri
     Elem<T> pre = combine<G, T, LEFT>(carry, block_exclusive<G, T, LEFT>(run, total, sh));
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      if (first + c < L) {
+      if (first + c < rows) {
         T row[G::D];
         store_elem<G, T>(row, combine<G, T, LEFT>(pre, loc[c]));
 #pragma unroll
-        for (int k = 0; k < G::D; ++k) dst[(first + c) * G::D + k] = row[k];
+        for (int k = 0; k < G::D; ++k) mine[c * G::D + k] = row[k];
       }
     }
+    tile_store<T, G::D, CH>(dst + base * G::D, rows * G::D, tile);
+    __syncthreads();                      // the next tile overwrites the staging buffer
     carry = combine<G, T, LEFT>(carry, total);
   }
 }
@@ -122,20 +187,25 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_kernel(const T* __restri
 template <class G, typename T, bool LEFT, int CH>
 __global__ void __launch_bounds__(kScanThreads) cumprod_tile_reduce_kernel(const T* __restrict__ in, long long L, int nt,
                                                                             T* __restrict__ agg) {
+  using TS = TileSmem<T, G::D, CH>;
   __shared__ T sh[(kScanThreads / 32) * 8];
+  __shared__ __align__(16) T tile[TS::WORDS];
   const long long gid = blockIdx.x;
   const long long b = gid / nt;
   const int t = (int)(gid - b * nt);
-  const T* src = in + b * L * G::D;
   constexpr long long TILE = (long long)kScanThreads * CH;
-  const long long first = (long long)t * TILE + (long long)threadIdx.x * CH;
+  const long long row0 = (long long)t * TILE;
+  const int rows = (int)(L - row0 < TILE ? L - row0 : TILE);
+  tile_load<T, G::D, CH>(in + (b * L + row0) * G::D, rows * G::D, tile);
+  const int first = threadIdx.x * CH;
+  const T* mine = tile + threadIdx.x * TS::STRIDE;
   Elem<T> run = elem_identity<T>();
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
-    if (first + c < L) {
+    if (first + c < rows) {
       T row[G::D];
 #pragma unroll
-      for (int k = 0; k < G::D; ++k) row[k] = src[(first + c) * G::D + k];
+      for (int k = 0; k < G::D; ++k) row[k] = mine[c * G::D + k];
       run = combine<G, T, LEFT>(run, load_elem<G, T>(row));
     }
   }
@@ -161,22 +231,26 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_tile_prefix_kernel(const
 template <class G, typename T, bool LEFT, int CH>
 __global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                            long long L, int nt, const T* __restrict__ pre) {
+  using TS = TileSmem<T, G::D, CH>;
   __shared__ T sh[(kScanThreads / 32) * 8];
+  __shared__ __align__(16) T tile[TS::WORDS];
   const long long gid = blockIdx.x;
   const long long b = gid / nt;
   const int t = (int)(gid - b * nt);
-  const T* src = in + b * L * G::D;
-  T* dst = out + b * L * G::D;
   constexpr long long TILE = (long long)kScanThreads * CH;
-  const long long first = (long long)t * TILE + (long long)threadIdx.x * CH;
+  const long long row0 = (long long)t * TILE;
+  const int rows = (int)(L - row0 < TILE ? L - row0 : TILE);
+  tile_load<T, G::D, CH>(in + (b * L + row0) * G::D, rows * G::D, tile);
+  const int first = threadIdx.x * CH;
+  T* mine = tile + threadIdx.x * TS::STRIDE;
   Elem<T> loc[CH];
   Elem<T> run = elem_identity<T>();
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
-    if (first + c < L) {
+    if (first + c < rows) {
       T row[G::D];
 #pragma unroll
-      for (int k = 0; k < G::D; ++k) row[k] = src[(first + c) * G::D + k];
+      for (int k = 0; k < G::D; ++k) row[k] = mine[c * G::D + k];
       run = combine<G, T, LEFT>(run, load_elem<G, T>(row));
     }
     loc[c] = run;
@@ -186,13 +260,14 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const 
   const Elem<T> pfx = combine<G, T, LEFT>(load_elem<Sim3g, T>(pre + gid * 8), pre_thread);
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
-    if (first + c < L) {
+    if (first + c < rows) {
       T row[G::D];
       store_elem<G, T>(row, combine<G, T, LEFT>(pfx, loc[c]));
 #pragma unroll
-      for (int k = 0; k < G::D; ++k) dst[(first + c) * G::D + k] = row[k];
+      for (int k = 0; k < G::D; ++k) mine[c * G::D + k] = row[k];      // own words only: no hazard with other threads
     }
   }
+  tile_store<T, G::D, CH>(out + (b * L + row0) * G::D, rows * G::D, tile);
 }
 
 template <typename T> constexpr int scan_ch() { return sizeof(T) == 8 ? 4 : 8; }
