@@ -85,20 +85,37 @@ template <typename T, int D, int CH> struct TileSmem {
 template <typename T, int D, int CH>
 __device__ __forceinline__ void tile_load(const T* __restrict__ src, int words, T* __restrict__ sm) {
   constexpr int PER = TileSmem<T, D, CH>::PER, EV = 16 / (int)sizeof(T);
+  constexpr int NV = PER / EV;                               // 16-byte vectors per thread in a full tile (= 2 D)
+  static_assert(PER % EV == 0, "a thread's rows are a whole number of 16-byte vectors");
   if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    const int nv = words / EV;
     const float4* v4 = reinterpret_cast<const float4*>(src);
-#pragma unroll 4
-    for (int v = threadIdx.x; v < nv; v += kScanThreads) {
-      const float4 x = v4[v];
-      const T* e = reinterpret_cast<const T*>(&x);
+    if (words == kScanThreads * PER) {                       // full tile: every load in flight before the first store
+      float4 x[NV];
 #pragma unroll
-      for (int k = 0; k < EV; ++k) {
-        const int w = v * EV + k;
-        sm[w + w / PER] = e[k];
+      for (int j = 0; j < NV; ++j) x[j] = v4[threadIdx.x + j * kScanThreads];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const T* e = reinterpret_cast<const T*>(&x[j]);
+#pragma unroll
+        for (int k = 0; k < EV; ++k) {
+          const int w = (threadIdx.x + j * kScanThreads) * EV + k;
+          sm[w + w / PER] = e[k];
+        }
       }
+    } else {
+      const int nv = words / EV;
+#pragma unroll 4
+      for (int v = threadIdx.x; v < nv; v += kScanThreads) {
+        const float4 x = v4[v];
+        const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+        for (int k = 0; k < EV; ++k) {
+          const int w = v * EV + k;
+          sm[w + w / PER] = e[k];
+        }
+      }
+      for (int w = nv * EV + threadIdx.x; w < words; w += kScanThreads) sm[w + w / PER] = src[w];
     }
-    for (int w = nv * EV + threadIdx.x; w < words; w += kScanThreads) sm[w + w / PER] = src[w];
   } else {
 #pragma unroll 8
     for (int w = threadIdx.x; w < words; w += kScanThreads) sm[w + w / PER] = src[w];
@@ -213,19 +230,48 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_tile_reduce_kernel(const
   block_exclusive<G, T, LEFT>(run, total, sh);
   if (threadIdx.x == 0) store_elem<Sim3g, T>(agg + gid * 8, total);
 }
-// exclusive scan of the nt tile aggregates of one sequence (one CTA per sequence, carry across rounds)
+// exclusive scan of the nt tile aggregates of one sequence: one CTA of kPrefixThreads per sequence, one aggregate per
+// thread and round (carry across rounds), two levels of warp-shuffle scans.  r2h ncu: the 128-thread version needed 8
+// rounds of a block scan for the 977 tiles of L = 1e6 and took 17.9 us — longer than either pass over the rows.
+constexpr int kPrefixThreads = 1024;
 template <class G, typename T, bool LEFT>
-__global__ void __launch_bounds__(kScanThreads) cumprod_tile_prefix_kernel(const T* __restrict__ agg, T* __restrict__ pre, int nt) {
-  __shared__ T sh[(kScanThreads / 32) * 8];
+__global__ void __launch_bounds__(kPrefixThreads) cumprod_tile_prefix_kernel(const T* __restrict__ agg, T* __restrict__ pre, int nt) {
+  constexpr int NW = kPrefixThreads / 32;
+  __shared__ T sh_tot[NW * 8];
+  __shared__ T sh_pre[(NW + 1) * 8];
   const long long b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Elem<T> carry = elem_identity<T>();
-  for (int base = 0; base < nt; base += kScanThreads) {
+  for (int base = 0; base < nt; base += kPrefixThreads) {
     const int t = base + threadIdx.x;
-    const Elem<T> mine = t < nt ? load_elem<Sim3g, T>(agg + (b * nt + t) * 8) : elem_identity<T>();
-    Elem<T> total;
-    const Elem<T> excl = block_exclusive<G, T, LEFT>(mine, total, sh);
-    if (t < nt) store_elem<Sim3g, T>(pre + (b * nt + t) * 8, combine<G, T, LEFT>(carry, excl));
+    Elem<T> inc = t < nt ? load_elem<Sim3g, T>(agg + (b * nt + t) * 8) : elem_identity<T>();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Elem<T> up = elem_shfl_up(inc, o);
+      if (lane >= o) inc = combine<G, T, LEFT>(up, inc);
+    }
+    Elem<T> excl = elem_shfl_up(inc, 1);
+    if (lane == 0) excl = elem_identity<T>();
+    if (lane == 31) store_elem<Sim3g, T>(sh_tot + warp * 8, inc);
+    __syncthreads();
+    if (warp == 0) {                                   // scan of the NW (= 32) warp totals by one warp
+      Elem<T> w = load_elem<Sim3g, T>(sh_tot + lane * 8);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        Elem<T> up = elem_shfl_up(w, o);
+        if (lane >= o) w = combine<G, T, LEFT>(up, w);
+      }
+      Elem<T> wex = elem_shfl_up(w, 1);
+      if (lane == 0) wex = elem_identity<T>();
+      store_elem<Sim3g, T>(sh_pre + lane * 8, wex);
+      if (lane == 31) store_elem<Sim3g, T>(sh_pre + NW * 8, w);
+    }
+    __syncthreads();
+    const Elem<T> wpre = load_elem<Sim3g, T>(sh_pre + warp * 8);
+    const Elem<T> total = load_elem<Sim3g, T>(sh_pre + NW * 8);
+    if (t < nt) store_elem<Sim3g, T>(pre + (b * nt + t) * 8, combine<G, T, LEFT>(carry, combine<G, T, LEFT>(wpre, excl)));
     carry = combine<G, T, LEFT>(carry, total);
+    __syncthreads();                                   // sh_tot / sh_pre are rewritten by the next round
   }
 }
 template <class G, typename T, bool LEFT, int CH>
@@ -291,11 +337,11 @@ int launch_cumprod_lb(const T* in, T* out, long long B, long long L, int left, v
   T* pre = agg + tiles * 8;
   if (left) {
     cumprod_tile_reduce_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
-    cumprod_tile_prefix_kernel<G, T, true><<<(unsigned)B, kScanThreads, 0, s>>>(agg, pre, (int)nt);
+    cumprod_tile_prefix_kernel<G, T, true><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
     cumprod_tile_apply_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
   } else {
     cumprod_tile_reduce_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
-    cumprod_tile_prefix_kernel<G, T, false><<<(unsigned)B, kScanThreads, 0, s>>>(agg, pre, (int)nt);
+    cumprod_tile_prefix_kernel<G, T, false><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
     cumprod_tile_apply_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
   }
   return (int)cudaGetLastError();
