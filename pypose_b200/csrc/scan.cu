@@ -96,11 +96,10 @@ __device__ __forceinline__ void tile_load(const T* __restrict__ src, int words, 
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const T* e = reinterpret_cast<const T*>(&x[j]);
+        const int v = threadIdx.x + j * kScanThreads;             // a vector never straddles two threads' words
+        T* d = sm + v * EV + v / NV;
 #pragma unroll
-        for (int k = 0; k < EV; ++k) {
-          const int w = (threadIdx.x + j * kScanThreads) * EV + k;
-          sm[w + w / PER] = e[k];
-        }
+        for (int k = 0; k < EV; ++k) d[k] = e[k];
       }
     } else {
       const int nv = words / EV;
@@ -125,8 +124,21 @@ __device__ __forceinline__ void tile_load(const T* __restrict__ src, int words, 
 template <typename T, int D, int CH>
 __device__ __forceinline__ void tile_store(T* __restrict__ dst, int words, const T* __restrict__ sm) {
   constexpr int PER = TileSmem<T, D, CH>::PER, EV = 16 / (int)sizeof(T);
+  constexpr int NV = PER / EV;
   __syncthreads();
-  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && words == kScanThreads * PER) {
+    float4* v4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int v = threadIdx.x + j * kScanThreads;
+      const T* d = sm + v * EV + v / NV;
+      float4 x;
+      T* e = reinterpret_cast<T*>(&x);
+#pragma unroll
+      for (int k = 0; k < EV; ++k) e[k] = d[k];
+      v4[v] = x;
+    }
+  } else if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const int nv = words / EV;
     float4* v4 = reinterpret_cast<float4*>(dst);
 #pragma unroll 4
@@ -274,7 +286,11 @@ __global__ void __launch_bounds__(kPrefixThreads) cumprod_tile_prefix_kernel(con
     __syncthreads();                                   // sh_tot / sh_pre are rewritten by the next round
   }
 }
-template <class G, typename T, bool LEFT, int CH>
+// FUSED: `pre` holds the tile AGGREGATES and every CTA multiplies the aggregates of the tiles before its own itself (at
+// most kFusedTiles of them: <= 8 per thread + one block reduction, ~a quarter of the tile's own work) — the separate prefix
+// launch was 11 us of a 44 us scan at L = 1e6 (r2j ncu).  Longer sequences keep the three-launch form.
+constexpr int kFusedTiles = 1024;
+template <class G, typename T, bool LEFT, int CH, bool FUSED>
 __global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                            long long L, int nt, const T* __restrict__ pre) {
   using TS = TileSmem<T, G::D, CH>;
@@ -286,6 +302,26 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const 
   constexpr long long TILE = (long long)kScanThreads * CH;
   const long long row0 = (long long)t * TILE;
   const int rows = (int)(L - row0 < TILE ? L - row0 : TILE);
+  Elem<T> tile_pfx;
+  if (FUSED) {
+    const T* a = pre + b * nt * 8;
+    const int c = (t + kScanThreads - 1) / kScanThreads;          // consecutive aggregates per thread (<= 8)
+    const int lo = threadIdx.x * c;
+    Elem<T> part = elem_identity<T>();
+    for (int j0 = 0; j0 < c; j0 += 4) {                           // 4 aggregates in flight
+      Elem<T> e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = lo + j0 + u;
+        e[u] = (j0 + u < c && j < t) ? load_elem<Sim3g, T>(a + (long long)j * 8) : elem_identity<T>();
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) part = combine<G, T, LEFT>(part, e[u]);
+    }
+    block_exclusive<G, T, LEFT>(part, tile_pfx, sh);               // total = ordered product of all parts
+  } else {
+    tile_pfx = load_elem<Sim3g, T>(pre + gid * 8);
+  }
   tile_load<T, G::D, CH>(in + (b * L + row0) * G::D, rows * G::D, tile);
   const int first = threadIdx.x * CH;
   T* mine = tile + threadIdx.x * TS::STRIDE;
@@ -303,7 +339,7 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const 
   }
   Elem<T> total;
   const Elem<T> pre_thread = block_exclusive<G, T, LEFT>(run, total, sh);
-  const Elem<T> pfx = combine<G, T, LEFT>(load_elem<Sim3g, T>(pre + gid * 8), pre_thread);
+  const Elem<T> pfx = combine<G, T, LEFT>(tile_pfx, pre_thread);
 #pragma unroll
   for (int c = 0; c < CH; ++c) {
     if (first + c < rows) {
@@ -335,14 +371,23 @@ int launch_cumprod_lb(const T* in, T* out, long long B, long long L, int left, v
   const long long nt = scan_tiles(L, (int)sizeof(T)), tiles = B * nt;
   T* agg = reinterpret_cast<T*>(ws);
   T* pre = agg + tiles * 8;
+  const bool fused = nt <= kFusedTiles;
   if (left) {
     cumprod_tile_reduce_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
-    cumprod_tile_prefix_kernel<G, T, true><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
-    cumprod_tile_apply_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
+    if (fused) {
+      cumprod_tile_apply_kernel<G, T, true, CH, true><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, agg);
+    } else {
+      cumprod_tile_prefix_kernel<G, T, true><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
+      cumprod_tile_apply_kernel<G, T, true, CH, false><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
+    }
   } else {
     cumprod_tile_reduce_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
-    cumprod_tile_prefix_kernel<G, T, false><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
-    cumprod_tile_apply_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
+    if (fused) {
+      cumprod_tile_apply_kernel<G, T, false, CH, true><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, agg);
+    } else {
+      cumprod_tile_prefix_kernel<G, T, false><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
+      cumprod_tile_apply_kernel<G, T, false, CH, false><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
+    }
   }
   return (int)cudaGetLastError();
 }
