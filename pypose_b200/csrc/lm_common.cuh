@@ -50,8 +50,9 @@ __device__ __forceinline__ bool reduce_sums(double (&v)[NS], double* ws) {
   if (is_last) {
     __threadfence();
     // Fixed-order fold by the whole CTA: thread-strided partial sums with the loads of kFold CTAs' partials issued before
-    // the first add (r2h ncu: the one-warp, one-load-at-a-time loop this replaces walked grid/32 dependent L2 round trips —
-    // ~10 us of a 30 us kernel at 1184 CTAs), then the same shuffle tree and a fixed-order sum of the warp results.
+    // the first add, then the shuffle tree and a fixed-order sum of the warp results.  (The one-warp, one-load-at-a-time loop
+    // this replaces walked grid/32 dependent L2 round trips; measured r2h -> r2j the change is worth ~1 us per launch at
+    // 625-1184 CTAs — the kernels that end with this reduction are bound elsewhere.)
     constexpr int kFold = 4;
     double t[NS];
 #pragma unroll
@@ -91,6 +92,13 @@ __device__ __forceinline__ bool reduce_sums(double (&v)[NS], double* ws) {
     }
   }
   return false;
+}
+
+// (n, 6) work vectors of the PCG entry points are accessed as 8-byte (float) / 16-byte (double) pairs
+constexpr int kMisaligned = 716;                      // cudaErrorMisalignedAddress
+template <typename T, typename... P> static inline bool pairs_aligned(const P*... ptrs) {
+  const uintptr_t bits = (0 | ... | reinterpret_cast<uintptr_t>(ptrs));
+  return (bits & (2 * sizeof(T) - 1)) == 0;
 }
 
 template <typename T> __device__ __forceinline__ Elem<T> load_se3(const T* p) { return load_elem<SE3g, T>(p); }

@@ -37,13 +37,24 @@ __device__ __forceinline__ void cg_after_update(double* cg, double rr, double it
   else if (cg[CG_SINCE] >= cg[CG_PATIENCE]) cg[CG_DONE] = 3.0;
 }
 
+// (n, 6) vectors are read and written as three 8-byte (float) / 16-byte (double) pairs: a node's six values start at a
+// multiple of 24 / 48 bytes, so the arrays only have to be 8- / 16-byte aligned (checked at the entry points).  Scalar
+// accesses cost one LSU wavefront per touched line and instruction — 36 per warp and vector instead of 18 (r2j: the PCG
+// kernels are LSU-bound, not DRAM-bound).
+template <typename T> struct Pair6;
+template <> struct Pair6<float> { using type = float2; };
+template <> struct Pair6<double> { using type = double2; };
 template <typename T> __device__ __forceinline__ void ld6(const T* p, long long i, T (&v)[6]) {
+  using P = typename Pair6<T>::type;
+  const P* q = reinterpret_cast<const P*>(p + i * 6);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) v[k] = p[i * 6 + k];
+  for (int k = 0; k < 3; ++k) { const P t = q[k]; v[2 * k] = t.x; v[2 * k + 1] = t.y; }
 }
 template <typename T> __device__ __forceinline__ void st6(T* p, long long i, const T (&v)[6]) {
+  using P = typename Pair6<T>::type;
+  P* q = reinterpret_cast<P*>(p + i * 6);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) p[i * 6 + k] = v[k];
+  for (int k = 0; k < 3; ++k) { P t; t.x = v[2 * k]; t.y = v[2 * k + 1]; q[k] = t; }
 }
 template <typename T> __device__ __forceinline__ void sym6_mv_packed(const T* a21, const T (&x)[6], T (&y)[6]) {
   T A[6][6];
@@ -161,13 +172,24 @@ __global__ void __launch_bounds__(kLmThreads) cg_update_kernel(const T* __restri
   }
   const T alpha = (T)(cg[par] / pq);
   double acc[2] = {0.0, 0.0};
-  for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kLmThreads) {
+  // The 21-word preconditioner blocks of a warp's 32 consecutive nodes are 2688 contiguous bytes: the warp copies them
+  // with 21 coalesced loads into shared memory (one wavefront each) and every lane reads its block from there (stride 21
+  // words: conflict-free) — read per lane straight from global memory, each of the 21 load instructions touched 21 lines.
+  __shared__ T sM[kLmThreads / 32][32 * 21];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long base = (long long)blockIdx.x * kLmThreads + warp * 32; base < n; base += (long long)gridDim.x * kLmThreads) {
+    const long long i = base + lane;
+    const int words = (int)(n - base < 32 ? n - base : 32) * 21;
+    __syncwarp();
+    for (int w = lane; w < words; w += 32) sM[warp][w] = Minv[base * 21 + w];
+    __syncwarp();
+    if (i >= n) continue;
     T pv[6], qv[6], xv[6], rv[6], zv[6];
     ld6(p, i, pv); ld6(q, i, qv); ld6(x, i, xv); ld6(r, i, rv);
     if (save) st6(xbest, i, xv);
 #pragma unroll
     for (int k = 0; k < 6; ++k) { xv[k] += alpha * pv[k]; rv[k] -= alpha * qv[k]; }
-    sym6_mv_packed(Minv + i * 21, rv, zv);
+    sym6_mv_packed(&sM[warp][lane * 21], rv, zv);
     st6(x, i, xv); st6(r, i, rv); st6(z, i, zv);
 #pragma unroll
     for (int k = 0; k < 6; ++k) { acc[0] += (double)rv[k] * (double)zv[k]; acc[1] += (double)rv[k] * (double)rv[k]; }
@@ -670,6 +692,7 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
                                         long long iters, const unsigned long long* bases, int rank, int world,        \
                                         long long stage, long long result, long long epoch, unsigned* tickets,        \
                                         long long n, void* stream) {                                                  \
+    if (!pairs_aligned<CT>(g, x, r, z, p, q, xbest)) return kMisaligned;                                              \
     return pgo_pcg_run<CT, false>(M, ei, ej, E, Minv, extra, g, x, r, z, p, q, xbest, cg, ws, tol, maxiter,           \
                                   first_iter, iters, n, (cudaStream_t)stream,                                         \
                                   make_pcg_comm(bases, rank, world, stage, result, epoch, tickets));                  \
@@ -708,6 +731,7 @@ static int ba_pcg_run(const CT* Y4, const CT* poses, const int* pidx, const int*
                                        const unsigned long long* bases, int rank, int world, long long stage,         \
                                        long long result, long long epoch, unsigned* tickets, long long n,             \
                                        void* stream) {                                                                \
+    if (!pairs_aligned<CT>(bneg, x, r, z, p, q, xbest)) return kMisaligned;                                           \
     return ba_pcg_run<CT>(Y4, poses, pidx, cseg, split, tpi, m, Y4p, cidx_p, pptr, Hc, Hpinv, Minv, bneg, x, r, z, p, \
                           q, t, part, xbest, cg, ws, tol, maxiter, P, first_iter, iters, n, (cudaStream_t)stream,     \
                           make_pcg_comm(bases, rank, world, stage, result, epoch, tickets));                          \

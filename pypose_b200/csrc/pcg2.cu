@@ -40,9 +40,15 @@ template <typename T> __device__ __forceinline__ void ld_block24(const T* __rest
   }
   sym6_unpack(a, A);
 }
+template <typename T> struct Pair6g;
+template <> struct Pair6g<float> { using type = float2; };
+template <> struct Pair6g<double> { using type = double2; };
+// gather of one node's six values as three 8- / 16-byte pairs (see pcg.cu ld6): half the LSU wavefronts of scalar loads
 template <typename T> __device__ __forceinline__ void ld6g(const T* __restrict__ p, long long i, T (&v)[6]) {
+  using P = typename Pair6g<T>::type;
+  const P* q = reinterpret_cast<const P*>(p + i * 6);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) v[k] = __ldg(p + i * 6 + k);
+  for (int k = 0; k < 3; ++k) { const P t = __ldg(q + k); v[2 * k] = t.x; v[2 * k + 1] = t.y; }
 }
 
 // Hd[n] (21) = sum of the node's blocks, g[n] (6) = sum of its signed u   (diagonal of J^T J and J^T R, optimizer.py:642-643,668)
@@ -168,6 +174,7 @@ using namespace b200pose;
                                          CT* xbest, double* cg, double* ws, double tol, long long maxiter,            \
                                          long long first_iter, long long iters, long long n, void* stream) {          \
     if (n <= 0) return 0;                                                                                             \
+    if (!pairs_aligned<CT>(g, x, r, z, p0, p1, q, xbest)) return kMisaligned;                                         \
     cudaStream_t st = (cudaStream_t)stream;                                                                           \
     const unsigned grid = lm_grid(n * kLanes, kLmThreads);                                                            \
     if (first_iter == 0) pcg_launch_init<CT>(Minv, g, x, r, z, q, cg, ws, tol, (double)maxiter, n, st);               \
@@ -183,6 +190,7 @@ using namespace b200pose;
   B200_EXPORT int b200_lm_pgo2_predicted_##SFX(const CT* Mn, const int* nother, const int* nptr, const CT* x,         \
                                                const CT* g, double* ws, long long n, void* stream) {                  \
     if (n <= 0) return 0;                                                                                             \
+    if (!pairs_aligned<CT>(x)) return kMisaligned;                                                                    \
     pgo2_operator_kernel<CT><<<lm_grid(n * kLanes, kLmThreads), kLmThreads, 0, (cudaStream_t)stream>>>(               \
         Mn, nother, nptr, (const CT*)nullptr, x, (const CT*)nullptr, (CT*)nullptr, (CT*)nullptr, g, (double*)nullptr, \
         ws, 1, 1, 0, n);                                                                                              \
