@@ -100,7 +100,9 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that falls out of step must fail the run in minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     return rank, world, local
 
 

@@ -37,7 +37,7 @@ def _time_steps(step_fn, reset_fn, warmup=3, min_ms=MIN_LEG_MS, min_steps=7, max
         for _ in range(run):
             step_fn()
     ts, tot = [], 0.0
-    while len(ts) < min_steps or (tot < min_ms and len(ts) < max_steps):
+    while _all_continue(len(ts) < min_steps or (tot < min_ms and len(ts) < max_steps)):
         reset_fn()
         e0.record()
         for _ in range(run):
@@ -48,6 +48,20 @@ def _time_steps(step_fn, reset_fn, warmup=3, min_ms=MIN_LEG_MS, min_steps=7, max
         tot += ts[-1] * run
     ts.sort()
     return ts[len(ts) // 2], len(ts) * run
+
+
+_WORLD = {"size": 1, "dev": None}
+
+
+def _all_continue(want):
+    """The sharded legs run collectives / peer exchanges inside a step, so every rank has to run the SAME number of timed
+    regions: a rank keeps going as long as any rank still wants to (decided outside the timed region)."""
+    if _WORLD["size"] == 1:
+        return want
+    import torch.distributed as dist
+    t = torch.tensor([1.0 if want else 0.0], device=_WORLD["dev"])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(t.item() > 0)
 
 
 def _time_async(fn, calls=20, repeats=7, graph=False):
@@ -129,6 +143,7 @@ def _reproj_problem(pp, dev, C, M, rank, world, seed, sorted_split):
 def run(args, rank, world, dev, peak):
     import pypose_b200 as pp
     group = True if world > 1 else None
+    _WORLD["size"], _WORLD["dev"] = world, dev
     out = {}
 
     # ---- BASELINE configs[2]: README InvNet, 1e5 SE3 poses per GPU (weak scaling), Constant(1e-4), Cholesky
@@ -285,10 +300,14 @@ def run(args, rank, world, dev, peak):
     # larger than nothing but smaller than L2: the second read of the rows is an L2 hit by design, the first is HBM)
     ms_call, k = _time_steps(lambda: xs.cumprod(dim=1, left=False), lambda: None, warmup=2, min_steps=5)
     ms = _max(_time_async(lambda: xs.cumprod(dim=1, left=False)), world, dev)
+    graph_err = None
     try:
-        ms_graph = _max(_time_async(lambda: xs.cumprod(dim=1, left=False), graph=True), world, dev)
+        ms_graph = _time_async(lambda: xs.cumprod(dim=1, left=False), graph=True)
     except Exception as exc:                                        # noqa: BLE001 — report, keep the eager number
-        ms_graph, graph_err = None, repr(exc)[:120]
+        ms_graph, graph_err = 1e9, repr(exc)[:120]
+    ms_graph = _max(ms_graph, world, dev)                           # every rank takes part, also after a failed capture
+    if ms_graph >= 1e9:
+        ms_graph, graph_err = None, graph_err or "capture failed on another rank"
     out["cumprod_1e6"] = {"melems_per_s": round(world * 1e6 / (ms * 1e-3) / 1e6, 1), "ms": round(ms, 4),
                           "ms_call": round(ms_call, 4), "ms_graph": None if ms_graph is None else round(ms_graph, 4),
                           "timed_steps": k, "scaling": "weak",

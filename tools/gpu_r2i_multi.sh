@@ -5,7 +5,7 @@ OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi topo -m 2>&1 | head -12 > $OUT/${TAG}_topo.log
 timeout 900 python -m pytest tests/test_dist_nccl.py -q -m gpu --tb=short 2>&1 | tail -15 | tee $OUT/${TAG}_pytest_${N}gpu.log
 PORT=$((20000 + RANDOM % 20000))
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
+timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
     bench.py --gpus $N --no-cpu > $OUT/${TAG}_bench_${N}gpu.json 2> $OUT/${TAG}_bench_${N}gpu.err
 tail -3 $OUT/${TAG}_bench_${N}gpu.err
 python - <<PY
