@@ -350,14 +350,15 @@ LM_OPS += [
       ("const int*", "seg", "(ncam+1) offsets of this rank's rows per camera"),
       ("REAL*", "H", "(ncam,21): the owner's rows hold the reduced blocks (kept for retries)"), ("REAL*", "g", "(ncam,6)"),
       ("const unsigned long long*", "bases", "HOST (world) exchange buffers, see b200_comm_open"), ("int", "rank", ""), ("int", "world", ""),
-      ("long long", "part_off", "payload byte offset of the partial blocks: world * ceil(ncam/world) * 27 elements"),
-      ("long long", "pt_off", "payload byte offset of the trial poses: ncam * 7 elements"),
+      ("long long", "part_off", "payload byte offset (16-byte aligned) of the partial blocks: world * ceil(ncam/world) slots of 28 elements"),
+      ("long long", "pt_off", "payload byte offset (16-byte aligned) of the trial poses: ncam slots of 8 elements"),
       ("long long", "epoch0", "count of linearisations so far (incl. this one unless retry)"),
       ("long long", "epoch1", "count of trials so far incl. this one"),
       ("double*", "ws0", "reduction workspace"), ("double*", "ws1", ""), ("double*", "ws2", ""),
       ("double*", "st", "(16) device state, see b200_lm_reproj_step"), ("double*", "host_out", "(16) pinned host memory or NULL"), ("long long", "seq", "see b200_lm_reproj_step"),
       ("const double*", "ctl", "HOST (14), see b200_lm_reproj_step"), ("int", "robust", ""), ("double", "delta", ""),
-      ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", "")],
+      ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", ""),
+      ("long long", "rows", "number of LOCAL observation rows (selects 8 or 32 lanes per camera)")],
      "b200_lm_reproj_step with the observations sharded over `world` GPUs: [H | g] is reduce-scattered to camera owners, "
      "trial poses are all-gathered and the scalar sums exchanged by stores into the peers' buffers (SURVEY.md §8e row 4); "
      "optimizer.py:659-680"),

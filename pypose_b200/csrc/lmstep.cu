@@ -437,29 +437,42 @@ __device__ __forceinline__ bool cta_ticket_last(unsigned* ticket) {     // call 
   return last;
 }
 
-template <typename T>
+// Exchange slots are padded to whole 16-byte vectors: 28 numbers per (source rank, camera) partial block (21 + 6 + pad),
+// 8 per trial pose.  Every remote store is a 16-byte store and a thread fences ONCE, after its last store (r2l: the first
+// version stored 27 scalars per camera from one lane and issued a system-scope fence per camera — the 2-GPU step took 2.4x
+// the 1-GPU step at 1e6 rows).
+constexpr int kPartSlot = 28, kPoseSlot = 8;
+
+// K1p: LPC lanes per camera over the local rows (same loop as reproj_trial_kernel), blocks staged in shared memory, then the
+// CTA copies them to the owners with 16-byte stores.
+template <typename T, int LPC>
 __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
                                                                         const T* __restrict__ pix, const int* __restrict__ seg,
                                                                         Peers P, PeerRegions R, double* ws,
                                                                         unsigned long long epoch, int rk, T rdelta, int ncam) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = kLmThreads / 32;
+  constexpr int cpb = kLmThreads / LPC;
+  constexpr int NV = kPartSlot * (int)sizeof(T) / 16;
+  __shared__ __align__(16) T sP[cpb][kPartSlot];
+  const int sub = threadIdx.x % LPC, slot = threadIdx.x / LPC;
+  const int rounds = (ncam + cpb - 1) / cpb;
   const int q = (ncam + P.world - 1) / P.world;
   double acc[1] = {0.0};
-  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+  for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+    const int c = rd * cpb + slot;
+    const bool valid = c < ncam;
+    const int cc = valid ? c : 0;
     T pr[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)cc * 7 + k];
     const Elem<T> Tc = load_se3(pr);
+    const int b = valid ? seg[cc] : 0, e = valid ? seg[cc + 1] : 0;
     Acc6<T> ac;
     ac.zero();
     T loss = T(0);
-    const int b = seg[c], e = seg[c + 1];
-    for (int k = b + lane; k < e; k += 32) {
-      const long long k0 = k;
+    auto accumulate = [&](const V3<T>& p, T zx, T zy) {
       T rx, ry;
       V3<T> y;
-      reproj_residual(Tc, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1], rx, ry, y);
+      reproj_residual(Tc, p, zx, zy, rx, ry, y);
       T j0[6], j1[6];
       reproj_rows(y, j0, j1);
       T rho, w;
@@ -473,10 +486,23 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
       ac.add_row(j0, rx);
       ac.add_row(j1, ry);
       loss += rho;
+    };
+    int k = b + sub;
+    for (; k + LPC < e; k += 2 * LPC) {
+      const long long k0 = k, k1 = k + LPC;
+      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
+      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
+      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
+      accumulate(p0, z0x, z0y);
+      accumulate(p1, z1x, z1y);
+    }
+    if (k < e) {
+      const long long k0 = k;
+      accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
     }
     Sys6<T> s = ac.finish();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = LPC / 2; o > 0; o >>= 1) {
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
         s.g[a] += __shfl_xor_sync(0xffffffffu, s.g[a], o);
@@ -485,27 +511,36 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
       }
       loss += __shfl_xor_sync(0xffffffffu, loss, o);
     }
-    if (lane == 0) {
-      const int owner = c / q;
-      T* dst = reinterpret_cast<T*>(P.base[owner] + kDataOffset + R.part) + ((long long)P.rank * q + (c - owner * q)) * 27;
+    if (sub == 0) {
       int t = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int bb = a; bb < 6; ++bb) dst[t++] = s.A[a][bb];
+        for (int bb = a; bb < 6; ++bb) sP[slot][t++] = s.A[a][bb];
 #pragma unroll
-      for (int a = 0; a < 6; ++a) dst[21 + a] = s.g[a];
-      acc[0] += (double)loss;
-      __threadfence_system();
+      for (int a = 0; a < 6; ++a) sP[slot][21 + a] = s.g[a];
+      sP[slot][27] = T(0);
+      if (valid) acc[0] += (double)loss;
     }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cpb * NV; j += kLmThreads) {
+      const int sl = j / NV, v = j - sl * NV, cj = rd * cpb + sl;
+      if (cj < ncam) {
+        const int owner = cj / q;
+        char* dst = P.base[owner] + kDataOffset + R.part +
+                    ((long long)P.rank * q + (cj - owner * q)) * (kPartSlot * (long long)sizeof(T)) + v * 16;
+        *reinterpret_cast<float4*>(dst) = reinterpret_cast<const float4*>(&sP[sl][0])[v];
+      }
+    }
+    __syncthreads();                                   // the next round overwrites the staging slots
   }
+  __threadfence_system();                              // this thread's remote stores are ordered before the CTA's ticket
   if (reduce_sums<1>(acc, ws)) {           // thread 0 of the last CTA: every CTA's stores are ordered before its ticket
     for (int r = 0; r < P.world; ++r) comm_scalars(P.base[r], CH_PART, P.rank)[(epoch & 1) * 4] = ws[0];
     comm_signal_all(P, CH_PART, epoch);
   }
 }
 
-// owner: reduce (or, on a retry, reuse) its cameras' blocks, solve, retract, broadcast the trial poses
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) reproj_reduce_solve_push_kernel(const T* __restrict__ poses, T* __restrict__ H,
                                                                                T* __restrict__ g, Peers P, PeerRegions R,
@@ -520,15 +555,23 @@ __global__ void __launch_bounds__(kLmThreads) reproj_reduce_solve_push_kernel(co
   }
   double acc[2] = {0.0, 0.0};
   const T* part = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.part);
+  constexpr int EV = 16 / (int)sizeof(T), NV = kPartSlot / EV, NVP = kPoseSlot / EV;
   for (int c = c0 + blockIdx.x * kLmThreads + threadIdx.x; c < c1; c += gridDim.x * kLmThreads) {
     Sys6<T> s;
     if (!retry) {
-      T v[27];
+      T v[kPartSlot];
 #pragma unroll
-      for (int t = 0; t < 27; ++t) v[t] = part[(long long)(c - c0) * 27 + t];
-      for (int r = 1; r < P.world; ++r)
+      for (int t = 0; t < kPartSlot; ++t) v[t] = T(0);
+      for (int r = 0; r < P.world; ++r) {              // rank order: the same sum on every run
+        const float4* p4 = reinterpret_cast<const float4*>(part + ((long long)r * q + (c - c0)) * kPartSlot);
 #pragma unroll
-        for (int t = 0; t < 27; ++t) v[t] += part[((long long)r * q + (c - c0)) * 27 + t];
+        for (int i = 0; i < NV; ++i) {
+          const float4 x = p4[i];
+          const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+          for (int kk = 0; kk < EV; ++kk) v[i * EV + kk] += e[kk];
+        }
+      }
       int t = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a)
@@ -547,19 +590,24 @@ __global__ void __launch_bounds__(kLmThreads) reproj_reduce_solve_push_kernel(co
     }
     T D[6], pred;
     const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
-    T pr[7], o[7];
+    T pr[7];
+    __align__(16) T o[kPoseSlot];
 #pragma unroll
     for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)c * 7 + k];
-    store_elem<SE3g, T>(o, se3_retract(D, load_se3(pr)));
-    for (int r = 0; r < P.world; ++r) {
-      T* dst = reinterpret_cast<T*>(P.base[r] + kDataOffset + R.pt) + (long long)c * 7;
+    T o7[7];
+    store_elem<SE3g, T>(o7, se3_retract(D, load_se3(pr)));
 #pragma unroll
-      for (int k = 0; k < 7; ++k) dst[k] = o[k];
+    for (int k = 0; k < 7; ++k) o[k] = o7[k];
+    o[7] = T(0);
+    for (int r = 0; r < P.world; ++r) {
+      float4* dst = reinterpret_cast<float4*>(P.base[r] + kDataOffset + R.pt + (long long)c * (kPoseSlot * (long long)sizeof(T)));
+#pragma unroll
+      for (int i = 0; i < NVP; ++i) dst[i] = reinterpret_cast<const float4*>(o)[i];
     }
     acc[0] += (double)pred;
     acc[1] += ok ? 0.0 : 1.0;
-    __threadfence_system();
   }
+  __threadfence_system();                              // once per thread, after its last remote store
   if (reduce_sums<2>(acc, ws)) {
     for (int r = 0; r < P.world; ++r) {
       double* sc = comm_scalars(P.base[r], CH_TRIAL, P.rank);
@@ -569,7 +617,8 @@ __global__ void __launch_bounds__(kLmThreads) reproj_reduce_solve_push_kernel(co
   }
 }
 
-template <typename T>
+// K3p: trial loss of the local rows with the trial poses every owner pushed; LPC lanes per camera, 4 rows in flight
+template <typename T, int LPC>
 __global__ void __launch_bounds__(kLmThreads) reproj_loss_push_kernel(const T* __restrict__ pts, const T* __restrict__ pix,
                                                                        const int* __restrict__ seg, Peers P, PeerRegions R,
                                                                        double* ws, unsigned long long epoch1, int rk, T rdelta,
@@ -577,24 +626,44 @@ __global__ void __launch_bounds__(kLmThreads) reproj_loss_push_kernel(const T* _
   if (threadIdx.x == 0) comm_wait_all(P, CH_TRIAL, epoch1);
   __syncthreads();
   const T* Pt = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.pt);
-  const int lane = threadIdx.x & 31;
-  const int wpb = kLmThreads / 32;
+  constexpr int cpb = kLmThreads / LPC;
+  const int sub = threadIdx.x % LPC, slot = threadIdx.x / LPC;
+  const int rounds = (ncam + cpb - 1) / cpb;
   double acc[1] = {0.0};
-  for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < ncam; c += gridDim.x * wpb) {
+  for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+    const int c = rd * cpb + slot;
+    if (c >= ncam) continue;
     const int b = seg[c], e = seg[c + 1];
     if (b == e) continue;
     T pr[7];
 #pragma unroll
-    for (int qk = 0; qk < 7; ++qk) pr[qk] = Pt[(long long)c * 7 + qk];
+    for (int qk = 0; qk < 7; ++qk) pr[qk] = Pt[(long long)c * kPoseSlot + qk];
     const Elem<T> Tc = load_se3(pr);
     T loss = T(0);
-    for (int k = b + lane; k < e; k += 32) {
-      const long long k0 = k;
+    auto trial = [&](const T* v) {
       T rx, ry, rho, w;
       V3<T> y;
-      reproj_residual(Tc, mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1], rx, ry, y);
+      reproj_residual(Tc, mk(v[0], v[1], v[2]), v[3], v[4], rx, ry, y);
       robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
       loss += rho;
+    };
+    constexpr int kRows = 4;
+    int k = b + sub;
+    for (; k + (kRows - 1) * LPC < e; k += kRows * LPC) {
+      T v[kRows][5];
+#pragma unroll
+      for (int u = 0; u < kRows; ++u) {
+        const long long ku = k + u * LPC;
+        v[u][0] = pts[ku * 3]; v[u][1] = pts[ku * 3 + 1]; v[u][2] = pts[ku * 3 + 2];
+        v[u][3] = pix[ku * 2]; v[u][4] = pix[ku * 2 + 1];
+      }
+#pragma unroll
+      for (int u = 0; u < kRows; ++u) trial(v[u]);
+    }
+    for (; k < e; k += LPC) {
+      const long long k0 = k;
+      const T v[5] = {pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2], pix[k0 * 2], pix[k0 * 2 + 1]};
+      trial(v);
     }
     acc[0] += (double)loss;
   }
@@ -603,8 +672,6 @@ __global__ void __launch_bounds__(kLmThreads) reproj_loss_push_kernel(const T* _
     comm_signal_all(P, CH_LOSS, epoch1);
   }
 }
-
-// every rank: add the scalars in rank order, decide (identical everywhere), commit the trial poses
 template <typename T>
 __global__ void __launch_bounds__(kLmThreads) reproj_decide_commit_kernel(Peers P, PeerRegions R, double* st, LmCtl ctl,
                                                                            HostOut ho, unsigned long long epoch0,
@@ -630,7 +697,7 @@ __global__ void __launch_bounds__(kLmThreads) reproj_decide_commit_kernel(Peers 
   if (sh[ST_STATUS] != 1.0) return;
   const T* Pt = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.pt);
   for (long long i = (long long)blockIdx.x * kLmThreads + threadIdx.x; i < count; i += (long long)gridDim.x * kLmThreads)
-    poses[i] = Pt[i];
+    poses[i] = Pt[(i / 7) * kPoseSlot + i % 7];          // trial poses sit in 8-number slots
 }
 
 // PoseInv, poses sharded: the trial kernel of each rank pushes its four sums; decide + commit after one exchange
@@ -849,24 +916,37 @@ B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
                                                  long long epoch1, double* ws0, double* ws1, double* ws2, double* st, \
                                                  double* host_out, long long seq, const double* ctl, int robust,      \
                                                  double delta, double scale, double dmin, double dmax, int retry,     \
-                                                 long long ncam, void* stream) {                                      \
+                                                 long long rows, long long ncam, void* stream) {                      \
     if (ncam <= 0) return 0;                                                                                          \
     cudaStream_t s = (cudaStream_t)stream;                                                                            \
     const LmCtl k = make_ctl(ctl);                                                                                    \
     const HostOut ho = make_host_out(host_out, seq);                                                                  \
     const Peers P = make_peers(bases, rank, world);                                                                   \
     const PeerRegions R = {part_off, pt_off};                                                                         \
-    const unsigned wgrid = lm_grid(ncam, kLmThreads / 32);                                                            \
+    const bool wide = rows >= 384 * ncam;                  /* lanes per camera from the LOCAL rows per camera */        \
+    const unsigned wgrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);                                    \
     const long long q = (ncam + world - 1) / world;                                                                   \
-    if (!retry)                                                                                                       \
-      reproj_accum_push_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0,                      \
-                                                                (unsigned long long)epoch0, robust, (CT)delta,        \
-                                                                (int)ncam);                                           \
+    if (!retry) {                                                                                                     \
+      if (wide)                                                                                                       \
+        reproj_accum_push_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0,                \
+                                                                      (unsigned long long)epoch0, robust, (CT)delta,  \
+                                                                      (int)ncam);                                     \
+      else                                                                                                            \
+        reproj_accum_push_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0,                 \
+                                                                     (unsigned long long)epoch0, robust, (CT)delta,   \
+                                                                     (int)ncam);                                      \
+    }                                                                                                                 \
     reproj_reduce_solve_push_kernel<CT><<<lm_grid(q, kLmThreads), kLmThreads, 0, s>>>(                                \
         poses, H, g, P, R, ws1, (unsigned long long)epoch0, (unsigned long long)epoch1, retry, (CT)scale, (CT)dmin,   \
         (CT)dmax, (int)ncam);                                                                                         \
-    reproj_loss_push_kernel<CT><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2, (unsigned long long)epoch1,    \
-                                                             robust, (CT)delta, (int)ncam);                           \
+    if (wide)                                                                                                         \
+      reproj_loss_push_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2,                          \
+                                                                   (unsigned long long)epoch1, robust, (CT)delta,     \
+                                                                   (int)ncam);                                        \
+    else                                                                                                              \
+      reproj_loss_push_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2,                           \
+                                                                  (unsigned long long)epoch1, robust, (CT)delta,      \
+                                                                  (int)ncam);                                         \
     reproj_decide_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(                             \
         P, R, st, k, ho, (unsigned long long)epoch0, (unsigned long long)epoch1, poses, ncam * 7);                    \
     return finish_step(host_out, seq, s);                                                                             \

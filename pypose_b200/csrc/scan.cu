@@ -927,8 +927,8 @@ B200_EXPORT int b200_imu_tma_mode(int mode) {
     const int tma_env = imu_tma_mode();                                                                                \
     const uintptr_t bits = (uintptr_t)dt | (uintptr_t)gyro | (uintptr_t)acc | (uintptr_t)rot_out | (uintptr_t)vel_out | \
                            (uintptr_t)pos_out | (uintptr_t)(F * (long long)sizeof(CT));                                \
-    if (tma_env && !a && !rot && rot_out && (bits & 15) == 0 && ch != 4) {                                             \
-      auto tgo = ch == 1 ? imu_tma_launch<CT, 1> : imu_tma_launch<CT, 2>;                                              \
+    if (tma_env && !a && !rot && rot_out && (bits & 15) == 0) {                                                        \
+      auto tgo = ch == 1 ? imu_tma_launch<CT, 1> : (ch == 4 ? imu_tma_launch<CT, 4> : imu_tma_launch<CT, 2>);          \
       return tgo(dt, gyro, acc, init_rot, init_stride, gravity3_host, init_pos, init_vel, pv_stride, rot_out, vel_out, \
                  pos_out, B, F, (cudaStream_t)s);                                                                      \
     }                                                                                                                  \

@@ -105,8 +105,8 @@ def _align(n, a=256):
 def reproj_payload(ncam, world, itemsize):
     """(part_off, pt_off, bytes) of the exchange payload of b200_lm_reproj_step_peer."""
     q = (ncam + world - 1) // world
-    part = _align(world * q * 27 * itemsize)
-    return 0, part, part + _align(ncam * 7 * itemsize)
+    part = _align(world * q * 28 * itemsize)          # 16-byte slots: 28 numbers per partial block, 8 per trial pose
+    return 0, part, part + _align(ncam * 8 * itemsize)
 
 
 def reproj_trial_peer(ds, prob, scale, dmin, dmax, retry):
@@ -120,7 +120,7 @@ def reproj_trial_peer(ds, prob, scale, dmin, dmax, retry):
                prob.seg.data_ptr(), H.data_ptr(), g.data_ptr(), c.bases_ptr, c.rank, c.world, ds.part_off, ds.pt_off,
                ds.epoch0, ds.epoch1, ds.W[0].data_ptr(), ds.W[1].data_ptr(), ds.W[2].data_ptr(), ds.state.data_ptr(),
                ds.host_ptr, ds.next_seq(), ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale), float(dmin), float(dmax),
-               1 if retry else 0, poses.shape[0])
+               1 if retry else 0, prob.pts.shape[0], poses.shape[0])
     return ds.read()
 
 
