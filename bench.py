@@ -101,6 +101,8 @@ def dist_setup(n_gpus):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # the version banner goes to stdout, next to the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         # a rank that falls out of step must fail the run in minutes, not after NCCL's default 10-minute watchdog
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     return rank, world, local

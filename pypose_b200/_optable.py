@@ -358,7 +358,10 @@ LM_OPS += [
       ("double*", "st", "(16) device state, see b200_lm_reproj_step"), ("double*", "host_out", "(16) pinned host memory or NULL"), ("long long", "seq", "see b200_lm_reproj_step"),
       ("const double*", "ctl", "HOST (14), see b200_lm_reproj_step"), ("int", "robust", ""), ("double", "delta", ""),
       ("double", "scale", ""), ("double", "dmin", ""), ("double", "dmax", ""), ("int", "retry", ""),
-      ("long long", "rows", "number of LOCAL observation rows (selects 8 or 32 lanes per camera)")],
+      ("long long", "rows", "number of LOCAL observation rows (selects 8 or 32 lanes per camera)"),
+      ("int", "gather", "0: blocks reduce-scattered to camera owners, trial poses all-gathered (3 exchanges per trial); "
+                        "1: every rank receives all partial blocks and solves every camera (2 exchanges; the partial-block "
+                        "region then holds world * ncam slots)")],
      "b200_lm_reproj_step with the observations sharded over `world` GPUs: [H | g] is reduce-scattered to camera owners, "
      "trial poses are all-gathered and the scalar sums exchanged by stores into the peers' buffers (SURVEY.md §8e row 4); "
      "optimizer.py:659-680"),

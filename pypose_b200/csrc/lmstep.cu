@@ -22,6 +22,7 @@
 namespace b200pose {
 
 constexpr int kMaxLmDevices = 64;
+constexpr int kAccRows = 4;          // rows per lane in flight in the register-fed accumulation loops
 
 // The deciding thread also publishes the state in mapped pinned host memory (zero-copy): the host spins on the sequence
 // number instead of paying an asynchronous copy plus a stream synchronisation (~10 us per trial, measured).
@@ -82,16 +83,21 @@ __global__ void __launch_bounds__(kLmThreads) reproj_trial_kernel(const T* __res
         ac.add_row(j1, ry);
         loss += rho;
       };
+      // kAccRows rows per lane in flight: at 96-110 registers only 16-20 warps are resident, so the bytes in flight have
+      // to come from the unroll (2 rows: 26 KB per SM, 0.35 of the HBM peak at 1e7 rows; r2h)
       int k = b + sub;
-      for (; k + LPC < e; k += 2 * LPC) {
-        const long long k0 = k, k1 = k + LPC;
-        const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
-        const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
-        const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
-        accumulate(p0, z0x, z0y);
-        accumulate(p1, z1x, z1y);
+      for (; k + (kAccRows - 1) * LPC < e; k += kAccRows * LPC) {
+        T v[kAccRows][5];
+#pragma unroll
+        for (int u = 0; u < kAccRows; ++u) {
+          const long long ku = k + u * LPC;
+          v[u][0] = pts[ku * 3]; v[u][1] = pts[ku * 3 + 1]; v[u][2] = pts[ku * 3 + 2];
+          v[u][3] = pix[ku * 2]; v[u][4] = pix[ku * 2 + 1];
+        }
+#pragma unroll
+        for (int u = 0; u < kAccRows; ++u) accumulate(mk(v[u][0], v[u][1], v[u][2]), v[u][3], v[u][4]);
       }
-      if (k < e) {
+      for (; k < e; k += LPC) {
         const long long k0 = k;
         accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
       }
@@ -445,7 +451,9 @@ constexpr int kPartSlot = 28, kPoseSlot = 8;
 
 // K1p: LPC lanes per camera over the local rows (same loop as reproj_trial_kernel), blocks staged in shared memory, then the
 // CTA copies them to the owners with 16-byte stores.
-template <typename T, int LPC>
+// ALL: every rank receives every rank's blocks (slot [source rank][camera]) — the "gather" form for small problems, see
+// reproj_gather_trial_kernel.
+template <typename T, int LPC, bool ALL>
 __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
                                                                         const T* __restrict__ pix, const int* __restrict__ seg,
                                                                         Peers P, PeerRegions R, double* ws,
@@ -488,15 +496,18 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
       loss += rho;
     };
     int k = b + sub;
-    for (; k + LPC < e; k += 2 * LPC) {
-      const long long k0 = k, k1 = k + LPC;
-      const V3<T> p0 = mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]);
-      const V3<T> p1 = mk(pts[k1 * 3], pts[k1 * 3 + 1], pts[k1 * 3 + 2]);
-      const T z0x = pix[k0 * 2], z0y = pix[k0 * 2 + 1], z1x = pix[k1 * 2], z1y = pix[k1 * 2 + 1];
-      accumulate(p0, z0x, z0y);
-      accumulate(p1, z1x, z1y);
+    for (; k + (kAccRows - 1) * LPC < e; k += kAccRows * LPC) {
+      T v[kAccRows][5];
+#pragma unroll
+      for (int u = 0; u < kAccRows; ++u) {
+        const long long ku = k + u * LPC;
+        v[u][0] = pts[ku * 3]; v[u][1] = pts[ku * 3 + 1]; v[u][2] = pts[ku * 3 + 2];
+        v[u][3] = pix[ku * 2]; v[u][4] = pix[ku * 2 + 1];
+      }
+#pragma unroll
+      for (int u = 0; u < kAccRows; ++u) accumulate(mk(v[u][0], v[u][1], v[u][2]), v[u][3], v[u][4]);
     }
-    if (k < e) {
+    for (; k < e; k += LPC) {
       const long long k0 = k;
       accumulate(mk(pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2]), pix[k0 * 2], pix[k0 * 2 + 1]);
     }
@@ -526,10 +537,16 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
     for (int j = threadIdx.x; j < cpb * NV; j += kLmThreads) {
       const int sl = j / NV, v = j - sl * NV, cj = rd * cpb + sl;
       if (cj < ncam) {
-        const int owner = cj / q;
-        char* dst = P.base[owner] + kDataOffset + R.part +
-                    ((long long)P.rank * q + (cj - owner * q)) * (kPartSlot * (long long)sizeof(T)) + v * 16;
-        *reinterpret_cast<float4*>(dst) = reinterpret_cast<const float4*>(&sP[sl][0])[v];
+        const float4 x = reinterpret_cast<const float4*>(&sP[sl][0])[v];
+        if (ALL) {
+          const long long off = kDataOffset + R.part + ((long long)P.rank * ncam + cj) * (kPartSlot * (long long)sizeof(T)) + v * 16;
+          for (int r = 0; r < P.world; ++r) *reinterpret_cast<float4*>(P.base[r] + off) = x;
+        } else {
+          const int owner = cj / q;
+          char* dst = P.base[owner] + kDataOffset + R.part +
+                      ((long long)P.rank * q + (cj - owner * q)) * (kPartSlot * (long long)sizeof(T)) + v * 16;
+          *reinterpret_cast<float4*>(dst) = x;
+        }
       }
     }
     __syncthreads();                                   // the next round overwrites the staging slots
@@ -538,6 +555,126 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
   if (reduce_sums<1>(acc, ws)) {           // thread 0 of the last CTA: every CTA's stores are ordered before its ticket
     for (int r = 0; r < P.world; ++r) comm_scalars(P.base[r], CH_PART, P.rank)[(epoch & 1) * 4] = ws[0];
     comm_signal_all(P, CH_PART, epoch);
+  }
+}
+
+// Gather form, K2g: every rank holds every rank's partial blocks, adds them in rank order per camera (bit-identical on all
+// ranks), solves, retracts, keeps the block for retries and the trial pose locally, and goes straight on to the trial loss
+// of its local rows — ONE exchange fewer than the owner form (no trial poses travel), at world x the partial-block traffic:
+// chosen when world * ncam blocks are a few MB (r2m: 1e4 cameras / 1e6 rows on 2 GPUs took 98 us per step in the owner form
+// against 54 us on one GPU; three flag waits were most of it).  Predicted reduction / failed pivots are counted by the
+// camera's owner only, so that the sums over ranks are the totals.
+template <typename T, int LPC>
+__global__ void __launch_bounds__(kLmThreads) reproj_gather_trial_kernel(
+    const T* __restrict__ poses, const T* __restrict__ pts, const T* __restrict__ pix, const int* __restrict__ seg,
+    T* __restrict__ H, T* __restrict__ g, Peers P, PeerRegions R, double* ws, unsigned long long epoch0,
+    unsigned long long epoch1, int retry, T scale, T dmin, T dmax, int rk, T rdelta, int ncam) {
+  constexpr int cpb = kLmThreads / LPC;
+  constexpr int EV = 16 / (int)sizeof(T), NV = kPartSlot / EV;
+  __shared__ __align__(16) T sP[cpb][kPartSlot];
+  if (!retry) {
+    if (threadIdx.x == 0) comm_wait_all(P, CH_PART, epoch0);
+    __syncthreads();
+  }
+  const T* part = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.part);
+  T* Pt = reinterpret_cast<T*>(P.base[P.rank] + kDataOffset + R.pt);
+  const int sub = threadIdx.x % LPC, slot = threadIdx.x / LPC;
+  const int rounds = (ncam + cpb - 1) / cpb;
+  const int q = (ncam + P.world - 1) / P.world;
+  double acc[3] = {0.0, 0.0, 0.0};                      // trial loss (local rows), predicted, failed (owner's cameras)
+  for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+    const int c = rd * cpb + slot;
+    const bool valid = c < ncam;
+    const int cc = valid ? c : 0;
+    if (!retry) {
+      // lanes v < NV of the camera's group each add one 16-byte vector of the `world` blocks
+      for (int v = sub; v < NV; v += LPC) {
+        T a[EV];
+#pragma unroll
+        for (int kk = 0; kk < EV; ++kk) a[kk] = T(0);
+        for (int r = 0; r < P.world; ++r) {
+          const float4 x = reinterpret_cast<const float4*>(part + ((long long)r * ncam + cc) * kPartSlot)[v];
+          const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+          for (int kk = 0; kk < EV; ++kk) a[kk] += e[kk];
+        }
+#pragma unroll
+        for (int kk = 0; kk < EV; ++kk) sP[slot][v * EV + kk] = a[kk];
+      }
+      __syncwarp();
+    }
+    Sys6<T> s;
+    {
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        s.g[a] = retry ? g[(long long)cc * 6 + a] : sP[slot][21 + a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) { s.A[a][b] = retry ? H[(long long)cc * 21 + t] : sP[slot][t]; ++t; }
+      }
+    }
+    T pr[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pr[k] = poses[(long long)cc * 7 + k];
+    T D[6], pred;
+    const bool ok = sys6_damped_solve(s, scale, dmin, dmax, D, pred);
+    const Elem<T> Pn = se3_retract(D, load_se3(pr));
+    if (valid && sub == 0) {
+      T o7[7];
+      store_elem<SE3g, T>(o7, Pn);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) Pt[(long long)c * kPoseSlot + k] = o7[k];
+      if (!retry) {
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          g[(long long)c * 6 + a] = s.g[a];
+#pragma unroll
+          for (int b = a; b < 6; ++b) H[(long long)c * 21 + t++] = s.A[a][b];
+        }
+      }
+      if (c / q == P.rank) {
+        acc[1] += (double)pred;
+        acc[2] += ok ? 0.0 : 1.0;
+      }
+    }
+    const int b = valid ? seg[cc] : 0, e = valid ? seg[cc + 1] : 0;
+    T tl = T(0);
+    auto trial = [&](const T* v) {
+      T rx, ry, rho, w;
+      V3<T> y;
+      reproj_residual(Pn, mk(v[0], v[1], v[2]), v[3], v[4], rx, ry, y);
+      robust_eval(rk, rdelta, rx * rx + ry * ry, rho, w);
+      tl += rho;
+    };
+    constexpr int kRows = 4;
+    int k = b + sub;
+    for (; k + (kRows - 1) * LPC < e; k += kRows * LPC) {
+      T v[kRows][5];
+#pragma unroll
+      for (int u = 0; u < kRows; ++u) {
+        const long long ku = k + u * LPC;
+        v[u][0] = pts[ku * 3]; v[u][1] = pts[ku * 3 + 1]; v[u][2] = pts[ku * 3 + 2];
+        v[u][3] = pix[ku * 2]; v[u][4] = pix[ku * 2 + 1];
+      }
+#pragma unroll
+      for (int u = 0; u < kRows; ++u) trial(v[u]);
+    }
+    for (; k < e; k += LPC) {
+      const long long k0 = k;
+      const T v[5] = {pts[k0 * 3], pts[k0 * 3 + 1], pts[k0 * 3 + 2], pix[k0 * 2], pix[k0 * 2 + 1]};
+      trial(v);
+    }
+    acc[0] += (double)tl;
+    __syncwarp();                                      // sP[slot] is rewritten by the next round
+  }
+  if (reduce_sums<3>(acc, ws)) {
+    for (int r = 0; r < P.world; ++r) {
+      double* sc = comm_scalars(P.base[r], CH_TRIAL, P.rank);
+      sc[0] = ws[1]; sc[1] = ws[2];
+      comm_scalars(P.base[r], CH_LOSS, P.rank)[0] = ws[0];
+    }
+    comm_signal_all(P, CH_LOSS, epoch1);
   }
 }
 
@@ -916,7 +1053,7 @@ B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
                                                  long long epoch1, double* ws0, double* ws1, double* ws2, double* st, \
                                                  double* host_out, long long seq, const double* ctl, int robust,      \
                                                  double delta, double scale, double dmin, double dmax, int retry,     \
-                                                 long long rows, long long ncam, void* stream) {                      \
+                                                 long long rows, int gather, long long ncam, void* stream) {          \
     if (ncam <= 0) return 0;                                                                                          \
     cudaStream_t s = (cudaStream_t)stream;                                                                            \
     const LmCtl k = make_ctl(ctl);                                                                                    \
@@ -926,27 +1063,40 @@ B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
     const bool wide = rows >= 384 * ncam;                  /* lanes per camera from the LOCAL rows per camera */        \
     const unsigned wgrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);                                    \
     const long long q = (ncam + world - 1) / world;                                                                   \
+    const unsigned long long e0 = (unsigned long long)epoch0, e1 = (unsigned long long)epoch1;                        \
     if (!retry) {                                                                                                     \
-      if (wide)                                                                                                       \
-        reproj_accum_push_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0,                \
-                                                                      (unsigned long long)epoch0, robust, (CT)delta,  \
-                                                                      (int)ncam);                                     \
+      if (wide && gather)                                                                                             \
+        reproj_accum_push_kernel<CT, 32, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,      \
+                                                                            robust, (CT)delta, (int)ncam);            \
+      else if (wide)                                                                                                  \
+        reproj_accum_push_kernel<CT, 32, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,     \
+                                                                             robust, (CT)delta, (int)ncam);           \
+      else if (gather)                                                                                                \
+        reproj_accum_push_kernel<CT, 8, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,       \
+                                                                           robust, (CT)delta, (int)ncam);             \
       else                                                                                                            \
-        reproj_accum_push_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0,                 \
-                                                                     (unsigned long long)epoch0, robust, (CT)delta,   \
-                                                                     (int)ncam);                                      \
+        reproj_accum_push_kernel<CT, 8, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,      \
+                                                                            robust, (CT)delta, (int)ncam);            \
     }                                                                                                                 \
-    reproj_reduce_solve_push_kernel<CT><<<lm_grid(q, kLmThreads), kLmThreads, 0, s>>>(                                \
-        poses, H, g, P, R, ws1, (unsigned long long)epoch0, (unsigned long long)epoch1, retry, (CT)scale, (CT)dmin,   \
-        (CT)dmax, (int)ncam);                                                                                         \
-    if (wide)                                                                                                         \
-      reproj_loss_push_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2,                          \
-                                                                   (unsigned long long)epoch1, robust, (CT)delta,     \
-                                                                   (int)ncam);                                        \
-    else                                                                                                              \
-      reproj_loss_push_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2,                           \
-                                                                  (unsigned long long)epoch1, robust, (CT)delta,      \
-                                                                  (int)ncam);                                         \
+    if (gather) {                                                                                                     \
+      if (wide)                                                                                                       \
+        reproj_gather_trial_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P, R, ws1, e0,    \
+                                                                        e1, retry, (CT)scale, (CT)dmin, (CT)dmax,     \
+                                                                        robust, (CT)delta, (int)ncam);                \
+      else                                                                                                            \
+        reproj_gather_trial_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P, R, ws1, e0, e1, \
+                                                                       retry, (CT)scale, (CT)dmin, (CT)dmax, robust,  \
+                                                                       (CT)delta, (int)ncam);                         \
+    } else {                                                                                                          \
+      reproj_reduce_solve_push_kernel<CT><<<lm_grid(q, kLmThreads), kLmThreads, 0, s>>>(                              \
+          poses, H, g, P, R, ws1, e0, e1, retry, (CT)scale, (CT)dmin, (CT)dmax, (int)ncam);                           \
+      if (wide)                                                                                                       \
+        reproj_loss_push_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2, e1, robust,            \
+                                                                     (CT)delta, (int)ncam);                           \
+      else                                                                                                            \
+        reproj_loss_push_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2, e1, robust, (CT)delta,  \
+                                                                    (int)ncam);                                       \
+    }                                                                                                                 \
     reproj_decide_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(                             \
         P, R, st, k, ho, (unsigned long long)epoch0, (unsigned long long)epoch1, poses, ncam * 7);                    \
     return finish_step(host_out, seq, s);                                                                             \

@@ -6,6 +6,7 @@ linearise, solve, retract, trial loss, `strategy.update`, the accept test and th
 call and the updated ones come back in the 16-double state, which is the step's only device->host read.
 """
 import ctypes
+import os
 
 import torch
 
@@ -102,9 +103,21 @@ def _align(n, a=256):
     return (n + a - 1) // a * a
 
 
+GATHER_BYTES = 8 << 20
+
+
+def reproj_gather(ncam, world, itemsize):
+    """Gather form of the sharded reprojection trial (every rank receives all partial blocks and solves every camera: one
+    exchange fewer per trial) while world * ncam blocks stay small; owner form (reduce-scatter + all-gather) beyond."""
+    force = os.environ.get("B200POSE_PEER_GATHER")      # "0" / "1": A/B and tests (must be the same on every rank)
+    if force in ("0", "1"):
+        return force == "1"
+    return world * ncam * 28 * itemsize <= GATHER_BYTES
+
+
 def reproj_payload(ncam, world, itemsize):
     """(part_off, pt_off, bytes) of the exchange payload of b200_lm_reproj_step_peer."""
-    q = (ncam + world - 1) // world
+    q = ncam if reproj_gather(ncam, world, itemsize) else (ncam + world - 1) // world
     part = _align(world * q * 28 * itemsize)          # 16-byte slots: 28 numbers per partial block, 8 per trial pose
     return 0, part, part + _align(ncam * 8 * itemsize)
 
@@ -120,7 +133,8 @@ def reproj_trial_peer(ds, prob, scale, dmin, dmax, retry):
                prob.seg.data_ptr(), H.data_ptr(), g.data_ptr(), c.bases_ptr, c.rank, c.world, ds.part_off, ds.pt_off,
                ds.epoch0, ds.epoch1, ds.W[0].data_ptr(), ds.W[1].data_ptr(), ds.W[2].data_ptr(), ds.state.data_ptr(),
                ds.host_ptr, ds.next_seq(), ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale), float(dmin), float(dmax),
-               1 if retry else 0, prob.pts.shape[0], poses.shape[0])
+               1 if retry else 0, prob.pts.shape[0], 1 if reproj_gather(poses.shape[0], c.world, poses.element_size()) else 0,
+               poses.shape[0])
     return ds.read()
 
 

@@ -61,7 +61,12 @@ def main():
     dist.all_gather(gathered, net.pose.detach().tensor().contiguous())
     res["poseinv_loss"], res["poseinv_poses"] = np.array(losses), torch.cat(gathered).cpu().numpy()
     # ---- Reproj: observations sharded, poses replicated
-    for case, steps in (("reproj", 4), ("reproj_hard", 6)):
+    # both exchange forms of the sharded reprojection trial (optim/_lmstep.py reproj_gather): owner = reduce-scatter of the
+    # blocks + all-gather of the trial poses, gather = every rank receives all blocks and solves every camera
+    for form, case, steps in (("owner", "reproj", 4), ("owner", "reproj_hard", 6), ("gather", "reproj", 4),
+                              ("gather", "reproj_hard", 6)):
+        os.environ["B200POSE_PEER_GATHER"] = "1" if form == "gather" else "0"
+        tag = case if form == "owner" else case + "_gather"
         pts, pix, cidx = g[f"{case}/pts"], g[f"{case}/pix"], g[f"{case}/cidx"]
         M = len(cidx)
         sl = slice(rank * M // world, (rank + 1) * M // world)
@@ -72,13 +77,14 @@ def main():
         for _ in range(steps):
             l2.append(float(opt2.step(inp)))
             rej.append(opt2.reject_count)
-        res[f"{case}_peer"] = np.array([int(getattr(opt2._problem, "_ds", None) is not None and opt2._problem._ds.comm is not None)])
-        res[f"{case}_loss"], res[f"{case}_poses"], res[f"{case}_reject"] = np.array(l2), net2.poses.detach().cpu().numpy(), np.array(rej)
+        res[f"{tag}_peer"] = np.array([int(getattr(opt2._problem, "_ds", None) is not None and opt2._problem._ds.comm is not None)])
+        res[f"{tag}_loss"], res[f"{tag}_poses"], res[f"{tag}_reject"] = np.array(l2), net2.poses.detach().cpu().numpy(), np.array(rej)
         # every rank holds the same poses bit for bit
         mine = net2.poses.detach().tensor().contiguous()
         other = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(other, mine)
         assert all(torch.equal(o, mine) for o in other), "replicated poses diverged between ranks"
+    os.environ.pop("B200POSE_PEER_GATHER", None)
     # ---- PGO: edges sharded, nodes replicated
     edges, Z = g["pgo/edges"], g["pgo/Z"]
     E = len(edges)

@@ -38,9 +38,11 @@ def test_sharded_lm_two_gpus_matches_reference(tmp_path, golden_lm):
     np.testing.assert_allclose(r["poseinv_loss"], g["poseinv/trustregion/loss"], rtol=1e-5, atol=1e-20)
     np.testing.assert_allclose(r["poseinv_poses"], g["poseinv/trustregion/poses"][-1], atol=1e-9)
     for case in ("reproj", "reproj_hard"):
-        np.testing.assert_allclose(r[f"{case}_loss"], g[f"{case}/trustregion/loss"], rtol=1e-6)
-        np.testing.assert_allclose(r[f"{case}_poses"], g[f"{case}/trustregion/poses"][-1], atol=1e-8)
-        np.testing.assert_array_equal(r[f"{case}_reject"], g[f"{case}/trustregion/reject"])
+        for tag in (case, case + "_gather"):               # owner form, gather form of the block exchange
+            assert r[f"{tag}_peer"][0] == 1
+            np.testing.assert_allclose(r[f"{tag}_loss"], g[f"{case}/trustregion/loss"], rtol=1e-6)
+            np.testing.assert_allclose(r[f"{tag}_poses"], g[f"{case}/trustregion/poses"][-1], atol=1e-8)
+            np.testing.assert_array_equal(r[f"{tag}_reject"], g[f"{case}/trustregion/reject"])
     np.testing.assert_allclose(r["pgo_loss"], g["pgo/trustregion/loss"], rtol=1e-6)
     np.testing.assert_allclose(r["pgo_poses"], g["pgo/trustregion/poses"][-1], atol=1e-7)
     np.testing.assert_allclose(r["ba_loss"], g["ba/trustregion/loss"], rtol=1e-5)
