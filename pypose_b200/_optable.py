@@ -403,7 +403,7 @@ SCAN_OPS = [
     (f"b200_{g}_cumprod_lb",
      [("const REAL*", "in", f"(B,L,{d})"), ("REAL*", "out", f"(B,L,{d})"), ("long long", "B", "sequences"),
       ("long long", "L", "scan length"), ("int", "left", "1: y_i = x_i y_{i-1}; 0: y_i = y_{i-1} x_i"),
-      ("void*", "ws", "b200_scan_workspace_bytes(B, L, sizeof(REAL)) bytes of scratch")],
+      ("void*", "ws", "b200_scan_workspace_bytes(B, L, sizeof(REAL)) bytes of scratch, 16-byte aligned")],
      "the same scan with the time axis split over CTAs (tile products, scan of the tile products, apply): for few long sequences; "
      "pypose/basics/ops.py:29-58, lietensor.py:171-193")
     for g, (_, d, _) in GROUPS.items()

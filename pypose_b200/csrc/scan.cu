@@ -213,6 +213,23 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_kernel(const T* __restri
 // every tile had to walk back over hundreds of unfinished predecessors — the look-back chain, not the bandwidth, set the
 // time.  Workspace (caller-owned, no initialisation needed): aggregates (tiles x 8) and prefixes (tiles x 8).
 // ------------------------------------------------------------------------------------------------
+// tile aggregates / prefixes live in 8-number slots (the widest group layout) of a 16-byte aligned workspace: moved as
+// 16-byte vectors (2 for float, 4 for double) instead of 8 scalars
+template <typename T> __device__ __forceinline__ Elem<T> load_agg(const T* __restrict__ p) {
+  constexpr int EV = 16 / (int)sizeof(T);
+  __align__(16) T v[8];
+#pragma unroll
+  for (int i = 0; i < 8 / EV; ++i) reinterpret_cast<float4*>(v)[i] = reinterpret_cast<const float4*>(p)[i];
+  return load_elem<Sim3g, T>(v);
+}
+template <typename T> __device__ __forceinline__ void store_agg(T* __restrict__ p, const Elem<T>& e) {
+  constexpr int EV = 16 / (int)sizeof(T);
+  __align__(16) T v[8];
+  store_elem<Sim3g, T>(v, e);
+#pragma unroll
+  for (int i = 0; i < 8 / EV; ++i) reinterpret_cast<float4*>(p)[i] = reinterpret_cast<const float4*>(v)[i];
+}
+
 template <class G, typename T, bool LEFT, int CH>
 __global__ void __launch_bounds__(kScanThreads) cumprod_tile_reduce_kernel(const T* __restrict__ in, long long L, int nt,
                                                                             T* __restrict__ agg) {
@@ -240,7 +257,7 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_tile_reduce_kernel(const
   }
   Elem<T> total;
   block_exclusive<G, T, LEFT>(run, total, sh);
-  if (threadIdx.x == 0) store_elem<Sim3g, T>(agg + gid * 8, total);
+  if (threadIdx.x == 0) store_agg(agg + gid * 8, total);
 }
 // exclusive scan of the nt tile aggregates of one sequence: one CTA of kPrefixThreads per sequence, one aggregate per
 // thread and round (carry across rounds), two levels of warp-shuffle scans.  r2h ncu: the 128-thread version needed 8
@@ -256,7 +273,7 @@ __global__ void __launch_bounds__(kPrefixThreads) cumprod_tile_prefix_kernel(con
   Elem<T> carry = elem_identity<T>();
   for (int base = 0; base < nt; base += kPrefixThreads) {
     const int t = base + threadIdx.x;
-    Elem<T> inc = t < nt ? load_elem<Sim3g, T>(agg + (b * nt + t) * 8) : elem_identity<T>();
+    Elem<T> inc = t < nt ? load_agg(agg + (b * nt + t) * 8) : elem_identity<T>();
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       Elem<T> up = elem_shfl_up(inc, o);
@@ -281,16 +298,12 @@ __global__ void __launch_bounds__(kPrefixThreads) cumprod_tile_prefix_kernel(con
     __syncthreads();
     const Elem<T> wpre = load_elem<Sim3g, T>(sh_pre + warp * 8);
     const Elem<T> total = load_elem<Sim3g, T>(sh_pre + NW * 8);
-    if (t < nt) store_elem<Sim3g, T>(pre + (b * nt + t) * 8, combine<G, T, LEFT>(carry, combine<G, T, LEFT>(wpre, excl)));
+    if (t < nt) store_agg(pre + (b * nt + t) * 8, combine<G, T, LEFT>(carry, combine<G, T, LEFT>(wpre, excl)));
     carry = combine<G, T, LEFT>(carry, total);
     __syncthreads();                                   // sh_tot / sh_pre are rewritten by the next round
   }
 }
-// FUSED: `pre` holds the tile AGGREGATES and every CTA multiplies the aggregates of the tiles before its own itself (at
-// most kFusedTiles of them: <= 8 per thread + one block reduction, ~a quarter of the tile's own work) — the separate prefix
-// launch was 11 us of a 44 us scan at L = 1e6 (r2j ncu).  Longer sequences keep the three-launch form.
-constexpr int kFusedTiles = 1024;
-template <class G, typename T, bool LEFT, int CH, bool FUSED>
+template <class G, typename T, bool LEFT, int CH>
 __global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                                            long long L, int nt, const T* __restrict__ pre) {
   using TS = TileSmem<T, G::D, CH>;
@@ -302,26 +315,7 @@ __global__ void __launch_bounds__(kScanThreads) cumprod_tile_apply_kernel(const 
   constexpr long long TILE = (long long)kScanThreads * CH;
   const long long row0 = (long long)t * TILE;
   const int rows = (int)(L - row0 < TILE ? L - row0 : TILE);
-  Elem<T> tile_pfx;
-  if (FUSED) {
-    const T* a = pre + b * nt * 8;
-    const int c = (t + kScanThreads - 1) / kScanThreads;          // consecutive aggregates per thread (<= 8)
-    const int lo = threadIdx.x * c;
-    Elem<T> part = elem_identity<T>();
-    for (int j0 = 0; j0 < c; j0 += 4) {                           // 4 aggregates in flight
-      Elem<T> e[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = lo + j0 + u;
-        e[u] = (j0 + u < c && j < t) ? load_elem<Sim3g, T>(a + (long long)j * 8) : elem_identity<T>();
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) part = combine<G, T, LEFT>(part, e[u]);
-    }
-    block_exclusive<G, T, LEFT>(part, tile_pfx, sh);               // total = ordered product of all parts
-  } else {
-    tile_pfx = load_elem<Sim3g, T>(pre + gid * 8);
-  }
+  const Elem<T> tile_pfx = load_agg(pre + gid * 8);
   tile_load<T, G::D, CH>(in + (b * L + row0) * G::D, rows * G::D, tile);
   const int first = threadIdx.x * CH;
   T* mine = tile + threadIdx.x * TS::STRIDE;
@@ -371,23 +365,14 @@ int launch_cumprod_lb(const T* in, T* out, long long B, long long L, int left, v
   const long long nt = scan_tiles(L, (int)sizeof(T)), tiles = B * nt;
   T* agg = reinterpret_cast<T*>(ws);
   T* pre = agg + tiles * 8;
-  const bool fused = nt <= kFusedTiles;
   if (left) {
     cumprod_tile_reduce_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
-    if (fused) {
-      cumprod_tile_apply_kernel<G, T, true, CH, true><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, agg);
-    } else {
-      cumprod_tile_prefix_kernel<G, T, true><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
-      cumprod_tile_apply_kernel<G, T, true, CH, false><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
-    }
+    cumprod_tile_prefix_kernel<G, T, true><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
+    cumprod_tile_apply_kernel<G, T, true, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
   } else {
     cumprod_tile_reduce_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, L, (int)nt, agg);
-    if (fused) {
-      cumprod_tile_apply_kernel<G, T, false, CH, true><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, agg);
-    } else {
-      cumprod_tile_prefix_kernel<G, T, false><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
-      cumprod_tile_apply_kernel<G, T, false, CH, false><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
-    }
+    cumprod_tile_prefix_kernel<G, T, false><<<(unsigned)B, kPrefixThreads, 0, s>>>(agg, pre, (int)nt);
+    cumprod_tile_apply_kernel<G, T, false, CH><<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, L, (int)nt, pre);
   }
   return (int)cudaGetLastError();
 }
