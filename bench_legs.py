@@ -172,7 +172,7 @@ def run(args, rank, world, dev, peak):
     if not args.no_large:
         sizes.append(("lm_reproj_2e8", 100_000, 200_000_000))
     for name, C, M in sizes:
-        init, inp = _reproj_problem(pp, dev, C, M, rank, world, 77, sorted_split=False)
+        init, inp = _reproj_problem(pp, dev, C, M, rank, world, 77, sorted_split=world > 1)   # sorted by pose, then split
         netr = pp.module.PoseReproj(init.clone())
         optr = pp.optim.LM(netr, strategy=pp.optim.strategy.TrustRegion(), group=group)
 

@@ -361,7 +361,12 @@ LM_OPS += [
       ("long long", "rows", "number of LOCAL observation rows (selects 8 or 32 lanes per camera)"),
       ("int", "gather", "0: blocks reduce-scattered to camera owners, trial poses all-gathered (3 exchanges per trial); "
                         "1: every rank receives all partial blocks and solves every camera (2 exchanges; the partial-block "
-                        "region then holds world * ncam slots)")],
+                        "region then holds world * ncam slots)"),
+      ("const unsigned char*", "present", "(world, ncam) 1 where that rank holds rows of that camera, or NULL = every rank "
+                                          "holds rows of every camera: a rank sends no block for a camera it has no rows of, "
+                                          "and the receivers skip those slots"),
+      ("const int*", "cams", "(nloc) the cameras this rank holds rows of, ascending (required with `present`), or NULL = all"),
+      ("long long", "nloc", "")],
      "b200_lm_reproj_step with the observations sharded over `world` GPUs: [H | g] is reduce-scattered to camera owners, "
      "trial poses are all-gathered and the scalar sums exchanged by stores into the peers' buffers (SURVEY.md §8e row 4); "
      "optimizer.py:659-680"),

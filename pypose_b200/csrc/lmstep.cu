@@ -457,17 +457,22 @@ template <typename T, int LPC, bool ALL>
 __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* __restrict__ poses, const T* __restrict__ pts,
                                                                         const T* __restrict__ pix, const int* __restrict__ seg,
                                                                         Peers P, PeerRegions R, double* ws,
-                                                                        unsigned long long epoch, int rk, T rdelta, int ncam) {
+                                                                        unsigned long long epoch, int rk, T rdelta, int ncam,
+                                                                        const int* __restrict__ cams, int nloc) {
+  // cams: the nloc cameras this rank holds rows of (with a `present` mask on the receivers), or NULL = all ncam cameras
   constexpr int cpb = kLmThreads / LPC;
   constexpr int NV = kPartSlot * (int)sizeof(T) / 16;
   __shared__ __align__(16) T sP[cpb][kPartSlot];
+  __shared__ int sC[cpb];
   const int sub = threadIdx.x % LPC, slot = threadIdx.x / LPC;
-  const int rounds = (ncam + cpb - 1) / cpb;
+  const int nwork = cams ? nloc : ncam;
+  const int rounds = (nwork + cpb - 1) / cpb;
   const int q = (ncam + P.world - 1) / P.world;
   double acc[1] = {0.0};
   for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
-    const int c = rd * cpb + slot;
-    const bool valid = c < ncam;
+    const int idx = rd * cpb + slot;
+    const bool valid = idx < nwork;
+    const int c = valid ? (cams ? cams[idx] : idx) : -1;
     const int cc = valid ? c : 0;
     T pr[7];
 #pragma unroll
@@ -531,12 +536,13 @@ __global__ void __launch_bounds__(kLmThreads) reproj_accum_push_kernel(const T* 
 #pragma unroll
       for (int a = 0; a < 6; ++a) sP[slot][21 + a] = s.g[a];
       sP[slot][27] = T(0);
+      sC[slot] = c;
       if (valid) acc[0] += (double)loss;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < cpb * NV; j += kLmThreads) {
-      const int sl = j / NV, v = j - sl * NV, cj = rd * cpb + sl;
-      if (cj < ncam) {
+      const int sl = j / NV, v = j - sl * NV, cj = sC[sl];
+      if (cj >= 0) {
         const float4 x = reinterpret_cast<const float4*>(&sP[sl][0])[v];
         if (ALL) {
           const long long off = kDataOffset + R.part + ((long long)P.rank * ncam + cj) * (kPartSlot * (long long)sizeof(T)) + v * 16;
@@ -568,7 +574,8 @@ template <typename T, int LPC>
 __global__ void __launch_bounds__(kLmThreads) reproj_gather_trial_kernel(
     const T* __restrict__ poses, const T* __restrict__ pts, const T* __restrict__ pix, const int* __restrict__ seg,
     T* __restrict__ H, T* __restrict__ g, Peers P, PeerRegions R, double* ws, unsigned long long epoch0,
-    unsigned long long epoch1, int retry, T scale, T dmin, T dmax, int rk, T rdelta, int ncam) {
+    unsigned long long epoch1, int retry, T scale, T dmin, T dmax, int rk, T rdelta, int ncam,
+    const unsigned char* __restrict__ present) {
   constexpr int cpb = kLmThreads / LPC;
   constexpr int EV = 16 / (int)sizeof(T), NV = kPartSlot / EV;
   __shared__ __align__(16) T sP[cpb][kPartSlot];
@@ -593,6 +600,7 @@ __global__ void __launch_bounds__(kLmThreads) reproj_gather_trial_kernel(
 #pragma unroll
         for (int kk = 0; kk < EV; ++kk) a[kk] = T(0);
         for (int r = 0; r < P.world; ++r) {
+          if (present && !present[(long long)r * ncam + cc]) continue;       // rank r holds no rows of this camera
           const float4 x = reinterpret_cast<const float4*>(part + ((long long)r * ncam + cc) * kPartSlot)[v];
           const T* e = reinterpret_cast<const T*>(&x);
 #pragma unroll
@@ -683,7 +691,8 @@ __global__ void __launch_bounds__(kLmThreads) reproj_reduce_solve_push_kernel(co
                                                                                T* __restrict__ g, Peers P, PeerRegions R,
                                                                                double* ws, unsigned long long epoch0,
                                                                                unsigned long long epoch1, int retry, T scale,
-                                                                               T dmin, T dmax, int ncam) {
+                                                                               T dmin, T dmax, int ncam,
+                                                                               const unsigned char* __restrict__ present) {
   const int q = (ncam + P.world - 1) / P.world;
   const int c0 = P.rank * q, c1 = min(ncam, c0 + q);
   if (!retry) {
@@ -700,6 +709,7 @@ __global__ void __launch_bounds__(kLmThreads) reproj_reduce_solve_push_kernel(co
 #pragma unroll
       for (int t = 0; t < kPartSlot; ++t) v[t] = T(0);
       for (int r = 0; r < P.world; ++r) {              // rank order: the same sum on every run
+        if (present && !present[(long long)r * ncam + c]) continue;            // rank r holds no rows of this camera
         const float4* p4 = reinterpret_cast<const float4*>(part + ((long long)r * q + (c - c0)) * kPartSlot);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
@@ -759,17 +769,19 @@ template <typename T, int LPC>
 __global__ void __launch_bounds__(kLmThreads) reproj_loss_push_kernel(const T* __restrict__ pts, const T* __restrict__ pix,
                                                                        const int* __restrict__ seg, Peers P, PeerRegions R,
                                                                        double* ws, unsigned long long epoch1, int rk, T rdelta,
-                                                                       int ncam) {
+                                                                       int ncam, const int* __restrict__ cams, int nloc) {
   if (threadIdx.x == 0) comm_wait_all(P, CH_TRIAL, epoch1);
   __syncthreads();
   const T* Pt = reinterpret_cast<const T*>(P.base[P.rank] + kDataOffset + R.pt);
   constexpr int cpb = kLmThreads / LPC;
   const int sub = threadIdx.x % LPC, slot = threadIdx.x / LPC;
-  const int rounds = (ncam + cpb - 1) / cpb;
+  const int nwork = cams ? nloc : ncam;
+  const int rounds = (nwork + cpb - 1) / cpb;
   double acc[1] = {0.0};
   for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
-    const int c = rd * cpb + slot;
-    if (c >= ncam) continue;
+    const int idx = rd * cpb + slot;
+    if (idx >= nwork) continue;
+    const int c = cams ? cams[idx] : idx;
     const int b = seg[c], e = seg[c + 1];
     if (b == e) continue;
     T pr[7];
@@ -1053,49 +1065,52 @@ B200_EXPORT int b200_lm_reproj_staged_mode(int mode) {
                                                  long long epoch1, double* ws0, double* ws1, double* ws2, double* st, \
                                                  double* host_out, long long seq, const double* ctl, int robust,      \
                                                  double delta, double scale, double dmin, double dmax, int retry,     \
-                                                 long long rows, int gather, long long ncam, void* stream) {          \
+                                                 long long rows, int gather, const unsigned char* present,            \
+                                                 const int* cams, long long nloc, long long ncam, void* stream) {     \
     if (ncam <= 0) return 0;                                                                                          \
     cudaStream_t s = (cudaStream_t)stream;                                                                            \
     const LmCtl k = make_ctl(ctl);                                                                                    \
     const HostOut ho = make_host_out(host_out, seq);                                                                  \
     const Peers P = make_peers(bases, rank, world);                                                                   \
     const PeerRegions R = {part_off, pt_off};                                                                         \
-    const bool wide = rows >= 384 * ncam;                  /* lanes per camera from the LOCAL rows per camera */        \
-    const unsigned wgrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);                                    \
+    const long long ncw = cams ? nloc : ncam;              /* cameras this rank works on */                           \
+    const bool wide = rows >= 384 * ncw;                   /* lanes per camera from the LOCAL rows per local camera */ \
+    const unsigned wgrid = lm_grid(ncw, wide ? kLmThreads / 32 : kLmThreads / 8);     /* K1 / K3p: local cameras */    \
+    const unsigned agrid = lm_grid(ncam, wide ? kLmThreads / 32 : kLmThreads / 8);    /* K2g: all cameras */           \
     const long long q = (ncam + world - 1) / world;                                                                   \
     const unsigned long long e0 = (unsigned long long)epoch0, e1 = (unsigned long long)epoch1;                        \
     if (!retry) {                                                                                                     \
       if (wide && gather)                                                                                             \
         reproj_accum_push_kernel<CT, 32, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,      \
-                                                                            robust, (CT)delta, (int)ncam);            \
+                                                                            robust, (CT)delta, (int)ncam, cams, (int)nloc);      \
       else if (wide)                                                                                                  \
         reproj_accum_push_kernel<CT, 32, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,     \
-                                                                             robust, (CT)delta, (int)ncam);           \
+                                                                             robust, (CT)delta, (int)ncam, cams, (int)nloc);     \
       else if (gather)                                                                                                \
         reproj_accum_push_kernel<CT, 8, true><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,       \
-                                                                           robust, (CT)delta, (int)ncam);             \
+                                                                           robust, (CT)delta, (int)ncam, cams, (int)nloc);       \
       else                                                                                                            \
         reproj_accum_push_kernel<CT, 8, false><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, P, R, ws0, e0,      \
-                                                                            robust, (CT)delta, (int)ncam);            \
+                                                                            robust, (CT)delta, (int)ncam, cams, (int)nloc);      \
     }                                                                                                                 \
     if (gather) {                                                                                                     \
       if (wide)                                                                                                       \
-        reproj_gather_trial_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P, R, ws1, e0,    \
+        reproj_gather_trial_kernel<CT, 32><<<agrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P, R, ws1, e0,    \
                                                                         e1, retry, (CT)scale, (CT)dmin, (CT)dmax,     \
-                                                                        robust, (CT)delta, (int)ncam);                \
+                                                                        robust, (CT)delta, (int)ncam, present);       \
       else                                                                                                            \
-        reproj_gather_trial_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P, R, ws1, e0, e1, \
+        reproj_gather_trial_kernel<CT, 8><<<agrid, kLmThreads, 0, s>>>(poses, pts, pix, seg, H, g, P, R, ws1, e0, e1, \
                                                                        retry, (CT)scale, (CT)dmin, (CT)dmax, robust,  \
-                                                                       (CT)delta, (int)ncam);                         \
+                                                                       (CT)delta, (int)ncam, present);                \
     } else {                                                                                                          \
       reproj_reduce_solve_push_kernel<CT><<<lm_grid(q, kLmThreads), kLmThreads, 0, s>>>(                              \
-          poses, H, g, P, R, ws1, e0, e1, retry, (CT)scale, (CT)dmin, (CT)dmax, (int)ncam);                           \
+          poses, H, g, P, R, ws1, e0, e1, retry, (CT)scale, (CT)dmin, (CT)dmax, (int)ncam, present);                  \
       if (wide)                                                                                                       \
         reproj_loss_push_kernel<CT, 32><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2, e1, robust,            \
-                                                                     (CT)delta, (int)ncam);                           \
+                                                                     (CT)delta, (int)ncam, cams, (int)nloc);          \
       else                                                                                                            \
         reproj_loss_push_kernel<CT, 8><<<wgrid, kLmThreads, 0, s>>>(pts, pix, seg, P, R, ws2, e1, robust, (CT)delta,  \
-                                                                    (int)ncam);                                       \
+                                                                    (int)ncam, cams, (int)nloc);                      \
     }                                                                                                                 \
     reproj_decide_commit_kernel<CT><<<lm_grid(ncam * 7, kLmThreads), kLmThreads, 0, s>>>(                             \
         P, R, st, k, ho, (unsigned long long)epoch0, (unsigned long long)epoch1, poses, ncam * 7);                    \

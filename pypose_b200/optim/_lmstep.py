@@ -122,10 +122,23 @@ def reproj_payload(ncam, world, itemsize):
     return 0, part, part + _align(ncam * 8 * itemsize)
 
 
+def _present_mask(prob, comm):
+    """(world, ncam) uint8: which rank holds rows of which camera.  One all-gather when the problem is set up; a rank sends
+    no block for a camera it has no rows of and the receivers skip those slots, so with rows sorted by camera before the split
+     a rank's accumulate pass only touches its own cameras."""
+    import torch.distributed as dist
+    mine = (prob.seg[1:] > prob.seg[:-1]).to(torch.uint8).contiguous()
+    out = [torch.empty_like(mine) for _ in range(comm.world)]
+    dist.all_gather(out, mine, group=None if prob.group is True else prob.group)
+    return torch.stack(out).contiguous(), torch.nonzero(mine).flatten().to(torch.int32).contiguous()
+
+
 def reproj_trial_peer(ds, prob, scale, dmin, dmax, retry):
     poses = prob._poses()
     H, g, _ = prob._buf
     c = ds.comm
+    if getattr(ds, 'present_for', None) is not prob.seg:
+        (ds.present, ds.cams), ds.present_for = _present_mask(prob, c), prob.seg
     if not retry:
         ds.epoch0 += 1
     ds.epoch1 += 1
@@ -134,7 +147,7 @@ def reproj_trial_peer(ds, prob, scale, dmin, dmax, retry):
                ds.epoch0, ds.epoch1, ds.W[0].data_ptr(), ds.W[1].data_ptr(), ds.W[2].data_ptr(), ds.state.data_ptr(),
                ds.host_ptr, ds.next_seq(), ds.ctl_ptr, int(prob.robust[0]), float(prob.robust[1]), float(scale), float(dmin), float(dmax),
                1 if retry else 0, prob.pts.shape[0], 1 if reproj_gather(poses.shape[0], c.world, poses.element_size()) else 0,
-               poses.shape[0])
+               ds.present.data_ptr(), ds.cams.data_ptr(), ds.cams.shape[0], poses.shape[0])
     return ds.read()
 
 

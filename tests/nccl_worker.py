@@ -63,11 +63,16 @@ def main():
     # ---- Reproj: observations sharded, poses replicated
     # both exchange forms of the sharded reprojection trial (optim/_lmstep.py reproj_gather): owner = reduce-scatter of the
     # blocks + all-gather of the trial poses, gather = every rank receives all blocks and solves every camera
-    for form, case, steps in (("owner", "reproj", 4), ("owner", "reproj_hard", 6), ("gather", "reproj", 4),
-                              ("gather", "reproj_hard", 6)):
+    # ... and both splits: rows as stored (every rank holds rows of every camera) and rows sorted by camera before the
+    # split (a rank then holds a subset of the cameras; the `present` mask / local camera list route)
+    for form, split, case, steps in [(f, sp, c, n) for f in ("owner", "gather") for sp in ("stored", "sorted")
+                                     for c, n in (("reproj", 4), ("reproj_hard", 6))]:
         os.environ["B200POSE_PEER_GATHER"] = "1" if form == "gather" else "0"
-        tag = case if form == "owner" else case + "_gather"
+        tag = case + ("_gather" if form == "gather" else "") + ("_sorted" if split == "sorted" else "")
         pts, pix, cidx = g[f"{case}/pts"], g[f"{case}/pix"], g[f"{case}/cidx"]
+        if split == "sorted":
+            order = np.argsort(cidx, kind="stable")
+            pts, pix, cidx = pts[order], pix[order], cidx[order]
         M = len(cidx)
         sl = slice(rank * M // world, (rank + 1) * M // world)
         net2 = pp.module.PoseReproj(pp.SE3(cu(g[f"{case}/poses0"])))

@@ -38,7 +38,7 @@ def test_sharded_lm_two_gpus_matches_reference(tmp_path, golden_lm):
     np.testing.assert_allclose(r["poseinv_loss"], g["poseinv/trustregion/loss"], rtol=1e-5, atol=1e-20)
     np.testing.assert_allclose(r["poseinv_poses"], g["poseinv/trustregion/poses"][-1], atol=1e-9)
     for case in ("reproj", "reproj_hard"):
-        for tag in (case, case + "_gather"):               # owner form, gather form of the block exchange
+        for tag in (case, case + "_gather", case + "_sorted", case + "_gather_sorted"):   # exchange forms x row splits
             assert r[f"{tag}_peer"][0] == 1
             np.testing.assert_allclose(r[f"{tag}_loss"], g[f"{case}/trustregion/loss"], rtol=1e-6)
             np.testing.assert_allclose(r[f"{tag}_poses"], g[f"{case}/trustregion/poses"][-1], atol=1e-8)
