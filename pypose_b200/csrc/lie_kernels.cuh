@@ -68,7 +68,7 @@ template <class Op, int EPT>
 __global__ void __launch_bounds__(kThreads) stream_kernel(StreamParams<typename Op::T, Op::NIN, Op::NOUT> p) {
   using T = typename Op::T;
   constexpr int TILE = kThreads * EPT;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   T* s_i0 = reinterpret_cast<T*>(smem_raw);
   T* s_i1 = s_i0 + TILE * Op::DI0;
   T* s_i2 = s_i1 + (Op::NIN > 1 ? TILE * Op::DI1 : 0);

@@ -424,24 +424,14 @@ __global__ void __launch_bounds__(kLmThreads) lm_commit_kernel(const double* __r
 // [H | g | loss] per iteration, small reduction per trial") as a reduce-scatter / all-gather pair fused into the kernels:
 //   K1p  every rank accumulates its observations' 27 sums per camera and stores them into the OWNER of that camera
 //        (owner k holds cameras [k q, (k+1) q), q = ceil(C / world));                       signal channel 0
-//   K2p  the owner adds the `world` partials in rank order, keeps the reduced block for retries, solves, retracts and
-//        stores the trial pose (7 numbers instead of 27) into every rank's copy;             signal channel 1
+//   K2p  the owner adds the partials of the ranks that hold rows of the camera in rank order, keeps the reduced block for
+//        retries, solves, retracts and stores the trial pose into every rank's copy;         signal channel 1
 //   K3p  trial loss of the local observations -> scalar to every rank;                      signal channel 2
 //   K4p  every rank adds the scalars in rank order (bit-identical decisions), decides, commits.
 // Scalars whose producer may run ahead of a slow consumer (current loss, PoseInv sums) are double-buffered by epoch parity.
 constexpr int CH_PART = 0, CH_TRIAL = 1, CH_LOSS = 2, CH_POSEINV = 3;
 
 struct PeerRegions { long long part, pt; };     // byte offsets inside the payload: partial blocks, trial poses
-
-__device__ __forceinline__ bool cta_ticket_last(unsigned* ticket) {     // call after __threadfence_system + __syncthreads
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
-    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    if (last) *ticket = 0u;
-  }
-  __syncthreads();
-  return last;
-}
 
 // Exchange slots are padded to whole 16-byte vectors: 28 numbers per (source rank, camera) partial block (21 + 6 + pad),
 // 8 per trial pose.  Every remote store is a 16-byte store and a thread fences ONCE, after its last store (r2l: the first

@@ -229,7 +229,6 @@ __global__ void __launch_bounds__(kLmThreads) cg_dir_kernel(const T* __restrict_
 // dot + update + dir of one iteration in ONE single-CTA launch, for systems small enough that a grid is only latency
 // (bundle adjustment: a few thousand cameras; the three separate kernels cost ~28 us at 1e3 rows, this one ~8 us).
 // Fixed-order block reductions (warp shuffles, then warp 0 over the 32 warp partials): deterministic.
-constexpr int kVecThreads = 1024;
 constexpr long long kVecSmallRows = 4096;
 template <int NS, int THREADS> __device__ __forceinline__ void block_sums(double (&v)[NS], double (*sh)[NS], double (&out)[NS]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
