@@ -197,7 +197,8 @@ def test_config5_reproj_1e4_poses_1e6_residuals_converges():
         l0 = loss if l0 is None else l0
     assert loss < 1e-3 * l0 or loss < 1e-4
     d = (pp.SE3(cu(gt, torch.float32)).Inv() @ net.poses).Log().tensor().abs().max().item()
-    assert d <= 1e-5 * 20, d      # fp32 pixels/points: converged pose error ~1e-5 (checked at 1e-5 in fp64 below)
+    print(f"config 5 (single-pose form) fp32: converged pose error max |Log(gt^-1 P)| = {d:.3e}, loss {loss:.3e}")
+    assert d <= 1e-5, d           # north_star's bound, in fp32 at the full size (measured on B200: 2.4e-7, r2w)
 
 
 def test_config5_small_fp64_pose_error():
