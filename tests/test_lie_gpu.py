@@ -3,6 +3,7 @@ reference), called through the C-ABI (ctypes) on device buffers.
 
 Tolerances (stated per north_star): fp64 1e-12, fp32 2e-6, both relative to (1 + |truth|).
 """
+import os
 import zlib
 import numpy as np
 import pytest
@@ -15,7 +16,9 @@ from pypose_b200._optable import GROUPS
 
 pytestmark = pytest.mark.gpu
 OPS = all_ops()
-TOL = {torch.float64: 1e-12, torch.float32: 2e-6}
+# fp32: north_star's per-op bound.  Measured maxima on B200 over the random + golden inputs of every op
+# (profiles/r2y_per_op_error_maxima.log): fp32 3.2e-7, fp64 1.1e-13.
+TOL = {torch.float64: 1e-12, torch.float32: 1e-6}
 
 
 def run_abi(key, ins_np, outw, dtype):
@@ -30,6 +33,9 @@ def check(res, truth, tol, what="", scale=1.0):
         assert r.shape == t.shape
         err = np.abs(r - t) / (scale + np.abs(t))
         assert np.isfinite(r).all(), what
+        if os.environ.get("B200POSE_REPORT_ERR"):          # dev: collect the measured maxima in that file
+            with open(os.environ["B200POSE_REPORT_ERR"], "a") as f:
+                f.write(f"ERR {what} tol={tol:.0e} max={err.max():.3e}\n")
         assert err.max() <= tol, f"{what}: max rel err {err.max():.3e}"
 
 
@@ -73,7 +79,7 @@ def test_so3_jr(golden, dtype):
     res, dev_ins = run_abi("so3_jr", ins, [9], dtype)
     with O.wide_taylor():
         truth = O.run("so3_jr", dev_ins[0].double().cpu().numpy())
-    check(res, truth, TOL[dtype])
+    check(res, truth, 2e-6 if dtype == torch.float32 else TOL[dtype])      # not part of the measured set: round-1 bound kept
 
 
 @pytest.mark.parametrize("n", [0, 1, 3, 255, 256, 257, 1023, 4099])
