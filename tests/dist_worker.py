@@ -72,6 +72,16 @@ def main():
     inp4 = (torch.from_numpy(pixb[sl]), torch.from_numpy(cb[sl]), torch.from_numpy(pb[sl]))
     res["ba_loss"] = np.array([float(opt4.step(inp4)) for _ in range(5)])
     res["ba_poses"], res["ba_points"] = net4.poses.detach().numpy(), net4.points_3d.detach().numpy()
+    # ---- bench_legs._all_continue: ranks that want a different number of timed regions run the same number (the sharded
+    # legs exchange data inside a step; the first 2-GPU bench of round 2 deadlocked on ranks falling out of step)
+    import bench_legs
+    bench_legs._WORLD["size"], bench_legs._WORLD["dev"] = world, "cpu"
+    wanted, ran = 5 + 4 * rank, 0
+    while bench_legs._all_continue(ran < wanted):
+        ran += 1
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([ran]))
+    res["regions_run"] = torch.cat(counts).numpy()
     if rank == 0:
         np.savez(out, **res)
     dist.barrier()

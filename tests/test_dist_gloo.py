@@ -41,3 +41,4 @@ def test_sharded_lm_world2_matches_reference(tmp_path, golden_lm):
     np.testing.assert_allclose(r["ba_loss"], g["ba/trustregion/loss"], rtol=1e-5)
     np.testing.assert_allclose(r["ba_poses"], g["ba/trustregion/poses"][-1], atol=1e-6)
     np.testing.assert_allclose(r["ba_points"], g["ba/trustregion/points"][-1], atol=1e-6)
+    assert r["regions_run"].tolist() == [9, 9]               # every rank ran as many timed regions as the slowest wanted
