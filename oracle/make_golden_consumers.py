@@ -1,6 +1,7 @@
 """Goldens for two consumers of the hot path, from the REFERENCE (pypose v0.9.5, fp64 CPU):
 * EPnP's Gauss-Newton refinement of beta (module/pnp.py:13-27 BetaObjective, :185-190 _refine: GaussNewton + LSTSQ +
   StopOnPlateau(steps=10, patience=3));
+* the whole EPnP module (module/pnp.py:33-320) and svdtf (function/geometry.py:315-358) on random scenes;
 * the g2o information-matrix layout (examples/module/pgo/pgo_dataset.py:22-29 info2mat).
     python oracle/make_golden_consumers.py     # writes tests/golden/consumers.npz
 Test infrastructure only."""
@@ -39,6 +40,25 @@ def main():
         losses.append(float(loss))
     out = {"pnp/base_w": base_w.numpy(), "pnp/nullv": nullv.numpy(), "pnp/beta0": beta0.numpy(),
            "pnp/beta": model.beta.detach().numpy(), "pnp/loss": np.array(losses)}
+    # ---- the whole EPnP module (module/pnp.py:33-320) on random scenes: exact pixels and pixels with 0.3 px of noise,
+    # batch shape (2, 3), 24 points, refine on / off
+    f = 600.0
+    K = torch.tensor([[f, 0, 320.0], [0, 1.1 * f, 240.0], [0, 0, 1]], dtype=DT)
+    pose = ref.se3(0.6 * torch.randn(2, 3, 6, generator=g, dtype=DT)).Exp()
+    pc = torch.rand(2, 3, 24, 3, generator=g, dtype=DT) * torch.tensor([4.0, 3.0, 4.0], dtype=DT) + torch.tensor([-2.0, -1.5, 4.0], dtype=DT)
+    pw = pose.unsqueeze(-2).Inv().Act(pc)
+    pix = ref.point2pixel(pc, K)
+    noisy = pix + 0.3 * torch.randn(pix.shape, generator=g, dtype=DT)
+    out.update({"epnp/K": K.numpy(), "epnp/points": pw.numpy(), "epnp/pixels": pix.numpy(), "epnp/pixels_noisy": noisy.numpy(),
+                "epnp/pose_true": pose.tensor().numpy()})
+    for tag, px in (("exact", pix), ("noisy", noisy)):
+        for refine in (False, True):
+            est = ref.module.EPnP(intrinsics=K, refine=refine)(pw, px)
+            out[f"epnp/{tag}/refine{int(refine)}"] = est.tensor().detach().numpy()
+    src = torch.randn(4, 30, 3, generator=g, dtype=DT)
+    T = ref.se3(torch.randn(4, 6, generator=g, dtype=DT)).Exp()
+    out.update({"svdtf/source": src.numpy(), "svdtf/target": T.unsqueeze(-2).Act(src).numpy(),
+                "svdtf/T": ref.svdtf(src, T.unsqueeze(-2).Act(src)).tensor().numpy()})
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, losses)
 

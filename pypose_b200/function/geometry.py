@@ -1,7 +1,7 @@
 """Projection / reprojection residual models (reference: pypose/function/geometry.py:7-225).
 
-Only the camera-model functions the LM configs use are in scope; the
-point-cloud utilities (knn, svdtf, filters) are not part of the hot path.
+Only the camera-model functions the LM configs use are in scope, plus `svdtf`, which EPnP
+(module/pnp.py) needs; the other point-cloud utilities (knn, filters) are not part of the hot path.
 """
 import torch
 
@@ -46,3 +46,19 @@ def reprojerr(points, pixels, intrinsics, extrinsics=None, reduction='none'):
     if reduction == 'sum':
         return err.sum(dim=-1)
     return err
+
+
+def svdtf(source, target):
+    """Rigid alignment of two associated point sets (..., N, 3) -> SE3 `T` with `T @ source ~ target`
+    (geometry.py:315-358): rotation from the SVD of the cross-covariance of the centred sets.  Kept quirk: an improper
+    solution (det = -1) is negated as a whole, as the reference does (:353-354), not by flipping one singular vector."""
+    from ..lietensor import mat2SE3
+    assert source.size(-2) == target.size(-2), "The number of points N has to be the same for both point clouds."
+    cs, ct = source.mean(dim=-2, keepdim=True), target.mean(dim=-2, keepdim=True)
+    cov = (target - ct).mT @ (source - cs)                       # (..., 3, 3): sum_n target_n source_n^T
+    U, _, Vh = torch.linalg.svd(cov)
+    R = U @ Vh
+    improper = (torch.linalg.det(R) + 1).abs() < 1e-6
+    R = torch.where(improper[..., None, None], -R, R)
+    t = ct.mT - R @ cs.mT
+    return mat2SE3(torch.cat([R, t], dim=-1), check=False)

@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 from torch import nn
 
@@ -82,3 +83,46 @@ def test_epnp_gauss_newton_refinement_matches_reference():
     assert len(losses) == len(g["pnp/loss"])
     np.testing.assert_allclose(losses, g["pnp/loss"], rtol=1e-6, atol=1e-28)
     np.testing.assert_allclose(model.beta.detach().numpy(), g["pnp/beta"], atol=1e-12)
+
+
+def test_svdtf_matches_reference():
+    """function/geometry.py:315-358: rigid alignment by SVD (golden: reference output on 4 random transforms)."""
+    g = np.load(GOLD)
+    T = pp.svdtf(torch.from_numpy(g["svdtf/source"].copy()), torch.from_numpy(g["svdtf/target"].copy()))
+    assert T.ltype == pp.SE3_type and T.shape == (4, 7)
+    np.testing.assert_allclose(T.tensor().numpy(), g["svdtf/T"], atol=1e-12)
+
+
+@pytest.mark.parametrize("tag,tol", [("exact", 1e-9), ("noisy", 1e-7)])
+@pytest.mark.parametrize("refine", [False, True])
+def test_epnp_module_matches_reference(tag, tol, refine):
+    """module/pnp.py:33-320 end to end on random scenes of batch shape (2, 3) with 24 points: control points, alphas, null
+    vectors, the four beta candidates, scale / sign, best candidate and (refine=True) the Gauss-Newton refinement through
+    this package's GaussNewton + LSTSQ + StopOnPlateau — poses of the reference (oracle/make_golden_consumers.py).  The
+    null vectors come from `eigh` here and from `eig` in the reference: equal up to sign, which the betas absorb."""
+    g = np.load(GOLD)
+    t = lambda k: torch.from_numpy(g[k].copy())
+    px = t("epnp/pixels") if tag == "exact" else t("epnp/pixels_noisy")
+    est = pp.module.EPnP(intrinsics=t("epnp/K"), refine=refine)(t("epnp/points"), px)
+    assert est.ltype == pp.SE3_type and est.shape == (2, 3, 7)
+    ref = g[f"epnp/{tag}/refine{int(refine)}"]
+    # q and -q are the same rotation: compare through the relative pose
+    d = (pp.SE3(torch.from_numpy(ref.copy())).Inv() @ est).Log().tensor().abs().max().item()
+    assert d <= tol, d
+    if tag == "exact":
+        dt = (pp.SE3(t("epnp/pose_true")).Inv() @ est).Log().tensor().abs().max().item()
+        assert dt <= 1e-9, dt
+
+
+def test_epnp_batch_and_override_intrinsics_shapes():
+    """tests/module/test_pnp.py:13-35 of the reference: an extra leading batch dimension gives the same poses, intrinsics
+    passed at call time override the buffer."""
+    g = np.load(GOLD)
+    t = lambda k: torch.from_numpy(g[k].copy())
+    e = pp.module.EPnP()
+    a = e(t("epnp/points"), t("epnp/pixels"), t("epnp/K"))
+    b = e(t("epnp/points")[None][[0, 0]], t("epnp/pixels")[None][[0, 0]], t("epnp/K").expand(2, 2, 3, 3, 3))
+    assert b.shape == (2, 2, 3, 7)
+    torch.testing.assert_close(b[0].tensor(), a.tensor())
+    with pytest.raises(AssertionError):
+        e(t("epnp/points")[..., :3, :], t("epnp/pixels")[..., :3, :], t("epnp/K"))
