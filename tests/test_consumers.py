@@ -126,3 +126,17 @@ def test_epnp_batch_and_override_intrinsics_shapes():
     torch.testing.assert_close(b[0].tensor(), a.tensor())
     with pytest.raises(AssertionError):
         e(t("epnp/points")[..., :3, :], t("epnp/pixels")[..., :3, :], t("epnp/K"))
+
+
+@pytest.mark.gpu
+def test_epnp_module_on_gpu():
+    """The same scenes on the GPU (cuSOLVER factorizations + this package's CUDA kernels for the LieTensor ops and the
+    Gauss-Newton refinement)."""
+    g = np.load(GOLD)
+    t = lambda k: torch.from_numpy(g[k].copy()).cuda()
+    for tag, tol in (("exact", 1e-9), ("noisy", 1e-7)):
+        px = t("epnp/pixels") if tag == "exact" else t("epnp/pixels_noisy")
+        est = pp.module.EPnP(intrinsics=t("epnp/K"), refine=True)(t("epnp/points"), px)
+        ref = pp.SE3(t(f"epnp/{tag}/refine1"))
+        d = (ref.Inv() @ est).Log().tensor().abs().max().item()
+        assert d <= tol, (tag, d)
