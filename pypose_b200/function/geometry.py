@@ -34,6 +34,19 @@ def point2pixel(points, intrinsics, extrinsics=None):
     return homo2cart(points @ intrinsics.mT)
 
 
+def pixel2point(pixels, depth, intrinsics):
+    """Back-projection of (..., N, 2) pixels with (..., N) depths through (..., 3, 3) pinhole intrinsics to (..., N, 3)
+    camera-frame points: z = depth, x = (u - cx) z / fx, y = (v - cy) z / fy (geometry.py:115-168)."""
+    assert pixels.size(-1) == 2, "Pixels shape incorrect"
+    assert depth.size(-1) == pixels.size(-2), "Depth shape does not match pixels"
+    assert intrinsics.size(-1) == intrinsics.size(-2) == 3, "Intrinsics shape incorrect."
+    focal = torch.stack([intrinsics[..., 0, 0], intrinsics[..., 1, 1]], dim=-1)
+    assert not torch.any(focal == 0), "fx / fy cannot contain zero"
+    centre = intrinsics[..., :2, 2]
+    xy = (pixels - centre.unsqueeze(-2)) * depth.unsqueeze(-1) / focal.unsqueeze(-2)
+    return torch.cat([xy, depth.unsqueeze(-1)], dim=-1)
+
+
 def reprojerr(points, pixels, intrinsics, extrinsics=None, reduction='none'):
     """Per-pixel reprojection error (geometry.py:171-225)."""
     torch.broadcast_shapes(points.shape[:-2], pixels.shape[:-2], intrinsics.shape[:-2])

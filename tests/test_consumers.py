@@ -146,3 +146,42 @@ def test_epnp_module_on_gpu():
     mine = pp.reprojerr(pw, px, K, est, reduction='norm').mean(-1)
     ref = pp.reprojerr(pw, px, K, pp.SE3(t("epnp/noisy/refine1")), reduction='norm').mean(-1)
     assert (mine <= 1.05 * ref + 1e-9).all(), (mine, ref)
+
+
+def test_local_bundle_adjustment_example_matches_reference():
+    """examples/module/reprojpgo/reprojpgo.py:16-28, 60-80 — the reference's `LocalBundleAdjustment` (one relative pose + N
+    depths as parameters, `pixel2point` -> `reprojerr` with `T.Inv()`, `step(input=())`) under LM(Cholesky,
+    TrustRegion(radius=1e3), Huber(0.1) + FastTriggs, min=1e-8, reject=128) and StopOnPlateau(steps=25, patience=4,
+    decreasing=1e-6): the number of steps, every loss and every pose of the reference's run (oracle/make_golden_localba.py)."""
+    from torch import nn
+    g = np.load(os.path.join(os.path.dirname(GOLD), "localba.npz"))
+    t = lambda k: torch.from_numpy(g[k].copy())
+
+    class LocalBundleAdjustment(nn.Module):
+        def __init__(self, K, pts1, pts2, depth, init_T):
+            super().__init__()
+            self.register_buffer("K", K)
+            self.register_buffer("pts1", pts1)
+            self.register_buffer("pts2", pts2)
+            self.T = pp.Parameter(init_T)
+            self.depth = nn.Parameter(depth)
+
+        def forward(self):
+            pts3d = pp.pixel2point(self.pts1, self.depth, self.K)
+            return pp.reprojerr(pts3d, self.pts2, self.K, self.T.Inv(), reduction='none')
+
+    graph = LocalBundleAdjustment(t("K"), t("pts1"), t("pts2"), t("depth0"), pp.SE3(t("T0")))
+    kernel = pp.optim.kernel.Huber(delta=0.1)
+    opt = pp.optim.LM(graph, solver=pp.optim.solver.Cholesky(), strategy=pp.optim.strategy.TrustRegion(radius=1e3), kernel=kernel,
+                      corrector=pp.optim.corrector.FastTriggs(kernel), min=1e-8, reject=128, vectorize=True)
+    sched = pp.optim.scheduler.StopOnPlateau(opt, steps=25, patience=4, decreasing=1e-6)
+    losses, Ts = [], []
+    while sched.continual():
+        loss = opt.step(input=())
+        sched.step(loss)
+        losses.append(float(loss))
+        Ts.append(graph.T.detach().tensor().numpy().copy())
+    assert len(losses) == len(g["loss"])
+    np.testing.assert_allclose(losses, g["loss"], rtol=1e-8)
+    np.testing.assert_allclose(np.stack(Ts), g["T"], atol=1e-9)
+    np.testing.assert_allclose(graph.depth.detach().numpy(), g["depth"], atol=1e-8)
