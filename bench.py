@@ -25,7 +25,12 @@ import sys
 import threading
 import time
 
-import torch
+# NCCL's version banner (NCCL_DEBUG=VERSION in the box's environment) goes to stdout, next to the one JSON line this script
+# prints; the debug level is read once, so it has to be lowered before anything touches NCCL
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -101,8 +106,6 @@ def dist_setup(n_gpus):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         import datetime
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # the version banner goes to stdout, next to the JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
         # a rank that falls out of step must fail the run in minutes, not after NCCL's default 10-minute watchdog
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     return rank, world, local
