@@ -25,10 +25,9 @@ import sys
 import threading
 import time
 
-# NCCL's version banner (NCCL_DEBUG=VERSION in the box's environment) goes to stdout, next to the one JSON line this script
-# prints; the debug level is read once, so it has to be lowered before anything touches NCCL
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL's version banner (NCCL_DEBUG=VERSION in the box's environment; NCCL prints it at the VERSION and WARN levels) goes
+# to stdout, next to the one JSON line this script prints: send NCCL's own log stream to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 
