@@ -25,9 +25,11 @@ import sys
 import threading
 import time
 
-# NCCL's version banner (NCCL_DEBUG=VERSION in the box's environment; NCCL prints it at the VERSION and WARN levels) goes
-# to stdout, next to the one JSON line this script prints: send NCCL's own log stream to stderr instead
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# NCCL_DEBUG=VERSION (set in the box's environment) makes NCCL print its version banner on stdout, next to the one JSON
+# line this script prints.  Measured: the banner is also printed at the WARN level and ignores NCCL_DEBUG_FILE, so the
+# variable is dropped (level NONE) when it only asks for the banner; any other setting of the user's is kept.
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]
 
 import torch  # noqa: E402
 
