@@ -79,6 +79,19 @@ def main():
     wanted, ran = 5 + 4 * rank, 0
     while bench_legs._all_continue(ran < wanted):
         ran += 1
+    # ---- optim/_lmstep.py: host side of the sharded reprojection exchange (which rank holds rows of which camera; sizes of
+    # the two exchange forms)
+    from types import SimpleNamespace
+    from pypose_b200.optim import _lmstep
+    C = 7
+    rows = {0: [3, 0, 2, 0, 0, 1, 0], 1: [0, 0, 4, 5, 0, 0, 0]}[rank]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(rows)]), dtype=torch.int32)
+    present, cams = _lmstep._present_mask(SimpleNamespace(seg=seg, group=True), SimpleNamespace(world=world))
+    res["present"], res["cams"] = present.numpy(), cams.numpy()
+    res["payload_gather"] = np.array(_lmstep.reproj_payload(1000, 2, 4))
+    os.environ["B200POSE_PEER_GATHER"] = "0"
+    res["payload_owner"] = np.array(_lmstep.reproj_payload(1000, 2, 4))
+    os.environ.pop("B200POSE_PEER_GATHER")
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([ran]))
     res["regions_run"] = torch.cat(counts).numpy()

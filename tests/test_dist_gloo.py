@@ -42,3 +42,9 @@ def test_sharded_lm_world2_matches_reference(tmp_path, golden_lm):
     np.testing.assert_allclose(r["ba_poses"], g["ba/trustregion/poses"][-1], atol=1e-6)
     np.testing.assert_allclose(r["ba_points"], g["ba/trustregion/points"][-1], atol=1e-6)
     assert r["regions_run"].tolist() == [9, 9]               # every rank ran as many timed regions as the slowest wanted
+    # host side of the sharded reprojection exchange: rank 0 wrote the file, so `cams` is rank 0's list
+    np.testing.assert_array_equal(r["present"], [[1, 0, 1, 0, 0, 1, 0], [0, 0, 1, 1, 0, 0, 0]])
+    np.testing.assert_array_equal(r["cams"], [0, 2, 5])
+    al = lambda n: (n + 255) // 256 * 256                    # regions are 256-byte aligned
+    assert r["payload_gather"].tolist() == [0, al(2 * 1000 * 28 * 4), al(2 * 1000 * 28 * 4) + al(1000 * 8 * 4)]   # all blocks to every rank
+    assert r["payload_owner"].tolist() == [0, al(2 * 500 * 28 * 4), al(2 * 500 * 28 * 4) + al(1000 * 8 * 4)]      # blocks to owners
